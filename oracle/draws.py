@@ -1,0 +1,132 @@
+"""Oracle (test infrastructure): normal draws consumed by the samplers.
+
+Restates
+  * `math/random_ops/multivariate_normal.py:47-451` (`multivariate_normal`
+    a.k.a. `mv_normal_sample`) for mean-only inputs (no scale matrix), the
+    form every caller on the hot path uses;
+  * `models/utils.py:20-128` (`generate_mc_normal_draws`).
+"""
+import enum
+import numpy as np
+from scipy import special
+
+from oracle import philox
+from oracle import sobol
+
+_SQRT_2 = np.sqrt(2.)
+
+
+@enum.unique
+class RandomType(enum.Enum):
+  """`multivariate_normal.py:27-44`."""
+  PSEUDO = 0
+  STATELESS = 1
+  HALTON = 2
+  HALTON_RANDOMIZED = 3
+  SOBOL = 4
+  PSEUDO_ANTITHETIC = 5
+  STATELESS_ANTITHETIC = 6
+
+
+def _erfinv_times_sqrt2(u, dtype):
+  """`tf.math.erfinv((u - 0.5) * 2) * sqrt(2)` (`multivariate_normal.py:420`).
+
+  TF's erfinv(x) is ndtri(0.5 x + 0.5) / sqrt(2) (Eigen / Cephes); here the
+  float64 Cephes `ndtri` of scipy is used and the result rounded to `dtype`.
+  """
+  dtype = np.dtype(dtype)
+  x = (u - dtype.type(0.5)) * dtype.type(2)            # exact for dyadic u
+  z = special.ndtri(0.5 * x.astype(np.float64) + 0.5)
+  return z.astype(dtype)
+
+
+def _mvnormal_pseudo(sample_shape, mean, random_type, seed, dtype):
+  """`multivariate_normal.py:248-273` with scale_matrix=None."""
+  out_shape = tuple(sample_shape) + tuple(mean.shape)
+  if random_type == RandomType.PSEUDO:
+    samples = philox.stateful_normal(out_shape, seed, dtype)
+  else:
+    if seed is None:
+      raise ValueError('`seed` should be specified if the `random_type` is '
+                       '`STATELESS` or `STATELESS_ANTITHETIC`')
+    samples = philox.stateless_normal(out_shape, seed, dtype)
+  return mean + samples
+
+
+def _mvnormal_pseudo_antithetic(sample_shape, mean, random_type, seed, dtype):
+  """`multivariate_normal.py:276-311`."""
+  n0 = int(sample_shape[0])
+  if n0 % 2 != 0:
+    raise ValueError('First dimension of `sample_shape` should be even for '
+                     'PSEUDO_ANTITHETIC random type')
+  half_shape = (n0 // 2,) + tuple(sample_shape[1:])
+  base = (RandomType.PSEUDO if random_type == RandomType.PSEUDO_ANTITHETIC
+          else RandomType.STATELESS)
+  r = _mvnormal_pseudo(half_shape, mean, base, seed, dtype)
+  return np.concatenate([r, 2 * mean - r], axis=0)
+
+
+def _mvnormal_sobol(sample_shape, mean, skip, dtype):
+  """`multivariate_normal.py:356-424` for SOBOL."""
+  batch_shape = tuple(mean.shape)
+  dim = batch_shape[-1]
+  sample_shape = tuple(int(s) for s in sample_shape)
+  output_shape_t = tuple(reversed(batch_shape)) + sample_shape
+  num_samples = int(np.prod(output_shape_t)) // dim
+  seq = sobol.sample(dim, num_samples, skip=skip, dtype=dtype)   # [n, dim]
+  seq = seq.T
+  size_sample = len(sample_shape)
+  size_batch = len(batch_shape)
+  perm = (list(range(size_batch, size_batch + size_sample)) +
+          list(range(size_batch - 1, -1, -1)))
+  seq = np.transpose(seq.reshape(output_shape_t), perm)
+  return mean + _erfinv_times_sqrt2(seq, dtype)
+
+
+def mv_normal_sample(sample_shape, mean, random_type=None, seed=None,
+                     dtype=None, skip=0):
+  """`multivariate_normal` restricted to `mean` only (identity scale)."""
+  random_type = RandomType.PSEUDO if random_type is None else random_type
+  random_type = RandomType(random_type.value)
+  mean = np.asarray(mean, dtype=dtype)
+  dtype = mean.dtype
+  if random_type in (RandomType.PSEUDO, RandomType.STATELESS):
+    return _mvnormal_pseudo(sample_shape, mean, random_type, seed, dtype)
+  if random_type in (RandomType.PSEUDO_ANTITHETIC,
+                     RandomType.STATELESS_ANTITHETIC):
+    return _mvnormal_pseudo_antithetic(sample_shape, mean, random_type, seed,
+                                       dtype)
+  if random_type == RandomType.SOBOL:
+    return _mvnormal_sobol(sample_shape, mean, skip, dtype)
+  raise NotImplementedError(
+      'Only STATELESS, PSEUDO, PSEUDO_ANTITHETIC, STATELESS_ANTITHETIC and '
+      'SOBOL are restated by the oracle. Supplied: {}'.format(random_type))
+
+
+def generate_mc_normal_draws(num_normal_draws, num_time_steps,
+                             num_sample_paths, random_type, batch_shape=None,
+                             skip=0, seed=None, dtype=None):
+  """`models/utils.py:20-128` -> [steps] + batch_shape + [paths, draws]."""
+  if skip is None:
+    skip = 0
+  dtype = np.dtype(np.float32 if dtype is None else dtype)
+  batch_shape = tuple(batch_shape or ())
+  random_type = RandomType(random_type.value)
+  total_dimension = np.zeros(num_time_steps * num_normal_draws, dtype=dtype)
+  if random_type in (RandomType.PSEUDO_ANTITHETIC,
+                     RandomType.STATELESS_ANTITHETIC):
+    sample_shape = (num_sample_paths,) + batch_shape
+    is_antithetic = True
+  else:
+    sample_shape = batch_shape + (num_sample_paths,)
+    is_antithetic = False
+  draws = mv_normal_sample(sample_shape, mean=total_dimension,
+                           random_type=random_type, seed=seed, skip=skip,
+                           dtype=dtype)
+  draws = draws.reshape(sample_shape + (num_time_steps, num_normal_draws))
+  rank = draws.ndim
+  if is_antithetic and rank > 3:
+    perm = [rank - 2] + list(range(1, rank - 2)) + [0, rank - 1]
+  else:
+    perm = [rank - 2] + list(range(rank - 2)) + [rank - 1]
+  return np.transpose(draws, perm)

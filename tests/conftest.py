@@ -1,0 +1,29 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'tf-quant-finance_b200')
+for p in (ROOT, PKG):
+  if p not in sys.path:
+    sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+  config.addinivalue_line('markers', 'gpu: test needs a CUDA device (B200)')
+
+
+def pytest_collection_modifyitems(config, items):
+  # `-m gpu` on a box without a GPU: skip loudly instead of failing on import.
+  try:
+    import torch
+    has_gpu = torch.cuda.is_available()
+  except Exception:  # pylint: disable=broad-except
+    has_gpu = False
+  if has_gpu:
+    return
+  skip = pytest.mark.skip(reason='no CUDA device')
+  for item in items:
+    if 'gpu' in item.keywords:
+      item.add_marker(skip)

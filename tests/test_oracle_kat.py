@@ -1,0 +1,190 @@
+"""Pins the CPU oracle against the reference's own known-answer tests.
+
+Each test cites the reference test (file:line under
+/root/reference/tf_quant_finance) that holds the expected values.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import draws
+from oracle import grid
+from oracle import philox
+from oracle import sobol
+
+REF_SOBOL = '/root/reference/third_party/sobol_data/new-joe-kuo-6.21201'
+
+
+# ---------------------------------------------------------------- Sobol ----
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_sobol_known_values_small_dimension(dtype):
+  # math/random_ops/sobol/sobol_test.py:28-38
+  expected = np.array([[0.5, 0.5], [0.25, 0.75], [0.75, 0.25],
+                       [0.125, 0.625], [0.625, 0.125]], dtype=dtype)
+  got = sobol.sample(2, 5, dtype=dtype)
+  assert got.dtype == dtype
+  np.testing.assert_array_equal(got, expected)
+
+
+def test_sobol_more_known_values():
+  # math/random_ops/sobol/sobol_test.py:40-81 (compared as a set of rows)
+  expected = [[0.5, 0.5, 0.5, 0.5, 0.5], [0.75, 0.25, 0.25, 0.25, 0.75],
+              [0.25, 0.75, 0.75, 0.75, 0.25],
+              [0.375, 0.375, 0.625, 0.875, 0.375],
+              [0.875, 0.875, 0.125, 0.375, 0.875],
+              [0.625, 0.125, 0.875, 0.625, 0.625],
+              [0.125, 0.625, 0.375, 0.125, 0.125],
+              [0.1875, 0.3125, 0.9375, 0.4375, 0.5625],
+              [0.6875, 0.8125, 0.4375, 0.9375, 0.0625],
+              [0.9375, 0.0625, 0.6875, 0.1875, 0.3125],
+              [0.4375, 0.5625, 0.1875, 0.6875, 0.8125],
+              [0.3125, 0.1875, 0.3125, 0.5625, 0.9375],
+              [0.8125, 0.6875, 0.8125, 0.0625, 0.4375],
+              [0.5625, 0.4375, 0.0625, 0.8125, 0.1875],
+              [0.0625, 0.9375, 0.5625, 0.3125, 0.6875],
+              [0.09375, 0.46875, 0.46875, 0.65625, 0.28125],
+              [0.59375, 0.96875, 0.96875, 0.15625, 0.78125],
+              [0.84375, 0.21875, 0.21875, 0.90625, 0.53125],
+              [0.34375, 0.71875, 0.71875, 0.40625, 0.03125],
+              [0.46875, 0.09375, 0.84375, 0.28125, 0.15625],
+              [0.96875, 0.59375, 0.34375, 0.78125, 0.65625],
+              [0.71875, 0.34375, 0.59375, 0.03125, 0.90625],
+              [0.21875, 0.84375, 0.09375, 0.53125, 0.40625],
+              [0.15625, 0.15625, 0.53125, 0.84375, 0.84375],
+              [0.65625, 0.65625, 0.03125, 0.34375, 0.34375],
+              [0.90625, 0.40625, 0.78125, 0.59375, 0.09375],
+              [0.40625, 0.90625, 0.28125, 0.09375, 0.59375],
+              [0.28125, 0.28125, 0.15625, 0.21875, 0.71875],
+              [0.78125, 0.78125, 0.65625, 0.71875, 0.21875],
+              [0.53125, 0.03125, 0.40625, 0.46875, 0.46875],
+              [0.03125, 0.53125, 0.90625, 0.96875, 0.96875]]
+  got = sobol.sample(5, 31, dtype=np.float32)
+  assert sorted(map(tuple, expected)) == sorted(map(tuple, got.tolist()))
+
+
+def test_sobol_skip():
+  # math/random_ops/sobol/sobol_test.py:83-91
+  a = sobol.sample(10, 67, dtype=np.float32)
+  b = sobol.sample(10, 50, skip=17, dtype=np.float32)
+  np.testing.assert_array_equal(a[17:], b)
+
+
+def test_sobol_large_skip():
+  # math/random_ops/sobol/sobol_test.py:93-98
+  got = sobol.sample(1, 3, skip=2**31 - 5, dtype=np.float32)
+  np.testing.assert_array_equal(got, [[0.25], [0.75], [0.5]])
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SOBOL),
+                    reason='reference checkout absent (GPU box)')
+def test_packed_joe_kuo_equals_reference_text():
+  poly_t, m_t = sobol.parse_joe_kuo_text(REF_SOBOL)
+  poly, m = sobol.load_joe_kuo()
+  np.testing.assert_array_equal(poly, poly_t)
+  np.testing.assert_array_equal(m, m_t)
+
+
+# ------------------------------------------------- Sobol -> normal layout ----
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_sobol_numbers_generation(dtype):
+  # models/utils_test.py:33-55
+  samples = draws.generate_mc_normal_draws(
+      num_normal_draws=2, num_time_steps=3, num_sample_paths=4,
+      random_type=draws.RandomType.SOBOL, dtype=dtype, skip=10)
+  expected = [[[0.8871465, 0.48877636], [-0.8871465, -0.48877636],
+               [0.48877636, 0.8871465], [-0.15731068, 0.15731068]],
+              [[0.8871465, -1.5341204], [1.5341204, -0.15731068],
+               [-0.15731068, 1.5341204], [-0.8871465, 0.48877636]],
+              [[-0.15731068, 1.5341204], [0.15731068, -0.48877636],
+               [-1.5341204, 0.8871465], [0.8871465, -1.5341204]]]
+  assert samples.dtype == dtype
+  np.testing.assert_allclose(samples, expected, rtol=1e-5, atol=1e-5)
+  # the flat index rule of SURVEY a3: (p, s, j) -> dimension s*dim + j of
+  # point skip+1+p
+  u = sobol.sample(6, 4, skip=10, dtype=np.float64)
+  from scipy import special
+  z = special.ndtri(u).reshape(4, 3, 2).transpose(1, 0, 2)
+  np.testing.assert_allclose(samples, z, rtol=2e-6 if dtype == np.float32 else 1e-14)
+
+
+# ----------------------------------------------------------------- grid ----
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_prepare_grid_num_time_step(dtype):
+  # models/utils_test.py:102-116
+  times = grid.tf_linspace(0.02, 1.0, 50, dtype)
+  time_step = times[-1] / dtype(100)
+  g, _, idx = grid.prepare_grid(times=times, time_step=time_step, dtype=dtype,
+                                num_time_steps=100)
+  np.testing.assert_allclose(g, np.linspace(0, 1, 101, dtype=dtype),
+                             rtol=1e-6, atol=1e-6)
+  np.testing.assert_array_equal(idx, [2 * i for i in range(1, 51)])
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_prepare_grid_time_step(dtype):
+  # models/utils_test.py:122-132
+  times = np.array([0.1, 0.5, 1, 2], dtype=dtype)
+  g, mask, idx = grid.prepare_grid(times=times, time_step=0.1, dtype=dtype)
+  np.testing.assert_allclose(g, np.linspace(0, 2, 21, dtype=dtype),
+                             rtol=1e-6, atol=1e-6)
+  np.testing.assert_allclose(g[idx], times, rtol=1e-6, atol=1e-6)
+  assert mask.sum() == 4 and not mask[0]
+
+
+def test_grid_sizes_of_the_configs():
+  # S = 100 (C1), 252 (C2), 360 (C3)
+  g, m, _ = grid.euler_grid([1.0], dtype=np.float64, time_step=0.01)
+  assert g.shape[0] == 101 and m[-1] and m.sum() == 1
+  g, m, _ = grid.euler_grid([1.0], dtype=np.float64, num_time_steps=252)
+  assert g.shape[0] == 253 and g[0] == 0 and g[-1] == 1.0
+  g, m, _ = grid.euler_grid([1.0], dtype=np.float32, num_time_steps=252)
+  assert g.shape[0] == 253
+
+
+# --------------------------------------------------------------- Philox ----
+def test_philox_core_random123_kat():
+  # Random123 kat_vectors, philox4x32 10 rounds.
+  def run(ctr, key):
+    return [int(x) for x in philox.philox4x32_10(
+        np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32))]
+  assert run([0, 0, 0, 0], [0, 0]) == [
+      0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+  assert run([0xffffffff] * 4, [0xffffffff] * 2) == [
+      0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+  assert run([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344],
+             [0xa4093822, 0x299f31d0]) == [
+                 0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_counter_add_carries():
+  c = np.array([0xfffffffe, 0xffffffff, 0x7, 0x1], dtype=np.uint32)
+  got = philox.counter_add(c, np.array([0, 1, 2, 3], dtype=np.uint64))
+  assert got.tolist() == [[0xfffffffe, 0xffffffff, 7, 1],
+                          [0xffffffff, 0xffffffff, 7, 1],
+                          [0, 0, 8, 1], [1, 0, 8, 1]]
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_stateless_prefix_stability_and_moments(dtype):
+  # math/random_ops/multivariate_normal_test.py:342-380 (structure only)
+  a = philox.stateless_normal([1000, 6], [4, 2], dtype)
+  b = philox.stateless_normal([2000, 6], [4, 2], dtype)
+  np.testing.assert_array_equal(a, b[:1000])
+  big = philox.stateless_normal([200000], [1, 7], dtype).astype(np.float64)
+  assert abs(big.mean()) < 1e-2 and abs(big.std() - 1) < 1e-2
+
+
+def test_antithetic_pairing():
+  # math/random_ops/multivariate_normal_test.py:249-281
+  mean = np.zeros(6)
+  z = draws.mv_normal_sample([10], mean,
+                             random_type=draws.RandomType.STATELESS_ANTITHETIC,
+                             seed=[1, 2], dtype=np.float64)
+  np.testing.assert_allclose(z[:5] + z[5:], 0.0, atol=1e-10)
+  d = draws.generate_mc_normal_draws(
+      2, 3, 10, draws.RandomType.STATELESS_ANTITHETIC, seed=[1, 2],
+      dtype=np.float64)
+  assert d.shape == (3, 10, 2)
+  np.testing.assert_array_equal(d[:, :5], -d[:, 5:])
+  np.testing.assert_array_equal(d[1, 3], z[3].reshape(3, 2)[1])
