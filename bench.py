@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the fused Euler Monte-Carlo path engine (BASELINE.json metric:
+Euler path-steps/sec, fp64).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference]
+
+One "step" = one pass of the hot path over the whole workload (all paths x all
+Euler steps, normals generated in-kernel, payoffs reduced in-kernel).  Default
+workload = BASELINE.json configs[1] (C2): Heston Euler, 10M paths x 252 steps,
+float64, Sobol, European + up-and-out barrier call.  Paths shard across ranks
+by disjoint Sobol index ranges / Philox counter ranges; the only collective is
+the all-reduce of the per-GPU payoff sums ("scaling": "weak" is not used: the
+total workload is the named config, so scaling is "strong").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'tf-quant-finance_b200')
+for _p in (ROOT, PKG):
+  if _p not in sys.path:
+    sys.path.insert(0, _p)
+
+METRIC = 'euler_path_steps_per_sec'
+UNIT = 'path-steps/s'
+
+# Algorithmic FP64-pipe instructions per path-step (frozen; DESIGN.md section 5,
+# SURVEY.md 8(d)): C2 = 2 Sobol normals x 38 + Heston Euler update 20.
+ALGO_FP64_INSTR = {'c1': 27, 'c2': 96, 'c3': 48}
+
+WORKLOADS = {
+    'c1': dict(name='C1 GBM call (log-space affine), 100k paths x 100 steps, fp64, PSEUDO_ANTITHETIC seed 42',
+               paths=100_000, steps=100, dtype='f64'),
+    'c2': dict(name='C2 Heston Euler, 10M paths x 252 steps, fp64, Sobol, European + up-and-out call',
+               paths=10_000_000, steps=252, dtype='f64'),
+    'c3': dict(name='C3 Hull-White 1F (Euler, affine) 50M paths x 360 steps, fp64, Philox stateless seed [4,2], call on r_T',
+               paths=50_000_000, steps=360, dtype='f64'),
+}
+
+
+# ------------------------------------------------------------ workloads ----
+def make_workload(name, num_paths=None):
+  """Returns (spec, all_times, x0, rng kwargs, payoffs, paths, steps)."""
+  import tff_b200 as tff
+  from tff_b200 import engine
+  from tff_b200.models import closures
+  from tff_b200.models import utils
+  w = WORKLOADS[name]
+  n = int(num_paths or w['paths'])
+  rt = tff.math.random.RandomType
+  if name == 'c2':
+    model = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=0.5,
+                                   rho=-0.7, dtype=np.float64)
+    spec = closures.resolve_spec(model.drift_fn(), model.volatility_fn())
+    times = np.array([1.0])
+    all_times, mask, _ = utils.prepare_grid(
+        times=times, time_step=np.float64(1.0 / 252), num_time_steps=252,
+        dtype=np.float64)
+    x0 = np.array([np.log(100.0), 0.04])
+    rng = dict(random_type=rt.SOBOL, seed=None, skip=0)
+    payoffs = [engine.european_call(100.0, log_state=True),
+               engine.up_and_out_call(100.0, 130.0, log_state=True)]
+  elif name == 'c1':
+    r, sigma = 0.03, 0.1
+    d, v = closures.affine_closures(r - sigma**2 / 2, 0.0, sigma)
+    spec = closures.resolve_spec(d, v)
+    times = np.array([1.0])
+    all_times, mask, _ = utils.prepare_grid(times=times, time_step=np.float64(0.01),
+                                            dtype=np.float64)
+    x0 = np.array([np.log(700.0)])
+    rng = dict(random_type=rt.PSEUDO_ANTITHETIC, seed=42, skip=0)
+    payoffs = [engine.european_call(k, log_state=True, scale=np.exp(-r))
+               for k in (600.0, 650.0, 680.0)]
+  elif name == 'c3':
+    # Hull-White 1F short rate in Euler form with a flat 1% curve
+    # (vector_hull_white.py:292-306): drift = k f + s^2/(2k)(1-e^{-2kt}) - k x.
+    a, s, f0 = 0.03, 0.02, 0.01
+    d, v = closures.affine_closures(
+        lambda t: a * f0 + s * s / (2 * a) * (1 - np.exp(-2 * a * t)), -a, s)
+    spec = closures.resolve_spec(d, v)
+    times = np.array([1.0])
+    all_times, mask, _ = utils.prepare_grid(times=times, time_step=np.float64(1.0 / 360),
+                                            dtype=np.float64)
+    x0 = np.array([f0])
+    rng = dict(random_type=rt.STATELESS, seed=[4, 2], skip=0)
+    payoffs = [engine.european_call(0.01, log_state=False)]
+  else:
+    raise ValueError(name)
+  steps, _ = engine.record_plan(mask, 1)
+  return spec, all_times, x0, rng, payoffs, n, steps
+
+
+# ---------------------------------------------------------------- clocks ----
+class ClockSampler(threading.Thread):
+  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index, self.samples, self.reasons, self._stop = index, [], set(), False
+    self.max_mhz = None
+
+  def run(self):
+    q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    while not self._stop:
+      try:
+        out = subprocess.run(
+            ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+             '--format=csv,noheader,nounits'], capture_output=True, text=True,
+            timeout=5).stdout.strip().split(',')
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for nm, val in zip(names, out[2:]):
+          if val.strip().lower().startswith('active'):
+            self.reasons.add(nm)
+      except Exception:  # pylint: disable=broad-except
+        pass
+      time.sleep(0.1)
+
+  def stop(self):
+    self._stop = True
+    self.join(timeout=3)
+    med = float(np.median(self.samples)) if self.samples else None
+    return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+# --------------------------------------------------------- CPU baselines ----
+def _oracle_chunk(args):
+  name, skip, count = args
+  from oracle import draws as odraws
+  from oracle import euler as oeuler
+  from oracle import models as omodels
+  if name == 'c2':
+    d, v = omodels.heston_closures(2.0, 0.04, 0.5, -0.7, np.float64)
+    paths = oeuler.sample(2, d, v, [1.0], num_time_steps=252, num_samples=count,
+                          initial_state=np.array([np.log(100.0), 0.04]),
+                          random_type=odraws.RandomType.SOBOL, skip=skip,
+                          dtype=np.float64)
+    st = np.exp(paths[:, -1, 0])
+    return float(np.maximum(st - 100.0, 0).sum()), 252
+  if name == 'c1':
+    r, sigma = 0.03, 0.1
+    paths = oeuler.sample(
+        1, lambda t, x: (r - sigma**2 / 2) + 0 * x,
+        lambda t, x: sigma * np.ones(x.shape + (1,)), [1.0], time_step=0.01,
+        num_samples=count, initial_state=np.array([np.log(700.0)]),
+        random_type=odraws.RandomType.PSEUDO_ANTITHETIC, seed=42 + skip,
+        dtype=np.float64)
+    return float(np.maximum(np.exp(paths[:, 0, 0]) - 650.0, 0).sum()), 100
+  if name == 'c3':
+    a, s, f0 = 0.03, 0.02, 0.01
+    paths = oeuler.sample(
+        1, lambda t, x: a * f0 + s * s / (2 * a) * (1 - np.exp(-2 * a * t)) - a * x,
+        lambda t, x: s * np.ones(x.shape + (1,)), [1.0], time_step=1.0 / 360,
+        num_samples=count, initial_state=np.array([f0]),
+        random_type=odraws.RandomType.STATELESS, seed=[4, 2 + skip],
+        dtype=np.float64)
+    return float(np.maximum(paths[:, 0, 0] - 0.01, 0).sum()), 360
+  raise ValueError(name)
+
+
+def cpu_run(name, sample_paths, procs):
+  """Times the oracle (numpy port of the reference path: precomputed draws
+  tensor + one vectorised update per step) on `sample_paths` paths split over
+  `procs` worker processes.  Returns (path_steps_per_s, seconds, steps)."""
+  import multiprocessing as mp
+  chunk = max(sample_paths // procs, 2)
+  chunk -= chunk % 2
+  jobs = [(name, i * chunk, chunk) for i in range(procs)]
+  t0 = time.perf_counter()
+  if procs == 1:
+    res = [_oracle_chunk(jobs[0])]
+  else:
+    with mp.get_context('fork').Pool(procs) as pool:
+      res = pool.map(_oracle_chunk, jobs)
+  dt = time.perf_counter() - t0
+  steps = res[0][1]
+  return chunk * procs * steps / dt, dt, steps, chunk * procs
+
+
+def run_reference(args):
+  """`--impl reference`: the reference's CPU path.  TensorFlow cannot be
+  installed in this image (no wheel, no network), so the oracle port -- the
+  numpy restatement pinned by the reference's known-answer tests -- is timed
+  on all host cores."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  cores = os.cpu_count() or 1
+  sample = {'c1': 100_000, 'c2': 8192 * cores, 'c3': 16384 * cores}[args.workload]
+  for _ in range(args.warmup):
+    cpu_run(args.workload, max(sample // 8, 2 * cores), cores)
+  vals, secs = [], []
+  for _ in range(args.steps):
+    v, dt, steps, n = cpu_run(args.workload, sample, cores)
+    vals.append(v)
+    secs.append(dt)
+  value = float(np.sum([sample * steps for _ in secs]) / np.sum(secs))
+  w = WORKLOADS[args.workload]
+  line = {
+      'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': 1e3 * float(np.mean(secs)), 'higher_is_better': True,
+      'scaling': 'strong', 'vs_baseline': None, 'dtype': w['dtype'],
+      'data': 'synthetic',
+      'config': {'workload': w['name'], 'sample_paths': n,
+                 'note': 'bounded sample of the workload; oracle port of the TF CPU path'},
+      'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                       'sample': '%d paths x %d steps per step, %d processes' % (n, steps, cores)},
+      'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line))
+
+
+# -------------------------------------------------------------- GPU arm ----
+def run_gpu(args):
+  import torch
+  import torch.distributed as dist
+  from tff_b200 import engine
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+  spec, all_times, x0, rngkw, payoffs, n, steps = make_workload(args.workload, args.paths)
+  rng = engine.RngSpec(**rngkw)
+  plan = engine.Plan(spec, all_times, steps, x0, rng, n, np.float64)
+  units = plan.units
+  per = (units + world - 1) // world
+  lo, hi = min(rank * per, units), min((rank + 1) * per, units)
+  stream = torch.cuda.current_stream()
+
+  def one_step():
+    sums = plan.price_sums(payoffs, lo, hi - lo)
+    if world > 1:
+      dist.all_reduce(sums)
+    return sums
+
+  flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device='cuda')
+  for _ in range(max(args.warmup, 3)):
+    sums = one_step()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  sampler = ClockSampler(local) if rank == 0 else None
+  if sampler:
+    sampler.start()
+  evs = []
+  torch.cuda.synchronize()
+  t_wall0 = time.perf_counter()
+  for _ in range(args.steps):
+    flush.zero_()                           # evict L2 between timed iterations
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sums = one_step()
+    e1.record(stream)
+    evs.append((e0, e1))
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  t_wall = time.perf_counter() - t_wall0
+  clocks = sampler.stop() if sampler else None
+  ms = sum(a.elapsed_time(b) for a, b in evs)
+  t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_total = float(t.item())
+  ms_per_step = ms_total / args.steps
+  value = n * steps / (ms_per_step * 1e-3)
+  prices = (sums[:, 0] / n).cpu().numpy().tolist()
+
+  # End to end through the public API with HOST buffers: model parameters and
+  # times are numpy arrays (H2D of the coefficient / direction-number tables
+  # happens inside), the result comes back as a numpy array (D2H of the sums).
+  table_bytes = steps * spec.num_coef * 8 + 8 * spec.dim
+  if rng.type == 2:
+    table_bytes += plan.num_steps_total * spec.num_factors * 32 * 4
+  d2h_bytes = len(payoffs) * 4 * 8
+
+  def e2e_step():
+    p = engine.Plan(spec, all_times, steps, x0, engine.RngSpec(**rngkw), n, np.float64)
+    s = p.price_sums(payoffs, lo, hi - lo)
+    if world > 1:
+      dist.all_reduce(s)
+    out = s.cpu().numpy()[:, 0] / n
+    p.close()
+    return out
+
+  e2e_step()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    e2e_step()
+  torch.cuda.synchronize()
+  e2e_s = time.perf_counter() - t0
+  te = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+  if world > 1:
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+  e2e_value = n * steps * args.steps / float(te.item())
+
+  if rank == 0:
+    dfma, ffma = engine.measure_fma_peaks()
+    algo = ALGO_FP64_INSTR[args.workload]
+    # dominant kernel = path_kernel; its share of the step is ~100% (the
+    # reduce kernel is a few microseconds) -- see profiles/.
+    per_gpu_rate = (hi - lo) * (2 if rng.antithetic else 1) * steps / (ms_per_step * 1e-3)
+    achieved = per_gpu_rate * algo / 1e9
+    roofline = {'bound': 'fp64', 'achieved': achieved, 'peak': dfma / 1e9,
+                'unit': 'G FP64-pipe instr/s', 'frac': achieved / (dfma / 1e9),
+                'traffic': None,
+                'note': 'achieved = path-steps/s/GPU x %d algorithmic FP64 instr per path-step; '
+                        'peak = DFMA issue rate measured live by tqf_measure_fp64_peak '
+                        '(MEASURED_PEAKS.json has no FP64 entry); kernel has no HBM traffic' % algo}
+    cores = 1
+    csample = {'c1': 100_000, 'c2': 32768, 'c3': 65536}[args.workload]
+    cv, cdt, csteps, cn = cpu_run(args.workload, csample, cores)
+    w = WORKLOADS[args.workload]
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': w['dtype'], 'data': 'synthetic',
+        'config': {'workload': w['name'] if args.paths is None else w['name'] + ' [paths=%d]' % n,
+                   'paths': n, 'euler_steps': steps, 'payoffs': len(payoffs),
+                   'sharding': 'disjoint path ranges per rank; all-reduce of payoff sums',
+                   'l2': 'flushed (256 MiB memset) between timed iterations; the kernel reads <100 KB of tables'},
+        'prices': prices,
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': table_bytes,
+                'd2h_bytes_per_step': d2h_bytes},
+        'gpu_launches': 2 * args.steps,
+        'wall_s_timed_region': t_wall,
+        'roofline': roofline,
+        'fp32_ffma_peak_ginstr': ffma / 1e9,
+        'cpu_baseline': {'value': cv, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d paths x %d steps, single process numpy oracle (%.1f s)' % (cn, csteps, cdt)},
+    }
+    print(json.dumps(line))
+  plan.close()
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=5)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+  ap.add_argument('--paths', type=int, default=None,
+                  help='override the number of paths (parity / debugging only)')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_gpu(args)
+
+
+if __name__ == '__main__':
+  main()

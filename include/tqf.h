@@ -1,0 +1,226 @@
+/* tqf.h -- C ABI of the B200 Monte-Carlo path engine (libtqf.so).
+ *
+ * The reference (google/tf-quant-finance) has no FFI for this path: the Euler
+ * sampler is Python calling TensorFlow ops.  This header is therefore the NEW
+ * boundary that the Python mirror of the reference API (tff_b200) binds with
+ * ctypes.  Each entry point cites the reference code whose device work it
+ * replaces (paths relative to tf_quant_finance/ in the reference checkout).
+ *
+ * Conventions
+ *   - every function returns an int status: TQF_OK (0) or a negative
+ *     TQF_ERR_* code; `tqf_last_error()` returns a thread-local message;
+ *   - `*_dev` pointers are CUDA device pointers owned by the caller (obtained
+ *     zero-copy from framework tensors through DLPack on the Python side);
+ *     every other pointer is host memory that is only read during the call;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream);
+ *     all device work is enqueued on it and the call returns without
+ *     synchronising unless stated otherwise;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with TQF_ERR_CUDA.
+ */
+#ifndef TQF_H_
+#define TQF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQF_VERSION 100
+
+/* status codes */
+#define TQF_OK 0
+#define TQF_ERR_INVALID_ARGUMENT (-1)
+#define TQF_ERR_UNSUPPORTED (-2)
+#define TQF_ERR_CUDA (-3)
+#define TQF_ERR_IO (-4)
+
+/* dtypes */
+#define TQF_F32 0
+#define TQF_F64 1
+
+/* random number generators (math/random_ops/multivariate_normal.py:27-44) */
+#define TQF_RNG_PHILOX 1 /* PSEUDO / STATELESS (+ *_ANTITHETIC)              */
+#define TQF_RNG_SOBOL 2  /* SOBOL                                            */
+#define TQF_RNG_DRAWS 3  /* caller-supplied normal_draws=                    */
+
+/* models: the drift/volatility closures the Euler loop evaluates per step */
+#define TQF_MODEL_AFFINE_1F 1     /* x' = x + dt (a0 + a1 x) + b sqrt_dt z  */
+#define TQF_MODEL_GBM_1F 2        /* a = mu x,  S = sigma x                  */
+#define TQF_MODEL_HESTON_EULER 3  /* heston/heston_model.py:143-173          */
+#define TQF_MODEL_HESTON_QE 4     /* heston/heston_model.py:322-572          */
+#define TQF_MODEL_MVGBM 5         /* multivariate_geometric_brownian_motion  */
+#define TQF_MODEL_LINEAR_1F 6     /* x' = A x + B + C z (HW exact OU step)   */
+
+/* payoff kinds (reduced in-kernel; callers: e.g. hull_white/swaption.py:310) */
+#define TQF_PAYOFF_CALL 1          /* max(f(X_T) - K, 0)                    */
+#define TQF_PAYOFF_PUT 2           /* max(K - f(X_T), 0)                    */
+#define TQF_PAYOFF_UP_OUT_CALL 3   /* call, knocked out if max_t f > B      */
+#define TQF_PAYOFF_DOWN_OUT_PUT 4  /* put, knocked out if min_t f < B       */
+#define TQF_PAYOFF_UP_OUT_PUT 5
+#define TQF_PAYOFF_DOWN_OUT_CALL 6
+#define TQF_PAYOFF_IDENTITY 7      /* f(X_T) (moments)                      */
+#define TQF_PAYOFF_HW_SWAPTION 8   /* hull_white/swaption.py:291-312        */
+
+/* state transform applied before the payoff */
+#define TQF_TRANSFORM_NONE 0
+#define TQF_TRANSFORM_EXP 1 /* state is log-price */
+
+#define TQF_MAX_PAYOFFS 8
+#define TQF_MAX_SWAPTION_PAYMENTS 64
+
+const char* tqf_last_error(void);
+int tqf_version(void);
+/* Number of visible CUDA devices (0 when there is none). */
+int tqf_device_count(void);
+
+/* ------------------------------------------------------------------------
+ * Stand-alone generators (bit-exact stream tests; also `tff.math.random`).
+ * ---------------------------------------------------------------------- */
+
+/* TF `GenerateKey` (stateless seed scrambling) and `PhiloxRandom(seed,seed2)`
+ * of a fresh stateful kernel: replaces the key/counter set-up inside
+ * tf.random.stateless_normal / tf.random.normal
+ * (math/random_ops/multivariate_normal.py:261-269).  Host only. */
+int tqf_philox_stateless_key_counter(const int64_t seed[2], uint32_t key[2],
+                                     uint32_t counter[4]);
+int tqf_philox_stateful_key_counter(int64_t op_seed, uint32_t key[2],
+                                    uint32_t counter[4]);
+
+/* Raw Philox4x32-10 words of groups [first_group, first_group+num_groups):
+ * out_dev is uint32 [num_groups][4]. */
+int tqf_philox_raw_fill(const uint32_t key[2], const uint32_t counter[4],
+                        uint64_t first_group, uint64_t num_groups,
+                        uint32_t* out_dev, void* stream);
+
+/* Elements [first_element, first_element+num_elements) of the flat normal
+ * stream of tf.random.stateless_normal / tf.random.normal for `dtype`
+ * (fp64: 2 elements per group, fp32: 4).  out_dev is dtype [num_elements]. */
+int tqf_philox_normal_fill(const uint32_t key[2], const uint32_t counter[4],
+                           uint64_t first_element, uint64_t num_elements,
+                           int dtype, void* out_dev, void* stream);
+
+/* Direction numbers m[dim][32] (int32) from the Joe-Kuo table: replaces
+ * `load_data` + `_compute_direction_numbers`
+ * (math/random_ops/sobol/sobol_impl.py:171-197, 237-261).
+ *   poly_a[k]  = the column `a`, degree[k] = the column `s`,
+ *   m_init     = [num_rows][18] initial m_i (zero padded).  Host only. */
+int tqf_sobol_direction_numbers(const uint32_t* poly_a, const uint8_t* degree,
+                                const uint32_t* m_init, int num_rows, int dim,
+                                int32_t* out);
+/* Same, parsing the original text file `new-joe-kuo-6.21201`. */
+int tqf_sobol_direction_numbers_from_file(const char* path, int dim,
+                                          int32_t* out);
+
+/* Sobol points `sobol.sample(dim, num_results, skip)` in natural order
+ * (sobol_impl.py:39-167).  direction_numbers: host int32 [dim][32].
+ *   kind 0: int32 integer points x (num_digits bits)        -> int32 out
+ *   kind 1: uniforms x / 2^num_digits in `dtype`            -> dtype out
+ *   kind 2: normals sqrt(2) erfinv(2u-1)                    -> dtype out
+ * (multivariate_normal.py:420).  out_dev is [num_results][dim] row-major.
+ * `first_result` lets a shard produce rows [first_result, first_result+count)
+ * of the num_results-row matrix (num_digits stays that of the full call). */
+int tqf_sobol_fill(const int32_t* direction_numbers, int dim,
+                   uint64_t num_results, uint64_t skip, uint64_t first_result,
+                   uint64_t count, int kind, int dtype, void* out_dev,
+                   void* stream);
+
+/* ------------------------------------------------------------------------
+ * The path engine: replaces the device work of
+ *   models/euler_sampling.py:335-537  (_sample, _while_loop, _euler_step)
+ *   models/utils.py:20-128            (generate_mc_normal_draws)
+ * and of the payoff reductions of the callers.
+ * ---------------------------------------------------------------------- */
+
+typedef struct tqf_rng_desc {
+  int32_t type;        /* TQF_RNG_*                                         */
+  int32_t antithetic;  /* 1: path p >= N/2 uses -z of path p - N/2          */
+  uint32_t key[2];     /* Philox key                                        */
+  uint32_t counter[4]; /* Philox base counter                               */
+  uint64_t skip;       /* Sobol: number of initial points skipped           */
+  /* Sobol: host int32 [num_steps_total*num_factors][32] direction numbers  */
+  const int32_t* direction_numbers;
+  /* TQF_RNG_DRAWS: device pointer, dtype of the model, layout
+   * [num_paths][num_steps_total][num_factors] (normal_draws= argument)     */
+  const void* draws_dev;
+} tqf_rng_desc;
+
+typedef struct tqf_model_desc {
+  int32_t kind;            /* TQF_MODEL_*                                   */
+  int32_t dtype;           /* TQF_F32 / TQF_F64                             */
+  int32_t dim;             /* state dimension                               */
+  int32_t num_factors;     /* normal draws per step                         */
+  int32_t num_steps;       /* steps to execute                              */
+  int32_t num_steps_total; /* len(all_times)-1: stride of the draw layout   */
+  int32_t num_coef;        /* columns of `coef`                             */
+  int32_t reserved;
+  /* host double [num_steps][num_coef]; column meaning depends on `kind`
+   * (documented in DESIGN.md); values are exactly representable in `dtype`.
+   * Columns 0/1 are always dt and sqrt(dt).                                */
+  const double* coef;
+  const double* x0;        /* host double [dim] initial state               */
+  const double* matrix;    /* MVGBM: host double [dim][dim] Cholesky factor */
+  const double* vector;    /* MVGBM: host double [2][dim] means, vols       */
+} tqf_model_desc;
+
+typedef struct tqf_payoff_desc {
+  int32_t kind;       /* TQF_PAYOFF_*                                       */
+  int32_t component;  /* state component; -1 = arithmetic mean over dim     */
+  int32_t transform;  /* TQF_TRANSFORM_*                                    */
+  int32_t reserved;
+  double strike;
+  double barrier;
+  double scale;       /* multiplies the payoff (discount factor, notional)  */
+  /* TQF_PAYOFF_HW_SWAPTION (hjm/swaption_util.py:28-170 + swaption.py:300) */
+  int32_t expiry_step;    /* payoff evaluated on the state after this step  */
+  int32_t num_payments;
+  int32_t is_payer;
+  int32_t reserved2;
+  double hw_y;            /* y(t_expiry) (vector_hull_white.py:857-874)     */
+  double hw_fwd;          /* f(0, t_expiry)                                 */
+  double pay_g[TQF_MAX_SWAPTION_PAYMENTS];     /* G(tau_j)=(1-e^{-k tau})/k */
+  double pay_p0[TQF_MAX_SWAPTION_PAYMENTS];    /* P0(T_j)/P0(t_expiry)      */
+  double pay_coef[TQF_MAX_SWAPTION_PAYMENTS];  /* coupon*tau_j (+1 on last) */
+} tqf_payoff_desc;
+
+typedef struct tqf_plan tqf_plan;
+
+/* Builds a plan: validates the descriptors and uploads the small tables
+ * (coefficients, direction numbers, Cholesky factor) to the current device.
+ * `num_paths_total` is the GLOBAL number of paths N of the reference call
+ * (it fixes the antithetic pairing and the Sobol num_digits); shards pass
+ * their own [path_offset, path_offset+path_count) to the run calls. */
+int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
+                    uint64_t num_paths_total, tqf_plan** out_plan);
+int tqf_plan_destroy(tqf_plan* plan);
+
+/* Fused mode: simulate paths [path_offset, path_offset+path_count) and reduce
+ * `num_payoffs` payoffs in-kernel.  sums_dev is double [num_payoffs][4]:
+ * {sum, sum of squares, number of non-finite payoffs, unused}; UNNORMALISED so
+ * that shards add (NCCL all-reduce across GPUs, then divide by N).
+ * For antithetic plans path_offset/path_count address the first-half paths and
+ * each unit contributes both partners.                                     */
+int tqf_plan_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                   const tqf_payoff_desc* payoffs, int num_payoffs,
+                   double* sums_dev, void* stream);
+
+/* Materialising mode: writes the state at the recorded steps.
+ *   record_slot: host int32 [num_steps+1]; entry 0 refers to the initial
+ *   state, entry s+1 to the state after step s; value = output time slot or -1.
+ *   out_dev[(p - path_offset)*stride_path + slot*stride_time + j*stride_dim]
+ *   (strides in elements of the model dtype).                              */
+int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                   const int32_t* record_slot, void* out_dev,
+                   int64_t stride_path, int64_t stride_time, int64_t stride_dim,
+                   void* stream);
+
+/* Measures the FP64 DFMA issue peak of the current device (Ginstr/s): the
+ * roofline denominator for the fused mode (not in MEASURED_PEAKS.json).
+ * Synchronises. */
+int tqf_measure_fp64_peak(double* dfma_per_second, double* ffma_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TQF_H_ */

@@ -125,11 +125,12 @@ def normals_from_words(words, dtype):
     return out.reshape(-1)
   if dtype == np.float32:
     eps = np.float32(1.0e-7)
-    two_pi = np.float32(2.0) * np.float32(np.pi)
+    two_pi = 2.0 * np.pi      # `2.0f * M_PI * u`: the product is a double
     outs = []
     for i in (0, 2):
       u1 = np.maximum(uint32_to_float(w[:, i]), eps)
-      v1 = two_pi * uint32_to_float(w[:, i + 1])
+      v1 = (two_pi * uint32_to_float(w[:, i + 1]).astype(np.float64)
+            ).astype(np.float32)
       u2 = np.sqrt(np.float32(-2.0) * np.log(u1))
       outs += [np.sin(v1) * u2, np.cos(v1) * u2]
     return np.stack(outs, axis=-1).astype(np.float32).reshape(-1)

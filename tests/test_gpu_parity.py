@@ -1,0 +1,314 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): Sobol points and Philox uint32 streams
+bit-exact; normals / path values / prices within 1e-12 relative in float64 and
+1e-5 in float32 (a small absolute floor covers values that pass through zero).
+"""
+import numpy as np
+import pytest
+
+from oracle import draws as odraws
+from oracle import euler as oeuler
+from oracle import models as omodels
+from oracle import philox as ophilox
+from oracle import sobol as osobol
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.float64: 1e-12, np.float32: 1e-5}
+ATOL = {np.float64: 1e-13, np.float32: 2e-6}
+
+
+def _tff():
+  import tff_b200 as tff
+  return tff
+
+
+def _np(t):
+  return t.detach().cpu().numpy()
+
+
+def _close(got, want, dtype, scale=1.0):
+  np.testing.assert_allclose(got, want, rtol=RTOL[dtype], atol=ATOL[dtype] * scale)
+
+
+# ------------------------------------------------------------- Philox ------
+@pytest.mark.parametrize('key,ctr,first', [
+    ([0, 0], [0, 0, 0, 0], 0),
+    ([0xa4093822, 0x299f31d0], [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], 0),
+    ([1, 2], [0xfffffff0, 0xffffffff, 0xffffffff, 5], 0),       # carries
+    ([7, 9], [0, 0, 3, 4], 2**33 + 5),
+])
+def test_philox_raw_words_bit_exact(key, ctr, first):
+  from tff_b200.math.random import philox
+  got = _np(philox.raw_words(key, ctr, first, 4099).view(__import__('torch').int32)).view(np.uint32)
+  want = ophilox.raw_words(np.array(key, np.uint32), np.array(ctr, np.uint32), first, 4099)
+  np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('shape,seed', [([1001, 7], [4, 2]), ([33], [-5, 123456789012])])
+def test_stateless_normal(dtype, shape, seed):
+  tff = _tff()
+  got = _np(tff.math.random.stateless_normal(shape, seed, dtype))
+  want = ophilox.stateless_normal(shape, seed, dtype)
+  assert got.dtype == dtype and got.shape == tuple(shape)
+  _close(got, want, dtype)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_stateful_normal_first_call(dtype):
+  tff = _tff()
+  got = _np(tff.math.random.normal([513, 3], dtype=dtype, seed=42))
+  want = ophilox.stateful_normal([513, 3], 42, dtype)
+  _close(got, want, dtype)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('first', [1, 2, 3, 1000003])
+def test_normal_fill_offsets(dtype, first):
+  from tff_b200.math.random import philox
+  key, ctr = philox.stateless_key_counter([9, 8])
+  got = _np(philox._fill(key, ctr, [777], dtype, first_element=first))
+  okey, octr = ophilox.stateless_key_counter([9, 8])
+  want = ophilox.normal_fill(okey, octr, 777, dtype, first_element=first)
+  _close(got, want, dtype)
+
+
+# -------------------------------------------------------------- Sobol ------
+@pytest.mark.parametrize('dim,n,skip', [(2, 5, 0), (50, 1000, 0), (7, 333, 17),
+                                        (1, 3, 2**31 - 5), (600, 64, 123456),
+                                        (3, 5000, 2**24 - 100)])
+def test_sobol_integer_points_bit_exact(dim, n, skip):
+  from tff_b200.math.random import sobol
+  got = _np(sobol.sample_integers(dim, n, skip)).astype(np.int64)
+  want, _ = osobol.sample_integers(dim, n, skip)
+  np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('dim,n,skip', [(2, 5, 0), (40, 2000, 3), (3, 4096, 2**25)])
+def test_sobol_uniforms_exact(dtype, dim, n, skip):
+  tff = _tff()
+  got = _np(tff.math.random.sobol.sample(dim, n, skip=skip, dtype=dtype))
+  want = osobol.sample(dim, n, skip=skip, dtype=dtype)
+  assert got.dtype == dtype
+  np.testing.assert_array_equal(got, want)
+
+
+def test_sobol_known_values():
+  # math/random_ops/sobol/sobol_test.py:28-38 and :93-98 on the device path
+  tff = _tff()
+  got = _np(tff.math.random.sobol.sample(2, 5, dtype=np.float64))
+  np.testing.assert_array_equal(
+      got, [[0.5, 0.5], [0.25, 0.75], [0.75, 0.25], [0.125, 0.625], [0.625, 0.125]])
+  got = _np(tff.math.random.sobol.sample(1, 3, skip=2**31 - 5))
+  np.testing.assert_array_equal(got, [[0.25], [0.75], [0.5]])
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_generate_mc_normal_draws_sobol_kat(dtype):
+  # models/utils_test.py:33-55
+  tff = _tff()
+  got = _np(tff.models.utils.generate_mc_normal_draws(
+      num_normal_draws=2, num_time_steps=3, num_sample_paths=4,
+      random_type=tff.math.random.RandomType.SOBOL, dtype=dtype, skip=10))
+  expected = [[[0.8871465, 0.48877636], [-0.8871465, -0.48877636],
+               [0.48877636, 0.8871465], [-0.15731068, 0.15731068]],
+              [[0.8871465, -1.5341204], [1.5341204, -0.15731068],
+               [-0.15731068, 1.5341204], [-0.8871465, 0.48877636]],
+              [[-0.15731068, 1.5341204], [0.15731068, -0.48877636],
+               [-1.5341204, 0.8871465], [0.8871465, -1.5341204]]]
+  np.testing.assert_allclose(got, expected, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('rt,seed', [('SOBOL', None), ('STATELESS', [1, 2]),
+                                     ('STATELESS_ANTITHETIC', [3, 4]),
+                                     ('PSEUDO', 11), ('PSEUDO_ANTITHETIC', 12)])
+def test_generate_mc_normal_draws_matches_oracle(dtype, rt, seed):
+  tff = _tff()
+  got = _np(tff.models.utils.generate_mc_normal_draws(
+      num_normal_draws=3, num_time_steps=5, num_sample_paths=130,
+      random_type=tff.math.random.RandomType[rt], dtype=dtype, seed=seed, skip=7))
+  want = odraws.generate_mc_normal_draws(
+      3, 5, 130, odraws.RandomType[rt], dtype=dtype, seed=seed, skip=7)
+  assert got.shape == want.shape == (5, 130, 3)
+  _close(got, want, dtype)
+
+
+# ------------------------------------------------------------- Euler ------
+def _models(dtype):
+  tff = _tff()
+  from tff_b200.models import closures
+  from tff_b200.math import piecewise
+  pw = piecewise.PiecewiseConstantFunc([0.3, 0.8], [0.1, 0.2, 0.15], dtype=dtype)
+  opw = omodels.PiecewiseConstantFunc([0.3, 0.8], [0.1, 0.2, 0.15], dtype=dtype)
+  r, s = 0.03, 0.1
+  out = {}
+  out['affine_loggbm'] = (
+      1, closures.affine_closures(r - s * s / 2, 0.0, s),
+      (lambda t, x: (r - s * s / 2) + 0 * x,
+       lambda t, x: s * np.ones(x.shape + (1,), dtype=x.dtype)),
+      np.array([np.log(700.0)]))
+  out['affine_ou'] = (
+      1, closures.affine_closures(lambda t: 0.5 * np.sqrt(t), -0.7, lambda t: 0.2 * t + 0.1),
+      (lambda t, x: np.asarray(0.5 * np.sqrt(t), x.dtype) - np.asarray(0.7, x.dtype) * x,
+       lambda t, x: np.asarray(0.2 * t + 0.1, x.dtype) * np.ones(x.shape + (1,), dtype=x.dtype)),
+      np.array([0.1]))
+  out['gbm'] = (1, closures.gbm_closures(0.03, pw),
+                omodels.gbm_closures(0.03, opw, dtype), np.array([100.0]))
+  hm = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=pw,
+                              rho=-0.7, dtype=dtype)
+  out['heston'] = (2, (hm.drift_fn(), hm.volatility_fn()),
+                   omodels.heston_closures(2.0, 0.04, opw, -0.7, dtype),
+                   np.array([np.log(100.0), 0.04]))
+  return out
+
+
+GRIDS = [dict(times=[1.0], time_step=0.05),
+         dict(times=[0.25, 0.5, 1.0], num_time_steps=12),
+         dict(times=[0.0, 0.4, 1.0], time_step=0.1),
+         dict(times=[0.3, 0.75], times_grid=[0.0, 0.25, 0.5, 0.75, 1.0, 1.25])]
+RNGS = [('SOBOL', None, 0), ('SOBOL', None, 1000), ('STATELESS', [4, 2], 0),
+        ('STATELESS_ANTITHETIC', [4, 2], 0), ('PSEUDO', 42, 0),
+        ('PSEUDO_ANTITHETIC', 42, 0)]
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('model', ['affine_loggbm', 'affine_ou', 'gbm', 'heston'])
+@pytest.mark.parametrize('rng', RNGS, ids=lambda r: f'{r[0]}-{r[2]}')
+@pytest.mark.parametrize('gi', range(len(GRIDS)))
+def test_euler_paths_match_oracle(dtype, model, rng, gi):
+  tff = _tff()
+  dim, (drift, vol), (odrift, ovol), x0 = _models(dtype)[model]
+  rt, seed, skip = rng
+  g = GRIDS[gi]
+  n = 1000
+  kw = dict(num_samples=n, initial_state=x0.astype(dtype), seed=seed, skip=skip,
+            dtype=dtype, **{k: v for k, v in g.items() if k != 'times'})
+  got = _np(tff.models.euler_sampling.sample(
+      dim, drift, vol, g['times'], random_type=tff.math.random.RandomType[rt], **kw))
+  want = oeuler.sample(dim, odrift, ovol, g['times'],
+                       random_type=odraws.RandomType[rt], **kw)
+  assert got.shape == want.shape == (n, len(g['times']), dim)
+  assert got.dtype == dtype
+  _close(got, want, dtype, scale=np.abs(want).max())
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_euler_with_supplied_normal_draws(dtype):
+  import torch
+  tff = _tff()
+  dim, (drift, vol), (odrift, ovol), x0 = _models(dtype)['heston']
+  rs = np.random.RandomState(0)
+  draws = rs.standard_normal((300, 10, 2)).astype(dtype)
+  got = _np(tff.models.euler_sampling.sample(
+      dim, drift, vol, [0.5, 1.0], time_step=0.1, initial_state=x0.astype(dtype),
+      normal_draws=torch.as_tensor(draws).cuda(), dtype=dtype))
+  want = oeuler.sample(dim, odrift, ovol, [0.5, 1.0], time_step=0.1,
+                       initial_state=x0.astype(dtype), normal_draws=draws, dtype=dtype)
+  _close(got, want, dtype, scale=np.abs(want).max())
+
+
+def test_large_sobol_index_block_alignment():
+  # chunks straddle 128-aligned Sobol index blocks with a large skip
+  tff = _tff()
+  dtype = np.float64
+  dim, (drift, vol), (odrift, ovol), x0 = _models(dtype)['heston']
+  kw = dict(num_samples=777, initial_state=x0, skip=2**22 + 77, dtype=dtype,
+            num_time_steps=6)
+  got = _np(tff.models.euler_sampling.sample(
+      dim, drift, vol, [1.0], random_type=tff.math.random.RandomType.SOBOL, **kw))
+  want = oeuler.sample(dim, odrift, ovol, [1.0],
+                       random_type=odraws.RandomType.SOBOL, **kw)
+  _close(got, want, dtype, scale=np.abs(want).max())
+
+
+# ------------------------------------------------------------ pricing ------
+@pytest.mark.parametrize('rng', [('SOBOL', None), ('STATELESS', [4, 2]),
+                                 ('PSEUDO_ANTITHETIC', 42)], ids=lambda r: r[0])
+def test_fused_price_matches_oracle(rng):
+  tff = _tff()
+  from tff_b200 import engine
+  dtype = np.float64
+  rt, seed = rng
+  dim, (drift, vol), (odrift, ovol), x0 = _models(dtype)['heston']
+  n, steps = 4096, 20
+  times = np.linspace(0.05, 1.0, steps)
+  payoffs = [engine.european_call(100.0, log_state=True),
+             engine.european_put(95.0, log_state=True, scale=0.97),
+             engine.up_and_out_call(100.0, 120.0, log_state=True),
+             engine.down_and_out_put(105.0, 85.0, log_state=True),
+             engine.identity(component=1)]
+  mean, stderr, bad = tff.models.euler_sampling.price(
+      dim, drift, vol, [1.0], payoffs, time_step=0.05, num_samples=n,
+      initial_state=x0, random_type=tff.math.random.RandomType[rt], seed=seed,
+      dtype=dtype, return_stats=True)
+  paths = oeuler.sample(dim, odrift, ovol, times, time_step=0.05, num_samples=n,
+                        initial_state=x0, random_type=odraws.RandomType[rt],
+                        seed=seed, dtype=dtype)
+  s = np.exp(paths[:, :, 0])
+  st = s[:, -1]
+  smax = np.maximum(s.max(axis=1), 100.0)
+  smin = np.minimum(s.min(axis=1), 100.0)
+  want = [np.maximum(st - 100, 0),
+          0.97 * np.maximum(95 - st, 0),
+          np.where(smax > 120.0, 0.0, np.maximum(st - 100, 0)),
+          np.where(smin < 85.0, 0.0, np.maximum(105 - st, 0)),
+          paths[:, -1, 1]]
+  np.testing.assert_allclose(mean, [w.mean() for w in want], rtol=1e-12)
+  np.testing.assert_allclose(
+      stderr, [np.sqrt(max((w**2).mean() - w.mean()**2, 0) / n) for w in want],
+      rtol=1e-9)
+  assert np.all(bad == 0)
+
+
+def test_sharded_price_adds_up():
+  tff = _tff()
+  from tff_b200 import engine
+  from tff_b200.models import closures
+  dtype = np.float64
+  dim, (drift, vol), _, x0 = _models(dtype)['heston']
+  spec = closures.resolve_spec(drift, vol)
+  times = np.linspace(0, 1, 11)
+  pay = [engine.european_call(100.0, log_state=True)]
+  for rt, seed in (('SOBOL', None), ('STATELESS', [1, 2]), ('STATELESS_ANTITHETIC', [1, 2])):
+    rng = engine.RngSpec(tff.math.random.RandomType[rt], seed, 5)
+    plan = engine.Plan(spec, times, 10, x0, rng, 3000, dtype)
+    full = _np(plan.price_sums(pay))
+    units = plan.units
+    parts = [_np(plan.price_sums(pay, a, b - a))
+             for a, b in ((0, 1001), (1001, 1002), (1002, units))]
+    np.testing.assert_allclose(sum(parts)[:, :2], full[:, :2], rtol=1e-13)
+    plan.close()
+
+
+def test_c1_notebook_configuration():
+  # examples/jupyter_notebooks/Monte_Carlo_Euler_Scheme.ipynb:223-275
+  tff = _tff()
+  from tff_b200 import engine
+  from tff_b200.models import closures
+  r, sigma, spot = 0.03, 0.1, 700.0
+  strikes = [600.0, 650.0, 680.0]
+  drift, vol = closures.affine_closures(r - sigma**2 / 2, 0.0, sigma)
+  process = tff.models.GenericItoProcess(1, drift, vol, dtype=np.float64)
+  n = 100000
+  payoffs = [engine.european_call(k, log_state=True, scale=np.exp(-r)) for k in strikes]
+  got = process.price([1.0], payoffs, num_samples=n,
+                      initial_state=np.array([np.log(spot)]),
+                      random_type=tff.math.random.RandomType.PSEUDO_ANTITHETIC,
+                      seed=42, time_step=0.01)
+  ref = oeuler.sample(
+      1, lambda t, x: (r - sigma**2 / 2) + 0 * x,
+      lambda t, x: sigma * np.ones(x.shape + (1,)), [1.0], time_step=0.01,
+      num_samples=n, initial_state=np.array([np.log(spot)]),
+      random_type=odraws.RandomType.PSEUDO_ANTITHETIC, seed=42, dtype=np.float64)
+  want = [np.exp(-r) * np.maximum(np.exp(ref[:, 0, 0]) - k, 0).mean() for k in strikes]
+  np.testing.assert_allclose(got, want, rtol=1e-12)
+  # Black-Scholes sanity (statistical, 3 standard errors)
+  from scipy.stats import norm
+  for k, g in zip(strikes, got):
+    d1 = (np.log(spot / k) + (r + sigma**2 / 2)) / sigma
+    bs = spot * norm.cdf(d1) - k * np.exp(-r) * norm.cdf(d1 - sigma)
+    assert abs(g - bs) < 0.5

@@ -1,0 +1,160 @@
+"""CPU tests of the product's host logic and of the C-ABI surface (no GPU).
+
+The product package must not import the oracle; here the oracle is the
+checker for the host-side restatements (time grids, record plan, key
+derivation, direction numbers).
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import grid as ogrid
+from oracle import philox as ophilox
+from oracle import sobol as osobol
+from tff_b200 import _lib
+from tff_b200 import engine
+from tff_b200.math import piecewise
+from tff_b200.math.random import philox
+from tff_b200.math.random import sobol
+from tff_b200.models import utils
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+  header = open(os.path.join(ROOT, 'include', 'tqf.h')).read()
+  declared = set(re.findall(r'\b(tqf_[a-z0-9_]+)\s*\(', header))
+  assert declared, 'no declarations found'
+  handle = _lib.lib()
+  for name in sorted(declared):
+    assert hasattr(handle, name), name
+  assert declared == set(_lib.EXPORTED_SYMBOLS)
+  assert handle.tqf_version() == 100
+
+
+def test_struct_layouts_match_header_sizes():
+  # sizes implied by include/tqf.h on LP64
+  assert C.sizeof(_lib.RngDesc) == 4 + 4 + 8 + 16 + 8 + 8 + 8
+  assert C.sizeof(_lib.ModelDesc) == 8 * 4 + 4 * 8
+  assert C.sizeof(_lib.PayoffDesc) == 16 + 24 + 16 + 16 + 3 * 64 * 8
+
+
+def test_product_does_not_import_oracle():
+  pkg = os.path.join(ROOT, 'tf-quant-finance_b200')
+  for base, _, files in os.walk(pkg):
+    for f in files:
+      if f.endswith('.py'):
+        src = open(os.path.join(base, f)).read()
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f
+
+
+GRID_CASES = [
+    dict(times=[1.0], time_step=0.01),
+    dict(times=[1.0], num_time_steps=252),
+    dict(times=[0.1, 0.5, 1.0, 2.0], time_step=0.1),
+    dict(times=[0.0, 0.5, 1.0], time_step=0.25),
+    dict(times=[1.0], time_step=1 / 252),
+    dict(times=[1.0], time_step=1 / 360),
+    dict(times=[0.3, 0.77, 1.9], time_step=0.07),
+    dict(times=[0.3, 0.77, 1.9], num_time_steps=5),
+    dict(times=[0.3, 0.77, 1.9], num_time_steps=2),
+    dict(times=[0.3, 0.75], times_grid=[0.0, 0.25, 0.5, 0.75, 1.0]),
+    dict(times=[0.31, 0.74], times_grid=[0.0, 0.25, 0.5, 0.75, 1.0]),
+    dict(times=np.linspace(0, 1, 50), time_step=0.01),
+]
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('case', GRID_CASES)
+def test_prepare_grid_matches_oracle(case, dtype):
+  times = np.asarray(case['times'], dtype=dtype)
+  ts = case.get('time_step')
+  nts = case.get('num_time_steps')
+  tg = case.get('times_grid')
+  if ts is None and tg is None:
+    ts = dtype(times[-1] / dtype(nts))
+  got = utils.prepare_grid(times=times, time_step=ts, dtype=dtype,
+                           num_time_steps=nts, times_grid=tg)
+  want = ogrid.prepare_grid(times=times, time_step=ts, dtype=dtype,
+                            num_time_steps=nts, times_grid=tg)
+  for g, w in zip(got, want):
+    np.testing.assert_array_equal(g, w)
+  assert got[0].dtype == dtype
+
+
+def test_record_plan_replays_the_while_loop():
+  # keep_mask, k -> (steps executed, slots)
+  n, slots = engine.record_plan([False, False, True, False, True], 2)
+  assert n == 4 and slots.tolist() == [-1, -1, 0, -1, 1]
+  # times[0] == 0: the initial state is slot 0
+  n, slots = engine.record_plan([True, False, True], 2)
+  assert n == 2 and slots.tolist() == [0, -1, 1]
+  # grid longer than the requested times: stop early
+  n, slots = engine.record_plan([False, True, False, False], 1)
+  assert n == 1 and slots.tolist() == [-1, 0]
+  # only the initial time requested
+  n, slots = engine.record_plan([True, False], 1)
+  assert n == 0 and slots.tolist() == [0]
+
+
+@pytest.mark.parametrize('seed', [[4, 2], [0, 0], [-1, 7], [2**31 - 1, -2**31],
+                                  [123456789012, 5]])
+def test_stateless_key_counter_matches_oracle(seed):
+  key, ctr = philox.stateless_key_counter(seed)
+  okey, octr = ophilox.stateless_key_counter(seed)
+  assert list(key) == okey.tolist() and list(ctr) == octr.tolist()
+
+
+@pytest.mark.parametrize('seed', [42, 0, 1, 2**31 - 1, 2**31 + 5, 87654321])
+def test_stateful_key_counter_matches_oracle(seed):
+  key, ctr = philox.stateful_key_counter(seed)
+  okey, octr = ophilox.stateful_key_counter(seed)
+  assert list(key) == okey.tolist() and list(ctr) == octr.tolist()
+
+
+def test_direction_numbers_match_oracle():
+  dn = sobol.direction_numbers(700)
+  want = osobol.direction_numbers(700)
+  # columns 0..30 are the ones `sample` can use; column 31 wraps in int32
+  np.testing.assert_array_equal(dn[:, :31].astype(np.int64), want[:, :31])
+  np.testing.assert_array_equal(dn.view(np.uint32)[:, 31].astype(np.int64),
+                                want[:, 31] & 0xFFFFFFFF)
+
+
+@pytest.mark.skipif(
+    not os.path.exists('/root/reference/third_party/sobol_data/new-joe-kuo-6.21201'),
+    reason='reference checkout absent')
+def test_direction_numbers_from_reference_text_file():
+  path = '/root/reference/third_party/sobol_data/new-joe-kuo-6.21201'
+  a = sobol.direction_numbers_from_file(path, 300)
+  np.testing.assert_array_equal(a, sobol.direction_numbers(300))
+
+
+def test_piecewise_constant_func():
+  # math/piecewise.py docstring example (lines 38-50)
+  f = piecewise.PiecewiseConstantFunc([0.1, 10], [3, 4, 5], dtype=np.float64)
+  np.testing.assert_array_equal(f(np.array([0., 0.1, 2., 11.])), [3, 3, 4, 5])
+  x = np.array([0., 0.1, 2., 11.])
+  np.testing.assert_allclose(f.integrate(x, x + 1), [3.9, 4, 4, 5])
+
+
+def test_heston_coefficient_table():
+  volvol = piecewise.PiecewiseConstantFunc([0.5], [1.0, 1.1], dtype=np.float64)
+  spec = engine.HestonEulerSpec(0.5, 0.04, volvol, 0.1)
+  t = np.array([0.0, 0.25, 0.5, 0.75])
+  tab = spec.coef_table(t, np.float64)
+  assert tab.shape == (3, 7)
+  np.testing.assert_allclose(tab[:, 0], 0.25)
+  np.testing.assert_allclose(tab[:, 4], [0.1, 0.1, 0.11])   # volvol(t_{i+1}) rho
+
+
+def test_no_gpu_fails_loudly():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('GPU present')
+  import tff_b200 as tff
+  with pytest.raises(_lib.TqfError):
+    tff.math.random.stateless_normal([4], [1, 2], np.float64)

@@ -1,0 +1,328 @@
+// Host side of the path engine: plans (device-resident tables), the fused
+// pricing launch and the path-materialising launch.  C ABI in include/tqf.h.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "tqf_paths_kernel.cuh"
+
+namespace tqf {
+
+int upload_sobol_table(const int32_t* direction_numbers, int dim, uint32_t** out_dev,
+                       cudaStream_t stream);
+
+#define TQF_EXTERN_MODEL(M)                                                             \
+  extern template int launch_path_kernel<M<double>>(int, bool, int, int, size_t,        \
+                                                    const KParams<double>&, cudaStream_t); \
+  extern template int launch_path_kernel<M<float>>(int, bool, int, int, size_t,         \
+                                                   const KParams<float>&, cudaStream_t);
+TQF_EXTERN_MODEL(AffineModel1F)
+TQF_EXTERN_MODEL(GbmModel1F)
+TQF_EXTERN_MODEL(LinearModel1F)
+TQF_EXTERN_MODEL(HestonEulerModel)
+#undef TQF_EXTERN_MODEL
+
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_blocks,
+                                       int num_payoffs, double* __restrict__ sums) {
+  // One warp per (payoff, statistic); fixed summation order -> reproducible.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  for (int item = warp; item < num_payoffs * 4; item += nwarps) {
+    const int q = item >> 2, k = item & 3;
+    double v = 0.0;
+    if (k < 3) {
+      for (int b = lane; b < num_blocks; b += 32)
+        v += partials[(static_cast<size_t>(b) * TQF_MAX_PAYOFFS + q) * 4 + k];
+    }
+    v = warp_sum(v);
+    if (lane == 0) sums[q * 4 + k] = v;
+  }
+}
+
+struct ModelInfo {
+  int dim, nf, ncoef;
+};
+
+static bool model_info(int kind, ModelInfo* info) {
+  switch (kind) {
+    case TQF_MODEL_AFFINE_1F: *info = {1, 1, 5}; return true;
+    case TQF_MODEL_GBM_1F: *info = {1, 1, 4}; return true;
+    case TQF_MODEL_LINEAR_1F: *info = {1, 1, 5}; return true;
+    case TQF_MODEL_HESTON_EULER: *info = {2, 2, 7}; return true;
+    default: return false;
+  }
+}
+
+}  // namespace tqf
+
+using namespace tqf;
+
+struct tqf_plan {
+  tqf_model_desc model;
+  tqf_rng_desc rng;
+  ModelInfo info;
+  uint64_t num_paths_total;
+  int device;
+  int max_grid;
+  void* coef_dev;           // Real [num_steps][ncoef]
+  uint32_t* sobol_dev;      // [S_total*nf][32]
+  double* partials_dev;     // [max_grid][TQF_MAX_PAYOFFS][4]
+  int* record_dev;          // [num_steps+1]
+  double x0[2];
+};
+
+template <typename Real>
+static int upload_coef(const tqf_model_desc* m, int ncoef, void** out) {
+  const size_t n = static_cast<size_t>(m->num_steps) * ncoef;
+  std::vector<Real> host(n > 0 ? n : 1);
+  for (size_t i = 0; i < n; ++i) host[i] = static_cast<Real>(m->coef[i]);
+  void* dev = nullptr;
+  TQF_CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(Real)));
+  cudaError_t e = cudaMemcpy(dev, host.data(), host.size() * sizeof(Real), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(dev);
+    return cuda_fail(e, "upload_coef");
+  }
+  *out = dev;
+  return TQF_OK;
+}
+
+template <typename Real>
+static void fill_common(const tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                        KParams<Real>* P) {
+  std::memset(P, 0, sizeof(*P));
+  P->coef = static_cast<const Real*>(plan->coef_dev);
+  P->num_steps = plan->model.num_steps;
+  P->num_steps_total = plan->model.num_steps_total;
+  P->x0[0] = static_cast<Real>(plan->x0[0]);
+  P->x0[1] = static_cast<Real>(plan->x0[1]);
+  P->key = PhiloxKey{plan->rng.key[0], plan->rng.key[1]};
+  P->ctr = PhiloxCtr{plan->rng.counter[0], plan->rng.counter[1], plan->rng.counter[2],
+                     plan->rng.counter[3]};
+  P->sobol_v = plan->sobol_dev;
+  P->draws = static_cast<const Real*>(plan->rng.draws_dev);
+  P->path_offset = path_offset;
+  P->path_count = path_count;
+  P->first_index = plan->rng.type == TQF_RNG_SOBOL ? plan->rng.skip + 1 + path_offset : path_offset;
+  P->chunk_base = P->first_index & ~static_cast<uint64_t>(kBlock - 1);
+  const uint64_t end = P->first_index + path_count;
+  P->num_chunks = (end - P->chunk_base + kBlock - 1) / kBlock;
+}
+
+static int rng_kind(const tqf_plan* plan) {
+  switch (plan->rng.type) {
+    case TQF_RNG_PHILOX: return RNGK_PHILOX;
+    case TQF_RNG_SOBOL: return RNGK_SOBOL;
+    default: return RNGK_DRAWS;
+  }
+}
+
+template <typename Real>
+static int dispatch(const tqf_plan* plan, int mode, int grid, size_t smem, const KParams<Real>& P,
+                    cudaStream_t stream) {
+  const int rk = rng_kind(plan);
+  const bool anti = plan->rng.antithetic != 0;
+  switch (plan->model.kind) {
+    case TQF_MODEL_AFFINE_1F:
+      return launch_path_kernel<AffineModel1F<Real>>(rk, anti, mode, grid, smem, P, stream);
+    case TQF_MODEL_GBM_1F:
+      return launch_path_kernel<GbmModel1F<Real>>(rk, anti, mode, grid, smem, P, stream);
+    case TQF_MODEL_LINEAR_1F:
+      return launch_path_kernel<LinearModel1F<Real>>(rk, anti, mode, grid, smem, P, stream);
+    case TQF_MODEL_HESTON_EULER:
+      return launch_path_kernel<HestonEulerModel<Real>>(rk, anti, mode, grid, smem, P, stream);
+    default:
+      set_error("model kind not supported by the generic path kernel");
+      return TQF_ERR_UNSUPPORTED;
+  }
+}
+
+template <typename Real>
+static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                     const tqf_payoff_desc* payoffs, int num_payoffs, double* sums_dev,
+                     cudaStream_t stream) {
+  KParams<Real> P;
+  fill_common(plan, path_offset, path_count, &P);
+  P.num_payoffs = num_payoffs;
+  for (int q = 0; q < num_payoffs; ++q) {
+    const tqf_payoff_desc& d = payoffs[q];
+    TQF_REQUIRE(d.kind >= TQF_PAYOFF_CALL && d.kind <= TQF_PAYOFF_IDENTITY,
+                "payoff kind not supported by this model");
+    TQF_REQUIRE(d.component >= 0 && d.component < plan->info.dim, "payoff component out of range");
+    P.pay[q] = PayoffK{d.kind, d.component, d.transform, 0, d.strike, d.barrier, d.scale};
+    if (d.kind >= TQF_PAYOFF_UP_OUT_CALL && d.kind <= TQF_PAYOFF_DOWN_OUT_CALL) P.need_extrema = 1;
+  }
+  P.partials = plan->partials_dev;
+  int grid = static_cast<int>(P.num_chunks < static_cast<uint64_t>(plan->max_grid)
+                                  ? P.num_chunks
+                                  : static_cast<uint64_t>(plan->max_grid));
+  if (grid < 1) grid = 1;
+  const int rk = rng_kind(plan);
+  bool in_smem = true;
+  size_t smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PRICE, true);
+  if (smem > 96 * 1024) {
+    in_smem = false;
+    smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PRICE, false);
+  }
+  P.tables_in_smem = in_smem ? 1 : 0;
+  int rc = dispatch<Real>(plan, MODE_PRICE, grid, smem, P, stream);
+  if (rc != TQF_OK) return rc;
+  reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev);
+  TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
+}
+
+template <typename Real>
+static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                     const int32_t* record_slot, void* out_dev, int64_t stride_path,
+                     int64_t stride_time, int64_t stride_dim, cudaStream_t stream) {
+  KParams<Real> P;
+  fill_common(plan, path_offset, path_count, &P);
+  const size_t nrec = static_cast<size_t>(plan->model.num_steps) + 1;
+  TQF_CUDA_OK(cudaMemcpyAsync(plan->record_dev, record_slot, nrec * sizeof(int),
+                              cudaMemcpyHostToDevice, stream));
+  P.record_slot = plan->record_dev;
+  P.out = static_cast<Real*>(out_dev);
+  P.stride_path = stride_path;
+  P.stride_time = stride_time;
+  P.stride_dim = stride_dim;
+  P.anti_half = path_count;  // rows of the antithetic partners follow the shard's own rows
+  int grid = static_cast<int>(P.num_chunks < static_cast<uint64_t>(plan->max_grid)
+                                  ? P.num_chunks
+                                  : static_cast<uint64_t>(plan->max_grid));
+  if (grid < 1) grid = 1;
+  const int rk = rng_kind(plan);
+  bool in_smem = true;
+  size_t smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PATHS, true);
+  if (smem > 96 * 1024) {
+    in_smem = false;
+    smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PATHS, false);
+  }
+  P.tables_in_smem = in_smem ? 1 : 0;
+  return dispatch<Real>(plan, MODE_PATHS, grid, smem, P, stream);
+}
+
+extern "C" {
+
+int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
+                    uint64_t num_paths_total, tqf_plan** out_plan) {
+  TQF_REQUIRE(model && rng && out_plan, "null argument");
+  *out_plan = nullptr;
+  ModelInfo info;
+  if (!model_info(model->kind, &info)) {
+    set_error("unknown model kind");
+    return TQF_ERR_UNSUPPORTED;
+  }
+  TQF_REQUIRE(model->dtype == TQF_F32 || model->dtype == TQF_F64, "bad dtype");
+  TQF_REQUIRE(model->dim == info.dim && model->num_factors == info.nf &&
+                  model->num_coef == info.ncoef,
+              "dim / num_factors / num_coef do not match the model kind");
+  TQF_REQUIRE(model->num_steps >= 0 && model->num_steps <= model->num_steps_total,
+              "num_steps must be in [0, num_steps_total]");
+  TQF_REQUIRE(model->num_steps == 0 || model->coef, "null coefficient table");
+  TQF_REQUIRE(model->x0, "null initial state");
+  TQF_REQUIRE(rng->type == TQF_RNG_PHILOX || rng->type == TQF_RNG_SOBOL ||
+                  rng->type == TQF_RNG_DRAWS,
+              "unknown rng type");
+  if (rng->antithetic) {
+    TQF_REQUIRE(rng->type == TQF_RNG_PHILOX, "antithetic sampling needs the Philox generator");
+    TQF_REQUIRE(num_paths_total % 2 == 0,
+                "First dimension of `sample_shape` should be even for PSEUDO_ANTITHETIC random type");
+  }
+  const uint64_t dims = static_cast<uint64_t>(model->num_steps_total) * info.nf;
+  if (rng->type == TQF_RNG_SOBOL) {
+    TQF_REQUIRE(rng->direction_numbers, "null direction numbers");
+    TQF_REQUIRE(dims <= 21201, "Sobol dimension (steps * factors) exceeds 21201");
+    TQF_REQUIRE(rng->skip + num_paths_total < 2147483647ull, "skip + num_samples too large");
+  }
+  if (rng->type == TQF_RNG_DRAWS) TQF_REQUIRE(rng->draws_dev, "null normal_draws");
+
+  int ndev = 0;
+  TQF_CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) {
+    set_error("no CUDA device: libtqf has no CPU fallback");
+    return TQF_ERR_CUDA;
+  }
+  tqf_plan* plan = new (std::nothrow) tqf_plan();
+  TQF_REQUIRE(plan, "out of memory");
+  std::memset(plan, 0, sizeof(*plan));
+  plan->model = *model;
+  plan->rng = *rng;
+  plan->info = info;
+  plan->num_paths_total = num_paths_total;
+  for (int j = 0; j < info.dim; ++j) plan->x0[j] = model->x0[j];
+  int rc = TQF_OK;
+  cudaError_t e = cudaGetDevice(&plan->device);
+  int sms = kSMs;
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device);
+  if (e != cudaSuccess) rc = cuda_fail(e, "cudaGetDevice");
+  plan->max_grid = sms * 16;
+  if (rc == TQF_OK) {
+    rc = model->dtype == TQF_F64 ? upload_coef<double>(model, info.ncoef, &plan->coef_dev)
+                                 : upload_coef<float>(model, info.ncoef, &plan->coef_dev);
+  }
+  if (rc == TQF_OK && rng->type == TQF_RNG_SOBOL)
+    rc = upload_sobol_table(rng->direction_numbers, static_cast<int>(dims), &plan->sobol_dev, 0);
+  if (rc == TQF_OK) {
+    e = cudaMalloc(&plan->partials_dev,
+                   static_cast<size_t>(plan->max_grid) * TQF_MAX_PAYOFFS * 4 * sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMalloc(&plan->record_dev, (static_cast<size_t>(model->num_steps) + 1) * sizeof(int));
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(plan scratch)");
+  }
+  // the descriptors' host pointers are not kept
+  plan->model.coef = nullptr;
+  plan->model.x0 = nullptr;
+  plan->model.matrix = nullptr;
+  plan->model.vector = nullptr;
+  plan->rng.direction_numbers = nullptr;
+  if (rc != TQF_OK) {
+    tqf_plan_destroy(plan);
+    return rc;
+  }
+  *out_plan = plan;
+  return TQF_OK;
+}
+
+int tqf_plan_destroy(tqf_plan* plan) {
+  if (!plan) return TQF_OK;
+  cudaFree(plan->coef_dev);
+  cudaFree(plan->sobol_dev);
+  cudaFree(plan->partials_dev);
+  cudaFree(plan->record_dev);
+  delete plan;
+  return TQF_OK;
+}
+
+int tqf_plan_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                   const tqf_payoff_desc* payoffs, int num_payoffs, double* sums_dev,
+                   void* stream) {
+  TQF_REQUIRE(plan && sums_dev, "null argument");
+  TQF_REQUIRE(num_payoffs >= 1 && num_payoffs <= TQF_MAX_PAYOFFS && payoffs,
+              "num_payoffs must be in [1, TQF_MAX_PAYOFFS]");
+  const uint64_t units = plan->rng.antithetic ? plan->num_paths_total / 2 : plan->num_paths_total;
+  TQF_REQUIRE(path_offset + path_count <= units, "shard exceeds the number of paths");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return plan->model.dtype == TQF_F64
+             ? run_price<double>(plan, path_offset, path_count, payoffs, num_payoffs, sums_dev, s)
+             : run_price<float>(plan, path_offset, path_count, payoffs, num_payoffs, sums_dev, s);
+}
+
+int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                   const int32_t* record_slot, void* out_dev, int64_t stride_path,
+                   int64_t stride_time, int64_t stride_dim, void* stream) {
+  TQF_REQUIRE(plan && record_slot, "null argument");
+  const uint64_t units = plan->rng.antithetic ? plan->num_paths_total / 2 : plan->num_paths_total;
+  TQF_REQUIRE(path_offset + path_count <= units, "shard exceeds the number of paths");
+  if (path_count == 0) return TQF_OK;
+  TQF_REQUIRE(out_dev, "null output");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return plan->model.dtype == TQF_F64
+             ? run_paths<double>(plan, path_offset, path_count, record_slot, out_dev, stride_path,
+                                 stride_time, stride_dim, s)
+             : run_paths<float>(plan, path_offset, path_count, record_slot, out_dev, stride_path,
+                                stride_time, stride_dim, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,336 @@
+// Stand-alone generators of libtqf: Philox raw / normal fills and Sobol fills.
+// They exist so that the uint32 streams can be checked bit for bit against
+// the oracle, and they back `tff_b200.math.random` (stateless_normal,
+// sobol.sample, mv_normal_sample).  The path kernels use the same device
+// functions (tqf_common.cuh) in registers.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "tqf_common.cuh"
+
+namespace tqf {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return TQF_ERR_CUDA;
+}
+
+// ------------------------------------------------------------- kernels ----
+__global__ void philox_raw_kernel(PhiloxKey key, PhiloxCtr ctr, uint64_t first_group,
+                                  uint64_t num_groups, uint4* __restrict__ out) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       g < num_groups; g += stride) {
+    out[g] = philox_group(ctr, key, first_group + g);
+  }
+}
+
+// One thread per Philox group; writes the elements of the group that fall into
+// [first_element, first_element + n).
+__global__ void philox_normal_f64_kernel(PhiloxKey key, PhiloxCtr ctr,
+                                         uint64_t first_element, uint64_t n,
+                                         double* __restrict__ out) {
+  const uint64_t g0 = first_element >> 1;
+  const uint64_t g1 = (first_element + n + 1) >> 1;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t g = g0 + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       g < g1; g += stride) {
+    const uint4 w = philox_group(ctr, key, g);
+    double a, b;
+    box_muller(w.x, w.y, w.z, w.w, &a, &b);
+    const uint64_t e = g << 1;
+    if (e >= first_element && e < first_element + n) out[e - first_element] = a;
+    if (e + 1 >= first_element && e + 1 < first_element + n) out[e + 1 - first_element] = b;
+  }
+}
+
+__global__ void philox_normal_f32_kernel(PhiloxKey key, PhiloxCtr ctr,
+                                         uint64_t first_element, uint64_t n,
+                                         float* __restrict__ out) {
+  const uint64_t g0 = first_element >> 2;
+  const uint64_t g1 = (first_element + n + 3) >> 2;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t g = g0 + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       g < g1; g += stride) {
+    const uint4 w = philox_group(ctr, key, g);
+    float v[4];
+    box_muller(w.x, w.y, &v[0], &v[1]);
+    box_muller(w.z, w.w, &v[2], &v[3]);
+    const uint64_t e = g << 2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (e + k >= first_element && e + k < first_element + n) out[e + k - first_element] = v[k];
+    }
+  }
+}
+
+// Sobol fill: one thread per (row, dim) element, rows fastest within a warp
+// would make stores strided, so threads run over the flattened [count][dim]
+// output (coalesced stores); the XOR walks the set bits of the index.
+template <int KIND, typename Out>
+__global__ void sobol_fill_kernel(const uint32_t* __restrict__ v_table, int dim,
+                                  uint64_t first_index, uint64_t count,
+                                  int num_digits, Out* __restrict__ out) {
+  const uint64_t total = count * static_cast<uint64_t>(dim);
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       e < total; e += stride) {
+    const uint64_t row = e / dim;
+    const int d = static_cast<int>(e - row * dim);
+    uint32_t i = static_cast<uint32_t>(first_index + row);
+    const uint32_t* v = v_table + static_cast<size_t>(d) * 32;
+    uint32_t x = 0;
+    while (i) {
+      const int b = __ffs(i) - 1;
+      x ^= __ldg(v + b);
+      i &= i - 1;
+    }
+    if constexpr (KIND == 0) {
+      out[e] = static_cast<Out>(x >> (32 - num_digits));
+    } else if constexpr (KIND == 1) {
+      out[e] = RealTraits<Out>::sobol_uniform(x);
+    } else {
+      out[e] = ndtri(RealTraits<Out>::sobol_uniform(x));
+    }
+  }
+}
+
+static int grid_for(uint64_t work_items, int block) {
+  uint64_t blocks = (work_items + block - 1) / block;
+  const uint64_t cap = static_cast<uint64_t>(kSMs) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// Host: left-aligned device table from m[dim][32].
+int upload_sobol_table(const int32_t* direction_numbers, int dim, uint32_t** out_dev,
+                       cudaStream_t stream) {
+  std::vector<uint32_t> v(static_cast<size_t>(dim) * 32);
+  for (int d = 0; d < dim; ++d) {
+    for (int b = 0; b < 32; ++b) {
+      const uint32_t m = static_cast<uint32_t>(direction_numbers[static_cast<size_t>(d) * 32 + b]);
+      v[static_cast<size_t>(d) * 32 + b] = m << (31 - b);
+    }
+  }
+  uint32_t* dev = nullptr;
+  TQF_CUDA_OK(cudaMalloc(&dev, v.size() * sizeof(uint32_t)));
+  cudaError_t e = cudaMemcpyAsync(dev, v.data(), v.size() * sizeof(uint32_t),
+                                  cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // v is a local
+  if (e != cudaSuccess) {
+    cudaFree(dev);
+    return cuda_fail(e, "upload_sobol_table");
+  }
+  *out_dev = dev;
+  return TQF_OK;
+}
+
+int sobol_num_digits(uint64_t skip, uint64_t num_results) {
+  // ceil(log2(skip + num_results + 1)) (sobol_impl.py:118-123).
+  const uint64_t max_index = skip + num_results + 1;
+  int nd = 0;
+  while ((1ull << nd) < max_index) ++nd;
+  return nd;
+}
+
+}  // namespace tqf
+
+using namespace tqf;
+
+extern "C" {
+
+const char* tqf_last_error(void) { return g_last_error.c_str(); }
+
+int tqf_version(void) { return TQF_VERSION; }
+
+int tqf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int tqf_philox_stateless_key_counter(const int64_t seed[2], uint32_t key[2],
+                                     uint32_t counter[4]) {
+  TQF_REQUIRE(seed && key && counter, "null argument");
+  const uint64_t s0 = static_cast<uint64_t>(seed[0]);
+  const uint64_t s1 = static_cast<uint64_t>(seed[1]);
+  const uint4 mix = philox4x32_10(static_cast<uint32_t>(s0), static_cast<uint32_t>(s0 >> 32),
+                                  static_cast<uint32_t>(s1), static_cast<uint32_t>(s1 >> 32),
+                                  0x3ec8f720u, 0x02461e29u);
+  key[0] = mix.x;
+  key[1] = mix.y;
+  counter[0] = 0;
+  counter[1] = 0;
+  counter[2] = mix.z;
+  counter[3] = mix.w;
+  return TQF_OK;
+}
+
+int tqf_philox_stateful_key_counter(int64_t op_seed, uint32_t key[2], uint32_t counter[4]) {
+  TQF_REQUIRE(key && counter, "null argument");
+  const int64_t kMaxInt32 = 2147483647;
+  int64_t a = 87654321 % kMaxInt32;        // DEFAULT_GRAPH_SEED
+  int64_t b = ((op_seed % kMaxInt32) + kMaxInt32) % kMaxInt32;  // python %
+  if (a == 0 && b == 0) b = kMaxInt32;
+  key[0] = static_cast<uint32_t>(a);
+  key[1] = static_cast<uint32_t>(static_cast<uint64_t>(a) >> 32);
+  counter[0] = 0;
+  counter[1] = 0;
+  counter[2] = static_cast<uint32_t>(b);
+  counter[3] = static_cast<uint32_t>(static_cast<uint64_t>(b) >> 32);
+  return TQF_OK;
+}
+
+int tqf_philox_raw_fill(const uint32_t key[2], const uint32_t counter[4],
+                        uint64_t first_group, uint64_t num_groups, uint32_t* out_dev,
+                        void* stream) {
+  TQF_REQUIRE(key && counter, "null key/counter");
+  if (num_groups == 0) return TQF_OK;
+  TQF_REQUIRE(out_dev, "null output");
+  const PhiloxKey k{key[0], key[1]};
+  const PhiloxCtr c{counter[0], counter[1], counter[2], counter[3]};
+  philox_raw_kernel<<<grid_for(num_groups, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      k, c, first_group, num_groups, reinterpret_cast<uint4*>(out_dev));
+  TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
+}
+
+int tqf_philox_normal_fill(const uint32_t key[2], const uint32_t counter[4],
+                           uint64_t first_element, uint64_t num_elements, int dtype,
+                           void* out_dev, void* stream) {
+  TQF_REQUIRE(key && counter, "null key/counter");
+  TQF_REQUIRE(dtype == TQF_F32 || dtype == TQF_F64, "dtype must be TQF_F32 or TQF_F64");
+  if (num_elements == 0) return TQF_OK;
+  TQF_REQUIRE(out_dev, "null output");
+  const PhiloxKey k{key[0], key[1]};
+  const PhiloxCtr c{counter[0], counter[1], counter[2], counter[3]};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == TQF_F64) {
+    philox_normal_f64_kernel<<<grid_for(num_elements / 2 + 1, 256), 256, 0, s>>>(
+        k, c, first_element, num_elements, static_cast<double*>(out_dev));
+  } else {
+    philox_normal_f32_kernel<<<grid_for(num_elements / 4 + 1, 256), 256, 0, s>>>(
+        k, c, first_element, num_elements, static_cast<float*>(out_dev));
+  }
+  TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
+}
+
+int tqf_sobol_direction_numbers(const uint32_t* poly_a, const uint8_t* degree,
+                                const uint32_t* m_init, int num_rows, int dim,
+                                int32_t* out) {
+  TQF_REQUIRE(out && dim >= 1, "bad output / dim");
+  TQF_REQUIRE(dim - 1 <= num_rows, "dim exceeds the direction-number table");
+  TQF_REQUIRE(dim == 1 || (poly_a && degree && m_init), "null table");
+  for (int j = 0; j < 32; ++j) out[j] = 1;  // dimension 0 (sobol_impl.py:186)
+  for (int k = 0; k + 1 < dim; ++k) {
+    const int deg = degree[k];
+    TQF_REQUIRE(deg >= 1 && deg <= 18, "degree out of range");
+    // a_k = 2^s + 2a + 1 (sobol_impl.py:257); bit i of a_k for 0 <= i < deg.
+    const uint64_t a_k = (1ull << deg) + 2ull * poly_a[k] + 1ull;
+    uint64_t m[32];
+    for (int j = 0; j < deg; ++j) m[j] = m_init[static_cast<size_t>(k) * 18 + j];
+    for (int j = deg; j < 32; ++j) {
+      uint64_t v = m[j - deg];
+      for (int i = 0; i < deg; ++i) {
+        if ((a_k >> i) & 1ull) v ^= m[j - deg + i] << (deg - i);
+      }
+      m[j] = v;
+    }
+    // int32 storage like the reference (column 31 wraps there and is unused).
+    for (int j = 0; j < 32; ++j)
+      out[static_cast<size_t>(k + 1) * 32 + j] = static_cast<int32_t>(static_cast<uint32_t>(m[j]));
+  }
+  return TQF_OK;
+}
+
+int tqf_sobol_direction_numbers_from_file(const char* path, int dim, int32_t* out) {
+  TQF_REQUIRE(path && out && dim >= 1, "bad arguments");
+  FILE* f = std::fopen(path, "r");
+  if (!f) {
+    set_error(std::string("cannot open ") + path);
+    return TQF_ERR_IO;
+  }
+  std::vector<uint32_t> a;
+  std::vector<uint8_t> s;
+  std::vector<uint32_t> m;
+  char line[1024];
+  bool header = true;
+  while (std::fgets(line, sizeof line, f) && static_cast<int>(a.size()) + 1 < dim) {
+    if (header) {
+      header = false;
+      continue;
+    }
+    unsigned long d = 0, sv = 0, av = 0;
+    int pos = 0;
+    if (std::sscanf(line, "%lu %lu %lu%n", &d, &sv, &av, &pos) < 3) continue;
+    a.push_back(static_cast<uint32_t>(av));
+    s.push_back(static_cast<uint8_t>(sv));
+    size_t base = m.size();
+    m.resize(base + 18, 0u);
+    const char* p = line + pos;
+    for (int i = 0; i < 18; ++i) {
+      unsigned long mv = 0;
+      int adv = 0;
+      if (std::sscanf(p, "%lu%n", &mv, &adv) < 1) break;
+      m[base + i] = static_cast<uint32_t>(mv);
+      p += adv;
+    }
+  }
+  std::fclose(f);
+  return tqf_sobol_direction_numbers(a.data(), s.data(), m.data(), static_cast<int>(a.size()),
+                                     dim, out);
+}
+
+int tqf_sobol_fill(const int32_t* direction_numbers, int dim, uint64_t num_results,
+                   uint64_t skip, uint64_t first_result, uint64_t count, int kind, int dtype,
+                   void* out_dev, void* stream) {
+  TQF_REQUIRE(direction_numbers && dim >= 1, "null direction numbers / bad dim");
+  TQF_REQUIRE(kind >= 0 && kind <= 2, "kind must be 0, 1 or 2");
+  TQF_REQUIRE(dtype == TQF_F32 || dtype == TQF_F64, "dtype must be TQF_F32 or TQF_F64");
+  TQF_REQUIRE(first_result + count <= num_results, "shard exceeds num_results");
+  // skip + num_results must stay below 2^31 - 1 (sobol_impl.py:98-104).
+  TQF_REQUIRE(skip + num_results < 2147483647ull, "skip + num_results too large");
+  if (count == 0) return TQF_OK;
+  TQF_REQUIRE(out_dev, "null output");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nd = sobol_num_digits(skip, num_results);
+  uint32_t* table = nullptr;
+  int rc = upload_sobol_table(direction_numbers, dim, &table, s);
+  if (rc != TQF_OK) return rc;
+  const uint64_t first_index = skip + 1 + first_result;
+  const int grid = grid_for(count * dim, 256);
+  if (kind == 0) {
+    sobol_fill_kernel<0, int32_t><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd,
+                                                        static_cast<int32_t*>(out_dev));
+  } else if (kind == 1 && dtype == TQF_F64) {
+    sobol_fill_kernel<1, double><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd,
+                                                       static_cast<double*>(out_dev));
+  } else if (kind == 1) {
+    sobol_fill_kernel<1, float><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd,
+                                                      static_cast<float*>(out_dev));
+  } else if (dtype == TQF_F64) {
+    sobol_fill_kernel<2, double><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd,
+                                                       static_cast<double*>(out_dev));
+  } else {
+    sobol_fill_kernel<2, float><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd,
+                                                      static_cast<float*>(out_dev));
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the table is freed below
+  cudaFree(table);
+  if (e != cudaSuccess) return cuda_fail(e, "sobol_fill_kernel");
+  return TQF_OK;
+}
+
+}  // extern "C"

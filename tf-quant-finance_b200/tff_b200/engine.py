@@ -1,0 +1,327 @@
+"""Host driver of the fused B200 path engine (libtqf `tqf_plan_*`).
+
+A *model spec* turns model parameters into the per-step coefficient table the
+kernels consume (parameters are evaluated at `times[i + 1]`, the END of each
+step, exactly as `_euler_step` does -- `models/euler_sampling.py:520`).  A
+`Plan` owns the device-resident tables; `Plan.paths` materialises states,
+`Plan.price` reduces payoffs in-kernel.
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+import torch
+
+from tff_b200 import _lib
+from tff_b200 import _tensor
+from tff_b200.math import random
+from tff_b200.math.random import philox
+from tff_b200.math.random import sobol
+
+
+# ----------------------------------------------------------------- specs ----
+def _eval_param(p, t, dtype):
+  """Scalar model parameter at the array of times `t` (host)."""
+  if callable(p):
+    return np.asarray(_tensor.to_numpy(p(t), dtype), dtype=dtype).reshape(t.shape)
+  return np.broadcast_to(np.asarray(_tensor.to_numpy(p, dtype)).reshape(()),
+                         t.shape).astype(dtype)
+
+
+class ModelSpec:
+  """Base class: a model the device kernels can step."""
+  kind = None
+  dim = None
+  num_factors = None
+  num_coef = None
+
+  def coef_table(self, all_times, dtype):
+    """float64 [S, num_coef]; values exactly representable in `dtype`."""
+    raise NotImplementedError
+
+  @staticmethod
+  def _dt_columns(all_times, dtype):
+    t = np.asarray(all_times, dtype=dtype)
+    dt = (t[1:] - t[:-1]).astype(dtype)
+    return t[1:], dt, np.sqrt(dt).astype(dtype)
+
+
+class AffineSpec1F(ModelSpec):
+  """dX = (a0(t) + a1(t) X) dt + b(t) dW."""
+  kind, dim, num_factors, num_coef = _lib.MODEL_AFFINE_1F, 1, 1, 5
+
+  def __init__(self, a0, a1, b):
+    self.a0, self.a1, self.b = a0, a1, b
+
+  def coef_table(self, all_times, dtype):
+    t, dt, sq = self._dt_columns(all_times, dtype)
+    cols = [dt, sq, _eval_param(self.a0, t, dtype), _eval_param(self.a1, t, dtype),
+            _eval_param(self.b, t, dtype)]
+    return np.stack(cols, -1).astype(np.float64)
+
+
+class GbmSpec1F(ModelSpec):
+  """dX = mu(t) X dt + sigma(t) X dW."""
+  kind, dim, num_factors, num_coef = _lib.MODEL_GBM_1F, 1, 1, 4
+
+  def __init__(self, mean, volatility):
+    self.mean, self.volatility = mean, volatility
+
+  def coef_table(self, all_times, dtype):
+    t, dt, sq = self._dt_columns(all_times, dtype)
+    cols = [dt, sq, _eval_param(self.mean, t, dtype),
+            _eval_param(self.volatility, t, dtype)]
+    return np.stack(cols, -1).astype(np.float64)
+
+
+class LinearSpec1F(ModelSpec):
+  """x' = A_i x + B_i + C_i z with explicit per-step tables (exact OU step)."""
+  kind, dim, num_factors, num_coef = _lib.MODEL_LINEAR_1F, 1, 1, 5
+
+  def __init__(self, table_fn):
+    self._table_fn = table_fn          # all_times, dtype -> (A, B, C) arrays
+
+  def coef_table(self, all_times, dtype):
+    _, dt, sq = self._dt_columns(all_times, dtype)
+    a, b, c = self._table_fn(np.asarray(all_times, dtype=dtype), dtype)
+    cols = [dt, sq, np.asarray(a, dtype), np.asarray(b, dtype), np.asarray(c, dtype)]
+    return np.stack(cols, -1).astype(np.float64)
+
+
+class HestonEulerSpec(ModelSpec):
+  """Heston closures (`heston/heston_model.py:143-173`), state [log S, V]."""
+  kind, dim, num_factors, num_coef = _lib.MODEL_HESTON_EULER, 2, 2, 7
+
+  def __init__(self, mean_reversion, theta, volvol, rho):
+    self.mean_reversion, self.theta = mean_reversion, theta
+    self.volvol, self.rho = volvol, rho
+
+  def coef_table(self, all_times, dtype):
+    t, dt, sq = self._dt_columns(all_times, dtype)
+    kappa = _eval_param(self.mean_reversion, t, dtype)
+    theta = _eval_param(self.theta, t, dtype)
+    volvol = _eval_param(self.volvol, t, dtype)
+    rho = _eval_param(self.rho, t, dtype)
+    one = np.dtype(dtype).type(1)
+    c4 = (volvol * rho).astype(dtype)
+    c5 = (volvol * np.sqrt(one - rho**2).astype(dtype)).astype(dtype)
+    cols = [dt, sq, kappa, theta, c4, c5, np.zeros_like(dt)]
+    return np.stack(cols, -1).astype(np.float64)
+
+
+# --------------------------------------------------------------- payoffs ----
+class Payoff:
+  """A payoff reduced in-kernel (the `tf.reduce_mean(tf.nn.relu(...))` tails
+  of the reference's callers, e.g. `hull_white/swaption.py:310-311`)."""
+
+  def __init__(self, kind, strike=0.0, barrier=0.0, component=0, log_state=False,
+               scale=1.0):
+    self.kind, self.strike, self.barrier = kind, float(strike), float(barrier)
+    self.component, self.log_state, self.scale = int(component), bool(log_state), float(scale)
+
+  def desc(self):
+    d = _lib.PayoffDesc()
+    d.kind, d.component = self.kind, self.component
+    d.transform = _lib.TRANSFORM_EXP if self.log_state else _lib.TRANSFORM_NONE
+    d.strike, d.barrier, d.scale = self.strike, self.barrier, self.scale
+    return d
+
+
+def european_call(strike, **kw):
+  return Payoff(_lib.PAYOFF_CALL, strike=strike, **kw)
+
+
+def european_put(strike, **kw):
+  return Payoff(_lib.PAYOFF_PUT, strike=strike, **kw)
+
+
+def up_and_out_call(strike, barrier, **kw):
+  return Payoff(_lib.PAYOFF_UP_OUT_CALL, strike=strike, barrier=barrier, **kw)
+
+
+def up_and_out_put(strike, barrier, **kw):
+  return Payoff(_lib.PAYOFF_UP_OUT_PUT, strike=strike, barrier=barrier, **kw)
+
+
+def down_and_out_put(strike, barrier, **kw):
+  return Payoff(_lib.PAYOFF_DOWN_OUT_PUT, strike=strike, barrier=barrier, **kw)
+
+
+def down_and_out_call(strike, barrier, **kw):
+  return Payoff(_lib.PAYOFF_DOWN_OUT_CALL, strike=strike, barrier=barrier, **kw)
+
+
+def identity(**kw):
+  return Payoff(_lib.PAYOFF_IDENTITY, **kw)
+
+
+# ----------------------------------------------------------- record plan ----
+def record_plan(keep_mask, num_requested_times):
+  """Replays the slot bookkeeping of `_while_loop`
+  (`models/euler_sampling.py:405-464`, `_euler_step` 531-535).
+
+  Returns (num_steps_to_execute, record_slot int32 [steps + 1]) where entry 0
+  refers to the initial state and entry s + 1 to the state after step s.
+  """
+  keep_mask = np.asarray(keep_mask, dtype=bool)
+  steps_num = keep_mask.shape[0] - 1
+  k = int(num_requested_times)
+  last_writer = {0: 0}                    # slot -> entry (0 = initial state)
+  written = int(keep_mask[0])
+  i = 0
+  while i < steps_num and written < k:
+    last_writer[written] = i + 1
+    written += int(keep_mask[i + 1])
+    i += 1
+  slots = np.full(i + 1, -1, dtype=np.int32)
+  for slot, entry in last_writer.items():
+    if slot < k:
+      slots[entry] = slot
+  return i, slots
+
+
+# ------------------------------------------------------------------ plan ----
+class RngSpec:
+  """Resolved random-number configuration of one sampling call."""
+
+  def __init__(self, random_type=None, seed=None, skip=0, normal_draws=None):
+    rt = random.RandomType.PSEUDO if random_type is None else random_type
+    if isinstance(rt, enum.Enum):
+      rt = random.RandomType(rt.value)
+    self.random_type = rt
+    self.seed, self.skip = seed, int(skip or 0)
+    self.normal_draws = normal_draws
+    self.antithetic = rt in (random.RandomType.PSEUDO_ANTITHETIC,
+                             random.RandomType.STATELESS_ANTITHETIC)
+    if normal_draws is not None:
+      self.type = _lib.RNG_DRAWS
+      self.antithetic = False
+    elif rt in (random.RandomType.PSEUDO, random.RandomType.PSEUDO_ANTITHETIC):
+      self.type = _lib.RNG_PHILOX
+      self.key, self.counter = philox.stateful_key_counter(seed)
+    elif rt in (random.RandomType.STATELESS,
+                random.RandomType.STATELESS_ANTITHETIC):
+      if seed is None:
+        raise ValueError('`seed` should be specified if the `random_type` is '
+                         '`STATELESS` or `STATELESS_ANTITHETIC`')
+      self.type = _lib.RNG_PHILOX
+      self.key, self.counter = philox.stateless_key_counter(seed)
+    elif rt == random.RandomType.SOBOL:
+      self.type = _lib.RNG_SOBOL
+    elif rt in (random.RandomType.HALTON, random.RandomType.HALTON_RANDOMIZED):
+      raise NotImplementedError(
+          'HALTON sequences are outside the B200 hot path; supported: PSEUDO, '
+          'STATELESS, PSEUDO_ANTITHETIC, STATELESS_ANTITHETIC, SOBOL.')
+    else:
+      raise NotImplementedError(
+          'Only STATELESS, PSEUDO, PSEUDO_ANTITHETIC, STATELESS_ANTITHETIC,  '
+          'HALTON, HALTON_RANDOMIZED, and SOBOL random types are currently '
+          'supported. Supplied: {}'.format(random_type))
+
+
+class Plan:
+  """Device-resident tables of one (model, grid, rng) configuration."""
+
+  def __init__(self, spec, all_times, num_steps, x0, rng, num_samples, dtype):
+    self.spec, self.rng = spec, rng
+    self.dtype = np.dtype(dtype)
+    self.num_samples = int(num_samples)
+    self.num_steps = int(num_steps)
+    all_times = np.asarray(all_times, dtype=self.dtype)
+    self.num_steps_total = all_times.shape[0] - 1
+    if rng.antithetic and self.num_samples % 2 != 0:
+      raise ValueError('First dimension of `sample_shape` should be even for '
+                       'PSEUDO_ANTITHETIC random type')
+    self.units = self.num_samples // 2 if rng.antithetic else self.num_samples
+
+    table = np.ascontiguousarray(
+        spec.coef_table(all_times, self.dtype)[:self.num_steps], dtype=np.float64)
+    x0 = np.ascontiguousarray(np.asarray(x0, dtype=self.dtype).reshape(-1),
+                              dtype=np.float64)
+    if x0.shape[0] != spec.dim:
+      raise ValueError('initial state must have {} components'.format(spec.dim))
+    self._keep = [table, x0]
+
+    m = _lib.ModelDesc()
+    m.kind, m.dtype = spec.kind, _tensor.tqf_dtype(self.dtype)
+    m.dim, m.num_factors = spec.dim, spec.num_factors
+    m.num_steps, m.num_steps_total = self.num_steps, self.num_steps_total
+    m.num_coef = spec.num_coef
+    m.coef = table.ctypes.data
+    m.x0 = x0.ctypes.data
+    extra = getattr(spec, 'device_arrays', None)
+    if extra is not None:
+      mat, vec = extra(self.dtype)
+      self._keep += [mat, vec]
+      m.matrix, m.vector = mat.ctypes.data, vec.ctypes.data
+
+    r = _lib.RngDesc()
+    r.type, r.antithetic, r.skip = rng.type, int(rng.antithetic), rng.skip
+    if rng.type == _lib.RNG_PHILOX:
+      r.key = rng.key
+      r.counter = rng.counter
+    elif rng.type == _lib.RNG_SOBOL:
+      dn = sobol.direction_numbers(self.num_steps_total * spec.num_factors)
+      self._keep.append(dn)
+      r.direction_numbers = dn.ctypes.data
+    else:
+      draws = _tensor.from_dlpack(rng.normal_draws)
+      want = (self.num_samples, self.num_steps_total, spec.num_factors)
+      if tuple(draws.shape) != want:
+        raise ValueError('normal_draws must have shape {} but has {}'.format(
+            want, tuple(draws.shape)))
+      draws = draws.to(device=_tensor.device(),
+                       dtype=_tensor.torch_dtype(self.dtype)).contiguous()
+      self._keep.append(draws)
+      r.draws_dev = draws.data_ptr()
+
+    _lib.require_cuda()
+    handle = C.c_void_p()
+    _lib.check(_lib.lib().tqf_plan_create(C.byref(m), C.byref(r),
+                                          self.num_samples, C.byref(handle)))
+    self._handle = handle
+
+  def close(self):
+    if getattr(self, '_handle', None):
+      _lib.lib().tqf_plan_destroy(self._handle)
+      self._handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  def paths(self, record_slot, num_times, unit_offset=0, unit_count=None):
+    """States at the recorded steps: a `[rows, num_times, dim]` VIEW of a
+    time-major `[num_times, dim, rows]` buffer (coalesced stores, no
+    transpose).  rows = units (x2 for antithetic: partners follow)."""
+    unit_count = self.units - unit_offset if unit_count is None else unit_count
+    rows = unit_count * (2 if self.rng.antithetic else 1)
+    dim = self.spec.dim
+    buf = _tensor.empty((num_times, dim, rows), self.dtype)
+    rec = np.ascontiguousarray(record_slot, dtype=np.int32)
+    _lib.check(_lib.lib().tqf_plan_paths(
+        self._handle, unit_offset, unit_count, rec.ctypes.data, buf.data_ptr(),
+        1, dim * rows, rows, _tensor.current_stream_ptr()))
+    return buf.permute(2, 0, 1)
+
+  def price_sums(self, payoffs, unit_offset=0, unit_count=None):
+    """Unnormalised per-payoff sums as a device tensor [num_payoffs, 4]:
+    (sum, sum of squares, number of non-finite payoffs, 0)."""
+    unit_count = self.units - unit_offset if unit_count is None else unit_count
+    descs = (_lib.PayoffDesc * len(payoffs))(*[p.desc() for p in payoffs])
+    sums = torch.zeros((len(payoffs), 4), dtype=torch.float64,
+                       device=_tensor.device())
+    _lib.check(_lib.lib().tqf_plan_price(
+        self._handle, unit_offset, unit_count, descs, len(payoffs),
+        sums.data_ptr(), _tensor.current_stream_ptr()))
+    return sums
+
+
+def measure_fma_peaks():
+  """(DFMA/s, FFMA/s) issue peaks of the current device."""
+  _lib.require_cuda()
+  d, f = C.c_double(), C.c_double()
+  _lib.check(_lib.lib().tqf_measure_fp64_peak(C.byref(d), C.byref(f)))
+  return d.value, f.value

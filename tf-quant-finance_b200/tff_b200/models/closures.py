@@ -1,0 +1,118 @@
+"""Drift / volatility callables that the device engine can recognise.
+
+The reference accepts arbitrary Python `drift_fn(t, x)` / `volatility_fn(t, x)`
+(`models/euler_sampling.py:27-47`).  A CUDA kernel cannot run Python, so the
+engine recognises callables that carry a `ModelSpec` (`tqf_spec`): the ones the
+model classes of this package return, or ones built with the helpers below.
+They stay ordinary callables -- `fn(t, x)` evaluates on the host with torch --
+so code that inspects drift / volatility values keeps working.  Anything else
+is rejected with NotImplementedError; there is no silent CPU fallback.
+"""
+import numpy as np
+import torch
+
+from tff_b200 import engine
+
+
+class DeviceClosure:
+  """A `drift_fn` or `volatility_fn` bound to a device model spec."""
+
+  def __init__(self, spec, role, host_fn):
+    self.tqf_spec = spec
+    self.role = role
+    self._host_fn = host_fn
+
+  def __call__(self, t, x):
+    return self._host_fn(t, x)
+
+
+def resolve_spec(drift_fn, volatility_fn):
+  """The ModelSpec shared by a (drift_fn, volatility_fn) pair."""
+  ds = getattr(drift_fn, 'tqf_spec', None)
+  vs = getattr(volatility_fn, 'tqf_spec', None)
+  if ds is None or vs is None:
+    raise NotImplementedError(
+        'The B200 path engine cannot run arbitrary Python drift/volatility '
+        'callables inside a CUDA kernel. Pass the closures of a model class '
+        '(GeometricBrownianMotion, HestonModel, HullWhiteModel1F, '
+        'MultivariateGeometricBrownianMotion) or build them with '
+        'tff_b200.models.closures.affine_closures / gbm_closures. '
+        'There is no CPU fallback.')
+  if ds is not vs:
+    raise NotImplementedError(
+        '`drift_fn` and `volatility_fn` must come from the same device model')
+  return ds
+
+
+def _as_tensor(x, like=None):
+  if isinstance(x, torch.Tensor):
+    return x
+  x = np.asarray(x)
+  t = torch.as_tensor(x)
+  if like is not None:
+    t = t.to(device=like.device, dtype=like.dtype)
+  return t
+
+
+def _p(param, t, like):
+  """Parameter value at scalar time `t` as a tensor like `like`."""
+  if callable(param):
+    tt = float(t.item() if isinstance(t, torch.Tensor) else t)
+    v = np.asarray(param(np.asarray([tt])))[0]
+  else:
+    v = np.asarray(param)
+  return torch.as_tensor(v, dtype=like.dtype, device=like.device)
+
+
+def affine_closures(a0, a1, b):
+  """(drift_fn, volatility_fn) of dX = (a0(t) + a1(t) X) dt + b(t) dW, dim 1.
+
+  `a0`, `a1`, `b` are scalars or callables of an array of times.  Covers the
+  log-space GBM of the reference's Monte-Carlo notebook
+  (`examples/jupyter_notebooks/Monte_Carlo_Euler_Scheme.ipynb:223-275`).
+  """
+  spec = engine.AffineSpec1F(a0, a1, b)
+
+  def drift(t, x):
+    x = _as_tensor(x)
+    return _p(a0, t, x) + _p(a1, t, x) * x
+
+  def vol(t, x):
+    x = _as_tensor(x)
+    return _p(b, t, x) * torch.ones(x.shape + (1,), dtype=x.dtype, device=x.device)
+  return DeviceClosure(spec, 'drift', drift), DeviceClosure(spec, 'volatility', vol)
+
+
+def gbm_closures(mean, volatility):
+  """(drift_fn, volatility_fn) of dX = mean(t) X dt + volatility(t) X dW."""
+  spec = engine.GbmSpec1F(mean, volatility)
+
+  def drift(t, x):
+    x = _as_tensor(x)
+    return _p(mean, t, x) * x
+
+  def vol(t, x):
+    x = _as_tensor(x)
+    return _p(volatility, t, x) * x.unsqueeze(-1)
+  return DeviceClosure(spec, 'drift', drift), DeviceClosure(spec, 'volatility', vol)
+
+
+def heston_closures(mean_reversion, theta, volvol, rho):
+  """Heston closures (`heston/heston_model.py:143-173`)."""
+  spec = engine.HestonEulerSpec(mean_reversion, theta, volvol, rho)
+
+  def vol(t, x):
+    x = _as_tensor(x)
+    v = torch.sqrt(torch.abs(x[..., 1]))
+    zeros = torch.zeros_like(v)
+    r, vv = _p(rho, t, x), _p(volvol, t, x)
+    col1 = torch.stack([v, vv * r * v], -1)
+    col2 = torch.stack([zeros, vv * torch.sqrt(1 - r**2) * v], -1)
+    return torch.stack([col1, col2], -1)
+
+  def drift(t, x):
+    x = _as_tensor(x)
+    var = x[..., 1]
+    k, th = _p(mean_reversion, t, x), _p(theta, t, x)
+    return torch.stack([-var / 2, k * (th - var)], -1)
+  return DeviceClosure(spec, 'drift', drift), DeviceClosure(spec, 'volatility', vol)

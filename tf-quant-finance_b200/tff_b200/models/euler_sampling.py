@@ -1,0 +1,169 @@
+"""The Euler sampling method for Ito processes -- B200 engine.
+
+Drop-in for `tf_quant_finance.models.euler_sampling.sample`
+(`models/euler_sampling.py:27-332`): same arguments, same output shape
+`batch_shape + [num_samples, k, dim]`, same draw layout for every
+`random_type`, so results equal the reference's on identical seeds.  The
+draws tensor of the reference is never built: normals are generated in the
+kernel that steps the paths.  `price` is the fused extension that also
+reduces payoffs in-kernel (no path leaves the registers).
+"""
+import numpy as np
+
+from tff_b200 import _tensor
+from tff_b200 import engine
+from tff_b200.math import random
+from tff_b200.models import closures
+from tff_b200.models import utils
+
+
+class InvalidArgumentError(ValueError):
+  """Stands in for `tf.errors.InvalidArgumentError` (TensorFlow is optional)."""
+
+
+def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
+             num_samples, initial_state, random_type, seed, skip, times_grid,
+             normal_draws, watch_params, validate_args, tolerance, dtype):
+  """Argument normalisation of `sample` (`euler_sampling.py:232-310`)."""
+  if watch_params is not None:
+    raise NotImplementedError(
+        '`watch_params` (pathwise Greeks through custom_loops.for_loop) is not '
+        'implemented by the B200 engine yet (SURVEY 8f-3).')
+  dtype = _tensor.infer_dtype(times, dtype)
+  times = _tensor.to_numpy(times, dtype).reshape(-1)
+  if tolerance is None:
+    tolerance = 1e-10 if dtype == np.float64 else 1e-6
+  tolerance = dtype.type(tolerance)
+  if validate_args and not np.all(times[1:] > times[:-1] + tolerance):
+    raise InvalidArgumentError('`times` increments should be greater '
+                               'than tolerance {0}'.format(tolerance))
+  if initial_state is None:
+    initial_state = np.zeros(dim, dtype=dtype)
+  initial_state = _tensor.to_numpy(initial_state, dtype)
+  batch_shape = initial_state.shape[:-2]
+  if num_time_steps is not None and time_step is not None:
+    raise ValueError(
+        'When `times_grid` is not supplied only one of either '
+        '`num_time_steps` or `time_step` should be defined but not both.')
+  if times_grid is None:
+    if time_step is None:
+      if num_time_steps is None:
+        raise ValueError(
+            'When `times_grid` is not supplied, either `num_time_steps` '
+            'or `time_step` should be defined.')
+      num_time_steps = int(num_time_steps)
+      time_step = dtype.type(times[-1] / dtype.type(num_time_steps))
+    else:
+      time_step = dtype.type(_tensor.to_numpy(time_step))
+  else:
+    times_grid = _tensor.to_numpy(times_grid, dtype)
+    if validate_args and not np.all(
+        times_grid[1:] > times_grid[:-1] + tolerance):
+      raise InvalidArgumentError('`times_grid` increments should be greater '
+                                 'than tolerance {0}'.format(tolerance))
+  all_times, keep_mask, _ = utils.prepare_grid(
+      times=times, time_step=time_step, num_time_steps=num_time_steps,
+      times_grid=times_grid, tolerance=tolerance, dtype=dtype)
+
+  if normal_draws is not None:
+    normal_draws = _tensor.from_dlpack(normal_draws)
+    # batch_shape + [num_samples, num_time_points, dim]
+    num_samples = int(normal_draws.shape[-3])
+    draws_dim = int(normal_draws.shape[-1])
+    if dim != draws_dim:
+      raise ValueError(
+          '`dim` should be equal to `normal_draws.shape[2]` but are '
+          '{0} and {1} respectively'.format(dim, draws_dim))
+    if validate_args and int(normal_draws.shape[-2]) != keep_mask.shape[0] - 1:
+      raise InvalidArgumentError('`num_time_steps` should be equal to '
+                                 '`tf.shape(normal_draws)[1]`')
+  if batch_shape or (normal_draws is not None and normal_draws.dim() > 3):
+    raise NotImplementedError(
+        'batched processes (`initial_state` of rank > 2) are not implemented '
+        'by the B200 engine yet; loop over the batch on the host.')
+  x0 = initial_state.reshape(-1, dim)
+  if x0.shape[0] != 1 and not np.all(x0 == x0[0]):
+    raise NotImplementedError(
+        'per-path initial states are not implemented by the B200 engine yet.')
+  spec = closures.resolve_spec(drift_fn, volatility_fn)
+  if spec.dim != dim:
+    raise ValueError('`dim` is {} but the model has dimension {}'.format(
+        dim, spec.dim))
+  rng = engine.RngSpec(random_type, seed, skip, normal_draws)
+  num_steps, record_slot = engine.record_plan(keep_mask, times.shape[0])
+  plan = engine.Plan(spec, all_times, num_steps, x0[0], rng, int(num_samples),
+                     dtype)
+  return plan, record_slot, times.shape[0]
+
+
+def sample(dim,
+           drift_fn,
+           volatility_fn,
+           times,
+           time_step=None,
+           num_time_steps=None,
+           num_samples=1,
+           initial_state=None,
+           random_type=None,
+           seed=None,
+           swap_memory=True,
+           skip=0,
+           precompute_normal_draws=True,
+           times_grid=None,
+           normal_draws=None,
+           watch_params=None,
+           validate_args=False,
+           tolerance=None,
+           dtype=None,
+           name=None):
+  """Returns a sample of paths from the process using the Euler method.
+
+  Same contract as the reference's `sample`.  `swap_memory`,
+  `precompute_normal_draws` and `name` only steer TensorFlow's execution and
+  are ignored: draws are never precomputed, and the result is defined to equal
+  the reference's precomputed-draws path.
+
+  Returns:
+    CUDA tensor of shape `[num_samples, k, dim]` (a zero-copy view of a
+    time-major buffer; call `.contiguous()` for sample-major memory).
+  """
+  del swap_memory, precompute_normal_draws, name
+  plan, record_slot, k = _prepare(
+      dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
+      num_samples, initial_state, random_type, seed, skip, times_grid,
+      normal_draws, watch_params, validate_args, tolerance, dtype)
+  try:
+    return plan.paths(record_slot, k)
+  finally:
+    plan.close()
+
+
+def price(dim, drift_fn, volatility_fn, times, payoffs, time_step=None,
+          num_time_steps=None, num_samples=1, initial_state=None,
+          random_type=None, seed=None, skip=0, times_grid=None,
+          normal_draws=None, validate_args=False, tolerance=None, dtype=None,
+          return_stats=False):
+  """Fused mode: Monte-Carlo means of `payoffs` on the state at `times[-1]`.
+
+  Equals `mean(payoff(sample(...)[:, -1, :]))` of the materialising path (and
+  barrier payoffs monitored on every grid point) without storing any path.
+  Returns a float64 numpy array `[len(payoffs)]`; with `return_stats` also the
+  standard errors and the number of non-finite payoffs.
+  """
+  plan, _, _ = _prepare(
+      dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
+      num_samples, initial_state, random_type, seed, skip, times_grid,
+      normal_draws, None, validate_args, tolerance, dtype)
+  try:
+    sums = plan.price_sums(list(payoffs)).cpu().numpy()
+  finally:
+    plan.close()
+  n = float(plan.num_samples)
+  mean = sums[:, 0] / n
+  if not return_stats:
+    return mean
+  var = np.maximum(sums[:, 1] / n - mean**2, 0.0)
+  return mean, np.sqrt(var / n), sums[:, 2]
+
+
+__all__ = ['sample', 'price']
