@@ -103,7 +103,7 @@ class ClockSampler(threading.Thread):
 
   def __init__(self, index):
     super().__init__(daemon=True)
-    self.index, self.samples, self.reasons, self._stop = index, [], set(), False
+    self.index, self.samples, self.reasons, self._halt = index, [], set(), False
     self.max_mhz = None
 
   def run(self):
@@ -111,7 +111,7 @@ class ClockSampler(threading.Thread):
          'clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    while not self._stop:
+    while not self._halt:
       try:
         out = subprocess.run(
             ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
@@ -127,7 +127,7 @@ class ClockSampler(threading.Thread):
       time.sleep(0.1)
 
   def stop(self):
-    self._stop = True
+    self._halt = True
     self.join(timeout=3)
     med = float(np.median(self.samples)) if self.samples else None
     return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}

@@ -235,7 +235,9 @@ def test_fused_price_matches_oracle(rng):
   rt, seed = rng
   dim, (drift, vol), (odrift, ovol), x0 = _models(dtype)['heston']
   n, steps = 4096, 20
-  times = np.linspace(0.05, 1.0, steps)
+  from oracle import grid as ogrid
+  all_times, _, _ = ogrid.euler_grid([1.0], dtype=dtype, time_step=0.05)
+  assert all_times.shape[0] == steps + 1
   payoffs = [engine.european_call(100.0, log_state=True),
              engine.european_put(95.0, log_state=True, scale=0.97),
              engine.up_and_out_call(100.0, 120.0, log_state=True),
@@ -245,9 +247,10 @@ def test_fused_price_matches_oracle(rng):
       dim, drift, vol, [1.0], payoffs, time_step=0.05, num_samples=n,
       initial_state=x0, random_type=tff.math.random.RandomType[rt], seed=seed,
       dtype=dtype, return_stats=True)
-  paths = oeuler.sample(dim, odrift, ovol, times, time_step=0.05, num_samples=n,
-                        initial_state=x0, random_type=odraws.RandomType[rt],
-                        seed=seed, dtype=dtype)
+  # every grid point of the times=[1.0] run, recorded through times_grid
+  paths = oeuler.sample(dim, odrift, ovol, all_times[1:], times_grid=all_times,
+                        num_samples=n, initial_state=x0,
+                        random_type=odraws.RandomType[rt], seed=seed, dtype=dtype)
   s = np.exp(paths[:, :, 0])
   st = s[:, -1]
   smax = np.maximum(s.max(axis=1), 100.0)
