@@ -220,6 +220,14 @@ int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
  * Synchronises. */
 int tqf_measure_fp64_peak(double* dfma_per_second, double* ffma_per_second);
 
+/* Test hook: evaluates one of the hand-written device math functions
+ * (csrc/tqf_math.cuh) elementwise on a device array, so that their accuracy
+ * can be checked against a multiprecision reference.
+ *   fn 0: log(x)  1: sqrt(x)  2: ndtri(x)  3: sin(x)  4: cos(x)  (x in the
+ *   domains stated in tqf_math.cuh). */
+int tqf_math_eval(int fn, const double* in_dev, double* out_dev, uint64_t n,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

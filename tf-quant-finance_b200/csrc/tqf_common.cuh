@@ -9,6 +9,7 @@
 #include <string>
 
 #include "tqf.h"
+#include "tqf_math.cuh"
 
 namespace tqf {
 
@@ -94,9 +95,9 @@ __device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, uint32_t x2
   double u1 = uint64_to_double(x0, x1);
   u1 = u1 < 1.0e-7 ? 1.0e-7 : u1;
   const double v1 = 6.283185307179586476925286766559 * uint64_to_double(x2, x3);
-  const double u2 = sqrt(-2.0 * log(u1));
+  const double u2 = fm::sqrt_pos(-2.0 * fm::log_pos(u1));
   double s, c;
-  sincos(v1, &s, &c);
+  fm::sincos_2pi(v1, &s, &c);
   *n0 = s * u2;
   *n1 = c * u2;
 }
@@ -117,7 +118,7 @@ __device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float* n0,
 
 // --------------------------------------------------------- inverse CDF ----
 // sqrt(2) erfinv(2u - 1) == ndtri(u) (multivariate_normal.py:420).
-__device__ __forceinline__ double ndtri(double u) { return normcdfinv(u); }
+__device__ __forceinline__ double ndtri(double u) { return fm::ndtri_q(u - 0.5); }
 __device__ __forceinline__ float ndtri(float u) { return normcdfinvf(u); }
 
 // ------------------------------------------------------------- Sobol ------

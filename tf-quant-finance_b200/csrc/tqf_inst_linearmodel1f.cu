@@ -4,7 +4,7 @@
 
 namespace tqf {
 template int launch_path_kernel<LinearModel1F<double>>(int, bool, int, int, size_t,
-                                            const KParams<double>&, cudaStream_t);
+                                            const KParams<double>&, cudaStream_t, int*);
 template int launch_path_kernel<LinearModel1F<float>>(int, bool, int, int, size_t,
-                                           const KParams<float>&, cudaStream_t);
+                                           const KParams<float>&, cudaStream_t, int*);
 }  // namespace tqf

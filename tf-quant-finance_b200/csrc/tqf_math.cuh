@@ -1,0 +1,202 @@
+// Hand-written FP64 device math for the fused path kernels.
+//
+// The fused mode is bound by the FP64 pipe (64 DFMA/clk/SM) and by issue slots,
+// so the transcendental functions behind every normal draw are written for a
+// minimal DFMA count with (almost) no integer / branch overhead, instead of
+// calling libdevice (normcdfinv, log, sincos, sqrt carry special-case handling
+// that more than doubles the issued instructions -- profiles/README.md).
+//
+// Everything is vectorised over K independent arguments held by ONE thread:
+// sm_100a's DFMA cannot take a constant-bank operand, so every polynomial
+// coefficient costs a load (LDC.128 fetches two); evaluating K Horner chains
+// side by side amortises that load over K DFMAs and gives the FP64 pipe K
+// independent dependency chains per thread.
+//
+// Coefficients: tools/fit_math.py -> tqf_math_coef.h (highest order first).
+// Accuracy (checked on the GPU against mpmath by tests/test_gpu_math.py):
+// <= 2 ulp for log / sqrt / sincos on their stated domains, <= 4e-16 relative
+// for ndtri.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tqf_math_coef.h"
+
+namespace tqf {
+namespace fm {
+
+// Two consecutive coefficients from the constant bank.  `volatile` keeps the
+// compiler from hoisting all of them out of the step loop into registers.
+__device__ __forceinline__ void ldc2(const double* c, double* a, double* b) {
+  asm volatile("ld.const.v2.f64 {%0, %1}, [%2];"
+               : "=d"(*a), "=d"(*b)
+               : "l"(__cvta_generic_to_constant(c)));
+}
+
+// p[k] = sum_i c[i] y[k]^(N-1-i)  (c highest order first, padded to even).
+template <int N, int K>
+__device__ __forceinline__ void horner_v(const double* c, const double (&y)[K],
+                                         double (&p)[K]) {
+  double c0, c1;
+  ldc2(c, &c0, &c1);
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = fma(c0, y[k], c1);
+#pragma unroll
+  for (int i = 2; i + 1 < N; i += 2) {
+    ldc2(c + i, &c0, &c1);
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = fma(fma(p[k], y[k], c0), y[k], c1);
+  }
+  if (N & 1) {
+    ldc2(c + N - 1, &c0, &c1);  // c1 is the zero pad
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = fma(p[k], y[k], c0);
+  }
+}
+
+// 1/d, d normal and positive: MUFU.RCP64H (2^-23) + two Newton steps.
+__device__ __forceinline__ double rcp_pos(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// sqrt(v), v normal and positive: MUFU.RSQ64H (2^-22), one coupled
+// Goldschmidt step (2^-43) and a final Newton correction.  7 FP64 ops.
+__device__ __forceinline__ double sqrt_pos(double v) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+  double g = v * y;
+  double h = 0.5 * y;
+  const double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  const double d = fma(-g, g, v);
+  return fma(d, h, g);
+}
+
+// log(a[k]), a normal, positive and finite (no zero / inf / nan / denormal
+// handling: the callers' arguments are in [2^-60, 2]).
+//   a = 2^k m, m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1),
+//   log a = k ln2 + 2 s + s^3 R(s^2).
+template <int K>
+__device__ __forceinline__ void log_pos_v(const double (&a)[K], double (&out)[K]) {
+  const double kLn2Hi = 6.93147180369123816490e-01;  // fdlibm split
+  const double kLn2Lo = 1.90821492927058770002e-10;
+  double s[K], z[K], kd[K], R[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int hi = __double2hiint(a[k]);
+    const int lo = __double2loint(a[k]);
+    const int e = (hi - 0x3fe6a09e) >> 20;
+    hi -= e << 20;
+    const double m = __hiloint2double(hi, lo);
+    kd[k] = static_cast<double>(e);
+    s[k] = (m - 1.0) * rcp_pos(m + 1.0);
+    z[k] = s[k] * s[k];
+  }
+  horner_v<TQF_LOG_R_N, K>(TQF_LOG_R, z, R);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double t = fma(s[k] * z[k], R[k], kd[k] * kLn2Lo);
+    out[k] = fma(kd[k], kLn2Hi, fma(2.0, s[k], t));
+  }
+}
+
+// Inverse normal CDF of u = 1/2 + q (q exact), |q| < 1/2:
+//   sqrt(2) erfinv(2 q) = q * P(w),  w = -log(1 - 4 q^2)
+// (the parametrisation of M. Giles, "Approximating the erfinv function", 2010,
+// with our own double-precision fits).  The central branch w < 6.25 covers
+// |q| < 0.49903, i.e. 99.8% of uniform draws; the tail branch is entered by a
+// thread only when one of its K draws needs it.
+template <int K>
+__device__ __forceinline__ void ndtri_q_v(const double (&q)[K], double (&zout)[K]) {
+  double a[K], w[K], y[K], p[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) a[k] = fma(-4.0 * q[k], q[k], 1.0);
+  log_pos_v<K>(a, w);
+  bool tail = false;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    w[k] = -w[k];
+    y[k] = w[k] - TQF_NDTRI_C_MID;
+    tail = tail || (w[k] >= TQF_NDTRI_W0);
+  }
+  horner_v<TQF_NDTRI_C_N, K>(TQF_NDTRI_C, y, p);
+  if (tail) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (w[k] >= TQF_NDTRI_W0) {
+        const double yt[1] = {sqrt_pos(w[k]) - TQF_NDTRI_T_MID};
+        double pt[1];
+        horner_v<TQF_NDTRI_T_N, 1>(TQF_NDTRI_T, yt, pt);
+        p[k] = pt[0];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) zout[k] = q[k] * p[k];
+}
+
+// sin(v[k]), cos(v[k]) for v in [0, 2 pi] (Box-Muller angle): Cody-Waite
+// reduction by pi/2 with an FMA pair, then the kernels on |f| <= pi/4.
+template <int K>
+__device__ __forceinline__ void sincos_2pi_v(const double (&v)[K], double (&sn)[K],
+                                             double (&cs)[K]) {
+  const double kTwoOverPi = 6.36619772367581382433e-01;
+  const double kPio2Hi = 1.57079632679489655800e+00;
+  const double kPio2Lo = 6.12323399573676603587e-17;
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+  double f[K], z[K], ps[K], pc[K];
+  int j[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double jm = fma(v[k], kTwoOverPi, kMagic);
+    j[k] = __double2loint(jm);
+    const double jd = jm - kMagic;
+    f[k] = fma(-jd, kPio2Lo, fma(-jd, kPio2Hi, v[k]));
+    z[k] = f[k] * f[k];
+  }
+  horner_v<TQF_SIN_P_N, K>(TQF_SIN_P, z, ps);
+  horner_v<TQF_COS_P_N, K>(TQF_COS_P, z, pc);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double s = f[k] * ps[k];
+    const double c = pc[k];
+    double rs = (j[k] & 1) ? c : s;
+    double rc = (j[k] & 1) ? s : c;
+    if (j[k] & 2) rs = -rs;
+    if ((j[k] + 1) & 2) rc = -rc;
+    sn[k] = rs;
+    cs[k] = rc;
+  }
+}
+
+// scalar conveniences (fill kernels, test hook)
+__device__ __forceinline__ double log_pos(double a) {
+  const double in[1] = {a};
+  double out[1];
+  log_pos_v<1>(in, out);
+  return out[0];
+}
+__device__ __forceinline__ double ndtri_q(double q) {
+  const double in[1] = {q};
+  double out[1];
+  ndtri_q_v<1>(in, out);
+  return out[0];
+}
+__device__ __forceinline__ void sincos_2pi(double v, double* sn, double* cs) {
+  const double in[1] = {v};
+  double s[1], c[1];
+  sincos_2pi_v<1>(in, s, c);
+  *sn = s[0];
+  *cs = c[0];
+}
+
+}  // namespace fm
+}  // namespace tqf

@@ -14,9 +14,9 @@ int upload_sobol_table(const int32_t* direction_numbers, int dim, uint32_t** out
 
 #define TQF_EXTERN_MODEL(M)                                                             \
   extern template int launch_path_kernel<M<double>>(int, bool, int, int, size_t,        \
-                                                    const KParams<double>&, cudaStream_t); \
+                                                    const KParams<double>&, cudaStream_t, int*); \
   extern template int launch_path_kernel<M<float>>(int, bool, int, int, size_t,         \
-                                                   const KParams<float>&, cudaStream_t);
+                                                   const KParams<float>&, cudaStream_t, int*);
 TQF_EXTERN_MODEL(AffineModel1F)
 TQF_EXTERN_MODEL(GbmModel1F)
 TQF_EXTERN_MODEL(LinearModel1F)
@@ -120,18 +120,18 @@ static int rng_kind(const tqf_plan* plan) {
 
 template <typename Real>
 static int dispatch(const tqf_plan* plan, int mode, int grid, size_t smem, const KParams<Real>& P,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, int* grid_out) {
   const int rk = rng_kind(plan);
   const bool anti = plan->rng.antithetic != 0;
   switch (plan->model.kind) {
     case TQF_MODEL_AFFINE_1F:
-      return launch_path_kernel<AffineModel1F<Real>>(rk, anti, mode, grid, smem, P, stream);
+      return launch_path_kernel<AffineModel1F<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     case TQF_MODEL_GBM_1F:
-      return launch_path_kernel<GbmModel1F<Real>>(rk, anti, mode, grid, smem, P, stream);
+      return launch_path_kernel<GbmModel1F<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     case TQF_MODEL_LINEAR_1F:
-      return launch_path_kernel<LinearModel1F<Real>>(rk, anti, mode, grid, smem, P, stream);
+      return launch_path_kernel<LinearModel1F<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     case TQF_MODEL_HESTON_EULER:
-      return launch_path_kernel<HestonEulerModel<Real>>(rk, anti, mode, grid, smem, P, stream);
+      return launch_path_kernel<HestonEulerModel<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     default:
       set_error("model kind not supported by the generic path kernel");
       return TQF_ERR_UNSUPPORTED;
@@ -154,10 +154,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     if (d.kind >= TQF_PAYOFF_UP_OUT_CALL && d.kind <= TQF_PAYOFF_DOWN_OUT_CALL) P.need_extrema = 1;
   }
   P.partials = plan->partials_dev;
-  int grid = static_cast<int>(P.num_chunks < static_cast<uint64_t>(plan->max_grid)
-                                  ? P.num_chunks
-                                  : static_cast<uint64_t>(plan->max_grid));
-  if (grid < 1) grid = 1;
+  int grid = 1;
   const int rk = rng_kind(plan);
   bool in_smem = true;
   size_t smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PRICE, true);
@@ -166,7 +163,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PRICE, false);
   }
   P.tables_in_smem = in_smem ? 1 : 0;
-  int rc = dispatch<Real>(plan, MODE_PRICE, grid, smem, P, stream);
+  int rc = dispatch<Real>(plan, MODE_PRICE, plan->max_grid, smem, P, stream, &grid);
   if (rc != TQF_OK) return rc;
   reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev);
   TQF_CUDA_OK(cudaGetLastError());
@@ -188,10 +185,7 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   P.stride_time = stride_time;
   P.stride_dim = stride_dim;
   P.anti_half = path_count;  // rows of the antithetic partners follow the shard's own rows
-  int grid = static_cast<int>(P.num_chunks < static_cast<uint64_t>(plan->max_grid)
-                                  ? P.num_chunks
-                                  : static_cast<uint64_t>(plan->max_grid));
-  if (grid < 1) grid = 1;
+  int grid = 1;
   const int rk = rng_kind(plan);
   bool in_smem = true;
   size_t smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PATHS, true);
@@ -200,7 +194,7 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PATHS, false);
   }
   P.tables_in_smem = in_smem ? 1 : 0;
-  return dispatch<Real>(plan, MODE_PATHS, grid, smem, P, stream);
+  return dispatch<Real>(plan, MODE_PATHS, plan->max_grid, smem, P, stream, &grid);
 }
 
 extern "C" {

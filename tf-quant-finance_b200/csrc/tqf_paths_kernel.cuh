@@ -23,6 +23,7 @@ constexpr int kBlock = 128;       // threads per CTA == Sobol indices per chunk
 constexpr int kLowBits = 7;       // log2(kBlock)
 constexpr int kSobolTileDims = 512;  // Sobol dimensions staged in smem at once
 constexpr int kWarps = kBlock / 32;
+constexpr int kMaxPPT = 4;      // most paths carried by one thread
 
 enum { MODE_PRICE = 0, MODE_PATHS = 1 };
 enum { RNGK_PHILOX = 0, RNGK_SOBOL = 1, RNGK_DRAWS = 2 };
@@ -78,7 +79,7 @@ struct AffineModel1F {  // a = a0 + a1 x, S = b
   using Real = R;
   static constexpr int DIM = 1, NF = 1, NCOEF = 5;
   __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
-                                              const Real* c) {
+                                              const Real (&c)[NCOEF]) {
     const Real dw = z[0] * c[1];
     const Real dt_inc = c[0] * (c[2] + c[3] * x[0]);
     const Real dw_inc = c[4] * dw;
@@ -91,7 +92,7 @@ struct GbmModel1F {  // a = mu x, S = sigma x  (univariate_geometric_brownian_mo
   using Real = R;
   static constexpr int DIM = 1, NF = 1, NCOEF = 4;
   __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
-                                              const Real* c) {
+                                              const Real (&c)[NCOEF]) {
     const Real dw = z[0] * c[1];
     const Real dt_inc = c[0] * (c[2] * x[0]);
     const Real dw_inc = (c[3] * x[0]) * dw;
@@ -104,7 +105,7 @@ struct LinearModel1F {  // x' = A x + B + C z  (HW exact OU step, vector_hull_wh
   using Real = R;
   static constexpr int DIM = 1, NF = 1, NCOEF = 5;
   __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
-                                              const Real* c) {
+                                              const Real (&c)[NCOEF]) {
     x[0] = (c[2] * x[0] + c[3]) + c[4] * z[0];
   }
 };
@@ -115,7 +116,7 @@ struct HestonEulerModel {  // heston/heston_model.py:143-173; state [X = log S, 
   static constexpr int DIM = 2, NF = 2, NCOEF = 7;
   // c: dt, sqrt_dt, kappa, theta, volvol*rho, volvol*sqrt(1-rho^2), unused
   __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
-                                              const Real* c) {
+                                              const Real (&c)[NCOEF]) {
     const Real var = x[1];
     const Real vol = sqrt(fabs(var));
     const Real dw0 = z[0] * c[1];
@@ -128,63 +129,102 @@ struct HestonEulerModel {  // heston/heston_model.py:143-173; state [X = log S, 
 };
 
 // ------------------------------------------------------- normal streams ---
-template <typename Real>
-struct PhiloxStream;
+// PPT independent Philox streams held by one thread (one per path it carries);
+// all of them sit at the same position inside their group, so the Box-Muller
+// of the PPT groups is evaluated side by side (tqf_math.cuh).
+template <typename Real, int PPT>
+struct PhiloxStreamV;
 
-template <>
-struct PhiloxStream<double> {
-  uint64_t group;
-  double b0, b1;
+template <int PPT>
+struct PhiloxStreamV<double, PPT> {
+  uint64_t group[PPT];
+  double b0[PPT], b1[PPT];
   int pos;
   __device__ __forceinline__ void refill(const PhiloxKey& key, const PhiloxCtr& ctr) {
-    const uint4 w = philox_group(ctr, key, group);
-    box_muller(w.x, w.y, w.z, w.w, &b0, &b1);
-    ++group;
+    double u1[PPT], v1[PPT], lg[PPT], sn[PPT], cs[PPT];
+#pragma unroll
+    for (int a = 0; a < PPT; ++a) {
+      const uint4 w = philox_group(ctr, key, group[a]);
+      ++group[a];
+      const double u = uint64_to_double(w.x, w.y);
+      u1[a] = u < 1.0e-7 ? 1.0e-7 : u;
+      v1[a] = 6.283185307179586476925286766559 * uint64_to_double(w.z, w.w);
+    }
+    fm::log_pos_v<PPT>(u1, lg);
+    fm::sincos_2pi_v<PPT>(v1, sn, cs);
+#pragma unroll
+    for (int a = 0; a < PPT; ++a) {
+      const double r = fm::sqrt_pos(-2.0 * lg[a]);
+      b0[a] = sn[a] * r;
+      b1[a] = cs[a] * r;
+    }
   }
   __device__ __forceinline__ void init(const PhiloxKey& key, const PhiloxCtr& ctr,
-                                       uint64_t first_element) {
-    group = first_element >> 1;
+                                       const uint64_t (&first_element)[PPT]) {
+#pragma unroll
+    for (int a = 0; a < PPT; ++a) group[a] = first_element[a] >> 1;
     refill(key, ctr);
-    pos = static_cast<int>(first_element & 1);
+    pos = static_cast<int>(first_element[0] & 1);
   }
-  __device__ __forceinline__ double next(const PhiloxKey& key, const PhiloxCtr& ctr) {
+  __device__ __forceinline__ void next(const PhiloxKey& key, const PhiloxCtr& ctr,
+                                       double (&z)[PPT]) {
     if (pos == 2) {
       refill(key, ctr);
       pos = 0;
     }
-    const double r = pos == 0 ? b0 : b1;
+#pragma unroll
+    for (int a = 0; a < PPT; ++a) z[a] = pos == 0 ? b0[a] : b1[a];
     ++pos;
-    return r;
   }
 };
 
-template <>
-struct PhiloxStream<float> {
-  uint64_t group;
-  float b0, b1, b2, b3;
+template <int PPT>
+struct PhiloxStreamV<float, PPT> {
+  uint64_t group[PPT];
+  float b[PPT][4];
   int pos;
   __device__ __forceinline__ void refill(const PhiloxKey& key, const PhiloxCtr& ctr) {
-    const uint4 w = philox_group(ctr, key, group);
-    box_muller(w.x, w.y, &b0, &b1);
-    box_muller(w.z, w.w, &b2, &b3);
-    ++group;
+#pragma unroll
+    for (int a = 0; a < PPT; ++a) {
+      const uint4 w = philox_group(ctr, key, group[a]);
+      ++group[a];
+      box_muller(w.x, w.y, &b[a][0], &b[a][1]);
+      box_muller(w.z, w.w, &b[a][2], &b[a][3]);
+    }
   }
   __device__ __forceinline__ void init(const PhiloxKey& key, const PhiloxCtr& ctr,
-                                       uint64_t first_element) {
-    group = first_element >> 2;
+                                       const uint64_t (&first_element)[PPT]) {
+#pragma unroll
+    for (int a = 0; a < PPT; ++a) group[a] = first_element[a] >> 2;
     refill(key, ctr);
-    pos = static_cast<int>(first_element & 3);
+    pos = static_cast<int>(first_element[0] & 3);
   }
-  __device__ __forceinline__ float next(const PhiloxKey& key, const PhiloxCtr& ctr) {
+  __device__ __forceinline__ void next(const PhiloxKey& key, const PhiloxCtr& ctr,
+                                       float (&z)[PPT]) {
     if (pos == 4) {
       refill(key, ctr);
       pos = 0;
     }
-    const float r = pos == 0 ? b0 : (pos == 1 ? b1 : (pos == 2 ? b2 : b3));
+#pragma unroll
+    for (int a = 0; a < PPT; ++a)
+      z[a] = pos == 0 ? b[a][0] : (pos == 1 ? b[a][1] : (pos == 2 ? b[a][2] : b[a][3]));
     ++pos;
-    return r;
   }
 };
+
+// Inverse-CDF transform of K Sobol integer points.
+template <int K>
+__device__ __forceinline__ void sobol_normals(const uint32_t (&xb)[K], double (&z)[K]) {
+  double q[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = sobol_uniform_f64(xb[k]) - 0.5;
+  fm::ndtri_q_v<K>(q, z);
+}
+template <int K>
+__device__ __forceinline__ void sobol_normals(const uint32_t (&xb)[K], float (&z)[K]) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) z[k] = ndtri(sobol_uniform_f32(xb[k]));
+}
 
 // ------------------------------------------------------------ payoffs -----
 __device__ __forceinline__ double eval_payoff(const PayoffK& d, double x_final, double x_max,
@@ -223,16 +263,24 @@ __device__ __forceinline__ double eval_payoff(const PayoffK& d, double x_final, 
 }
 
 // -------------------------------------------------------------- kernel ----
+// Paths carried by one thread: enough that PPT * (draws per step) = 4 inverse
+// CDFs (Sobol) or 4 Box-Muller pairs (Philox) are evaluated side by side.
+template <class Model, int RNGK>
+struct PathsPerThread {
+  static constexpr int value = (RNGK == RNGK_SOBOL) ? (Model::NF >= 4 ? 1 : 4 / Model::NF) : 4;
+};
+
 template <class Model, int RNGK, bool ANTI, int MODE>
 __global__ void __launch_bounds__(kBlock)
 path_kernel(const KParams<typename Model::Real> P) {
   using Real = typename Model::Real;
   constexpr int DIM = Model::DIM, NF = Model::NF, NCOEF = Model::NCOEF;
   constexpr int NPATH = ANTI ? 2 : 1;
+  constexpr int PPT = PathsPerThread<Model, RNGK>::value;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: coef [S][NCOEF] Real | record_slot [S+1] int | sobol high [T] u32
-  //         | sobol low [T][8] u32 | accumulators [kWarps][8][3] double
+  // layout: coef [S][NCOEF] Real | record_slot [S+1] int | sobol high [PPT][T]
+  //         u32 | sobol low [T][8] u32 | accumulators [kWarps][8][3] double
   Real* s_coef = reinterpret_cast<Real*>(smem_raw);
   size_t off = 0;
   if (P.tables_in_smem) {
@@ -243,7 +291,7 @@ path_kernel(const KParams<typename Model::Real> P) {
   if (MODE == MODE_PATHS && P.tables_in_smem)
     off += ((static_cast<size_t>(P.num_steps) + 1) * sizeof(int) + 15) & ~static_cast<size_t>(15);
   uint32_t* s_high = reinterpret_cast<uint32_t*>(smem_raw + off);
-  if (RNGK == RNGK_SOBOL) off += kSobolTileDims * sizeof(uint32_t);
+  if (RNGK == RNGK_SOBOL) off += static_cast<size_t>(kMaxPPT) * kSobolTileDims * sizeof(uint32_t);
   uint4* s_low = reinterpret_cast<uint4*>(smem_raw + off);
   if (RNGK == RNGK_SOBOL) off += static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   double* s_acc = reinterpret_cast<double*>(smem_raw + off);
@@ -264,48 +312,56 @@ path_kernel(const KParams<typename Model::Real> P) {
   }
   __syncthreads();
 
-  // Sobol: masks of this thread's low index bits (constant over chunks).
+  // Sobol: masks of this thread's low index bits (the same for all its paths).
   uint32_t lowmask[kLowBits];
 #pragma unroll
   for (int b = 0; b < kLowBits; ++b) lowmask[b] = 0u - ((static_cast<uint32_t>(tid) >> b) & 1u);
 
   constexpr int TILE_STEPS = (kSobolTileDims / NF) > 0 ? (kSobolTileDims / NF) : 1;
   const uint64_t stream_stride = static_cast<uint64_t>(P.num_steps_total) * NF;
+  const uint64_t num_super = (P.num_chunks + PPT - 1) / PPT;
 
-  for (uint64_t chunk = blockIdx.x; chunk < P.num_chunks; chunk += gridDim.x) {
-    const uint64_t index = P.chunk_base + chunk * kBlock + tid;  // global unit / Sobol index
-    const bool valid = index >= P.first_index && index < P.first_index + P.path_count;
-    const uint64_t local = index - P.first_index;              // row inside the shard
-    const uint64_t unit = P.path_offset + local;               // global path (or pair) number
+  for (uint64_t sc = blockIdx.x; sc < num_super; sc += gridDim.x) {
+    // path a of this thread: Sobol index / unit number chunk_base + (sc*PPT+a)*128 + tid
+    bool valid[PPT];
+    uint64_t local[PPT];
+    uint64_t first_element[PPT];
+#pragma unroll
+    for (int a = 0; a < PPT; ++a) {
+      const uint64_t index = P.chunk_base + (sc * PPT + a) * kBlock + tid;
+      valid[a] = index >= P.first_index && index < P.first_index + P.path_count;
+      local[a] = index - P.first_index;  // row inside the shard
+      first_element[a] = valid[a] ? (P.path_offset + local[a]) * stream_stride : 0;
+    }
 
-    Real x[NPATH][DIM];
+    Real x[PPT][NPATH][DIM], xmax[PPT][NPATH][DIM], xmin[PPT][NPATH][DIM];
 #pragma unroll
-    for (int a = 0; a < NPATH; ++a)
+    for (int a = 0; a < PPT; ++a)
 #pragma unroll
-      for (int j = 0; j < DIM; ++j) x[a][j] = P.x0[j];
-    Real xmax[NPATH][DIM], xmin[NPATH][DIM];
+      for (int h = 0; h < NPATH; ++h)
 #pragma unroll
-    for (int a = 0; a < NPATH; ++a)
-#pragma unroll
-      for (int j = 0; j < DIM; ++j) {
-        xmax[a][j] = x[a][j];
-        xmin[a][j] = x[a][j];
-      }
+        for (int j = 0; j < DIM; ++j) {
+          x[a][h][j] = P.x0[j];
+          xmax[a][h][j] = P.x0[j];
+          xmin[a][h][j] = P.x0[j];
+        }
 
-    PhiloxStream<Real> stream;
-    if (RNGK == RNGK_PHILOX) stream.init(P.key, P.ctr, valid ? unit * stream_stride : 0);
-    const Real* my_draws = nullptr;
-    if (RNGK == RNGK_DRAWS) my_draws = P.draws + (valid ? unit : 0) * stream_stride;
+    PhiloxStreamV<Real, PPT> stream;
+    if (RNGK == RNGK_PHILOX) stream.init(P.key, P.ctr, first_element);
 
     if (MODE == MODE_PATHS) {
       const int slot = rec_tab[0];
-      if (slot >= 0 && valid) {
+      if (slot >= 0) {
 #pragma unroll
-        for (int a = 0; a < NPATH; ++a)
+        for (int a = 0; a < PPT; ++a)
+          if (valid[a]) {
 #pragma unroll
-          for (int j = 0; j < DIM; ++j)
-            P.out[static_cast<int64_t>(local + a * P.anti_half) * P.stride_path +
-                  slot * P.stride_time + j * P.stride_dim] = x[a][j];
+            for (int h = 0; h < NPATH; ++h)
+#pragma unroll
+              for (int j = 0; j < DIM; ++j)
+                P.out[static_cast<int64_t>(local[a] + h * P.anti_half) * P.stride_path +
+                      slot * P.stride_time + j * P.stride_dim] = x[a][h][j];
+          }
       }
     }
 
@@ -313,76 +369,106 @@ path_kernel(const KParams<typename Model::Real> P) {
       const int s1 = min(P.num_steps, s0 + TILE_STEPS);
       if (RNGK == RNGK_SOBOL) {
         // Stage the direction numbers of dimensions [s0*NF, s1*NF): the XOR of
-        // the chunk's common high index bits, and the kLowBits low columns.
+        // each chunk's common high index bits, and the kLowBits low columns.
         __syncthreads();
-        const uint32_t high_bits = static_cast<uint32_t>((P.chunk_base + chunk * kBlock) >> kLowBits);
         for (int dd = tid; dd < (s1 - s0) * NF; dd += kBlock) {
           const uint32_t* v = P.sobol_v + (static_cast<size_t>(s0) * NF + dd) * 32;
-          const uint4 l0 = *reinterpret_cast<const uint4*>(v);
-          const uint4 l1 = *reinterpret_cast<const uint4*>(v + 4);
-          s_low[2 * dd] = l0;
-          s_low[2 * dd + 1] = l1;
-          uint32_t h = 0;
-          uint32_t hb = high_bits;
-          while (hb) {
-            const int b = __ffs(hb) - 1;
-            h ^= v[kLowBits + b];
-            hb &= hb - 1;
+          s_low[2 * dd] = *reinterpret_cast<const uint4*>(v);
+          s_low[2 * dd + 1] = *reinterpret_cast<const uint4*>(v + 4);
+#pragma unroll
+          for (int a = 0; a < PPT; ++a) {
+            uint32_t hb = static_cast<uint32_t>(
+                (P.chunk_base + (sc * PPT + a) * kBlock) >> kLowBits);
+            uint32_t h = 0;
+            while (hb) {
+              const int b = __ffs(hb) - 1;
+              h ^= v[kLowBits + b];
+              hb &= hb - 1;
+            }
+            s_high[a * kSobolTileDims + dd] = h;
           }
-          s_high[dd] = h;
         }
         __syncthreads();
       }
       for (int s = s0; s < s1; ++s) {
-        Real z[NF];
+        Real z[PPT][NF];
+        if (RNGK == RNGK_PHILOX) {
 #pragma unroll
-        for (int j = 0; j < NF; ++j) {
-          if (RNGK == RNGK_PHILOX) {
-            z[j] = stream.next(P.key, P.ctr);
-          } else if (RNGK == RNGK_SOBOL) {
+          for (int j = 0; j < NF; ++j) {
+            Real zz[PPT];
+            stream.next(P.key, P.ctr, zz);
+#pragma unroll
+            for (int a = 0; a < PPT; ++a) z[a][j] = zz[a];
+          }
+        } else if (RNGK == RNGK_SOBOL) {
+          uint32_t xb[PPT * NF];
+#pragma unroll
+          for (int j = 0; j < NF; ++j) {
             const int dd = (s - s0) * NF + j;
             const uint4 l0 = s_low[2 * dd];
             const uint4 l1 = s_low[2 * dd + 1];
-            uint32_t xb = s_high[dd];
-            xb ^= l0.x & lowmask[0];
-            xb ^= l0.y & lowmask[1];
-            xb ^= l0.z & lowmask[2];
-            xb ^= l0.w & lowmask[3];
-            xb ^= l1.x & lowmask[4];
-            xb ^= l1.y & lowmask[5];
-            xb ^= l1.z & lowmask[6];
-            z[j] = ndtri(RealTraits<Real>::sobol_uniform(xb));
-          } else {
-            z[j] = my_draws[static_cast<size_t>(s) * NF + j];
+            uint32_t lowx = l0.x & lowmask[0];
+            lowx ^= l0.y & lowmask[1];
+            lowx ^= l0.z & lowmask[2];
+            lowx ^= l0.w & lowmask[3];
+            lowx ^= l1.x & lowmask[4];
+            lowx ^= l1.y & lowmask[5];
+            lowx ^= l1.z & lowmask[6];
+#pragma unroll
+            for (int a = 0; a < PPT; ++a) xb[a * NF + j] = lowx ^ s_high[a * kSobolTileDims + dd];
           }
+          Real zz[PPT * NF];
+          sobol_normals<PPT * NF>(xb, zz);
+#pragma unroll
+          for (int a = 0; a < PPT; ++a)
+#pragma unroll
+            for (int j = 0; j < NF; ++j) z[a][j] = zz[a * NF + j];
+        } else {
+#pragma unroll
+          for (int a = 0; a < PPT; ++a)
+#pragma unroll
+            for (int j = 0; j < NF; ++j)
+              z[a][j] = P.draws[first_element[a] + static_cast<size_t>(s) * NF + j];
         }
         const Real* c = coef_tab + s * NCOEF;
-        Model::step(x[0], z, c);
-        if (ANTI) {
-          Real zm[NF];
+        Real cc[NCOEF];
 #pragma unroll
-          for (int j = 0; j < NF; ++j) zm[j] = -z[j];
-          Model::step(x[NPATH - 1], zm, c);
+        for (int i = 0; i < NCOEF; ++i) cc[i] = c[i];
+#pragma unroll
+        for (int a = 0; a < PPT; ++a) {
+          Model::step(x[a][0], z[a], cc);
+          if (ANTI) {
+            Real zm[NF];
+#pragma unroll
+            for (int j = 0; j < NF; ++j) zm[j] = -z[a][j];
+            Model::step(x[a][NPATH - 1], zm, cc);
+          }
         }
         if (MODE == MODE_PRICE) {
           if (P.need_extrema) {
 #pragma unroll
-            for (int a = 0; a < NPATH; ++a)
+            for (int a = 0; a < PPT; ++a)
 #pragma unroll
-              for (int j = 0; j < DIM; ++j) {
-                xmax[a][j] = x[a][j] > xmax[a][j] ? x[a][j] : xmax[a][j];
-                xmin[a][j] = x[a][j] < xmin[a][j] ? x[a][j] : xmin[a][j];
-              }
+              for (int h = 0; h < NPATH; ++h)
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) {
+                  xmax[a][h][j] = x[a][h][j] > xmax[a][h][j] ? x[a][h][j] : xmax[a][h][j];
+                  xmin[a][h][j] = x[a][h][j] < xmin[a][h][j] ? x[a][h][j] : xmin[a][h][j];
+                }
           }
         } else {
           const int slot = rec_tab[s + 1];
-          if (slot >= 0 && valid) {
+          if (slot >= 0) {
 #pragma unroll
-            for (int a = 0; a < NPATH; ++a)
+            for (int a = 0; a < PPT; ++a)
+              if (valid[a]) {
 #pragma unroll
-              for (int j = 0; j < DIM; ++j)
-                P.out[static_cast<int64_t>(local + a * P.anti_half) * P.stride_path +
-                      slot * P.stride_time + j * P.stride_dim] = x[a][j];
+                for (int h = 0; h < NPATH; ++h)
+#pragma unroll
+                  for (int j = 0; j < DIM; ++j)
+                    P.out[static_cast<int64_t>(local[a] + h * P.anti_half) * P.stride_path +
+                          slot * P.stride_time + j * P.stride_dim] = x[a][h][j];
+              }
           }
         }
       }
@@ -393,24 +479,27 @@ path_kernel(const KParams<typename Model::Real> P) {
       for (int q = 0; q < P.num_payoffs; ++q) {
         const PayoffK& d = P.pay[q];
         double sum = 0.0, sq = 0.0, bad = 0.0;
-        if (valid) {
 #pragma unroll
-          for (int a = 0; a < NPATH; ++a) {
-            double xf = 0.0, xa = 0.0, xi = 0.0;
+        for (int a = 0; a < PPT; ++a) {
+          if (valid[a]) {
 #pragma unroll
-            for (int j = 0; j < DIM; ++j) {
-              if (j == d.component) {
-                xf = static_cast<double>(x[a][j]);
-                xa = static_cast<double>(xmax[a][j]);
-                xi = static_cast<double>(xmin[a][j]);
+            for (int h = 0; h < NPATH; ++h) {
+              double xf = 0.0, xa = 0.0, xi = 0.0;
+#pragma unroll
+              for (int j = 0; j < DIM; ++j) {
+                if (j == d.component) {
+                  xf = static_cast<double>(x[a][h][j]);
+                  xa = static_cast<double>(xmax[a][h][j]);
+                  xi = static_cast<double>(xmin[a][h][j]);
+                }
               }
-            }
-            const double v = eval_payoff(d, xf, xa, xi);
-            if (isfinite(v)) {
-              sum += v;
-              sq += v * v;
-            } else {
-              bad += 1.0;
+              const double v = eval_payoff(d, xf, xa, xi);
+              if (isfinite(v)) {
+                sum += v;
+                sq += v * v;
+              } else {
+                bad += 1.0;
+              }
             }
           }
         }
@@ -451,18 +540,25 @@ size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool table
     off = (off + 15) & ~static_cast<size_t>(15);
     if (mode == MODE_PATHS) off += ((static_cast<size_t>(num_steps) + 1) * sizeof(int) + 15) & ~static_cast<size_t>(15);
   }
-  if (rngk == RNGK_SOBOL) off += kSobolTileDims * sizeof(uint32_t) + static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
+  if (rngk == RNGK_SOBOL) off += static_cast<size_t>(kMaxPPT) * kSobolTileDims * sizeof(uint32_t) + static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   off += static_cast<size_t>(kWarps) * TQF_MAX_PAYOFFS * 3 * sizeof(double);
   return off;
 }
 
 // Launches the right instantiation for (rng kind, antithetic, mode).
 template <class Model>
-int launch_path_kernel(int rngk, bool anti, int mode, int grid, size_t smem,
-                       const KParams<typename Model::Real>& P, cudaStream_t stream) {
+int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem,
+                       const KParams<typename Model::Real>& P, cudaStream_t stream,
+                       int* grid_out) {
 #define TQF_LAUNCH(RK, AN, MD)                                                         \
   do {                                                                                 \
     auto kern = path_kernel<Model, RK, AN, MD>;                                        \
+    constexpr int ppt = PathsPerThread<Model, RK>::value;                              \
+    const uint64_t num_super = (P.num_chunks + ppt - 1) / ppt;                         \
+    int grid = static_cast<int>(num_super < static_cast<uint64_t>(max_grid)            \
+                                    ? num_super : static_cast<uint64_t>(max_grid));    \
+    if (grid < 1) grid = 1;                                                            \
+    *grid_out = grid;                                                                  \
     if (smem > 48 * 1024)                                                              \
       TQF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        static_cast<int>(smem)));                       \

@@ -101,6 +101,24 @@ __global__ void sobol_fill_kernel(const uint32_t* __restrict__ v_table, int dim,
   }
 }
 
+__global__ void math_eval_kernel(int fn, const double* __restrict__ in, double* __restrict__ out,
+                                 uint64_t n) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    const double x = in[i];
+    double r, s, c;
+    switch (fn) {
+      case 0: r = fm::log_pos(x); break;
+      case 1: r = fm::sqrt_pos(x); break;
+      case 2: r = ndtri(x); break;
+      case 3: fm::sincos_2pi(x, &s, &c); r = s; break;
+      default: fm::sincos_2pi(x, &s, &c); r = c; break;
+    }
+    out[i] = r;
+  }
+}
+
 static int grid_for(uint64_t work_items, int block) {
   uint64_t blocks = (work_items + block - 1) / block;
   const uint64_t cap = static_cast<uint64_t>(kSMs) * 16;
@@ -290,6 +308,16 @@ int tqf_sobol_direction_numbers_from_file(const char* path, int dim, int32_t* ou
   std::fclose(f);
   return tqf_sobol_direction_numbers(a.data(), s.data(), m.data(), static_cast<int>(a.size()),
                                      dim, out);
+}
+
+int tqf_math_eval(int fn, const double* in_dev, double* out_dev, uint64_t n, void* stream) {
+  TQF_REQUIRE(fn >= 0 && fn <= 4, "fn must be in [0, 4]");
+  if (n == 0) return TQF_OK;
+  TQF_REQUIRE(in_dev && out_dev, "null argument");
+  math_eval_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      fn, in_dev, out_dev, n);
+  TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
 }
 
 int tqf_sobol_fill(const int32_t* direction_numbers, int dim, uint64_t num_results,

@@ -129,6 +129,8 @@ _SIGNATURES = {
     'tqf_plan_paths':
         (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                    C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    'tqf_math_eval':
+        (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     'tqf_measure_fp64_peak':
         (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
