@@ -146,9 +146,9 @@ def test_heston_coefficient_table():
   spec = engine.HestonEulerSpec(0.5, 0.04, volvol, 0.1)
   t = np.array([0.0, 0.25, 0.5, 0.75])
   tab = spec.coef_table(t, np.float64)
-  assert tab.shape == (3, 7)
-  np.testing.assert_allclose(tab[:, 0], 0.25)
-  np.testing.assert_allclose(tab[:, 4], [0.1, 0.1, 0.11])   # volvol(t_{i+1}) rho
+  assert tab.shape == (3, 6)
+  np.testing.assert_allclose(tab[:, 0], 0.5)
+  np.testing.assert_allclose(tab[:, 4], [0.05, 0.05, 0.055])   # volvol(t_{i+1}) rho sqrt_dt
 
 
 def test_no_gpu_fails_loudly():

@@ -130,6 +130,10 @@ __device__ __forceinline__ double sobol_uniform_f64(uint32_t x32) {
   // (2^52 + x32) * 2^-32 - 2^20, exact.
   return __hiloint2double(0x41300000, static_cast<int>(x32)) - 1048576.0;
 }
+// t = 2u - 1 = x32 / 2^31 - 1 in ONE exact subtraction: (2^21 + x32 2^-31) - (2^21 + 1).
+__device__ __forceinline__ double sobol_centered_f64(uint32_t x32) {
+  return __hiloint2double(0x41400000, static_cast<int>(x32)) - 2097153.0;
+}
 __device__ __forceinline__ float sobol_uniform_f32(uint32_t x32) {
   // The reference casts the integer point to float32 (round to nearest even)
   // and divides by a power of two: identical to rounding x32 and scaling.

@@ -26,30 +26,48 @@
 namespace tqf {
 namespace fm {
 
-// Two consecutive coefficients from the constant bank.  `volatile` keeps the
-// compiler from hoisting all of them out of the step loop into registers.
-__device__ __forceinline__ void ldc2(const double* c, double* a, double* b) {
-  asm volatile("ld.const.v2.f64 {%0, %1}, [%2];"
-               : "=d"(*a), "=d"(*b)
-               : "l"(__cvta_generic_to_constant(c)));
+// Where the polynomial coefficients are fetched from.
+//  * SmemTab: a per-CTA copy of TQF_COEF in shared memory, read with volatile
+//    LDS.128 (two coefficients per load).  Used by the path kernels: the loads
+//    land in ordinary registers right where the DFMAs need them, instead of
+//    being hoisted into the (too few) uniform registers and spilled.
+//  * ConstTab: the constant bank directly (fill kernels, test hook).
+struct SmemTab {
+  uint32_t base;  // shared-window address of the table
+  __device__ __forceinline__ explicit SmemTab(const double* table)
+      : base(static_cast<uint32_t>(__cvta_generic_to_shared(table))) {}
+  __device__ __forceinline__ void load2(int off, double* a, double* b) const {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(*a), "=d"(*b)
+                 : "r"(base + static_cast<uint32_t>(off) * 8u));
+  }
+};
+struct ConstTab {
+  __device__ __forceinline__ void load2(int off, double* a, double* b) const {
+    *a = TQF_COEF[off];
+    *b = TQF_COEF[off + 1];
+  }
+};
+// Copies TQF_COEF into shared memory (call before a __syncthreads()).
+__device__ __forceinline__ void fill_smem_coef(double* dst, int tid, int nthreads) {
+  for (int i = tid; i < TQF_COEF_COUNT; i += nthreads) dst[i] = TQF_COEF[i];
 }
 
-// p[k] = sum_i c[i] y[k]^(N-1-i)  (c highest order first, padded to even).
-template <int N, int K>
-__device__ __forceinline__ void horner_v(const double* c, const double (&y)[K],
-                                         double (&p)[K]) {
+// p[k] = sum_i c[OFF+i] y[k]^(N-1-i)  (highest order first, padded to even).
+template <int OFF, int N, int K, class Tab>
+__device__ __forceinline__ void horner_v(const Tab& tab, const double (&y)[K], double (&p)[K]) {
   double c0, c1;
-  ldc2(c, &c0, &c1);
+  tab.load2(OFF, &c0, &c1);
 #pragma unroll
   for (int k = 0; k < K; ++k) p[k] = fma(c0, y[k], c1);
 #pragma unroll
   for (int i = 2; i + 1 < N; i += 2) {
-    ldc2(c + i, &c0, &c1);
+    tab.load2(OFF + i, &c0, &c1);
 #pragma unroll
     for (int k = 0; k < K; ++k) p[k] = fma(fma(p[k], y[k], c0), y[k], c1);
   }
   if (N & 1) {
-    ldc2(c + N - 1, &c0, &c1);  // c1 is the zero pad
+    tab.load2(OFF + N - 1, &c0, &c1);  // c1 is the zero pad
 #pragma unroll
     for (int k = 0; k < K; ++k) p[k] = fma(p[k], y[k], c0);
   }
@@ -84,8 +102,8 @@ __device__ __forceinline__ double sqrt_pos(double v) {
 // handling: the callers' arguments are in [2^-60, 2]).
 //   a = 2^k m, m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1),
 //   log a = k ln2 + 2 s + s^3 R(s^2).
-template <int K>
-__device__ __forceinline__ void log_pos_v(const double (&a)[K], double (&out)[K]) {
+template <int K, class Tab>
+__device__ __forceinline__ void log_pos_v(const Tab& tab, const double (&a)[K], double (&out)[K]) {
   const double kLn2Hi = 6.93147180369123816490e-01;  // fdlibm split
   const double kLn2Lo = 1.90821492927058770002e-10;
   double s[K], z[K], kd[K], R[K];
@@ -100,7 +118,7 @@ __device__ __forceinline__ void log_pos_v(const double (&a)[K], double (&out)[K]
     s[k] = (m - 1.0) * rcp_pos(m + 1.0);
     z[k] = s[k] * s[k];
   }
-  horner_v<TQF_LOG_R_N, K>(TQF_LOG_R, z, R);
+  horner_v<TQF_LOG_R_OFF, TQF_LOG_R_N, K>(tab, z, R);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const double t = fma(s[k] * z[k], R[k], kd[k] * kLn2Lo);
@@ -108,45 +126,44 @@ __device__ __forceinline__ void log_pos_v(const double (&a)[K], double (&out)[K]
   }
 }
 
-// Inverse normal CDF of u = 1/2 + q (q exact), |q| < 1/2:
-//   sqrt(2) erfinv(2 q) = q * P(w),  w = -log(1 - 4 q^2)
+// Inverse normal CDF of u = (1 + t) / 2 (t = 2u - 1 exact), |t| < 1:
+//   sqrt(2) erfinv(t) = t * P(w),  w = -log(1 - t^2)
 // (the parametrisation of M. Giles, "Approximating the erfinv function", 2010,
 // with our own double-precision fits).  The central branch w < 6.25 covers
-// |q| < 0.49903, i.e. 99.8% of uniform draws; the tail branch is entered by a
+// |t| < 0.99806, i.e. 99.8% of uniform draws; the tail branch is entered by a
 // thread only when one of its K draws needs it.
-template <int K>
-__device__ __forceinline__ void ndtri_q_v(const double (&q)[K], double (&zout)[K]) {
+template <int K, class Tab>
+__device__ __forceinline__ void ndtri_t_v(const Tab& tab, const double (&t)[K], double (&zout)[K]) {
   double a[K], w[K], y[K], p[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) a[k] = fma(-4.0 * q[k], q[k], 1.0);
-  log_pos_v<K>(a, w);
+  for (int k = 0; k < K; ++k) a[k] = fma(-t[k], t[k], 1.0);
+  log_pos_v<K>(tab, a, w);
   bool tail = false;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    w[k] = -w[k];
-    y[k] = w[k] - TQF_NDTRI_C_MID;
-    tail = tail || (w[k] >= TQF_NDTRI_W0);
+    y[k] = -TQF_NDTRI_C_MID - w[k];   // w[k] holds log(a) = -w
+    tail = tail || (w[k] <= -TQF_NDTRI_W0);
   }
-  horner_v<TQF_NDTRI_C_N, K>(TQF_NDTRI_C, y, p);
+  horner_v<TQF_NDTRI_C_OFF, TQF_NDTRI_C_N, K>(tab, y, p);
   if (tail) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      if (w[k] >= TQF_NDTRI_W0) {
-        const double yt[1] = {sqrt_pos(w[k]) - TQF_NDTRI_T_MID};
+      if (w[k] <= -TQF_NDTRI_W0) {
+        const double yt[1] = {sqrt_pos(-w[k]) - TQF_NDTRI_T_MID};
         double pt[1];
-        horner_v<TQF_NDTRI_T_N, 1>(TQF_NDTRI_T, yt, pt);
+        horner_v<TQF_NDTRI_T_OFF, TQF_NDTRI_T_N, 1>(tab, yt, pt);
         p[k] = pt[0];
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < K; ++k) zout[k] = q[k] * p[k];
+  for (int k = 0; k < K; ++k) zout[k] = t[k] * p[k];
 }
 
 // sin(v[k]), cos(v[k]) for v in [0, 2 pi] (Box-Muller angle): Cody-Waite
 // reduction by pi/2 with an FMA pair, then the kernels on |f| <= pi/4.
-template <int K>
-__device__ __forceinline__ void sincos_2pi_v(const double (&v)[K], double (&sn)[K],
+template <int K, class Tab>
+__device__ __forceinline__ void sincos_2pi_v(const Tab& tab, const double (&v)[K], double (&sn)[K],
                                              double (&cs)[K]) {
   const double kTwoOverPi = 6.36619772367581382433e-01;
   const double kPio2Hi = 1.57079632679489655800e+00;
@@ -162,8 +179,8 @@ __device__ __forceinline__ void sincos_2pi_v(const double (&v)[K], double (&sn)[
     f[k] = fma(-jd, kPio2Lo, fma(-jd, kPio2Hi, v[k]));
     z[k] = f[k] * f[k];
   }
-  horner_v<TQF_SIN_P_N, K>(TQF_SIN_P, z, ps);
-  horner_v<TQF_COS_P_N, K>(TQF_COS_P, z, pc);
+  horner_v<TQF_SIN_P_OFF, TQF_SIN_P_N, K>(tab, z, ps);
+  horner_v<TQF_COS_P_OFF, TQF_COS_P_N, K>(tab, z, pc);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const double s = f[k] * ps[k];
@@ -177,23 +194,25 @@ __device__ __forceinline__ void sincos_2pi_v(const double (&v)[K], double (&sn)[
   }
 }
 
-// scalar conveniences (fill kernels, test hook)
+// scalar conveniences (fill kernels, test hook): coefficients straight from
+// the constant bank.
 __device__ __forceinline__ double log_pos(double a) {
   const double in[1] = {a};
   double out[1];
-  log_pos_v<1>(in, out);
+  log_pos_v<1>(ConstTab(), in, out);
   return out[0];
 }
+// ndtri(u) for u = 1/2 + q, q exact.
 __device__ __forceinline__ double ndtri_q(double q) {
-  const double in[1] = {q};
+  const double in[1] = {q + q};
   double out[1];
-  ndtri_q_v<1>(in, out);
+  ndtri_t_v<1>(ConstTab(), in, out);
   return out[0];
 }
 __device__ __forceinline__ void sincos_2pi(double v, double* sn, double* cs) {
   const double in[1] = {v};
   double s[1], c[1];
-  sincos_2pi_v<1>(in, s, c);
+  sincos_2pi_v<1>(ConstTab(), in, s, c);
   *sn = s[0];
   *cs = c[0];
 }

@@ -49,7 +49,7 @@ static bool model_info(int kind, ModelInfo* info) {
     case TQF_MODEL_AFFINE_1F: *info = {1, 1, 5}; return true;
     case TQF_MODEL_GBM_1F: *info = {1, 1, 4}; return true;
     case TQF_MODEL_LINEAR_1F: *info = {1, 1, 5}; return true;
-    case TQF_MODEL_HESTON_EULER: *info = {2, 2, 7}; return true;
+    case TQF_MODEL_HESTON_EULER: *info = {2, 2, 6}; return true;
     default: return false;
   }
 }
@@ -145,14 +145,22 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   KParams<Real> P;
   fill_common(plan, path_offset, path_count, &P);
   P.num_payoffs = num_payoffs;
+  int monitor = -1;
   for (int q = 0; q < num_payoffs; ++q) {
     const tqf_payoff_desc& d = payoffs[q];
     TQF_REQUIRE(d.kind >= TQF_PAYOFF_CALL && d.kind <= TQF_PAYOFF_IDENTITY,
                 "payoff kind not supported by this model");
     TQF_REQUIRE(d.component >= 0 && d.component < plan->info.dim, "payoff component out of range");
     P.pay[q] = PayoffK{d.kind, d.component, d.transform, 0, d.strike, d.barrier, d.scale};
-    if (d.kind >= TQF_PAYOFF_UP_OUT_CALL && d.kind <= TQF_PAYOFF_DOWN_OUT_CALL) P.need_extrema = 1;
+    if (d.kind >= TQF_PAYOFF_UP_OUT_CALL && d.kind <= TQF_PAYOFF_DOWN_OUT_CALL) {
+      TQF_REQUIRE(monitor < 0 || monitor == d.component,
+                  "all barrier payoffs of one call must watch the same state component");
+      monitor = d.component;
+      const bool up = d.kind == TQF_PAYOFF_UP_OUT_CALL || d.kind == TQF_PAYOFF_UP_OUT_PUT;
+      P.need_extrema |= up ? 1 : 2;
+    }
   }
+  P.monitor = monitor < 0 ? 0 : monitor;
   P.partials = plan->partials_dev;
   int grid = 1;
   const int rk = rng_kind(plan);

@@ -60,7 +60,8 @@ struct KParams {
   uint64_t chunk_base;       // first_index rounded down to a multiple of kBlock
   // MODE_PRICE
   int num_payoffs;
-  int need_extrema;
+  int need_extrema;          // bit 0: running max, bit 1: running min of `monitor`
+  int monitor;               // state component the barrier payoffs watch
   PayoffK pay[TQF_MAX_PAYOFFS];
   double* partials;          // device [gridDim.x][TQF_MAX_PAYOFFS][4]
   // MODE_PATHS
@@ -113,19 +114,25 @@ struct LinearModel1F {  // x' = A x + B + C z  (HW exact OU step, vector_hull_wh
 template <typename R>
 struct HestonEulerModel {  // heston/heston_model.py:143-173; state [X = log S, V]
   using Real = R;
-  static constexpr int DIM = 2, NF = 2, NCOEF = 7;
-  // c: dt, sqrt_dt, kappa, theta, volvol*rho, volvol*sqrt(1-rho^2), unused
+  static constexpr int DIM = 2, NF = 2, NCOEF = 6;
+  // c: sqrt_dt, -dt/2, dt*kappa, theta, volvol*rho*sqrt_dt, volvol*sqrt(1-rho^2)*sqrt_dt
+  // (per-step products formed once on the host).  Same update as _euler_step
+  // with the Heston closures,
+  //   X' = X + dt (-V/2) + sqrt|V| sqrt_dt z0
+  //   V' = V + dt kappa (theta - V) + volvol sqrt|V| sqrt_dt (rho z0 + sqrt(1-rho^2) z1),
+  // regrouped into 8 FMA-pipe operations + the square root.
   __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
                                               const Real (&c)[NCOEF]) {
     const Real var = x[1];
-    const Real vol = sqrt(fabs(var));
-    const Real dw0 = z[0] * c[1];
-    const Real dw1 = z[1] * c[1];
-    const Real dx = c[0] * (Real(-0.5) * var);
-    const Real dv = c[0] * (c[2] * (c[3] - var));
-    x[0] = (x[0] + dx) + vol * dw0;
-    x[1] = (var + dv) + ((c[4] * vol) * dw0 + (c[5] * vol) * dw1);
+    const Real vol = sqrt_abs(var);
+    x[0] = fma(vol, z[0] * c[0], fma(c[1], var, x[0]));
+    x[1] = fma(vol, fma(c[5], z[1], c[4] * z[0]), fma(c[2], c[3] - var, var));
   }
+  __device__ static __forceinline__ double sqrt_abs(double v) {
+    // |V| == 0 would make rsqrt infinite: nudge it (the addend is absorbed otherwise).
+    return fm::sqrt_pos(fabs(v) + 1e-300);  // absorbed unless V == 0
+  }
+  __device__ static __forceinline__ float sqrt_abs(float v) { return sqrtf(fabsf(v)); }
 };
 
 // ------------------------------------------------------- normal streams ---
@@ -140,7 +147,8 @@ struct PhiloxStreamV<double, PPT> {
   uint64_t group[PPT];
   double b0[PPT], b1[PPT];
   int pos;
-  __device__ __forceinline__ void refill(const PhiloxKey& key, const PhiloxCtr& ctr) {
+  __device__ __forceinline__ void refill(const PhiloxKey& key, const PhiloxCtr& ctr,
+                                         const fm::SmemTab& tab) {
     double u1[PPT], v1[PPT], lg[PPT], sn[PPT], cs[PPT];
 #pragma unroll
     for (int a = 0; a < PPT; ++a) {
@@ -150,8 +158,8 @@ struct PhiloxStreamV<double, PPT> {
       u1[a] = u < 1.0e-7 ? 1.0e-7 : u;
       v1[a] = 6.283185307179586476925286766559 * uint64_to_double(w.z, w.w);
     }
-    fm::log_pos_v<PPT>(u1, lg);
-    fm::sincos_2pi_v<PPT>(v1, sn, cs);
+    fm::log_pos_v<PPT>(tab, u1, lg);
+    fm::sincos_2pi_v<PPT>(tab, v1, sn, cs);
 #pragma unroll
     for (int a = 0; a < PPT; ++a) {
       const double r = fm::sqrt_pos(-2.0 * lg[a]);
@@ -160,16 +168,17 @@ struct PhiloxStreamV<double, PPT> {
     }
   }
   __device__ __forceinline__ void init(const PhiloxKey& key, const PhiloxCtr& ctr,
+                                       const fm::SmemTab& tab,
                                        const uint64_t (&first_element)[PPT]) {
 #pragma unroll
     for (int a = 0; a < PPT; ++a) group[a] = first_element[a] >> 1;
-    refill(key, ctr);
+    refill(key, ctr, tab);
     pos = static_cast<int>(first_element[0] & 1);
   }
   __device__ __forceinline__ void next(const PhiloxKey& key, const PhiloxCtr& ctr,
-                                       double (&z)[PPT]) {
+                                       const fm::SmemTab& tab, double (&z)[PPT]) {
     if (pos == 2) {
-      refill(key, ctr);
+      refill(key, ctr, tab);
       pos = 0;
     }
 #pragma unroll
@@ -193,6 +202,7 @@ struct PhiloxStreamV<float, PPT> {
     }
   }
   __device__ __forceinline__ void init(const PhiloxKey& key, const PhiloxCtr& ctr,
+                                       const fm::SmemTab&,
                                        const uint64_t (&first_element)[PPT]) {
 #pragma unroll
     for (int a = 0; a < PPT; ++a) group[a] = first_element[a] >> 2;
@@ -200,7 +210,7 @@ struct PhiloxStreamV<float, PPT> {
     pos = static_cast<int>(first_element[0] & 3);
   }
   __device__ __forceinline__ void next(const PhiloxKey& key, const PhiloxCtr& ctr,
-                                       float (&z)[PPT]) {
+                                       const fm::SmemTab&, float (&z)[PPT]) {
     if (pos == 4) {
       refill(key, ctr);
       pos = 0;
@@ -214,14 +224,16 @@ struct PhiloxStreamV<float, PPT> {
 
 // Inverse-CDF transform of K Sobol integer points.
 template <int K>
-__device__ __forceinline__ void sobol_normals(const uint32_t (&xb)[K], double (&z)[K]) {
-  double q[K];
+__device__ __forceinline__ void sobol_normals(const fm::SmemTab& tab, const uint32_t (&xb)[K],
+                                              double (&z)[K]) {
+  double t[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) q[k] = sobol_uniform_f64(xb[k]) - 0.5;
-  fm::ndtri_q_v<K>(q, z);
+  for (int k = 0; k < K; ++k) t[k] = sobol_centered_f64(xb[k]);
+  fm::ndtri_t_v<K>(tab, t, z);
 }
 template <int K>
-__device__ __forceinline__ void sobol_normals(const uint32_t (&xb)[K], float (&z)[K]) {
+__device__ __forceinline__ void sobol_normals(const fm::SmemTab&, const uint32_t (&xb)[K],
+                                              float (&z)[K]) {
 #pragma unroll
   for (int k = 0; k < K; ++k) z[k] = ndtri(sobol_uniform_f32(xb[k]));
 }
@@ -296,7 +308,10 @@ path_kernel(const KParams<typename Model::Real> P) {
   if (RNGK == RNGK_SOBOL) off += static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   double* s_acc = reinterpret_cast<double*>(smem_raw + off);
 
+  __shared__ __align__(16) double s_cst[TQF_COEF_COUNT];
   const int tid = threadIdx.x;
+  fm::fill_smem_coef(s_cst, tid, kBlock);
+  const fm::SmemTab tab(s_cst);
   const Real* coef_tab = P.coef;
   const int* rec_tab = P.record_slot;
   if (P.tables_in_smem) {
@@ -315,7 +330,10 @@ path_kernel(const KParams<typename Model::Real> P) {
   // Sobol: masks of this thread's low index bits (the same for all its paths).
   uint32_t lowmask[kLowBits];
 #pragma unroll
-  for (int b = 0; b < kLowBits; ++b) lowmask[b] = 0u - ((static_cast<uint32_t>(tid) >> b) & 1u);
+  for (int b = 0; b < kLowBits; ++b) {
+    lowmask[b] = 0u - ((static_cast<uint32_t>(tid) >> b) & 1u);
+    asm volatile("" : "+r"(lowmask[b]));  // keep in a register; do not rematerialise per draw
+  }
 
   constexpr int TILE_STEPS = (kSobolTileDims / NF) > 0 ? (kSobolTileDims / NF) : 1;
   const uint64_t stream_stride = static_cast<uint64_t>(P.num_steps_total) * NF;
@@ -334,7 +352,7 @@ path_kernel(const KParams<typename Model::Real> P) {
       first_element[a] = valid[a] ? (P.path_offset + local[a]) * stream_stride : 0;
     }
 
-    Real x[PPT][NPATH][DIM], xmax[PPT][NPATH][DIM], xmin[PPT][NPATH][DIM];
+    Real x[PPT][NPATH][DIM], xmax[PPT][NPATH], xmin[PPT][NPATH];
 #pragma unroll
     for (int a = 0; a < PPT; ++a)
 #pragma unroll
@@ -342,12 +360,14 @@ path_kernel(const KParams<typename Model::Real> P) {
 #pragma unroll
         for (int j = 0; j < DIM; ++j) {
           x[a][h][j] = P.x0[j];
-          xmax[a][h][j] = P.x0[j];
-          xmin[a][h][j] = P.x0[j];
+          if (j == 0 || j == P.monitor) {
+            xmax[a][h] = P.x0[j];
+            xmin[a][h] = P.x0[j];
+          }
         }
 
     PhiloxStreamV<Real, PPT> stream;
-    if (RNGK == RNGK_PHILOX) stream.init(P.key, P.ctr, first_element);
+    if (RNGK == RNGK_PHILOX) stream.init(P.key, P.ctr, tab, first_element);
 
     if (MODE == MODE_PATHS) {
       const int slot = rec_tab[0];
@@ -396,7 +416,7 @@ path_kernel(const KParams<typename Model::Real> P) {
 #pragma unroll
           for (int j = 0; j < NF; ++j) {
             Real zz[PPT];
-            stream.next(P.key, P.ctr, zz);
+            stream.next(P.key, P.ctr, tab, zz);
 #pragma unroll
             for (int a = 0; a < PPT; ++a) z[a][j] = zz[a];
           }
@@ -418,7 +438,7 @@ path_kernel(const KParams<typename Model::Real> P) {
             for (int a = 0; a < PPT; ++a) xb[a * NF + j] = lowx ^ s_high[a * kSobolTileDims + dd];
           }
           Real zz[PPT * NF];
-          sobol_normals<PPT * NF>(xb, zz);
+          sobol_normals<PPT * NF>(tab, xb, zz);
 #pragma unroll
           for (int a = 0; a < PPT; ++a)
 #pragma unroll
@@ -446,15 +466,17 @@ path_kernel(const KParams<typename Model::Real> P) {
         }
         if (MODE == MODE_PRICE) {
           if (P.need_extrema) {
+            // running extrema of the ONE monitored state component
 #pragma unroll
             for (int a = 0; a < PPT; ++a)
 #pragma unroll
-              for (int h = 0; h < NPATH; ++h)
+              for (int h = 0; h < NPATH; ++h) {
+                Real xm = x[a][h][0];
 #pragma unroll
-                for (int j = 0; j < DIM; ++j) {
-                  xmax[a][h][j] = x[a][h][j] > xmax[a][h][j] ? x[a][h][j] : xmax[a][h][j];
-                  xmin[a][h][j] = x[a][h][j] < xmin[a][h][j] ? x[a][h][j] : xmin[a][h][j];
-                }
+                for (int j = 1; j < DIM; ++j) xm = (j == P.monitor) ? x[a][h][j] : xm;
+                if (P.need_extrema & 1) xmax[a][h] = xm > xmax[a][h] ? xm : xmax[a][h];
+                if (P.need_extrema & 2) xmin[a][h] = xm < xmin[a][h] ? xm : xmin[a][h];
+              }
           }
         } else {
           const int slot = rec_tab[s + 1];
@@ -484,14 +506,12 @@ path_kernel(const KParams<typename Model::Real> P) {
           if (valid[a]) {
 #pragma unroll
             for (int h = 0; h < NPATH; ++h) {
-              double xf = 0.0, xa = 0.0, xi = 0.0;
+              double xf = 0.0;
+              const double xa = static_cast<double>(xmax[a][h]);
+              const double xi = static_cast<double>(xmin[a][h]);
 #pragma unroll
               for (int j = 0; j < DIM; ++j) {
-                if (j == d.component) {
-                  xf = static_cast<double>(x[a][h][j]);
-                  xa = static_cast<double>(xmax[a][h][j]);
-                  xi = static_cast<double>(xmin[a][h][j]);
-                }
+                if (j == d.component) xf = static_cast<double>(x[a][h][j]);
               }
               const double v = eval_payoff(d, xf, xa, xi);
               if (isfinite(v)) {

@@ -89,8 +89,12 @@ class LinearSpec1F(ModelSpec):
 
 
 class HestonEulerSpec(ModelSpec):
-  """Heston closures (`heston/heston_model.py:143-173`), state [log S, V]."""
-  kind, dim, num_factors, num_coef = _lib.MODEL_HESTON_EULER, 2, 2, 7
+  """Heston closures (`heston/heston_model.py:143-173`), state [log S, V].
+
+  Columns: sqrt_dt, -dt/2, dt kappa, theta, volvol rho sqrt_dt,
+  volvol sqrt(1 - rho^2) sqrt_dt -- the per-step products the kernel needs,
+  formed once here in `dtype` (parameters at t_{i+1})."""
+  kind, dim, num_factors, num_coef = _lib.MODEL_HESTON_EULER, 2, 2, 6
 
   def __init__(self, mean_reversion, theta, volvol, rho):
     self.mean_reversion, self.theta = mean_reversion, theta
@@ -98,14 +102,14 @@ class HestonEulerSpec(ModelSpec):
 
   def coef_table(self, all_times, dtype):
     t, dt, sq = self._dt_columns(all_times, dtype)
+    ty = np.dtype(dtype).type
     kappa = _eval_param(self.mean_reversion, t, dtype)
     theta = _eval_param(self.theta, t, dtype)
     volvol = _eval_param(self.volvol, t, dtype)
     rho = _eval_param(self.rho, t, dtype)
-    one = np.dtype(dtype).type(1)
-    c4 = (volvol * rho).astype(dtype)
-    c5 = (volvol * np.sqrt(one - rho**2).astype(dtype)).astype(dtype)
-    cols = [dt, sq, kappa, theta, c4, c5, np.zeros_like(dt)]
+    c4 = ((volvol * rho).astype(dtype) * sq).astype(dtype)
+    c5 = ((volvol * np.sqrt(ty(1) - rho**2).astype(dtype)).astype(dtype) * sq).astype(dtype)
+    cols = [sq, (ty(-0.5) * dt).astype(dtype), (dt * kappa).astype(dtype), theta, c4, c5]
     return np.stack(cols, -1).astype(np.float64)
 
 
