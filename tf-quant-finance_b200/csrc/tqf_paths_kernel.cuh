@@ -21,9 +21,9 @@ namespace tqf {
 
 constexpr int kBlock = 128;       // threads per CTA == Sobol indices per chunk
 constexpr int kLowBits = 7;       // log2(kBlock)
-constexpr int kSobolTileDims = 512;  // Sobol dimensions staged in smem at once
+constexpr int kSobolTileDims = 256;  // Sobol dimensions staged in smem at once
 constexpr int kWarps = kBlock / 32;
-constexpr int kMaxPPT = 4;      // most paths carried by one thread
+constexpr int kMaxPPT = 8;      // most paths carried by one thread
 
 enum { MODE_PRICE = 0, MODE_PATHS = 1 };
 enum { RNGK_PHILOX = 0, RNGK_SOBOL = 1, RNGK_DRAWS = 2 };
@@ -279,7 +279,7 @@ __device__ __forceinline__ double eval_payoff(const PayoffK& d, double x_final, 
 // CDFs (Sobol) or 4 Box-Muller pairs (Philox) are evaluated side by side.
 template <class Model, int RNGK>
 struct PathsPerThread {
-  static constexpr int value = (RNGK == RNGK_SOBOL) ? (Model::NF >= 4 ? 1 : 4 / Model::NF) : 4;
+  static constexpr int value = (RNGK == RNGK_SOBOL) ? (Model::NF >= 8 ? 1 : 8 / Model::NF) : 4;
 };
 
 template <class Model, int RNGK, bool ANTI, int MODE>
@@ -303,7 +303,7 @@ path_kernel(const KParams<typename Model::Real> P) {
   if (MODE == MODE_PATHS && P.tables_in_smem)
     off += ((static_cast<size_t>(P.num_steps) + 1) * sizeof(int) + 15) & ~static_cast<size_t>(15);
   uint32_t* s_high = reinterpret_cast<uint32_t*>(smem_raw + off);
-  if (RNGK == RNGK_SOBOL) off += static_cast<size_t>(kMaxPPT) * kSobolTileDims * sizeof(uint32_t);
+  if (RNGK == RNGK_SOBOL) off += static_cast<size_t>(PPT) * kSobolTileDims * sizeof(uint32_t);
   uint4* s_low = reinterpret_cast<uint4*>(smem_raw + off);
   if (RNGK == RNGK_SOBOL) off += static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   double* s_acc = reinterpret_cast<double*>(smem_raw + off);
@@ -553,27 +553,31 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
                                        int num_payoffs, double* __restrict__ sums);
 
 template <typename Real>
-size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool tables_in_smem) {
+size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool tables_in_smem,
+                        int ppt = kMaxPPT) {
   size_t off = 0;
   if (tables_in_smem) {
     off = static_cast<size_t>(num_steps) * ncoef * sizeof(Real);
     off = (off + 15) & ~static_cast<size_t>(15);
     if (mode == MODE_PATHS) off += ((static_cast<size_t>(num_steps) + 1) * sizeof(int) + 15) & ~static_cast<size_t>(15);
   }
-  if (rngk == RNGK_SOBOL) off += static_cast<size_t>(kMaxPPT) * kSobolTileDims * sizeof(uint32_t) + static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
+  if (rngk == RNGK_SOBOL) off += static_cast<size_t>(ppt) * kSobolTileDims * sizeof(uint32_t) + static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   off += static_cast<size_t>(kWarps) * TQF_MAX_PAYOFFS * 3 * sizeof(double);
   return off;
 }
 
 // Launches the right instantiation for (rng kind, antithetic, mode).
 template <class Model>
-int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem,
+int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_unused,
                        const KParams<typename Model::Real>& P, cudaStream_t stream,
                        int* grid_out) {
+  (void)smem_unused;
 #define TQF_LAUNCH(RK, AN, MD)                                                         \
   do {                                                                                 \
     auto kern = path_kernel<Model, RK, AN, MD>;                                        \
     constexpr int ppt = PathsPerThread<Model, RK>::value;                              \
+    const size_t smem = path_kernel_smem<typename Model::Real>(                        \
+        Model::NCOEF, P.num_steps, RK, MD, P.tables_in_smem != 0, ppt);                \
     const uint64_t num_super = (P.num_chunks + ppt - 1) / ppt;                         \
     int grid = static_cast<int>(num_super < static_cast<uint64_t>(max_grid)            \
                                     ? num_super : static_cast<uint64_t>(max_grid));    \

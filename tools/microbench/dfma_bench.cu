@@ -1,0 +1,68 @@
+// DFMA throughput microbenchmarks for the shapes the path kernel issues.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o dfma_bench dfma_bench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(128) horner_kernel(double* out, int iters, double seed) {
+  __shared__ __align__(16) double s_c[32];
+  if (threadIdx.x < 32) s_c[threadIdx.x] = 1.0 / (1.0 + threadIdx.x);
+  __syncthreads();
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(s_c));
+  double y[K], p[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { y[k] = seed + 1e-3 * (threadIdx.x + k); p[k] = y[k]; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 24; i += 2) {
+      double c0, c1;
+      if (MODE == 0) {           // coefficient pair from volatile LDS.128
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(base + i * 8u));
+      } else if (MODE == 1) {    // immediates folded by the compiler (uniform regs)
+        c0 = 0.123456789 + i; c1 = 0.987654321 - i;
+      } else {                   // c depends on registers only (no load)
+        c0 = y[0]; c1 = y[K - 1];
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) p[k] = fma(fma(p[k], y[k], c0), y[k], c1);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) s += p[k];
+  if (s == -1.2345) out[0] = s;
+}
+
+template <int K, int MODE>
+double run(int blocks_per_sm) {
+  double* out; cudaMalloc(&out, 8);
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = sms * blocks_per_sm, iters = 2000;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int r = 0; r < 4; ++r) {
+    cudaEventRecord(e0);
+    horner_kernel<K, MODE><<<grid, 128>>>(out, iters, 0.5);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double rate = double(grid) * 128 * iters * 24.0 * K / (ms * 1e-3);
+    if (r && rate > best) best = rate;
+  }
+  cudaFree(out);
+  return best;
+}
+
+int main() {
+  printf("K MODE blocks/SM  DFMA/s\n");
+  for (int b : {2, 4, 8}) {
+    printf("4 lds   %d %.3e\n", b, run<4, 0>(b));
+    printf("4 imm   %d %.3e\n", b, run<4, 1>(b));
+    printf("4 reg   %d %.3e\n", b, run<4, 2>(b));
+    printf("8 lds   %d %.3e\n", b, run<8, 0>(b));
+    printf("8 imm   %d %.3e\n", b, run<8, 1>(b));
+    printf("2 lds   %d %.3e\n", b, run<2, 0>(b));
+    printf("1 lds   %d %.3e\n", b, run<1, 0>(b));
+  }
+  return 0;
+}
