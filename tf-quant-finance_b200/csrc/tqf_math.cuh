@@ -37,9 +37,19 @@ struct SmemTab {
   __device__ __forceinline__ explicit SmemTab(const double* table)
       : base(static_cast<uint32_t>(__cvta_generic_to_shared(table))) {}
   __device__ __forceinline__ void load2(int off, double* a, double* b) const {
+#ifdef TQF_COEF_FROM_SMEM
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
                  : "=d"(*a), "=d"(*b)
                  : "r"(base + static_cast<uint32_t>(off) * 8u));
+#else
+    // Volatile constant-bank load: becomes LDCU.128 into uniform registers next
+    // to its DFMAs, which then take the coefficient as a UR operand -- measured
+    // 98-100% of the DFMA peak against 81-88% for LDS-fed register operands
+    // (tools/microbench/dfma_bench.cu).
+    asm volatile("ld.const.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(*a), "=d"(*b)
+                 : "l"(__cvta_generic_to_constant(TQF_COEF + off)));
+#endif
   }
 };
 struct ConstTab {
@@ -53,24 +63,134 @@ __device__ __forceinline__ void fill_smem_coef(double* dst, int tid, int nthread
   for (int i = tid; i < TQF_COEF_COUNT; i += nthreads) dst[i] = TQF_COEF[i];
 }
 
-// p[k] = sum_i c[OFF+i] y[k]^(N-1-i)  (highest order first, padded to even).
-template <int OFF, int N, int K, class Tab>
-__device__ __forceinline__ void horner_v(const Tab& tab, const double (&y)[K], double (&p)[K]) {
-  double c0, c1;
-  tab.load2(OFF, &c0, &c1);
+// ---- Horner steps as single asm statements --------------------------------
+// One `asm volatile` holds the coefficient-pair load and the K fused
+// multiply-adds that consume it.  Volatile statements keep their order, so the
+// K chains advance in lock step (K independent DFMAs between dependent ones)
+// and the coefficient is fetched by LDCU into a uniform register that the
+// DFMAs read as a UR operand -- the only shape that reaches the FP64 peak
+// (tools/microbench/dfma_bench.cu: 98-100% vs 81-90% for register operands).
+#define TQF_CADDR(off) "l"(__cvta_generic_to_constant(TQF_COEF + (off)))
+
+template <int K>
+struct HornerAsm;
+
+template <>
+struct HornerAsm<8> {
+  // p = c0 * y + c1
+  static __device__ __forceinline__ void first(int off, const double (&y)[8], double (&p)[8]) {
+    asm volatile(
+        "{\n\t.reg .f64 c0, c1;\n\t"
+        "ld.const.v2.f64 {c0, c1}, [%16];\n\t"
+        "fma.rn.f64 %0, c0, %8, c1;\n\tfma.rn.f64 %1, c0, %9, c1;\n\t"
+        "fma.rn.f64 %2, c0, %10, c1;\n\tfma.rn.f64 %3, c0, %11, c1;\n\t"
+        "fma.rn.f64 %4, c0, %12, c1;\n\tfma.rn.f64 %5, c0, %13, c1;\n\t"
+        "fma.rn.f64 %6, c0, %14, c1;\n\tfma.rn.f64 %7, c0, %15, c1;\n\t}"
+        : "=d"(p[0]), "=d"(p[1]), "=d"(p[2]), "=d"(p[3]), "=d"(p[4]), "=d"(p[5]), "=d"(p[6]),
+          "=d"(p[7])
+        : "d"(y[0]), "d"(y[1]), "d"(y[2]), "d"(y[3]), "d"(y[4]), "d"(y[5]), "d"(y[6]), "d"(y[7]),
+          TQF_CADDR(off));
+  }
+  // p = (p * y + c0) * y + c1
+  static __device__ __forceinline__ void pair(int off, const double (&y)[8], double (&p)[8]) {
+    asm volatile(
+        "{\n\t.reg .f64 c0, c1;\n\t"
+        "ld.const.v2.f64 {c0, c1}, [%16];\n\t"
+        "fma.rn.f64 %0, %0, %8, c0;\n\tfma.rn.f64 %1, %1, %9, c0;\n\t"
+        "fma.rn.f64 %2, %2, %10, c0;\n\tfma.rn.f64 %3, %3, %11, c0;\n\t"
+        "fma.rn.f64 %4, %4, %12, c0;\n\tfma.rn.f64 %5, %5, %13, c0;\n\t"
+        "fma.rn.f64 %6, %6, %14, c0;\n\tfma.rn.f64 %7, %7, %15, c0;\n\t"
+        "fma.rn.f64 %0, %0, %8, c1;\n\tfma.rn.f64 %1, %1, %9, c1;\n\t"
+        "fma.rn.f64 %2, %2, %10, c1;\n\tfma.rn.f64 %3, %3, %11, c1;\n\t"
+        "fma.rn.f64 %4, %4, %12, c1;\n\tfma.rn.f64 %5, %5, %13, c1;\n\t"
+        "fma.rn.f64 %6, %6, %14, c1;\n\tfma.rn.f64 %7, %7, %15, c1;\n\t}"
+        : "+d"(p[0]), "+d"(p[1]), "+d"(p[2]), "+d"(p[3]), "+d"(p[4]), "+d"(p[5]), "+d"(p[6]),
+          "+d"(p[7])
+        : "d"(y[0]), "d"(y[1]), "d"(y[2]), "d"(y[3]), "d"(y[4]), "d"(y[5]), "d"(y[6]), "d"(y[7]),
+          TQF_CADDR(off));
+  }
+  // p = p * y + c0
+  static __device__ __forceinline__ void single(int off, const double (&y)[8], double (&p)[8]) {
+    asm volatile(
+        "{\n\t.reg .f64 c0, c1;\n\t"
+        "ld.const.v2.f64 {c0, c1}, [%16];\n\t"
+        "fma.rn.f64 %0, %0, %8, c0;\n\tfma.rn.f64 %1, %1, %9, c0;\n\t"
+        "fma.rn.f64 %2, %2, %10, c0;\n\tfma.rn.f64 %3, %3, %11, c0;\n\t"
+        "fma.rn.f64 %4, %4, %12, c0;\n\tfma.rn.f64 %5, %5, %13, c0;\n\t"
+        "fma.rn.f64 %6, %6, %14, c0;\n\tfma.rn.f64 %7, %7, %15, c0;\n\t}"
+        : "+d"(p[0]), "+d"(p[1]), "+d"(p[2]), "+d"(p[3]), "+d"(p[4]), "+d"(p[5]), "+d"(p[6]),
+          "+d"(p[7])
+        : "d"(y[0]), "d"(y[1]), "d"(y[2]), "d"(y[3]), "d"(y[4]), "d"(y[5]), "d"(y[6]), "d"(y[7]),
+          TQF_CADDR(off));
+  }
+};
+
+template <>
+struct HornerAsm<4> {
+  static __device__ __forceinline__ void first(int off, const double (&y)[4], double (&p)[4]) {
+    asm volatile(
+        "{\n\t.reg .f64 c0, c1;\n\t"
+        "ld.const.v2.f64 {c0, c1}, [%8];\n\t"
+        "fma.rn.f64 %0, c0, %4, c1;\n\tfma.rn.f64 %1, c0, %5, c1;\n\t"
+        "fma.rn.f64 %2, c0, %6, c1;\n\tfma.rn.f64 %3, c0, %7, c1;\n\t}"
+        : "=d"(p[0]), "=d"(p[1]), "=d"(p[2]), "=d"(p[3])
+        : "d"(y[0]), "d"(y[1]), "d"(y[2]), "d"(y[3]), TQF_CADDR(off));
+  }
+  static __device__ __forceinline__ void pair(int off, const double (&y)[4], double (&p)[4]) {
+    asm volatile(
+        "{\n\t.reg .f64 c0, c1;\n\t"
+        "ld.const.v2.f64 {c0, c1}, [%8];\n\t"
+        "fma.rn.f64 %0, %0, %4, c0;\n\tfma.rn.f64 %1, %1, %5, c0;\n\t"
+        "fma.rn.f64 %2, %2, %6, c0;\n\tfma.rn.f64 %3, %3, %7, c0;\n\t"
+        "fma.rn.f64 %0, %0, %4, c1;\n\tfma.rn.f64 %1, %1, %5, c1;\n\t"
+        "fma.rn.f64 %2, %2, %6, c1;\n\tfma.rn.f64 %3, %3, %7, c1;\n\t}"
+        : "+d"(p[0]), "+d"(p[1]), "+d"(p[2]), "+d"(p[3])
+        : "d"(y[0]), "d"(y[1]), "d"(y[2]), "d"(y[3]), TQF_CADDR(off));
+  }
+  static __device__ __forceinline__ void single(int off, const double (&y)[4], double (&p)[4]) {
+    asm volatile(
+        "{\n\t.reg .f64 c0, c1;\n\t"
+        "ld.const.v2.f64 {c0, c1}, [%8];\n\t"
+        "fma.rn.f64 %0, %0, %4, c0;\n\tfma.rn.f64 %1, %1, %5, c0;\n\t"
+        "fma.rn.f64 %2, %2, %6, c0;\n\tfma.rn.f64 %3, %3, %7, c0;\n\t}"
+        : "+d"(p[0]), "+d"(p[1]), "+d"(p[2]), "+d"(p[3])
+        : "d"(y[0]), "d"(y[1]), "d"(y[2]), "d"(y[3]), TQF_CADDR(off));
+  }
+};
+
+// Generic K (1, 2, ...): plain C++ with the same volatile coefficient loads.
+template <int K>
+struct HornerAsm {
+  static __device__ __forceinline__ void ld(int off, double* c0, double* c1) {
+    asm volatile("ld.const.v2.f64 {%0, %1}, [%2];" : "=d"(*c0), "=d"(*c1) : TQF_CADDR(off));
+  }
+  static __device__ __forceinline__ void first(int off, const double (&y)[K], double (&p)[K]) {
+    double c0, c1;
+    ld(off, &c0, &c1);
 #pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma(c0, y[k], c1);
-#pragma unroll
-  for (int i = 2; i + 1 < N; i += 2) {
-    tab.load2(OFF + i, &c0, &c1);
+    for (int k = 0; k < K; ++k) p[k] = fma(c0, y[k], c1);
+  }
+  static __device__ __forceinline__ void pair(int off, const double (&y)[K], double (&p)[K]) {
+    double c0, c1;
+    ld(off, &c0, &c1);
 #pragma unroll
     for (int k = 0; k < K; ++k) p[k] = fma(fma(p[k], y[k], c0), y[k], c1);
   }
-  if (N & 1) {
-    tab.load2(OFF + N - 1, &c0, &c1);  // c1 is the zero pad
+  static __device__ __forceinline__ void single(int off, const double (&y)[K], double (&p)[K]) {
+    double c0, c1;
+    ld(off, &c0, &c1);
 #pragma unroll
     for (int k = 0; k < K; ++k) p[k] = fma(p[k], y[k], c0);
   }
+};
+
+// p[k] = sum_i c[OFF+i] y[k]^(N-1-i)  (highest order first, padded to even).
+template <int OFF, int N, int K, class Tab>
+__device__ __forceinline__ void horner_v(const Tab&, const double (&y)[K], double (&p)[K]) {
+  HornerAsm<K>::first(OFF, y, p);
+#pragma unroll
+  for (int i = 2; i + 1 < N; i += 2) HornerAsm<K>::pair(OFF + i, y, p);
+  if (N & 1) HornerAsm<K>::single(OFF + N - 1, y, p);
 }
 
 // 1/d, d normal and positive: MUFU.RCP64H (2^-23) + two Newton steps.

@@ -4,6 +4,35 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+__constant__ __align__(16) double g_c[32] = {1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32};
+
+// MODE 3: LDS.128 double-buffered one pair ahead.
+template <int K>
+__global__ void __launch_bounds__(128) horner_prefetch_kernel(double* out, int iters, double seed) {
+  __shared__ __align__(16) double s_c[32];
+  if (threadIdx.x < 32) s_c[threadIdx.x] = 1.0 / (1.0 + threadIdx.x);
+  __syncthreads();
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(s_c));
+  double y[K], p[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { y[k] = seed + 1e-3 * (threadIdx.x + k); p[k] = y[k]; }
+  for (int it = 0; it < iters; ++it) {
+    double c0, c1, n0, n1;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(base));
+#pragma unroll
+    for (int i = 0; i < 24; i += 2) {
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(n0), "=d"(n1) : "r"(base + ((i + 2) % 24) * 8u));
+#pragma unroll
+      for (int k = 0; k < K; ++k) p[k] = fma(fma(p[k], y[k], c0), y[k], c1);
+      c0 = n0; c1 = n1;
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) s += p[k];
+  if (s == -1.2345) out[0] = s;
+}
+
 template <int K, int MODE>
 __global__ void __launch_bounds__(128) horner_kernel(double* out, int iters, double seed) {
   __shared__ __align__(16) double s_c[32];
@@ -21,8 +50,12 @@ __global__ void __launch_bounds__(128) horner_kernel(double* out, int iters, dou
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(base + i * 8u));
       } else if (MODE == 1) {    // immediates folded by the compiler (uniform regs)
         c0 = 0.123456789 + i; c1 = 0.987654321 - i;
-      } else {                   // c depends on registers only (no load)
+      } else if (MODE == 2) {    // c depends on registers only (no load)
         c0 = y[0]; c1 = y[K - 1];
+      } else if (MODE == 4) {    // volatile constant-bank load
+        asm volatile("ld.const.v2.f64 {%0, %1}, [%2];" : "=d"(c0), "=d"(c1) : "l"(__cvta_generic_to_constant(g_c + i)));
+      } else {
+        c0 = 0; c1 = 0;
       }
 #pragma unroll
       for (int k = 0; k < K; ++k) p[k] = fma(fma(p[k], y[k], c0), y[k], c1);
@@ -43,7 +76,8 @@ double run(int blocks_per_sm) {
   double best = 0;
   for (int r = 0; r < 4; ++r) {
     cudaEventRecord(e0);
-    horner_kernel<K, MODE><<<grid, 128>>>(out, iters, 0.5);
+    if (MODE == 3) horner_prefetch_kernel<K><<<grid, 128>>>(out, iters, 0.5);
+    else horner_kernel<K, MODE><<<grid, 128>>>(out, iters, 0.5);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     double rate = double(grid) * 128 * iters * 24.0 * K / (ms * 1e-3);
@@ -55,7 +89,11 @@ double run(int blocks_per_sm) {
 
 int main() {
   printf("K MODE blocks/SM  DFMA/s\n");
-  for (int b : {2, 4, 8}) {
+  for (int b : {4}) {
+    printf("8 pref  %d %.3e\n", b, run<8, 3>(b));
+    printf("4 pref  %d %.3e\n", b, run<4, 3>(b));
+    printf("8 ldc   %d %.3e\n", b, run<8, 4>(b));
+    printf("4 ldc   %d %.3e\n", b, run<4, 4>(b));
     printf("4 lds   %d %.3e\n", b, run<4, 0>(b));
     printf("4 imm   %d %.3e\n", b, run<4, 1>(b));
     printf("4 reg   %d %.3e\n", b, run<4, 2>(b));
