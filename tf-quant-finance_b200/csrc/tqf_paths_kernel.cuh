@@ -19,6 +19,9 @@
 
 namespace tqf {
 
+#ifndef TQF_MIN_BLOCKS
+#define TQF_MIN_BLOCKS 3
+#endif
 constexpr int kBlock = 128;       // threads per CTA == Sobol indices per chunk
 constexpr int kLowBits = 7;       // log2(kBlock)
 constexpr int kSobolTileDims = 256;  // Sobol dimensions staged in smem at once
@@ -283,7 +286,7 @@ struct PathsPerThread {
 };
 
 template <class Model, int RNGK, bool ANTI, int MODE>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, TQF_MIN_BLOCKS)
 path_kernel(const KParams<typename Model::Real> P) {
   using Real = typename Model::Real;
   constexpr int DIM = Model::DIM, NF = Model::NF, NCOEF = Model::NCOEF;
