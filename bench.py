@@ -40,7 +40,7 @@ WORKLOADS = {
                paths=100_000, steps=100, dtype='f64'),
     'c2': dict(name='C2 Heston Euler, 10M paths x 252 steps, fp64, Sobol, European + up-and-out call',
                paths=10_000_000, steps=252, dtype='f64'),
-    'c3': dict(name='C3 Hull-White 1F (Euler, affine) 50M paths x 360 steps, fp64, Philox stateless seed [4,2], call on r_T',
+    'c3': dict(name='C3 Hull-White 1F payer swaption (exact OU step + discount integral), 50M paths x 360 steps, fp64, Philox stateless seed [4,2]',
                paths=50_000_000, steps=360, dtype='f64'),
 }
 
@@ -79,18 +79,31 @@ def make_workload(name, num_paths=None):
     payoffs = [engine.european_call(k, log_state=True, scale=np.exp(-r))
                for k in (600.0, 650.0, 680.0)]
   elif name == 'c3':
-    # Hull-White 1F short rate in Euler form with a flat 1% curve
-    # (vector_hull_white.py:292-306): drift = k f + s^2/(2k)(1-e^{-2kt}) - k x.
-    a, s, f0 = 0.03, 0.02, 0.01
-    d, v = closures.affine_closures(
-        lambda t: a * f0 + s * s / (2 * a) * (1 - np.exp(-2 * a * t)), -a, s)
-    spec = closures.resolve_spec(d, v)
-    times = np.array([1.0])
-    all_times, mask, _ = utils.prepare_grid(times=times, time_step=np.float64(1.0 / 360),
-                                            dtype=np.float64)
-    x0 = np.array([f0])
+    # swaption_test.py:30-44, 81-125 scaled up: 1y x 1y payer swaption, quarterly
+    # payments, a = 0.03, sigma = 0.02, flat 1% curve, time_step 1/360.
+    from tff_b200.models.hull_white import one_factor
+    from tff_b200.models.hull_white import swaption as swp
+    model = one_factor.HullWhiteModel1F(0.03, 0.02, lambda t: 0.01 + 0 * t,
+                                        dtype=np.float64)
+    ts = np.float64(1.0 / 360)
+    sim_times = np.sort(np.concatenate(
+        [[1.0], utils._tf_range(ts, 1.0, ts, np.float64)]), kind='stable')
+    all_times, mask, idx = model._prepare_grid(sim_times, None)
+    dts = np.concatenate([[0.0], sim_times[1:] - sim_times[:-1]])
+    w = np.zeros(all_times.shape[0] - 1)
+    for j, i in enumerate(idx):
+      if i >= 1:
+        w[i - 1] += dts[j]
+    spec = one_factor.HullWhite1FSpec(model._tables, model._fwd, w)
+    x0 = np.zeros(2)
     rng = dict(random_type=rt.STATELESS, seed=[4, 2], skip=0)
-    payoffs = [engine.european_call(0.01, log_state=False)]
+    pay = np.array([1.25, 1.5, 1.75, 2.0])
+    e_idx = idx[np.searchsorted(sim_times, 1.0, side='left')]
+    payoffs = [swp._RawPayoff(swp._swaption_desc(
+        model, all_times, e_idx, 1.0, pay, 0.011 * np.ones(4), 0.25 * np.ones(4),
+        True, 100.0))]
+    steps = int(e_idx)
+    return spec, all_times, x0, rng, payoffs, n, steps
   else:
     raise ValueError(name)
   steps, _ = engine.record_plan(mask, 1)
@@ -157,14 +170,15 @@ def _oracle_chunk(args):
         dtype=np.float64)
     return float(np.maximum(np.exp(paths[:, 0, 0]) - 650.0, 0).sum()), 100
   if name == 'c3':
-    a, s, f0 = 0.03, 0.02, 0.01
-    paths = oeuler.sample(
-        1, lambda t, x: a * f0 + s * s / (2 * a) * (1 - np.exp(-2 * a * t)) - a * x,
-        lambda t, x: s * np.ones(x.shape + (1,)), [1.0], time_step=1.0 / 360,
-        num_samples=count, initial_state=np.array([f0]),
+    from oracle import hull_white as ohw
+    price, payoff = ohw.swaption_price_mc(
+        expiries=np.array(1.0), fixed_leg_payment_times=np.array([1.25, 1.5, 1.75, 2.0]),
+        fixed_leg_daycount_fractions=0.25 * np.ones(4),
+        fixed_leg_coupon=0.011 * np.ones(4), reference_rate_fn=lambda t: 0.01 + 0 * t,
+        mean_reversion=0.03, volatility=0.02, notional=100., num_samples=count,
         random_type=odraws.RandomType.STATELESS, seed=[4, 2 + skip],
-        dtype=np.float64)
-    return float(np.maximum(paths[:, 0, 0] - 0.01, 0).sum()), 360
+        time_step=1.0 / 360, dtype=np.float64, return_payoffs=True)
+    return float(payoff.sum()), 360
   raise ValueError(name)
 
 

@@ -51,7 +51,8 @@ extern "C" {
 #define TQF_MODEL_HESTON_EULER 3  /* heston/heston_model.py:143-173          */
 #define TQF_MODEL_HESTON_QE 4     /* heston/heston_model.py:322-572          */
 #define TQF_MODEL_MVGBM 5         /* multivariate_geometric_brownian_motion  */
-#define TQF_MODEL_LINEAR_1F 6     /* x' = A x + B + C z (HW exact OU step)   */
+#define TQF_MODEL_LINEAR_1F 6     /* x' = A x + B + C z                      */
+#define TQF_MODEL_HW1F 7          /* HW exact OU step + short-rate integral  */
 
 /* payoff kinds (reduced in-kernel; callers: e.g. hull_white/swaption.py:310) */
 #define TQF_PAYOFF_CALL 1          /* max(f(X_T) - K, 0)                    */
@@ -172,15 +173,21 @@ typedef struct tqf_payoff_desc {
   double strike;
   double barrier;
   double scale;       /* multiplies the payoff (discount factor, notional)  */
-  /* TQF_PAYOFF_HW_SWAPTION (hjm/swaption_util.py:28-170 + swaption.py:300) */
-  int32_t expiry_step;    /* payoff evaluated on the state after this step  */
+  /* Every payoff is evaluated on the state after `expiry_step` steps
+   * (0 = after the last step of the plan).                                 */
+  int32_t expiry_step;
+  /* TQF_PAYOFF_HW_SWAPTION (hjm/swaption_util.py:28-170 + swaption.py:300):
+   *   P(t_e, T_j) = exp(pay_k[j] - pay_g[j] x),  x = r - f(0, t_e),
+   *   payoff = scale max(+-exp(-I) (1 - sum_j pay_coef[j] P(t_e, T_j)), 0),
+   * I = the path integral of the short rate carried by TQF_MODEL_HW1F.     */
   int32_t num_payments;
   int32_t is_payer;
   int32_t reserved2;
-  double hw_y;            /* y(t_expiry) (vector_hull_white.py:857-874)     */
-  double hw_fwd;          /* f(0, t_expiry)                                 */
+  double reserved3;
+  double reserved4;
   double pay_g[TQF_MAX_SWAPTION_PAYMENTS];     /* G(tau_j)=(1-e^{-k tau})/k */
-  double pay_p0[TQF_MAX_SWAPTION_PAYMENTS];    /* P0(T_j)/P0(t_expiry)      */
+  /* ln(P0(T_j)/P0(t_e)) - y(t_e) G_j^2 / 2 (vector_hull_white.py:783-814)  */
+  double pay_k[TQF_MAX_SWAPTION_PAYMENTS];
   double pay_coef[TQF_MAX_SWAPTION_PAYMENTS];  /* coupon*tau_j (+1 on last) */
 } tqf_payoff_desc;
 

@@ -158,3 +158,28 @@ def test_no_gpu_fails_loudly():
   import tff_b200 as tff
   with pytest.raises(_lib.TqfError):
     tff.math.random.stateless_normal([4], [1, 2], np.float64)
+
+
+def test_hw_bond_price_kat_host():
+  # models/hull_white/hull_white_test.py:465-485 through the product's host code
+  import tff_b200 as tff
+  m = tff.models.HullWhiteModel1F(0.1, 0.01, lambda t: 0.01 + 0 * t, dtype=np.float64)
+  got = m.discount_bond_price([[0.011], [0.01]], [1.0, 2.0], [2.0, 3.5])
+  np.testing.assert_allclose(got[:, 0], [0.98906753, 0.98495442], atol=5e-9)
+
+
+def test_hw_exact_tables_match_oracle():
+  from oracle import hull_white as ohw
+  from oracle import models as omodels
+  from tff_b200.models.hull_white import _exact
+  vol = piecewise.PiecewiseConstantFunc([0.1, 0.7], [0.01, 0.02, 0.015], dtype=np.float64)
+  ovol = omodels.PiecewiseConstantFunc([0.1, 0.7], [0.01, 0.02, 0.015], dtype=np.float64)
+  tab = _exact.ExactTables(0.1, vol, np.float64)
+  om = ohw.HullWhiteModel1F(0.1, ovol, lambda t: 0.01 + 0 * t)
+  t = np.array([0.0, 0.05, 0.1, 0.3, 0.7, 0.7, 1.0, 2.5])
+  np.testing.assert_array_equal(tab.conditional_mean_x(t), om.conditional_mean_x(t))
+  np.testing.assert_array_equal(tab.conditional_variance_x(t), om.conditional_variance_x(t))
+  np.testing.assert_array_equal(tab.y_t(t), om.compute_yt(t))
+  fwd, fwd_grad = _exact.forward_rate_fns(lambda t: 0.01 + 0.002 * t, np.float64)
+  np.testing.assert_allclose(fwd(np.array([0.0, 1.0])), [0.01, 0.014], rtol=1e-14)
+  np.testing.assert_allclose(fwd_grad(np.array([0.0, 1.0])), [0.004, 0.004], rtol=1e-9)

@@ -188,3 +188,49 @@ def test_antithetic_pairing():
   assert d.shape == (3, 10, 2)
   np.testing.assert_array_equal(d[:, :5], -d[:, 5:])
   np.testing.assert_array_equal(d[1, 3], z[3].reshape(3, 2)[1])
+
+
+# ----------------------------------------------------------- Hull-White ----
+def _flat_rate(t):
+  return 0.01 + 0 * t
+
+
+def test_hw_discount_bond_price_kat():
+  # models/hull_white/hull_white_test.py:465-485 (atol 1e-12 there)
+  from oracle import hull_white
+  m = hull_white.HullWhiteModel1F(0.1, 0.01, _flat_rate, np.float64)
+  got = m.discount_bond_price([[0.011], [0.01]], [1.0, 2.0], [2.0, 3.5])
+  np.testing.assert_allclose(got[:, 0], [0.98906753, 0.98495442], atol=5e-9)
+
+
+def test_hw_exact_moments():
+  # models/hull_white/hull_white_test.py:42-58, 100-131 (Brigo-Mercurio)
+  from oracle import hull_white
+  from oracle import models as omodels
+  a, sigma = 0.1, 0.01
+  vol = omodels.PiecewiseConstantFunc([0.1, 2.0], 3 * [sigma], dtype=np.float64)
+  m = hull_white.HullWhiteModel1F(a, vol, _flat_rate, np.float64)
+  paths = m.sample_paths([0.1, 0.5, 1.0], 50000, draws.RandomType.SOBOL,
+                         skip=1000000)
+  assert paths.shape == (50000, 3, 1)
+  x = paths[:, -1, 0]
+  true_mean = (0.01 + (sigma**2 / 2 / a**2) * (1 - np.exp(-a))**2)
+  true_var = sigma**2 / 2 / a * (1 - np.exp(-2 * a))
+  np.testing.assert_allclose(x.mean(), true_mean, rtol=1e-4, atol=1e-4)
+  np.testing.assert_allclose(x.var(), true_var, rtol=1e-4, atol=1e-4)
+
+
+def test_hw_swaption_mc_kat():
+  # models/hull_white/swaption_test.py:85-125: analytic 0.71632434, the
+  # reference's own MC tolerance is 1e-3 with 500k STATELESS_ANTITHETIC paths.
+  from oracle import hull_white
+  price = hull_white.swaption_price_mc(
+      expiries=np.array(1.0),
+      fixed_leg_payment_times=np.array([1.25, 1.5, 1.75, 2.0]),
+      fixed_leg_daycount_fractions=0.25 * np.ones(4),
+      fixed_leg_coupon=0.011 * np.ones(4), reference_rate_fn=_flat_rate,
+      notional=100., mean_reversion=0.03, volatility=0.02, num_samples=500000,
+      time_step=0.1, random_type=draws.RandomType.STATELESS_ANTITHETIC,
+      seed=[4, 2], dtype=np.float64)
+  assert price.shape == ()
+  np.testing.assert_allclose(price, 0.71632434, rtol=1e-3, atol=1e-3)

@@ -1,0 +1,11 @@
+// Explicit instantiations of the fused path kernel for HullWhite1FModel.
+#include "tqf_paths_kernel.cuh"
+
+namespace tqf {
+template int launch_path_kernel<HullWhite1FModel<double>>(int, bool, int, int, size_t,
+                                                          const KParams<double>&, cudaStream_t,
+                                                          int*);
+template int launch_path_kernel<HullWhite1FModel<float>>(int, bool, int, int, size_t,
+                                                         const KParams<float>&, cudaStream_t,
+                                                         int*);
+}  // namespace tqf

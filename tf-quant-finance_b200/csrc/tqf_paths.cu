@@ -21,6 +21,7 @@ TQF_EXTERN_MODEL(AffineModel1F)
 TQF_EXTERN_MODEL(GbmModel1F)
 TQF_EXTERN_MODEL(LinearModel1F)
 TQF_EXTERN_MODEL(HestonEulerModel)
+TQF_EXTERN_MODEL(HullWhite1FModel)
 #undef TQF_EXTERN_MODEL
 
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_blocks,
@@ -50,6 +51,7 @@ static bool model_info(int kind, ModelInfo* info) {
     case TQF_MODEL_GBM_1F: *info = {1, 1, 4}; return true;
     case TQF_MODEL_LINEAR_1F: *info = {1, 1, 5}; return true;
     case TQF_MODEL_HESTON_EULER: *info = {2, 2, 6}; return true;
+    case TQF_MODEL_HW1F: *info = {2, 1, 5}; return true;
     default: return false;
   }
 }
@@ -69,6 +71,7 @@ struct tqf_plan {
   uint32_t* sobol_dev;      // [S_total*nf][32]
   double* partials_dev;     // [max_grid][TQF_MAX_PAYOFFS][4]
   int* record_dev;          // [num_steps+1]
+  SwaptionK* swaptions_dev; // [TQF_MAX_PAYOFFS]
   double x0[2];
 };
 
@@ -132,6 +135,8 @@ static int dispatch(const tqf_plan* plan, int mode, int grid, size_t smem, const
       return launch_path_kernel<LinearModel1F<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     case TQF_MODEL_HESTON_EULER:
       return launch_path_kernel<HestonEulerModel<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+    case TQF_MODEL_HW1F:
+      return launch_path_kernel<HullWhite1FModel<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     default:
       set_error("model kind not supported by the generic path kernel");
       return TQF_ERR_UNSUPPORTED;
@@ -146,12 +151,36 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   fill_common(plan, path_offset, path_count, &P);
   P.num_payoffs = num_payoffs;
   int monitor = -1;
+  const int S = plan->model.num_steps;
+  std::vector<int> flags(static_cast<size_t>(S) + 1, -1);
+  std::vector<SwaptionK> swaptions;
   for (int q = 0; q < num_payoffs; ++q) {
     const tqf_payoff_desc& d = payoffs[q];
-    TQF_REQUIRE(d.kind >= TQF_PAYOFF_CALL && d.kind <= TQF_PAYOFF_IDENTITY,
-                "payoff kind not supported by this model");
+    TQF_REQUIRE(d.kind >= TQF_PAYOFF_CALL && d.kind <= TQF_PAYOFF_HW_SWAPTION,
+                "unknown payoff kind");
+    const int step = d.expiry_step > 0 ? d.expiry_step : S;
+    TQF_REQUIRE(step <= S, "payoff expiry_step exceeds the number of steps");
+    flags[step] = 1;
+    if (d.kind == TQF_PAYOFF_HW_SWAPTION) {
+      TQF_REQUIRE(plan->model.kind == TQF_MODEL_HW1F,
+                  "TQF_PAYOFF_HW_SWAPTION needs the TQF_MODEL_HW1F model");
+      TQF_REQUIRE(d.num_payments >= 1 && d.num_payments <= TQF_MAX_SWAPTION_PAYMENTS,
+                  "num_payments out of range");
+      if (swaptions.empty()) swaptions.resize(TQF_MAX_PAYOFFS);
+      SwaptionK& sw = swaptions[q];
+      std::memset(&sw, 0, sizeof(sw));
+      sw.num_payments = d.num_payments;
+      sw.is_payer = d.is_payer;
+      for (int j = 0; j < d.num_payments; ++j) {
+        sw.g[j] = d.pay_g[j];
+        sw.k[j] = d.pay_k[j];
+        sw.coef[j] = d.pay_coef[j];
+      }
+      P.pay[q] = PayoffK{d.kind, 0, 0, step, 0.0, 0.0, d.scale};
+      continue;
+    }
     TQF_REQUIRE(d.component >= 0 && d.component < plan->info.dim, "payoff component out of range");
-    P.pay[q] = PayoffK{d.kind, d.component, d.transform, 0, d.strike, d.barrier, d.scale};
+    P.pay[q] = PayoffK{d.kind, d.component, d.transform, step, d.strike, d.barrier, d.scale};
     if (d.kind >= TQF_PAYOFF_UP_OUT_CALL && d.kind <= TQF_PAYOFF_DOWN_OUT_CALL) {
       TQF_REQUIRE(monitor < 0 || monitor == d.component,
                   "all barrier payoffs of one call must watch the same state component");
@@ -161,6 +190,16 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     }
   }
   P.monitor = monitor < 0 ? 0 : monitor;
+  TQF_CUDA_OK(cudaMemcpyAsync(plan->record_dev, flags.data(), flags.size() * sizeof(int),
+                              cudaMemcpyHostToDevice, stream));
+  P.record_slot = plan->record_dev;
+  if (!swaptions.empty()) {
+    TQF_CUDA_OK(cudaMemcpyAsync(plan->swaptions_dev, swaptions.data(),
+                                swaptions.size() * sizeof(SwaptionK), cudaMemcpyHostToDevice,
+                                stream));
+    // the staging vector dies at return: pageable copies are complete on return
+  }
+  P.swaptions = plan->swaptions_dev;
   P.partials = plan->partials_dev;
   int grid = 1;
   const int rk = rng_kind(plan);
@@ -271,6 +310,8 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
                    static_cast<size_t>(plan->max_grid) * TQF_MAX_PAYOFFS * 4 * sizeof(double));
     if (e == cudaSuccess)
       e = cudaMalloc(&plan->record_dev, (static_cast<size_t>(model->num_steps) + 1) * sizeof(int));
+    if (e == cudaSuccess)
+      e = cudaMalloc(&plan->swaptions_dev, TQF_MAX_PAYOFFS * sizeof(SwaptionK));
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(plan scratch)");
   }
   // the descriptors' host pointers are not kept
@@ -293,6 +334,7 @@ int tqf_plan_destroy(tqf_plan* plan) {
   cudaFree(plan->sobol_dev);
   cudaFree(plan->partials_dev);
   cudaFree(plan->record_dev);
+  cudaFree(plan->swaptions_dev);
   delete plan;
   return TQF_OK;
 }

@@ -35,10 +35,20 @@ struct PayoffK {
   int32_t kind;
   int32_t component;
   int32_t transform;
-  int32_t pad;
+  int32_t step;   // evaluated on the state after this many steps
   double strike;
   double barrier;
   double scale;
+};
+
+// Device-side table of one Hull-White swaption payoff (TQF_PAYOFF_HW_SWAPTION):
+//   P(t_e, T_j) = exp(k_j - G_j x),  payoff = scale max(+-DF (1 - sum_j coef_j P_j), 0)
+struct SwaptionK {
+  int32_t num_payments;
+  int32_t is_payer;
+  double g[TQF_MAX_SWAPTION_PAYMENTS];
+  double k[TQF_MAX_SWAPTION_PAYMENTS];
+  double coef[TQF_MAX_SWAPTION_PAYMENTS];
 };
 
 template <typename Real>
@@ -67,6 +77,7 @@ struct KParams {
   int monitor;               // state component the barrier payoffs watch
   PayoffK pay[TQF_MAX_PAYOFFS];
   double* partials;          // device [gridDim.x][TQF_MAX_PAYOFFS][4]
+  const SwaptionK* swaptions; // device [num_payoffs] (HW swaption payoffs only)
   // MODE_PATHS
   const int* record_slot;    // device [num_steps + 1]
   Real* out;
@@ -111,6 +122,21 @@ struct LinearModel1F {  // x' = A x + B + C z  (HW exact OU step, vector_hull_wh
   __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
                                               const Real (&c)[NCOEF]) {
     x[0] = (c[2] * x[0] + c[3]) + c[4] * z[0];
+  }
+};
+
+template <typename R>
+struct HullWhite1FModel {
+  // Exact OU step of the one-factor Hull-White model
+  // (vector_hull_white.py:738-767) with the path integral of the short rate
+  // carried as a second state component (hjm/swaption_util.py:126-136):
+  //   x' = A x + B + C z ;  I' = I + W (x' + f(0, t')) = I + W x' + WF
+  using Real = R;
+  static constexpr int DIM = 2, NF = 1, NCOEF = 5;
+  __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
+                                              const Real (&c)[NCOEF]) {
+    x[0] = fma(c[2], z[0], fma(c[0], x[0], c[1]));
+    x[1] = fma(c[3], x[0], x[1] + c[4]);
   }
 };
 
@@ -303,7 +329,7 @@ path_kernel(const KParams<typename Model::Real> P) {
     off = (off + 15) & ~static_cast<size_t>(15);
   }
   int* s_rec = reinterpret_cast<int*>(smem_raw + off);
-  if (MODE == MODE_PATHS && P.tables_in_smem)
+  if (P.tables_in_smem)
     off += ((static_cast<size_t>(P.num_steps) + 1) * sizeof(int) + 15) & ~static_cast<size_t>(15);
   uint32_t* s_high = reinterpret_cast<uint32_t*>(smem_raw + off);
   if (RNGK == RNGK_SOBOL) off += static_cast<size_t>(PPT) * kSobolTileDims * sizeof(uint32_t);
@@ -320,10 +346,8 @@ path_kernel(const KParams<typename Model::Real> P) {
   if (P.tables_in_smem) {
     for (int i = tid; i < P.num_steps * NCOEF; i += kBlock) s_coef[i] = P.coef[i];
     coef_tab = s_coef;
-    if (MODE == MODE_PATHS) {
-      for (int i = tid; i <= P.num_steps; i += kBlock) s_rec[i] = P.record_slot[i];
-      rec_tab = s_rec;
-    }
+    for (int i = tid; i <= P.num_steps; i += kBlock) s_rec[i] = P.record_slot[i];
+    rec_tab = s_rec;
   }
   if (MODE == MODE_PRICE) {
     for (int i = tid; i < kWarps * TQF_MAX_PAYOFFS * 3; i += kBlock) s_acc[i] = 0.0;
@@ -387,6 +411,61 @@ path_kernel(const KParams<typename Model::Real> P) {
           }
       }
     }
+
+    // Evaluates and reduces the payoffs attached to `step_index`.
+    auto eval_payoffs = [&](int step_index) {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int q = 0; q < P.num_payoffs; ++q) {
+        const PayoffK& d = P.pay[q];
+        if (d.step != step_index) continue;
+        double sum = 0.0, sq = 0.0, bad = 0.0;
+#pragma unroll
+        for (int a = 0; a < PPT; ++a) {
+          if (valid[a]) {
+#pragma unroll
+            for (int h = 0; h < NPATH; ++h) {
+              double v;
+              if (d.kind == TQF_PAYOFF_HW_SWAPTION) {
+                const SwaptionK& sw = P.swaptions[q];
+                const double xs = static_cast<double>(x[a][h][0]);
+                const double integral = static_cast<double>(x[a][h][DIM - 1]);
+                double acc = 0.0;
+                for (int j = 0; j < sw.num_payments; ++j)
+                  acc = fma(sw.coef[j], exp(fma(-sw.g[j], xs, sw.k[j])), acc);
+                double swap = exp(-integral) * (1.0 - acc);
+                swap = sw.is_payer ? swap : -swap;
+                v = (swap > 0.0 ? swap : 0.0) * d.scale;
+              } else {
+                double xf = 0.0;
+                const double xa = static_cast<double>(xmax[a][h]);
+                const double xi = static_cast<double>(xmin[a][h]);
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) {
+                  if (j == d.component) xf = static_cast<double>(x[a][h][j]);
+                }
+                v = eval_payoff(d, xf, xa, xi);
+              }
+              if (isfinite(v)) {
+                sum += v;
+                sq += v * v;
+              } else {
+                bad += 1.0;
+              }
+            }
+          }
+        }
+        sum = warp_sum(sum);
+        sq = warp_sum(sq);
+        bad = warp_sum(bad);
+        if (lane == 0) {
+          double* acc = s_acc + (warp * TQF_MAX_PAYOFFS + q) * 3;
+          acc[0] += sum;
+          acc[1] += sq;
+          acc[2] += bad;
+        }
+      }
+    };
+    if (MODE == MODE_PRICE && rec_tab[0] >= 0) eval_payoffs(0);
 
     for (int s0 = 0; s0 < P.num_steps; s0 += TILE_STEPS) {
       const int s1 = min(P.num_steps, s0 + TILE_STEPS);
@@ -481,6 +560,7 @@ path_kernel(const KParams<typename Model::Real> P) {
                 if (P.need_extrema & 2) xmin[a][h] = xm < xmin[a][h] ? xm : xmin[a][h];
               }
           }
+          if (rec_tab[s + 1] >= 0) eval_payoffs(s + 1);
         } else {
           const int slot = rec_tab[s + 1];
           if (slot >= 0) {
@@ -499,44 +579,6 @@ path_kernel(const KParams<typename Model::Real> P) {
       }
     }
 
-    if (MODE == MODE_PRICE) {
-      const int warp = tid >> 5, lane = tid & 31;
-      for (int q = 0; q < P.num_payoffs; ++q) {
-        const PayoffK& d = P.pay[q];
-        double sum = 0.0, sq = 0.0, bad = 0.0;
-#pragma unroll
-        for (int a = 0; a < PPT; ++a) {
-          if (valid[a]) {
-#pragma unroll
-            for (int h = 0; h < NPATH; ++h) {
-              double xf = 0.0;
-              const double xa = static_cast<double>(xmax[a][h]);
-              const double xi = static_cast<double>(xmin[a][h]);
-#pragma unroll
-              for (int j = 0; j < DIM; ++j) {
-                if (j == d.component) xf = static_cast<double>(x[a][h][j]);
-              }
-              const double v = eval_payoff(d, xf, xa, xi);
-              if (isfinite(v)) {
-                sum += v;
-                sq += v * v;
-              } else {
-                bad += 1.0;
-              }
-            }
-          }
-        }
-        sum = warp_sum(sum);
-        sq = warp_sum(sq);
-        bad = warp_sum(bad);
-        if (lane == 0) {
-          double* acc = s_acc + (warp * TQF_MAX_PAYOFFS + q) * 3;
-          acc[0] += sum;
-          acc[1] += sq;
-          acc[2] += bad;
-        }
-      }
-    }
   }
 
   if (MODE == MODE_PRICE) {
@@ -562,7 +604,7 @@ size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool table
   if (tables_in_smem) {
     off = static_cast<size_t>(num_steps) * ncoef * sizeof(Real);
     off = (off + 15) & ~static_cast<size_t>(15);
-    if (mode == MODE_PATHS) off += ((static_cast<size_t>(num_steps) + 1) * sizeof(int) + 15) & ~static_cast<size_t>(15);
+    off += ((static_cast<size_t>(num_steps) + 1) * sizeof(int) + 15) & ~static_cast<size_t>(15);
   }
   if (rngk == RNGK_SOBOL) off += static_cast<size_t>(ppt) * kSobolTileDims * sizeof(uint32_t) + static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   off += static_cast<size_t>(kWarps) * TQF_MAX_PAYOFFS * 3 * sizeof(double);

@@ -25,6 +25,7 @@ MODEL_HESTON_EULER = 3
 MODEL_HESTON_QE = 4
 MODEL_MVGBM = 5
 MODEL_LINEAR_1F = 6
+MODEL_HW1F = 7
 PAYOFF_CALL = 1
 PAYOFF_PUT = 2
 PAYOFF_UP_OUT_CALL = 3
@@ -80,10 +81,10 @@ class PayoffDesc(C.Structure):
       ('num_payments', C.c_int32),
       ('is_payer', C.c_int32),
       ('reserved2', C.c_int32),
-      ('hw_y', C.c_double),
-      ('hw_fwd', C.c_double),
+      ('reserved3', C.c_double),
+      ('reserved4', C.c_double),
       ('pay_g', C.c_double * MAX_SWAPTION_PAYMENTS),
-      ('pay_p0', C.c_double * MAX_SWAPTION_PAYMENTS),
+      ('pay_k', C.c_double * MAX_SWAPTION_PAYMENTS),
       ('pay_coef', C.c_double * MAX_SWAPTION_PAYMENTS),
   ]
 

@@ -1,11 +1,14 @@
 """Mirror of `tf_quant_finance.models` for the Monte-Carlo hot path."""
 from tff_b200.models import closures
 from tff_b200.models import euler_sampling
+from tff_b200.models import hull_white
 from tff_b200.models import utils
 from tff_b200.models.generic_ito_process import GenericItoProcess
 from tff_b200.models.geometric_brownian_motion.univariate_geometric_brownian_motion import GeometricBrownianMotion
 from tff_b200.models.heston.heston_model import HestonModel
+from tff_b200.models.hull_white.one_factor import HullWhiteModel1F
 from tff_b200.models.ito_process import ItoProcess
 
 __all__ = ['closures', 'euler_sampling', 'utils', 'GenericItoProcess',
-           'GeometricBrownianMotion', 'HestonModel', 'ItoProcess']
+           'GeometricBrownianMotion', 'HestonModel', 'HullWhiteModel1F', 'ItoProcess',
+           'hull_white']

@@ -1,0 +1,160 @@
+"""Monte-Carlo European swaption pricing under the one-factor Hull-White model.
+
+Drop-in for the simulation branch of
+`tf_quant_finance.models.hull_white.swaption_price`
+(`models/hull_white/swaption.py:41-312`) together with
+`discount_factors_and_bond_prices_from_samples`
+(`models/hjm/swaption_util.py:28-170`).
+
+The reference materialises the short-rate paths `[N, k, 1]`, the bond-price
+tensor `[N, m, k, 1]` (of which one time column is used) and a `[k, k]`
+cumulative-sum matmul per path.  Here the fused kernel carries the path
+integral of the short rate next to the OU state and evaluates
+  payoff = notional * max(+-DF(t_e) (1 - P_N - sum_j c_j tau_j P_j), 0)
+in registers when the path reaches the expiry step; nothing is stored.
+"""
+import numpy as np
+
+from tff_b200 import _lib
+from tff_b200 import _tensor
+from tff_b200.models import utils
+from tff_b200.models.hull_white import _exact
+from tff_b200.models.hull_white import one_factor
+
+
+def _swaption_desc(model, all_times, step, expiry, pay_times, coupon, dcf,
+                   is_payer, notional):
+  """tqf_payoff_desc of one swaption evaluated after `step` steps."""
+  dt_ = model._dtype
+  k = model._tables.k
+  y = model._tables.y_t(np.asarray([expiry], dtype=dt_))[0]
+  rate = lambda t: _exact.discount_rate(model._initial_discount_rate_fn, t, dt_)
+  t_e = np.asarray(expiry, dtype=dt_)
+  ln_p0_ratio = -(rate(pay_times) * pay_times) + rate(t_e) * t_e
+  g = (1. - np.exp(-k * (pay_times - t_e))) / k
+  d = _lib.PayoffDesc()
+  d.kind = _lib.PAYOFF_HW_SWAPTION
+  d.expiry_step = int(step)
+  d.num_payments = int(pay_times.shape[0])
+  d.is_payer = int(bool(is_payer))
+  d.scale = float(notional)
+  coef = np.array(coupon * dcf, dtype=np.float64)
+  coef[-1] += 1.0                      # float leg: 1 - P(t_e, T_N)
+  for j in range(pay_times.shape[0]):
+    d.pay_g[j] = float(g[j])
+    d.pay_k[j] = float(ln_p0_ratio[j] - 0.5 * y * g[j]**2)
+    d.pay_coef[j] = float(coef[j])
+  del all_times
+  return d
+
+
+class _RawPayoff:
+  def __init__(self, d):
+    self._d = d
+
+  def desc(self):
+    return self._d
+
+
+def swaption_price(*,
+                   expiries,
+                   floating_leg_start_times,
+                   floating_leg_end_times,
+                   fixed_leg_payment_times,
+                   floating_leg_daycount_fractions,
+                   fixed_leg_daycount_fractions,
+                   fixed_leg_coupon,
+                   reference_rate_fn,
+                   mean_reversion,
+                   volatility,
+                   notional=None,
+                   is_payer_swaption=True,
+                   use_analytic_pricing=True,
+                   num_samples=100,
+                   random_type=None,
+                   seed=None,
+                   skip=0,
+                   time_step=None,
+                   dtype=None,
+                   name=None,
+                   return_stats=False):
+  """European swaption prices of shape `expiries.shape` (numpy float array).
+
+  Same arguments as the reference.  `use_analytic_pricing=True` (Jamshidian
+  decomposition, a closed form outside the Monte-Carlo hot path) is not
+  implemented by the B200 engine; pass `use_analytic_pricing=False`.
+  """
+  del floating_leg_daycount_fractions, floating_leg_start_times
+  del floating_leg_end_times, name
+  dt_ = _tensor.infer_dtype(expiries, dtype, default=np.float32)
+  expiries = _tensor.to_numpy(expiries, dt_)
+  pay_t = _tensor.to_numpy(fixed_leg_payment_times, dt_)
+  dcf = np.broadcast_to(_tensor.to_numpy(fixed_leg_daycount_fractions, dt_), pay_t.shape)
+  coupon = np.broadcast_to(_tensor.to_numpy(fixed_leg_coupon, dt_), pay_t.shape)
+  if expiries.ndim < pay_t.ndim - 1:
+    raise ValueError('Swaption expiries not specified for all swaptions '
+                     'in the batch. Expected rank {} but received {}.'.format(
+                         pay_t.ndim - 1, expiries.ndim))
+  notional = np.asarray(1.0 if notional is None else _tensor.to_numpy(notional, dt_), dtype=dt_)
+  is_payer = np.asarray(_tensor.to_numpy(is_payer_swaption), dtype=bool)
+  if use_analytic_pricing:
+    raise NotImplementedError(
+        'Analytic (Jamshidian) swaption valuation is a closed form outside the '
+        'B200 Monte-Carlo hot path; call with use_analytic_pricing=False.')
+  if time_step is None:
+    raise ValueError('`time_step` must be provided for simulation '
+                     'based bond option valuation.')
+  model = one_factor.HullWhiteModel1F(mean_reversion, volatility,
+                                      reference_rate_fn, dtype=dt_)
+  if model._tables is None:
+    raise NotImplementedError(
+        'swaption_price needs constant mean reversion and constant or '
+        'piecewise-constant volatility (exact discretisation).')
+  batch_shape = expiries.shape
+  m = pay_t.shape[-1]
+  exp_flat = np.broadcast_to(expiries[..., None], batch_shape + (m,)).reshape(-1, m)[:, 0]
+  pay_flat = np.broadcast_to(pay_t, batch_shape + (m,)).reshape(-1, m)
+  dcf_flat = np.broadcast_to(dcf, batch_shape + (m,)).reshape(-1, m)
+  cpn_flat = np.broadcast_to(coupon, batch_shape + (m,)).reshape(-1, m)
+  ntl_flat = np.broadcast_to(notional, batch_shape).reshape(-1)
+  payer_flat = np.broadcast_to(is_payer, batch_shape).reshape(-1)
+
+  # sim_times: unique expiries plus the uniform grid (swaption.py:284-288)
+  sim_times = np.unique(exp_flat)
+  longest = sim_times.max()
+  sim_times = np.sort(np.concatenate(
+      [sim_times, utils._tf_range(time_step, longest, time_step, dt_)]),
+                      kind='stable').astype(dt_)
+
+  def integral_weights(all_times, idx):
+    # DF(t_j) = exp(-sum_{i<=j} r(t_i) dt_i), dt_0 = 0 (swaption_util.py:126):
+    # the step that lands on sim time j >= 1 carries t_j - t_{j-1}.
+    w = np.zeros(all_times.shape[0] - 1, dtype=dt_)
+    dts = np.concatenate([[0.0], sim_times[1:] - sim_times[:-1]]).astype(dt_)
+    for j, i in enumerate(idx):
+      if i >= 1:
+        w[i - 1] += dts[j]
+    return w
+
+  plan, _, all_times, idx = model._exact_plan(
+      sim_times, int(num_samples), random_type, seed, skip, None, None,
+      integral_weights_fn=integral_weights)
+  try:
+    sim_idx = np.searchsorted(sim_times, exp_flat, side='left')
+    descs = [
+        _RawPayoff(_swaption_desc(model, all_times, idx[sim_idx[b]], exp_flat[b],
+                                  pay_flat[b], cpn_flat[b], dcf_flat[b],
+                                  payer_flat[b], ntl_flat[b]))
+        for b in range(exp_flat.shape[0])]
+    sums = []
+    for c0 in range(0, len(descs), _lib.MAX_PAYOFFS):
+      sums.append(plan.price_sums(descs[c0:c0 + _lib.MAX_PAYOFFS]).cpu().numpy())
+    sums = np.concatenate(sums, axis=0)
+  finally:
+    plan.close()
+  n = float(plan.num_samples)
+  price = (sums[:, 0] / n).astype(dt_).reshape(batch_shape)
+  if not return_stats:
+    return price
+  var = np.maximum(sums[:, 1] / n - (sums[:, 0] / n)**2, 0.0)
+  return price, np.sqrt(var / n).reshape(batch_shape), sums[:, 2].reshape(batch_shape)
