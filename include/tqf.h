@@ -222,6 +222,56 @@ int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                    int64_t stride_path, int64_t stride_time, int64_t stride_dim,
                    void* stream);
 
+/* ------------------------------------------------------------------------
+ * Longstaff-Schwartz regression passes on materialised paths: replaces the
+ * device work of models/longstaff_schwartz/lsm.py:231-436 (payoff_fn, basis_fn,
+ * the masked X'X / X'y matmuls, tf.where updates) for
+ *   payoff_fn = make_basket_put_payoff(strikes)   (payoff_utils.py:27-97)
+ *   basis_fn  = make_polynomial_basis(degree)      (lsm.py:50-125).
+ * The K x K pseudo-inverse is solved by the caller between passes (after the
+ * all-reduce of the sums when paths are sharded over GPUs).
+ * ---------------------------------------------------------------------- */
+typedef struct tqf_lsm_desc {
+  int32_t dtype;       /* TQF_F32 / TQF_F64 (dtype of the paths)             */
+  int32_t dim;         /* state dimension (<= 8)                             */
+  int32_t batch;       /* number of payoffs B (strikes)                      */
+  int32_t basis_size;  /* K = (degree+1)^dim (<= 128)                        */
+  const int32_t* exponents; /* host [K][dim] monomial exponents              */
+  const double* strikes;    /* host [B]                                      */
+  uint64_t num_paths;       /* local paths                                   */
+  uint64_t path_offset;     /* global index of local path 0                  */
+  uint64_t num_calibration_samples; /* regress on global paths < n; 0 = all  */
+  const void* paths_dev;    /* element (n, t, j) at n*stride_path +          */
+  int64_t stride_path;      /*   t*stride_time + j*stride_dim (+ b*stride_   */
+  int64_t stride_time;      /*   batch for batched sample paths), strides in */
+  int64_t stride_dim;       /*   elements                                    */
+  int64_t stride_batch;
+} tqf_lsm_desc;
+
+typedef struct tqf_lsm tqf_lsm;
+
+int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out);
+int tqf_lsm_destroy(tqf_lsm* lsm);
+/* sums_dev[b][t][j] = sum_n x[n, time_indices[t], j] (basis centring). */
+int tqf_lsm_column_sums(tqf_lsm* lsm, const int32_t* time_indices, int num_times,
+                        double* sums_dev, void* stream);
+/* W[b][n] = payoff_b(x[n, time_index, :]) (the terminal cashflow). */
+int tqf_lsm_init(tqf_lsm* lsm, int time_index, void* stream);
+/* One pass: optionally W' = ev > relu(X beta) ? ev : ratio_update W at time
+ * index t_update, then optionally accumulate the normal equations at t_acc with
+ * y = ratio_acc W'.  Host arrays: mean_* [B][dim], beta [B][K], ratio_* [B].
+ * sums_dev: double [B][num_sums] (layout: tqf_lsm_sums_layout). */
+int tqf_lsm_step(tqf_lsm* lsm, int do_update, int t_update, const double* mean_update,
+                 const double* beta, const double* ratio_update, int do_accumulate,
+                 int t_acc, const double* mean_acc, const double* ratio_acc,
+                 double* sums_dev, void* stream);
+/* num_sums doubles per payoff.  Packed (K <= 6): the upper triangle of a 6 x 6
+ * X'X row by row (21 entries) followed by 6 entries of X'y; otherwise X'X
+ * [K][K] row-major followed by X'y [K]. */
+int tqf_lsm_sums_layout(const tqf_lsm* lsm, int* num_sums, int* is_packed_symmetric);
+/* sums_dev[b] = {sum_n W[b][n], count} over global paths >= skip_below. */
+int tqf_lsm_value_sum(tqf_lsm* lsm, uint64_t skip_below, double* sums_dev, void* stream);
+
 /* Measures the FP64 DFMA issue peak of the current device (Ginstr/s): the
  * roofline denominator for the fused mode (not in MEASURED_PEAKS.json).
  * Synchronises. */

@@ -1,0 +1,108 @@
+"""GPU parity of the Longstaff-Schwartz passes: the reference's own KATs
+(models/longstaff_schwartz/lsm_test.py) and the oracle on simulated paths."""
+import numpy as np
+import pytest
+
+from oracle import draws as odraws
+from oracle import euler as oeuler
+from oracle import lsm as olsm
+
+pytestmark = pytest.mark.gpu
+
+_SAMPLES = np.expand_dims([[1.0, 1.09, 1.08, 1.34], [1.0, 1.16, 1.26, 1.54],
+                           [1.0, 1.22, 1.07, 1.03], [1.0, 0.93, 0.97, 0.92],
+                           [1.0, 1.11, 1.56, 1.52], [1.0, 0.76, 0.77, 0.90],
+                           [1.0, 0.92, 0.84, 1.01], [1.0, 0.88, 1.22, 1.34]], -1)
+_DF = np.exp(-np.cumsum([0.06, 0.06, 0.06]))
+
+
+def _lsm():
+  import tff_b200 as tff
+  return tff.models.longstaff_schwartz
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_reference_kats(dtype):
+  # lsm_test.py:60-127, 169-219
+  lsm = _lsm()
+  basis = lsm.make_polynomial_basis(2)
+  put = lsm.make_basket_put_payoff([1.1], dtype=dtype)
+  tol = dict(rtol=1e-4, atol=1e-4)
+  got = lsm.least_square_mc(_SAMPLES, [3], put, basis, discount_factors=[_DF[-1]], dtype=dtype)
+  assert got.dtype == dtype and got.shape == (1,)
+  np.testing.assert_allclose(got, [0.0564], **tol)
+  np.testing.assert_allclose(
+      lsm.least_square_mc(_SAMPLES, [1, 2, 3], put, basis, discount_factors=_DF, dtype=dtype),
+      [0.1144], **tol)
+  np.testing.assert_allclose(
+      lsm.least_square_mc(_SAMPLES, [1, 2, 3], put, basis, discount_factors=_DF,
+                          num_calibration_samples=4, dtype=dtype), [0.174226], **tol)
+  put2 = lsm.make_basket_put_payoff([1.1, 1.2], dtype=dtype)
+  df2 = np.exp(-np.cumsum([[0.06] * 3, [0.05] * 3], -1))[None]
+  np.testing.assert_allclose(
+      lsm.least_square_mc(_SAMPLES, [1, 2, 3], put2, basis, discount_factors=df2, dtype=dtype),
+      [0.1144, 0.199], **tol)
+  batch = np.stack([_SAMPLES, _SAMPLES + 0.1], 0)
+  np.testing.assert_allclose(
+      lsm.least_square_mc(batch, [1, 2, 3], put2, basis, discount_factors=df2, dtype=dtype),
+      [0.1144, 0.1157], **tol)
+
+
+def test_basket_degree_10_generic_path():
+  # lsm_test.py:129-157: K = 121 basis functions on 8 samples (rank deficient)
+  lsm = _lsm()
+  basis = lsm.make_polynomial_basis(10)
+  put = lsm.make_basket_put_payoff([1.1, 1.2, 1.3], dtype=np.float64)
+  s2 = np.concatenate([_SAMPLES, _SAMPLES], -1)
+  a = lsm.least_square_mc(s2, [1, 2, 3], put, basis, discount_factors=_DF, dtype=np.float64)
+  b = lsm.least_square_mc(_SAMPLES, [1, 2, 3], put, basis, discount_factors=_DF, dtype=np.float64)
+  assert a.shape == (3,)
+  np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-4)
+  ob = olsm.least_square_mc(_SAMPLES, [1, 2, 3], olsm.make_basket_put_payoff([1.1, 1.2, 1.3]),
+                            olsm.make_polynomial_basis(10), _DF, dtype=np.float64)
+  np.testing.assert_allclose(b, ob, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('degree,calib', [(3, None), (2, 20000), (5, None)])
+def test_american_put_on_engine_paths_matches_oracle(degree, calib):
+  # the docstring example of lsm.py:145-183 on the engine's own paths
+  import torch
+  import tff_b200 as tff
+  from tff_b200.models import closures
+  lsm = _lsm()
+  r, sigma, n = 0.1, 1.0, 1 << 16
+  times = np.linspace(0.0, 1.0, 13)
+  drift, vol = closures.affine_closures(r - sigma**2 / 2, 0.0, sigma)
+  kw = dict(num_samples=n, initial_state=np.array([0.0]), seed=[4, 2], time_step=0.05,
+            dtype=np.float64)
+  log_paths = tff.models.euler_sampling.sample(
+      1, drift, vol, times, random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, **kw)
+  paths = torch.exp(log_paths)                       # keeps the time-major strides
+  df = np.exp(-r * times)
+  got = lsm.least_square_mc(paths, np.arange(13), lsm.make_basket_put_payoff([1.1], dtype=np.float64),
+                            lsm.make_polynomial_basis(degree), discount_factors=df,
+                            num_calibration_samples=calib, dtype=np.float64)
+  opaths = np.exp(oeuler.sample(
+      1, lambda t, x: (r - sigma**2 / 2) + 0 * x, lambda t, x: sigma * np.ones(x.shape + (1,)),
+      times, random_type=odraws.RandomType.STATELESS_ANTITHETIC, **kw))
+  np.testing.assert_allclose(paths.cpu().numpy(), opaths, rtol=1e-12)
+  want = olsm.least_square_mc(opaths, np.arange(13), olsm.make_basket_put_payoff([1.1]),
+                              olsm.make_polynomial_basis(degree), df,
+                              num_calibration_samples=calib, dtype=np.float64)
+  # the regression is solved from differently ordered sums: exercise decisions
+  # of paths within ~1e-9 of the boundary may flip -> 1e-9 relative on the price
+  np.testing.assert_allclose(got, want, rtol=1e-9)
+
+
+def test_two_dimensional_basket_matches_oracle():
+  lsm = _lsm()
+  rs = np.random.RandomState(5)
+  n, T = 5000, 6
+  steps = rs.standard_normal((n, T, 2)) * 0.1
+  paths = np.exp(np.cumsum(steps, axis=1))
+  df = np.exp(-0.05 * np.arange(1, T + 1))
+  got = lsm.least_square_mc(paths, np.arange(T), lsm.make_basket_put_payoff([1.0, 1.1], dtype=np.float64),
+                            lsm.make_polynomial_basis(2), discount_factors=df, dtype=np.float64)
+  want = olsm.least_square_mc(paths, np.arange(T), olsm.make_basket_put_payoff([1.0, 1.1]),
+                              olsm.make_polynomial_basis(2), df, dtype=np.float64)
+  np.testing.assert_allclose(got, want, rtol=1e-9)

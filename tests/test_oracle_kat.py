@@ -234,3 +234,50 @@ def test_hw_swaption_mc_kat():
       seed=[4, 2], dtype=np.float64)
   assert price.shape == ()
   np.testing.assert_allclose(price, 0.71632434, rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------------ Longstaff-Schwartz ----
+_LS_SAMPLES = np.expand_dims([[1.0, 1.09, 1.08, 1.34], [1.0, 1.16, 1.26, 1.54],
+                              [1.0, 1.22, 1.07, 1.03], [1.0, 0.93, 0.97, 0.92],
+                              [1.0, 1.11, 1.56, 1.52], [1.0, 0.76, 0.77, 0.90],
+                              [1.0, 0.92, 0.84, 1.01], [1.0, 0.88, 1.22, 1.34]], -1)
+_LS_DF = np.exp(-np.cumsum([0.06, 0.06, 0.06]))
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_lsm_reference_kats(dtype):
+  # models/longstaff_schwartz/lsm_test.py:60-127, 169-219
+  from oracle import lsm
+  basis = lsm.make_polynomial_basis(2)
+  put = lsm.make_basket_put_payoff([1.1], dtype=dtype)
+  tol = dict(rtol=1e-4, atol=1e-4)
+  np.testing.assert_allclose(
+      lsm.least_square_mc(_LS_SAMPLES, [3], put, basis, [_LS_DF[-1]], dtype=dtype),
+      [0.0564], **tol)
+  np.testing.assert_allclose(
+      lsm.least_square_mc(_LS_SAMPLES, [1, 2, 3], put, basis, _LS_DF, dtype=dtype),
+      [0.1144], **tol)
+  np.testing.assert_allclose(
+      lsm.least_square_mc(_LS_SAMPLES, [1, 2, 3], put, basis, _LS_DF,
+                          num_calibration_samples=4, dtype=dtype), [0.174226], **tol)
+  put2 = lsm.make_basket_put_payoff([1.1, 1.2], dtype=dtype)
+  df2 = np.exp(-np.cumsum([[0.06] * 3, [0.05] * 3], -1))[None]
+  np.testing.assert_allclose(
+      lsm.least_square_mc(_LS_SAMPLES, [1, 2, 3], put2, basis, df2, dtype=dtype),
+      [0.1144, 0.199], **tol)
+  batch = np.stack([_LS_SAMPLES, _LS_SAMPLES + 0.1], 0)
+  np.testing.assert_allclose(
+      lsm.least_square_mc(batch, [1, 2, 3], put2, basis, df2, dtype=dtype),
+      [0.1144, 0.1157], **tol)
+
+
+def test_lsm_basket_degree_10():
+  # models/longstaff_schwartz/lsm_test.py:129-157 (rank-deficient regression)
+  from oracle import lsm
+  basis = lsm.make_polynomial_basis(10)
+  put = lsm.make_basket_put_payoff([1.1, 1.2, 1.3], dtype=np.float64)
+  s2 = np.concatenate([_LS_SAMPLES, _LS_SAMPLES], -1)
+  a = lsm.least_square_mc(s2, [1, 2, 3], put, basis, _LS_DF, dtype=np.float64)
+  b = lsm.least_square_mc(_LS_SAMPLES, [1, 2, 3], put, basis, _LS_DF, dtype=np.float64)
+  assert a.shape == (3,)
+  np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-4)

@@ -1,0 +1,582 @@
+// Longstaff-Schwartz regression passes on materialised paths.
+//
+// Replaces the device work of models/longstaff_schwartz/lsm.py:231-436 of the
+// reference (payoff_fn, basis_fn, the masked X'X / X'y matmuls and the
+// tf.where updates, each a full pass over [N] tensors there).  Per exercise
+// date ONE streaming pass updates the merged state W = cashflow + values
+//   W' = exercise_value > relu(X beta) ? exercise_value : ratio W
+// (exact because one of cashflow / values is always zero, lsm.py:391-399) and
+// accumulates the normal equations of the NEXT (earlier) date from W'.  The
+// K x K pseudo-inverse happens between passes on the reduced sums (and, on
+// several GPUs, after the all-reduce of those sums).
+//
+// HBM-bound: per path and date it reads x at two time columns and reads +
+// writes W (4 x 8 B in fp64).  Paths are expected time-major (stride_path = 1),
+// the layout tqf_plan_paths writes; any strides work.
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "tqf_common.cuh"
+
+namespace tqf {
+
+constexpr int kLsmBlock = 256;
+constexpr int kLsmFastK = 6;                                  // register path
+constexpr int kLsmFastNS = kLsmFastK * (kLsmFastK + 1) / 2 + kLsmFastK;  // 27
+constexpr int kLsmMaxDim = 8;
+constexpr int kLsmMaxK = 128;
+constexpr int kLsmTile = 32;   // paths per tile of the generic path
+
+template <typename Real>
+struct LsmArgs {
+  const Real* paths;
+  int64_t stride_path, stride_time, stride_dim, stride_batch;
+  Real* w;              // [B][N]
+  uint64_t num_paths;   // local
+  uint64_t path_offset; // global index of local path 0
+  uint64_t num_calib;   // regression uses global paths < num_calib
+  int dim, K, batch;
+  const int* exponents;    // device [K][dim]
+  const double* strikes;   // device [B]
+  // update part
+  int do_update, t_update;
+  const double* mean_update;  // device [B][dim]
+  const double* beta;         // device [B][K]
+  const double* ratio_update; // device [B]
+  // accumulate part
+  int do_acc, t_acc;
+  const double* mean_acc;     // device [B][dim]
+  const double* ratio_acc;    // device [B]
+  double* partials;           // device [gridDim.x][B][NS]
+  int NS;
+};
+
+template <typename Real>
+__device__ __forceinline__ Real lsm_payoff(const LsmArgs<Real>& A, const Real* xp, int b) {
+  // relu(strike - mean_j x_j) (payoff_utils.py:95-97)
+  Real s = 0;
+  for (int j = 0; j < A.dim; ++j) s += xp[j * A.stride_dim];
+  const Real avg = s / static_cast<Real>(A.dim);
+  const Real v = static_cast<Real>(A.strikes[b]) - avg;
+  return v > Real(0) ? v : Real(0);
+}
+
+// phi[k] = prod_j (x_j - mean_j)^e[k][j]  (lsm.py:110-124)
+template <typename Real>
+__device__ __forceinline__ void lsm_basis(const LsmArgs<Real>& A, const Real* xp,
+                                          const double* mean, Real* phi) {
+  if (A.dim == 1) {
+    const Real c = xp[0] - static_cast<Real>(mean[0]);
+    // exponents of the 1-d basis are 0..K-1 in order
+    Real p = 1;
+    for (int k = 0; k < A.K; ++k) {
+      phi[k] = p;
+      p *= c;
+    }
+    return;
+  }
+  Real c[kLsmMaxDim];
+  for (int j = 0; j < A.dim; ++j) c[j] = xp[j * A.stride_dim] - static_cast<Real>(mean[j]);
+  for (int k = 0; k < A.K; ++k) {
+    Real p = 1;
+    for (int j = 0; j < A.dim; ++j) {
+      const int e = A.exponents[k * A.dim + j];
+      Real q = 1;
+      for (int i = 0; i < e; ++i) q *= c[j];
+      p *= q;
+    }
+    phi[k] = p;
+  }
+}
+
+// Fast path: K <= 6, accumulators in registers.  grid = (blocks, B).
+template <typename Real>
+__global__ void __launch_bounds__(kLsmBlock) lsm_step_fast_kernel(const LsmArgs<Real> A) {
+  const int b = blockIdx.y;
+  const int K = A.K;
+  const Real* base = A.paths + b * A.stride_batch;
+  Real* w = A.w + static_cast<size_t>(b) * A.num_paths;
+  double acc[kLsmFastNS];
+#pragma unroll
+  for (int i = 0; i < kLsmFastNS; ++i) acc[i] = 0.0;
+  double beta[kLsmFastK];
+#pragma unroll
+  for (int k = 0; k < kLsmFastK; ++k) beta[k] = (A.do_update && k < K) ? A.beta[b * K + k] : 0.0;
+  const Real ratio_u = A.do_update ? static_cast<Real>(A.ratio_update[b]) : Real(1);
+  const Real ratio_a = A.do_acc ? static_cast<Real>(A.ratio_acc[b]) : Real(1);
+
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t n = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; n < A.num_paths;
+       n += stride) {
+    const Real* xn = base + static_cast<int64_t>(n) * A.stride_path;
+    Real wn = w[n];
+    Real phi[kLsmFastK];
+    if (A.do_update) {
+      const Real* xp = xn + A.t_update * A.stride_time;
+      const Real ev = lsm_payoff(A, xp, b);
+      lsm_basis(A, xp, A.mean_update + b * A.dim, phi);
+      // continuation = relu(X beta) evaluated in the working dtype
+      Real cont = 0;
+#pragma unroll
+      for (int k = 0; k < kLsmFastK; ++k)
+        if (k < K) cont += phi[k] * static_cast<Real>(beta[k]);
+      cont = cont > Real(0) ? cont : Real(0);
+      wn = ev > cont ? ev : ratio_u * wn;
+      w[n] = wn;
+    }
+    if (A.do_acc) {
+      const Real* xp = xn + A.t_acc * A.stride_time;
+      const Real ev = lsm_payoff(A, xp, b);
+      const bool use = ev > Real(0) && (A.path_offset + n) < A.num_calib;
+      if (use) {
+        lsm_basis(A, xp, A.mean_acc + b * A.dim, phi);
+        const double y = static_cast<double>(ratio_a * wn);
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < kLsmFastK; ++i) {
+#pragma unroll
+          for (int j = i; j < kLsmFastK; ++j) {
+            if (j < K && i < K)
+              acc[idx] += static_cast<double>(phi[i]) * static_cast<double>(phi[j]);
+            ++idx;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kLsmFastK; ++i)
+          if (i < K) acc[kLsmFastK * (kLsmFastK + 1) / 2 + i] += static_cast<double>(phi[i]) * y;
+      }
+    }
+  }
+  if (A.do_acc) {
+    __shared__ double s_red[kLsmBlock / 32][kLsmFastNS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < kLsmFastNS; ++i) {
+      const double v = warp_sum(acc[i]);
+      if (lane == 0) s_red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLsmFastNS) {
+      double v = 0.0;
+      for (int wi = 0; wi < kLsmBlock / 32; ++wi) v += s_red[wi][threadIdx.x];
+      A.partials[(static_cast<size_t>(blockIdx.x) * A.batch + b) * kLsmFastNS + threadIdx.x] = v;
+    }
+  }
+}
+
+// Generic path (K <= 128): the update is per thread, the outer products are
+// formed tile by tile from shared memory.  grid = (blocks, B); NS = K*K + K.
+template <typename Real>
+__global__ void __launch_bounds__(kLsmBlock) lsm_step_generic_kernel(const LsmArgs<Real> A) {
+  extern __shared__ double s_gen[];   // [kLsmTile][K] phi, [kLsmTile] y
+  const int b = blockIdx.y;
+  const int K = A.K;
+  const Real* base = A.paths + b * A.stride_batch;
+  Real* w = A.w + static_cast<size_t>(b) * A.num_paths;
+  double* s_phi = s_gen;
+  double* s_y = s_gen + kLsmTile * K;
+  const int NS = K * K + K;
+  double* out = A.partials + (static_cast<size_t>(blockIdx.x) * A.batch + b) * NS;
+  for (int i = threadIdx.x; i < NS; i += blockDim.x) out[i] = 0.0;
+  const Real ratio_u = A.do_update ? static_cast<Real>(A.ratio_update[b]) : Real(1);
+  const Real ratio_a = A.do_acc ? static_cast<Real>(A.ratio_acc[b]) : Real(1);
+  Real phi[kLsmMaxK];
+  const uint64_t tiles = (A.num_paths + kLsmTile - 1) / kLsmTile;
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < kLsmTile) {
+      const uint64_t n = tile * kLsmTile + threadIdx.x;
+      bool use = false;
+      double y = 0.0;
+      if (n < A.num_paths) {
+        const Real* xn = base + static_cast<int64_t>(n) * A.stride_path;
+        Real wn = w[n];
+        if (A.do_update) {
+          const Real* xp = xn + A.t_update * A.stride_time;
+          const Real ev = lsm_payoff(A, xp, b);
+          lsm_basis(A, xp, A.mean_update + b * A.dim, phi);
+          Real cont = 0;
+          for (int k = 0; k < K; ++k) cont += phi[k] * static_cast<Real>(A.beta[b * K + k]);
+          cont = cont > Real(0) ? cont : Real(0);
+          wn = ev > cont ? ev : ratio_u * wn;
+          w[n] = wn;
+        }
+        if (A.do_acc) {
+          const Real* xp = xn + A.t_acc * A.stride_time;
+          const Real ev = lsm_payoff(A, xp, b);
+          use = ev > Real(0) && (A.path_offset + n) < A.num_calib;
+          if (use) {
+            lsm_basis(A, xp, A.mean_acc + b * A.dim, phi);
+            y = static_cast<double>(ratio_a * wn);
+          }
+        }
+      }
+      for (int k = 0; k < K; ++k) s_phi[threadIdx.x * K + k] = use ? static_cast<double>(phi[k]) : 0.0;
+      s_y[threadIdx.x] = use ? y : 0.0;
+    }
+    __syncthreads();
+    if (A.do_acc) {
+      for (int e = threadIdx.x; e < NS; e += blockDim.x) {
+        double v = 0.0;
+        if (e < K * K) {
+          const int i = e / K, j = e - i * K;
+          for (int p = 0; p < kLsmTile; ++p) v += s_phi[p * K + i] * s_phi[p * K + j];
+        } else {
+          const int i = e - K * K;
+          for (int p = 0; p < kLsmTile; ++p) v += s_phi[p * K + i] * s_y[p];
+        }
+        out[e] += v;
+      }
+    }
+  }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(kLsmBlock) lsm_init_kernel(const LsmArgs<Real> A, int t_index) {
+  const int b = blockIdx.y;
+  const Real* base = A.paths + b * A.stride_batch;
+  Real* w = A.w + static_cast<size_t>(b) * A.num_paths;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t n = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; n < A.num_paths;
+       n += stride) {
+    const Real* xp = base + static_cast<int64_t>(n) * A.stride_path + t_index * A.stride_time;
+    w[n] = lsm_payoff(A, xp, b);
+  }
+}
+
+// Column sums sum_n x[n, t, j] for the basis centring (lsm.py:110-111).
+// grid = (blocks, num_columns, B); column c = (time slot, dim j).
+template <typename Real>
+__global__ void __launch_bounds__(kLsmBlock) lsm_colsum_kernel(const LsmArgs<Real> A,
+                                                               const int* time_indices,
+                                                               int num_times, double* partials) {
+  const int c = blockIdx.y, b = blockIdx.z;
+  const int ti = c / A.dim, j = c - ti * A.dim;
+  const Real* base = A.paths + b * A.stride_batch + time_indices[ti] * A.stride_time +
+                     j * A.stride_dim;
+  double s = 0.0;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t n = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; n < A.num_paths;
+       n += stride)
+    s += static_cast<double>(base[static_cast<int64_t>(n) * A.stride_path]);
+  __shared__ double s_red[kLsmBlock / 32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int wi = 0; wi < kLsmBlock / 32; ++wi) v += s_red[wi];
+    partials[(static_cast<size_t>(blockIdx.x) * A.batch + b) * (num_times * A.dim) + c] = v;
+  }
+}
+
+// sum_n W[b][n] over the non-calibration paths -> partials [grid][B][2].
+template <typename Real>
+__global__ void __launch_bounds__(kLsmBlock) lsm_wsum_kernel(const LsmArgs<Real> A,
+                                                             uint64_t skip_below,
+                                                             double* partials) {
+  const int b = blockIdx.y;
+  const Real* w = A.w + static_cast<size_t>(b) * A.num_paths;
+  double s = 0.0, cnt = 0.0;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t n = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; n < A.num_paths;
+       n += stride) {
+    if (A.path_offset + n >= skip_below) {
+      s += static_cast<double>(w[n]);
+      cnt += 1.0;
+    }
+  }
+  __shared__ double s_red[2][kLsmBlock / 32];
+  s = warp_sum(s);
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) {
+    s_red[0][threadIdx.x >> 5] = s;
+    s_red[1][threadIdx.x >> 5] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double v = 0.0;
+    for (int wi = 0; wi < kLsmBlock / 32; ++wi) v += s_red[threadIdx.x][wi];
+    partials[(static_cast<size_t>(blockIdx.x) * A.batch + b) * 2 + threadIdx.x] = v;
+  }
+}
+
+// sums[m] = sum_blocks partials[block][m], fixed order.
+__global__ void lsm_reduce_kernel(const double* __restrict__ partials, int num_blocks, int M,
+                                  double* __restrict__ sums) {
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int bk = 0; bk < num_blocks; ++bk) v += partials[static_cast<size_t>(bk) * M + m];
+    sums[m] = v;
+  }
+}
+
+}  // namespace tqf
+
+using namespace tqf;
+
+struct tqf_lsm {
+  tqf_lsm_desc desc;
+  int K, NS, grid;
+  bool fast;
+  void* w_dev;           // Real [B][N]
+  int* exponents_dev;    // [K][dim]
+  double* strikes_dev;   // [B]
+  double* small_dev;     // staging: mean_u [B][dim] | mean_a [B][dim] | beta [B][K] | ratio_u [B] | ratio_a [B]
+  double* partials_dev;  // [grid][B][max(NS, T*dim, 2)]
+  size_t partials_doubles;
+  int* times_dev;
+  int times_cap;
+};
+
+template <typename Real>
+static void fill_args(const tqf_lsm* h, LsmArgs<Real>* A) {
+  std::memset(A, 0, sizeof(*A));
+  const tqf_lsm_desc& d = h->desc;
+  A->paths = static_cast<const Real*>(d.paths_dev);
+  A->stride_path = d.stride_path;
+  A->stride_time = d.stride_time;
+  A->stride_dim = d.stride_dim;
+  A->stride_batch = d.stride_batch;
+  A->w = static_cast<Real*>(h->w_dev);
+  A->num_paths = d.num_paths;
+  A->path_offset = d.path_offset;
+  A->num_calib = d.num_calibration_samples == 0 ? ~0ull : d.num_calibration_samples;
+  A->dim = d.dim;
+  A->K = h->K;
+  A->batch = d.batch;
+  A->exponents = h->exponents_dev;
+  A->strikes = h->strikes_dev;
+  A->partials = h->partials_dev;
+  A->NS = h->NS;
+}
+
+static int ensure_partials(tqf_lsm* h, size_t doubles) {
+  if (doubles <= h->partials_doubles) return TQF_OK;
+  cudaFree(h->partials_dev);
+  h->partials_dev = nullptr;
+  h->partials_doubles = 0;
+  TQF_CUDA_OK(cudaMalloc(&h->partials_dev, doubles * sizeof(double)));
+  h->partials_doubles = doubles;
+  return TQF_OK;
+}
+
+template <typename Real>
+static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* mean_update,
+                         const double* beta, const double* ratio_update, int do_acc, int t_acc,
+                         const double* mean_acc, const double* ratio_acc, double* sums_dev,
+                         cudaStream_t s) {
+  const tqf_lsm_desc& d = h->desc;
+  const int B = d.batch, K = h->K, dim = d.dim;
+  // stage the small host arrays
+  std::vector<double> small(static_cast<size_t>(2 * B * dim + B * K + 2 * B), 0.0);
+  double* p = small.data();
+  double* mu = p;  p += B * dim;
+  double* ma = p;  p += B * dim;
+  double* be = p;  p += B * K;
+  double* ru = p;  p += B;
+  double* ra = p;
+  if (do_update) {
+    std::memcpy(mu, mean_update, sizeof(double) * B * dim);
+    std::memcpy(be, beta, sizeof(double) * B * K);
+    std::memcpy(ru, ratio_update, sizeof(double) * B);
+  }
+  if (do_acc) {
+    std::memcpy(ma, mean_acc, sizeof(double) * B * dim);
+    std::memcpy(ra, ratio_acc, sizeof(double) * B);
+  }
+  TQF_CUDA_OK(cudaMemcpyAsync(h->small_dev, small.data(), small.size() * sizeof(double),
+                              cudaMemcpyHostToDevice, s));
+  LsmArgs<Real> A;
+  fill_args(h, &A);
+  A.do_update = do_update;
+  A.t_update = t_update;
+  A.mean_update = h->small_dev;
+  A.mean_acc = h->small_dev + B * dim;
+  A.beta = h->small_dev + 2 * B * dim;
+  A.ratio_update = h->small_dev + 2 * B * dim + B * K;
+  A.ratio_acc = A.ratio_update + B;
+  A.do_acc = do_acc;
+  A.t_acc = t_acc;
+  int rc = ensure_partials(h, static_cast<size_t>(h->grid) * B * h->NS);
+  if (rc != TQF_OK) return rc;
+  A.partials = h->partials_dev;
+  const dim3 grid(h->grid, B);
+  if (h->fast) {
+    lsm_step_fast_kernel<Real><<<grid, kLsmBlock, 0, s>>>(A);
+  } else {
+    const size_t smem = (static_cast<size_t>(kLsmTile) * K + kLsmTile) * sizeof(double);
+    lsm_step_generic_kernel<Real><<<grid, kLsmBlock, smem, s>>>(A);
+  }
+  TQF_CUDA_OK(cudaGetLastError());
+  if (do_acc) {
+    const int M = B * h->NS;
+    lsm_reduce_kernel<<<(M + 127) / 128, 128, 0, s>>>(h->partials_dev, h->grid, M, sums_dev);
+    TQF_CUDA_OK(cudaGetLastError());
+  }
+  return TQF_OK;
+}
+
+extern "C" {
+
+int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
+  TQF_REQUIRE(desc && out, "null argument");
+  *out = nullptr;
+  TQF_REQUIRE(desc->dtype == TQF_F32 || desc->dtype == TQF_F64, "bad dtype");
+  TQF_REQUIRE(desc->dim >= 1 && desc->dim <= kLsmMaxDim, "dim must be in [1, 8]");
+  TQF_REQUIRE(desc->batch >= 1, "batch must be >= 1");
+  TQF_REQUIRE(desc->basis_size >= 1 && desc->basis_size <= kLsmMaxK,
+              "basis size must be in [1, 128]");
+  TQF_REQUIRE(desc->exponents && desc->strikes && desc->paths_dev, "null pointer in descriptor");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: libtqf has no CPU fallback");
+    return TQF_ERR_CUDA;
+  }
+  tqf_lsm* h = new (std::nothrow) tqf_lsm();
+  TQF_REQUIRE(h, "out of memory");
+  std::memset(h, 0, sizeof(*h));
+  h->desc = *desc;
+  h->K = desc->basis_size;
+  // the register path assumes the 1-d exponent order 0..K-1 or takes any
+  // exponents for dim > 1 through lsm_basis
+  h->fast = h->K <= kLsmFastK;
+  h->NS = h->fast ? kLsmFastNS : h->K * h->K + h->K;
+  int sms = kSMs;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  uint64_t blocks = (desc->num_paths + kLsmBlock - 1) / kLsmBlock;
+  const uint64_t cap = static_cast<uint64_t>(sms) * (h->fast ? 8 : 2);
+  h->grid = static_cast<int>(blocks < cap ? (blocks ? blocks : 1) : cap);
+  const size_t esize = desc->dtype == TQF_F64 ? 8 : 4;
+  cudaError_t e = cudaMalloc(&h->w_dev, esize * desc->batch * (desc->num_paths ? desc->num_paths : 1));
+  if (e == cudaSuccess) e = cudaMalloc(&h->exponents_dev, sizeof(int) * h->K * desc->dim);
+  if (e == cudaSuccess) e = cudaMalloc(&h->strikes_dev, sizeof(double) * desc->batch);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&h->small_dev,
+                   sizeof(double) * (2 * desc->batch * desc->dim + desc->batch * h->K + 2 * desc->batch));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(h->exponents_dev, desc->exponents, sizeof(int) * h->K * desc->dim,
+                   cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(h->strikes_dev, desc->strikes, sizeof(double) * desc->batch,
+                   cudaMemcpyHostToDevice);
+  h->desc.exponents = nullptr;
+  h->desc.strikes = nullptr;
+  if (e != cudaSuccess) {
+    tqf_lsm_destroy(h);
+    return cuda_fail(e, "tqf_lsm_create");
+  }
+  *out = h;
+  return TQF_OK;
+}
+
+int tqf_lsm_destroy(tqf_lsm* h) {
+  if (!h) return TQF_OK;
+  cudaFree(h->w_dev);
+  cudaFree(h->exponents_dev);
+  cudaFree(h->strikes_dev);
+  cudaFree(h->small_dev);
+  cudaFree(h->partials_dev);
+  cudaFree(h->times_dev);
+  delete h;
+  return TQF_OK;
+}
+
+int tqf_lsm_column_sums(tqf_lsm* h, const int32_t* time_indices, int num_times, double* sums_dev,
+                        void* stream) {
+  TQF_REQUIRE(h && time_indices && sums_dev && num_times >= 1, "bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const tqf_lsm_desc& d = h->desc;
+  if (num_times > h->times_cap) {
+    cudaFree(h->times_dev);
+    h->times_dev = nullptr;
+    TQF_CUDA_OK(cudaMalloc(&h->times_dev, sizeof(int) * num_times));
+    h->times_cap = num_times;
+  }
+  TQF_CUDA_OK(cudaMemcpyAsync(h->times_dev, time_indices, sizeof(int) * num_times,
+                              cudaMemcpyHostToDevice, s));
+  const int cols = num_times * d.dim;
+  const int gx = h->grid < 64 ? h->grid : 64;
+  int rc = ensure_partials(h, static_cast<size_t>(gx) * d.batch * cols);
+  if (rc != TQF_OK) return rc;
+  const dim3 grid(gx, cols, d.batch);
+  if (d.dtype == TQF_F64) {
+    LsmArgs<double> A;
+    fill_args(h, &A);
+    lsm_colsum_kernel<double><<<grid, kLsmBlock, 0, s>>>(A, h->times_dev, num_times, h->partials_dev);
+  } else {
+    LsmArgs<float> A;
+    fill_args(h, &A);
+    lsm_colsum_kernel<float><<<grid, kLsmBlock, 0, s>>>(A, h->times_dev, num_times, h->partials_dev);
+  }
+  TQF_CUDA_OK(cudaGetLastError());
+  const int M = d.batch * cols;
+  lsm_reduce_kernel<<<(M + 127) / 128, 128, 0, s>>>(h->partials_dev, gx, M, sums_dev);
+  TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
+}
+
+int tqf_lsm_init(tqf_lsm* h, int time_index, void* stream) {
+  TQF_REQUIRE(h, "null handle");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const dim3 grid(h->grid, h->desc.batch);
+  if (h->desc.dtype == TQF_F64) {
+    LsmArgs<double> A;
+    fill_args(h, &A);
+    lsm_init_kernel<double><<<grid, kLsmBlock, 0, s>>>(A, time_index);
+  } else {
+    LsmArgs<float> A;
+    fill_args(h, &A);
+    lsm_init_kernel<float><<<grid, kLsmBlock, 0, s>>>(A, time_index);
+  }
+  TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
+}
+
+int tqf_lsm_step(tqf_lsm* h, int do_update, int t_update, const double* mean_update,
+                 const double* beta, const double* ratio_update, int do_accumulate, int t_acc,
+                 const double* mean_acc, const double* ratio_acc, double* sums_dev, void* stream) {
+  TQF_REQUIRE(h, "null handle");
+  TQF_REQUIRE(!do_update || (mean_update && beta && ratio_update), "null update argument");
+  TQF_REQUIRE(!do_accumulate || (mean_acc && ratio_acc && sums_dev), "null accumulate argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return h->desc.dtype == TQF_F64
+             ? lsm_step_impl<double>(h, do_update, t_update, mean_update, beta, ratio_update,
+                                     do_accumulate, t_acc, mean_acc, ratio_acc, sums_dev, s)
+             : lsm_step_impl<float>(h, do_update, t_update, mean_update, beta, ratio_update,
+                                    do_accumulate, t_acc, mean_acc, ratio_acc, sums_dev, s);
+}
+
+int tqf_lsm_sums_layout(const tqf_lsm* h, int* num_sums, int* is_packed_symmetric) {
+  TQF_REQUIRE(h && num_sums && is_packed_symmetric, "null argument");
+  *num_sums = h->NS;
+  *is_packed_symmetric = h->fast ? 1 : 0;
+  return TQF_OK;
+}
+
+int tqf_lsm_value_sum(tqf_lsm* h, uint64_t skip_below, double* sums_dev, void* stream) {
+  TQF_REQUIRE(h && sums_dev, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const tqf_lsm_desc& d = h->desc;
+  int rc = ensure_partials(h, static_cast<size_t>(h->grid) * d.batch * 2);
+  if (rc != TQF_OK) return rc;
+  const dim3 grid(h->grid, d.batch);
+  if (d.dtype == TQF_F64) {
+    LsmArgs<double> A;
+    fill_args(h, &A);
+    lsm_wsum_kernel<double><<<grid, kLsmBlock, 0, s>>>(A, skip_below, h->partials_dev);
+  } else {
+    LsmArgs<float> A;
+    fill_args(h, &A);
+    lsm_wsum_kernel<float><<<grid, kLsmBlock, 0, s>>>(A, skip_below, h->partials_dev);
+  }
+  TQF_CUDA_OK(cudaGetLastError());
+  const int M = d.batch * 2;
+  lsm_reduce_kernel<<<1, 128, 0, s>>>(h->partials_dev, h->grid, M, sums_dev);
+  TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
+}
+
+}  // extern "C"

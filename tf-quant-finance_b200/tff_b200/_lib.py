@@ -89,6 +89,25 @@ class PayoffDesc(C.Structure):
   ]
 
 
+class LsmDesc(C.Structure):
+  _fields_ = [
+      ('dtype', C.c_int32),
+      ('dim', C.c_int32),
+      ('batch', C.c_int32),
+      ('basis_size', C.c_int32),
+      ('exponents', C.c_void_p),
+      ('strikes', C.c_void_p),
+      ('num_paths', C.c_uint64),
+      ('path_offset', C.c_uint64),
+      ('num_calibration_samples', C.c_uint64),
+      ('paths_dev', C.c_void_p),
+      ('stride_path', C.c_int64),
+      ('stride_time', C.c_int64),
+      ('stride_dim', C.c_int64),
+      ('stride_batch', C.c_int64),
+  ]
+
+
 class TqfError(RuntimeError):
   """A libtqf call failed (status code + tqf_last_error())."""
 
@@ -130,6 +149,17 @@ _SIGNATURES = {
     'tqf_plan_paths':
         (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                    C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    'tqf_lsm_create': (C.c_int, [C.POINTER(LsmDesc), C.POINTER(C.c_void_p)]),
+    'tqf_lsm_destroy': (C.c_int, [C.c_void_p]),
+    'tqf_lsm_column_sums':
+        (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'tqf_lsm_init': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    'tqf_lsm_step':
+        (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'tqf_lsm_sums_layout':
+        (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'tqf_lsm_value_sum': (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     'tqf_math_eval':
         (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     'tqf_measure_fp64_peak':

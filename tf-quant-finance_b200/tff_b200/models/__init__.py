@@ -2,6 +2,7 @@
 from tff_b200.models import closures
 from tff_b200.models import euler_sampling
 from tff_b200.models import hull_white
+from tff_b200.models import longstaff_schwartz
 from tff_b200.models import utils
 from tff_b200.models.generic_ito_process import GenericItoProcess
 from tff_b200.models.geometric_brownian_motion.univariate_geometric_brownian_motion import GeometricBrownianMotion
@@ -11,4 +12,4 @@ from tff_b200.models.ito_process import ItoProcess
 
 __all__ = ['closures', 'euler_sampling', 'utils', 'GenericItoProcess',
            'GeometricBrownianMotion', 'HestonModel', 'HullWhiteModel1F', 'ItoProcess',
-           'hull_white']
+           'hull_white', 'longstaff_schwartz']

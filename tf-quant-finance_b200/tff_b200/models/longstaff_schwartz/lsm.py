@@ -1,0 +1,203 @@
+"""Longstaff-Schwartz least-squares Monte Carlo on the device
+(`tf_quant_finance/models/longstaff_schwartz/lsm.py`).
+
+Per exercise date the reference runs payoff_fn, basis_fn, two matmuls, a
+pseudo-inverse and several `tf.where` passes over `[N]` tensors.  Here one
+streaming kernel per date updates the merged state W = cashflow + values and
+accumulates the normal equations of the next (earlier) date; the K x K
+pseudo-inverse (numpy, rcond 10 K eps as `tf.linalg.pinv`) runs on the reduced
+sums, after the all-reduce when paths are sharded over GPUs.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from tff_b200 import _lib
+from tff_b200 import _tensor
+from tff_b200.models.longstaff_schwartz import payoff_utils
+
+
+class PolynomialBasis:
+  """All monomials prod_j (x_j - mean_j)^{k_j}, 0 <= k_j <= degree
+  (`lsm.py:50-125`).  Callable on the host like the reference's `basis`."""
+
+  def __init__(self, degree):
+    self.degree = int(degree)
+
+  def exponents(self, dim):
+    grid = np.arange(self.degree + 1)
+    mesh = np.meshgrid(*(dim * [grid]))                     # 'xy' like tf.meshgrid
+    return np.stack(mesh, -1).reshape(-1, dim).astype(np.int32)
+
+  def __call__(self, sample_paths, time_index):
+    x = sample_paths if isinstance(sample_paths, torch.Tensor) else torch.as_tensor(
+        np.asarray(sample_paths))
+    if x.dim() == 3:
+      x = x.unsqueeze(0)
+    sl = x[:, :, int(time_index):int(time_index) + 1, :]
+    c = sl - sl.mean(dim=1, keepdim=True)
+    e = torch.as_tensor(self.exponents(x.shape[-1]), dtype=x.dtype, device=x.device)
+    return torch.prod(c**e, dim=-1).permute(0, 2, 1)
+
+
+def make_polynomial_basis(degree):
+  """Produces a callable from samples to a polynomial basis (`lsm.py:50-125`)."""
+  return PolynomialBasis(degree)
+
+
+def _unpack_sums(sums, K, packed):
+  """[B, NS] reduced sums -> (lhs [B, K, K], rhs [B, K])."""
+  B = sums.shape[0]
+  if not packed:
+    return sums[:, :K * K].reshape(B, K, K), sums[:, K * K:K * K + K]
+  lhs = np.zeros((B, K, K))
+  idx = 0
+  for i in range(6):
+    for j in range(i, 6):
+      if i < K and j < K:
+        lhs[:, i, j] = sums[:, idx]
+        lhs[:, j, i] = sums[:, idx]
+      idx += 1
+  return lhs, sums[:, 21:21 + K]
+
+
+def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
+                    discount_factors=None, num_calibration_samples=None,
+                    dtype=None, name=None, *, global_path_offset=0,
+                    all_reduce=None):
+  """Values Amercian style options using the LSM algorithm (`lsm.py:128-295`).
+
+  Args are those of the reference; `exercise_times` are indices into the time
+  axis of `sample_paths` (`[num_samples, num_times, dim]` or
+  `[batch_size, num_samples, num_times, dim]`, a CUDA tensor -- e.g. the
+  time-major view returned by the path engine -- or anything DLPack/numpy).
+  `payoff_fn` / `basis_fn` must come from `make_basket_put_payoff` /
+  `make_polynomial_basis` (arbitrary Python callables cannot run in a kernel).
+
+  Extension for sharded paths: `global_path_offset` is the global index of the
+  first local path and `all_reduce(tensor)` sums a device tensor in place over
+  the ranks (e.g. `torch.distributed.all_reduce`).
+
+  Returns a numpy array `[batch_size]`.
+  """
+  del name
+  if not isinstance(payoff_fn, payoff_utils.BasketPutPayoff) or not isinstance(
+      basis_fn, PolynomialBasis):
+    raise NotImplementedError(
+        'The B200 LSM passes evaluate the payoff and the basis inside CUDA '
+        'kernels: use make_basket_put_payoff(strikes) and '
+        'make_polynomial_basis(degree). There is no CPU fallback.')
+  if isinstance(sample_paths, torch.Tensor) or hasattr(sample_paths, '__dlpack__'):
+    x = _tensor.from_dlpack(sample_paths)
+    if dtype is not None:
+      x = x.to(_tensor.torch_dtype(_tensor.np_dtype(dtype)))
+  else:
+    x = torch.as_tensor(_tensor.to_numpy(sample_paths, None if dtype is None
+                                         else _tensor.np_dtype(dtype)))
+  x = x.to(_tensor.device())
+  dt = _tensor.np_dtype(x.dtype)
+  batched = x.dim() == 4
+  if x.dim() not in (3, 4):
+    raise ValueError('sample_paths must have rank 3 or 4')
+  n_local, dim = int(x.shape[-3]), int(x.shape[-1])
+  strikes = payoff_fn.strikes.astype(np.float64)
+  B = int(x.shape[0]) if batched else strikes.shape[0]
+  if batched and strikes.shape[0] not in (1, B):
+    raise ValueError('strikes batch does not match the batch of sample paths')
+  strikes = np.ascontiguousarray(np.broadcast_to(strikes, (B,)))
+  ex_times = np.asarray(_tensor.to_numpy(exercise_times)).astype(np.int64).reshape(-1)
+  T = ex_times.shape[0]
+
+  # discount factors: [T+1, B] with a leading 1 (lsm.py:239-256)
+  if discount_factors is None:
+    df = np.ones((1, 1, T), dtype=dt)
+  else:
+    df = _tensor.to_numpy(discount_factors, dt)
+  if df.ndim == 0:
+    df = df.reshape(1, 1, 1)
+  if df.ndim == 1:
+    df = df.reshape(1, 1, -1)
+  if df.ndim != 3:
+    raise NotImplementedError('discount_factors must have rank 0, 1 or 3')
+  if df.shape[0] != 1:
+    raise NotImplementedError(
+        'per-sample discount factors are not implemented by the B200 engine')
+  df = np.concatenate([np.ones(df.shape[:2] + (1,), dtype=dt), df], axis=-1)
+  df = np.broadcast_to(np.transpose(df, [2, 0, 1])[:, 0, :], (df.shape[-1], B))
+  ratio = (df[1:] / df[:-1]).astype(dt).astype(np.float64)        # [T, B]
+
+  exps = np.ascontiguousarray(basis_fn.exponents(dim), dtype=np.int32)
+  K = exps.shape[0]
+  stream = _tensor.current_stream_ptr()
+  d = _lib.LsmDesc()
+  d.dtype, d.dim, d.batch, d.basis_size = _tensor.tqf_dtype(dt), dim, B, K
+  d.exponents, d.strikes = exps.ctypes.data, strikes.ctypes.data
+  d.num_paths, d.path_offset = n_local, int(global_path_offset)
+  d.num_calibration_samples = int(num_calibration_samples or 0)
+  d.paths_dev = x.data_ptr()
+  st = x.stride()
+  if batched:
+    d.stride_batch, d.stride_path, d.stride_time, d.stride_dim = st
+  else:
+    d.stride_batch = 0
+    d.stride_path, d.stride_time, d.stride_dim = st
+  handle = C.c_void_p()
+  lib = _lib.lib()
+  _lib.require_cuda()
+  _lib.check(lib.tqf_lsm_create(C.byref(d), C.byref(handle)))
+  try:
+    ns, packed = C.c_int(), C.c_int()
+    _lib.check(lib.tqf_lsm_sums_layout(handle, C.byref(ns), C.byref(packed)))
+    dev = x.device
+    # column means over ALL samples (lsm.py:110-111)
+    tidx = np.ascontiguousarray(ex_times, dtype=np.int32)
+    colsum = torch.zeros((B, T, dim), dtype=torch.float64, device=dev)
+    _lib.check(lib.tqf_lsm_column_sums(handle, tidx.ctypes.data, T,
+                                       colsum.data_ptr(), stream))
+    count = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
+    if all_reduce is not None:
+      all_reduce(colsum)
+      all_reduce(count)
+    n_total = float(count.item())
+    means = (colsum.cpu().numpy() / n_total).astype(dt).astype(np.float64)  # [B, T, dim]
+
+    def mean_at(e):          # exercise index e uses time slot e - 1
+      return np.ascontiguousarray(means[:, e - 1, :])
+
+    def ratio_at(e):
+      return np.ascontiguousarray(ratio[e])
+
+    _lib.check(lib.tqf_lsm_init(handle, int(ex_times[T - 1]), stream))
+    sums = torch.zeros((B, ns.value), dtype=torch.float64, device=dev)
+    e = T - 1
+    if e > 0:
+      ma, ra = mean_at(e), ratio_at(e)
+      _lib.check(lib.tqf_lsm_step(handle, 0, 0, None, None, None, 1,
+                                  int(ex_times[e - 1]), ma.ctypes.data,
+                                  ra.ctypes.data, sums.data_ptr(), stream))
+    rcond = 10 * K * np.finfo(dt).eps
+    while e > 0:
+      if all_reduce is not None:
+        all_reduce(sums)
+      lhs, rhs = _unpack_sums(sums.cpu().numpy(), K, bool(packed.value))
+      beta = np.stack([np.linalg.pinv(lhs[b].astype(dt), rcond=rcond).astype(np.float64)
+                       @ rhs[b].astype(dt).astype(np.float64) for b in range(B)])
+      beta = np.ascontiguousarray(beta.astype(dt).astype(np.float64))
+      mu, ru = mean_at(e), ratio_at(e)
+      do_acc = 1 if e - 1 > 0 else 0
+      ma, ra = (mean_at(e - 1), ratio_at(e - 1)) if do_acc else (mu, ru)
+      _lib.check(lib.tqf_lsm_step(
+          handle, 1, int(ex_times[e - 1]), mu.ctypes.data, beta.ctypes.data,
+          ru.ctypes.data, do_acc, int(ex_times[e - 2]) if do_acc else 0,
+          ma.ctypes.data, ra.ctypes.data, sums.data_ptr(), stream))
+      e -= 1
+    vs = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+    _lib.check(lib.tqf_lsm_value_sum(handle, int(num_calibration_samples or 0),
+                                     vs.data_ptr(), stream))
+    if all_reduce is not None:
+      all_reduce(vs)
+    vs = vs.cpu().numpy()
+  finally:
+    lib.tqf_lsm_destroy(handle)
+  return (ratio[0] * vs[:, 0] / vs[:, 1]).astype(dt)
