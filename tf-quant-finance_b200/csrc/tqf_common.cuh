@@ -119,7 +119,8 @@ __device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float* n0,
 // --------------------------------------------------------- inverse CDF ----
 // sqrt(2) erfinv(2u - 1) == ndtri(u) (multivariate_normal.py:420).
 __device__ __forceinline__ double ndtri(double u) { return fm::ndtri_q(u - 0.5); }
-__device__ __forceinline__ float ndtri(float u) { return normcdfinvf(u); }
+// (u - 0.5) * 2 as the reference forms it (multivariate_normal.py:420), exact in fp32.
+__device__ __forceinline__ float ndtri(float u) { return fm::ndtri_t_f32((u - 0.5f) * 2.0f); }
 
 // ------------------------------------------------------------- Sobol ------
 // Device table V[d][32]: direction number m[d][b] left-aligned in 32 bits,

@@ -314,6 +314,29 @@ __device__ __forceinline__ void sincos_2pi_v(const Tab& tab, const double (&v)[K
   }
 }
 
+// float32 inverse CDF: sqrt(2) erfinv(t) = t P(w), w = -log(1 - t^2), with the
+// SFU logarithm and float coefficients as FFMA immediates (~18 instructions).
+// t = +-1 (u rounded to 0 or 1) gives +-inf like the reference.
+__device__ __forceinline__ float ndtri_t_f32(float t) {
+  const float a = fmaf(-t, t, 1.0f);
+  const float w = -__logf(a);
+  float p;
+  if (w < 6.25f) {
+    const float c[TQF_NDTRI_F32_C_N] = {TQF_NDTRI_F32_C_LIST};
+    const float y = w - TQF_NDTRI_F32_C_MID;
+    p = c[0];
+#pragma unroll
+    for (int i = 1; i < TQF_NDTRI_F32_C_N; ++i) p = fmaf(p, y, c[i]);
+  } else {
+    const float c[TQF_NDTRI_F32_T_N] = {TQF_NDTRI_F32_T_LIST};
+    const float y = sqrtf(w) - TQF_NDTRI_F32_T_MID;
+    p = c[0];
+#pragma unroll
+    for (int i = 1; i < TQF_NDTRI_F32_T_N; ++i) p = fmaf(p, y, c[i]);
+  }
+  return t * p;
+}
+
 // scalar conveniences (fill kernels, test hook): coefficients straight from
 // the constant bank.
 __device__ __forceinline__ double log_pos(double a) {

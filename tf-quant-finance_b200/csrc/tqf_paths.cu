@@ -45,8 +45,9 @@ struct ModelInfo {
   int dim, nf, ncoef;
 };
 
-static bool model_info(int kind, ModelInfo* info) {
+static bool model_info(int kind, int dim, ModelInfo* info) {
   switch (kind) {
+    case TQF_MODEL_MVGBM: *info = {dim, dim, 2}; return dim >= 1 && dim <= 64;
     case TQF_MODEL_AFFINE_1F: *info = {1, 1, 5}; return true;
     case TQF_MODEL_GBM_1F: *info = {1, 1, 4}; return true;
     case TQF_MODEL_LINEAR_1F: *info = {1, 1, 5}; return true;
@@ -72,7 +73,9 @@ struct tqf_plan {
   double* partials_dev;     // [max_grid][TQF_MAX_PAYOFFS][4]
   int* record_dev;          // [num_steps+1]
   SwaptionK* swaptions_dev; // [TQF_MAX_PAYOFFS]
-  double x0[2];
+  double x0[64];
+  double mu[64], sigma[64];
+  double chol[64 * 64];
 };
 
 template <typename Real>
@@ -179,7 +182,16 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
       P.pay[q] = PayoffK{d.kind, 0, 0, step, 0.0, 0.0, d.scale};
       continue;
     }
-    TQF_REQUIRE(d.component >= 0 && d.component < plan->info.dim, "payoff component out of range");
+    if (plan->model.kind == TQF_MODEL_MVGBM) {
+      TQF_REQUIRE(d.component >= -1 && d.component < plan->info.dim,
+                  "payoff component out of range (-1 = basket mean)");
+      TQF_REQUIRE(d.kind == TQF_PAYOFF_CALL || d.kind == TQF_PAYOFF_PUT ||
+                      d.kind == TQF_PAYOFF_IDENTITY,
+                  "MVGBM supports call / put / identity payoffs");
+    } else {
+      TQF_REQUIRE(d.component >= 0 && d.component < plan->info.dim,
+                  "payoff component out of range");
+    }
     P.pay[q] = PayoffK{d.kind, d.component, d.transform, step, d.strike, d.barrier, d.scale};
     if (d.kind >= TQF_PAYOFF_UP_OUT_CALL && d.kind <= TQF_PAYOFF_DOWN_OUT_CALL) {
       TQF_REQUIRE(monitor < 0 || monitor == d.component,
@@ -202,6 +214,39 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   P.swaptions = plan->swaptions_dev;
   P.partials = plan->partials_dev;
   int grid = 1;
+  if (plan->model.kind == TQF_MODEL_MVGBM) {
+    TQF_REQUIRE(!plan->rng.antithetic && plan->rng.type != TQF_RNG_DRAWS,
+                "MVGBM supports the Philox and Sobol generators without antithetic pairing");
+    MvLaunch a;
+    std::memset(&a, 0, sizeof(a));
+    a.dtype = plan->model.dtype;
+    a.dim = plan->info.dim;
+    a.num_steps = S;
+    a.num_steps_total = plan->model.num_steps_total;
+    a.rngk = rng_kind(plan);
+    a.mode = MODE_PRICE;
+    a.max_grid = plan->max_grid;
+    a.coef_dev = plan->coef_dev;
+    a.x0 = plan->x0;
+    a.mu = plan->mu;
+    a.sigma = plan->sigma;
+    a.chol = plan->chol;
+    a.key = P.key;
+    a.ctr = P.ctr;
+    a.sobol_v = plan->sobol_dev;
+    a.first_index = P.first_index;
+    a.path_offset = path_offset;
+    a.path_count = path_count;
+    a.num_payoffs = num_payoffs;
+    a.pay = P.pay;
+    a.partials = plan->partials_dev;
+    a.record_dev = plan->record_dev;
+    int rc = launch_mvgbm(a, stream, &grid);
+    if (rc != TQF_OK) return rc;
+    reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev);
+    TQF_CUDA_OK(cudaGetLastError());
+    return TQF_OK;
+  }
   const int rk = rng_kind(plan);
   bool in_smem = true;
   size_t smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PRICE, true);
@@ -231,6 +276,37 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   P.stride_path = stride_path;
   P.stride_time = stride_time;
   P.stride_dim = stride_dim;
+  if (plan->model.kind == TQF_MODEL_MVGBM) {
+    TQF_REQUIRE(!plan->rng.antithetic && plan->rng.type != TQF_RNG_DRAWS,
+                "MVGBM supports the Philox and Sobol generators without antithetic pairing");
+    MvLaunch a;
+    std::memset(&a, 0, sizeof(a));
+    a.dtype = plan->model.dtype;
+    a.dim = plan->info.dim;
+    a.num_steps = plan->model.num_steps;
+    a.num_steps_total = plan->model.num_steps_total;
+    a.rngk = rng_kind(plan);
+    a.mode = MODE_PATHS;
+    a.max_grid = plan->max_grid;
+    a.coef_dev = plan->coef_dev;
+    a.x0 = plan->x0;
+    a.mu = plan->mu;
+    a.sigma = plan->sigma;
+    a.chol = plan->chol;
+    a.key = P.key;
+    a.ctr = P.ctr;
+    a.sobol_v = plan->sobol_dev;
+    a.first_index = P.first_index;
+    a.path_offset = path_offset;
+    a.path_count = path_count;
+    a.record_dev = plan->record_dev;
+    a.out = out_dev;
+    a.stride_path = stride_path;
+    a.stride_time = stride_time;
+    a.stride_dim = stride_dim;
+    int g = 1;
+    return launch_mvgbm(a, stream, &g);
+  }
   P.anti_half = path_count;  // rows of the antithetic partners follow the shard's own rows
   int grid = 1;
   const int rk = rng_kind(plan);
@@ -251,7 +327,7 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
   TQF_REQUIRE(model && rng && out_plan, "null argument");
   *out_plan = nullptr;
   ModelInfo info;
-  if (!model_info(model->kind, &info)) {
+  if (!model_info(model->kind, model->dim, &info)) {
     set_error("unknown model kind");
     return TQF_ERR_UNSUPPORTED;
   }
@@ -293,6 +369,19 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
   plan->info = info;
   plan->num_paths_total = num_paths_total;
   for (int j = 0; j < info.dim; ++j) plan->x0[j] = model->x0[j];
+  if (model->kind == TQF_MODEL_MVGBM) {
+    if (!model->matrix || !model->vector) {
+      delete plan;
+      set_error("MVGBM needs the Cholesky factor (matrix) and means / volatilities (vector)");
+      return TQF_ERR_INVALID_ARGUMENT;
+    }
+    for (int i = 0; i < info.dim; ++i) {
+      plan->mu[i] = model->vector[i];
+      plan->sigma[i] = model->vector[info.dim + i];
+      for (int j = 0; j < info.dim; ++j)
+        plan->chol[i * info.dim + j] = model->matrix[static_cast<size_t>(i) * info.dim + j];
+    }
+  }
   int rc = TQF_OK;
   cudaError_t e = cudaGetDevice(&plan->device);
   int sms = kSMs;

@@ -651,4 +651,26 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
   return TQF_ERR_UNSUPPORTED;
 }
 
+// Launch descriptor of the multi-asset GBM kernel (tqf_mvgbm.cu).
+struct MvLaunch {
+  int dtype, dim, num_steps, num_steps_total, rngk, mode, max_grid;
+  const void* coef_dev;      // Real [S][2]
+  const double* x0;          // host [dim]
+  const double* mu;          // host [dim]
+  const double* sigma;       // host [dim]
+  const double* chol;        // host [dim][dim] lower triangular
+  PhiloxKey key;
+  PhiloxCtr ctr;
+  const uint32_t* sobol_v;
+  uint64_t first_index, path_offset, path_count;
+  int num_payoffs;
+  const PayoffK* pay;
+  double* partials;
+  const int* record_dev;
+  void* out;
+  int64_t stride_path, stride_time, stride_dim;
+};
+
+int launch_mvgbm(const MvLaunch& a, cudaStream_t stream, int* grid_out);
+
 }  // namespace tqf

@@ -113,6 +113,35 @@ class HestonEulerSpec(ModelSpec):
     return np.stack(cols, -1).astype(np.float64)
 
 
+class MvGbmSpec(ModelSpec):
+  """Correlated multi-asset GBM closures
+  (`geometric_brownian_motion/multivariate_geometric_brownian_motion.py:130-151`):
+  a_i = mu_i x_i, S_ij = sigma_i x_i L_ij with L = cholesky(corr).  Table
+  columns: dt, sqrt_dt; the Cholesky factor and (mu, sigma) travel as kernel
+  parameters."""
+  kind, num_coef = _lib.MODEL_MVGBM, 2
+
+  def __init__(self, means, volatilities, corr_matrix, dim):
+    self.dim = self.num_factors = int(dim)
+    self.means, self.volatilities, self.corr_matrix = means, volatilities, corr_matrix
+
+  def coef_table(self, all_times, dtype):
+    _, dt, sq = self._dt_columns(all_times, dtype)
+    return np.stack([dt, sq], -1).astype(np.float64)
+
+  def device_arrays(self, dtype):
+    d = self.dim
+    mu = np.broadcast_to(np.asarray(self.means, dtype=dtype), (d,))
+    sg = np.broadcast_to(np.asarray(self.volatilities, dtype=dtype), (d,))
+    if self.corr_matrix is None:
+      chol = np.eye(d, dtype=dtype)
+    else:
+      chol = np.linalg.cholesky(np.asarray(self.corr_matrix, dtype=dtype)).astype(dtype)
+    mat = np.ascontiguousarray(chol, dtype=np.float64)
+    vec = np.ascontiguousarray(np.stack([mu, sg]), dtype=np.float64)
+    return mat, vec
+
+
 # --------------------------------------------------------------- payoffs ----
 class Payoff:
   """A payoff reduced in-kernel (the `tf.reduce_mean(tf.nn.relu(...))` tails

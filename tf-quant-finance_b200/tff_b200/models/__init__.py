@@ -5,11 +5,12 @@ from tff_b200.models import hull_white
 from tff_b200.models import longstaff_schwartz
 from tff_b200.models import utils
 from tff_b200.models.generic_ito_process import GenericItoProcess
+from tff_b200.models.geometric_brownian_motion.multivariate_geometric_brownian_motion import MultivariateGeometricBrownianMotion
 from tff_b200.models.geometric_brownian_motion.univariate_geometric_brownian_motion import GeometricBrownianMotion
 from tff_b200.models.heston.heston_model import HestonModel
 from tff_b200.models.hull_white.one_factor import HullWhiteModel1F
 from tff_b200.models.ito_process import ItoProcess
 
 __all__ = ['closures', 'euler_sampling', 'utils', 'GenericItoProcess',
-           'GeometricBrownianMotion', 'HestonModel', 'HullWhiteModel1F', 'ItoProcess',
+           'GeometricBrownianMotion', 'MultivariateGeometricBrownianMotion', 'HestonModel', 'HullWhiteModel1F', 'ItoProcess',
            'hull_white', 'longstaff_schwartz']

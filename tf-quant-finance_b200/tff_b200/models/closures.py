@@ -116,3 +116,25 @@ def heston_closures(mean_reversion, theta, volvol, rho):
     k, th = _p(mean_reversion, t, x), _p(theta, t, x)
     return torch.stack([-var / 2, k * (th - var)], -1)
   return DeviceClosure(spec, 'drift', drift), DeviceClosure(spec, 'volatility', vol)
+
+
+def mvgbm_closures(means, volatilities, corr_matrix, dim):
+  """(drift_fn, volatility_fn) of the correlated multi-asset GBM
+  (`multivariate_geometric_brownian_motion.py:130-151`)."""
+  spec = engine.MvGbmSpec(means, volatilities, corr_matrix, dim)
+
+  def drift(t, x):
+    del t
+    x = _as_tensor(x)
+    return torch.as_tensor(np.asarray(means), dtype=x.dtype, device=x.device) * x
+
+  def vol(t, x):
+    del t
+    x = _as_tensor(x)
+    vols = torch.as_tensor(np.asarray(volatilities), dtype=x.dtype, device=x.device) * x
+    if corr_matrix is None:
+      return torch.diag_embed(vols)
+    chol = torch.linalg.cholesky(torch.as_tensor(np.asarray(corr_matrix), dtype=x.dtype,
+                                                 device=x.device))
+    return vols.unsqueeze(-1) * chol
+  return DeviceClosure(spec, 'drift', drift), DeviceClosure(spec, 'volatility', vol)
