@@ -33,7 +33,7 @@ UNIT = 'path-steps/s'
 
 # Algorithmic FP64-pipe instructions per path-step (frozen; DESIGN.md section 5,
 # SURVEY.md 8(d)): C2 = 2 Sobol normals x 38 + Heston Euler update 20.
-ALGO_FP64_INSTR = {'c1': 27, 'c2': 96, 'c3': 48}
+ALGO_FP64_INSTR = {'c1': 27, 'c2': 96, 'c3': 48, 'c4': 3616, 'c5': 25}
 
 WORKLOADS = {
     'c1': dict(name='C1 GBM call (log-space affine), 100k paths x 100 steps, fp64, PSEUDO_ANTITHETIC seed 42',
@@ -42,6 +42,11 @@ WORKLOADS = {
                paths=10_000_000, steps=252, dtype='f64'),
     'c3': dict(name='C3 Hull-White 1F payer swaption (exact OU step + discount integral), 50M paths x 360 steps, fp64, Philox stateless seed [4,2]',
                paths=50_000_000, steps=360, dtype='f64'),
+    'c4': dict(name='C4 correlated 64-asset GBM basket call, 20M paths x 252 steps, fp32, Sobol + Cholesky',
+               paths=20_000_000, steps=252, dtype='f32'),
+    'c5': dict(name='C5 American put, Longstaff-Schwartz on log-GBM Euler paths, 8M paths x 50 exercise dates '
+                    '(148 Euler steps, time_step 0.01), fp64, STATELESS_ANTITHETIC seed [4,2], cubic basis',
+               paths=8_000_000, steps=148, dtype='f64'),
 }
 
 
@@ -104,6 +109,18 @@ def make_workload(name, num_paths=None):
         True, 100.0))]
     steps = int(e_idx)
     return spec, all_times, x0, rng, payoffs, n, steps
+  elif name == 'c4':
+    dim = 64
+    spec = engine.MvGbmSpec(np.full(dim, 0.03, np.float32),
+                            np.linspace(0.1, 0.4, dim).astype(np.float32),
+                            (0.3 + 0.7 * np.eye(dim)).astype(np.float32), dim)
+    times = np.array([1.0], dtype=np.float32)
+    all_times, mask, _ = utils.prepare_grid(
+        times=times, time_step=np.float32(1.0) / np.float32(252), num_time_steps=252,
+        dtype=np.float32)
+    x0 = 100.0 * np.ones(dim, dtype=np.float32)
+    rng = dict(random_type=rt.SOBOL, seed=None, skip=0)
+    payoffs = [engine.european_call(100.0, component=-1)]
   else:
     raise ValueError(name)
   steps, _ = engine.record_plan(mask, 1)
@@ -179,6 +196,29 @@ def _oracle_chunk(args):
         random_type=odraws.RandomType.STATELESS, seed=[4, 2 + skip],
         time_step=1.0 / 360, dtype=np.float64, return_payoffs=True)
     return float(payoff.sum()), 360
+  if name == 'c4':
+    dim = 64
+    d, v = omodels.mvgbm_closures(np.full(dim, 0.03, np.float32),
+                                  np.linspace(0.1, 0.4, dim).astype(np.float32),
+                                  (0.3 + 0.7 * np.eye(dim)).astype(np.float32), np.float32)
+    paths = oeuler.sample(dim, d, v, np.array([1.0], np.float32), num_time_steps=252,
+                          num_samples=count, initial_state=100.0 * np.ones(dim, np.float32),
+                          random_type=odraws.RandomType.SOBOL, skip=skip, dtype=np.float32)
+    return float(np.maximum(paths[:, 0, :].mean(axis=1) - 100.0, 0).sum()), 252
+  if name == 'c5':
+    from oracle import lsm as olsm
+    r, sigma = 0.1, 1.0
+    times = np.linspace(0.0, 1.0, 50)
+    paths = np.exp(oeuler.sample(
+        1, lambda t, x: (r - sigma**2 / 2) + 0 * x,
+        lambda t, x: sigma * np.ones(x.shape + (1,)), times, time_step=0.01,
+        num_samples=count, initial_state=np.array([0.0]),
+        random_type=odraws.RandomType.STATELESS_ANTITHETIC, seed=[4, 2 + skip],
+        dtype=np.float64))
+    price = olsm.least_square_mc(paths, np.arange(50), olsm.make_basket_put_payoff([1.1]),
+                                 olsm.make_polynomial_basis(3), np.exp(-r * times),
+                                 dtype=np.float64)
+    return float(price[0]) * count, 148
   raise ValueError(name)
 
 
@@ -210,7 +250,8 @@ def run_reference(args):
   if rank != 0:
     return
   cores = os.cpu_count() or 1
-  sample = {'c1': 100_000, 'c2': 8192 * cores, 'c3': 16384 * cores}[args.workload]
+  sample = {'c1': 100_000, 'c2': 8192 * cores, 'c3': 16384 * cores, 'c4': 256 * cores,
+            'c5': 16384 * cores}[args.workload]
   for _ in range(args.warmup):
     cpu_run(args.workload, max(sample // 8, 2 * cores), cores)
   vals, secs = [], []
@@ -251,7 +292,8 @@ def run_gpu(args):
 
   spec, all_times, x0, rngkw, payoffs, n, steps = make_workload(args.workload, args.paths)
   rng = engine.RngSpec(**rngkw)
-  plan = engine.Plan(spec, all_times, steps, x0, rng, n, np.float64)
+  wdtype = np.float32 if WORKLOADS[args.workload]['dtype'] == 'f32' else np.float64
+  plan = engine.Plan(spec, all_times, steps, x0, rng, n, wdtype)
   units = plan.units
   per = (units + world - 1) // world
   lo, hi = min(rank * per, units), min((rank + 1) * per, units)
@@ -306,7 +348,7 @@ def run_gpu(args):
   d2h_bytes = len(payoffs) * 4 * 8
 
   def e2e_step():
-    p = engine.Plan(spec, all_times, steps, x0, engine.RngSpec(**rngkw), n, np.float64)
+    p = engine.Plan(spec, all_times, steps, x0, engine.RngSpec(**rngkw), n, wdtype)
     s = p.price_sums(payoffs, lo, hi - lo)
     if world > 1:
       dist.all_reduce(s)
@@ -335,14 +377,17 @@ def run_gpu(args):
     # reduce kernel is a few microseconds) -- see profiles/.
     per_gpu_rate = (hi - lo) * (2 if rng.antithetic else 1) * steps / (ms_per_step * 1e-3)
     achieved = per_gpu_rate * algo / 1e9
-    roofline = {'bound': 'fp64', 'achieved': achieved, 'peak': dfma / 1e9,
-                'unit': 'G FP64-pipe instr/s', 'frac': achieved / (dfma / 1e9),
-                'traffic': None,
-                'note': 'achieved = path-steps/s/GPU x %d algorithmic FP64 instr per path-step; '
-                        'peak = DFMA issue rate measured live by tqf_measure_fp64_peak '
-                        '(MEASURED_PEAKS.json has no FP64 entry); kernel has no HBM traffic' % algo}
+    fp32 = WORKLOADS[args.workload]['dtype'] == 'f32'
+    peak = (ffma if fp32 else dfma) / 1e9
+    roofline = {'bound': 'fp32' if fp32 else 'fp64', 'achieved': achieved, 'peak': peak,
+                'unit': 'G %s-pipe instr/s' % ('FP32' if fp32 else 'FP64'),
+                'frac': achieved / peak, 'traffic': None,
+                'note': 'achieved = path-steps/s/GPU x %d algorithmic %s instr per path-step; '
+                        'peak = %s issue rate measured live by tqf_measure_fp64_peak '
+                        '(MEASURED_PEAKS.json has no FP64/FP32 entry); kernel has no HBM traffic'
+                        % (algo, 'FP32' if fp32 else 'FP64', 'FFMA' if fp32 else 'DFMA')}
     cores = 1
-    csample = {'c1': 100_000, 'c2': 32768, 'c3': 65536}[args.workload]
+    csample = {'c1': 100_000, 'c2': 32768, 'c3': 65536, 'c4': 1024, 'c5': 65536}[args.workload]
     cv, cdt, csteps, cn = cpu_run(args.workload, csample, cores)
     w = WORKLOADS[args.workload]
     line = {
@@ -371,6 +416,122 @@ def run_gpu(args):
     dist.destroy_process_group()
 
 
+def run_gpu_c5(args):
+  """C5: materialise 8M x 50 log-GBM Euler paths (time-major) and run the
+  Longstaff-Schwartz passes on them.  One step = generation + regression."""
+  import torch
+  import torch.distributed as dist
+  import tff_b200 as tff
+  from tff_b200 import engine
+  from tff_b200.models import closures
+  lsm = tff.models.longstaff_schwartz
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+  w = WORKLOADS['c5']
+  n = int(args.paths or w['paths'])
+  r, sigma = 0.1, 1.0
+  times = np.linspace(0.0, 1.0, 50)
+  drift, vol = closures.affine_closures(r - sigma**2 / 2, 0.0, sigma)
+  spec = closures.resolve_spec(drift, vol)
+  from tff_b200.models import utils
+  all_times, mask, _ = utils.prepare_grid(times=times, time_step=np.float64(0.01),
+                                          dtype=np.float64)
+  steps, record_slot = engine.record_plan(mask, 50)
+  rng = engine.RngSpec(tff.math.random.RandomType.STATELESS_ANTITHETIC, [4, 2], 0)
+  plan = engine.Plan(spec, all_times, steps, np.array([0.0]), rng, n, np.float64)
+  units = plan.units
+  per = (units + world - 1) // world
+  lo, hi = min(rank * per, units), min((rank + 1) * per, units)
+  df = np.exp(-r * times)
+  put = lsm.make_basket_put_payoff([1.1], dtype=np.float64)
+  basis = lsm.make_polynomial_basis(3)
+  reduce_fn = (lambda t: dist.all_reduce(t)) if world > 1 else None
+  stream = torch.cuda.current_stream()
+  times_ms = {'gen': 0.0, 'lsm': 0.0}
+
+  def one_step(timed):
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record(stream)
+    log_paths = plan.paths(record_slot, 50, lo, hi - lo)     # [rows, 50, 1] time-major view
+    paths = torch.exp_(log_paths)
+    e1.record(stream)
+    # antithetic shard rows: [+ partners of units lo..hi) | - partners]; the global
+    # index only matters for num_calibration_samples (unused here)
+    price = lsm.least_square_mc(paths, np.arange(50), put, basis, discount_factors=df,
+                                dtype=np.float64, global_path_offset=2 * lo,
+                                all_reduce=reduce_fn)
+    e2.record(stream)
+    if timed:
+      torch.cuda.synchronize()
+      times_ms['gen'] += e0.elapsed_time(e1)
+      times_ms['lsm'] += e1.elapsed_time(e2)
+    return price
+
+  for _ in range(max(args.warmup, 3)):
+    price = one_step(False)
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  sampler = ClockSampler(local) if rank == 0 else None
+  if sampler:
+    sampler.start()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    price = one_step(True)
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  wall = time.perf_counter() - t0
+  clocks = sampler.stop() if sampler else None
+  tt = torch.tensor([times_ms['gen'] + times_ms['lsm'], times_ms['gen'], times_ms['lsm'], wall * 1e3],
+                    dtype=torch.float64, device='cuda')
+  if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+  tot, gen, lsm_ms, wall_ms = (float(v) / args.steps for v in tt.tolist())
+  if rank == 0:
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:  # pylint: disable=broad-except
+      pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    rows = 2 * (hi - lo)
+    lsm_bytes = 49.0 * rows * 32.0
+    achieved = lsm_bytes / (lsm_ms * 1e-3) / 1e9
+    cv, cdt, csteps, cn = cpu_run('c5', 65536, 1)
+    line = {
+        'metric': METRIC, 'value': n * steps / (wall_ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': wall_ms,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': w['name'] if args.paths is None else w['name'] + ' [paths=%d]' % n,
+                   'paths': n, 'euler_steps': steps, 'exercise_dates': 50,
+                   'l2': 'inputs (3.2 GB of paths) exceed L2',
+                   'timing': 'wall clock around generation + LSM incl. the per-date host pinv '
+                             '(device events: generation %.2f ms, LSM passes incl. host solves %.2f ms)'
+                             % (gen, lsm_ms)},
+        'prices': [float(price[0])], 'clocks': clocks,
+        'e2e': {'value': n * steps / (wall_ms * 1e-3), 'unit': UNIT,
+                'h2d_bytes_per_step': 49 * 8 * 16, 'd2h_bytes_per_step': 49 * 27 * 8},
+        'gpu_launches': args.steps * (1 + 2 + 2 + 49 * 2 + 2),
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                     'frac': achieved / hbm_peak, 'traffic': None,
+                     'note': 'LSM passes: 32 algorithmic bytes per path per exercise date (SURVEY 8d) '
+                             '/ time between the device events around least_square_mc, which still '
+                             'includes 49 host pseudo-inverse round trips; peak = MEASURED_PEAKS.json hbm_gbs'},
+        'cpu_baseline': {'value': cv, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                         'sample': '%d paths x %d steps + LSM, single process numpy oracle (%.1f s)' % (cn, csteps, cdt)},
+    }
+    print(json.dumps(line))
+  plan.close()
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -383,6 +544,8 @@ def main():
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)
+  elif args.workload == 'c5':
+    run_gpu_c5(args)
   else:
     run_gpu(args)
 
