@@ -259,12 +259,18 @@ int tqf_lsm_column_sums(tqf_lsm* lsm, const int32_t* time_indices, int num_times
 int tqf_lsm_init(tqf_lsm* lsm, int time_index, void* stream);
 /* One pass: optionally W' = ev > relu(X beta) ? ev : ratio_update W at time
  * index t_update, then optionally accumulate the normal equations at t_acc with
- * y = ratio_acc W'.  Host arrays: mean_* [B][dim], beta [B][K], ratio_* [B].
- * sums_dev: double [B][num_sums] (layout: tqf_lsm_sums_layout). */
-int tqf_lsm_step(tqf_lsm* lsm, int do_update, int t_update, const double* mean_update,
-                 const double* beta, const double* ratio_update, int do_accumulate,
-                 int t_acc, const double* mean_acc, const double* ratio_acc,
-                 double* sums_dev, void* stream);
+ * y = ratio_acc W'.  DEVICE arrays: mean_* (payoff b at b*mean_stride, `dim`
+ * entries), beta [B][K], ratio_* [B].  sums_dev: double [B][num_sums]
+ * (layout: tqf_lsm_sums_layout).  Nothing synchronises with the host. */
+int tqf_lsm_step(tqf_lsm* lsm, int do_update, int t_update, const double* mean_update_dev,
+                 const double* beta_dev, const double* ratio_update_dev, int do_accumulate,
+                 int t_acc, const double* mean_acc_dev, const double* ratio_acc_dev,
+                 int64_t mean_stride, double* sums_dev, void* stream);
+/* beta_dev[b] = pinv(X'X_b) X'y_b from the reduced sums (Jacobi eigen-solver on
+ * the device, singular values below rcond * max dropped like tf.linalg.pinv).
+ * Packed layout (K <= 6) only; TQF_ERR_UNSUPPORTED otherwise (solve on host). */
+int tqf_lsm_solve(tqf_lsm* lsm, const double* sums_dev, double rcond, double* beta_dev,
+                  void* stream);
 /* num_sums doubles per payoff.  Packed (K <= 6): the upper triangle of a 6 x 6
  * X'X row by row (21 entries) followed by 6 entries of X'y; otherwise X'X
  * [K][K] row-major followed by X'y [K]. */

@@ -39,15 +39,16 @@ struct LsmArgs {
   int dim, K, batch;
   const int* exponents;    // device [K][dim]
   const double* strikes;   // device [B]
-  // update part
+  // update part (all pointers device memory)
   int do_update, t_update;
-  const double* mean_update;  // device [B][dim]
-  const double* beta;         // device [B][K]
-  const double* ratio_update; // device [B]
+  const double* mean_update;  // [B][mean_stride] -> first `dim` entries used
+  const double* beta;         // [B][K]
+  const double* ratio_update; // [B]
   // accumulate part
   int do_acc, t_acc;
-  const double* mean_acc;     // device [B][dim]
-  const double* ratio_acc;    // device [B]
+  const double* mean_acc;
+  const double* ratio_acc;    // [B]
+  int64_t mean_stride;        // doubles between the means of consecutive payoffs
   double* partials;           // device [gridDim.x][B][NS]
   int NS;
 };
@@ -106,45 +107,93 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_step_fast_kernel(const LsmArgs<
   const Real ratio_u = A.do_update ? static_cast<Real>(A.ratio_update[b]) : Real(1);
   const Real ratio_a = A.do_acc ? static_cast<Real>(A.ratio_acc[b]) : Real(1);
 
+  constexpr int U = 4;  // paths in flight per thread
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-  for (uint64_t n = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; n < A.num_paths;
-       n += stride) {
-    const Real* xn = base + static_cast<int64_t>(n) * A.stride_path;
-    Real wn = w[n];
-    Real phi[kLsmFastK];
-    if (A.do_update) {
-      const Real* xp = xn + A.t_update * A.stride_time;
-      const Real ev = lsm_payoff(A, xp, b);
-      lsm_basis(A, xp, A.mean_update + b * A.dim, phi);
-      // continuation = relu(X beta) evaluated in the working dtype
-      Real cont = 0;
+  const double* mean_u = A.mean_update + b * A.mean_stride;
+  const double* mean_a = A.mean_acc + b * A.mean_stride;
+  for (uint64_t n0 = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       n0 < A.num_paths; n0 += U * stride) {
+    Real wn[U], xu[U], xa[U];
+    bool live[U];
+    // issue every load of the U paths first (single-asset fast path keeps the
+    // two time columns in registers; dim > 1 re-reads inside the helpers)
 #pragma unroll
-      for (int k = 0; k < kLsmFastK; ++k)
-        if (k < K) cont += phi[k] * static_cast<Real>(beta[k]);
-      cont = cont > Real(0) ? cont : Real(0);
-      wn = ev > cont ? ev : ratio_u * wn;
-      w[n] = wn;
+    for (int u = 0; u < U; ++u) {
+      const uint64_t n = n0 + u * stride;
+      live[u] = n < A.num_paths;
+      const Real* xn = base + static_cast<int64_t>(live[u] ? n : 0) * A.stride_path;
+      wn[u] = live[u] ? w[n] : Real(0);
+      xu[u] = (live[u] && A.do_update) ? xn[A.t_update * A.stride_time] : Real(0);
+      xa[u] = (live[u] && A.do_acc) ? xn[A.t_acc * A.stride_time] : Real(0);
     }
-    if (A.do_acc) {
-      const Real* xp = xn + A.t_acc * A.stride_time;
-      const Real ev = lsm_payoff(A, xp, b);
-      const bool use = ev > Real(0) && (A.path_offset + n) < A.num_calib;
-      if (use) {
-        lsm_basis(A, xp, A.mean_acc + b * A.dim, phi);
-        const double y = static_cast<double>(ratio_a * wn);
-        int idx = 0;
 #pragma unroll
-        for (int i = 0; i < kLsmFastK; ++i) {
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) continue;
+      const uint64_t n = n0 + u * stride;
+      const Real* xn = base + static_cast<int64_t>(n) * A.stride_path;
+      Real phi[kLsmFastK];
+      if (A.do_update) {
+        const Real* xp = xn + A.t_update * A.stride_time;
+        Real ev;
+        if (A.dim == 1) {
+          const Real v = static_cast<Real>(A.strikes[b]) - xu[u];
+          ev = v > Real(0) ? v : Real(0);
+          const Real c = xu[u] - static_cast<Real>(mean_u[0]);
+          Real pw = 1;
 #pragma unroll
-          for (int j = i; j < kLsmFastK; ++j) {
-            if (j < K && i < K)
-              acc[idx] += static_cast<double>(phi[i]) * static_cast<double>(phi[j]);
-            ++idx;
+          for (int k = 0; k < kLsmFastK; ++k) {
+            phi[k] = pw;
+            pw *= c;
           }
+        } else {
+          ev = lsm_payoff(A, xp, b);
+          lsm_basis(A, xp, mean_u, phi);
         }
+        Real cont = 0;
 #pragma unroll
-        for (int i = 0; i < kLsmFastK; ++i)
-          if (i < K) acc[kLsmFastK * (kLsmFastK + 1) / 2 + i] += static_cast<double>(phi[i]) * y;
+        for (int k = 0; k < kLsmFastK; ++k)
+          if (k < K) cont += phi[k] * static_cast<Real>(beta[k]);
+        cont = cont > Real(0) ? cont : Real(0);
+        wn[u] = ev > cont ? ev : ratio_u * wn[u];
+        w[n] = wn[u];
+      }
+      if (A.do_acc) {
+        const Real* xp = xn + A.t_acc * A.stride_time;
+        Real ev;
+        if (A.dim == 1) {
+          const Real v = static_cast<Real>(A.strikes[b]) - xa[u];
+          ev = v > Real(0) ? v : Real(0);
+        } else {
+          ev = lsm_payoff(A, xp, b);
+        }
+        const bool use = ev > Real(0) && (A.path_offset + n) < A.num_calib;
+        if (use) {
+          if (A.dim == 1) {
+            const Real c = xa[u] - static_cast<Real>(mean_a[0]);
+            Real pw = 1;
+#pragma unroll
+            for (int k = 0; k < kLsmFastK; ++k) {
+              phi[k] = pw;
+              pw *= c;
+            }
+          } else {
+            lsm_basis(A, xp, mean_a, phi);
+          }
+          const double y = static_cast<double>(ratio_a * wn[u]);
+          int idx = 0;
+#pragma unroll
+          for (int i = 0; i < kLsmFastK; ++i) {
+#pragma unroll
+            for (int j = i; j < kLsmFastK; ++j) {
+              if (j < K && i < K)
+                acc[idx] += static_cast<double>(phi[i]) * static_cast<double>(phi[j]);
+              ++idx;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kLsmFastK; ++i)
+            if (i < K) acc[kLsmFastK * (kLsmFastK + 1) / 2 + i] += static_cast<double>(phi[i]) * y;
+        }
       }
     }
   }
@@ -195,7 +244,7 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_step_generic_kernel(const LsmAr
         if (A.do_update) {
           const Real* xp = xn + A.t_update * A.stride_time;
           const Real ev = lsm_payoff(A, xp, b);
-          lsm_basis(A, xp, A.mean_update + b * A.dim, phi);
+          lsm_basis(A, xp, A.mean_update + b * A.mean_stride, phi);
           Real cont = 0;
           for (int k = 0; k < K; ++k) cont += phi[k] * static_cast<Real>(A.beta[b * K + k]);
           cont = cont > Real(0) ? cont : Real(0);
@@ -207,7 +256,7 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_step_generic_kernel(const LsmAr
           const Real ev = lsm_payoff(A, xp, b);
           use = ev > Real(0) && (A.path_offset + n) < A.num_calib;
           if (use) {
-            lsm_basis(A, xp, A.mean_acc + b * A.dim, phi);
+            lsm_basis(A, xp, A.mean_acc + b * A.mean_stride, phi);
             y = static_cast<double>(ratio_a * wn);
           }
         }
@@ -302,13 +351,94 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_wsum_kernel(const LsmArgs<Real>
   }
 }
 
-// sums[m] = sum_blocks partials[block][m], fixed order.
+// sums[m] = sum_blocks partials[block][m]: one warp per output, lanes stride
+// over the blocks, fixed order -> reproducible.
 __global__ void lsm_reduce_kernel(const double* __restrict__ partials, int num_blocks, int M,
                                   double* __restrict__ sums) {
-  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M;
+       m += gridDim.x * warps_per_block) {
     double v = 0.0;
-    for (int bk = 0; bk < num_blocks; ++bk) v += partials[static_cast<size_t>(bk) * M + m];
-    sums[m] = v;
+    for (int bk = lane; bk < num_blocks; bk += 32) v += partials[static_cast<size_t>(bk) * M + m];
+    v = warp_sum(v);
+    if (lane == 0) sums[m] = v;
+  }
+}
+
+// beta = pinv(X'X) X'y for the packed layout (K <= 6): cyclic Jacobi
+// eigen-decomposition of the symmetric PSD matrix; eigenvalues below
+// rcond * max eigenvalue are dropped, as tf.linalg.pinv / numpy.linalg.pinv do
+// with singular values (lsm.py:369-377).  One thread per payoff.
+__global__ void lsm_solve_kernel(const double* __restrict__ sums, int B, int K, double rcond,
+                                 int round_to_float, double* __restrict__ beta) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* sp = sums + static_cast<size_t>(b) * kLsmFastNS;
+  double a[kLsmFastK][kLsmFastK], v[kLsmFastK][kLsmFastK], rhs[kLsmFastK];
+  int idx = 0;
+  for (int i = 0; i < kLsmFastK; ++i)
+    for (int j = i; j < kLsmFastK; ++j) {
+      double x = (i < K && j < K) ? sp[idx] : 0.0;
+      if (round_to_float) x = static_cast<double>(static_cast<float>(x));
+      a[i][j] = x;
+      a[j][i] = x;
+      ++idx;
+    }
+  for (int i = 0; i < kLsmFastK; ++i) {
+    double x = i < K ? sp[kLsmFastK * (kLsmFastK + 1) / 2 + i] : 0.0;
+    if (round_to_float) x = static_cast<double>(static_cast<float>(x));
+    rhs[i] = x;
+    for (int j = 0; j < kLsmFastK; ++j) v[i][j] = i == j ? 1.0 : 0.0;
+  }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < K; ++i) {
+      diag += a[i][i] * a[i][i];
+      for (int j = i + 1; j < K; ++j) off += a[i][j] * a[i][j];
+    }
+    if (off <= 1e-300 || off <= 1e-34 * diag) break;
+    for (int p = 0; p < K - 1; ++p)
+      for (int q = p + 1; q < K; ++q) {
+        const double apq = a[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < K; ++k) {
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = c * akp - sn * akq;
+          a[k][q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < K; ++k) {
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = c * apk - sn * aqk;
+          a[q][k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < K; ++k) {
+          const double vkp = v[k][p], vkq = v[k][q];
+          v[k][p] = c * vkp - sn * vkq;
+          v[k][q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  double lmax = 0.0;
+  for (int i = 0; i < K; ++i) lmax = fmax(lmax, fabs(a[i][i]));
+  const double cutoff = rcond * lmax;
+  for (int i = 0; i < kLsmFastK; ++i) {
+    double s = 0.0;
+    if (i < K) {
+      for (int e = 0; e < K; ++e) {
+        const double lam = a[e][e];
+        if (fabs(lam) > cutoff) {
+          double proj = 0.0;
+          for (int j = 0; j < K; ++j) proj += v[j][e] * rhs[j];
+          s += v[i][e] * proj / lam;
+        }
+      }
+    }
+    if (round_to_float) s = static_cast<double>(static_cast<float>(s));
+    if (i < K) beta[static_cast<size_t>(b) * K + i] = s;
   }
 }
 
@@ -323,7 +453,6 @@ struct tqf_lsm {
   void* w_dev;           // Real [B][N]
   int* exponents_dev;    // [K][dim]
   double* strikes_dev;   // [B]
-  double* small_dev;     // staging: mean_u [B][dim] | mean_a [B][dim] | beta [B][K] | ratio_u [B] | ratio_a [B]
   double* partials_dev;  // [grid][B][max(NS, T*dim, 2)]
   size_t partials_doubles;
   int* times_dev;
@@ -365,40 +494,22 @@ static int ensure_partials(tqf_lsm* h, size_t doubles) {
 template <typename Real>
 static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* mean_update,
                          const double* beta, const double* ratio_update, int do_acc, int t_acc,
-                         const double* mean_acc, const double* ratio_acc, double* sums_dev,
-                         cudaStream_t s) {
+                         const double* mean_acc, const double* ratio_acc, int64_t mean_stride,
+                         double* sums_dev, cudaStream_t s) {
   const tqf_lsm_desc& d = h->desc;
-  const int B = d.batch, K = h->K, dim = d.dim;
-  // stage the small host arrays
-  std::vector<double> small(static_cast<size_t>(2 * B * dim + B * K + 2 * B), 0.0);
-  double* p = small.data();
-  double* mu = p;  p += B * dim;
-  double* ma = p;  p += B * dim;
-  double* be = p;  p += B * K;
-  double* ru = p;  p += B;
-  double* ra = p;
-  if (do_update) {
-    std::memcpy(mu, mean_update, sizeof(double) * B * dim);
-    std::memcpy(be, beta, sizeof(double) * B * K);
-    std::memcpy(ru, ratio_update, sizeof(double) * B);
-  }
-  if (do_acc) {
-    std::memcpy(ma, mean_acc, sizeof(double) * B * dim);
-    std::memcpy(ra, ratio_acc, sizeof(double) * B);
-  }
-  TQF_CUDA_OK(cudaMemcpyAsync(h->small_dev, small.data(), small.size() * sizeof(double),
-                              cudaMemcpyHostToDevice, s));
+  const int B = d.batch, K = h->K;
   LsmArgs<Real> A;
   fill_args(h, &A);
   A.do_update = do_update;
   A.t_update = t_update;
-  A.mean_update = h->small_dev;
-  A.mean_acc = h->small_dev + B * dim;
-  A.beta = h->small_dev + 2 * B * dim;
-  A.ratio_update = h->small_dev + 2 * B * dim + B * K;
-  A.ratio_acc = A.ratio_update + B;
+  A.mean_update = mean_update;
+  A.beta = beta;
+  A.ratio_update = ratio_update;
   A.do_acc = do_acc;
   A.t_acc = t_acc;
+  A.mean_acc = do_acc ? mean_acc : mean_update;
+  A.ratio_acc = do_acc ? ratio_acc : ratio_update;
+  A.mean_stride = mean_stride;
   int rc = ensure_partials(h, static_cast<size_t>(h->grid) * B * h->NS);
   if (rc != TQF_OK) return rc;
   A.partials = h->partials_dev;
@@ -412,7 +523,8 @@ static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* 
   TQF_CUDA_OK(cudaGetLastError());
   if (do_acc) {
     const int M = B * h->NS;
-    lsm_reduce_kernel<<<(M + 127) / 128, 128, 0, s>>>(h->partials_dev, h->grid, M, sums_dev);
+    const int blocks = (M + 3) / 4 < 592 ? (M + 3) / 4 : 592;
+    lsm_reduce_kernel<<<blocks, 128, 0, s>>>(h->partials_dev, h->grid, M, sums_dev);
     TQF_CUDA_OK(cudaGetLastError());
   }
   return TQF_OK;
@@ -454,9 +566,6 @@ int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->exponents_dev, sizeof(int) * h->K * desc->dim);
   if (e == cudaSuccess) e = cudaMalloc(&h->strikes_dev, sizeof(double) * desc->batch);
   if (e == cudaSuccess)
-    e = cudaMalloc(&h->small_dev,
-                   sizeof(double) * (2 * desc->batch * desc->dim + desc->batch * h->K + 2 * desc->batch));
-  if (e == cudaSuccess)
     e = cudaMemcpy(h->exponents_dev, desc->exponents, sizeof(int) * h->K * desc->dim,
                    cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
@@ -477,7 +586,6 @@ int tqf_lsm_destroy(tqf_lsm* h) {
   cudaFree(h->w_dev);
   cudaFree(h->exponents_dev);
   cudaFree(h->strikes_dev);
-  cudaFree(h->small_dev);
   cudaFree(h->partials_dev);
   cudaFree(h->times_dev);
   delete h;
@@ -513,7 +621,7 @@ int tqf_lsm_column_sums(tqf_lsm* h, const int32_t* time_indices, int num_times, 
   }
   TQF_CUDA_OK(cudaGetLastError());
   const int M = d.batch * cols;
-  lsm_reduce_kernel<<<(M + 127) / 128, 128, 0, s>>>(h->partials_dev, gx, M, sums_dev);
+  lsm_reduce_kernel<<<(M + 3) / 4 < 592 ? (M + 3) / 4 : 592, 128, 0, s>>>(h->partials_dev, gx, M, sums_dev);
   TQF_CUDA_OK(cudaGetLastError());
   return TQF_OK;
 }
@@ -535,18 +643,37 @@ int tqf_lsm_init(tqf_lsm* h, int time_index, void* stream) {
   return TQF_OK;
 }
 
-int tqf_lsm_step(tqf_lsm* h, int do_update, int t_update, const double* mean_update,
-                 const double* beta, const double* ratio_update, int do_accumulate, int t_acc,
-                 const double* mean_acc, const double* ratio_acc, double* sums_dev, void* stream) {
+int tqf_lsm_step(tqf_lsm* h, int do_update, int t_update, const double* mean_update_dev,
+                 const double* beta_dev, const double* ratio_update_dev, int do_accumulate,
+                 int t_acc, const double* mean_acc_dev, const double* ratio_acc_dev,
+                 int64_t mean_stride, double* sums_dev, void* stream) {
   TQF_REQUIRE(h, "null handle");
-  TQF_REQUIRE(!do_update || (mean_update && beta && ratio_update), "null update argument");
-  TQF_REQUIRE(!do_accumulate || (mean_acc && ratio_acc && sums_dev), "null accumulate argument");
+  TQF_REQUIRE(!do_update || (mean_update_dev && beta_dev && ratio_update_dev),
+              "null update argument");
+  TQF_REQUIRE(!do_accumulate || (mean_acc_dev && ratio_acc_dev && sums_dev),
+              "null accumulate argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return h->desc.dtype == TQF_F64
-             ? lsm_step_impl<double>(h, do_update, t_update, mean_update, beta, ratio_update,
-                                     do_accumulate, t_acc, mean_acc, ratio_acc, sums_dev, s)
-             : lsm_step_impl<float>(h, do_update, t_update, mean_update, beta, ratio_update,
-                                    do_accumulate, t_acc, mean_acc, ratio_acc, sums_dev, s);
+             ? lsm_step_impl<double>(h, do_update, t_update, mean_update_dev, beta_dev,
+                                     ratio_update_dev, do_accumulate, t_acc, mean_acc_dev,
+                                     ratio_acc_dev, mean_stride, sums_dev, s)
+             : lsm_step_impl<float>(h, do_update, t_update, mean_update_dev, beta_dev,
+                                    ratio_update_dev, do_accumulate, t_acc, mean_acc_dev,
+                                    ratio_acc_dev, mean_stride, sums_dev, s);
+}
+
+int tqf_lsm_solve(tqf_lsm* h, const double* sums_dev, double rcond, double* beta_dev,
+                  void* stream) {
+  TQF_REQUIRE(h && sums_dev && beta_dev, "null argument");
+  if (!h->fast) {
+    set_error("device solve is implemented for basis sizes <= 6; solve on the host");
+    return TQF_ERR_UNSUPPORTED;
+  }
+  const int B = h->desc.batch;
+  lsm_solve_kernel<<<(B + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums_dev, B, h->K, rcond, h->desc.dtype == TQF_F32 ? 1 : 0, beta_dev);
+  TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
 }
 
 int tqf_lsm_sums_layout(const tqf_lsm* h, int* num_sums, int* is_packed_symmetric) {

@@ -156,7 +156,10 @@ _SIGNATURES = {
     'tqf_lsm_init': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'tqf_lsm_step':
         (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                   C.c_void_p]),
+    'tqf_lsm_solve':
+        (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     'tqf_lsm_sums_layout':
         (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'tqf_lsm_value_sum': (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

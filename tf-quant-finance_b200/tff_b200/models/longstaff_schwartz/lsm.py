@@ -159,38 +159,47 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
     if all_reduce is not None:
       all_reduce(colsum)
       all_reduce(count)
-    n_total = float(count.item())
-    means = (colsum.cpu().numpy() / n_total).astype(dt).astype(np.float64)  # [B, T, dim]
+    # means in the working dtype (the reference reduces in dtype), as doubles;
+    # everything below stays on the device: no host round trip per date.
+    tdt = _tensor.torch_dtype(dt)
+    means = (colsum / count).to(tdt).to(torch.float64).contiguous()     # [B, T, dim]
+    ratio_dev = torch.as_tensor(np.ascontiguousarray(ratio), device=dev)    # [T, B]
+    mean_stride = T * dim
 
-    def mean_at(e):          # exercise index e uses time slot e - 1
-      return np.ascontiguousarray(means[:, e - 1, :])
+    def mean_ptr(e):         # exercise index e uses time slot e - 1
+      return means.data_ptr() + (e - 1) * dim * 8
 
-    def ratio_at(e):
-      return np.ascontiguousarray(ratio[e])
+    def ratio_ptr(e):
+      return ratio_dev.data_ptr() + e * B * 8
 
     _lib.check(lib.tqf_lsm_init(handle, int(ex_times[T - 1]), stream))
     sums = torch.zeros((B, ns.value), dtype=torch.float64, device=dev)
+    beta_dev = torch.zeros((B, K), dtype=torch.float64, device=dev)
+    rcond = 10 * K * float(np.finfo(dt).eps)
     e = T - 1
     if e > 0:
-      ma, ra = mean_at(e), ratio_at(e)
       _lib.check(lib.tqf_lsm_step(handle, 0, 0, None, None, None, 1,
-                                  int(ex_times[e - 1]), ma.ctypes.data,
-                                  ra.ctypes.data, sums.data_ptr(), stream))
-    rcond = 10 * K * np.finfo(dt).eps
+                                  int(ex_times[e - 1]), mean_ptr(e), ratio_ptr(e),
+                                  mean_stride, sums.data_ptr(), stream))
+    device_solve = bool(packed.value)
     while e > 0:
       if all_reduce is not None:
         all_reduce(sums)
-      lhs, rhs = _unpack_sums(sums.cpu().numpy(), K, bool(packed.value))
-      beta = np.stack([np.linalg.pinv(lhs[b].astype(dt), rcond=rcond).astype(np.float64)
-                       @ rhs[b].astype(dt).astype(np.float64) for b in range(B)])
-      beta = np.ascontiguousarray(beta.astype(dt).astype(np.float64))
-      mu, ru = mean_at(e), ratio_at(e)
+      if device_solve:
+        _lib.check(lib.tqf_lsm_solve(handle, sums.data_ptr(), rcond,
+                                     beta_dev.data_ptr(), stream))
+      else:
+        # large bases (K > 6): the K x K pseudo-inverse runs on the host
+        lhs, rhs = _unpack_sums(sums.cpu().numpy(), K, False)
+        beta = np.stack([np.linalg.pinv(lhs[b].astype(dt), rcond=rcond).astype(np.float64)
+                         @ rhs[b].astype(dt).astype(np.float64) for b in range(B)])
+        beta_dev.copy_(torch.as_tensor(np.ascontiguousarray(beta.astype(dt).astype(np.float64))))
       do_acc = 1 if e - 1 > 0 else 0
-      ma, ra = (mean_at(e - 1), ratio_at(e - 1)) if do_acc else (mu, ru)
       _lib.check(lib.tqf_lsm_step(
-          handle, 1, int(ex_times[e - 1]), mu.ctypes.data, beta.ctypes.data,
-          ru.ctypes.data, do_acc, int(ex_times[e - 2]) if do_acc else 0,
-          ma.ctypes.data, ra.ctypes.data, sums.data_ptr(), stream))
+          handle, 1, int(ex_times[e - 1]), mean_ptr(e), beta_dev.data_ptr(), ratio_ptr(e),
+          do_acc, int(ex_times[e - 2]) if do_acc else 0,
+          mean_ptr(e - 1) if do_acc else None, ratio_ptr(e - 1) if do_acc else None,
+          mean_stride, sums.data_ptr(), stream))
       e -= 1
     vs = torch.zeros((B, 2), dtype=torch.float64, device=dev)
     _lib.check(lib.tqf_lsm_value_sum(handle, int(num_calibration_samples or 0),
