@@ -456,8 +456,8 @@ def run_gpu_c5(args):
   def one_step(timed):
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record(stream)
-    log_paths = plan.paths(record_slot, 50, lo, hi - lo)     # [rows, 50, 1] time-major view
-    paths = torch.exp_(log_paths)
+    # [rows, 50, 1] time-major view of exp(log-price), exponentiated on store
+    paths = plan.paths(record_slot, 50, lo, hi - lo, exp_transform=True)
     e1.record(stream)
     # antithetic shard rows: [+ partners of units lo..hi) | - partners]; the global
     # index only matters for num_calibration_samples (unused here)

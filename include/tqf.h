@@ -216,11 +216,12 @@ int tqf_plan_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
  *   record_slot: host int32 [num_steps+1]; entry 0 refers to the initial
  *   state, entry s+1 to the state after step s; value = output time slot or -1.
  *   out_dev[(p - path_offset)*stride_path + slot*stride_time + j*stride_dim]
- *   (strides in elements of the model dtype).                              */
+ *   (strides in elements of the model dtype).  transform = TQF_TRANSFORM_EXP
+ *   stores exp(state) (log-space models whose prices feed the LSM passes).  */
 int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                    const int32_t* record_slot, void* out_dev,
                    int64_t stride_path, int64_t stride_time, int64_t stride_dim,
-                   void* stream);
+                   int transform, void* stream);
 
 /* ------------------------------------------------------------------------
  * Longstaff-Schwartz regression passes on materialised paths: replaces the

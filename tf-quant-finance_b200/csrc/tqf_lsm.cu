@@ -214,6 +214,115 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_step_fast_kernel(const LsmArgs<
   }
 }
 
+// Single-asset specialisation (the American put of config C5): K compile-time,
+// 1 + x + ... + x^(K-1) basis, K (K + 1) / 2 + K accumulators in registers, four
+// paths in flight per thread.  Same packed partials layout as the general fast
+// kernel (6 x 6 upper triangle + 6), unused entries zero.
+template <typename Real, int KT>
+__global__ void __launch_bounds__(kLsmBlock, 3) lsm_step_dim1_kernel(const LsmArgs<Real> A) {
+  const int b = blockIdx.y;
+  const Real* base = A.paths + b * A.stride_batch;
+  Real* w = A.w + static_cast<size_t>(b) * A.num_paths;
+  constexpr int NA = KT * (KT + 1) / 2 + KT;
+  double acc[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) acc[i] = 0.0;
+  Real beta[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) beta[k] = A.do_update ? static_cast<Real>(A.beta[b * KT + k]) : Real(0);
+  const Real ratio_u = A.do_update ? static_cast<Real>(A.ratio_update[b]) : Real(1);
+  const Real ratio_a = A.do_acc ? static_cast<Real>(A.ratio_acc[b]) : Real(1);
+  const Real strike = static_cast<Real>(A.strikes[b]);
+  const Real mean_u = A.do_update ? static_cast<Real>(A.mean_update[b * A.mean_stride]) : Real(0);
+  const Real mean_a = A.do_acc ? static_cast<Real>(A.mean_acc[b * A.mean_stride]) : Real(0);
+  const int64_t off_u = A.t_update * A.stride_time, off_a = A.t_acc * A.stride_time;
+  constexpr int U = 4;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t n0 = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       n0 < A.num_paths; n0 += U * stride) {
+    Real wn[U], xu[U], xa[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t n = n0 + u * stride;
+      const bool live = n < A.num_paths;
+      const Real* xn = base + static_cast<int64_t>(live ? n : 0) * A.stride_path;
+      wn[u] = live ? w[n] : Real(0);
+      xu[u] = (live && A.do_update) ? xn[off_u] : strike;   // strike -> exercise value 0
+      xa[u] = (live && A.do_acc) ? xn[off_a] : strike;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t n = n0 + u * stride;
+      if (n >= A.num_paths) continue;
+      if (A.do_update) {
+        const Real v = strike - xu[u];
+        const Real ev = v > Real(0) ? v : Real(0);
+        const Real c = xu[u] - mean_u;
+        Real cont = beta[KT - 1];
+#pragma unroll
+        for (int k = KT - 2; k >= 0; --k) cont = fma(cont, c, beta[k]);
+        // (Horner; the reference's matmul sums phi_k beta_k -- same value up to rounding)
+        cont = cont > Real(0) ? cont : Real(0);
+        wn[u] = ev > cont ? ev : ratio_u * wn[u];
+        w[n] = wn[u];
+      }
+      if (A.do_acc) {
+        const Real v = strike - xa[u];
+        if (v > Real(0) && (A.path_offset + n) < A.num_calib) {
+          double phi[KT];
+          const double c = static_cast<double>(static_cast<Real>(xa[u] - mean_a));
+          phi[0] = 1.0;
+#pragma unroll
+          for (int k = 1; k < KT; ++k)
+            phi[k] = static_cast<double>(static_cast<Real>(static_cast<Real>(phi[k - 1]) * static_cast<Real>(c)));
+          const double y = static_cast<double>(ratio_a * wn[u]);
+          int idx = 0;
+#pragma unroll
+          for (int i = 0; i < KT; ++i)
+#pragma unroll
+            for (int j = i; j < KT; ++j) {
+              acc[idx] = fma(phi[i], phi[j], acc[idx]);
+              ++idx;
+            }
+#pragma unroll
+          for (int i = 0; i < KT; ++i) acc[KT * (KT + 1) / 2 + i] = fma(phi[i], y, acc[KT * (KT + 1) / 2 + i]);
+        }
+      }
+    }
+  }
+  if (A.do_acc) {
+    __shared__ double s_red[kLsmBlock / 32][NA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const double v = warp_sum(acc[i]);
+      if (lane == 0) s_red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLsmFastNS) {
+      // map packed (6 x 6) slot -> compact (KT x KT) slot
+      const int slot = threadIdx.x;
+      int src = -1;
+      if (slot < kLsmFastK * (kLsmFastK + 1) / 2) {
+        int i = 0, rem = slot;
+        while (rem >= kLsmFastK - i) {
+          rem -= kLsmFastK - i;
+          ++i;
+        }
+        const int j = i + rem;
+        if (i < KT && j < KT) src = i * KT - i * (i - 1) / 2 + (j - i);
+      } else {
+        const int i = slot - kLsmFastK * (kLsmFastK + 1) / 2;
+        if (i < KT) src = KT * (KT + 1) / 2 + i;
+      }
+      double v = 0.0;
+      if (src >= 0)
+        for (int wi = 0; wi < kLsmBlock / 32; ++wi) v += s_red[wi][src];
+      A.partials[(static_cast<size_t>(blockIdx.x) * A.batch + b) * kLsmFastNS + slot] = v;
+    }
+  }
+}
+
 // Generic path (K <= 128): the update is per thread, the outer products are
 // formed tile by tile from shared memory.  grid = (blocks, B); NS = K*K + K.
 template <typename Real>
@@ -367,78 +476,106 @@ __global__ void lsm_reduce_kernel(const double* __restrict__ partials, int num_b
 }
 
 // beta = pinv(X'X) X'y for the packed layout (K <= 6): cyclic Jacobi
-// eigen-decomposition of the symmetric PSD matrix; eigenvalues below
-// rcond * max eigenvalue are dropped, as tf.linalg.pinv / numpy.linalg.pinv do
-// with singular values (lsm.py:369-377).  One thread per payoff.
+// eigen-decomposition of the symmetric PSD matrix, fully unrolled so that the
+// matrices live in registers; eigenvalues below rcond * max eigenvalue are
+// dropped, as tf.linalg.pinv / numpy.linalg.pinv do with singular values
+// (lsm.py:369-377).  One thread per payoff.
+template <int K>
+__device__ void lsm_solve_one(const double* __restrict__ sp, double rcond, int round_to_float,
+                              double* __restrict__ beta) {
+  double a[K][K], v[K][K], rhs[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+#pragma unroll
+    for (int j = i; j < K; ++j) {
+      // packed index of (i, j) in the 6 x 6 upper triangle
+      double x = sp[i * kLsmFastK - i * (i - 1) / 2 + (j - i)];
+      if (round_to_float) x = static_cast<double>(static_cast<float>(x));
+      a[i][j] = x;
+      a[j][i] = x;
+    }
+    double r = sp[kLsmFastK * (kLsmFastK + 1) / 2 + i];
+    if (round_to_float) r = static_cast<double>(static_cast<float>(r));
+    rhs[i] = r;
+#pragma unroll
+    for (int j = 0; j < K; ++j) v[i][j] = i == j ? 1.0 : 0.0;
+  }
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    double off = 0.0, diag = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      diag += a[i][i] * a[i][i];
+#pragma unroll
+      for (int j = i + 1; j < K; ++j) off += a[i][j] * a[i][j];
+    }
+    if (off <= 1e-300 || off <= 1e-34 * diag) break;
+#pragma unroll
+    for (int p = 0; p < K - 1; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < K; ++q) {
+        const double apq = a[p][q];
+        if (apq != 0.0) {
+          const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const double akp = a[k][p], akq = a[k][q];
+            a[k][p] = c * akp - sn * akq;
+            a[k][q] = sn * akp + c * akq;
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const double apk = a[p][k], aqk = a[q][k];
+            a[p][k] = c * apk - sn * aqk;
+            a[q][k] = sn * apk + c * aqk;
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const double vkp = v[k][p], vkq = v[k][q];
+            v[k][p] = c * vkp - sn * vkq;
+            v[k][q] = sn * vkp + c * vkq;
+          }
+        }
+      }
+    }
+  }
+  double lmax = 0.0;
+#pragma unroll
+  for (int i = 0; i < K; ++i) lmax = fmax(lmax, fabs(a[i][i]));
+  const double cutoff = rcond * lmax;
+  double coef[K];
+#pragma unroll
+  for (int e = 0; e < K; ++e) {
+    double proj = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) proj += v[j][e] * rhs[j];
+    const double lam = a[e][e];
+    coef[e] = fabs(lam) > cutoff ? proj / lam : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < K; ++e) s += v[i][e] * coef[e];
+    if (round_to_float) s = static_cast<double>(static_cast<float>(s));
+    beta[i] = s;
+  }
+}
+
 __global__ void lsm_solve_kernel(const double* __restrict__ sums, int B, int K, double rcond,
                                  int round_to_float, double* __restrict__ beta) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const double* sp = sums + static_cast<size_t>(b) * kLsmFastNS;
-  double a[kLsmFastK][kLsmFastK], v[kLsmFastK][kLsmFastK], rhs[kLsmFastK];
-  int idx = 0;
-  for (int i = 0; i < kLsmFastK; ++i)
-    for (int j = i; j < kLsmFastK; ++j) {
-      double x = (i < K && j < K) ? sp[idx] : 0.0;
-      if (round_to_float) x = static_cast<double>(static_cast<float>(x));
-      a[i][j] = x;
-      a[j][i] = x;
-      ++idx;
-    }
-  for (int i = 0; i < kLsmFastK; ++i) {
-    double x = i < K ? sp[kLsmFastK * (kLsmFastK + 1) / 2 + i] : 0.0;
-    if (round_to_float) x = static_cast<double>(static_cast<float>(x));
-    rhs[i] = x;
-    for (int j = 0; j < kLsmFastK; ++j) v[i][j] = i == j ? 1.0 : 0.0;
-  }
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = 0.0, diag = 0.0;
-    for (int i = 0; i < K; ++i) {
-      diag += a[i][i] * a[i][i];
-      for (int j = i + 1; j < K; ++j) off += a[i][j] * a[i][j];
-    }
-    if (off <= 1e-300 || off <= 1e-34 * diag) break;
-    for (int p = 0; p < K - 1; ++p)
-      for (int q = p + 1; q < K; ++q) {
-        const double apq = a[p][q];
-        if (apq == 0.0) continue;
-        const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
-        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
-        for (int k = 0; k < K; ++k) {
-          const double akp = a[k][p], akq = a[k][q];
-          a[k][p] = c * akp - sn * akq;
-          a[k][q] = sn * akp + c * akq;
-        }
-        for (int k = 0; k < K; ++k) {
-          const double apk = a[p][k], aqk = a[q][k];
-          a[p][k] = c * apk - sn * aqk;
-          a[q][k] = sn * apk + c * aqk;
-        }
-        for (int k = 0; k < K; ++k) {
-          const double vkp = v[k][p], vkq = v[k][q];
-          v[k][p] = c * vkp - sn * vkq;
-          v[k][q] = sn * vkp + c * vkq;
-        }
-      }
-  }
-  double lmax = 0.0;
-  for (int i = 0; i < K; ++i) lmax = fmax(lmax, fabs(a[i][i]));
-  const double cutoff = rcond * lmax;
-  for (int i = 0; i < kLsmFastK; ++i) {
-    double s = 0.0;
-    if (i < K) {
-      for (int e = 0; e < K; ++e) {
-        const double lam = a[e][e];
-        if (fabs(lam) > cutoff) {
-          double proj = 0.0;
-          for (int j = 0; j < K; ++j) proj += v[j][e] * rhs[j];
-          s += v[i][e] * proj / lam;
-        }
-      }
-    }
-    if (round_to_float) s = static_cast<double>(static_cast<float>(s));
-    if (i < K) beta[static_cast<size_t>(b) * K + i] = s;
+  double* out = beta + static_cast<size_t>(b) * K;
+  switch (K) {
+    case 1: lsm_solve_one<1>(sp, rcond, round_to_float, out); break;
+    case 2: lsm_solve_one<2>(sp, rcond, round_to_float, out); break;
+    case 3: lsm_solve_one<3>(sp, rcond, round_to_float, out); break;
+    case 4: lsm_solve_one<4>(sp, rcond, round_to_float, out); break;
+    case 5: lsm_solve_one<5>(sp, rcond, round_to_float, out); break;
+    default: lsm_solve_one<6>(sp, rcond, round_to_float, out); break;
   }
 }
 
@@ -514,7 +651,16 @@ static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* 
   if (rc != TQF_OK) return rc;
   A.partials = h->partials_dev;
   const dim3 grid(h->grid, B);
-  if (h->fast) {
+  if (h->fast && d.dim == 1) {
+    switch (K) {
+      case 1: lsm_step_dim1_kernel<Real, 1><<<grid, kLsmBlock, 0, s>>>(A); break;
+      case 2: lsm_step_dim1_kernel<Real, 2><<<grid, kLsmBlock, 0, s>>>(A); break;
+      case 3: lsm_step_dim1_kernel<Real, 3><<<grid, kLsmBlock, 0, s>>>(A); break;
+      case 4: lsm_step_dim1_kernel<Real, 4><<<grid, kLsmBlock, 0, s>>>(A); break;
+      case 5: lsm_step_dim1_kernel<Real, 5><<<grid, kLsmBlock, 0, s>>>(A); break;
+      default: lsm_step_dim1_kernel<Real, 6><<<grid, kLsmBlock, 0, s>>>(A); break;
+    }
+  } else if (h->fast) {
     lsm_step_fast_kernel<Real><<<grid, kLsmBlock, 0, s>>>(A);
   } else {
     const size_t smem = (static_cast<size_t>(kLsmTile) * K + kLsmTile) * sizeof(double);

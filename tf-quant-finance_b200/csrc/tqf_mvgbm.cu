@@ -37,6 +37,7 @@ struct MvParams {
   const int* record_slot;  // device [S+1]: eval flags (price) / slots (paths)
   Real* out;
   int64_t stride_path, stride_time, stride_dim;
+  int store_exp;
   Real x0[DMAX], mu[DMAX], sigma[DMAX];
   Real L[DMAX * (DMAX + 1) / 2];  // packed rows of the lower-triangular factor
 };
@@ -118,7 +119,7 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
         for (int i = 0; i < DMAX; ++i)
           if (i < dim)
             P.out[static_cast<int64_t>(local) * P.stride_path + slot * P.stride_time +
-                  i * P.stride_dim] = x[i];
+                  i * P.stride_dim] = P.store_exp ? static_cast<Real>(exp(x[i])) : x[i];
       }
     };
     if (P.record_slot[0] >= 0) {
@@ -243,6 +244,7 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
   P.stride_path = a.stride_path;
   P.stride_time = a.stride_time;
   P.stride_dim = a.stride_dim;
+  P.store_exp = a.store_exp;
   for (int i = 0; i < DMAX; ++i) {
     const bool in = i < a.dim;
     P.x0[i] = in ? static_cast<Real>(a.x0[i]) : Real(0);

@@ -265,7 +265,8 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
 template <typename Real>
 static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                      const int32_t* record_slot, void* out_dev, int64_t stride_path,
-                     int64_t stride_time, int64_t stride_dim, cudaStream_t stream) {
+                     int64_t stride_time, int64_t stride_dim, int transform,
+                     cudaStream_t stream) {
   KParams<Real> P;
   fill_common(plan, path_offset, path_count, &P);
   const size_t nrec = static_cast<size_t>(plan->model.num_steps) + 1;
@@ -276,6 +277,7 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   P.stride_path = stride_path;
   P.stride_time = stride_time;
   P.stride_dim = stride_dim;
+  P.store_exp = transform == TQF_TRANSFORM_EXP ? 1 : 0;
   if (plan->model.kind == TQF_MODEL_MVGBM) {
     TQF_REQUIRE(!plan->rng.antithetic && plan->rng.type != TQF_RNG_DRAWS,
                 "MVGBM supports the Philox and Sobol generators without antithetic pairing");
@@ -304,6 +306,7 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.stride_path = stride_path;
     a.stride_time = stride_time;
     a.stride_dim = stride_dim;
+    a.store_exp = transform == TQF_TRANSFORM_EXP ? 1 : 0;
     int g = 1;
     return launch_mvgbm(a, stream, &g);
   }
@@ -444,7 +447,7 @@ int tqf_plan_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
 
 int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                    const int32_t* record_slot, void* out_dev, int64_t stride_path,
-                   int64_t stride_time, int64_t stride_dim, void* stream) {
+                   int64_t stride_time, int64_t stride_dim, int transform, void* stream) {
   TQF_REQUIRE(plan && record_slot, "null argument");
   const uint64_t units = plan->rng.antithetic ? plan->num_paths_total / 2 : plan->num_paths_total;
   TQF_REQUIRE(path_offset + path_count <= units, "shard exceeds the number of paths");
@@ -453,9 +456,9 @@ int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return plan->model.dtype == TQF_F64
              ? run_paths<double>(plan, path_offset, path_count, record_slot, out_dev, stride_path,
-                                 stride_time, stride_dim, s)
+                                 stride_time, stride_dim, transform, s)
              : run_paths<float>(plan, path_offset, path_count, record_slot, out_dev, stride_path,
-                                stride_time, stride_dim, s);
+                                stride_time, stride_dim, transform, s);
 }
 
 }  // extern "C"

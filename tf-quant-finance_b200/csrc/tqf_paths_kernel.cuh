@@ -82,6 +82,7 @@ struct KParams {
   const int* record_slot;    // device [num_steps + 1]
   Real* out;
   int64_t stride_path, stride_time, stride_dim;
+  int store_exp;             // store exp(state) (log-space models feeding LSM)
 };
 
 // ------------------------------------------------------------- models -----
@@ -407,7 +408,8 @@ path_kernel(const KParams<typename Model::Real> P) {
 #pragma unroll
               for (int j = 0; j < DIM; ++j)
                 P.out[static_cast<int64_t>(local[a] + h * P.anti_half) * P.stride_path +
-                      slot * P.stride_time + j * P.stride_dim] = x[a][h][j];
+                      slot * P.stride_time + j * P.stride_dim] =
+                    P.store_exp ? static_cast<Real>(exp(x[a][h][j])) : x[a][h][j];
           }
       }
     }
@@ -572,7 +574,8 @@ path_kernel(const KParams<typename Model::Real> P) {
 #pragma unroll
                   for (int j = 0; j < DIM; ++j)
                     P.out[static_cast<int64_t>(local[a] + h * P.anti_half) * P.stride_path +
-                          slot * P.stride_time + j * P.stride_dim] = x[a][h][j];
+                          slot * P.stride_time + j * P.stride_dim] =
+                        P.store_exp ? static_cast<Real>(exp(x[a][h][j])) : x[a][h][j];
               }
           }
         }
@@ -669,6 +672,7 @@ struct MvLaunch {
   const int* record_dev;
   void* out;
   int64_t stride_path, stride_time, stride_dim;
+  int store_exp;
 };
 
 int launch_mvgbm(const MvLaunch& a, cudaStream_t stream, int* grid_out);

@@ -325,10 +325,12 @@ class Plan:
     except Exception:  # pylint: disable=broad-except
       pass
 
-  def paths(self, record_slot, num_times, unit_offset=0, unit_count=None):
+  def paths(self, record_slot, num_times, unit_offset=0, unit_count=None,
+            exp_transform=False):
     """States at the recorded steps: a `[rows, num_times, dim]` VIEW of a
     time-major `[num_times, dim, rows]` buffer (coalesced stores, no
-    transpose).  rows = units (x2 for antithetic: partners follow)."""
+    transpose).  rows = units (x2 for antithetic: partners follow).
+    `exp_transform` stores exp(state) (log-space models)."""
     unit_count = self.units - unit_offset if unit_count is None else unit_count
     rows = unit_count * (2 if self.rng.antithetic else 1)
     dim = self.spec.dim
@@ -336,7 +338,9 @@ class Plan:
     rec = np.ascontiguousarray(record_slot, dtype=np.int32)
     _lib.check(_lib.lib().tqf_plan_paths(
         self._handle, unit_offset, unit_count, rec.ctypes.data, buf.data_ptr(),
-        1, dim * rows, rows, _tensor.current_stream_ptr()))
+        1, dim * rows, rows,
+        _lib.TRANSFORM_EXP if exp_transform else _lib.TRANSFORM_NONE,
+        _tensor.current_stream_ptr()))
     return buf.permute(2, 0, 1)
 
   def price_sums(self, payoffs, unit_offset=0, unit_count=None):
