@@ -315,3 +315,38 @@ def test_c1_notebook_configuration():
     d1 = (np.log(spot / k) + (r + sigma**2 / 2)) / sigma
     bs = spot * norm.cdf(d1) - k * np.exp(-r) * norm.cdf(d1 - sigma)
     assert abs(g - bs) < 0.5
+
+
+# ---------------------------------------------------------- Heston QE ------
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('rng', [('SOBOL', None, 0), ('STATELESS', [4, 2], 0),
+                                 ('PSEUDO_ANTITHETIC', 3, 0)], ids=lambda r: r[0])
+@pytest.mark.parametrize('grid', [dict(time_step=0.05), dict(num_time_steps=7),
+                                  dict(times_grid=[0.0, 0.1, 0.3, 0.5, 0.8, 1.0, 1.3])],
+                         ids=['dt', 'nsteps', 'grid'])
+def test_heston_qe_matches_oracle(dtype, rng, grid):
+  # HestonModel.sample_paths = Andersen QE (heston_model.py:177-460)
+  from oracle import heston_qe as oqe
+  tff = _tff()
+  from tff_b200.math import piecewise
+  rt, seed, skip = rng
+  volvol = piecewise.PiecewiseConstantFunc([0.5], [0.5, 0.9], dtype=dtype)
+  ovolvol = omodels.PiecewiseConstantFunc([0.5], [0.5, 0.9], dtype=dtype)
+  model = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=volvol,
+                                 rho=-0.7, dtype=dtype)
+  x0 = np.array([np.log(100.0), 0.02], dtype=dtype)
+  times = [0.5, 1.0]
+  n = 2000
+  got = _np(model.sample_paths(times, x0, num_samples=n,
+                               random_type=tff.math.random.RandomType[rt], seed=seed,
+                               skip=skip, **grid))
+  want = oqe.sample_paths(2.0, 0.04, ovolvol, -0.7, times, x0, num_samples=n,
+                          random_type=odraws.RandomType[rt], seed=seed, skip=skip,
+                          dtype=dtype, **grid)
+  assert got.shape == want.shape == (n, 2, 2) and got.dtype == dtype
+  if dtype == np.float64:
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
+  else:
+    # float32: the psi < 1.5 switch can flip for isolated paths; compare robustly
+    close = np.isclose(got, want, rtol=2e-4, atol=2e-5)
+    assert close.mean() > 0.999

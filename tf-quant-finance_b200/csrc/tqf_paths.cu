@@ -22,6 +22,7 @@ TQF_EXTERN_MODEL(GbmModel1F)
 TQF_EXTERN_MODEL(LinearModel1F)
 TQF_EXTERN_MODEL(HestonEulerModel)
 TQF_EXTERN_MODEL(HullWhite1FModel)
+TQF_EXTERN_MODEL(HestonQeModel)
 #undef TQF_EXTERN_MODEL
 
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_blocks,
@@ -53,6 +54,7 @@ static bool model_info(int kind, int dim, ModelInfo* info) {
     case TQF_MODEL_LINEAR_1F: *info = {1, 1, 5}; return true;
     case TQF_MODEL_HESTON_EULER: *info = {2, 2, 6}; return true;
     case TQF_MODEL_HW1F: *info = {2, 1, 5}; return true;
+    case TQF_MODEL_HESTON_QE: *info = {2, 2, 10}; return true;
     default: return false;
   }
 }
@@ -140,6 +142,8 @@ static int dispatch(const tqf_plan* plan, int mode, int grid, size_t smem, const
       return launch_path_kernel<HestonEulerModel<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     case TQF_MODEL_HW1F:
       return launch_path_kernel<HullWhite1FModel<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+    case TQF_MODEL_HESTON_QE:
+      return launch_path_kernel<HestonQeModel<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     default:
       set_error("model kind not supported by the generic path kernel");
       return TQF_ERR_UNSUPPORTED;

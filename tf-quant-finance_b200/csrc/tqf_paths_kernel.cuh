@@ -165,6 +165,39 @@ struct HestonEulerModel {  // heston/heston_model.py:143-173; state [X = log S, 
   __device__ static __forceinline__ float sqrt_abs(float v) { return sqrtf(fabsf(v)); }
 };
 
+template <typename R>
+struct HestonQeModel {
+  // Andersen's Quadratic-Exponential step (heston/heston_model.py:402-431,
+  // 522-572): z[0] drives the variance, z[1] the log-spot.  Per-step constants
+  // from the host: active (dt > tolerance), e = exp(-kappa dt), theta,
+  // s^2 = c_s1 V + c_s0, and k0..k4 of the log-spot update.
+  using Real = R;
+  static constexpr int DIM = 2, NF = 2, NCOEF = 10;
+  __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
+                                              const Real (&c)[NCOEF]) {
+    if (c[0] == Real(0)) return;  // zero-length step: consumes its draws only
+    const Real v = x[1];
+    const Real m = c[2] + (v - c[2]) * c[1];
+    const Real s2 = fma(v, c[3], c[4]);
+    const Real psi = s2 / (m * m);
+    Real vn;
+    if (psi < Real(1.5)) {
+      const Real psi_inv = Real(2) / psi;
+      const Real b2 = psi_inv - Real(1) + sqrt(psi_inv * (psi_inv - Real(1)));
+      const Real a = m / (Real(1) + b2);
+      const Real t = sqrt(b2) + z[0];
+      vn = a * (t * t);
+    } else {
+      const Real p = (psi - Real(1)) / (psi + Real(1));
+      const Real beta = (Real(1) - p) / m;
+      const Real u = Real(0.5) * (Real(1) + erf(z[0] * Real(0.70710678118654752440)));
+      vn = u > p ? (log(Real(1) - p) - log(Real(1) - u)) / beta : Real(0);
+    }
+    x[0] = (((x[0] + c[5]) + c[6] * v) + c[7] * vn) + sqrt(c[8] * v + c[9] * vn) * z[1];
+    x[1] = vn;
+  }
+};
+
 // ------------------------------------------------------- normal streams ---
 // PPT independent Philox streams held by one thread (one per path it carries);
 // all of them sit at the same position inside their group, so the Box-Muller
