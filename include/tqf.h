@@ -155,7 +155,7 @@ typedef struct tqf_model_desc {
   int32_t num_steps;       /* steps to execute                              */
   int32_t num_steps_total; /* len(all_times)-1: stride of the draw layout   */
   int32_t num_coef;        /* columns of `coef`                             */
-  int32_t reserved;
+  int32_t reserved;        /* MVGBM: 1 = exact log-space step (state = log x) */
   /* host double [num_steps][num_coef]; column meaning depends on `kind`
    * (documented in DESIGN.md); values are exactly representable in `dtype`.
    * Columns 0/1 are always dt and sqrt(dt).                                */

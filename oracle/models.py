@@ -155,3 +155,58 @@ def hull_white_1f_closures(mean_reversion, volatility, forward_rate_fn,
     drift = drift + (s**2 / 2 / k * (1 - np.exp(-2 * k * t)) - k * x)
     return drift
   return drift_fn, vol_fn
+
+
+def gbm_exact_sample_paths(mean, volatility, times, initial_state=None,
+                           num_samples=1, random_type=None, seed=None, skip=0,
+                           dtype=np.float64):
+  """`GeometricBrownianMotion.sample_paths` (exact log-normal sampler,
+  `univariate_geometric_brownian_motion.py:155-317`) -> [N, k, 1]."""
+  from oracle import draws as draws_lib
+  dtype = np.dtype(dtype)
+  times = np.asarray(times, dtype=dtype)
+  k = times.shape[0]
+  x0 = np.ones(1, dtype) if initial_state is None else np.asarray(initial_state, dtype)
+  z = draws_lib.generate_mc_normal_draws(
+      1, k, num_samples, draws_lib.RandomType.PSEUDO if random_type is None else random_type,
+      seed=seed, dtype=dtype, skip=skip)                      # [k, N, 1]
+  t = np.concatenate([np.zeros(1, dtype), times])
+
+  def integ(p, square=False):
+    if callable(p):
+      q = p if not square else PiecewiseConstantFunc(p.jump_locations(), p.values()**2, dtype=dtype)
+      return q.integrate(t[:-1], t[1:])
+    v = np.asarray(p, dtype)
+    return (v * v if square else v) * (t[1:] - t[:-1])
+  mean_int = integ(mean)
+  vol2_int = integ(volatility, square=True)
+  log_inc = (mean_int - vol2_int / 2)[None, :] + np.sqrt(vol2_int)[None, :] * z[:, :, 0].T
+  lower = np.tril(np.ones((k, k), dtype))
+  cumsum = log_inc @ lower.T
+  return (x0[..., None] * np.exp(cumsum))[..., None].astype(dtype)
+
+
+def mvgbm_exact_sample_paths(means, volatilities, corr_matrix, times,
+                             initial_state=None, num_samples=1, random_type=None,
+                             seed=None, skip=0, dtype=np.float64):
+  """`MultivariateGeometricBrownianMotion.sample_paths`
+  (`multivariate_geometric_brownian_motion.py:153-282`) -> [N, k, dim]."""
+  from oracle import draws as draws_lib
+  dtype = np.dtype(dtype)
+  means = np.asarray(means, dtype)
+  vols = np.asarray(volatilities, dtype)
+  dim = means.shape[0]
+  times = np.asarray(times, dtype=dtype)
+  k = times.shape[0]
+  x0 = np.ones(dim, dtype) if initial_state is None else np.asarray(initial_state, dtype)
+  z = draws_lib.generate_mc_normal_draws(
+      dim, k, num_samples, draws_lib.RandomType.PSEUDO if random_type is None else random_type,
+      seed=seed, dtype=dtype, skip=skip)                      # [k, N, dim]
+  t = np.concatenate([np.zeros(1, dtype), times])
+  dt = (t[1:] - t[:-1])[:, None, None]
+  if corr_matrix is not None:
+    chol = np.linalg.cholesky(np.asarray(corr_matrix, dtype)).astype(dtype)
+    z = np.einsum('ij,knj->kni', chol, z).astype(dtype)
+  log_inc = (means - vols**2 / 2) * dt + np.sqrt(dt) * vols * z    # [k, N, dim]
+  cumsum = np.cumsum(log_inc, axis=0)
+  return (x0 * np.exp(np.transpose(cumsum, [1, 0, 2]))).astype(dtype)

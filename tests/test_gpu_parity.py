@@ -350,3 +350,45 @@ def test_heston_qe_matches_oracle(dtype, rng, grid):
     # float32: the psi < 1.5 switch can flip for isolated paths; compare robustly
     close = np.isclose(got, want, rtol=2e-4, atol=2e-5)
     assert close.mean() > 0.999
+
+
+# ------------------------------------------------ exact GBM samplers ------
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('rng', [('SOBOL', None, 5), ('STATELESS', [4, 2], 0),
+                                 ('STATELESS_ANTITHETIC', [1, 2], 0)], ids=lambda r: r[0])
+def test_exact_gbm_sample_paths(dtype, rng):
+  # GeometricBrownianMotion.sample_paths (univariate_...py:155-317)
+  tff = _tff()
+  from tff_b200.math import piecewise
+  rt, seed, skip = rng
+  vol = piecewise.PiecewiseConstantFunc([0.3, 0.8], [0.1, 0.2, 0.15], dtype=dtype)
+  ovol = omodels.PiecewiseConstantFunc([0.3, 0.8], [0.1, 0.2, 0.15], dtype=dtype)
+  model = tff.models.GeometricBrownianMotion(0.03, vol, dtype=dtype)
+  times = [0.1, 0.5, 1.0, 2.0]
+  n = 3000
+  got = _np(model.sample_paths(times, initial_state=np.array([1.5], dtype), num_samples=n,
+                               random_type=tff.math.random.RandomType[rt], seed=seed, skip=skip))
+  want = omodels.gbm_exact_sample_paths(0.03, ovol, times, np.array([1.5], dtype), n,
+                                        odraws.RandomType[rt], seed, skip, dtype)
+  assert got.shape == want.shape == (n, 4, 1) and got.dtype == dtype
+  np.testing.assert_allclose(got, want, rtol=1e-12 if dtype == np.float64 else 2e-5)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_exact_multivariate_gbm_sample_paths(dtype):
+  # MultivariateGeometricBrownianMotion.sample_paths (multivariate_...py:153-282)
+  tff = _tff()
+  dim = 5
+  means = np.linspace(0.01, 0.05, dim).astype(dtype)
+  vols = np.linspace(0.1, 0.3, dim).astype(dtype)
+  corr = (0.2 + 0.8 * np.eye(dim)).astype(dtype)
+  model = tff.models.MultivariateGeometricBrownianMotion(dim, means, vols, corr, dtype=dtype)
+  times = [0.25, 1.0, 1.5]
+  x0 = np.linspace(1.0, 2.0, dim).astype(dtype)
+  n = 2500
+  got = _np(model.sample_paths(times, initial_state=x0, num_samples=n,
+                               random_type=tff.math.random.RandomType.SOBOL, skip=11))
+  want = omodels.mvgbm_exact_sample_paths(means, vols, corr, times, x0, n,
+                                          odraws.RandomType.SOBOL, None, 11, dtype)
+  assert got.shape == want.shape == (n, 3, dim)
+  np.testing.assert_allclose(got, want, rtol=1e-12 if dtype == np.float64 else 2e-5)

@@ -38,6 +38,7 @@ struct MvParams {
   Real* out;
   int64_t stride_path, stride_time, stride_dim;
   int store_exp;
+  int exact_log;  // additive log-space step (exact sampler) instead of the Euler step
   Real x0[DMAX], mu[DMAX], sigma[DMAX];
   Real L[DMAX * (DMAX + 1) / 2];  // packed rows of the lower-triangular factor
 };
@@ -193,9 +194,15 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
         const Real dt = P.coef[2 * s], sq = P.coef[2 * s + 1];
 #pragma unroll
         for (int i = 0; i < DMAX; ++i) {
-          const Real dt_inc = dt * (P.mu[i] * x[i]);
-          const Real dw_inc = (P.sigma[i] * x[i]) * (z[i] * sq);
-          x[i] = (x[i] + dt_inc) + dw_inc;
+          if (P.exact_log) {
+            // exact log-normal increment (multivariate_geometric_brownian_motion.py:262-266);
+            // mu holds means - vols^2 / 2
+            x[i] = x[i] + (P.mu[i] * dt + (sq * P.sigma[i]) * z[i]);
+          } else {
+            const Real dt_inc = dt * (P.mu[i] * x[i]);
+            const Real dw_inc = (P.sigma[i] * x[i]) * (z[i] * sq);
+            x[i] = (x[i] + dt_inc) + dw_inc;
+          }
         }
         const int flag = P.record_slot[s + 1];
         if (flag >= 0) {
@@ -245,6 +252,7 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
   P.stride_time = a.stride_time;
   P.stride_dim = a.stride_dim;
   P.store_exp = a.store_exp;
+  P.exact_log = a.exact_log;
   for (int i = 0; i < DMAX; ++i) {
     const bool in = i < a.dim;
     P.x0[i] = in ? static_cast<Real>(a.x0[i]) : Real(0);

@@ -245,6 +245,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.pay = P.pay;
     a.partials = plan->partials_dev;
     a.record_dev = plan->record_dev;
+    a.exact_log = plan->model.reserved;
     int rc = launch_mvgbm(a, stream, &grid);
     if (rc != TQF_OK) return rc;
     reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev);
@@ -311,6 +312,7 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.stride_time = stride_time;
     a.stride_dim = stride_dim;
     a.store_exp = transform == TQF_TRANSFORM_EXP ? 1 : 0;
+    a.exact_log = plan->model.reserved;
     int g = 1;
     return launch_mvgbm(a, stream, &g);
   }

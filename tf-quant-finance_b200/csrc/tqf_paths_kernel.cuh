@@ -706,6 +706,7 @@ struct MvLaunch {
   void* out;
   int64_t stride_path, stride_time, stride_dim;
   int store_exp;
+  int exact_log;
 };
 
 int launch_mvgbm(const MvLaunch& a, cudaStream_t stream, int* grid_out);

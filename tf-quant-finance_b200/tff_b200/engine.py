@@ -121,9 +121,12 @@ class MvGbmSpec(ModelSpec):
   parameters."""
   kind, num_coef = _lib.MODEL_MVGBM, 2
 
-  def __init__(self, means, volatilities, corr_matrix, dim):
+  def __init__(self, means, volatilities, corr_matrix, dim, exact_log=False):
     self.dim = self.num_factors = int(dim)
     self.means, self.volatilities, self.corr_matrix = means, volatilities, corr_matrix
+    # exact_log: the state is log x and the step adds the exact log-normal
+    # increment (means - vols^2/2) dt + sqrt(dt) vols (L z)
+    self.exact_log = bool(exact_log)
 
   def coef_table(self, all_times, dtype):
     _, dt, sq = self._dt_columns(all_times, dtype)
@@ -133,6 +136,8 @@ class MvGbmSpec(ModelSpec):
     d = self.dim
     mu = np.broadcast_to(np.asarray(self.means, dtype=dtype), (d,))
     sg = np.broadcast_to(np.asarray(self.volatilities, dtype=dtype), (d,))
+    if self.exact_log:
+      mu = (mu - sg**2 / 2).astype(dtype)
     if self.corr_matrix is None:
       chol = np.eye(d, dtype=dtype)
     else:
@@ -280,6 +285,7 @@ class Plan:
     m.dim, m.num_factors = spec.dim, spec.num_factors
     m.num_steps, m.num_steps_total = self.num_steps, self.num_steps_total
     m.num_coef = spec.num_coef
+    m.reserved = int(getattr(spec, 'exact_log', False))
     m.coef = table.ctypes.data
     m.x0 = x0.ctypes.data
     extra = getattr(spec, 'device_arrays', None)

@@ -81,6 +81,8 @@ class MultivariateGeometricBrownianMotion(ito_process.ItoProcess):
                    random_type=None, seed=None, skip=0, normal_draws=None,
                    name=None):
     """Exact log-normal sampler (`multivariate_...py:153-282`)."""
-    raise NotImplementedError(
-        'The exact multivariate GBM sampler is not implemented by the B200 '
-        'engine yet (SURVEY 8f-1); use sample_paths_euler.')
+    from tff_b200.models.geometric_brownian_motion import exact  # pylint: disable=g-import-not-at-top
+    del name
+    return exact.sample_paths_multivariate(
+        self, times, initial_state=initial_state, num_samples=num_samples,
+        random_type=random_type, seed=seed, skip=skip, normal_draws=normal_draws)
