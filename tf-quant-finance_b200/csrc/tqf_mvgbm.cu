@@ -50,6 +50,12 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
   __shared__ uint4 s_low[kSobolTileDims * 2];
   __shared__ double s_acc[kWarps * TQF_MAX_PAYOFFS * 3];
   __shared__ __align__(16) double s_cst[TQF_COEF_COUNT];
+  // normals of one step, [dim][kBlock]: the draw loop is ROLLED (small code) and
+  // hands its results to the unrolled mat-vec through shared memory -- the fully
+  // unrolled version overflowed the instruction cache (ncu: 2.0 no_instruction
+  // stalls per issue).
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  Real* s_z = reinterpret_cast<Real*>(s_dyn);
   const int tid = threadIdx.x;
   fm::fill_smem_coef(s_cst, tid, kBlock);
   const fm::SmemTab tab(s_cst);
@@ -147,61 +153,71 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
         __syncthreads();
       }
       for (int s = s0; s < s1; ++s) {
-        Real z[DMAX];
         if (P.rngk == RNGK_SOBOL) {
-#pragma unroll
-          for (int j = 0; j < DMAX; ++j) {
-            if (j < dim) {
-              const int dd = (s - s0) * dim + j;
-              const uint4 l0 = s_low[2 * dd];
-              const uint4 l1 = s_low[2 * dd + 1];
-              uint32_t xb = s_high[dd];
-              xb ^= l0.x & lowmask[0];
-              xb ^= l0.y & lowmask[1];
-              xb ^= l0.z & lowmask[2];
-              xb ^= l0.w & lowmask[3];
-              xb ^= l1.x & lowmask[4];
-              xb ^= l1.y & lowmask[5];
-              xb ^= l1.z & lowmask[6];
-              const uint32_t xin[1] = {xb};
-              Real zo[1];
-              sobol_normals<1>(tab, xin, zo);
-              z[j] = zo[0];
-            } else {
-              z[j] = 0;
-            }
+          const uint4* lp = s_low + 2 * (s - s0) * dim;
+          const uint32_t* hp = s_high + (s - s0) * dim;
+#pragma unroll 8
+          for (int j = 0; j < dim; ++j) {
+            const uint4 l0 = lp[2 * j];
+            const uint4 l1 = lp[2 * j + 1];
+            uint32_t xb = hp[j];
+            xb ^= l0.x & lowmask[0];
+            xb ^= l0.y & lowmask[1];
+            xb ^= l0.z & lowmask[2];
+            xb ^= l0.w & lowmask[3];
+            xb ^= l1.x & lowmask[4];
+            xb ^= l1.y & lowmask[5];
+            xb ^= l1.z & lowmask[6];
+            const uint32_t xin[1] = {xb};
+            Real zo[1];
+            sobol_normals<1>(tab, xin, zo);
+            s_z[j * kBlock + tid] = zo[0];
           }
         } else {
-#pragma unroll
-          for (int j = 0; j < DMAX; ++j) {
-            if (j < dim) {
-              Real zo[1];
-              stream.next(P.key, P.ctr, tab, zo);
-              z[j] = zo[0];
-            } else {
-              z[j] = 0;
-            }
+          for (int j = 0; j < dim; ++j) {
+            Real zo[1];
+            stream.next(P.key, P.ctr, tab, zo);
+            s_z[j * kBlock + tid] = zo[0];
           }
         }
+        // own column only: no barrier needed between the writes above and the reads
+        Real z[DMAX];
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) z[j] = j < dim ? s_z[j * kBlock + tid] : Real(0);
         // correlate in place, highest row first: z_i <- sum_{j<=i} L_ij z_j
-#pragma unroll
-        for (int i = DMAX - 1; i >= 0; --i) {
-          Real acc = 0;
-#pragma unroll
-          for (int j = 0; j <= i; ++j) acc = fma(P.L[i * (i + 1) / 2 + j], z[j], acc);
-          z[i] = acc;
-        }
         const Real dt = P.coef[2 * s], sq = P.coef[2 * s + 1];
+        // Rows are processed from the bottom in blocks of RB, each block with RB
+        // independent accumulators (the rows only read z_j, j <= i, which are
+        // still the raw normals: results overwrite z from the top down).
+        constexpr int RB = DMAX >= 8 ? 8 : DMAX;
 #pragma unroll
-        for (int i = 0; i < DMAX; ++i) {
-          if (P.exact_log) {
-            // exact log-normal increment (multivariate_geometric_brownian_motion.py:262-266);
-            // mu holds means - vols^2 / 2
-            x[i] = x[i] + (P.mu[i] * dt + (sq * P.sigma[i]) * z[i]);
-          } else {
-            const Real dt_inc = dt * (P.mu[i] * x[i]);
-            const Real dw_inc = (P.sigma[i] * x[i]) * (z[i] * sq);
-            x[i] = (x[i] + dt_inc) + dw_inc;
+        for (int ib = DMAX - 1; ib >= 0; ib -= RB) {
+          Real acc[RB];
+#pragma unroll
+          for (int r = 0; r < RB; ++r) acc[r] = 0;
+#pragma unroll
+          for (int j = 0; j <= ib; ++j) {
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+              const int i = ib - r;
+              if (i >= 0 && j <= i) acc[r] = fma(P.L[i * (i + 1) / 2 + j], z[j], acc[r]);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const int i = ib - r;
+            if (i >= 0) {
+              z[i] = acc[r];
+              if (P.exact_log) {
+                // exact log-normal increment (multivariate_geometric_brownian_motion.py:262-266);
+                // mu holds means - vols^2 / 2
+                x[i] = x[i] + (P.mu[i] * dt + (sq * P.sigma[i]) * z[i]);
+              } else {
+                const Real dt_inc = dt * (P.mu[i] * x[i]);
+                const Real dw_inc = (P.sigma[i] * x[i]) * (z[i] * sq);
+                x[i] = (x[i] + dt_inc) + dw_inc;
+              }
+            }
           }
         }
         const int flag = P.record_slot[s + 1];
@@ -267,7 +283,12 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
                                   : static_cast<uint64_t>(a.max_grid));
   if (grid < 1) grid = 1;
   *grid_out = grid;
-  mvgbm_kernel<Real, DMAX><<<grid, kBlock, 0, stream>>>(P);
+  const size_t smem = static_cast<size_t>(DMAX) * kBlock * sizeof(Real);
+  if (smem > 48 * 1024)
+    TQF_CUDA_OK(cudaFuncSetAttribute(mvgbm_kernel<Real, DMAX>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+  mvgbm_kernel<Real, DMAX><<<grid, kBlock, smem, stream>>>(P);
   TQF_CUDA_OK(cudaGetLastError());
   return TQF_OK;
 }
