@@ -241,8 +241,9 @@ __device__ __forceinline__ void log_pos_v(const Tab& tab, const double (&a)[K], 
   horner_v<TQF_LOG_R_OFF, TQF_LOG_R_N, K>(tab, z, R);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const double t = fma(s[k] * z[k], R[k], kd[k] * kLn2Lo);
-    out[k] = fma(kd[k], kLn2Hi, fma(2.0, s[k], t));
+    // k ln2_hi + (s (2 + z R) + k ln2_lo)
+    const double q = fma(z[k], R[k], 2.0);
+    out[k] = fma(kd[k], kLn2Hi, fma(s[k], q, kd[k] * kLn2Lo));
   }
 }
 
@@ -258,12 +259,16 @@ __device__ __forceinline__ void ndtri_t_v(const Tab& tab, const double (&t)[K], 
 #pragma unroll
   for (int k = 0; k < K; ++k) a[k] = fma(-t[k], t[k], 1.0);
   log_pos_v<K>(tab, a, w);
-  bool tail = false;
+  // w[k] holds log(a) = -w <= 0: its high word, read as unsigned, grows with w,
+  // so one integer max + compare finds out whether any draw is in the tail.
+  uint32_t hmax = 0;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    y[k] = -TQF_NDTRI_C_MID - w[k];   // w[k] holds log(a) = -w
-    tail = tail || (w[k] <= -TQF_NDTRI_W0);
+    y[k] = -TQF_NDTRI_C_MID - w[k];
+    const uint32_t h = static_cast<uint32_t>(__double2hiint(w[k]));
+    hmax = h > hmax ? h : hmax;
   }
+  const bool tail = hmax >= 0xC0190000u;  // high word of -6.25
   horner_v<TQF_NDTRI_C_OFF, TQF_NDTRI_C_N, K>(tab, y, p);
   if (tail) {
 #pragma unroll

@@ -567,10 +567,14 @@ path_kernel(const KParams<typename Model::Real> P) {
             for (int j = 0; j < NF; ++j)
               z[a][j] = P.draws[first_element[a] + static_cast<size_t>(s) * NF + j];
         }
-        const Real* c = coef_tab + s * NCOEF;
         Real cc[NCOEF];
+        if (P.tables_in_smem) {   // shared-window loads (LDS), not generic LD
 #pragma unroll
-        for (int i = 0; i < NCOEF; ++i) cc[i] = c[i];
+          for (int i = 0; i < NCOEF; ++i) cc[i] = s_coef[s * NCOEF + i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < NCOEF; ++i) cc[i] = P.coef[s * NCOEF + i];
+        }
 #pragma unroll
         for (int a = 0; a < PPT; ++a) {
           Model::step(x[a][0], z[a], cc);
