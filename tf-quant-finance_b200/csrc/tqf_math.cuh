@@ -14,7 +14,7 @@
 //
 // Coefficients: tools/fit_math.py -> tqf_math_coef.h (highest order first).
 // Accuracy (checked on the GPU against mpmath by tests/test_gpu_math.py):
-// <= 2 ulp for log / sqrt / sincos on their stated domains, <= 4e-16 relative
+// <= 3 ulp for log, <= 1 ulp for sqrt, <= 2 ulp for sincos on their stated domains, <= 5e-16 relative
 // for ndtri.
 #pragma once
 
