@@ -46,13 +46,14 @@ extern "C" {
 #define TQF_RNG_DRAWS 3  /* caller-supplied normal_draws=                    */
 
 /* models: the drift/volatility closures the Euler loop evaluates per step */
-#define TQF_MODEL_AFFINE_1F 1     /* x' = x + dt (a0 + a1 x) + b sqrt_dt z  */
+#define TQF_MODEL_AFFINE_1F 1     /* a = a0 + a1 x,  S = b0 + b1 x (dim 1)   */
 #define TQF_MODEL_GBM_1F 2        /* a = mu x,  S = sigma x                  */
 #define TQF_MODEL_HESTON_EULER 3  /* heston/heston_model.py:143-173          */
 #define TQF_MODEL_HESTON_QE 4     /* heston/heston_model.py:322-572          */
 #define TQF_MODEL_MVGBM 5         /* multivariate_geometric_brownian_motion  */
 #define TQF_MODEL_LINEAR_1F 6     /* x' = A x + B + C z                      */
 #define TQF_MODEL_HW1F 7          /* HW exact OU step + short-rate integral  */
+#define TQF_MODEL_AFFINE_ND 8     /* a = a0 + A1 x, S = B, dim 2..4          */
 
 /* payoff kinds (reduced in-kernel; callers: e.g. hull_white/swaption.py:310) */
 #define TQF_PAYOFF_CALL 1          /* max(f(X_T) - K, 0)                    */

@@ -23,6 +23,9 @@ TQF_EXTERN_MODEL(LinearModel1F)
 TQF_EXTERN_MODEL(HestonEulerModel)
 TQF_EXTERN_MODEL(HullWhite1FModel)
 TQF_EXTERN_MODEL(HestonQeModel)
+TQF_EXTERN_MODEL(AffineModel2D)
+TQF_EXTERN_MODEL(AffineModel3D)
+TQF_EXTERN_MODEL(AffineModel4D)
 #undef TQF_EXTERN_MODEL
 
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_blocks,
@@ -49,7 +52,10 @@ struct ModelInfo {
 static bool model_info(int kind, int dim, ModelInfo* info) {
   switch (kind) {
     case TQF_MODEL_MVGBM: *info = {dim, dim, 2}; return dim >= 1 && dim <= 64;
-    case TQF_MODEL_AFFINE_1F: *info = {1, 1, 5}; return true;
+    case TQF_MODEL_AFFINE_1F: *info = {1, 1, 6}; return true;
+    case TQF_MODEL_AFFINE_ND:
+      *info = {dim, dim, 2 + dim + 2 * dim * dim};
+      return dim >= 2 && dim <= 4;
     case TQF_MODEL_GBM_1F: *info = {1, 1, 4}; return true;
     case TQF_MODEL_LINEAR_1F: *info = {1, 1, 5}; return true;
     case TQF_MODEL_HESTON_EULER: *info = {2, 2, 6}; return true;
@@ -103,8 +109,7 @@ static void fill_common(const tqf_plan* plan, uint64_t path_offset, uint64_t pat
   P->coef = static_cast<const Real*>(plan->coef_dev);
   P->num_steps = plan->model.num_steps;
   P->num_steps_total = plan->model.num_steps_total;
-  P->x0[0] = static_cast<Real>(plan->x0[0]);
-  P->x0[1] = static_cast<Real>(plan->x0[1]);
+  for (int j = 0; j < 4; ++j) P->x0[j] = static_cast<Real>(plan->x0[j]);
   P->key = PhiloxKey{plan->rng.key[0], plan->rng.key[1]};
   P->ctr = PhiloxCtr{plan->rng.counter[0], plan->rng.counter[1], plan->rng.counter[2],
                      plan->rng.counter[3]};
@@ -144,6 +149,12 @@ static int dispatch(const tqf_plan* plan, int mode, int grid, size_t smem, const
       return launch_path_kernel<HullWhite1FModel<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     case TQF_MODEL_HESTON_QE:
       return launch_path_kernel<HestonQeModel<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+    case TQF_MODEL_AFFINE_ND:
+      if (plan->info.dim == 2)
+        return launch_path_kernel<AffineModel2D<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+      if (plan->info.dim == 3)
+        return launch_path_kernel<AffineModel3D<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+      return launch_path_kernel<AffineModel4D<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     default:
       set_error("model kind not supported by the generic path kernel");
       return TQF_ERR_UNSUPPORTED;

@@ -58,7 +58,7 @@ struct KParams {
   int tables_in_smem;  // coef / record_slot staged in shared memory
   int num_steps;
   int num_steps_total;
-  Real x0[2];
+  Real x0[4];
   // rng
   PhiloxKey key;
   PhiloxCtr ctr;
@@ -91,17 +91,48 @@ struct KParams {
 // x' = (x + dt a(t,x)) + S(t,x) dw with t = times[i+1].
 
 template <typename R>
-struct AffineModel1F {  // a = a0 + a1 x, S = b
+struct AffineModel1F {  // a = a0 + a1 x, S = b0 + b1 x
   using Real = R;
-  static constexpr int DIM = 1, NF = 1, NCOEF = 5;
+  static constexpr int DIM = 1, NF = 1, NCOEF = 6;
   __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
                                               const Real (&c)[NCOEF]) {
     const Real dw = z[0] * c[1];
     const Real dt_inc = c[0] * (c[2] + c[3] * x[0]);
-    const Real dw_inc = c[4] * dw;
+    const Real dw_inc = (c[4] + c[5] * x[0]) * dw;
     x[0] = (x[0] + dt_inc) + dw_inc;
   }
 };
+
+// Generic affine Ito process of dimension D (2..4):
+//   a(t, x) = a0(t) + A1(t) x,   S(t, x) = B(t)   (state-independent volatility)
+// coef: dt, sqrt_dt, a0[D], A1[D][D] row-major, B[D][D] row-major.
+template <typename R, int D>
+struct AffineModelND {
+  using Real = R;
+  static constexpr int DIM = D, NF = D, NCOEF = 2 + D + 2 * D * D;
+  __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
+                                              const Real (&c)[NCOEF]) {
+    Real dw[D], xn[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) dw[j] = z[j] * c[1];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      Real drift = c[2 + i];
+      Real diff = 0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        drift = fma(c[2 + D + i * D + j], x[j], drift);
+        diff = fma(c[2 + D + D * D + i * D + j], dw[j], diff);
+      }
+      xn[i] = (x[i] + c[0] * drift) + diff;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = xn[i];
+  }
+};
+template <typename R> using AffineModel2D = AffineModelND<R, 2>;
+template <typename R> using AffineModel3D = AffineModelND<R, 3>;
+template <typename R> using AffineModel4D = AffineModelND<R, 4>;
 
 template <typename R>
 struct GbmModel1F {  // a = mu x, S = sigma x  (univariate_geometric_brownian_motion.py:127-153)

@@ -26,6 +26,7 @@ MODEL_HESTON_QE = 4
 MODEL_MVGBM = 5
 MODEL_LINEAR_1F = 6
 MODEL_HW1F = 7
+MODEL_AFFINE_ND = 8
 PAYOFF_CALL = 1
 PAYOFF_PUT = 2
 PAYOFF_UP_OUT_CALL = 3

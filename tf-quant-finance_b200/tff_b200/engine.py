@@ -47,17 +47,97 @@ class ModelSpec:
 
 
 class AffineSpec1F(ModelSpec):
-  """dX = (a0(t) + a1(t) X) dt + b(t) dW."""
-  kind, dim, num_factors, num_coef = _lib.MODEL_AFFINE_1F, 1, 1, 5
+  """dX = (a0(t) + a1(t) X) dt + (b0(t) + b1(t) X) dW."""
+  kind, dim, num_factors, num_coef = _lib.MODEL_AFFINE_1F, 1, 1, 6
 
-  def __init__(self, a0, a1, b):
-    self.a0, self.a1, self.b = a0, a1, b
+  def __init__(self, a0, a1, b, b1=0.0):
+    self.a0, self.a1, self.b, self.b1 = a0, a1, b, b1
 
   def coef_table(self, all_times, dtype):
     t, dt, sq = self._dt_columns(all_times, dtype)
     cols = [dt, sq, _eval_param(self.a0, t, dtype), _eval_param(self.a1, t, dtype),
-            _eval_param(self.b, t, dtype)]
+            _eval_param(self.b, t, dtype), _eval_param(self.b1, t, dtype)]
     return np.stack(cols, -1).astype(np.float64)
+
+
+class ProbedAffineSpec(ModelSpec):
+  """An arbitrary Python (drift_fn, volatility_fn) pair that turns out to be
+  affine: a(t, x) = a0(t) + A1(t) x and S(t, x) = B0(t) (+ B1(t) x for dim 1).
+
+  The callables are evaluated ON THE HOST at every grid time for a few probe
+  states; the coefficients are solved from the probes and verified on two
+  further random states.  A pair that is not affine is rejected -- the CUDA
+  kernels cannot run Python, and there is no CPU fallback."""
+
+  def __init__(self, dim, drift_fn, volatility_fn):
+    if dim < 1 or dim > 4:
+      raise NotImplementedError(
+          'generic drift/volatility callables are supported for dim <= 4')
+    self.dim = self.num_factors = int(dim)
+    self.kind = _lib.MODEL_AFFINE_1F if dim == 1 else _lib.MODEL_AFFINE_ND
+    self.num_coef = 6 if dim == 1 else 2 + dim + 2 * dim * dim
+    self.drift_fn, self.volatility_fn = drift_fn, volatility_fn
+
+  def _call(self, fn, t, x, dtype, want_matrix):
+    """fn(t, x) with torch tensors first, numpy as a second attempt."""
+    d = self.dim
+    errors = []
+    for mode in ('torch', 'numpy'):
+      try:
+        if mode == 'torch':
+          tt = torch.tensor(float(t), dtype=_tensor.torch_dtype(dtype))
+          xx = torch.as_tensor(np.ascontiguousarray(x, dtype=dtype))
+          out = fn(tt, xx)
+          if isinstance(out, torch.Tensor):
+            out = out.detach().cpu().numpy()
+        else:
+          out = fn(dtype.type(t), np.ascontiguousarray(x, dtype=dtype))
+        out = np.asarray(out, dtype=np.float64)
+        shape = (x.shape[0], d, d) if want_matrix else (x.shape[0], d)
+        return np.broadcast_to(out, shape)
+      except Exception as e:  # pylint: disable=broad-except
+        errors.append('%s: %r' % (mode, e))
+    raise NotImplementedError(
+        'could not evaluate the drift/volatility callable on the host '
+        '(tried torch and numpy inputs): ' + '; '.join(errors))
+
+  def coef_table(self, all_times, dtype):
+    dtype = np.dtype(dtype)
+    d = self.dim
+    t, dt, sq = self._dt_columns(all_times, dtype)
+    rs = np.random.RandomState(12345)
+    # probes: origin, unit vectors, two random check points
+    probes = np.concatenate([np.zeros((1, d)), np.eye(d), rs.uniform(0.5, 2.0, (2, d))])
+    rows = []
+    for i in range(t.shape[0]):
+      a = self._call(self.drift_fn, t[i], probes, dtype, False)          # [P, d]
+      s_ = self._call(self.volatility_fn, t[i], probes, dtype, True)     # [P, d, d]
+      a0 = a[0]
+      a1 = (a[1:1 + d] - a0).T                                           # A1[i][j]
+      b0 = s_[0]
+      b1 = s_[1:1 + d] - b0                                              # [j][., .]
+      for c in (d + 1, d + 2):
+        x = probes[c]
+        pred_a = a0 + a1 @ x
+        pred_s = b0 + np.tensordot(x, b1, axes=(0, 0))
+        scale = 1.0 + np.abs(a[c]).max() + np.abs(s_[c]).max()
+        if (np.abs(pred_a - a[c]).max() > 1e-6 * scale or
+            np.abs(pred_s - s_[c]).max() > 1e-6 * scale):
+          raise NotImplementedError(
+              'The B200 path engine runs affine drift/volatility callables '
+              '(a = a0(t) + A1(t) x, S = B(t)) and the closures of its model '
+              'classes; this callable pair is not affine in the state at t={}. '
+              'There is no CPU fallback.'.format(float(t[i])))
+      if d == 1:
+        rows.append([dt[i], sq[i], a0[0], a1[0, 0], b0[0, 0], b1[0, 0, 0]])
+      else:
+        if np.abs(b1).max() > 1e-9 * (1.0 + np.abs(b0).max()):
+          raise NotImplementedError(
+              'state-dependent volatility callables are supported for dim 1 '
+              'only (dim > 1: use the model classes); no CPU fallback.')
+        rows.append(np.concatenate([[dt[i], sq[i]], a0, a1.reshape(-1), b0.reshape(-1)]))
+    table = np.asarray(rows, dtype=np.float64).reshape(t.shape[0], self.num_coef)
+    return table.astype(dtype).astype(np.float64)
 
 
 class GbmSpec1F(ModelSpec):

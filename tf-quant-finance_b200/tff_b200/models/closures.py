@@ -26,10 +26,14 @@ class DeviceClosure:
     return self._host_fn(t, x)
 
 
-def resolve_spec(drift_fn, volatility_fn):
+def resolve_spec(drift_fn, volatility_fn, dim=None):
   """The ModelSpec shared by a (drift_fn, volatility_fn) pair."""
   ds = getattr(drift_fn, 'tqf_spec', None)
   vs = getattr(volatility_fn, 'tqf_spec', None)
+  if ds is None and vs is None and dim is not None and callable(drift_fn) and callable(
+      volatility_fn):
+    # plain Python callables: accepted when they are affine in the state
+    return engine.ProbedAffineSpec(dim, drift_fn, volatility_fn)
   if ds is None or vs is None:
     raise NotImplementedError(
         'The B200 path engine cannot run arbitrary Python drift/volatility '
@@ -64,14 +68,14 @@ def _p(param, t, like):
   return torch.as_tensor(v, dtype=like.dtype, device=like.device)
 
 
-def affine_closures(a0, a1, b):
-  """(drift_fn, volatility_fn) of dX = (a0(t) + a1(t) X) dt + b(t) dW, dim 1.
+def affine_closures(a0, a1, b, b1=0.0):
+  """(drift_fn, volatility_fn) of dX = (a0(t) + a1(t) X) dt + (b(t) + b1(t) X) dW, dim 1.
 
   `a0`, `a1`, `b` are scalars or callables of an array of times.  Covers the
   log-space GBM of the reference's Monte-Carlo notebook
   (`examples/jupyter_notebooks/Monte_Carlo_Euler_Scheme.ipynb:223-275`).
   """
-  spec = engine.AffineSpec1F(a0, a1, b)
+  spec = engine.AffineSpec1F(a0, a1, b, b1)
 
   def drift(t, x):
     x = _as_tensor(x)
@@ -79,7 +83,7 @@ def affine_closures(a0, a1, b):
 
   def vol(t, x):
     x = _as_tensor(x)
-    return _p(b, t, x) * torch.ones(x.shape + (1,), dtype=x.dtype, device=x.device)
+    return (_p(b, t, x) + _p(b1, t, x) * x).unsqueeze(-1)
   return DeviceClosure(spec, 'drift', drift), DeviceClosure(spec, 'volatility', vol)
 
 

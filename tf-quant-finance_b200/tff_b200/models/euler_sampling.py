@@ -85,7 +85,7 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
   if x0.shape[0] != 1 and not np.all(x0 == x0[0]):
     raise NotImplementedError(
         'per-path initial states are not implemented by the B200 engine yet.')
-  spec = closures.resolve_spec(drift_fn, volatility_fn)
+  spec = closures.resolve_spec(drift_fn, volatility_fn, dim)
   if spec.dim != dim:
     raise ValueError('`dim` is {} but the model has dimension {}'.format(
         dim, spec.dim))
