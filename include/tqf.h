@@ -248,10 +248,19 @@ typedef struct tqf_lsm_desc {
   int64_t stride_time;      /*   batch for batched sample paths), strides in */
   int64_t stride_dim;       /*   elements                                    */
   int64_t stride_batch;
+  /* Optional caller-owned workspaces (e.g. from the framework's caching
+   * allocator; NULL = the library allocates): W [B][num_paths] in `dtype`, and
+   * partial sums of `partials_doubles` doubles (tqf_lsm_workspace). */
+  void* w_dev;
+  double* partials_dev;
+  uint64_t partials_doubles;
 } tqf_lsm_desc;
 
 typedef struct tqf_lsm tqf_lsm;
 
+/* Doubles of partial-sum workspace a handle for this descriptor can need
+ * (`num_times` = number of exercise dates passed to tqf_lsm_column_sums). */
+int tqf_lsm_workspace(const tqf_lsm_desc* desc, int num_times, uint64_t* partials_doubles);
 int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out);
 int tqf_lsm_destroy(tqf_lsm* lsm);
 /* sums_dev[b][t][j] = sum_n x[n, time_indices[t], j] (basis centring). */
@@ -263,16 +272,20 @@ int tqf_lsm_init(tqf_lsm* lsm, int time_index, void* stream);
  * index t_update, then optionally accumulate the normal equations at t_acc with
  * y = ratio_acc W'.  DEVICE arrays: mean_* (payoff b at b*mean_stride, `dim`
  * entries), beta [B][K], ratio_* [B].  sums_dev: double [B][num_sums]
- * (layout: tqf_lsm_sums_layout).  Nothing synchronises with the host. */
+ * (layout: tqf_lsm_sums_layout); NULL leaves the per-CTA partials for a fused
+ * tqf_lsm_solve(reduce_partials = 1).  Nothing synchronises with the host. */
 int tqf_lsm_step(tqf_lsm* lsm, int do_update, int t_update, const double* mean_update_dev,
                  const double* beta_dev, const double* ratio_update_dev, int do_accumulate,
                  int t_acc, const double* mean_acc_dev, const double* ratio_acc_dev,
                  int64_t mean_stride, double* sums_dev, void* stream);
-/* beta_dev[b] = pinv(X'X_b) X'y_b from the reduced sums (Jacobi eigen-solver on
- * the device, singular values below rcond * max dropped like tf.linalg.pinv).
- * Packed layout (K <= 6) only; TQF_ERR_UNSUPPORTED otherwise (solve on host). */
-int tqf_lsm_solve(tqf_lsm* lsm, const double* sums_dev, double rcond, double* beta_dev,
-                  void* stream);
+/* beta_dev[b] = pinv(X'X_b) X'y_b (Jacobi eigen-solver on the device, singular
+ * values below rcond * max dropped like tf.linalg.pinv).  reduce_partials = 1:
+ * the preceding tqf_lsm_step was called with sums_dev = NULL and this call first
+ * reduces its per-CTA partials into sums_dev (single-GPU fast path, one launch
+ * less per date); 0: sums_dev already holds the (all-reduced) sums.  Packed
+ * layout (K <= 6) only; TQF_ERR_UNSUPPORTED otherwise (solve on the host). */
+int tqf_lsm_solve(tqf_lsm* lsm, double* sums_dev, int reduce_partials, double rcond,
+                  double* beta_dev, void* stream);
 /* num_sums doubles per payoff.  Packed (K <= 6): the upper triangle of a 6 x 6
  * X'X row by row (21 entries) followed by 6 entries of X'y; otherwise X'X
  * [K][K] row-major followed by X'y [K]. */

@@ -500,6 +500,70 @@ __device__ void lsm_solve_one(const double* __restrict__ sp, double rcond, int r
 #pragma unroll
     for (int j = 0; j < K; ++j) v[i][j] = i == j ? 1.0 : 0.0;
   }
+  // Fast path: Cholesky.  With A = L L', trace(A^-1) = ||L^-1||_F^2 >= 1/lambda_min
+  // and trace(A) >= lambda_max, so 1/trace(A^-1) > rcond trace(A) proves that no
+  // singular value falls under the pinv cut-off, i.e. pinv(A) = A^-1 exactly and
+  // beta = L^-T L^-1 b.  (Tight within a factor K^2; everything else -- rank
+  // deficient or borderline -- takes the eigen-decomposition below.)
+  {
+    double l[K][K], li[K][K];
+    bool ok = true;
+    double tr = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      tr += a[j][j];
+      double d = a[j][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) d = fma(-l[j][k], l[j][k], d);
+      ok = ok && (d > 0.0);
+      const double dj = d > 0.0 ? d : 1.0;
+      const double inv = rsqrt(dj);
+      l[j][j] = dj * inv;
+      li[j][j] = inv;
+#pragma unroll
+      for (int i = j + 1; i < K; ++i) {
+        double v2 = a[i][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) v2 = fma(-l[i][k], l[j][k], v2);
+        l[i][j] = v2 * inv;
+      }
+    }
+    // L^-1 (lower triangular)
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+#pragma unroll
+      for (int i = j + 1; i < K; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = j; k < i; ++k) acc = fma(l[i][k], li[k][j], acc);
+        li[i][j] = -acc * li[i][i];
+      }
+    }
+    double tr_inv = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) tr_inv = fma(li[i][j], li[i][j], tr_inv);
+    if (ok && tr_inv > 0.0 && 1.0 / tr_inv > rcond * tr) {
+      double y[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) acc = fma(li[i][j], rhs[j], acc);
+        y[i] = acc;
+      }
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = j; i < K; ++i) acc = fma(li[i][j], y[i], acc);
+        if (round_to_float) acc = static_cast<double>(static_cast<float>(acc));
+        beta[j] = acc;
+      }
+      return;
+    }
+  }
   for (int sweep = 0; sweep < 24; ++sweep) {
     double off = 0.0, diag = 0.0;
 #pragma unroll
@@ -508,7 +572,7 @@ __device__ void lsm_solve_one(const double* __restrict__ sp, double rcond, int r
 #pragma unroll
       for (int j = i + 1; j < K; ++j) off += a[i][j] * a[i][j];
     }
-    if (off <= 1e-300 || off <= 1e-34 * diag) break;
+    if (off <= 1e-300 || off <= 1e-32 * diag) break;
 #pragma unroll
     for (int p = 0; p < K - 1; ++p) {
 #pragma unroll
@@ -517,7 +581,7 @@ __device__ void lsm_solve_one(const double* __restrict__ sp, double rcond, int r
         if (apq != 0.0) {
           const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
           const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+          const double c = rsqrt(t * t + 1.0), sn = t * c;
 #pragma unroll
           for (int k = 0; k < K; ++k) {
             const double akp = a[k][p], akq = a[k][q];
@@ -563,8 +627,22 @@ __device__ void lsm_solve_one(const double* __restrict__ sp, double rcond, int r
   }
 }
 
-__global__ void lsm_solve_kernel(const double* __restrict__ sums, int B, int K, double rcond,
+// `partials` != nullptr: first reduce the per-CTA partial rows (fixed order)
+// into `sums`, then solve -- one launch instead of two on a single GPU.
+__global__ void lsm_solve_kernel(const double* __restrict__ partials, int num_blocks,
+                                 double* __restrict__ sums, int B, int K, double rcond,
                                  int round_to_float, double* __restrict__ beta) {
+  if (partials != nullptr) {
+    const int M = B * kLsmFastNS;
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int m = threadIdx.x >> 5; m < M; m += nwarps) {
+      double v = 0.0;
+      for (int bk = lane; bk < num_blocks; bk += 32) v += partials[static_cast<size_t>(bk) * M + m];
+      v = warp_sum(v);
+      if (lane == 0) sums[m] = v;
+    }
+    __syncthreads();
+  }
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const double* sp = sums + static_cast<size_t>(b) * kLsmFastNS;
@@ -594,6 +672,7 @@ struct tqf_lsm {
   size_t partials_doubles;
   int* times_dev;
   int times_cap;
+  bool external_w, external_partials;
 };
 
 template <typename Real>
@@ -620,6 +699,10 @@ static void fill_args(const tqf_lsm* h, LsmArgs<Real>* A) {
 
 static int ensure_partials(tqf_lsm* h, size_t doubles) {
   if (doubles <= h->partials_doubles) return TQF_OK;
+  if (h->external_partials) {
+    set_error("caller-provided LSM partials workspace is too small");
+    return TQF_ERR_INVALID_ARGUMENT;
+  }
   cudaFree(h->partials_dev);
   h->partials_dev = nullptr;
   h->partials_doubles = 0;
@@ -667,7 +750,7 @@ static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* 
     lsm_step_generic_kernel<Real><<<grid, kLsmBlock, smem, s>>>(A);
   }
   TQF_CUDA_OK(cudaGetLastError());
-  if (do_acc) {
+  if (do_acc && sums_dev != nullptr) {
     const int M = B * h->NS;
     const int blocks = (M + 3) / 4 < 592 ? (M + 3) / 4 : 592;
     lsm_reduce_kernel<<<blocks, 128, 0, s>>>(h->partials_dev, h->grid, M, sums_dev);
@@ -677,6 +760,23 @@ static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* 
 }
 
 extern "C" {
+
+int tqf_lsm_workspace(const tqf_lsm_desc* desc, int num_times, uint64_t* partials_doubles) {
+  TQF_REQUIRE(desc && partials_doubles && num_times >= 1, "bad arguments");
+  const int K = desc->basis_size;
+  const int NS = K <= kLsmFastK ? kLsmFastNS : K * K + K;
+  int sms = kSMs;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess) {
+    cudaGetLastError();
+    sms = kSMs;
+  }
+  const uint64_t grid = static_cast<uint64_t>(sms) * 8;
+  uint64_t need = grid * desc->batch * NS;
+  const uint64_t cols = 64ull * desc->batch * num_times * desc->dim;
+  if (cols > need) need = cols;
+  *partials_doubles = need + 64;
+  return TQF_OK;
+}
 
 int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
   TQF_REQUIRE(desc && out, "null argument");
@@ -708,7 +808,18 @@ int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
   const uint64_t cap = static_cast<uint64_t>(sms) * (h->fast ? 8 : 2);
   h->grid = static_cast<int>(blocks < cap ? (blocks ? blocks : 1) : cap);
   const size_t esize = desc->dtype == TQF_F64 ? 8 : 4;
-  cudaError_t e = cudaMalloc(&h->w_dev, esize * desc->batch * (desc->num_paths ? desc->num_paths : 1));
+  cudaError_t e = cudaSuccess;
+  if (desc->w_dev) {               // caller-owned workspace (framework allocator)
+    h->w_dev = desc->w_dev;
+    h->external_w = true;
+  } else {
+    e = cudaMalloc(&h->w_dev, esize * desc->batch * (desc->num_paths ? desc->num_paths : 1));
+  }
+  if (desc->partials_dev) {
+    h->partials_dev = desc->partials_dev;
+    h->partials_doubles = desc->partials_doubles;
+    h->external_partials = true;
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->exponents_dev, sizeof(int) * h->K * desc->dim);
   if (e == cudaSuccess) e = cudaMalloc(&h->strikes_dev, sizeof(double) * desc->batch);
   if (e == cudaSuccess)
@@ -729,10 +840,10 @@ int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
 
 int tqf_lsm_destroy(tqf_lsm* h) {
   if (!h) return TQF_OK;
-  cudaFree(h->w_dev);
+  if (!h->external_w) cudaFree(h->w_dev);
   cudaFree(h->exponents_dev);
   cudaFree(h->strikes_dev);
-  cudaFree(h->partials_dev);
+  if (!h->external_partials) cudaFree(h->partials_dev);
   cudaFree(h->times_dev);
   delete h;
   return TQF_OK;
@@ -796,8 +907,9 @@ int tqf_lsm_step(tqf_lsm* h, int do_update, int t_update, const double* mean_upd
   TQF_REQUIRE(h, "null handle");
   TQF_REQUIRE(!do_update || (mean_update_dev && beta_dev && ratio_update_dev),
               "null update argument");
-  TQF_REQUIRE(!do_accumulate || (mean_acc_dev && ratio_acc_dev && sums_dev),
-              "null accumulate argument");
+  TQF_REQUIRE(!do_accumulate || (mean_acc_dev && ratio_acc_dev), "null accumulate argument");
+  TQF_REQUIRE(!do_accumulate || sums_dev || h->fast,
+              "sums_dev may only be omitted for the packed (K <= 6) layout");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return h->desc.dtype == TQF_F64
              ? lsm_step_impl<double>(h, do_update, t_update, mean_update_dev, beta_dev,
@@ -808,16 +920,23 @@ int tqf_lsm_step(tqf_lsm* h, int do_update, int t_update, const double* mean_upd
                                     ratio_acc_dev, mean_stride, sums_dev, s);
 }
 
-int tqf_lsm_solve(tqf_lsm* h, const double* sums_dev, double rcond, double* beta_dev,
-                  void* stream) {
+int tqf_lsm_solve(tqf_lsm* h, double* sums_dev, int reduce_partials, double rcond,
+                  double* beta_dev, void* stream) {
   TQF_REQUIRE(h && sums_dev && beta_dev, "null argument");
   if (!h->fast) {
     set_error("device solve is implemented for basis sizes <= 6; solve on the host");
     return TQF_ERR_UNSUPPORTED;
   }
   const int B = h->desc.batch;
-  lsm_solve_kernel<<<(B + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      sums_dev, B, h->K, rcond, h->desc.dtype == TQF_F32 ? 1 : 0, beta_dev);
+  TQF_REQUIRE(!reduce_partials || B <= 128, "fused reduction supports up to 128 payoffs");
+  if (reduce_partials) {
+    lsm_solve_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->partials_dev, h->grid, sums_dev, B, h->K, rcond, h->desc.dtype == TQF_F32 ? 1 : 0,
+        beta_dev);
+  } else {
+    lsm_solve_kernel<<<(B + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        nullptr, 0, sums_dev, B, h->K, rcond, h->desc.dtype == TQF_F32 ? 1 : 0, beta_dev);
+  }
   TQF_CUDA_OK(cudaGetLastError());
   return TQF_OK;
 }

@@ -106,6 +106,9 @@ class LsmDesc(C.Structure):
       ('stride_time', C.c_int64),
       ('stride_dim', C.c_int64),
       ('stride_batch', C.c_int64),
+      ('w_dev', C.c_void_p),
+      ('partials_dev', C.c_void_p),
+      ('partials_doubles', C.c_uint64),
   ]
 
 
@@ -150,6 +153,7 @@ _SIGNATURES = {
     'tqf_plan_paths':
         (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                    C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
+    'tqf_lsm_workspace': (C.c_int, [C.POINTER(LsmDesc), C.c_int, C.POINTER(C.c_uint64)]),
     'tqf_lsm_create': (C.c_int, [C.POINTER(LsmDesc), C.POINTER(C.c_void_p)]),
     'tqf_lsm_destroy': (C.c_int, [C.c_void_p]),
     'tqf_lsm_column_sums':
@@ -160,7 +164,7 @@ _SIGNATURES = {
                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                    C.c_void_p]),
     'tqf_lsm_solve':
-        (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+        (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     'tqf_lsm_sums_layout':
         (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'tqf_lsm_value_sum': (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

@@ -145,6 +145,13 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
   handle = C.c_void_p()
   lib = _lib.lib()
   _lib.require_cuda()
+  # workspaces from torch's caching allocator (cudaMalloc / cudaFree per call
+  # would synchronise the device)
+  need = C.c_uint64()
+  _lib.check(lib.tqf_lsm_workspace(C.byref(d), T, C.byref(need)))
+  w_buf = torch.empty((B, max(n_local, 1)), dtype=x.dtype, device=x.device)
+  part_buf = torch.empty((int(need.value),), dtype=torch.float64, device=x.device)
+  d.w_dev, d.partials_dev, d.partials_doubles = w_buf.data_ptr(), part_buf.data_ptr(), need.value
   _lib.check(lib.tqf_lsm_create(C.byref(d), C.byref(handle)))
   try:
     ns, packed = C.c_int(), C.c_int()
@@ -177,16 +184,20 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
     beta_dev = torch.zeros((B, K), dtype=torch.float64, device=dev)
     rcond = 10 * K * float(np.finfo(dt).eps)
     e = T - 1
+    device_solve = bool(packed.value)
+    # single rank + device solve: the per-CTA partials are reduced inside the
+    # solve kernel (one launch less per date)
+    fused = device_solve and all_reduce is None and B <= 128
+    sums_arg = None if fused else sums.data_ptr()
     if e > 0:
       _lib.check(lib.tqf_lsm_step(handle, 0, 0, None, None, None, 1,
                                   int(ex_times[e - 1]), mean_ptr(e), ratio_ptr(e),
-                                  mean_stride, sums.data_ptr(), stream))
-    device_solve = bool(packed.value)
+                                  mean_stride, sums_arg, stream))
     while e > 0:
       if all_reduce is not None:
         all_reduce(sums)
       if device_solve:
-        _lib.check(lib.tqf_lsm_solve(handle, sums.data_ptr(), rcond,
+        _lib.check(lib.tqf_lsm_solve(handle, sums.data_ptr(), 1 if fused else 0, rcond,
                                      beta_dev.data_ptr(), stream))
       else:
         # large bases (K > 6): the K x K pseudo-inverse runs on the host
@@ -199,7 +210,7 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
           handle, 1, int(ex_times[e - 1]), mean_ptr(e), beta_dev.data_ptr(), ratio_ptr(e),
           do_acc, int(ex_times[e - 2]) if do_acc else 0,
           mean_ptr(e - 1) if do_acc else None, ratio_ptr(e - 1) if do_acc else None,
-          mean_stride, sums.data_ptr(), stream))
+          mean_stride, sums_arg, stream))
       e -= 1
     vs = torch.zeros((B, 2), dtype=torch.float64, device=dev)
     _lib.check(lib.tqf_lsm_value_sum(handle, int(num_calibration_samples or 0),
