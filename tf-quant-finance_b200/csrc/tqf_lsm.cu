@@ -323,6 +323,138 @@ __global__ void __launch_bounds__(kLsmBlock, 3) lsm_step_dim1_kernel(const LsmAr
   }
 }
 
+// Contiguous variant of the single-asset kernel (time-major paths,
+// stride_path == 1, even number of paths, 16-byte aligned columns): two paths
+// per vector load/store, 32-bit indexing.  The general kernel above spends
+// ~135 instructions per path, mostly on 64-bit address arithmetic and
+// predication -- enough to be issue-bound below the HBM roofline.
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+template <typename Real, int KT>
+__global__ void __launch_bounds__(kLsmBlock, 3) lsm_step_dim1_vec_kernel(const LsmArgs<Real> A) {
+  using V = typename Vec2<Real>::type;
+  const int b = blockIdx.y;
+  const Real* base = A.paths + b * A.stride_batch;
+  V* __restrict__ w = reinterpret_cast<V*>(A.w + static_cast<size_t>(b) * A.num_paths);
+  const V* __restrict__ colu = reinterpret_cast<const V*>(base + A.t_update * A.stride_time);
+  const V* __restrict__ cola = reinterpret_cast<const V*>(base + A.t_acc * A.stride_time);
+  constexpr int NA = KT * (KT + 1) / 2 + KT;
+  double acc[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) acc[i] = 0.0;
+  Real beta[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) beta[k] = A.do_update ? static_cast<Real>(A.beta[b * KT + k]) : Real(0);
+  const Real ratio_u = A.do_update ? static_cast<Real>(A.ratio_update[b]) : Real(1);
+  const Real ratio_a = A.do_acc ? static_cast<Real>(A.ratio_acc[b]) : Real(1);
+  const Real strike = static_cast<Real>(A.strikes[b]);
+  const Real mean_u = A.do_update ? static_cast<Real>(A.mean_update[b * A.mean_stride]) : Real(0);
+  const Real mean_a = A.do_acc ? static_cast<Real>(A.mean_acc[b * A.mean_stride]) : Real(0);
+  const uint32_t npairs = static_cast<uint32_t>(A.num_paths >> 1);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const bool calib_all = A.num_calib == ~0ull;
+  constexpr int U = 2;  // vector pairs in flight per thread
+  for (uint32_t p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < npairs; p0 += U * stride) {
+    V wv[U], xu[U], xa[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t p = p0 + u * stride;
+      if (p < npairs) {
+        wv[u] = w[p];
+        if (A.do_update) xu[u] = colu[p];
+        if (A.do_acc) xa[u] = cola[p];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t p = p0 + u * stride;
+      if (p >= npairs) continue;
+      Real wn[2] = {wv[u].x, wv[u].y};
+      const Real xus[2] = {xu[u].x, xu[u].y};
+      const Real xas[2] = {xa[u].x, xa[u].y};
+      if (A.do_update) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const Real v = strike - xus[e];
+          const Real ev = v > Real(0) ? v : Real(0);
+          const Real c = xus[e] - mean_u;
+          Real cont = beta[KT - 1];
+#pragma unroll
+          for (int k = KT - 2; k >= 0; --k) cont = fma(cont, c, beta[k]);
+          cont = cont > Real(0) ? cont : Real(0);
+          wn[e] = ev > cont ? ev : ratio_u * wn[e];
+        }
+        V out;
+        out.x = wn[0];
+        out.y = wn[1];
+        w[p] = out;
+      }
+      if (A.do_acc) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const Real v = strike - xas[e];
+          const bool use = v > Real(0) &&
+                           (calib_all || (A.path_offset + 2ull * p + e) < A.num_calib);
+          if (use) {
+            double phi[KT];
+            const Real cr = xas[e] - mean_a;
+            Real pw = 1;
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+              phi[k] = static_cast<double>(pw);
+              pw *= cr;
+            }
+            const double y = static_cast<double>(ratio_a * wn[e]);
+            int idx = 0;
+#pragma unroll
+            for (int i = 0; i < KT; ++i)
+#pragma unroll
+              for (int j = i; j < KT; ++j) {
+                acc[idx] = fma(phi[i], phi[j], acc[idx]);
+                ++idx;
+              }
+#pragma unroll
+            for (int i = 0; i < KT; ++i)
+              acc[KT * (KT + 1) / 2 + i] = fma(phi[i], y, acc[KT * (KT + 1) / 2 + i]);
+          }
+        }
+      }
+    }
+  }
+  if (A.do_acc) {
+    __shared__ double s_red[kLsmBlock / 32][NA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const double v = warp_sum(acc[i]);
+      if (lane == 0) s_red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLsmFastNS) {
+      const int slot = threadIdx.x;
+      int src = -1;
+      if (slot < kLsmFastK * (kLsmFastK + 1) / 2) {
+        int i = 0, rem = slot;
+        while (rem >= kLsmFastK - i) {
+          rem -= kLsmFastK - i;
+          ++i;
+        }
+        const int j = i + rem;
+        if (i < KT && j < KT) src = i * KT - i * (i - 1) / 2 + (j - i);
+      } else {
+        const int i = slot - kLsmFastK * (kLsmFastK + 1) / 2;
+        if (i < KT) src = KT * (KT + 1) / 2 + i;
+      }
+      double v = 0.0;
+      if (src >= 0)
+        for (int wi = 0; wi < kLsmBlock / 32; ++wi) v += s_red[wi][src];
+      A.partials[(static_cast<size_t>(blockIdx.x) * A.batch + b) * kLsmFastNS + slot] = v;
+    }
+  }
+}
+
 // Generic path (K <= 128): the update is per thread, the outer products are
 // formed tile by tile from shared memory.  grid = (blocks, B); NS = K*K + K.
 template <typename Real>
@@ -734,7 +866,22 @@ static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* 
   if (rc != TQF_OK) return rc;
   A.partials = h->partials_dev;
   const dim3 grid(h->grid, B);
-  if (h->fast && d.dim == 1) {
+  const size_t esz = sizeof(Real);
+  const bool vec_ok =
+      h->fast && d.dim == 1 && d.stride_path == 1 && (d.num_paths % 2) == 0 &&
+      d.num_paths < (1ull << 32) && (reinterpret_cast<uintptr_t>(d.paths_dev) % (2 * esz)) == 0 &&
+      (reinterpret_cast<uintptr_t>(h->w_dev) % (2 * esz)) == 0 && (d.stride_time % 2) == 0 &&
+      (d.stride_batch % 2) == 0;
+  if (vec_ok) {
+    switch (K) {
+      case 1: lsm_step_dim1_vec_kernel<Real, 1><<<grid, kLsmBlock, 0, s>>>(A); break;
+      case 2: lsm_step_dim1_vec_kernel<Real, 2><<<grid, kLsmBlock, 0, s>>>(A); break;
+      case 3: lsm_step_dim1_vec_kernel<Real, 3><<<grid, kLsmBlock, 0, s>>>(A); break;
+      case 4: lsm_step_dim1_vec_kernel<Real, 4><<<grid, kLsmBlock, 0, s>>>(A); break;
+      case 5: lsm_step_dim1_vec_kernel<Real, 5><<<grid, kLsmBlock, 0, s>>>(A); break;
+      default: lsm_step_dim1_vec_kernel<Real, 6><<<grid, kLsmBlock, 0, s>>>(A); break;
+    }
+  } else if (h->fast && d.dim == 1) {
     switch (K) {
       case 1: lsm_step_dim1_kernel<Real, 1><<<grid, kLsmBlock, 0, s>>>(A); break;
       case 2: lsm_step_dim1_kernel<Real, 2><<<grid, kLsmBlock, 0, s>>>(A); break;
