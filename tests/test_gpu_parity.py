@@ -392,3 +392,73 @@ def test_exact_multivariate_gbm_sample_paths(dtype):
                                           odraws.RandomType.SOBOL, None, 11, dtype)
   assert got.shape == want.shape == (n, 3, dim)
   np.testing.assert_allclose(got, want, rtol=1e-12 if dtype == np.float64 else 2e-5)
+
+
+# ------------------------------------------------------------ edge cases ----
+def test_many_steps_tables_in_global_memory():
+  # 15 000 steps: the coefficient table (720 KB) no longer fits shared memory
+  tff = _tff()
+  dtype = np.float64
+  dim, (drift, vol), (odrift, ovol), x0 = _models(dtype)['affine_ou']
+  kw = dict(num_samples=256, initial_state=x0, seed=[4, 2], time_step=1.0 / 15000, dtype=dtype)
+  got = _np(tff.models.euler_sampling.sample(
+      dim, drift, vol, [0.5, 1.0], random_type=tff.math.random.RandomType.STATELESS, **kw))
+  want = oeuler.sample(dim, odrift, ovol, [0.5, 1.0],
+                       random_type=odraws.RandomType.STATELESS, **kw)
+  np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize('n', [1, 2, 127, 128, 129, 1025])
+def test_ragged_path_counts(n):
+  tff = _tff()
+  dtype = np.float64
+  dim, (drift, vol), (odrift, ovol), x0 = _models(dtype)['heston']
+  for rt, seed, skip in (('SOBOL', None, 126), ('STATELESS', [1, 1], 0)):
+    kw = dict(num_samples=n, initial_state=x0, seed=seed, skip=skip, num_time_steps=5, dtype=dtype)
+    got = _np(tff.models.euler_sampling.sample(
+        dim, drift, vol, [1.0], random_type=tff.math.random.RandomType[rt], **kw))
+    want = oeuler.sample(dim, odrift, ovol, [1.0], random_type=odraws.RandomType[rt], **kw)
+    assert got.shape == (n, 1, 2)
+    _close(got, want, dtype, scale=np.abs(want).max())
+
+
+def test_only_initial_time_requested():
+  tff = _tff()
+  dtype = np.float64
+  dim, (drift, vol), _, x0 = _models(dtype)['heston']
+  got = _np(tff.models.euler_sampling.sample(
+      dim, drift, vol, [0.0], num_samples=10, initial_state=x0, time_step=0.1, seed=[1, 2],
+      random_type=tff.math.random.RandomType.STATELESS, dtype=dtype))
+  np.testing.assert_array_equal(got, np.broadcast_to(x0, (10, 1, 2)))
+
+
+def test_limits_are_reported():
+  tff = _tff()
+  dtype = np.float64
+  dim, (drift, vol), _, x0 = _models(dtype)['heston']
+  sample = tff.models.euler_sampling.sample
+  rt = tff.math.random.RandomType
+  with pytest.raises(ValueError):          # Sobol dimension 2 * 11000 > 21201
+    sample(dim, drift, vol, [1.0], num_samples=8, initial_state=x0, num_time_steps=11000,
+           random_type=rt.SOBOL, dtype=dtype)
+  with pytest.raises(ValueError):          # skip + num_samples >= 2^31 - 1
+    sample(dim, drift, vol, [1.0], num_samples=8, initial_state=x0, num_time_steps=4,
+           random_type=rt.SOBOL, skip=2**31 - 5, dtype=dtype)
+  with pytest.raises(ValueError):          # STATELESS needs a seed
+    sample(dim, drift, vol, [1.0], num_samples=8, initial_state=x0, num_time_steps=4,
+           random_type=rt.STATELESS, dtype=dtype)
+  with pytest.raises(NotImplementedError):  # batched initial state
+    sample(dim, drift, vol, [1.0], num_samples=8, initial_state=np.zeros((3, 1, 2)),
+           num_time_steps=4, seed=1, dtype=dtype)
+
+
+def test_pseudo_without_seed_is_random_but_valid():
+  tff = _tff()
+  dtype = np.float64
+  dim, (drift, vol), _, x0 = _models(dtype)['gbm']
+  a = _np(tff.models.euler_sampling.sample(dim, drift, vol, [1.0], num_samples=4096,
+                                           initial_state=x0, time_step=0.1, dtype=dtype))
+  b = _np(tff.models.euler_sampling.sample(dim, drift, vol, [1.0], num_samples=4096,
+                                           initial_state=x0, time_step=0.1, dtype=dtype))
+  assert np.all(np.isfinite(a)) and not np.array_equal(a, b)
+  assert abs(np.log(a / 100.0).mean() - (0.03 - 0.5 * 0.0225)) < 0.02
