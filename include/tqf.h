@@ -146,6 +146,11 @@ typedef struct tqf_rng_desc {
   /* TQF_RNG_DRAWS: device pointer, dtype of the model, layout
    * [num_paths][num_steps_total][num_factors] (normal_draws= argument)     */
   const void* draws_dev;
+  /* Draw unit of path p (batched calls, models/utils.py:98-107): the flat draw
+   * index / Sobol point of path p is that of unit p * unit_stride + unit_offset
+   * (unit_stride 0 is read as 1).  Sobol requires unit_stride == 1.         */
+  uint64_t unit_stride;
+  uint64_t unit_offset;
 } tqf_rng_desc;
 
 typedef struct tqf_model_desc {

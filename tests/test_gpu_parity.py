@@ -447,9 +447,9 @@ def test_limits_are_reported():
   with pytest.raises(ValueError):          # STATELESS needs a seed
     sample(dim, drift, vol, [1.0], num_samples=8, initial_state=x0, num_time_steps=4,
            random_type=rt.STATELESS, dtype=dtype)
-  with pytest.raises(NotImplementedError):  # batched initial state
-    sample(dim, drift, vol, [1.0], num_samples=8, initial_state=np.zeros((3, 1, 2)),
-           num_time_steps=4, seed=1, dtype=dtype)
+  with pytest.raises(NotImplementedError):  # per-path initial states
+    sample(dim, drift, vol, [1.0], num_samples=8,
+           initial_state=np.arange(16.0).reshape(8, 2), num_time_steps=4, seed=1, dtype=dtype)
 
 
 def test_pseudo_without_seed_is_random_but_valid():
@@ -462,3 +462,44 @@ def test_pseudo_without_seed_is_random_but_valid():
                                            initial_state=x0, time_step=0.1, dtype=dtype))
   assert np.all(np.isfinite(a)) and not np.array_equal(a, b)
   assert abs(np.log(a / 100.0).mean() - (0.03 - 0.5 * 0.0225)) < 0.02
+
+
+# ------------------------------------------------------ batched processes ----
+@pytest.mark.parametrize('rng', [('SOBOL', None, 3), ('STATELESS', [4, 2], 0),
+                                 ('STATELESS_ANTITHETIC', [4, 2], 0), ('PSEUDO_ANTITHETIC', 9, 0)],
+                         ids=lambda r: r[0])
+def test_batch_of_initial_states(rng):
+  # batch_shape = initial_state.shape[:-2] (euler_sampling.py:251); draws laid
+  # out [steps] + batch + [N, dim] (models/utils.py:98-128)
+  tff = _tff()
+  dtype = np.float64
+  rt, seed, skip = rng
+  dim, (drift, vol), (odrift, ovol), _ = _models(dtype)['heston']
+  x0 = np.array([[[np.log(100.0), 0.04]], [[np.log(90.0), 0.09]], [[np.log(120.0), 0.01]]])
+  n = 512
+  kw = dict(num_samples=n, initial_state=x0, seed=seed, skip=skip, num_time_steps=6, dtype=dtype)
+  got = _np(tff.models.euler_sampling.sample(
+      dim, drift, vol, [0.5, 1.0], random_type=tff.math.random.RandomType[rt], **kw))
+  want = oeuler.sample(dim, odrift, ovol, [0.5, 1.0], random_type=odraws.RandomType[rt], **kw)
+  assert got.shape == want.shape == (3, n, 2, 2)
+  _close(got, want, dtype, scale=np.abs(want).max())
+
+
+def test_batch_of_gbm_parameters():
+  # batched GBM parameters of shape batch_shape + [1] (univariate_...py:66-80)
+  tff = _tff()
+  from tff_b200.models import closures
+  dtype = np.float64
+  mean = np.array([[0.01], [0.05]])
+  vol = np.array([[0.1], [0.3]])
+  drift, volf = closures.gbm_closures(mean, vol)
+  x0 = np.array([[[1.0]], [[2.0]]])
+  n = 700
+  kw = dict(num_samples=n, initial_state=x0, seed=[1, 5], time_step=0.1, dtype=dtype)
+  got = _np(tff.models.euler_sampling.sample(
+      1, drift, volf, [1.0], random_type=tff.math.random.RandomType.STATELESS, **kw))
+  want = oeuler.sample(1, lambda t, x: mean[:, None, :] * x,
+                       lambda t, x: (vol[:, None, :] * x)[..., None], [1.0],
+                       random_type=odraws.RandomType.STATELESS, **kw)
+  assert got.shape == want.shape == (2, n, 1, 1)
+  _close(got, want, dtype, scale=np.abs(want).max())

@@ -117,7 +117,11 @@ static void fill_common(const tqf_plan* plan, uint64_t path_offset, uint64_t pat
   P->draws = static_cast<const Real*>(plan->rng.draws_dev);
   P->path_offset = path_offset;
   P->path_count = path_count;
-  P->first_index = plan->rng.type == TQF_RNG_SOBOL ? plan->rng.skip + 1 + path_offset : path_offset;
+  P->unit_stride = plan->rng.unit_stride ? plan->rng.unit_stride : 1;
+  P->unit_offset = plan->rng.unit_offset;
+  P->first_index = plan->rng.type == TQF_RNG_SOBOL
+                       ? plan->rng.skip + 1 + plan->rng.unit_offset + path_offset
+                       : path_offset;
   P->chunk_base = P->first_index & ~static_cast<uint64_t>(kBlock - 1);
   const uint64_t end = P->first_index + path_count;
   P->num_chunks = (end - P->chunk_base + kBlock - 1) / kBlock;
@@ -371,9 +375,14 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
   if (rng->type == TQF_RNG_SOBOL) {
     TQF_REQUIRE(rng->direction_numbers, "null direction numbers");
     TQF_REQUIRE(dims <= 21201, "Sobol dimension (steps * factors) exceeds 21201");
-    TQF_REQUIRE(rng->skip + num_paths_total < 2147483647ull, "skip + num_samples too large");
+    TQF_REQUIRE(rng->skip + rng->unit_offset + num_paths_total < 2147483647ull,
+                "skip + num_samples too large");
   }
   if (rng->type == TQF_RNG_DRAWS) TQF_REQUIRE(rng->draws_dev, "null normal_draws");
+  TQF_REQUIRE(rng->type != TQF_RNG_SOBOL || rng->unit_stride <= 1,
+              "Sobol draws need unit_stride == 1");
+  TQF_REQUIRE(model->kind != TQF_MODEL_MVGBM || (rng->unit_stride <= 1 && rng->unit_offset == 0),
+              "MVGBM does not support batched draw units");
 
   int ndev = 0;
   TQF_CUDA_OK(cudaGetDeviceCount(&ndev));

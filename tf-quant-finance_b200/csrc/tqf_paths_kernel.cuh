@@ -68,6 +68,7 @@ struct KParams {
   const Real* draws;         // device [N][S_total][NF]
   // work
   uint64_t path_offset;
+  uint64_t unit_stride, unit_offset;  // draw unit of path p: p * unit_stride + unit_offset
   uint64_t path_count;
   uint64_t num_chunks;
   uint64_t chunk_base;       // first_index rounded down to a multiple of kBlock
@@ -441,7 +442,8 @@ path_kernel(const KParams<typename Model::Real> P) {
       const uint64_t index = P.chunk_base + (sc * PPT + a) * kBlock + tid;
       valid[a] = index >= P.first_index && index < P.first_index + P.path_count;
       local[a] = index - P.first_index;  // row inside the shard
-      first_element[a] = valid[a] ? (P.path_offset + local[a]) * stream_stride : 0;
+      first_element[a] =
+          valid[a] ? ((P.path_offset + local[a]) * P.unit_stride + P.unit_offset) * stream_stride : 0;
     }
 
     Real x[PPT][NPATH][DIM], xmax[PPT][NPATH], xmin[PPT][NPATH];

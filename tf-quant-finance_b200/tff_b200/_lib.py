@@ -49,6 +49,8 @@ class RngDesc(C.Structure):
       ('skip', C.c_uint64),
       ('direction_numbers', C.c_void_p),
       ('draws_dev', C.c_void_p),
+      ('unit_stride', C.c_uint64),
+      ('unit_offset', C.c_uint64),
   ]
 
 

@@ -147,6 +147,16 @@ class GbmSpec1F(ModelSpec):
   def __init__(self, mean, volatility):
     self.mean, self.volatility = mean, volatility
 
+  def for_batch(self, index, batch_shape):
+    """The spec of one element of a batch of GBMs (parameters of shape
+    `batch_shape + [1]`, broadcastable)."""
+    def pick(p):
+      if callable(p) or np.ndim(p) == 0:
+        return p
+      arr = np.broadcast_to(np.asarray(p), tuple(batch_shape) + (1,))
+      return arr[tuple(index)][0]
+    return GbmSpec1F(pick(self.mean), pick(self.volatility))
+
   def coef_table(self, all_times, dtype):
     t, dt, sq = self._dt_columns(all_times, dtype)
     cols = [dt, sq, _eval_param(self.mean, t, dtype),
@@ -302,7 +312,11 @@ def record_plan(keep_mask, num_requested_times):
 class RngSpec:
   """Resolved random-number configuration of one sampling call."""
 
-  def __init__(self, random_type=None, seed=None, skip=0, normal_draws=None):
+  def __init__(self, random_type=None, seed=None, skip=0, normal_draws=None,
+               unit_stride=1, unit_offset=0, total_units=None):
+    # batched calls: path p draws unit p * unit_stride + unit_offset
+    self.unit_stride, self.unit_offset = int(unit_stride), int(unit_offset)
+    self.total_units = total_units
     rt = random.RandomType.PSEUDO if random_type is None else random_type
     if isinstance(rt, enum.Enum):
       rt = random.RandomType(rt.value)
@@ -376,6 +390,7 @@ class Plan:
 
     r = _lib.RngDesc()
     r.type, r.antithetic, r.skip = rng.type, int(rng.antithetic), rng.skip
+    r.unit_stride, r.unit_offset = rng.unit_stride, rng.unit_offset
     if rng.type == _lib.RNG_PHILOX:
       r.key = rng.key
       r.counter = rng.counter
@@ -412,7 +427,7 @@ class Plan:
       pass
 
   def paths(self, record_slot, num_times, unit_offset=0, unit_count=None,
-            exp_transform=False):
+            exp_transform=False, out=None):
     """States at the recorded steps: a `[rows, num_times, dim]` VIEW of a
     time-major `[num_times, dim, rows]` buffer (coalesced stores, no
     transpose).  rows = units (x2 for antithetic: partners follow).
@@ -420,7 +435,8 @@ class Plan:
     unit_count = self.units - unit_offset if unit_count is None else unit_count
     rows = unit_count * (2 if self.rng.antithetic else 1)
     dim = self.spec.dim
-    buf = _tensor.empty((num_times, dim, rows), self.dtype)
+    buf = _tensor.empty((num_times, dim, rows), self.dtype) if out is None else out
+    assert tuple(buf.shape) == (num_times, dim, rows) and buf.is_contiguous()
     rec = np.ascontiguousarray(record_slot, dtype=np.int32)
     _lib.check(_lib.lib().tqf_plan_paths(
         self._handle, unit_offset, unit_count, rec.ctypes.data, buf.data_ptr(),

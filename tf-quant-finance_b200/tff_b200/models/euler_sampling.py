@@ -77,23 +77,35 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
     if validate_args and int(normal_draws.shape[-2]) != keep_mask.shape[0] - 1:
       raise InvalidArgumentError('`num_time_steps` should be equal to '
                                  '`tf.shape(normal_draws)[1]`')
-  if batch_shape or (normal_draws is not None and normal_draws.dim() > 3):
+  if normal_draws is not None and (batch_shape or normal_draws.dim() > 3):
     raise NotImplementedError(
-        'batched processes (`initial_state` of rank > 2) are not implemented '
-        'by the B200 engine yet; loop over the batch on the host.')
-  x0 = initial_state.reshape(-1, dim)
-  if x0.shape[0] != 1 and not np.all(x0 == x0[0]):
-    raise NotImplementedError(
-        'per-path initial states are not implemented by the B200 engine yet.')
+        'batched `normal_draws` are not implemented by the B200 engine yet.')
   spec = closures.resolve_spec(drift_fn, volatility_fn, dim)
   if spec.dim != dim:
     raise ValueError('`dim` is {} but the model has dimension {}'.format(
         dim, spec.dim))
-  rng = engine.RngSpec(random_type, seed, skip, normal_draws)
   num_steps, record_slot = engine.record_plan(keep_mask, times.shape[0])
-  plan = engine.Plan(spec, all_times, num_steps, x0[0], rng, int(num_samples),
-                     dtype)
-  return plan, record_slot, times.shape[0]
+  num_samples = int(num_samples)
+  # one plan per element of the batch of processes (a single one without batch)
+  x0_full = np.broadcast_to(initial_state, batch_shape + initial_state.shape[len(batch_shape):])
+  batch_size = int(np.prod(batch_shape)) if batch_shape else 1
+  antithetic = normal_draws is None and random_type is not None and random_type.value in (
+      random.RandomType.PSEUDO_ANTITHETIC.value, random.RandomType.STATELESS_ANTITHETIC.value)
+  plans = []
+  for bi, index in enumerate(np.ndindex(*batch_shape)):
+    x0 = np.asarray(x0_full[index]).reshape(-1, dim)
+    if x0.shape[0] != 1 and not np.all(x0 == x0[0]):
+      raise NotImplementedError(
+          'per-path initial states are not implemented by the B200 engine yet.')
+    spec_b = spec.for_batch(index, batch_shape) if (
+        batch_shape and hasattr(spec, 'for_batch')) else spec
+    # draw units of a batch (models/utils.py:98-107): [batch, N] row-major, or
+    # [N/2, batch] for the antithetic types (sample_shape = [N] + batch_shape)
+    stride, offset = (batch_size, bi) if antithetic else (1, bi * num_samples)
+    rng = engine.RngSpec(random_type, seed, skip, normal_draws, unit_stride=stride,
+                         unit_offset=offset)
+    plans.append(engine.Plan(spec_b, all_times, num_steps, x0[0], rng, num_samples, dtype))
+  return plans, record_slot, times.shape[0], batch_shape
 
 
 def sample(dim,
@@ -124,18 +136,27 @@ def sample(dim,
   the reference's precomputed-draws path.
 
   Returns:
-    CUDA tensor of shape `[num_samples, k, dim]` (a zero-copy view of a
-    time-major buffer; call `.contiguous()` for sample-major memory).
+    CUDA tensor of shape `batch_shape + [num_samples, k, dim]` (a zero-copy view
+    of a time-major buffer; call `.contiguous()` for sample-major memory).
   """
   del swap_memory, precompute_normal_draws, name
-  plan, record_slot, k = _prepare(
+  plans, record_slot, k, batch_shape = _prepare(
       dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
       num_samples, initial_state, random_type, seed, skip, times_grid,
       normal_draws, watch_params, validate_args, tolerance, dtype)
   try:
-    return plan.paths(record_slot, k)
+    if not batch_shape:
+      return plans[0].paths(record_slot, k)
+    n = plans[0].num_samples
+    buf = _tensor.empty((len(plans), k, dim, n), plans[0].dtype)
+    for bi, plan in enumerate(plans):
+      plan.paths(record_slot, k, out=buf[bi])
+    nb = len(batch_shape)
+    out = buf.reshape(tuple(batch_shape) + (k, dim, n))
+    return out.permute(*range(nb), nb + 2, nb, nb + 1)
   finally:
-    plan.close()
+    for plan in plans:
+      plan.close()
 
 
 def price(dim, drift_fn, volatility_fn, times, payoffs, time_step=None,
@@ -150,10 +171,15 @@ def price(dim, drift_fn, volatility_fn, times, payoffs, time_step=None,
   Returns a float64 numpy array `[len(payoffs)]`; with `return_stats` also the
   standard errors and the number of non-finite payoffs.
   """
-  plan, _, _ = _prepare(
+  plans, _, _, batch_shape = _prepare(
       dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
       num_samples, initial_state, random_type, seed, skip, times_grid,
       normal_draws, None, validate_args, tolerance, dtype)
+  if batch_shape:
+    for plan in plans:
+      plan.close()
+    raise NotImplementedError('batched processes are not supported by `price` yet')
+  plan = plans[0]
   try:
     sums = plan.price_sums(list(payoffs)).cpu().numpy()
   finally:
