@@ -76,6 +76,9 @@ const char* tqf_last_error(void);
 int tqf_version(void);
 /* Number of visible CUDA devices (0 when there is none). */
 int tqf_device_count(void);
+/* sizeof of {tqf_rng_desc, tqf_model_desc, tqf_payoff_desc, tqf_lsm_desc} as
+ * compiled into the library (lets a binding verify its struct layouts). */
+int tqf_abi_sizes(int32_t out[4]);
 
 /* ------------------------------------------------------------------------
  * Stand-alone generators (bit-exact stream tests; also `tff.math.random`).

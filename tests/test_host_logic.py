@@ -42,6 +42,13 @@ def test_struct_layouts_match_header_sizes():
   assert C.sizeof(_lib.PayoffDesc) == 16 + 24 + 16 + 16 + 3 * 64 * 8
 
 
+def test_ctypes_structs_match_the_compiled_abi():
+  sizes = (C.c_int32 * 4)()
+  _lib.check(_lib.lib().tqf_abi_sizes(sizes))
+  assert list(sizes) == [C.sizeof(_lib.RngDesc), C.sizeof(_lib.ModelDesc),
+                         C.sizeof(_lib.PayoffDesc), C.sizeof(_lib.LsmDesc)]
+
+
 def test_product_does_not_import_oracle():
   pkg = os.path.join(ROOT, 'tf-quant-finance_b200')
   for base, _, files in os.walk(pkg):

@@ -177,6 +177,15 @@ int tqf_device_count(void) {
   return n;
 }
 
+int tqf_abi_sizes(int32_t out[4]) {
+  TQF_REQUIRE(out, "null argument");
+  out[0] = static_cast<int32_t>(sizeof(tqf_rng_desc));
+  out[1] = static_cast<int32_t>(sizeof(tqf_model_desc));
+  out[2] = static_cast<int32_t>(sizeof(tqf_payoff_desc));
+  out[3] = static_cast<int32_t>(sizeof(tqf_lsm_desc));
+  return TQF_OK;
+}
+
 int tqf_philox_stateless_key_counter(const int64_t seed[2], uint32_t key[2],
                                      uint32_t counter[4]) {
   TQF_REQUIRE(seed && key && counter, "null argument");

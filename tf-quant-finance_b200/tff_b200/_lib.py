@@ -128,6 +128,7 @@ _SIGNATURES = {
     'tqf_last_error': (C.c_char_p, []),
     'tqf_version': (C.c_int, []),
     'tqf_device_count': (C.c_int, []),
+    'tqf_abi_sizes': (C.c_int, [C.POINTER(C.c_int32)]),
     'tqf_philox_stateless_key_counter':
         (C.c_int, [C.POINTER(C.c_int64), _u32p, _u32p]),
     'tqf_philox_stateful_key_counter': (C.c_int, [C.c_int64, _u32p, _u32p]),
