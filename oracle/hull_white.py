@@ -234,3 +234,60 @@ def swaption_price_mc(*, expiries, fixed_leg_payment_times,
   if return_payoffs:
     return price, payoff
   return price
+
+
+def bond_option_price_mc(*, strikes, expiries, maturities, discount_rate_fn,
+                         mean_reversion, volatility, is_call_options=True,
+                         num_samples=1, random_type=None, seed=None, skip=0,
+                         time_step=None, dtype=np.float64):
+  """`bond_option_price(use_analytic_pricing=False)`
+  (`hull_white/zero_coupon_bond_option.py:186-210`) with
+  `options_price_from_samples` (`hjm/zero_coupon_bond_option_util.py:85-153`).
+  All of `strikes`, `expiries`, `maturities` broadcast to `strikes.shape`."""
+  dtype = np.dtype(dtype)
+  strikes = np.asarray(strikes, dtype=dtype)
+  shape = strikes.shape
+  expiries = np.broadcast_to(np.asarray(expiries, dtype=dtype), shape)
+  maturities = np.broadcast_to(np.asarray(maturities, dtype=dtype), shape)
+  is_call = np.broadcast_to(np.asarray(is_call_options, dtype=bool), shape)
+  model = HullWhiteModel1F(mean_reversion, volatility, discount_rate_fn, dtype)
+
+  from oracle import grid as grid_lib
+  sim_times = np.unique(expiries.reshape(-1))
+  longest = sim_times.max()
+  sim_times = np.unique(np.concatenate(
+      [sim_times, grid_lib.tf_range(time_step, longest, time_step, dtype)]))
+  tau = maturities - expiries
+  curve_times = np.unique(tau.reshape(-1))
+  p_t_tau, r_t = model.sample_discount_curve_paths(
+      sim_times, curve_times, num_samples, random_type, seed, skip)
+  dt = np.concatenate([[0.0], sim_times[1:] - sim_times[:-1]]).astype(dtype)
+  df = np.cumprod(np.exp(-r_t[:, :, 0] * dt[None, :]), axis=1)   # [N, k]
+  sim_idx = np.searchsorted(sim_times, expiries.reshape(-1), side='left')
+  curve_idx = np.searchsorted(curve_times, tau.reshape(-1), side='left')
+  payoff_df = df[:, sim_idx].reshape((num_samples,) + shape)
+  bond = p_t_tau[:, curve_idx, sim_idx, 0].reshape((num_samples,) + shape)
+  payoff = np.where(is_call, np.maximum(bond - strikes, 0.0),
+                    np.maximum(strikes - bond, 0.0))
+  return (payoff_df * payoff).mean(axis=0)
+
+
+def cap_floor_price_mc(*, strikes, expiries, maturities, daycount_fractions,
+                       reference_rate_fn, mean_reversion, volatility,
+                       notional=1.0, is_cap=True, num_samples=1,
+                       random_type=None, seed=None, skip=0, time_step=None,
+                       dtype=np.float64):
+  """`cap_floor_price(use_analytic_pricing=False)` (`hull_white/cap_floor.py:196-235`)."""
+  dtype = np.dtype(dtype)
+  strikes = np.asarray(strikes, dtype=dtype)
+  expiries = np.asarray(expiries, dtype=dtype)
+  dcf = np.asarray(daycount_fractions, dtype=dtype)
+  is_cap = np.asarray(is_cap, dtype=bool)
+  caplets = bond_option_price_mc(
+      strikes=1.0 / (1.0 + dcf * strikes), expiries=expiries,
+      maturities=maturities, discount_rate_fn=reference_rate_fn,
+      mean_reversion=mean_reversion, volatility=volatility,
+      is_call_options=~is_cap, num_samples=num_samples, random_type=random_type,
+      seed=seed, skip=skip, time_step=time_step, dtype=dtype)
+  caplets = np.where(np.broadcast_to(expiries, caplets.shape) < 0.0, 0.0, caplets)
+  return np.sum(np.asarray(notional, dtype) * (1.0 + dcf * strikes) * caplets, axis=-1)

@@ -171,3 +171,125 @@ def test_swaption_batch_with_different_expiries():
       random_type=odraws.RandomType.STATELESS, seed=[9, 9], dtype=np.float64, **kw)
   assert got.shape == (3,)
   np.testing.assert_allclose(got, want, rtol=1e-12)
+
+
+# ---------------------------------------------------------------- bond options
+@pytest.mark.parametrize('rng', [('STATELESS', [4, 2]), ('STATELESS_ANTITHETIC', [4, 2]),
+                                 ('SOBOL', None)], ids=lambda r: r[0])
+def test_bond_option_matches_oracle(rng):
+  import tff_b200 as tff
+  from tff_b200.math import piecewise
+  rt, seed = rng
+  n = 1 << 15
+  strikes = np.array([[0.95, 0.97], [0.93, 0.99]])
+  expiries = np.array([[1.0, 1.0], [0.55, 2.0]])
+  maturities = np.array([[5.0, 3.0], [4.0, 2.5]])
+  is_call = np.array([[True, False], [False, True]])
+  vol = piecewise.PiecewiseConstantFunc([0.5], [0.01, 0.02], dtype=np.float64)
+  ovol = omodels.PiecewiseConstantFunc([0.5], [0.01, 0.02], dtype=np.float64)
+  got = tff.models.hull_white.bond_option_price(
+      strikes=strikes, expiries=expiries, maturities=maturities,
+      discount_rate_fn=_curve, mean_reversion=0.03, volatility=vol,
+      is_call_options=is_call, use_analytic_pricing=False, num_samples=n,
+      time_step=0.1, random_type=tff.math.random.RandomType[rt], seed=seed,
+      dtype=np.float64)
+  want = ohw.bond_option_price_mc(
+      strikes=strikes, expiries=expiries, maturities=maturities,
+      discount_rate_fn=_curve, mean_reversion=0.03, volatility=ovol,
+      is_call_options=is_call, num_samples=n, time_step=0.1,
+      random_type=odraws.RandomType[rt], seed=seed)
+  assert got.shape == (2, 2) and got.dtype == np.float64
+  np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-16)
+
+
+def test_bond_option_reference_kat():
+  # models/hull_white/zero_coupon_bond_option_test.py:49-73 (0.02817777 +- 1e-4,
+  # 500k antithetic paths) and :119-146 (time-dependent vol, 0.02237839); the
+  # dt = 0.1 discount-factor quadrature alone biases the price by +5.5e-5
+  import tff_b200 as tff
+  from tff_b200.math import piecewise
+  expiries, maturities = np.array(1.0), np.array(5.0)
+  strikes = np.exp(-0.01 * maturities) / np.exp(-0.01 * expiries)
+  kw = dict(strikes=strikes, expiries=expiries, maturities=maturities,
+            mean_reversion=0.03, discount_rate_fn=_flat, use_analytic_pricing=False,
+            num_samples=500000, time_step=0.1,
+            random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, seed=[1, 7],
+            dtype=np.float64)
+  price = tff.models.hull_white.bond_option_price(volatility=0.02, **kw)
+  assert price.shape == ()
+  np.testing.assert_allclose(price, 0.02817777, rtol=1e-4, atol=1e-4)
+  vol = piecewise.PiecewiseConstantFunc([0.5], [0.01, 0.02], dtype=np.float64)
+  price = tff.models.hull_white.bond_option_price(volatility=vol, **kw)
+  np.testing.assert_allclose(price, 0.02237839, rtol=1e-4, atol=1e-4)
+
+
+def test_bond_option_errors():
+  import tff_b200 as tff
+  kw = dict(strikes=np.array(0.9), expiries=np.array(1.0), maturities=np.array(2.0),
+            discount_rate_fn=_flat, mean_reversion=0.03, volatility=0.02,
+            dtype=np.float64)
+  with pytest.raises(ValueError, match='time_step'):
+    tff.models.hull_white.bond_option_price(use_analytic_pricing=False, **kw)
+  with pytest.raises(NotImplementedError):
+    tff.models.hull_white.bond_option_price(use_analytic_pricing=True, **kw)
+
+
+# ----------------------------------------------------------------- caps/floors
+CAP = dict(expiries=np.array([0.0, 0.25, 0.5, 0.75]),
+           maturities=np.array([0.25, 0.5, 0.75, 1.0]),
+           strikes=0.01 * np.ones(4), daycount_fractions=0.25 * np.ones(4))
+
+
+def test_cap_price_reference_kat_and_oracle():
+  # models/hull_white/cap_floor_test.py:57-83: 0.4072088281493774 +- 1e-3 with
+  # 50k STATELESS_ANTITHETIC paths, seed [42, 42] (first caplet expires at t=0)
+  import tff_b200 as tff
+  kw = dict(notional=100.0, mean_reversion=0.03, volatility=0.02,
+            reference_rate_fn=_flat, num_samples=50_000, time_step=0.1,
+            seed=[42, 42], dtype=np.float64, **CAP)
+  price = tff.models.hull_white.cap_floor_price(
+      use_analytic_pricing=False,
+      random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, **kw)
+  assert price.shape == () and price.dtype == np.float64
+  np.testing.assert_allclose(price, 0.4072088281493774, rtol=1e-3, atol=1e-3)
+  want = ohw.cap_floor_price_mc(
+      random_type=odraws.RandomType.STATELESS_ANTITHETIC, **kw)
+  np.testing.assert_allclose(price, want, rtol=1e-12)
+
+
+def test_cap_floor_batch_matches_oracle():
+  # cap_floor_test.py:228-263 style 2-d batch: caps and floors, two strikes,
+  # piecewise-constant volatility
+  import tff_b200 as tff
+  from tff_b200.math import piecewise
+  expiries = np.broadcast_to(CAP['expiries'], (2, 2, 4))
+  maturities = np.broadcast_to(CAP['maturities'], (2, 2, 4))
+  strikes = np.array([[0.01, 0.02], [0.01, 0.02]])[..., None] * np.ones(4)
+  dcf = 0.25 * np.ones((2, 2, 4))
+  is_cap = np.array([[True, True], [False, False]])[..., None]
+  vol = piecewise.PiecewiseConstantFunc([0.5], [0.01, 0.02], dtype=np.float64)
+  ovol = omodels.PiecewiseConstantFunc([0.5], [0.01, 0.02], dtype=np.float64)
+  kw = dict(strikes=strikes, expiries=expiries, maturities=maturities,
+            daycount_fractions=dcf, notional=100.0, mean_reversion=0.03,
+            reference_rate_fn=_curve, is_cap=is_cap, num_samples=1 << 15,
+            time_step=0.1, seed=[3, 5], dtype=np.float64)
+  got = tff.models.hull_white.cap_floor_price(
+      volatility=vol, use_analytic_pricing=False,
+      random_type=tff.math.random.RandomType.STATELESS, **kw)
+  want = ohw.cap_floor_price_mc(
+      volatility=ovol, random_type=odraws.RandomType.STATELESS, **kw)
+  assert got.shape == (2, 2)
+  np.testing.assert_allclose(got, want, rtol=1e-12)
+
+
+def test_cap_reference_kat_time_dependent_vol():
+  # cap_floor_test.py:142-170: 0.2394242699989869 +- 1e-2
+  import tff_b200 as tff
+  from tff_b200.math import piecewise
+  vol = piecewise.PiecewiseConstantFunc([0.5], [0.01, 0.02], dtype=np.float64)
+  price = tff.models.hull_white.cap_floor_price(
+      notional=100.0, mean_reversion=0.03, volatility=vol, reference_rate_fn=_flat,
+      use_analytic_pricing=False, num_samples=100_000, time_step=0.1,
+      random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, seed=[42, 42],
+      dtype=np.float64, **CAP)
+  np.testing.assert_allclose(price, 0.2394242699989869, rtol=1e-2, atol=1e-2)

@@ -76,7 +76,7 @@ def test_ndtri():
   want = _mp(ref, u)
   nz = want != 0
   rel = np.abs(got[nz] - want[nz]) / np.abs(want[nz])
-  assert rel.max() <= 5e-16, rel.max()   # ~2 ulp (CUDA normcdfinv documents 5)
+  assert rel.max() <= 1e-15, rel.max()   # ~4 ulp (CUDA normcdfinv documents 5)
   assert np.all(got[~nz] == 0)
   # agreement with the oracle's scipy ndtri well inside the 1e-12 budget
   from scipy import special

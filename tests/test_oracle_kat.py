@@ -236,6 +236,37 @@ def test_hw_swaption_mc_kat():
   np.testing.assert_allclose(price, 0.71632434, rtol=1e-3, atol=1e-3)
 
 
+
+def test_hw_bond_option_mc_kat():
+  # models/hull_white/zero_coupon_bond_option_test.py:49-73 (analytic 0.02817777;
+  # the reference's MC tolerance is 1e-4 with 500k PSEUDO_ANTITHETIC paths)
+  from oracle import hull_white
+  expiries, maturities = np.array(1.0), np.array(5.0)
+  strikes = np.exp(-0.01 * maturities) / np.exp(-0.01 * expiries)
+  price = hull_white.bond_option_price_mc(
+      strikes=strikes, expiries=expiries, maturities=maturities,
+      discount_rate_fn=_flat_rate, mean_reversion=0.03, volatility=0.02,
+      num_samples=500000, time_step=0.1,
+      random_type=draws.RandomType.STATELESS_ANTITHETIC, seed=[1, 7])
+  assert price.shape == ()
+  np.testing.assert_allclose(price, 0.02817777, rtol=1e-4, atol=1e-4)
+
+
+def test_hw_cap_mc_kat():
+  # models/hull_white/cap_floor_test.py:57-83: 0.4072088281493774 +- 1e-3 with
+  # 50k STATELESS_ANTITHETIC paths, seed [42, 42]; first caplet expires at t = 0.
+  from oracle import hull_white
+  price = hull_white.cap_floor_price_mc(
+      strikes=0.01 * np.ones(4), expiries=np.array([0.0, 0.25, 0.5, 0.75]),
+      maturities=np.array([0.25, 0.5, 0.75, 1.0]),
+      daycount_fractions=0.25 * np.ones(4), notional=100.0,
+      reference_rate_fn=_flat_rate, mean_reversion=0.03, volatility=0.02,
+      num_samples=50_000, time_step=0.1,
+      random_type=draws.RandomType.STATELESS_ANTITHETIC, seed=[42, 42])
+  assert price.shape == ()
+  np.testing.assert_allclose(price, 0.4072088281493774, rtol=1e-3, atol=1e-3)
+
+
 # ------------------------------------------------------ Longstaff-Schwartz ----
 _LS_SAMPLES = np.expand_dims([[1.0, 1.09, 1.08, 1.34], [1.0, 1.16, 1.26, 1.54],
                               [1.0, 1.22, 1.07, 1.03], [1.0, 0.93, 0.97, 0.92],

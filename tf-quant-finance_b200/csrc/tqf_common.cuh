@@ -16,6 +16,8 @@ namespace tqf {
 // ------------------------------------------------------------ errors ------
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
+// Device-global {T, 1/c} table of the table logarithm (tqf_rng.cu).
+int device_logtab(const double** out);
 
 #define TQF_CUDA_OK(expr)                                        \
   do {                                                           \
@@ -118,9 +120,13 @@ __device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float* n0,
 
 // --------------------------------------------------------- inverse CDF ----
 // sqrt(2) erfinv(2u - 1) == ndtri(u) (multivariate_normal.py:420).
-__device__ __forceinline__ double ndtri(double u) { return fm::ndtri_q(u - 0.5); }
+// `logtab`: device-global table of the table logarithm (tqf::device_logtab()).
+__device__ __forceinline__ double ndtri(double u, const double* logtab) {
+  return fm::ndtri_q(u - 0.5, logtab);
+}
 // (u - 0.5) * 2 as the reference forms it (multivariate_normal.py:420), exact in fp32.
 __device__ __forceinline__ float ndtri(float u) { return fm::ndtri_t_f32((u - 0.5f) * 2.0f); }
+__device__ __forceinline__ float ndtri(float u, const double*) { return ndtri(u); }
 
 // ------------------------------------------------------------- Sobol ------
 // Device table V[d][32]: direction number m[d][b] left-aligned in 32 bits,

@@ -26,41 +26,47 @@
 namespace tqf {
 namespace fm {
 
-// Where the polynomial coefficients are fetched from.
-//  * SmemTab: a per-CTA copy of TQF_COEF in shared memory, read with volatile
-//    LDS.128 (two coefficients per load).  Used by the path kernels: the loads
-//    land in ordinary registers right where the DFMAs need them, instead of
-//    being hoisted into the (too few) uniform registers and spilled.
-//  * ConstTab: the constant bank directly (fill kernels, test hook).
+// Polynomial coefficients always come from the constant bank (TQF_COEF): a
+// volatile `ld.const.v2.f64` becomes an LDCU.128 into uniform registers next to
+// its DFMAs, which then take the coefficient as a UR operand -- measured
+// 98-100% of the DFMA peak against 81-88% for LDS-fed register operands
+// (tools/microbench/dfma_bench.cu).
+//
+// The "Tab" objects say where the {T, 1/c} table of the table logarithm
+// (tqf_logtab.inc, 20 KB) is read from:
+//  * SmemTab: a per-CTA copy in shared memory (fused path kernels; one LDS.128
+//    per draw, divergent index);
+//  * ConstTab: the device-global copy through the read-only path (fill kernels,
+//    test hook, kernels that cannot spare the shared memory).
 struct SmemTab {
-  uint32_t base;  // shared-window address of the table
-  __device__ __forceinline__ explicit SmemTab(const double* table)
-      : base(static_cast<uint32_t>(__cvta_generic_to_shared(table))) {}
-  __device__ __forceinline__ void load2(int off, double* a, double* b) const {
-#ifdef TQF_COEF_FROM_SMEM
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
-                 : "=d"(*a), "=d"(*b)
-                 : "r"(base + static_cast<uint32_t>(off) * 8u));
-#else
-    // Volatile constant-bank load: becomes LDCU.128 into uniform registers next
-    // to its DFMAs, which then take the coefficient as a UR operand -- measured
-    // 98-100% of the DFMA peak against 81-88% for LDS-fed register operands
-    // (tools/microbench/dfma_bench.cu).
-    asm volatile("ld.const.v2.f64 {%0, %1}, [%2];"
-                 : "=d"(*a), "=d"(*b)
-                 : "l"(__cvta_generic_to_constant(TQF_COEF + off)));
-#endif
+  static constexpr bool kClampHigh = false;  // arguments come from integer uniforms: a <= 1
+  uint32_t logbase;  // shared-window address of the log table (0: none)
+  __device__ __forceinline__ SmemTab() : logbase(0) {}
+  __device__ __forceinline__ explicit SmemTab(const double* s_logtab)
+      : logbase(static_cast<uint32_t>(__cvta_generic_to_shared(s_logtab))) {}
+  __device__ __forceinline__ void log_entry(int idx, double* t, double* invc) const {
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];"
+        : "=d"(*t), "=d"(*invc)
+        : "r"(logbase + static_cast<uint32_t>(idx) * 16u));
   }
 };
 struct ConstTab {
-  __device__ __forceinline__ void load2(int off, double* a, double* b) const {
-    *a = TQF_COEF[off];
-    *b = TQF_COEF[off + 1];
+  static constexpr bool kClampHigh = true;   // test hook: arbitrary (nan, > 1) arguments
+  const double* logtab;  // device-global table
+  __device__ __forceinline__ ConstTab() : logtab(nullptr) {}
+  __device__ __forceinline__ explicit ConstTab(const double* g) : logtab(g) {}
+  __device__ __forceinline__ void log_entry(int idx, double* t, double* invc) const {
+    const double2 e = __ldg(reinterpret_cast<const double2*>(logtab) + idx);
+    *t = e.x;
+    *invc = e.y;
   }
 };
-// Copies TQF_COEF into shared memory (call before a __syncthreads()).
-__device__ __forceinline__ void fill_smem_coef(double* dst, int tid, int nthreads) {
-  for (int i = tid; i < TQF_COEF_COUNT; i += nthreads) dst[i] = TQF_COEF[i];
+// Copies the log table into shared memory (call before a __syncthreads()).
+__device__ __forceinline__ void fill_smem_logtab(double* dst, const double* src, int tid,
+                                                 int nthreads) {
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+  double2* d2 = reinterpret_cast<double2*>(dst);
+  for (int i = tid; i < TQF_LOGTAB_COUNT; i += nthreads) d2[i] = __ldg(s2 + i);
 }
 
 // ---- Horner steps as single asm statements --------------------------------
@@ -247,34 +253,65 @@ __device__ __forceinline__ void log_pos_v(const Tab& tab, const double (&a)[K], 
   }
 }
 
+// y[k] = -log(a[k]) - TQF_NDTRI_C_MID for a in [exp(-6.25), 1] by table lookup:
+//   a = 2^e m;  i = (e, top 7 mantissa bits of m);  r = m * invc[i] - 1 (one
+//   exact FMA, |r| <= 2^-8);  y = T[i] - log1p(r),  T[i] = -MID - log(2^e / invc[i])
+// 8 FP64 instructions and one 16-byte table load, against 18 + MUFU + I2F for
+// log_pos_v.  Absolute error <= 1e-15 (T and T - r are each rounded once at
+// magnitude <= 4), which is what the polynomial in w needs: d(ndtri)/ndtri =
+// (P'/P) dw <= 0.26 dw.  Arguments below 2^-10 read entry 0 and give garbage:
+// the caller recomputes those (tail) draws with log_pos_v.
+template <int K, class Tab>
+__device__ __forceinline__ void neg_log_mid_tab_v(const Tab& tab, const double (&a)[K],
+                                                  double (&y)[K], uint32_t* hmin_out) {
+  double r[K], tr[K], q[K];
+  uint32_t hmin = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int hi = __double2hiint(a[k]);
+    const int lo = __double2loint(a[k]);
+    const uint32_t uh = static_cast<uint32_t>(hi);
+    hmin = uh < hmin ? uh : hmin;
+    int idx = (hi >> (20 - TQF_LOGTAB_BITS)) - ((1023 + TQF_LOGTAB_EMIN) << TQF_LOGTAB_BITS);
+    idx = max(idx, 0);
+    if (Tab::kClampHigh) idx = min(idx, TQF_LOGTAB_COUNT - 1);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    double t, invc;
+    tab.log_entry(idx, &t, &invc);
+    r[k] = fma(m, invc, -1.0);
+    tr[k] = t - r[k];
+  }
+  horner_v<TQF_LOG1P_OFF, TQF_LOG1P_N, K>(tab, r, q);
+#pragma unroll
+  for (int k = 0; k < K; ++k) y[k] = fma(r[k] * r[k], q[k], tr[k]);
+  *hmin_out = hmin;
+}
+
 // Inverse normal CDF of u = (1 + t) / 2 (t = 2u - 1 exact), |t| < 1:
 //   sqrt(2) erfinv(t) = t * P(w),  w = -log(1 - t^2)
 // (the parametrisation of M. Giles, "Approximating the erfinv function", 2010,
 // with our own double-precision fits).  The central branch w < 6.25 covers
-// |t| < 0.99806, i.e. 99.8% of uniform draws; the tail branch is entered by a
-// thread only when one of its K draws needs it.
+// |t| < 0.99806, i.e. 99.8% of uniform draws, and takes w from the table
+// logarithm; the tail branch is entered by a thread only when one of its K
+// draws needs it and recomputes w with the full-precision logarithm.
 template <int K, class Tab>
 __device__ __forceinline__ void ndtri_t_v(const Tab& tab, const double (&t)[K], double (&zout)[K]) {
-  double a[K], w[K], y[K], p[K];
+  double a[K], y[K], p[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) a[k] = fma(-t[k], t[k], 1.0);
-  log_pos_v<K>(tab, a, w);
-  // w[k] holds log(a) = -w <= 0: its high word, read as unsigned, grows with w,
-  // so one integer max + compare finds out whether any draw is in the tail.
-  uint32_t hmax = 0;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    y[k] = -TQF_NDTRI_C_MID - w[k];
-    const uint32_t h = static_cast<uint32_t>(__double2hiint(w[k]));
-    hmax = h > hmax ? h : hmax;
-  }
-  const bool tail = hmax >= 0xC0190000u;  // high word of -6.25
+  uint32_t hmin;
+  neg_log_mid_tab_v<K>(tab, a, y, &hmin);
   horner_v<TQF_NDTRI_C_OFF, TQF_NDTRI_C_N, K>(tab, y, p);
-  if (tail) {
+  // positive doubles order like their high words: one integer min + compare
+  // finds out whether any draw has 1 - t^2 < exp(-6.25)
+  if (hmin < TQF_NDTRI_TAIL_HI) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      if (w[k] <= -TQF_NDTRI_W0) {
-        const double yt[1] = {sqrt_pos(-w[k]) - TQF_NDTRI_T_MID};
+      if (static_cast<uint32_t>(__double2hiint(a[k])) < TQF_NDTRI_TAIL_HI) {
+        const double ak[1] = {a[k]};
+        double lg[1];
+        log_pos_v<1>(tab, ak, lg);
+        const double yt[1] = {sqrt_pos(-lg[0]) - TQF_NDTRI_T_MID};
         double pt[1];
         horner_v<TQF_NDTRI_T_OFF, TQF_NDTRI_T_N, 1>(tab, yt, pt);
         p[k] = pt[0];
@@ -350,11 +387,11 @@ __device__ __forceinline__ double log_pos(double a) {
   log_pos_v<1>(ConstTab(), in, out);
   return out[0];
 }
-// ndtri(u) for u = 1/2 + q, q exact.
-__device__ __forceinline__ double ndtri_q(double q) {
+// ndtri(u) for u = 1/2 + q, q exact; `logtab` = device-global log table.
+__device__ __forceinline__ double ndtri_q(double q, const double* logtab) {
   const double in[1] = {q + q};
   double out[1];
-  ndtri_t_v<1>(ConstTab(), in, out);
+  ndtri_t_v<1>(ConstTab(logtab), in, out);
   return out[0];
 }
 __device__ __forceinline__ void sincos_2pi(double v, double* sn, double* cs) {

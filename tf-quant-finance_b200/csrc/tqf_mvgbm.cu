@@ -30,6 +30,7 @@ struct MvParams {
   PhiloxKey key;
   PhiloxCtr ctr;
   const uint32_t* sobol_v;
+  const double* logtab;  // device-global log table (read through L1)
   uint64_t first_index, path_offset, path_count, num_chunks, chunk_base;
   int mode, num_payoffs;
   PayoffK pay[TQF_MAX_PAYOFFS];
@@ -49,7 +50,6 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
   __shared__ uint32_t s_high[kSobolTileDims];
   __shared__ uint4 s_low[kSobolTileDims * 2];
   __shared__ double s_acc[kWarps * TQF_MAX_PAYOFFS * 3];
-  __shared__ __align__(16) double s_cst[TQF_COEF_COUNT];
   // normals of one step, [dim][kBlock]: the draw loop is ROLLED (small code) and
   // hands its results to the unrolled mat-vec through shared memory -- the fully
   // unrolled version overflowed the instruction cache (ncu: 2.0 no_instruction
@@ -57,8 +57,7 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   Real* s_z = reinterpret_cast<Real*>(s_dyn);
   const int tid = threadIdx.x;
-  fm::fill_smem_coef(s_cst, tid, kBlock);
-  const fm::SmemTab tab(s_cst);
+  const fm::ConstTab tab(P.logtab);
   for (int i = tid; i < kWarps * TQF_MAX_PAYOFFS * 3; i += kBlock) s_acc[i] = 0.0;
   __syncthreads();
 
@@ -253,6 +252,7 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
   P.key = a.key;
   P.ctr = a.ctr;
   P.sobol_v = a.sobol_v;
+  P.logtab = a.logtab;
   P.first_index = a.first_index;
   P.path_offset = a.path_offset;
   P.path_count = a.path_count;

@@ -78,6 +78,7 @@ struct tqf_plan {
   int max_grid;
   void* coef_dev;           // Real [num_steps][ncoef]
   uint32_t* sobol_dev;      // [S_total*nf][32]
+  const double* logtab_dev; // shared per-device log table (not owned)
   double* partials_dev;     // [max_grid][TQF_MAX_PAYOFFS][4]
   int* record_dev;          // [num_steps+1]
   SwaptionK* swaptions_dev; // [TQF_MAX_PAYOFFS]
@@ -114,6 +115,7 @@ static void fill_common(const tqf_plan* plan, uint64_t path_offset, uint64_t pat
   P->ctr = PhiloxCtr{plan->rng.counter[0], plan->rng.counter[1], plan->rng.counter[2],
                      plan->rng.counter[3]};
   P->sobol_v = plan->sobol_dev;
+  P->logtab = plan->logtab_dev;
   P->draws = static_cast<const Real*>(plan->rng.draws_dev);
   P->path_offset = path_offset;
   P->path_count = path_count;
@@ -253,6 +255,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.key = P.key;
     a.ctr = P.ctr;
     a.sobol_v = plan->sobol_dev;
+    a.logtab = plan->logtab_dev;
     a.first_index = P.first_index;
     a.path_offset = path_offset;
     a.path_count = path_count;
@@ -318,6 +321,7 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.key = P.key;
     a.ctr = P.ctr;
     a.sobol_v = plan->sobol_dev;
+    a.logtab = plan->logtab_dev;
     a.first_index = P.first_index;
     a.path_offset = path_offset;
     a.path_count = path_count;
@@ -423,6 +427,7 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
   }
   if (rc == TQF_OK && rng->type == TQF_RNG_SOBOL)
     rc = upload_sobol_table(rng->direction_numbers, static_cast<int>(dims), &plan->sobol_dev, 0);
+  if (rc == TQF_OK) rc = device_logtab(&plan->logtab_dev);
   if (rc == TQF_OK) {
     e = cudaMalloc(&plan->partials_dev,
                    static_cast<size_t>(plan->max_grid) * TQF_MAX_PAYOFFS * 4 * sizeof(double));

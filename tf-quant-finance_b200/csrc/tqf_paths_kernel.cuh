@@ -24,7 +24,10 @@ namespace tqf {
 #endif
 constexpr int kBlock = 128;       // threads per CTA == Sobol indices per chunk
 constexpr int kLowBits = 7;       // log2(kBlock)
-constexpr int kSobolTileDims = 256;  // Sobol dimensions staged in smem at once
+#ifndef TQF_SOBOL_TILE
+#define TQF_SOBOL_TILE 256
+#endif
+constexpr int kSobolTileDims = TQF_SOBOL_TILE;  // Sobol dimensions staged in smem at once
 constexpr int kWarps = kBlock / 32;
 constexpr int kMaxPPT = 8;      // most paths carried by one thread
 
@@ -64,6 +67,7 @@ struct KParams {
   PhiloxCtr ctr;
   uint64_t anti_half;        // N/2 for antithetic plans
   const uint32_t* sobol_v;   // device [S_total*NF][32], left aligned
+  const double* logtab;      // device-global log table (tqf_math.cuh), double Sobol only
   uint64_t first_index;      // Sobol: skip + 1 + path_offset ; else path_offset
   const Real* draws;         // device [N][S_total][NF]
   // work
@@ -242,8 +246,9 @@ struct PhiloxStreamV<double, PPT> {
   uint64_t group[PPT];
   double b0[PPT], b1[PPT];
   int pos;
+  template <class Tab>
   __device__ __forceinline__ void refill(const PhiloxKey& key, const PhiloxCtr& ctr,
-                                         const fm::SmemTab& tab) {
+                                         const Tab& tab) {
     double u1[PPT], v1[PPT], lg[PPT], sn[PPT], cs[PPT];
 #pragma unroll
     for (int a = 0; a < PPT; ++a) {
@@ -262,16 +267,18 @@ struct PhiloxStreamV<double, PPT> {
       b1[a] = cs[a] * r;
     }
   }
+  template <class Tab>
   __device__ __forceinline__ void init(const PhiloxKey& key, const PhiloxCtr& ctr,
-                                       const fm::SmemTab& tab,
+                                       const Tab& tab,
                                        const uint64_t (&first_element)[PPT]) {
 #pragma unroll
     for (int a = 0; a < PPT; ++a) group[a] = first_element[a] >> 1;
     refill(key, ctr, tab);
     pos = static_cast<int>(first_element[0] & 1);
   }
+  template <class Tab>
   __device__ __forceinline__ void next(const PhiloxKey& key, const PhiloxCtr& ctr,
-                                       const fm::SmemTab& tab, double (&z)[PPT]) {
+                                       const Tab& tab, double (&z)[PPT]) {
     if (pos == 2) {
       refill(key, ctr, tab);
       pos = 0;
@@ -296,16 +303,18 @@ struct PhiloxStreamV<float, PPT> {
       box_muller(w.z, w.w, &b[a][2], &b[a][3]);
     }
   }
+  template <class Tab>
   __device__ __forceinline__ void init(const PhiloxKey& key, const PhiloxCtr& ctr,
-                                       const fm::SmemTab&,
+                                       const Tab&,
                                        const uint64_t (&first_element)[PPT]) {
 #pragma unroll
     for (int a = 0; a < PPT; ++a) group[a] = first_element[a] >> 2;
     refill(key, ctr);
     pos = static_cast<int>(first_element[0] & 3);
   }
+  template <class Tab>
   __device__ __forceinline__ void next(const PhiloxKey& key, const PhiloxCtr& ctr,
-                                       const fm::SmemTab&, float (&z)[PPT]) {
+                                       const Tab&, float (&z)[PPT]) {
     if (pos == 4) {
       refill(key, ctr);
       pos = 0;
@@ -318,19 +327,43 @@ struct PhiloxStreamV<float, PPT> {
 };
 
 // Inverse-CDF transform of K Sobol integer points.
-template <int K>
-__device__ __forceinline__ void sobol_normals(const fm::SmemTab& tab, const uint32_t (&xb)[K],
+template <int K, class Tab>
+__device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&xb)[K],
                                               double (&z)[K]) {
   double t[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) t[k] = sobol_centered_f64(xb[k]);
   fm::ndtri_t_v<K>(tab, t, z);
 }
-template <int K>
-__device__ __forceinline__ void sobol_normals(const fm::SmemTab&, const uint32_t (&xb)[K],
+template <int K, class Tab>
+__device__ __forceinline__ void sobol_normals(const Tab&, const uint32_t (&xb)[K],
                                               float (&z)[K]) {
 #pragma unroll
   for (int k = 0; k < K; ++k) z[k] = ndtri(sobol_uniform_f32(xb[k]));
+}
+
+// v[comp] for a register-resident state vector.  Written with opaque `selp`s:
+// a plain `j == comp ? v[j] : r` chain is turned into an indexed load by the
+// compiler, which moves the whole state array to local memory (an LDL/STL pair
+// per path and step in the hot loop).
+__device__ __forceinline__ double selp_real(double a, double b, int take_a) {
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}"
+      : "=d"(r) : "d"(a), "d"(b), "r"(take_a));
+  return r;
+}
+__device__ __forceinline__ float selp_real(float a, float b, int take_a) {
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}"
+      : "=f"(r) : "f"(a), "f"(b), "r"(take_a));
+  return r;
+}
+template <typename Real, int DIM>
+__device__ __forceinline__ Real select_component(const Real (&v)[DIM], int comp) {
+  Real r = v[0];
+#pragma unroll
+  for (int j = 1; j < DIM; ++j) r = selp_real(v[j], r, j == comp ? 1 : 0);
+  return r;
 }
 
 // ------------------------------------------------------------ payoffs -----
@@ -372,9 +405,39 @@ __device__ __forceinline__ double eval_payoff(const PayoffK& d, double x_final, 
 // -------------------------------------------------------------- kernel ----
 // Paths carried by one thread: enough that PPT * (draws per step) = 4 inverse
 // CDFs (Sobol) or 4 Box-Muller pairs (Philox) are evaluated side by side.
+// One step's NCOEF model constants through a generic pointer (shared or global
+// table); 16-byte loads when the row size allows (rows start 16-byte aligned).
+template <typename Real, int NCOEF>
+__device__ __forceinline__ void load_step_coef(const Real* row, Real (&cc)[NCOEF]) {
+  constexpr int PER16 = 16 / sizeof(Real);
+  if ((NCOEF % PER16) == 0) {
+    const uint4* v = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int i = 0; i < NCOEF / PER16; ++i) {
+      const uint4 q = v[i];
+      if (sizeof(Real) == 8) {
+        cc[2 * i] = static_cast<Real>(__hiloint2double(static_cast<int>(q.y), static_cast<int>(q.x)));
+        cc[2 * i + 1] = static_cast<Real>(__hiloint2double(static_cast<int>(q.w), static_cast<int>(q.z)));
+      } else {
+        cc[4 * i] = static_cast<Real>(__uint_as_float(q.x));
+        cc[4 * i + 1] = static_cast<Real>(__uint_as_float(q.y));
+        cc[4 * i + 2] = static_cast<Real>(__uint_as_float(q.z));
+        cc[4 * i + 3] = static_cast<Real>(__uint_as_float(q.w));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NCOEF; ++i) cc[i] = row[i];
+  }
+}
+
+#ifndef TQF_SOBOL_DRAWS
+#define TQF_SOBOL_DRAWS 8   // inverse CDFs evaluated side by side by one thread (tuning knob)
+#endif
 template <class Model, int RNGK>
 struct PathsPerThread {
-  static constexpr int value = (RNGK == RNGK_SOBOL) ? (Model::NF >= 8 ? 1 : 8 / Model::NF) : 4;
+  static constexpr int value =
+      (RNGK == RNGK_SOBOL) ? (Model::NF >= TQF_SOBOL_DRAWS ? 1 : TQF_SOBOL_DRAWS / Model::NF) : 4;
 };
 
 template <class Model, int RNGK, bool ANTI, int MODE>
@@ -402,11 +465,14 @@ path_kernel(const KParams<typename Model::Real> P) {
   uint4* s_low = reinterpret_cast<uint4*>(smem_raw + off);
   if (RNGK == RNGK_SOBOL) off += static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   double* s_acc = reinterpret_cast<double*>(smem_raw + off);
+  off += static_cast<size_t>(kWarps) * TQF_MAX_PAYOFFS * 3 * sizeof(double);
+  // {T, 1/c} table of the table logarithm behind the FP64 inverse CDF
+  constexpr bool kLogTab = RNGK == RNGK_SOBOL && sizeof(Real) == 8;
+  double* s_logtab = reinterpret_cast<double*>(smem_raw + off);
 
-  __shared__ __align__(16) double s_cst[TQF_COEF_COUNT];
   const int tid = threadIdx.x;
-  fm::fill_smem_coef(s_cst, tid, kBlock);
-  const fm::SmemTab tab(s_cst);
+  if (kLogTab) fm::fill_smem_logtab(s_logtab, P.logtab, tid, kBlock);
+  const fm::SmemTab tab = kLogTab ? fm::SmemTab(s_logtab) : fm::SmemTab();
   const Real* coef_tab = P.coef;
   const int* rec_tab = P.record_slot;
   if (P.tables_in_smem) {
@@ -504,13 +570,9 @@ path_kernel(const KParams<typename Model::Real> P) {
                 swap = sw.is_payer ? swap : -swap;
                 v = (swap > 0.0 ? swap : 0.0) * d.scale;
               } else {
-                double xf = 0.0;
                 const double xa = static_cast<double>(xmax[a][h]);
                 const double xi = static_cast<double>(xmin[a][h]);
-#pragma unroll
-                for (int j = 0; j < DIM; ++j) {
-                  if (j == d.component) xf = static_cast<double>(x[a][h][j]);
-                }
+                const double xf = static_cast<double>(select_component<Real, DIM>(x[a][h], d.component));
                 v = eval_payoff(d, xf, xa, xi);
               }
               if (isfinite(v)) {
@@ -561,6 +623,11 @@ path_kernel(const KParams<typename Model::Real> P) {
         __syncthreads();
       }
       for (int s = s0; s < s1; ++s) {
+        // step constants and record flag: loaded here, consumed after the draws
+        // (the loads' latency hides behind the inverse CDFs)
+        const int rec_next = rec_tab[s + 1];
+        Real cc[NCOEF];
+        load_step_coef<Real, NCOEF>(coef_tab + static_cast<size_t>(s) * NCOEF, cc);
         Real z[PPT][NF];
         if (RNGK == RNGK_PHILOX) {
 #pragma unroll
@@ -600,14 +667,6 @@ path_kernel(const KParams<typename Model::Real> P) {
             for (int j = 0; j < NF; ++j)
               z[a][j] = P.draws[first_element[a] + static_cast<size_t>(s) * NF + j];
         }
-        Real cc[NCOEF];
-        if (P.tables_in_smem) {   // shared-window loads (LDS), not generic LD
-#pragma unroll
-          for (int i = 0; i < NCOEF; ++i) cc[i] = s_coef[s * NCOEF + i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < NCOEF; ++i) cc[i] = P.coef[s * NCOEF + i];
-        }
 #pragma unroll
         for (int a = 0; a < PPT; ++a) {
           Model::step(x[a][0], z[a], cc);
@@ -620,21 +679,37 @@ path_kernel(const KParams<typename Model::Real> P) {
         }
         if (MODE == MODE_PRICE) {
           if (P.need_extrema) {
-            // running extrema of the ONE monitored state component
+            // running extrema of the ONE monitored state component; the flags are
+            // uniform, so each block is a branch around straight-line code
+            if (DIM == 1 || P.monitor == 0) {
+              if (P.need_extrema & 1) {
 #pragma unroll
-            for (int a = 0; a < PPT; ++a)
+                for (int a = 0; a < PPT; ++a)
 #pragma unroll
-              for (int h = 0; h < NPATH; ++h) {
-                Real xm = x[a][h][0];
-#pragma unroll
-                for (int j = 1; j < DIM; ++j) xm = (j == P.monitor) ? x[a][h][j] : xm;
-                if (P.need_extrema & 1) xmax[a][h] = xm > xmax[a][h] ? xm : xmax[a][h];
-                if (P.need_extrema & 2) xmin[a][h] = xm < xmin[a][h] ? xm : xmin[a][h];
+                  for (int h = 0; h < NPATH; ++h)
+                    xmax[a][h] = x[a][h][0] > xmax[a][h] ? x[a][h][0] : xmax[a][h];
               }
+              if (P.need_extrema & 2) {
+#pragma unroll
+                for (int a = 0; a < PPT; ++a)
+#pragma unroll
+                  for (int h = 0; h < NPATH; ++h)
+                    xmin[a][h] = x[a][h][0] < xmin[a][h] ? x[a][h][0] : xmin[a][h];
+              }
+            } else {
+#pragma unroll
+              for (int a = 0; a < PPT; ++a)
+#pragma unroll
+                for (int h = 0; h < NPATH; ++h) {
+                  const Real xm = select_component<Real, DIM>(x[a][h], P.monitor);
+                  if (P.need_extrema & 1) xmax[a][h] = xm > xmax[a][h] ? xm : xmax[a][h];
+                  if (P.need_extrema & 2) xmin[a][h] = xm < xmin[a][h] ? xm : xmin[a][h];
+                }
+            }
           }
-          if (rec_tab[s + 1] >= 0) eval_payoffs(s + 1);
+          if (rec_next >= 0) eval_payoffs(s + 1);
         } else {
-          const int slot = rec_tab[s + 1];
+          const int slot = rec_next;
           if (slot >= 0) {
 #pragma unroll
             for (int a = 0; a < PPT; ++a)
@@ -681,6 +756,8 @@ size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool table
   }
   if (rngk == RNGK_SOBOL) off += static_cast<size_t>(ppt) * kSobolTileDims * sizeof(uint32_t) + static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   off += static_cast<size_t>(kWarps) * TQF_MAX_PAYOFFS * 3 * sizeof(double);
+  if (rngk == RNGK_SOBOL && sizeof(Real) == 8)
+    off += static_cast<size_t>(TQF_LOGTAB_COUNT) * 2 * sizeof(double);
   return off;
 }
 
@@ -735,6 +812,7 @@ struct MvLaunch {
   PhiloxKey key;
   PhiloxCtr ctr;
   const uint32_t* sobol_v;
+  const double* logtab;
   uint64_t first_index, path_offset, path_count;
   int num_payoffs;
   const PayoffK* pay;

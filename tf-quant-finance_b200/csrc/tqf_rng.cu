@@ -21,6 +21,33 @@ int cuda_fail(cudaError_t e, const char* what) {
   return TQF_ERR_CUDA;
 }
 
+// Device-global copy of the {T, 1/c} table of the table logarithm
+// (tqf_math.cuh); uploaded once per device and kept for the process lifetime.
+static const double kLogTabHost[2 * TQF_LOGTAB_COUNT] = {
+#include "tqf_logtab.inc"
+};
+
+int device_logtab(const double** out) {
+  static std::mutex mu;
+  static const double* tables[64] = {nullptr};
+  int dev = 0;
+  TQF_CUDA_OK(cudaGetDevice(&dev));
+  TQF_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
+  std::lock_guard<std::mutex> lock(mu);
+  if (!tables[dev]) {
+    double* d = nullptr;
+    TQF_CUDA_OK(cudaMalloc(&d, sizeof(kLogTabHost)));
+    cudaError_t e = cudaMemcpy(d, kLogTabHost, sizeof(kLogTabHost), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(d);
+      return cuda_fail(e, "cudaMemcpy(log table)");
+    }
+    tables[dev] = d;
+  }
+  *out = tables[dev];
+  return TQF_OK;
+}
+
 // ------------------------------------------------------------- kernels ----
 __global__ void philox_raw_kernel(PhiloxKey key, PhiloxCtr ctr, uint64_t first_group,
                                   uint64_t num_groups, uint4* __restrict__ out) {
@@ -76,7 +103,8 @@ __global__ void philox_normal_f32_kernel(PhiloxKey key, PhiloxCtr ctr,
 template <int KIND, typename Out>
 __global__ void sobol_fill_kernel(const uint32_t* __restrict__ v_table, int dim,
                                   uint64_t first_index, uint64_t count,
-                                  int num_digits, Out* __restrict__ out) {
+                                  int num_digits, const double* __restrict__ logtab,
+                                  Out* __restrict__ out) {
   const uint64_t total = count * static_cast<uint64_t>(dim);
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -96,13 +124,13 @@ __global__ void sobol_fill_kernel(const uint32_t* __restrict__ v_table, int dim,
     } else if constexpr (KIND == 1) {
       out[e] = RealTraits<Out>::sobol_uniform(x);
     } else {
-      out[e] = ndtri(RealTraits<Out>::sobol_uniform(x));
+      out[e] = ndtri(RealTraits<Out>::sobol_uniform(x), logtab);
     }
   }
 }
 
 __global__ void math_eval_kernel(int fn, const double* __restrict__ in, double* __restrict__ out,
-                                 uint64_t n) {
+                                 uint64_t n, const double* __restrict__ logtab) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += stride) {
@@ -111,7 +139,7 @@ __global__ void math_eval_kernel(int fn, const double* __restrict__ in, double* 
     switch (fn) {
       case 0: r = fm::log_pos(x); break;
       case 1: r = fm::sqrt_pos(x); break;
-      case 2: r = ndtri(x); break;
+      case 2: r = ndtri(x, logtab); break;
       case 3: fm::sincos_2pi(x, &s, &c); r = s; break;
       default: fm::sincos_2pi(x, &s, &c); r = c; break;
     }
@@ -323,8 +351,11 @@ int tqf_math_eval(int fn, const double* in_dev, double* out_dev, uint64_t n, voi
   TQF_REQUIRE(fn >= 0 && fn <= 4, "fn must be in [0, 4]");
   if (n == 0) return TQF_OK;
   TQF_REQUIRE(in_dev && out_dev, "null argument");
+  const double* logtab = nullptr;
+  int rc = device_logtab(&logtab);
+  if (rc != TQF_OK) return rc;
   math_eval_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      fn, in_dev, out_dev, n);
+      fn, in_dev, out_dev, n, logtab);
   TQF_CUDA_OK(cudaGetLastError());
   return TQF_OK;
 }
@@ -342,25 +373,28 @@ int tqf_sobol_fill(const int32_t* direction_numbers, int dim, uint64_t num_resul
   TQF_REQUIRE(out_dev, "null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nd = sobol_num_digits(skip, num_results);
+  const double* logtab = nullptr;
+  int rc = device_logtab(&logtab);
+  if (rc != TQF_OK) return rc;
   uint32_t* table = nullptr;
-  int rc = upload_sobol_table(direction_numbers, dim, &table, s);
+  rc = upload_sobol_table(direction_numbers, dim, &table, s);
   if (rc != TQF_OK) return rc;
   const uint64_t first_index = skip + 1 + first_result;
   const int grid = grid_for(count * dim, 256);
   if (kind == 0) {
-    sobol_fill_kernel<0, int32_t><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd,
+    sobol_fill_kernel<0, int32_t><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd, logtab,
                                                         static_cast<int32_t*>(out_dev));
   } else if (kind == 1 && dtype == TQF_F64) {
-    sobol_fill_kernel<1, double><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd,
+    sobol_fill_kernel<1, double><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd, logtab,
                                                        static_cast<double*>(out_dev));
   } else if (kind == 1) {
-    sobol_fill_kernel<1, float><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd,
+    sobol_fill_kernel<1, float><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd, logtab,
                                                       static_cast<float*>(out_dev));
   } else if (dtype == TQF_F64) {
-    sobol_fill_kernel<2, double><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd,
+    sobol_fill_kernel<2, double><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd, logtab,
                                                        static_cast<double*>(out_dev));
   } else {
-    sobol_fill_kernel<2, float><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd,
+    sobol_fill_kernel<2, float><<<grid, 256, 0, s>>>(table, dim, first_index, count, nd, logtab,
                                                       static_cast<float*>(out_dev));
   }
   cudaError_t e = cudaGetLastError();

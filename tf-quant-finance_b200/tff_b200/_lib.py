@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libtqf.so')
+# TQF_LIBRARY: developer override used to A/B differently tuned builds.
+LIB_PATH = os.environ.get('TQF_LIBRARY') or os.path.join(_HERE, 'lib', 'libtqf.so')
 
 TQF_OK = 0
 TQF_ERR_INVALID_ARGUMENT = -1

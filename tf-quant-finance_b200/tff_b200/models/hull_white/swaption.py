@@ -22,8 +22,8 @@ from tff_b200.models.hull_white import _exact
 from tff_b200.models.hull_white import one_factor
 
 
-def _swaption_desc(model, all_times, step, expiry, pay_times, coupon, dcf,
-                   is_payer, notional):
+def _swaption_desc(model, step, expiry, pay_times, coupon, dcf, is_payer,
+                   notional):
   """tqf_payoff_desc of one swaption evaluated after `step` steps."""
   dt_ = model._dtype
   k = model._tables.k
@@ -44,7 +44,6 @@ def _swaption_desc(model, all_times, step, expiry, pay_times, coupon, dcf,
     d.pay_g[j] = float(g[j])
     d.pay_k[j] = float(ln_p0_ratio[j] - 0.5 * y * g[j]**2)
     d.pay_coef[j] = float(coef[j])
-  del all_times
   return d
 
 
@@ -54,6 +53,52 @@ class _RawPayoff:
 
   def desc(self):
     return self._d
+
+
+def _price_on_grid(model, sim_times, expiries, make_desc, num_samples,
+                   random_type, seed, skip):
+  """Runs the fused HW1F price kernel over `sim_times` and returns the payoff
+  sums `[len(expiries), 4]` and the number of simulated paths.
+
+  `make_desc(b, step)` builds the payoff descriptor of claim `b`, which is
+  evaluated when its path reaches simulation step `step` (the step that lands
+  on `expiries[b]`).  The path discount factor follows the reference's
+  convention DF(t_j) = exp(-sum_{i<=j} r(t_i) dt_i) with dt_0 = 0
+  (`hjm/swaption_util.py:126`, `hjm/zero_coupon_bond_option_util.py:102-113`).
+  """
+  dt_ = model._dtype
+
+  def integral_weights(all_times, idx):
+    # the step that lands on sim time j >= 1 carries t_j - t_{j-1}
+    w = np.zeros(all_times.shape[0] - 1, dtype=dt_)
+    dts = np.concatenate([[0.0], sim_times[1:] - sim_times[:-1]]).astype(dt_)
+    for j, i in enumerate(idx):
+      if i >= 1:
+        w[i - 1] += dts[j]
+    return w
+
+  plan, _, all_times, idx = model._exact_plan(
+      sim_times, int(num_samples), random_type, seed, skip, None, None,
+      integral_weights_fn=integral_weights)
+  try:
+    sim_idx = np.searchsorted(sim_times, expiries, side='left')
+    descs = []
+    for b in range(expiries.shape[0]):
+      step = int(idx[sim_idx[b]])
+      if step == 0:
+        # expiry at t = 0: the grid is [0, 0, ...] and the zero-length first
+        # step leaves the state at its initial value (x = 0, integral = 0).
+        if not (all_times.shape[0] > 1 and all_times[1] == all_times[0]):
+          raise ValueError('expiries must be non-negative.')
+        step = 1
+      descs.append(_RawPayoff(make_desc(b, step)))
+    sums = []
+    for c0 in range(0, len(descs), _lib.MAX_PAYOFFS):
+      sums.append(plan.price_sums(descs[c0:c0 + _lib.MAX_PAYOFFS]).cpu().numpy())
+    sums = np.concatenate(sums, axis=0)
+  finally:
+    plan.close()
+  return sums, float(plan.num_samples)
 
 
 def swaption_price(*,
@@ -126,33 +171,11 @@ def swaption_price(*,
       [sim_times, utils._tf_range(time_step, longest, time_step, dt_)]),
                       kind='stable').astype(dt_)
 
-  def integral_weights(all_times, idx):
-    # DF(t_j) = exp(-sum_{i<=j} r(t_i) dt_i), dt_0 = 0 (swaption_util.py:126):
-    # the step that lands on sim time j >= 1 carries t_j - t_{j-1}.
-    w = np.zeros(all_times.shape[0] - 1, dtype=dt_)
-    dts = np.concatenate([[0.0], sim_times[1:] - sim_times[:-1]]).astype(dt_)
-    for j, i in enumerate(idx):
-      if i >= 1:
-        w[i - 1] += dts[j]
-    return w
-
-  plan, _, all_times, idx = model._exact_plan(
-      sim_times, int(num_samples), random_type, seed, skip, None, None,
-      integral_weights_fn=integral_weights)
-  try:
-    sim_idx = np.searchsorted(sim_times, exp_flat, side='left')
-    descs = [
-        _RawPayoff(_swaption_desc(model, all_times, idx[sim_idx[b]], exp_flat[b],
-                                  pay_flat[b], cpn_flat[b], dcf_flat[b],
-                                  payer_flat[b], ntl_flat[b]))
-        for b in range(exp_flat.shape[0])]
-    sums = []
-    for c0 in range(0, len(descs), _lib.MAX_PAYOFFS):
-      sums.append(plan.price_sums(descs[c0:c0 + _lib.MAX_PAYOFFS]).cpu().numpy())
-    sums = np.concatenate(sums, axis=0)
-  finally:
-    plan.close()
-  n = float(plan.num_samples)
+  def make_desc(b, step):
+    return _swaption_desc(model, step, exp_flat[b], pay_flat[b], cpn_flat[b],
+                          dcf_flat[b], payer_flat[b], ntl_flat[b])
+  sums, n = _price_on_grid(model, sim_times, exp_flat, make_desc, num_samples,
+                           random_type, seed, skip)
   price = (sums[:, 0] / n).astype(dt_).reshape(batch_shape)
   if not return_stats:
     return price
