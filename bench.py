@@ -31,9 +31,11 @@ for _p in (ROOT, PKG):
 METRIC = 'euler_path_steps_per_sec'
 UNIT = 'path-steps/s'
 
-# Algorithmic FP64-pipe instructions per path-step (frozen; DESIGN.md section 5,
-# SURVEY.md 8(d)): C2 = 2 Sobol normals x 38 + Heston Euler update 20.
-ALGO_FP64_INSTR = {'c1': 27, 'c2': 96, 'c3': 48, 'c4': 3616, 'c5': 25}
+# Algorithmic FP64-pipe instructions per path-step (DESIGN.md section 4.1,
+# SURVEY.md 8(d)).  C2 = 2 Sobol normals x 32 (t, 1-t^2, table log 8, degree-21
+# polynomial, t*P) + Heston Euler update 14 (sqrt 6, state 8) + barrier compare 1;
+# it was 96 before the table logarithm replaced the 18-instruction log.
+ALGO_FP64_INSTR = {'c1': 26, 'c2': 79, 'c3': 47, 'c4': 3616, 'c5': 25}
 
 WORKLOADS = {
     'c1': dict(name='C1 GBM call (log-space affine), 100k paths x 100 steps, fp64, PSEUDO_ANTITHETIC seed 42',
@@ -105,7 +107,7 @@ def make_workload(name, num_paths=None):
     pay = np.array([1.25, 1.5, 1.75, 2.0])
     e_idx = idx[np.searchsorted(sim_times, 1.0, side='left')]
     payoffs = [swp._RawPayoff(swp._swaption_desc(
-        model, all_times, e_idx, 1.0, pay, 0.011 * np.ones(4), 0.25 * np.ones(4),
+        model, e_idx, 1.0, pay, 0.011 * np.ones(4), 0.25 * np.ones(4),
         True, 100.0))]
     steps = int(e_idx)
     return spec, all_times, x0, rng, payoffs, n, steps

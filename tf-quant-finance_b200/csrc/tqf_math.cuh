@@ -39,26 +39,24 @@ namespace fm {
 //  * ConstTab: the device-global copy through the read-only path (fill kernels,
 //    test hook, kernels that cannot spare the shared memory).
 struct SmemTab {
-  static constexpr bool kClampHigh = false;  // arguments come from integer uniforms: a <= 1
   uint32_t logbase;  // shared-window address of the log table (0: none)
   __device__ __forceinline__ SmemTab() : logbase(0) {}
   __device__ __forceinline__ explicit SmemTab(const double* s_logtab)
       : logbase(static_cast<uint32_t>(__cvta_generic_to_shared(s_logtab))) {}
-  __device__ __forceinline__ void log_entry(int idx, double* t, double* invc) const {
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];"
-        : "=d"(*t), "=d"(*invc)
-        : "r"(logbase + static_cast<uint32_t>(idx) * 16u));
+  // entry at byte offset `off16` (a multiple of 16 below 16 * TQF_LOGTAB_COUNT)
+  __device__ __forceinline__ void log_entry(uint32_t off16, double* t, double* s) const {
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(*t), "=d"(*s) : "r"(logbase + off16));
   }
 };
 struct ConstTab {
-  static constexpr bool kClampHigh = true;   // test hook: arbitrary (nan, > 1) arguments
   const double* logtab;  // device-global table
   __device__ __forceinline__ ConstTab() : logtab(nullptr) {}
   __device__ __forceinline__ explicit ConstTab(const double* g) : logtab(g) {}
-  __device__ __forceinline__ void log_entry(int idx, double* t, double* invc) const {
-    const double2 e = __ldg(reinterpret_cast<const double2*>(logtab) + idx);
+  __device__ __forceinline__ void log_entry(uint32_t off16, double* t, double* s) const {
+    const double2 e = __ldg(reinterpret_cast<const double2*>(
+        reinterpret_cast<const char*>(logtab) + off16));
     *t = e.x;
-    *invc = e.y;
+    *s = e.y;
   }
 };
 // Copies the log table into shared memory (call before a __syncthreads()).
@@ -210,18 +208,19 @@ __device__ __forceinline__ double rcp_pos(double d) {
   return r;
 }
 
-// sqrt(v), v normal and positive: MUFU.RSQ64H (2^-22), one coupled
-// Goldschmidt step (2^-43) and a final Newton correction.  7 FP64 ops.
+// sqrt(v), v normal and positive: MUFU.RSQ64H (y0 = rsqrt to 2^-22) and two
+// Newton steps on g ~ sqrt(v) that share h = y0 / 2 (an exponent decrement on
+// the integer pipe):  g <- g + (v - g^2) h.  The first step leaves 1.5 * 2^-44,
+// the second 2^-44 * 2^-22 (h is only 22 bits good, which is enough for a
+// correction term).  5 FP64 operations; <= 1 ulp (tests/test_gpu_math.py).
 __device__ __forceinline__ double sqrt_pos(double v) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+  const double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
   double g = v * y;
-  double h = 0.5 * y;
-  const double r = fma(-g, h, 0.5);
-  g = fma(g, r, g);
-  h = fma(h, r, h);
-  const double d = fma(-g, g, v);
-  return fma(d, h, g);
+  g = fma(fma(-g, g, v), h, g);
+  g = fma(fma(-g, g, v), h, g);
+  return g;
 }
 
 // log(a[k]), a normal, positive and finite (no zero / inf / nan / denormal
@@ -253,14 +252,17 @@ __device__ __forceinline__ void log_pos_v(const Tab& tab, const double (&a)[K], 
   }
 }
 
-// y[k] = -log(a[k]) - TQF_NDTRI_C_MID for a in [exp(-6.25), 1] by table lookup:
-//   a = 2^e m;  i = (e, top 7 mantissa bits of m);  r = m * invc[i] - 1 (one
-//   exact FMA, |r| <= 2^-8);  y = T[i] - log1p(r),  T[i] = -MID - log(2^e / invc[i])
-// 8 FP64 instructions and one 16-byte table load, against 18 + MUFU + I2F for
-// log_pos_v.  Absolute error <= 1e-15 (T and T - r are each rounded once at
-// magnitude <= 4), which is what the polynomial in w needs: d(ndtri)/ndtri =
-// (P'/P) dw <= 0.26 dw.  Arguments below 2^-10 read entry 0 and give garbage:
-// the caller recomputes those (tail) draws with log_pos_v.
+// y[k] = -log(a[k]) - TQF_NDTRI_C_MID for a in [2^-15, 1] by table lookup:
+//   a = 2^e m;  entry i = bits [13, 24) of the high word of a (low 4 exponent
+//   bits, top 7 mantissa bits: 2048 entries, any bit pattern stays in bounds);
+//   r = a * s[i] - 1 with s = 2^-e / c (one exact FMA, |r| <= 2^-8);
+//   y = T[i] - log1p(r),  T[i] = -MID - log(2^e c).
+// 8 FP64 instructions, 2 integer instructions and one 16-byte table load,
+// against 18 FP64 + MUFU + I2F + 6 integer for log_pos_v.  Absolute error
+// <= 1e-15 (T and T - r are each rounded once at magnitude <= 8), which is what
+// the polynomial in w needs: d(ndtri)/ndtri = (P'/P) dw <= 0.26 dw.  Arguments
+// below 2^-15 alias another row and give garbage: the caller recomputes those
+// (far tail) draws with log_pos_v.
 template <int K, class Tab>
 __device__ __forceinline__ void neg_log_mid_tab_v(const Tab& tab, const double (&a)[K],
                                                   double (&y)[K], uint32_t* hmin_out) {
@@ -268,23 +270,38 @@ __device__ __forceinline__ void neg_log_mid_tab_v(const Tab& tab, const double (
   uint32_t hmin = 0xffffffffu;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const int hi = __double2hiint(a[k]);
-    const int lo = __double2loint(a[k]);
-    const uint32_t uh = static_cast<uint32_t>(hi);
+    const uint32_t uh = static_cast<uint32_t>(__double2hiint(a[k]));
     hmin = uh < hmin ? uh : hmin;
-    int idx = (hi >> (20 - TQF_LOGTAB_BITS)) - ((1023 + TQF_LOGTAB_EMIN) << TQF_LOGTAB_BITS);
-    idx = max(idx, 0);
-    if (Tab::kClampHigh) idx = min(idx, TQF_LOGTAB_COUNT - 1);
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    double t, invc;
-    tab.log_entry(idx, &t, &invc);
-    r[k] = fma(m, invc, -1.0);
+    const uint32_t off16 = (uh >> (20 - TQF_LOGTAB_BITS - 4)) & ((TQF_LOGTAB_COUNT - 1) << 4);
+    double t, sc;
+    tab.log_entry(off16, &t, &sc);
+    r[k] = fma(a[k], sc, -1.0);
     tr[k] = t - r[k];
   }
   horner_v<TQF_LOG1P_OFF, TQF_LOG1P_N, K>(tab, r, q);
 #pragma unroll
   for (int k = 0; k < K; ++k) y[k] = fma(r[k] * r[k], q[k], tr[k]);
   *hmin_out = hmin;
+}
+
+// Tail polynomial of ndtri (TQF_NDTRI_T, degree 24) for ONE argument: the
+// branch is entered by single lanes, so its cost is dependent-instruction
+// latency -- even and odd powers run as two interleaved Horner chains in y^2
+// (13 dependent FMAs instead of 24); each ld.const pair feeds both chains.
+__device__ __forceinline__ double ndtri_tail_poly(double y) {
+  static_assert(TQF_NDTRI_T_N == 25, "tail polynomial layout");
+  const double y2 = y * y;
+  double e, o, c0, c1;
+  HornerAsm<1>::ld(TQF_NDTRI_T_OFF, &e, &o);
+#pragma unroll
+  for (int i = 2; i < TQF_NDTRI_T_N - 1; i += 2) {
+    HornerAsm<1>::ld(TQF_NDTRI_T_OFF + i, &c0, &c1);
+    e = fma(e, y2, c0);
+    o = fma(o, y2, c1);
+  }
+  HornerAsm<1>::ld(TQF_NDTRI_T_OFF + TQF_NDTRI_T_N - 1, &c0, &c1);
+  e = fma(e, y2, c0);
+  return fma(y, o, e);
 }
 
 // Inverse normal CDF of u = (1 + t) / 2 (t = 2u - 1 exact), |t| < 1:
@@ -307,14 +324,17 @@ __device__ __forceinline__ void ndtri_t_v(const Tab& tab, const double (&t)[K], 
   if (hmin < TQF_NDTRI_TAIL_HI) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      if (static_cast<uint32_t>(__double2hiint(a[k])) < TQF_NDTRI_TAIL_HI) {
-        const double ak[1] = {a[k]};
-        double lg[1];
-        log_pos_v<1>(tab, ak, lg);
-        const double yt[1] = {sqrt_pos(-lg[0]) - TQF_NDTRI_T_MID};
-        double pt[1];
-        horner_v<TQF_NDTRI_T_OFF, TQF_NDTRI_T_N, 1>(tab, yt, pt);
-        p[k] = pt[0];
+      const uint32_t hk = static_cast<uint32_t>(__double2hiint(a[k]));
+      if (hk < TQF_NDTRI_TAIL_HI) {
+        // w: from the table value while the table covers a, else the full logarithm
+        double w = y[k] + TQF_NDTRI_C_MID;
+        if (hk < ((1023u + TQF_LOGTAB_EMIN) << 20)) {
+          const double ak[1] = {a[k]};
+          double lg[1];
+          log_pos_v<1>(tab, ak, lg);
+          w = -lg[0];
+        }
+        p[k] = ndtri_tail_poly(sqrt_pos(w) - TQF_NDTRI_T_MID);
       }
     }
   }

@@ -116,6 +116,7 @@ static void fill_common(const tqf_plan* plan, uint64_t path_offset, uint64_t pat
                      plan->rng.counter[3]};
   P->sobol_v = plan->sobol_dev;
   P->logtab = plan->logtab_dev;
+  for (int k = 0; k < 8; ++k) P->sobol_hi[k] = 0x41400000;
   P->draws = static_cast<const Real*>(plan->rng.draws_dev);
   P->path_offset = path_offset;
   P->path_count = path_count;

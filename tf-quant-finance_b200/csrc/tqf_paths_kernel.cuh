@@ -68,6 +68,8 @@ struct KParams {
   uint64_t anti_half;        // N/2 for antithetic plans
   const uint32_t* sobol_v;   // device [S_total*NF][32], left aligned
   const double* logtab;      // device-global log table (tqf_math.cuh), double Sobol only
+  int sobol_hi[8];           // 8 x 0x41400000 (see sobol_normals): separate params so that
+                             // each lives in its own register
   uint64_t first_index;      // Sobol: skip + 1 + path_offset ; else path_offset
   const Real* draws;         // device [N][S_total][NF]
   // work
@@ -335,11 +337,30 @@ __device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&x
   for (int k = 0; k < K; ++k) t[k] = sobol_centered_f64(xb[k]);
   fm::ndtri_t_v<K>(tab, t, z);
 }
+// The same with the constant high word of (2^21 + x32 2^-31) held in K registers
+// the caller keeps alive (`hi[k]` = 0x41400000, opaque to the compiler): the
+// integer point lands in the low half of a register pair whose high half is
+// already in place, instead of costing one MOV per draw.
+template <int K, class Tab>
+__device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&xb)[K],
+                                              const int (&hi)[K], double (&z)[K]) {
+  double t[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    t[k] = __hiloint2double(hi[k], static_cast<int>(xb[k])) - 2097153.0;
+  fm::ndtri_t_v<K>(tab, t, z);
+}
+
 template <int K, class Tab>
 __device__ __forceinline__ void sobol_normals(const Tab&, const uint32_t (&xb)[K],
                                               float (&z)[K]) {
 #pragma unroll
   for (int k = 0; k < K; ++k) z[k] = ndtri(sobol_uniform_f32(xb[k]));
+}
+template <int K, class Tab>
+__device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&xb)[K],
+                                              const int (&)[K], float (&z)[K]) {
+  sobol_normals<K>(tab, xb, z);
 }
 
 // v[comp] for a register-resident state vector.  Written with opaque `selp`s:
@@ -449,12 +470,17 @@ path_kernel(const KParams<typename Model::Real> P) {
   constexpr int PPT = PathsPerThread<Model, RNGK>::value;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: coef [S][NCOEF] Real | record_slot [S+1] int | sobol high [PPT][T]
-  //         u32 | sobol low [T][8] u32 | accumulators [kWarps][8][3] double
-  Real* s_coef = reinterpret_cast<Real*>(smem_raw);
-  size_t off = 0;
+  // layout: log table (double Sobol only) | coef [S][NCOEF] Real | record_slot
+  //         [S+1] int | sobol high [PPT][T] u32 | sobol low [T][8] u32 |
+  //         accumulators [kWarps][8][3] double
+  // {T, s} table of the table logarithm behind the FP64 inverse CDF: first, so
+  // that its shared address is a compile-time constant in the LDS
+  constexpr bool kLogTab = RNGK == RNGK_SOBOL && sizeof(Real) == 8;
+  double* s_logtab = reinterpret_cast<double*>(smem_raw);
+  size_t off = kLogTab ? static_cast<size_t>(TQF_LOGTAB_COUNT) * 2 * sizeof(double) : 0;
+  Real* s_coef = reinterpret_cast<Real*>(smem_raw + off);
   if (P.tables_in_smem) {
-    off = static_cast<size_t>(P.num_steps) * NCOEF * sizeof(Real);
+    off += static_cast<size_t>(P.num_steps) * NCOEF * sizeof(Real);
     off = (off + 15) & ~static_cast<size_t>(15);
   }
   int* s_rec = reinterpret_cast<int*>(smem_raw + off);
@@ -465,10 +491,6 @@ path_kernel(const KParams<typename Model::Real> P) {
   uint4* s_low = reinterpret_cast<uint4*>(smem_raw + off);
   if (RNGK == RNGK_SOBOL) off += static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   double* s_acc = reinterpret_cast<double*>(smem_raw + off);
-  off += static_cast<size_t>(kWarps) * TQF_MAX_PAYOFFS * 3 * sizeof(double);
-  // {T, 1/c} table of the table logarithm behind the FP64 inverse CDF
-  constexpr bool kLogTab = RNGK == RNGK_SOBOL && sizeof(Real) == 8;
-  double* s_logtab = reinterpret_cast<double*>(smem_raw + off);
 
   const int tid = threadIdx.x;
   if (kLogTab) fm::fill_smem_logtab(s_logtab, P.logtab, tid, kBlock);
@@ -492,6 +514,13 @@ path_kernel(const KParams<typename Model::Real> P) {
   for (int b = 0; b < kLowBits; ++b) {
     lowmask[b] = 0u - ((static_cast<uint32_t>(tid) >> b) & 1u);
     asm volatile("" : "+r"(lowmask[b]));  // keep in a register; do not rematerialise per draw
+  }
+
+  // high words of the Sobol -> double conversion (see sobol_normals)
+  int t_hi[PPT * NF];
+#pragma unroll
+  for (int k = 0; k < PPT * NF; ++k) {
+    t_hi[k] = (RNGK == RNGK_SOBOL && sizeof(Real) == 8) ? P.sobol_hi[k & 7] : 0x41400000;
   }
 
   constexpr int TILE_STEPS = (kSobolTileDims / NF) > 0 ? (kSobolTileDims / NF) : 1;
@@ -655,7 +684,7 @@ path_kernel(const KParams<typename Model::Real> P) {
             for (int a = 0; a < PPT; ++a) xb[a * NF + j] = lowx ^ s_high[a * kSobolTileDims + dd];
           }
           Real zz[PPT * NF];
-          sobol_normals<PPT * NF>(tab, xb, zz);
+          sobol_normals<PPT * NF>(tab, xb, t_hi, zz);
 #pragma unroll
           for (int a = 0; a < PPT; ++a)
 #pragma unroll

@@ -87,7 +87,66 @@ double run(int blocks_per_sm) {
   return best;
 }
 
+// Dispatch-port test: K = 8 DFMA chains with NI independent integer ops (LOP3)
+// after every ND DFMAs.  If a DFMA held the SMSP dispatch port for its 2 pipe
+// cycles, the integer ops would add to the run time; if they issue in the
+// shadow of the FP64 pipe, the DFMA rate stays at the peak.
+template <int NI, int ND>
+__global__ void __launch_bounds__(128) mix_kernel(double* out, int iters, double seed) {
+  double y[8], p[8];
+  uint32_t q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { y[k] = seed + 1e-3 * (threadIdx.x + k); p[k] = y[k]; q[k] = threadIdx.x * 7 + k; }
+  const double c = seed * 0.25;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(p[k]) : "d"(y[k]), "d"(c));
+        if (((i * 8 + k) % ND) == ND - 1) {
+#pragma unroll
+          for (int n = 0; n < NI; ++n)
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(q[(k + n) & 7]) : "r"(q[(k + n + 3) & 7]), "r"(it));
+        }
+      }
+    }
+  }
+  double s = 0;
+  uint32_t t = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s += p[k]; t ^= q[k]; }
+  if (s == -1.2345 || t == 0x12345u) out[0] = s + t;
+}
+
+template <int NI, int ND>
+double run_mix(int blocks_per_sm) {
+  double* out; cudaMalloc(&out, 8);
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = sms * blocks_per_sm, iters = 2000;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int r = 0; r < 4; ++r) {
+    cudaEventRecord(e0);
+    mix_kernel<NI, ND><<<grid, 128>>>(out, iters, 0.5);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double rate = double(grid) * 128 * iters * 24.0 * 8 / (ms * 1e-3);
+    if (r && rate > best) best = rate;
+  }
+  cudaFree(out);
+  return best;
+}
+
 int main() {
+  printf("dispatch test (DFMA/s): int ops per DFMA\n");
+  for (int b : {3, 4}) {
+    printf("b=%d  0    %.3e\n", b, run_mix<0, 1>(b));
+    printf("b=%d  1/4  %.3e\n", b, run_mix<1, 4>(b));
+    printf("b=%d  1/2  %.3e\n", b, run_mix<1, 2>(b));
+    printf("b=%d  1    %.3e\n", b, run_mix<1, 1>(b));
+    printf("b=%d  2    %.3e\n", b, run_mix<2, 1>(b));
+  }
   printf("K MODE blocks/SM  DFMA/s\n");
   for (int b : {4}) {
     printf("8 pref  %d %.3e\n", b, run<8, 3>(b));
