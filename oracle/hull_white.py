@@ -291,3 +291,100 @@ def cap_floor_price_mc(*, strikes, expiries, maturities, daycount_fractions,
       seed=seed, skip=skip, time_step=time_step, dtype=dtype)
   caplets = np.where(np.broadcast_to(expiries, caplets.shape) < 0.0, 0.0, caplets)
   return np.sum(np.asarray(notional, dtype) * (1.0 + dcf * strikes) * caplets, axis=-1)
+
+
+class VectorHullWhiteModel:
+  """Correlated Hull-White factors, exact discretisation
+  (`vector_hull_white.py:641-781` for dim > 1): constant mean reversions,
+  constant or piecewise-constant volatilities (one `PiecewiseConstantFunc` or
+  scalar per factor), constant or piecewise-constant correlation matrix.
+
+  `initial_discount_rate_fn(t)` returns `t.shape` or `t.shape + [dim]` (numpy,
+  analytic in t)."""
+
+  def __init__(self, dim, mean_reversion, volatility, initial_discount_rate_fn,
+               corr_matrix=None, dtype=np.float64):
+    self.dim = int(dim)
+    self.dtype = np.dtype(dtype)
+    mr = np.broadcast_to(np.asarray(mean_reversion, dtype=self.dtype), (self.dim,))
+    vols = volatility if isinstance(volatility, (list, tuple)) else [
+        v for v in np.broadcast_to(np.asarray(volatility, dtype=self.dtype), (self.dim,))]
+
+    def rate_i(i):
+      def fn(t):
+        r = np.asarray(initial_discount_rate_fn(t))
+        return r[..., i] if r.ndim == np.ndim(t) + 1 else r
+      return fn
+    self.factors = [HullWhiteModel1F(mr[i], vols[i], rate_i(i), self.dtype)
+                    for i in range(self.dim)]
+    self.corr = corr_matrix
+
+  def _corr_root(self, t):
+    """Cholesky factors at times `t` ([n, dim, dim]); identity when no corr."""
+    n = t.shape[0]
+    if self.corr is None:
+      return None
+    if callable(self.corr):
+      c = np.asarray(self.corr(t), dtype=self.dtype)
+    else:
+      c = np.broadcast_to(np.asarray(self.corr, dtype=self.dtype), (n, self.dim, self.dim))
+    return np.linalg.cholesky(c)
+
+  def sample_paths(self, times, num_samples, random_type=None, seed=None, skip=0,
+                   times_grid=None, normal_draws=None):
+    """Short rates [num_samples, k, dim]."""
+    times = np.asarray(times, dtype=self.dtype)
+    k = times.shape[0]
+    if times_grid is None:
+      jumps = [f.jumps for f in self.factors]
+      all_times = np.sort(np.concatenate([np.zeros(1, self.dtype), times] + jumps),
+                          kind='stable').astype(self.dtype)
+      idx = np.searchsorted(all_times, times, side='left')
+    else:
+      all_times = np.asarray(times_grid, dtype=self.dtype)
+      idx = np.minimum(np.searchsorted(all_times, times, side='left'), all_times.shape[0] - 1)
+      d1 = all_times[idx] - times
+      d2 = all_times[np.maximum(idx - 1, 0)] - times
+      idx = np.where(np.abs(d2) > np.abs(d1), idx, np.maximum(idx - 1, 0))
+    keep_mask = np.zeros(all_times.shape[0], dtype=bool)
+    keep_mask[idx] = True
+    dt = all_times[1:] - all_times[:-1]
+    steps = dt.shape[0]
+    if normal_draws is None:
+      normal_draws = draws_lib.generate_mc_normal_draws(
+          self.dim, steps, num_samples,
+          draws_lib.RandomType.PSEUDO if random_type is None else random_type,
+          seed=seed, dtype=self.dtype, skip=skip)               # [steps, N, dim]
+    else:
+      normal_draws = np.transpose(np.asarray(normal_draws, self.dtype), [1, 0, 2])
+    exp_x = np.stack([f.conditional_mean_x(all_times) for f in self.factors], -1)   # [S, dim]
+    var_x = np.stack([f.conditional_variance_x(all_times) for f in self.factors], -1)
+    kk = np.asarray([f.k for f in self.factors], dtype=self.dtype)
+    root = self._corr_root(all_times + dt.min() / 2) if steps else None
+
+    def f0(t):
+      return np.asarray([f.fwd(t) for f in self.factors], dtype=self.dtype)
+    x = np.zeros((num_samples, self.dim), dtype=self.dtype)
+    record = k != 1
+    slots = [None] * k
+    out = x + f0(all_times[0])
+    if record:
+      slots[0] = out
+    written = int(keep_mask[0])
+    i = 0
+    while i < steps and written < k:
+      normals = normal_draws[i]
+      if root is not None:
+        normals = np.einsum('ij,nj->ni', root[i], normals)
+      vol = np.sqrt(np.maximum(var_x[i], 0))
+      vol = np.where(vol > 0, vol, 0)
+      x = np.exp(-kk * dt[i]) * x + exp_x[i] + vol * normals
+      out = x + f0(all_times[i + 1])
+      if record:
+        slots[written] = out
+      written += int(keep_mask[i + 1])
+      i += 1
+    if not record:
+      return out[:, None, :]
+    slots = [np.zeros_like(x) if s is None else s for s in slots]
+    return np.transpose(np.stack(slots, 0), [1, 0, 2])

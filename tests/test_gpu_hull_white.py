@@ -293,3 +293,147 @@ def test_cap_reference_kat_time_dependent_vol():
       random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, seed=[42, 42],
       dtype=np.float64, **CAP)
   np.testing.assert_allclose(price, 0.2394242699989869, rtol=1e-2, atol=1e-2)
+
+
+# ------------------------------------------------------ correlated factors ----
+def _flat2(t):
+  import torch
+  if isinstance(t, torch.Tensor):
+    return 0.01 + 0 * t.unsqueeze(-1) * torch.ones(2, dtype=t.dtype)
+  return 0.01 + 0 * np.asarray(t)[..., None] * np.ones(2)
+
+
+def _curve2(t):
+  import torch
+  if isinstance(t, torch.Tensor):
+    return 0.01 + t.unsqueeze(-1) * torch.tensor([0.002, 0.001], dtype=t.dtype)
+  return 0.01 + np.asarray(t)[..., None] * np.array([0.002, 0.001])
+
+
+def _vector_models(curve, corr_kind, dtype=np.float64):
+  import tff_b200 as tff
+  from tff_b200.math import piecewise
+  mr = [0.1, 0.05]
+  jumps = [[0.1, 0.2, 0.5], [0.1, 2.0, 3.0]]
+  vals = [[0.01, 0.012, 0.011, 0.013], [0.02, 0.018, 0.02, 0.02]]
+  vol = piecewise.PiecewiseConstantFunc(jumps, vals, dtype=dtype)
+  ovol = [omodels.PiecewiseConstantFunc(jumps[i], vals[i], dtype=dtype) for i in range(2)]
+  if corr_kind == 'none':
+    corr = ocorr = None
+  elif corr_kind == 'const':
+    corr = ocorr = [[1., 0.5], [0.5, 1.]]
+  else:
+    cv = [[[1., 0.5], [0.5, 1.]], [[1., 0.6], [0.6, 1.]], [[1., 0.9], [0.9, 1.]]]
+    corr = piecewise.PiecewiseConstantFunc([0.5, 2.0], cv, dtype=dtype)
+    ocorr = omodels.PiecewiseConstantFunc([0.5, 2.0], cv, dtype=dtype)
+  model = tff.models.hull_white.VectorHullWhiteModel(
+      2, mr, vol, curve, corr_matrix=corr, dtype=dtype)
+  omodel = ohw.VectorHullWhiteModel(2, mr, ovol, curve, ocorr, dtype)
+  return model, omodel
+
+
+@pytest.mark.parametrize('rng', RNGS, ids=lambda r: r[0])
+@pytest.mark.parametrize('corr_kind', ['none', 'const', 'piecewise'])
+def test_vector_hw_paths_match_oracle(rng, corr_kind):
+  import tff_b200 as tff
+  rt, seed, skip = rng
+  model, omodel = _vector_models(_curve2, corr_kind)
+  times = [0.1, 0.5, 1.0, 2.5]
+  n = 2000
+  got = _np(model.sample_paths(times, num_samples=n,
+                               random_type=tff.math.random.RandomType[rt],
+                               seed=seed, skip=skip))
+  want = omodel.sample_paths(times, n, odraws.RandomType[rt], seed=seed, skip=skip)
+  assert got.shape == want.shape == (n, 4, 2)
+  np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
+
+
+def test_vector_hw_reference_moments_kat():
+  # hull_white_test.py:223-270: mean / variance (1e-4) and correlation (1e-2)
+  # at t = 1 with 50k STATELESS_ANTITHETIC paths, seed [1, 2]
+  import tff_b200 as tff
+  from tff_b200.math import piecewise
+  a, sigma = np.array([0.1, 0.05]), np.array([0.01, 0.02])
+  vol = piecewise.PiecewiseConstantFunc(
+      [[0.1, 0.2, 0.5], [0.1, 2.0, 3.0]], [4 * [sigma[0]], 4 * [sigma[1]]], dtype=np.float64)
+  model = tff.models.hull_white.VectorHullWhiteModel(
+      2, a, vol, _flat2, corr_matrix=[[1., 0.5], [0.5, 1.]], dtype=np.float64)
+  paths = _np(model.sample_paths(
+      [0.1, 0.5, 1.0], num_samples=50000,
+      random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, seed=[1, 2]))
+  assert paths.shape == (50000, 3, 2) and paths.dtype == np.float64
+  x = paths[:, -1, :]
+  np.testing.assert_allclose(x.mean(0), 0.01 + sigma**2 / 2 / a**2 * (1 - np.exp(-a))**2,
+                             rtol=1e-4, atol=1e-4)
+  np.testing.assert_allclose(x.var(0), sigma**2 / 2 / a * (1 - np.exp(-2 * a)),
+                             rtol=1e-4, atol=1e-4)
+  np.testing.assert_allclose(np.corrcoef(x[:, 0], x[:, 1])[0, 1], 0.5, atol=1e-2)
+
+
+def test_vector_hw_supplied_draws_and_grid():
+  # hull_white_test.py:283-342 ("SupplyDrawsSupplyGrid"): user draws [N, steps, 2]
+  # on a user grid
+  import torch
+  import tff_b200 as tff
+  model, omodel = _vector_models(_flat2, 'piecewise')
+  grid = [0.0, 0.1, 0.2, 0.5, 1.0]
+  n = 1000
+  half = np.random.RandomState(3).standard_normal((n // 2, 4, 2))
+  draws = np.concatenate([half, -half], 0)
+  got = _np(model.sample_paths([0.1, 0.5, 1.0], normal_draws=torch.as_tensor(draws).cuda(),
+                               times_grid=grid))
+  want = omodel.sample_paths([0.1, 0.5, 1.0], n, normal_draws=draws, times_grid=grid)
+  assert got.shape == (n, 3, 2)
+  np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
+
+
+def test_vector_hw_generic_corr_uses_euler():
+  # hull_white_test.py:344-383: a generic callable correlation -> Euler scheme
+  # on the model closures; parity with the oracle Euler sampler on the same
+  # closures
+  import torch
+  import tff_b200 as tff
+  a, sigma = np.array([0.1, 0.05]), np.array([0.01, 0.02])
+
+  def corr(t):
+    one = torch.ones((), dtype=torch.float64) if isinstance(t, torch.Tensor) else 1.0
+    rho = 0.5 * one
+    if isinstance(t, torch.Tensor):
+      return torch.stack([torch.stack([one, rho]), torch.stack([rho, one])])
+    return np.array([[1.0, 0.5], [0.5, 1.0]])
+  model = tff.models.hull_white.VectorHullWhiteModel(
+      2, a, sigma, _flat2, corr_matrix=corr, dtype=np.float64)
+  with pytest.raises(ValueError, match='time_step'):
+    model.sample_paths([0.5, 1.0], num_samples=10)
+  n = 4000
+  got = _np(model.sample_paths([0.5, 1.0], num_samples=n, time_step=0.1,
+                               random_type=tff.math.random.RandomType.STATELESS,
+                               seed=[7, 1]))
+  root = np.linalg.cholesky(np.array([[1.0, 0.5], [0.5, 1.0]]))
+
+  def drift_fn(t, x):
+    return a * 0.01 + sigma**2 / 2 / a * (1 - np.exp(-2 * a * t)) - a * x
+
+  def vol_fn(t, x):
+    return np.broadcast_to(sigma[:, None] * root, x.shape[:-1] + (2, 2))
+  want = oeuler.sample(2, drift_fn, vol_fn, [0.5, 1.0], time_step=0.1, num_samples=n,
+                       initial_state=np.array([0.01, 0.01]),
+                       random_type=odraws.RandomType.STATELESS, seed=[7, 1],
+                       dtype=np.float64)
+  assert got.shape == (n, 2, 2)
+  np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
+
+
+def test_vector_hw_dim1_and_errors():
+  import tff_b200 as tff
+  m1 = tff.models.hull_white.VectorHullWhiteModel(1, [0.1], [0.01], _flat, dtype=np.float64)
+  m0 = tff.models.HullWhiteModel1F(0.1, 0.01, _flat, dtype=np.float64)
+  kw = dict(num_samples=500, random_type=tff.math.random.RandomType.STATELESS, seed=[1, 2])
+  np.testing.assert_array_equal(_np(m1.sample_paths([0.5, 1.0], **kw)),
+                                _np(m0.sample_paths([0.5, 1.0], **kw)))
+  with pytest.raises(ValueError, match='should be the same as `dims`'):
+    tff.models.hull_white.VectorHullWhiteModel(2, [0.1], [0.01, 0.02], _flat2, dtype=np.float64)
+  m2 = tff.models.hull_white.VectorHullWhiteModel(2, [0.1, 0.2], [0.01, 0.02], _flat2,
+                                                  dtype=np.float64)
+  with pytest.raises(ValueError, match='rank 1'):
+    m2.sample_paths([[0.5, 1.0]], num_samples=10)

@@ -237,6 +237,28 @@ def test_hw_swaption_mc_kat():
 
 
 
+
+def test_vector_hw_2d_moments_kat():
+  # models/hull_white/hull_white_test.py:223-270: two correlated factors with
+  # (batched) piecewise-constant volatilities; terminal mean / variance against
+  # the Brigo-Mercurio closed forms (1e-4) and the correlation (1e-2).
+  from oracle import hull_white
+  from oracle import models
+  a = np.array([0.1, 0.05]); sigma = np.array([0.01, 0.02])
+  vols = [models.PiecewiseConstantFunc([0.1, 0.2, 0.5], 4 * [sigma[0]]),
+          models.PiecewiseConstantFunc([0.1, 2.0, 3.0], 4 * [sigma[1]])]
+  m = hull_white.VectorHullWhiteModel(2, a, vols, _flat_rate, [[1., 0.5], [0.5, 1.]])
+  paths = m.sample_paths([0.1, 0.5, 1.0], 50000, draws.RandomType.STATELESS_ANTITHETIC,
+                         seed=[1, 2])
+  assert paths.shape == (50000, 3, 2)
+  x = paths[:, -1, :]
+  true_mean = 0.01 + sigma**2 / 2 / a**2 * (1 - np.exp(-a))**2
+  true_var = sigma**2 / 2 / a * (1 - np.exp(-2 * a))
+  np.testing.assert_allclose(x.mean(0), true_mean, rtol=1e-4, atol=1e-4)
+  np.testing.assert_allclose(x.var(0), true_var, rtol=1e-4, atol=1e-4)
+  np.testing.assert_allclose(np.corrcoef(x[:, 0], x[:, 1])[0, 1], 0.5, atol=1e-2)
+
+
 def test_hw_bond_option_mc_kat():
   # models/hull_white/zero_coupon_bond_option_test.py:49-73 (analytic 0.02817777;
   # the reference's MC tolerance is 1e-4 with 500k PSEUDO_ANTITHETIC paths)

@@ -9,8 +9,9 @@ from tff_b200.models.geometric_brownian_motion.multivariate_geometric_brownian_m
 from tff_b200.models.geometric_brownian_motion.univariate_geometric_brownian_motion import GeometricBrownianMotion
 from tff_b200.models.heston.heston_model import HestonModel
 from tff_b200.models.hull_white.one_factor import HullWhiteModel1F
+from tff_b200.models.hull_white.vector_hull_white import VectorHullWhiteModel
 from tff_b200.models.ito_process import ItoProcess
 
 __all__ = ['closures', 'euler_sampling', 'utils', 'GenericItoProcess',
-           'GeometricBrownianMotion', 'MultivariateGeometricBrownianMotion', 'HestonModel', 'HullWhiteModel1F', 'ItoProcess',
+           'GeometricBrownianMotion', 'MultivariateGeometricBrownianMotion', 'HestonModel', 'HullWhiteModel1F', 'VectorHullWhiteModel', 'ItoProcess',
            'hull_white', 'longstaff_schwartz']

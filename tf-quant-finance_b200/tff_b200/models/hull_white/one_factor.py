@@ -198,7 +198,7 @@ class HullWhiteModel1F(generic_ito_process.GenericItoProcess):
     k = float(self._tables.k)
 
     def dv(a):
-      return torch.as_tensor(np.asarray(a, dtype=self._dtype), device=dev, dtype=td)
+      return torch.as_tensor(np.array(a, dtype=self._dtype), device=dev, dtype=td)
     f0 = dv(self._fwd(times))
     p0t = dv(np.exp(-_exact.discount_rate(self._initial_discount_rate_fn, times, self._dtype) * times))
     p0T = dv(np.exp(-_exact.discount_rate(self._initial_discount_rate_fn, maturities, self._dtype) * maturities))
