@@ -31,6 +31,7 @@ struct MvParams {
   PhiloxCtr ctr;
   const uint32_t* sobol_v;
   const double* logtab;  // device-global log table (read through L1)
+  const Real* lsplit;    // device: factor / mu / sigma in the split kernel's order (dim > 8)
   uint64_t first_index, path_offset, path_count, num_chunks, chunk_base;
   int mode, num_payoffs;
   PayoffK pay[TQF_MAX_PAYOFFS];
@@ -238,6 +239,407 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// dim > 8: one path is carried by kMvParts = 4 threads (one per warp of the
+// CTA), each owning the 16 interleaved rows i = 4 r + part of the state and of
+// the Cholesky factor.  The one-thread-per-path kernel above needs ~190
+// registers for 64 assets (2 warps per scheduler, issue slots half empty); here
+// a thread holds 16 prices + 16 accumulators, 8-10 CTAs fit on an SM and the
+// FFMA stream of one warp covers the latencies of the others.
+//   * lanes = 32 consecutive paths / Sobol indices (5 low index bits per lane);
+//   * per step every thread draws 16 of the 64 normals (contiguous dimensions
+//     16 part .. 16 part + 15) into shared memory, grouped by 4 so that the
+//     mat-vec reads them back with 16-byte loads;
+//   * the normals are double-buffered over steps: ONE barrier per step;
+//   * row i needs z_0..z_i: the interleaved row assignment balances the
+//     triangular work (496..544 FMAs per thread).
+constexpr int kMvParts = 4, kMvRows = 16, kMvLanes = 32, kMvDim = 64;
+constexpr int kMvTileDims = 256;   // Sobol dimensions staged at once (4 steps of 64)
+constexpr int kMvLowBits = 5;
+
+// Per part: 544 factor entries in the order mv_rows consumes them, then
+// mu[16], sigma[16] of its rows.  The sm_100a ALU takes no constant-bank
+// operand: coefficients fetched one LDCU each from the 8 KB parameter block miss
+// the small constant cache (measured 80 cycles per LDCU) -- broadcast LDS.128
+// from shared memory delivers four at a time.
+constexpr int kMvSplitL = 544;                       // sum_r (4 r + 4)
+constexpr int kMvSplitStride = kMvSplitL + 2 * kMvRows;
+
+// 16-byte / 4-byte shared-memory accesses by shared-window address (no generic
+// address conversion in the loops).
+template <typename Real>
+__device__ __forceinline__ void lds16(uint32_t addr, Real* dst) {
+  uint32_t a, b, c, d;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+  if (sizeof(Real) == 4) {
+    dst[0] = static_cast<Real>(__uint_as_float(a));
+    dst[1] = static_cast<Real>(__uint_as_float(b));
+    dst[2] = static_cast<Real>(__uint_as_float(c));
+    dst[3] = static_cast<Real>(__uint_as_float(d));
+  } else {
+    dst[0] = static_cast<Real>(__hiloint2double(static_cast<int>(b), static_cast<int>(a)));
+    dst[1] = static_cast<Real>(__hiloint2double(static_cast<int>(d), static_cast<int>(c)));
+  }
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 q;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+  return q;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_real(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_real(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" :: "r"(addr), "d"(v) : "memory");
+}
+
+// Rows i = 4 r + part of  x' = step(x, L z)  for the NP paths of a thread.
+// Every part runs the SAME code (one copy in the instruction cache for all
+// warps): row r is given the 4 r + 4 coefficients j = 0 .. 4 r + 3, those with
+// j > i stored as zeros (4.6 % more FMAs than the exact triangle).  A
+// coefficient costs one quarter of a broadcast LDS.128 and feeds NP FMAs: the
+// shared-memory return path (512 B per warp-wide 16-byte load) is what bounds
+// this kernel, so carrying two paths per thread halves its cost per path.
+// `lp_addr`: this part's table, `z_addr`: this lane's normals of path 0 (path
+// q is kMvLanes * 4 values further), both shared-window addresses.
+template <typename Real, int NP>
+__device__ __forceinline__ void mv_rows(uint32_t lp_addr, int exact_log, uint32_t z_addr, Real dt,
+                                        Real sq, Real (&x)[NP][kMvRows]) {
+  constexpr int PER16 = 16 / sizeof(Real);   // values per 16-byte load
+  Real acc[NP][kMvRows];
+#pragma unroll
+  for (int q = 0; q < NP; ++q)
+#pragma unroll
+    for (int r = 0; r < kMvRows; ++r) acc[q][r] = 0;
+  Real cq[PER16];
+  int k = 0;   // compile-time after unrolling
+#pragma unroll
+  for (int jg = 0; jg < kMvDim / 4; ++jg) {
+    Real zq[NP][4];
+#pragma unroll
+    for (int q = 0; q < NP; ++q)
+#pragma unroll
+      for (int v = 0; v < 4 / PER16; ++v)
+        lds16<Real>(z_addr + ((jg * NP + q) * kMvLanes * 4 + v * PER16) * sizeof(Real),
+                    zq[q] + v * PER16);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int r = jg; r < kMvRows; ++r) {       // j = 4 jg + u <= 4 r + 3
+        if ((k % PER16) == 0) lds16<Real>(lp_addr + k * sizeof(Real), cq);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc[q][r] = fma(cq[k % PER16], zq[q][u], acc[q][r]);
+        ++k;
+      }
+    }
+  }
+  Real mu[kMvRows], sg[kMvRows];
+#pragma unroll
+  for (int r = 0; r < kMvRows; r += PER16) {
+    lds16<Real>(lp_addr + (kMvSplitL + r) * sizeof(Real), mu + r);
+    lds16<Real>(lp_addr + (kMvSplitL + kMvRows + r) * sizeof(Real), sg + r);
+  }
+#pragma unroll
+  for (int q = 0; q < NP; ++q)
+#pragma unroll
+    for (int r = 0; r < kMvRows; ++r) {
+      if (exact_log) {
+        // exact log-normal increment (multivariate_geometric_brownian_motion.py:262-266);
+        // mu holds means - vols^2 / 2
+        x[q][r] = x[q][r] + (mu[r] * dt + (sq * sg[r]) * acc[q][r]);
+      } else {
+        const Real dt_inc = dt * (mu[r] * x[q][r]);
+        const Real dw_inc = (sg[r] * x[q][r]) * (acc[q][r] * sq);
+        x[q][r] = (x[q][r] + dt_inc) + dw_inc;
+      }
+    }
+}
+
+// Host: factor (row-major [dim][dim], lower triangle), mu, sigma -> the split
+// kernel's consumption order, [kMvParts][kMvSplitStride] values of `Real`.
+template <typename Real>
+static void build_split(const double* chol, const double* mu, const double* sigma, int dim,
+                        std::vector<Real>* out) {
+  out->assign(static_cast<size_t>(kMvParts) * kMvSplitStride, Real(0));
+  for (int part = 0; part < kMvParts; ++part) {
+    Real* lp = out->data() + static_cast<size_t>(part) * kMvSplitStride;
+    int k = 0;
+    for (int j = 0; j < kMvDim; ++j)
+      for (int r = j / 4; r < kMvRows; ++r) {       // the order mv_rows reads them
+        const int i = 4 * r + part;
+        lp[k++] = (j <= i && i < dim && j < dim)
+                      ? static_cast<Real>(chol[static_cast<size_t>(i) * dim + j]) : Real(0);
+      }
+    for (int r = 0; r < kMvRows; ++r) {
+      const int i = 4 * r + part;
+      lp[kMvSplitL + r] = i < dim ? static_cast<Real>(mu[i]) : Real(0);
+      lp[kMvSplitL + kMvRows + r] = i < dim ? static_cast<Real>(sigma[i]) : Real(0);
+    }
+  }
+}
+
+int mvgbm_upload_split(const double* chol, const double* mu, const double* sigma, int dim,
+                       int dtype, void** out_dev) {
+  void* dev = nullptr;
+  cudaError_t e;
+  if (dtype == TQF_F64) {
+    std::vector<double> host;
+    build_split<double>(chol, mu, sigma, dim, &host);
+    TQF_CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(double)));
+    e = cudaMemcpy(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice);
+  } else {
+    std::vector<float> host;
+    build_split<float>(chol, mu, sigma, dim, &host);
+    TQF_CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(float)));
+    e = cudaMemcpy(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    cudaFree(dev);
+    return cuda_fail(e, "mvgbm_upload_split");
+  }
+  *out_dev = dev;
+  return TQF_OK;
+}
+
+template <typename Real>
+struct MvSplitCfg {
+  static constexpr int NP = sizeof(Real) == 4 ? 2 : 1;       // paths per thread
+  static constexpr int kPaths = kMvLanes * NP;                // paths per CTA chunk
+  static constexpr int kIdxBits = kMvLowBits + (NP == 2 ? 1 : 0);
+  static constexpr int kMinBlocks = sizeof(Real) == 4 ? 4 : 3;
+  static constexpr size_t kDynSmem =
+      (2 * kMvDim * kPaths + kMvParts * kMvSplitStride) * sizeof(Real);
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(kMvParts * kMvLanes, MvSplitCfg<Real>::kMinBlocks)
+mvgbm_split_kernel(const __grid_constant__ MvParams<Real, kMvDim> P) {
+  using Cfg = MvSplitCfg<Real>;
+  constexpr int NP = Cfg::NP, kPaths = Cfg::kPaths;
+  __shared__ uint32_t s_high[kMvTileDims];
+  __shared__ uint4 s_low[kMvTileDims * 2];
+  __shared__ double s_acc[TQF_MAX_PAYOFFS * 3];
+  __shared__ Real s_red[kMvParts][kPaths];
+  // dynamic: normals [2][16 groups][NP][32 lanes][4] | factor / mu / sigma
+  extern __shared__ __align__(16) unsigned char s_mv_dyn[];
+  Real* s_zall = reinterpret_cast<Real*>(s_mv_dyn);
+  Real* s_split = s_zall + 2 * kMvDim * kPaths;
+  const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
+  for (int i = tid; i < kMvParts * kMvSplitStride; i += blockDim.x) s_split[i] = P.lsplit[i];
+  const fm::ConstTab tab(P.logtab);
+  for (int i = tid; i < TQF_MAX_PAYOFFS * 3; i += blockDim.x) s_acc[i] = 0.0;
+  __syncthreads();
+
+  // Sobol index of path q of this thread: chunk * kPaths + q * 32 + lane -> the
+  // 5 low bits come from the lane, bit 5 (NP == 2) is q, the rest from the chunk
+  uint32_t lowmask[kMvLowBits];
+#pragma unroll
+  for (int b = 0; b < kMvLowBits; ++b) {
+    lowmask[b] = 0u - ((static_cast<uint32_t>(lane) >> b) & 1u);
+    asm volatile("" : "+r"(lowmask[b]));
+  }
+  const int dim = P.dim;
+  const int tile_steps = dim <= kMvTileDims ? kMvTileDims / dim : 1;
+  const uint64_t stream_stride = static_cast<uint64_t>(P.num_steps_total) * dim;
+  const uint64_t chunk_base = P.first_index & ~static_cast<uint64_t>(kPaths - 1);
+  const uint64_t num_chunks = (P.first_index + P.path_count - chunk_base + kPaths - 1) / kPaths;
+  const int j_begin = part * kMvRows;                                   // draws of this thread
+  const int j_count = max(0, min(kMvRows, dim - j_begin));
+  // shared-window addresses used by the step loop
+  const uint32_t zall_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_zall));
+  const uint32_t lp_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_split)) +
+                           part * kMvSplitStride * sizeof(Real);
+  const uint32_t low_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_low));
+  const uint32_t high_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_high));
+  // normal j of path q of this lane sits at (((j / 4) * NP + q) * 32 + lane) * 4 + j % 4;
+  // this thread writes j = 16 part + jj: groups 4 part + jj / 4
+  const uint32_t zlane_off = lane * 4 * sizeof(Real);
+  const uint32_t zwrite_off = (part * 4 * NP * kMvLanes * 4) * sizeof(Real) + zlane_off;
+  constexpr uint32_t kZq = kMvLanes * 4 * sizeof(Real);        // bytes between paths q, q + 1
+  constexpr uint32_t kZg = NP * kZq;                            // bytes between groups
+
+  for (uint64_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
+    bool valid[NP];
+    uint64_t local[NP], elem_base[NP];
+    Real x[NP][kMvRows];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      const uint64_t index = chunk_base + chunk * kPaths + q * kMvLanes + lane;
+      valid[q] = index >= P.first_index && index < P.first_index + P.path_count;
+      local[q] = index - P.first_index;
+      elem_base[q] = valid[q] ? (P.path_offset + local[q]) * stream_stride : 0;
+#pragma unroll
+      for (int r = 0; r < kMvRows; ++r) x[q][r] = P.x0[4 * r + part];
+    }
+
+    // payoffs / stores of the state after `step_index` steps
+    auto record = [&](int step_index, int slot) {
+      if (P.mode != MODE_PRICE) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+          if (valid[q]) {
+#pragma unroll
+            for (int r = 0; r < kMvRows; ++r) {
+              const int i = 4 * r + part;
+              if (i < dim)
+                P.out[static_cast<int64_t>(local[q]) * P.stride_path + slot * P.stride_time +
+                      i * P.stride_dim] = P.store_exp ? static_cast<Real>(exp(x[q][r])) : x[q][r];
+            }
+          }
+        return;
+      }
+      for (int pq = 0; pq < P.num_payoffs; ++pq) {
+        const PayoffK& d = P.pay[pq];
+        if (d.step != step_index) continue;
+        // basket mean (component < 0) or one component, assembled through smem
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          Real part_val = 0;
+#pragma unroll
+          for (int r = 0; r < kMvRows; ++r) {
+            const int i = 4 * r + part;
+            const bool take = d.component < 0 ? i < dim : i == d.component;
+            part_val += selp_real(x[q][r], Real(0), take ? 1 : 0);
+          }
+          s_red[part][q * kMvLanes + lane] = part_val;
+        }
+        __syncthreads();
+        if (part == 0) {
+          double sum = 0.0, sq = 0.0, bad = 0.0;
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            const int c = q * kMvLanes + lane;
+            Real m = (s_red[0][c] + s_red[1][c]) + (s_red[2][c] + s_red[3][c]);
+            if (d.component < 0) m = m / static_cast<Real>(dim);
+            if (valid[q]) {
+              const double v = eval_payoff(d, static_cast<double>(m), 0.0, 0.0);
+              if (isfinite(v)) {
+                sum += v;
+                sq += v * v;
+              } else {
+                bad += 1.0;
+              }
+            }
+          }
+          sum = warp_sum(sum);
+          sq = warp_sum(sq);
+          bad = warp_sum(bad);
+          if (lane == 0) {
+            s_acc[pq * 3 + 0] += sum;
+            s_acc[pq * 3 + 1] += sq;
+            s_acc[pq * 3 + 2] += bad;
+          }
+        }
+      }
+    };
+    if (P.record_slot[0] >= 0) record(0, P.record_slot[0]);
+
+    for (int s0 = 0; s0 < P.num_steps; s0 += tile_steps) {
+      const int s1 = min(P.num_steps, s0 + tile_steps);
+      if (P.rngk == RNGK_SOBOL) {
+        __syncthreads();
+        const uint32_t high_bits =
+            static_cast<uint32_t>((chunk_base + chunk * kPaths) >> Cfg::kIdxBits);
+        for (int dd = tid; dd < (s1 - s0) * dim; dd += blockDim.x) {
+          // all 32 direction words at once (8 independent 16-byte loads), then the
+          // XOR of the words selected by the chunk's high index bits
+          const uint4* v4 = reinterpret_cast<const uint4*>(
+              P.sobol_v + (static_cast<size_t>(s0) * dim + dd) * 32);
+          uint4 w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) w[q] = __ldg(v4 + q);
+          s_low[2 * dd] = w[0];
+          s_low[2 * dd + 1] = w[1];
+          const uint32_t* wv = reinterpret_cast<const uint32_t*>(w);
+          uint32_t h = 0;
+#pragma unroll
+          for (int b = Cfg::kIdxBits; b < 32; ++b)
+            h ^= wv[b] & (0u - ((high_bits >> (b - Cfg::kIdxBits)) & 1u));
+          s_high[dd] = h;
+        }
+        __syncthreads();
+      }
+      for (int s = s0; s < s1; ++s) {
+        const uint32_t zbuf_addr = zall_addr + (s & 1) * (kMvDim * kPaths) * sizeof(Real);
+        const uint32_t zw = zbuf_addr + zwrite_off;
+        // ---- this thread's 16 x NP normals of step s
+        if (P.rngk == RNGK_SOBOL) {
+          const uint32_t la = low_addr + ((s - s0) * dim + j_begin) * 32;
+          const uint32_t ha = high_addr + ((s - s0) * dim + j_begin) * 4;
+#pragma unroll 4
+          for (int jj = 0; jj < kMvRows; ++jj) {
+            if (jj < j_count) {
+              const uint4 l0 = lds_u4(la + jj * 32);
+              const uint4 l1 = lds_u4(la + jj * 32 + 16);
+              uint32_t xb[NP];
+              xb[0] = lds_u32(ha + jj * 4);
+              xb[0] ^= l0.x & lowmask[0];
+              xb[0] ^= l0.y & lowmask[1];
+              xb[0] ^= l0.z & lowmask[2];
+              xb[0] ^= l0.w & lowmask[3];
+              xb[0] ^= l1.x & lowmask[4];
+              if (NP == 2) xb[NP - 1] = xb[0] ^ l1.y;      // index bit 5 set
+              Real zo[NP];
+              sobol_normals<NP>(tab, xb, zo);
+#pragma unroll
+              for (int q = 0; q < NP; ++q)
+                sts_real(zw + (jj >> 2) * kZg + q * kZq + (jj & 3) * sizeof(Real), zo[q]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < NP; ++q)
+                sts_real(zw + (jj >> 2) * kZg + q * kZq + (jj & 3) * sizeof(Real), Real(0));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            PhiloxStreamV<Real, 1> stream;
+            const uint64_t fe[1] = {elem_base[q] + static_cast<uint64_t>(s) * dim + j_begin};
+            if (j_count > 0) stream.init(P.key, P.ctr, tab, fe);
+            for (int jj = 0; jj < kMvRows; ++jj) {
+              Real zo[1] = {0};
+              if (jj < j_count) stream.next(P.key, P.ctr, tab, zo);
+              sts_real(zw + (jj >> 2) * kZg + q * kZq + (jj & 3) * sizeof(Real), zo[0]);
+            }
+          }
+        }
+        __syncthreads();   // the only barrier of the step (normals are double-buffered)
+        const Real dt = P.coef[2 * s], sq = P.coef[2 * s + 1];
+        mv_rows<Real, NP>(lp_addr, P.exact_log, zbuf_addr + zlane_off, dt, sq, x);
+        const int flag = P.record_slot[s + 1];
+        if (flag >= 0) record(s + 1, flag);
+      }
+    }
+  }
+  if (P.mode == MODE_PRICE) {
+    __syncthreads();
+    for (int i = tid; i < TQF_MAX_PAYOFFS * 3; i += blockDim.x) {
+      const int q = i / 3, k = i - q * 3;
+      P.partials[(static_cast<size_t>(blockIdx.x) * TQF_MAX_PAYOFFS + q) * 4 + k] = s_acc[i];
+    }
+  }
+}
+
+template <typename Real, int DMAX>
+static void launch_split(const MvParams<Real, DMAX>& P, int grid, cudaStream_t stream) {
+  if constexpr (DMAX == kMvDim) {
+    const size_t smem = MvSplitCfg<Real>::kDynSmem;
+    if (smem > 32 * 1024)
+      cudaFuncSetAttribute(mvgbm_split_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(smem));
+    mvgbm_split_kernel<Real><<<grid, kMvParts * kMvLanes, smem, stream>>>(P);
+  }
+}
+
 template <typename Real, int DMAX>
 static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
   static MvParams<Real, DMAX> P;   // large (up to 19 KB): keep off the stack
@@ -253,6 +655,7 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
   P.ctr = a.ctr;
   P.sobol_v = a.sobol_v;
   P.logtab = a.logtab;
+  P.lsplit = static_cast<const Real*>(a.lsplit_dev);
   P.first_index = a.first_index;
   P.path_offset = a.path_offset;
   P.path_count = a.path_count;
@@ -278,17 +681,31 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
       P.L[i * (i + 1) / 2 + j] =
           (in && j < a.dim) ? static_cast<Real>(a.chol[static_cast<size_t>(i) * a.dim + j]) : Real(0);
   }
+  if (DMAX == kMvDim) {
+    constexpr uint64_t kPaths = MvSplitCfg<Real>::kPaths;
+    const uint64_t base32 = a.first_index & ~(kPaths - 1);
+    const uint64_t chunks32 = (a.first_index + a.path_count - base32 + kPaths - 1) / kPaths;
+    int grid = static_cast<int>(chunks32 < static_cast<uint64_t>(a.max_grid)
+                                    ? chunks32 : static_cast<uint64_t>(a.max_grid));
+    if (grid < 1) grid = 1;
+    *grid_out = grid;
+    launch_split(P, grid, stream);
+    TQF_CUDA_OK(cudaGetLastError());
+    return TQF_OK;
+  }
   int grid = static_cast<int>(P.num_chunks < static_cast<uint64_t>(a.max_grid)
                                   ? P.num_chunks
                                   : static_cast<uint64_t>(a.max_grid));
   if (grid < 1) grid = 1;
   *grid_out = grid;
   const size_t smem = static_cast<size_t>(DMAX) * kBlock * sizeof(Real);
-  if (smem > 48 * 1024)
-    TQF_CUDA_OK(cudaFuncSetAttribute(mvgbm_kernel<Real, DMAX>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-  mvgbm_kernel<Real, DMAX><<<grid, kBlock, smem, stream>>>(P);
+  if constexpr (DMAX != kMvDim) {
+    if (smem > 48 * 1024)
+      TQF_CUDA_OK(cudaFuncSetAttribute(mvgbm_kernel<Real, DMAX>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    mvgbm_kernel<Real, DMAX><<<grid, kBlock, smem, stream>>>(P);
+  }
   TQF_CUDA_OK(cudaGetLastError());
   return TQF_OK;
 }

@@ -79,6 +79,7 @@ struct tqf_plan {
   void* coef_dev;           // Real [num_steps][ncoef]
   uint32_t* sobol_dev;      // [S_total*nf][32]
   const double* logtab_dev; // shared per-device log table (not owned)
+  void* lsplit_dev;         // MVGBM dim > 8: factor in the split kernel's order
   double* partials_dev;     // [max_grid][TQF_MAX_PAYOFFS][4]
   int* record_dev;          // [num_steps+1]
   SwaptionK* swaptions_dev; // [TQF_MAX_PAYOFFS]
@@ -257,6 +258,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.ctr = P.ctr;
     a.sobol_v = plan->sobol_dev;
     a.logtab = plan->logtab_dev;
+    a.lsplit_dev = plan->lsplit_dev;
     a.first_index = P.first_index;
     a.path_offset = path_offset;
     a.path_count = path_count;
@@ -323,6 +325,7 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.ctr = P.ctr;
     a.sobol_v = plan->sobol_dev;
     a.logtab = plan->logtab_dev;
+    a.lsplit_dev = plan->lsplit_dev;
     a.first_index = P.first_index;
     a.path_offset = path_offset;
     a.path_count = path_count;
@@ -429,6 +432,9 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
   if (rc == TQF_OK && rng->type == TQF_RNG_SOBOL)
     rc = upload_sobol_table(rng->direction_numbers, static_cast<int>(dims), &plan->sobol_dev, 0);
   if (rc == TQF_OK) rc = device_logtab(&plan->logtab_dev);
+  if (rc == TQF_OK && model->kind == TQF_MODEL_MVGBM && info.dim > 8)
+    rc = mvgbm_upload_split(plan->chol, plan->mu, plan->sigma, info.dim, model->dtype,
+                            &plan->lsplit_dev);
   if (rc == TQF_OK) {
     e = cudaMalloc(&plan->partials_dev,
                    static_cast<size_t>(plan->max_grid) * TQF_MAX_PAYOFFS * 4 * sizeof(double));
@@ -456,6 +462,7 @@ int tqf_plan_destroy(tqf_plan* plan) {
   if (!plan) return TQF_OK;
   cudaFree(plan->coef_dev);
   cudaFree(plan->sobol_dev);
+  cudaFree(plan->lsplit_dev);
   cudaFree(plan->partials_dev);
   cudaFree(plan->record_dev);
   cudaFree(plan->swaptions_dev);

@@ -842,6 +842,7 @@ struct MvLaunch {
   PhiloxCtr ctr;
   const uint32_t* sobol_v;
   const double* logtab;
+  const void* lsplit_dev;    // mvgbm_upload_split() table (dim > 8)
   uint64_t first_index, path_offset, path_count;
   int num_payoffs;
   const PayoffK* pay;
@@ -854,5 +855,8 @@ struct MvLaunch {
 };
 
 int launch_mvgbm(const MvLaunch& a, cudaStream_t stream, int* grid_out);
+// Uploads the factor / mu / sigma in the order the split kernel (dim > 8) reads them.
+int mvgbm_upload_split(const double* chol, const double* mu, const double* sigma, int dim,
+                       int dtype, void** out_dev);
 
 }  // namespace tqf
