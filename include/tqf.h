@@ -262,6 +262,22 @@ typedef struct tqf_lsm_desc {
   void* w_dev;
   double* partials_dev;
   uint64_t partials_doubles;
+  /* Optional: tabulated exercise values and per-path discounting (Bermudan
+   * swaptions on short-rate paths, hull_white/swaption.py:608-724, where the
+   * reference passes a payoff closure over precomputed swap values and rank-3
+   * discount factors).  With `exercise_time_indices` (host, [num_exercise_times],
+   * the time index of every exercise date in order) set:
+   *   exercise_values_dev: `dtype` [num_exercise_times][B][num_paths], the value
+   *     of exercising payoff b on path n at date t; replaces relu(strike - mean x);
+   *   path_ratio_dev: `dtype` [num_exercise_times][num_paths], entry [e][n] =
+   *     df[e+1]/df[e] of path n (lsm.py:304-325); replaces the ratio_* arguments
+   *     of tqf_lsm_step, and entry [0] weights tqf_lsm_value_sum.
+   * Either pointer may be NULL.  K <= 6 only. */
+  const int32_t* exercise_time_indices;
+  int32_t num_exercise_times;
+  int32_t reserved;
+  const void* exercise_values_dev;
+  const void* path_ratio_dev;
 } tqf_lsm_desc;
 
 typedef struct tqf_lsm tqf_lsm;

@@ -388,3 +388,71 @@ class VectorHullWhiteModel:
       return out[:, None, :]
     slots = [np.zeros_like(x) if s is None else s for s in slots]
     return np.transpose(np.stack(slots, 0), [1, 0, 2])
+
+
+def _unique_in_order(a):
+  """`tf.unique`: distinct values in order of first appearance + inverse index."""
+  _, first, inv = np.unique(a, return_index=True, return_inverse=True)
+  order = np.argsort(first, kind='stable')
+  rank = np.empty_like(order)
+  rank[order] = np.arange(order.shape[0])
+  return a[np.sort(first)], rank[inv]
+
+
+def bermudan_swaption_price_mc(*, exercise_times, fixed_leg_payment_times,
+                               fixed_leg_daycount_fractions, fixed_leg_coupon,
+                               reference_rate_fn, mean_reversion, volatility,
+                               notional=1.0, num_samples=100, random_type=None,
+                               seed=None, skip=0, time_step=None, dtype=np.float64):
+  """`bermudan_swaption_price(use_finite_difference=False)`
+  (`hull_white/swaption.py:608-724`): LSM (quadratic basis on the short rate,
+  one discount curve per path) on exact Hull-White paths.  `exercise_times`:
+  batch + [E]; leg arrays: batch + [E, m]."""
+  from oracle import grid as grid_lib
+  from oracle import lsm as lsm_lib
+  dtype = np.dtype(dtype)
+  ex = np.asarray(exercise_times, dtype=dtype)
+  pay_t = np.asarray(fixed_leg_payment_times, dtype=dtype)
+  dcf = np.broadcast_to(np.asarray(fixed_leg_daycount_fractions, dtype=dtype), pay_t.shape)
+  coupon = np.broadcast_to(np.asarray(fixed_leg_coupon, dtype=dtype), pay_t.shape)
+  batch_shape = ex.shape[:-1]
+  n_ex, m = ex.shape[-1], pay_t.shape[-1]
+  nb = int(np.prod(batch_shape)) if batch_shape else 1
+  ex_flat = ex.reshape(nb, n_ex)
+  pay_flat = pay_t.reshape(nb, n_ex, m)
+  model = HullWhiteModel1F(mean_reversion, volatility, reference_rate_fn, dtype)
+  uniq, ex_index = _unique_in_order(ex_flat.reshape(-1))
+  ex_index = ex_index.reshape(nb, n_ex)
+  longest = uniq[-1]
+  sim_times = np.unique(np.concatenate(
+      [uniq, grid_lib.tf_range(time_step, longest, time_step, dtype)]))
+  ex_b = np.repeat(ex_flat[..., None], m, axis=-1)
+  tau = pay_flat - ex_b
+  curve_times = np.unique(tau.reshape(-1))
+  p_t_tau, r_t = model.sample_discount_curve_paths(
+      sim_times, curve_times, num_samples, random_type, seed, skip)
+  dt = np.concatenate([[0.0], sim_times[1:] - sim_times[:-1]]).astype(dtype)
+  df = np.cumprod(np.exp(-r_t[:, :, 0] * dt[None, :]), axis=1)            # [N, k]
+  sim_idx_e = np.searchsorted(sim_times, ex_b.reshape(-1), side='left')
+  curve_idx = np.searchsorted(curve_times, tau.reshape(-1), side='left')
+  bond = p_t_tau[:, curve_idx, sim_idx_e, 0].reshape((num_samples, nb, n_ex, m))
+  fixed_pv = (coupon.reshape(nb, n_ex, m) * dcf.reshape(nb, n_ex, m) * bond).sum(axis=-1)
+  payoff_swap = (1.0 - bond[..., -1]) - fixed_pv                         # [N, nb, E], payer
+  sim_idx_u = np.searchsorted(sim_times, uniq, side='left')
+  short_rate = r_t[:, sim_idx_u, :]                                      # [N, U, 1]
+  u_count = uniq.shape[0]
+  is_ex = np.zeros((nb, u_count), dtype=bool)
+  tab = np.zeros((u_count, num_samples, nb), dtype=dtype)
+  for b in range(nb):
+    for e in range(n_ex):
+      is_ex[b, ex_index[b, e]] = True
+      tab[ex_index[b, e], :, b] = payoff_swap[:, b, e]
+
+  def payoff_fn(rt, time_index):
+    del rt
+    return np.where(is_ex[:, time_index][None, :], np.maximum(tab[time_index], 0.0), 0.0)
+  value = lsm_lib.least_square_mc(
+      short_rate, np.arange(u_count), payoff_fn, lsm_lib.make_polynomial_basis(2),
+      discount_factors=df[:, None, sim_idx_u], dtype=dtype)
+  return (np.broadcast_to(np.asarray(notional, dtype), batch_shape).reshape(-1) *
+          value).reshape(batch_shape)

@@ -437,3 +437,77 @@ def test_vector_hw_dim1_and_errors():
                                                   dtype=np.float64)
   with pytest.raises(ValueError, match='rank 1'):
     m2.sample_paths([[0.5, 1.0]], num_samples=10)
+
+
+# ------------------------------------------------------- Bermudan swaptions ----
+def _bermudan_legs(exercise):
+  start = np.array([np.clip(np.arange(8) * 0.5 + e, None, 5.0) for e in exercise])
+  end = np.clip(start + 0.5, 0.0, 5.0)
+  return dict(exercise_times=np.array(exercise), fixed_leg_payment_times=end,
+              fixed_leg_daycount_fractions=end - start,
+              fixed_leg_coupon=0.011 * np.ones_like(end))
+
+
+EX1 = [1.0, 1.5, 2.0, 2.5, 3.0, 3.5, 4.0, 4.5]
+EX2 = [2.0, 2.5, 3.0, 3.5, 4.0, 4.5, 5.0, 5.0]
+
+
+def _product_legs(legs):
+  return dict(floating_leg_start_times=legs['fixed_leg_payment_times'] -
+              legs['fixed_leg_daycount_fractions'],
+              floating_leg_end_times=legs['fixed_leg_payment_times'],
+              floating_leg_daycount_fractions=legs['fixed_leg_daycount_fractions'], **legs)
+
+
+def test_bermudan_swaption_reference_kat_and_oracle():
+  # bermudan_swaption_test.py:86-131: 1.8892 +- 1e-2 (10k paths, seed [0, 0])
+  import tff_b200 as tff
+  legs = _bermudan_legs(EX1)
+  kw = dict(reference_rate_fn=_flat, notional=100., mean_reversion=0.03, volatility=0.01,
+            num_samples=10000, time_step=0.1, seed=[0, 0], dtype=np.float64)
+  got = tff.models.hull_white.bermudan_swaption_price(
+      random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, **_product_legs(legs), **kw)
+  assert got.shape == () and got.dtype == np.float64
+  np.testing.assert_allclose(got, 1.8892, rtol=1e-2, atol=1e-2)
+  want = ohw.bermudan_swaption_price_mc(
+      random_type=odraws.RandomType.STATELESS_ANTITHETIC, **legs, **kw)
+  np.testing.assert_allclose(got, want, rtol=1e-9)
+
+
+@pytest.mark.parametrize('rng', [('STATELESS_ANTITHETIC', [0, 0]), ('SOBOL', None)],
+                         ids=lambda r: r[0])
+def test_bermudan_swaption_batch_matches_oracle(rng):
+  # bermudan_swaption_test.py:133-183: [5nc1, 5nc2] = [1.8892, 1.6633] +- 5e-3;
+  # piecewise-constant volatility and a sloped curve for the parity leg
+  import tff_b200 as tff
+  from tff_b200.math import piecewise
+  rt, seed = rng
+  l1, l2 = _bermudan_legs(EX1), _bermudan_legs(EX2)
+  legs = {k: np.stack([l1[k], l2[k]]) for k in l1}
+  kw = dict(notional=100., mean_reversion=0.03, num_samples=50000, time_step=0.1,
+            seed=seed, dtype=np.float64)
+  got = tff.models.hull_white.bermudan_swaption_price(
+      reference_rate_fn=_flat, volatility=0.01,
+      random_type=tff.math.random.RandomType[rt], **_product_legs(legs), **kw)
+  assert got.shape == (2,)
+  np.testing.assert_allclose(got, [1.8892, 1.6633], rtol=5e-3, atol=5e-3)
+  vol = piecewise.PiecewiseConstantFunc([2.0], [0.01, 0.012], dtype=np.float64)
+  ovol = omodels.PiecewiseConstantFunc([2.0], [0.01, 0.012], dtype=np.float64)
+  kw['num_samples'] = 20000
+  got = tff.models.hull_white.bermudan_swaption_price(
+      reference_rate_fn=_curve, volatility=vol,
+      random_type=tff.math.random.RandomType[rt], **_product_legs(legs), **kw)
+  want = ohw.bermudan_swaption_price_mc(
+      reference_rate_fn=_curve, volatility=ovol, random_type=odraws.RandomType[rt],
+      **legs, **kw)
+  np.testing.assert_allclose(got, want, rtol=1e-9)
+
+
+def test_bermudan_swaption_errors():
+  import tff_b200 as tff
+  legs = _product_legs(_bermudan_legs(EX1))
+  kw = dict(reference_rate_fn=_flat, mean_reversion=0.03, volatility=0.01, dtype=np.float64)
+  with pytest.raises(ValueError, match='time_step'):
+    tff.models.hull_white.bermudan_swaption_price(**legs, **kw)
+  with pytest.raises(NotImplementedError):
+    tff.models.hull_white.bermudan_swaption_price(use_finite_difference=True, **legs, **kw)

@@ -106,3 +106,28 @@ def test_two_dimensional_basket_matches_oracle():
   want = olsm.least_square_mc(paths, np.arange(T), olsm.make_basket_put_payoff([1.0, 1.1]),
                               olsm.make_polynomial_basis(2), df, dtype=np.float64)
   np.testing.assert_allclose(got, want, rtol=1e-9)
+
+
+def test_lsm_tabulated_payoff_and_per_path_discounting():
+  # the shape of the Bermudan swaption problem (hull_white/swaption.py:608-724):
+  # exercise values precomputed per (date, path, payoff), one discount curve per
+  # path, quadratic basis on a 1-d state
+  import torch
+  import tff_b200 as tff
+  from oracle import lsm as olsm
+  rs = np.random.RandomState(11)
+  n, t, b = 20000, 6, 3
+  state = np.cumsum(0.01 * rs.standard_normal((n, t, 1)), axis=1) + 0.02       # short rate
+  df = np.exp(-np.cumsum(np.abs(state[:, :, 0]) * 0.5, axis=1))[:, None, :]     # [N, 1, T]
+  values = np.maximum(rs.standard_normal((t, n, b)) * 0.01 +
+                      (state[:, :, 0].T[..., None] - 0.02) * np.array([1.0, -1.0, 0.5]), 0.0)
+  values[2, :, 1] = 0.0                       # a date on which payoff 1 cannot be exercised
+  lsm = tff.models.longstaff_schwartz
+  got = lsm.least_square_mc(
+      torch.as_tensor(state).cuda(), np.arange(t), lsm.make_tabulated_payoff(torch.as_tensor(values).cuda()),
+      lsm.make_polynomial_basis(2), discount_factors=torch.as_tensor(df).cuda(), dtype=np.float64)
+  want = olsm.least_square_mc(
+      state, np.arange(t), lambda x, ti: values[ti], olsm.make_polynomial_basis(2),
+      discount_factors=df, dtype=np.float64)
+  assert got.shape == (b,)
+  np.testing.assert_allclose(got, want, rtol=1e-10)

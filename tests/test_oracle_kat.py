@@ -289,6 +289,36 @@ def test_hw_cap_mc_kat():
   np.testing.assert_allclose(price, 0.4072088281493774, rtol=1e-3, atol=1e-3)
 
 
+
+def _bermudan_legs(exercise):
+  """`bermudan_swaption_test.py:31-80`: semi-annual 5y swap, payments clipped at 5y."""
+  start = np.array([np.clip(np.arange(8) * 0.5 + e, None, 5.0) for e in exercise])
+  end = np.clip(start + 0.5, 0.0, 5.0)
+  return dict(exercise_times=np.array(exercise), fixed_leg_payment_times=end,
+              fixed_leg_daycount_fractions=end - start,
+              fixed_leg_coupon=0.011 * np.ones_like(end))
+
+
+def test_hw_bermudan_swaption_mc_kat():
+  # models/hull_white/bermudan_swaption_test.py:86-183: 5nc1 1.8892 (tol 1e-2,
+  # 10k paths) and the [5nc1, 5nc2] batch [1.8892, 1.6633] (tol 5e-3, 50k paths),
+  # STATELESS_ANTITHETIC seed [0, 0], time_step 0.1
+  from oracle import hull_white
+  ex1 = [1.0, 1.5, 2.0, 2.5, 3.0, 3.5, 4.0, 4.5]
+  ex2 = [2.0, 2.5, 3.0, 3.5, 4.0, 4.5, 5.0, 5.0]
+  kw = dict(reference_rate_fn=_flat_rate, notional=100., mean_reversion=0.03,
+            volatility=0.01, time_step=0.1,
+            random_type=draws.RandomType.STATELESS_ANTITHETIC, seed=[0, 0])
+  price = hull_white.bermudan_swaption_price_mc(num_samples=10000, **_bermudan_legs(ex1), **kw)
+  assert price.shape == ()
+  np.testing.assert_allclose(price, 1.8892, rtol=1e-2, atol=1e-2)
+  l1, l2 = _bermudan_legs(ex1), _bermudan_legs(ex2)
+  legs = {k: np.stack([l1[k], l2[k]]) for k in l1}
+  price = hull_white.bermudan_swaption_price_mc(num_samples=50000, **legs, **kw)
+  assert price.shape == (2,)
+  np.testing.assert_allclose(price, [1.8892, 1.6633], rtol=5e-3, atol=5e-3)
+
+
 # ------------------------------------------------------ Longstaff-Schwartz ----
 _LS_SAMPLES = np.expand_dims([[1.0, 1.09, 1.08, 1.34], [1.0, 1.16, 1.26, 1.54],
                               [1.0, 1.22, 1.07, 1.03], [1.0, 0.93, 0.97, 0.92],

@@ -51,6 +51,10 @@ struct LsmArgs {
   int64_t mean_stride;        // doubles between the means of consecutive payoffs
   double* partials;           // device [gridDim.x][B][NS]
   int NS;
+  // tabulated exercise values [T][B][N] / per-path ratios [T][N] (either may be null)
+  const Real* ev_tab;
+  const Real* ratio_path;
+  int slot_update, slot_acc;  // exercise-date slots of t_update / t_acc
 };
 
 template <typename Real>
@@ -138,6 +142,8 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_step_fast_kernel(const LsmArgs<
         if (A.dim == 1) {
           const Real v = static_cast<Real>(A.strikes[b]) - xu[u];
           ev = v > Real(0) ? v : Real(0);
+          if (A.ev_tab)
+            ev = A.ev_tab[(static_cast<size_t>(A.slot_update) * A.batch + b) * A.num_paths + n];
           const Real c = xu[u] - static_cast<Real>(mean_u[0]);
           Real pw = 1;
 #pragma unroll
@@ -146,7 +152,9 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_step_fast_kernel(const LsmArgs<
             pw *= c;
           }
         } else {
-          ev = lsm_payoff(A, xp, b);
+          ev = A.ev_tab
+                   ? A.ev_tab[(static_cast<size_t>(A.slot_update) * A.batch + b) * A.num_paths + n]
+                   : lsm_payoff(A, xp, b);
           lsm_basis(A, xp, mean_u, phi);
         }
         Real cont = 0;
@@ -154,13 +162,18 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_step_fast_kernel(const LsmArgs<
         for (int k = 0; k < kLsmFastK; ++k)
           if (k < K) cont += phi[k] * static_cast<Real>(beta[k]);
         cont = cont > Real(0) ? cont : Real(0);
-        wn[u] = ev > cont ? ev : ratio_u * wn[u];
+        const Real ru = A.ratio_path
+                            ? A.ratio_path[static_cast<size_t>(A.slot_update + 1) * A.num_paths + n]
+                            : ratio_u;
+        wn[u] = ev > cont ? ev : ru * wn[u];
         w[n] = wn[u];
       }
       if (A.do_acc) {
         const Real* xp = xn + A.t_acc * A.stride_time;
         Real ev;
-        if (A.dim == 1) {
+        if (A.ev_tab) {
+          ev = A.ev_tab[(static_cast<size_t>(A.slot_acc) * A.batch + b) * A.num_paths + n];
+        } else if (A.dim == 1) {
           const Real v = static_cast<Real>(A.strikes[b]) - xa[u];
           ev = v > Real(0) ? v : Real(0);
         } else {
@@ -179,7 +192,10 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_step_fast_kernel(const LsmArgs<
           } else {
             lsm_basis(A, xp, mean_a, phi);
           }
-          const double y = static_cast<double>(ratio_a * wn[u]);
+          const Real ra = A.ratio_path
+                              ? A.ratio_path[static_cast<size_t>(A.slot_acc + 1) * A.num_paths + n]
+                              : ratio_a;
+          const double y = static_cast<double>(ra * wn[u]);
           int idx = 0;
 #pragma unroll
           for (int i = 0; i < kLsmFastK; ++i) {
@@ -531,7 +547,8 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_init_kernel(const LsmArgs<Real>
   for (uint64_t n = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; n < A.num_paths;
        n += stride) {
     const Real* xp = base + static_cast<int64_t>(n) * A.stride_path + t_index * A.stride_time;
-    w[n] = lsm_payoff(A, xp, b);
+    w[n] = A.ev_tab ? A.ev_tab[(static_cast<size_t>(A.slot_update) * A.batch + b) * A.num_paths + n]
+                    : lsm_payoff(A, xp, b);
   }
 }
 
@@ -573,7 +590,7 @@ __global__ void __launch_bounds__(kLsmBlock) lsm_wsum_kernel(const LsmArgs<Real>
   for (uint64_t n = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; n < A.num_paths;
        n += stride) {
     if (A.path_offset + n >= skip_below) {
-      s += static_cast<double>(w[n]);
+      s += static_cast<double>(A.ratio_path ? A.ratio_path[n] * w[n] : w[n]);
       cnt += 1.0;
     }
   }
@@ -805,7 +822,17 @@ struct tqf_lsm {
   int* times_dev;
   int times_cap;
   bool external_w, external_partials;
+  bool tabulated;                   // exercise values and / or per-path ratios given
+  std::vector<int>* exercise_times; // slot -> time index (tabulated mode)
 };
+
+// Exercise-date slot of a time index (tabulated mode); -1 when unknown.
+static int slot_of(const tqf_lsm* h, int time_index) {
+  if (!h->exercise_times) return -1;
+  for (size_t i = 0; i < h->exercise_times->size(); ++i)
+    if ((*h->exercise_times)[i] == time_index) return static_cast<int>(i);
+  return -1;
+}
 
 template <typename Real>
 static void fill_args(const tqf_lsm* h, LsmArgs<Real>* A) {
@@ -827,6 +854,8 @@ static void fill_args(const tqf_lsm* h, LsmArgs<Real>* A) {
   A->strikes = h->strikes_dev;
   A->partials = h->partials_dev;
   A->NS = h->NS;
+  A->ev_tab = static_cast<const Real*>(d.exercise_values_dev);
+  A->ratio_path = static_cast<const Real*>(d.path_ratio_dev);
 }
 
 static int ensure_partials(tqf_lsm* h, size_t doubles) {
@@ -862,13 +891,19 @@ static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* 
   A.mean_acc = do_acc ? mean_acc : mean_update;
   A.ratio_acc = do_acc ? ratio_acc : ratio_update;
   A.mean_stride = mean_stride;
+  if (h->tabulated) {
+    A.slot_update = do_update ? slot_of(h, t_update) : 0;
+    A.slot_acc = do_acc ? slot_of(h, t_acc) : 0;
+    TQF_REQUIRE(A.slot_update >= 0 && A.slot_acc >= 0,
+                "time index is not one of exercise_time_indices");
+  }
   int rc = ensure_partials(h, static_cast<size_t>(h->grid) * B * h->NS);
   if (rc != TQF_OK) return rc;
   A.partials = h->partials_dev;
   const dim3 grid(h->grid, B);
   const size_t esz = sizeof(Real);
   const bool vec_ok =
-      h->fast && d.dim == 1 && d.stride_path == 1 && (d.num_paths % 2) == 0 &&
+      !h->tabulated && h->fast && d.dim == 1 && d.stride_path == 1 && (d.num_paths % 2) == 0 &&
       d.num_paths < (1ull << 32) && (reinterpret_cast<uintptr_t>(d.paths_dev) % (2 * esz)) == 0 &&
       (reinterpret_cast<uintptr_t>(h->w_dev) % (2 * esz)) == 0 && (d.stride_time % 2) == 0 &&
       (d.stride_batch % 2) == 0;
@@ -881,7 +916,7 @@ static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* 
       case 5: lsm_step_dim1_vec_kernel<Real, 5><<<grid, kLsmBlock, 0, s>>>(A); break;
       default: lsm_step_dim1_vec_kernel<Real, 6><<<grid, kLsmBlock, 0, s>>>(A); break;
     }
-  } else if (h->fast && d.dim == 1) {
+  } else if (h->fast && d.dim == 1 && !h->tabulated) {
     switch (K) {
       case 1: lsm_step_dim1_kernel<Real, 1><<<grid, kLsmBlock, 0, s>>>(A); break;
       case 2: lsm_step_dim1_kernel<Real, 2><<<grid, kLsmBlock, 0, s>>>(A); break;
@@ -977,6 +1012,18 @@ int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
                    cudaMemcpyHostToDevice);
   h->desc.exponents = nullptr;
   h->desc.strikes = nullptr;
+  h->tabulated = desc->exercise_values_dev != nullptr || desc->path_ratio_dev != nullptr;
+  if (h->tabulated && e == cudaSuccess) {
+    if (!h->fast || !desc->exercise_time_indices || desc->num_exercise_times < 1) {
+      tqf_lsm_destroy(h);
+      set_error("tabulated exercise values / per-path ratios need K <= 6 and "
+                "exercise_time_indices");
+      return TQF_ERR_INVALID_ARGUMENT;
+    }
+    h->exercise_times = new std::vector<int>(
+        desc->exercise_time_indices, desc->exercise_time_indices + desc->num_exercise_times);
+  }
+  h->desc.exercise_time_indices = nullptr;
   if (e != cudaSuccess) {
     tqf_lsm_destroy(h);
     return cuda_fail(e, "tqf_lsm_create");
@@ -992,6 +1039,7 @@ int tqf_lsm_destroy(tqf_lsm* h) {
   cudaFree(h->strikes_dev);
   if (!h->external_partials) cudaFree(h->partials_dev);
   cudaFree(h->times_dev);
+  delete h->exercise_times;
   delete h;
   return TQF_OK;
 }
@@ -1034,13 +1082,17 @@ int tqf_lsm_init(tqf_lsm* h, int time_index, void* stream) {
   TQF_REQUIRE(h, "null handle");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const dim3 grid(h->grid, h->desc.batch);
+  const int slot = h->tabulated ? slot_of(h, time_index) : 0;
+  TQF_REQUIRE(slot >= 0, "time index is not one of exercise_time_indices");
   if (h->desc.dtype == TQF_F64) {
     LsmArgs<double> A;
     fill_args(h, &A);
+    A.slot_update = slot;
     lsm_init_kernel<double><<<grid, kLsmBlock, 0, s>>>(A, time_index);
   } else {
     LsmArgs<float> A;
     fill_args(h, &A);
+    A.slot_update = slot;
     lsm_init_kernel<float><<<grid, kLsmBlock, 0, s>>>(A, time_index);
   }
   TQF_CUDA_OK(cudaGetLastError());

@@ -112,6 +112,11 @@ class LsmDesc(C.Structure):
       ('w_dev', C.c_void_p),
       ('partials_dev', C.c_void_p),
       ('partials_doubles', C.c_uint64),
+      ('exercise_time_indices', C.c_void_p),
+      ('num_exercise_times', C.c_int32),
+      ('reserved', C.c_int32),
+      ('exercise_values_dev', C.c_void_p),
+      ('path_ratio_dev', C.c_void_p),
   ]
 
 

@@ -181,3 +181,147 @@ def swaption_price(*,
     return price
   var = np.maximum(sums[:, 1] / n - (sums[:, 0] / n)**2, 0.0)
   return price, np.sqrt(var / n).reshape(batch_shape), sums[:, 2].reshape(batch_shape)
+
+
+def _unique_in_order(a):
+  """`tf.unique`: distinct values in order of first appearance, and the inverse."""
+  _, first, inv = np.unique(a, return_index=True, return_inverse=True)
+  order = np.argsort(first, kind='stable')
+  rank = np.empty_like(order)
+  rank[order] = np.arange(order.shape[0])
+  return a[np.sort(first)], rank[inv]
+
+
+def bermudan_swaption_price(*,
+                            exercise_times,
+                            floating_leg_start_times,
+                            floating_leg_end_times,
+                            fixed_leg_payment_times,
+                            floating_leg_daycount_fractions,
+                            fixed_leg_daycount_fractions,
+                            fixed_leg_coupon,
+                            reference_rate_fn,
+                            mean_reversion,
+                            volatility,
+                            notional=None,
+                            is_payer_swaption=True,
+                            use_finite_difference=False,
+                            lsm_basis=None,
+                            num_samples=100,
+                            random_type=None,
+                            seed=None,
+                            skip=0,
+                            time_step=None,
+                            time_step_finite_difference=None,
+                            num_grid_points_finite_difference=101,
+                            dtype=None,
+                            name=None):
+  """Bermudan swaption prices by Longstaff-Schwartz on Hull-White short-rate
+  paths (`models/hull_white/swaption.py:314-724`, Monte-Carlo branch).
+
+  `exercise_times`: `batch_shape + [E]`; the leg arrays: `batch_shape + [E, m]`
+  (for every exercise date the remaining payments, padded).  Returns a numpy
+  array of shape `batch_shape`.
+
+  The short-rate state and its path integral come from the fused HW1F kernel
+  (nothing but the `[N, k, 2]` state is stored), the exercise values
+  `+-(1 - P_N - sum_j c_j tau_j P_j)` are tabulated on the device from the
+  closed-form bond prices, and the regression / exercise passes are the LSM
+  kernels with one discount curve per path.  As in the reference the swaption
+  is valued as a payer (`swaption.py:562`); the finite-difference branch is a
+  PDE solver outside the Monte-Carlo hot path and is not provided.
+  """
+  del floating_leg_daycount_fractions, floating_leg_start_times, floating_leg_end_times
+  del name, time_step_finite_difference, num_grid_points_finite_difference, is_payer_swaption
+  import torch
+  from tff_b200.models.longstaff_schwartz import lsm
+  from tff_b200.models.longstaff_schwartz import payoff_utils
+  dt_ = _tensor.infer_dtype(exercise_times, dtype, default=np.float32)
+  ex = _tensor.to_numpy(exercise_times, dt_)
+  pay_t = _tensor.to_numpy(fixed_leg_payment_times, dt_)
+  dcf = np.broadcast_to(_tensor.to_numpy(fixed_leg_daycount_fractions, dt_), pay_t.shape)
+  coupon = np.broadcast_to(_tensor.to_numpy(fixed_leg_coupon, dt_), pay_t.shape)
+  ntl = np.asarray(1.0 if notional is None else _tensor.to_numpy(notional, dt_), dtype=dt_)
+  if use_finite_difference:
+    raise NotImplementedError(
+        'The finite-difference Bermudan valuation is a PDE solver outside the '
+        'B200 Monte-Carlo hot path; call with use_finite_difference=False.')
+  if ex.ndim < pay_t.ndim - 1:
+    raise ValueError('Swaption exercise times not specified for all '
+                     'swaptions in the batch. Expected rank '
+                     '{} but received {}.'.format(pay_t.ndim - 1, ex.ndim))
+  if time_step is None:
+    raise ValueError('`time_step` must be provided for LSM valuation.')
+  basis_fn = lsm.make_polynomial_basis(2) if lsm_basis is None else lsm_basis
+  model = one_factor.HullWhiteModel1F(mean_reversion, volatility,
+                                      reference_rate_fn, dtype=dt_)
+  if model._tables is None:
+    raise NotImplementedError(
+        'bermudan_swaption_price needs constant mean reversion and constant or '
+        'piecewise-constant volatility (exact discretisation).')
+  batch_shape = ex.shape[:-1]
+  n_ex, m = ex.shape[-1], pay_t.shape[-1]
+  nb = int(np.prod(batch_shape)) if batch_shape else 1
+  ex_flat = ex.reshape(nb, n_ex)
+  pay_flat = np.broadcast_to(pay_t, batch_shape + (n_ex, m)).reshape(nb, n_ex, m)
+  coef = (np.broadcast_to(coupon, batch_shape + (n_ex, m)) *
+          np.broadcast_to(dcf, batch_shape + (n_ex, m))).reshape(nb, n_ex, m).astype(np.float64)
+  coef[..., -1] += 1.0                           # float leg: 1 - P(t_e, T_N)
+
+  # unique exercise dates in order of first appearance; simulation grid
+  # (swaption.py:571-574, 611-615; `longest` is the LAST unique date)
+  uniq, ex_index = _unique_in_order(ex_flat.reshape(-1))
+  ex_index = ex_index.reshape(nb, n_ex)
+  longest = uniq[-1]
+  sim_times = np.unique(np.concatenate(
+      [uniq, utils._tf_range(time_step, longest, time_step, dt_)])).astype(dt_)
+  k_sim = sim_times.shape[0]
+
+  def integral_weights(all_times, idx):
+    w = np.zeros(all_times.shape[0] - 1, dtype=dt_)
+    dts = np.concatenate([[0.0], sim_times[1:] - sim_times[:-1]]).astype(dt_)
+    for j, i in enumerate(idx):
+      if i >= 1:
+        w[i - 1] += dts[j]
+    return w
+  plan, record_slot, _, _ = model._exact_plan(
+      sim_times, int(num_samples), random_type, seed, skip, None, None,
+      integral_weights_fn=integral_weights)
+  try:
+    state = plan.paths(record_slot, k_sim)                   # [N, k, 2] = (x, integral)
+  finally:
+    plan.close()
+  n = int(state.shape[0])
+  dev, td = state.device, state.dtype
+  sim_idx = np.searchsorted(sim_times, uniq, side='left')   # [U]
+  sel = torch.as_tensor(sim_idx, device=dev)
+  x_u = state[:, sel, 0]                                      # [N, U]
+  f0 = torch.as_tensor(model._fwd(uniq), device=dev, dtype=td)
+  short_rate = (x_u + f0[None, :]).unsqueeze(-1).contiguous()      # [N, U, 1]
+  df_u = torch.exp(-state[:, sel, 1]).unsqueeze(1).contiguous()    # [N, 1, U]
+
+  # bond prices at the exercise dates: P(t, T_j) = exp(kk_j - g_j x(t))
+  kconst = model._tables.k
+  t_e = np.repeat(ex_flat[..., None], m, axis=-1)             # [nb, E, m]
+  rate = lambda t: _exact.discount_rate(model._initial_discount_rate_fn, t, dt_)
+  g = (1. - np.exp(-kconst * (pay_flat - t_e))) / kconst
+  y = model._tables.y_t(t_e.reshape(-1)).reshape(t_e.shape)
+  kk = -(rate(pay_flat) * pay_flat) + rate(t_e) * t_e - 0.5 * y * g**2
+  gd = torch.as_tensor(g, device=dev, dtype=td)
+  kd = torch.as_tensor(kk, device=dev, dtype=td)
+  cd = torch.as_tensor(coef, device=dev, dtype=td)
+  u_count = uniq.shape[0]
+  values = torch.zeros((u_count, n, nb), device=dev, dtype=td)
+  for b in range(nb):
+    for e in range(n_ex):
+      u = int(ex_index[b, e])
+      bonds = torch.exp(kd[b, e][None, :] - gd[b, e][None, :] * x_u[:, u:u + 1])   # [N, m]
+      swap = 1.0 - (cd[b, e][None, :] * bonds).sum(dim=-1)
+      # duplicates of an exercise date overwrite, as the scatter in
+      # `_map_payoff_to_sim_times` does
+      values[u, :, b] = torch.relu(swap)
+  price = lsm.least_square_mc(
+      short_rate, np.arange(u_count), payoff_utils.make_tabulated_payoff(values),
+      basis_fn, discount_factors=df_u, dtype=dt_)
+  price = (np.broadcast_to(ntl, batch_shape).reshape(-1) * price).astype(dt_)
+  return price.reshape(batch_shape)

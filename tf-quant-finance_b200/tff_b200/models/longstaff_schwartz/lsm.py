@@ -82,12 +82,14 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
   Returns a numpy array `[batch_size]`.
   """
   del name
-  if not isinstance(payoff_fn, payoff_utils.BasketPutPayoff) or not isinstance(
+  tabulated = isinstance(payoff_fn, payoff_utils.TabulatedPayoff)
+  if not (tabulated or isinstance(payoff_fn, payoff_utils.BasketPutPayoff)) or not isinstance(
       basis_fn, PolynomialBasis):
     raise NotImplementedError(
         'The B200 LSM passes evaluate the payoff and the basis inside CUDA '
-        'kernels: use make_basket_put_payoff(strikes) and '
-        'make_polynomial_basis(degree). There is no CPU fallback.')
+        'kernels: use make_basket_put_payoff(strikes) or '
+        'make_tabulated_payoff(values), and make_polynomial_basis(degree). '
+        'There is no CPU fallback.')
   if isinstance(sample_paths, torch.Tensor) or hasattr(sample_paths, '__dlpack__'):
     x = _tensor.from_dlpack(sample_paths)
     if dtype is not None:
@@ -101,31 +103,56 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
   if x.dim() not in (3, 4):
     raise ValueError('sample_paths must have rank 3 or 4')
   n_local, dim = int(x.shape[-3]), int(x.shape[-1])
-  strikes = payoff_fn.strikes.astype(np.float64)
-  B = int(x.shape[0]) if batched else strikes.shape[0]
-  if batched and strikes.shape[0] not in (1, B):
-    raise ValueError('strikes batch does not match the batch of sample paths')
-  strikes = np.ascontiguousarray(np.broadcast_to(strikes, (B,)))
   ex_times = np.asarray(_tensor.to_numpy(exercise_times)).astype(np.int64).reshape(-1)
   T = ex_times.shape[0]
+  ev_tab = None
+  if tabulated:
+    vals = payoff_fn.values.to(device=x.device, dtype=x.dtype)        # [times, N, B]
+    if int(vals.shape[1]) != n_local:
+      raise ValueError('tabulated payoff does not match the number of sample paths')
+    B = int(vals.shape[2])
+    if batched and int(x.shape[0]) not in (1, B):
+      raise ValueError('payoff batch does not match the batch of sample paths')
+    strikes = np.zeros(B, dtype=np.float64)
+    # [T, B, N]: one contiguous column per (exercise date, payoff)
+    ev_tab = vals[torch.as_tensor(ex_times, device=vals.device)].permute(0, 2, 1).contiguous()
+  else:
+    strikes = payoff_fn.strikes.astype(np.float64)
+    B = int(x.shape[0]) if batched else strikes.shape[0]
+    if batched and strikes.shape[0] not in (1, B):
+      raise ValueError('strikes batch does not match the batch of sample paths')
+    strikes = np.ascontiguousarray(np.broadcast_to(strikes, (B,)))
 
   # discount factors: [T+1, B] with a leading 1 (lsm.py:239-256)
-  if discount_factors is None:
-    df = np.ones((1, 1, T), dtype=dt)
+  ratio_path = None
+  per_path = (isinstance(discount_factors, torch.Tensor) and discount_factors.dim() == 3
+              and int(discount_factors.shape[0]) != 1)
+  if per_path:
+    # rank 3, one discount curve per sample: [N, 1, T] (lsm.py:208-256)
+    dfp = discount_factors.to(device=x.device, dtype=x.dtype)
+    if int(dfp.shape[0]) != n_local or int(dfp.shape[1]) != 1 or int(dfp.shape[2]) != T:
+      raise NotImplementedError(
+          'per-sample discount factors must have shape [num_samples, 1, num_exercise_times]')
+    dfp = torch.cat([torch.ones_like(dfp[:, :, :1]), dfp], dim=-1)[:, 0, :]      # [N, T+1]
+    ratio_path = (dfp[:, 1:] / dfp[:, :-1]).transpose(0, 1).contiguous()       # [T, N]
+    ratio = np.ones((T, B), dtype=np.float64)
   else:
-    df = _tensor.to_numpy(discount_factors, dt)
-  if df.ndim == 0:
-    df = df.reshape(1, 1, 1)
-  if df.ndim == 1:
-    df = df.reshape(1, 1, -1)
-  if df.ndim != 3:
-    raise NotImplementedError('discount_factors must have rank 0, 1 or 3')
-  if df.shape[0] != 1:
-    raise NotImplementedError(
-        'per-sample discount factors are not implemented by the B200 engine')
-  df = np.concatenate([np.ones(df.shape[:2] + (1,), dtype=dt), df], axis=-1)
-  df = np.broadcast_to(np.transpose(df, [2, 0, 1])[:, 0, :], (df.shape[-1], B))
-  ratio = (df[1:] / df[:-1]).astype(dt).astype(np.float64)        # [T, B]
+    if discount_factors is None:
+      df = np.ones((1, 1, T), dtype=dt)
+    else:
+      df = _tensor.to_numpy(discount_factors, dt)
+    if df.ndim == 0:
+      df = df.reshape(1, 1, 1)
+    if df.ndim == 1:
+      df = df.reshape(1, 1, -1)
+    if df.ndim != 3:
+      raise NotImplementedError('discount_factors must have rank 0, 1 or 3')
+    if df.shape[0] != 1:
+      raise NotImplementedError(
+          'per-sample discount factors must be a CUDA tensor [num_samples, 1, T]')
+    df = np.concatenate([np.ones(df.shape[:2] + (1,), dtype=dt), df], axis=-1)
+    df = np.broadcast_to(np.transpose(df, [2, 0, 1])[:, 0, :], (df.shape[-1], B))
+    ratio = (df[1:] / df[:-1]).astype(dt).astype(np.float64)        # [T, B]
 
   exps = np.ascontiguousarray(basis_fn.exponents(dim), dtype=np.int32)
   K = exps.shape[0]
@@ -135,6 +162,14 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
   d.exponents, d.strikes = exps.ctypes.data, strikes.ctypes.data
   d.num_paths, d.path_offset = n_local, int(global_path_offset)
   d.num_calibration_samples = int(num_calibration_samples or 0)
+  ex_i32 = np.ascontiguousarray(ex_times, dtype=np.int32)
+  if ev_tab is not None or ratio_path is not None:
+    if K > 6:
+      raise NotImplementedError(
+          'tabulated payoffs / per-sample discount factors need a basis of at most 6 functions')
+    d.exercise_time_indices, d.num_exercise_times = ex_i32.ctypes.data, T
+    d.exercise_values_dev = 0 if ev_tab is None else ev_tab.data_ptr()
+    d.path_ratio_dev = 0 if ratio_path is None else ratio_path.data_ptr()
   d.paths_dev = x.data_ptr()
   st = x.stride()
   if batched:
@@ -220,4 +255,5 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
     vs = vs.cpu().numpy()
   finally:
     lib.tqf_lsm_destroy(handle)
+  # per-sample discounting: the value sum already carries df[1] / df[0] per path
   return (ratio[0] * vs[:, 0] / vs[:, 1]).astype(dt)

@@ -34,3 +34,27 @@ def make_basket_put_payoff(strikes, dtype=None, name=None):
   """Produces the payoff of a simple basket put option (`payoff_utils.py:27-58`)."""
   del name
   return BasketPutPayoff(strikes, dtype)
+
+
+class TabulatedPayoff:
+  """Exercise values known in advance: `values[time_index]` is the
+  `[num_samples, batch_size]` payoff of exercising at `time_index`.
+
+  The reference's Bermudan swaption pricer hands `least_square_mc` a closure
+  over such a precomputed tensor (`hull_white/swaption.py:698-706`); a Python
+  closure cannot run inside the fused LSM passes, this descriptor can: the
+  passes read the values from device memory."""
+
+  def __init__(self, values):
+    self.values = _tensor.from_dlpack(values) if not isinstance(values, torch.Tensor) else values
+    if self.values.dim() != 3:
+      raise ValueError('values must have shape [num_times, num_samples, batch_size]')
+
+  def __call__(self, sample_paths, time_index):
+    del sample_paths
+    return self.values[int(time_index)]
+
+
+def make_tabulated_payoff(values):
+  """Payoff descriptor of precomputed exercise values `[num_times, N, B]`."""
+  return TabulatedPayoff(values)
