@@ -784,9 +784,20 @@ __global__ void lsm_solve_kernel(const double* __restrict__ partials, int num_bl
   if (partials != nullptr) {
     const int M = B * kLsmFastNS;
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // one warp per sum, 8 warps (the 188 registers of the solver cap the block at 256 threads);
+    // 8 independent loads in flight per lane, combined in a fixed order
     for (int m = threadIdx.x >> 5; m < M; m += nwarps) {
-      double v = 0.0;
-      for (int bk = lane; bk < num_blocks; bk += 32) v += partials[static_cast<size_t>(bk) * M + m];
+      double a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = 0.0;
+      int bk = lane;
+      for (; bk + 7 * 32 < num_blocks; bk += 8 * 32) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] += partials[static_cast<size_t>(bk + u * 32) * M + m];
+      }
+      double tail = 0.0;
+      for (; bk < num_blocks; bk += 32) tail += partials[static_cast<size_t>(bk) * M + m];
+      double v = (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) + tail;
       v = warp_sum(v);
       if (lane == 0) sums[m] = v;
     }
