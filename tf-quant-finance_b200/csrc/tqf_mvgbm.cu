@@ -15,6 +15,7 @@
 // constant operand -- no shared-memory traffic, no per-path matrix.  CUDA-core
 // FP32; a tensor-core formulation would need the [paths x dim] normal tile in
 // shared memory and only pays for the 48 % of the step that is the mat-vec.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -386,6 +387,9 @@ static void build_split(const double* chol, const double* mu, const double* sigm
   }
 }
 
+static void build_mma(const double* chol, const double* mu, const double* sigma, int dim,
+                      std::vector<float>* out);
+
 int mvgbm_upload_split(const double* chol, const double* mu, const double* sigma, int dim,
                        int dtype, void** out_dev) {
   void* dev = nullptr;
@@ -396,8 +400,10 @@ int mvgbm_upload_split(const double* chol, const double* mu, const double* sigma
     TQF_CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(double)));
     e = cudaMemcpy(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice);
   } else {
-    std::vector<float> host;
+    std::vector<float> host, mma;
     build_split<float>(chol, mu, sigma, dim, &host);
+    build_mma(chol, mu, sigma, dim, &mma);   // tensor-core kernel's tables follow
+    host.insert(host.end(), mma.begin(), mma.end());
     TQF_CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(float)));
     e = cudaMemcpy(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
   }
@@ -629,6 +635,332 @@ mvgbm_split_kernel(const __grid_constant__ MvParams<Real, kMvDim> P) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// float32, Sobol, 8 < dim <= 64: the triangular mat-vec of 16 paths at a time
+// IS a dense contraction, [64 x 64] factor times [64 x 16] normals, and runs on
+// the tensor cores (mma.sync m16n8k8, TF32 operands, FP32 accumulate).  A plain
+// TF32 product (10-bit mantissa) would break the 1e-5 parity bound, so both
+// operands are split, L = Lh + Ll (on the host), z = zh + zl (two instructions
+// per draw), and Lh zh + Ll zh + Lh zl is accumulated: error ~2^-21 per term.
+//   * a warp owns 16 paths (two n-tiles); the CTA's 4 warps = 64 Sobol indices;
+//   * every thread draws its normals DIRECTLY in the B-fragment layout (lane
+//     c = lane % 4 owns dimensions 8 kt + c and 8 kt + 4 + c of path lane / 4 of
+//     each n-tile): no shared-memory staging of the normals and no barrier in
+//     the step loop;
+//   * the 20 non-zero 16 x 8 tiles of the factor sit in shared memory in
+//     A-fragment order (one conflict-free LDS.128 per tile and split part);
+//   * the state lives in the C-fragment layout (rows 16 mt + g, 16 mt + 8 + g,
+//     paths 2 c, 2 c + 1 of each n-tile), where the Euler update is applied.
+// Per path-step this issues ~2.2x fewer instructions than mvgbm_split_kernel
+// (the 2 080 FFMAs become 7.5 warp-wide HMMAs).
+constexpr int kMmaWarps = 4, kMmaPathsPerWarp = 16, kMmaPaths = kMmaWarps * kMmaPathsPerWarp;
+constexpr int kMmaIdxBits = 6;
+constexpr int kMmaTiles = 20;                                    // (mt, kt) with kt <= 2 mt + 1
+constexpr int kMmaFragWords = kMmaTiles * 2 * 32 * 4;           // hi / lo fragments
+constexpr int kMmaTabWords = kMmaFragWords + 2 * kMvDim;        // + mu[64], sigma[64]
+constexpr int kMmaTileDims = 256;                                // Sobol dimensions staged at once
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+// Sobol integer point -> standard normal, float32: the reference's
+// (float(x) 2^-32 - 0.5) 2 equals RN(float(x) 2^-31 - 1) (the scaling by two
+// commutes with the rounding), one FFMA.
+__device__ __forceinline__ float sobol_normal_f32(uint32_t x32) {
+  const float t = fmaf(__uint2float_rn(x32), 4.656612873077393e-10f, -1.0f);
+  return fm::ndtri_t_f32(t);
+}
+
+static uint32_t tf32_round_bits(float f) {
+  uint32_t b;
+  std::memcpy(&b, &f, 4);
+  b += 0x00000fffu + ((b >> 13) & 1u);
+  return b & 0xffffe000u;
+}
+
+// Host: factor -> [tile][hi | lo][lane][4] A fragments (tile order: kt outer,
+// mt = kt / 2 .. 3 inner -- the order the kernel consumes them), then mu, sigma.
+static void build_mma(const double* chol, const double* mu, const double* sigma, int dim,
+                      std::vector<float>* out) {
+  out->assign(kMmaTabWords, 0.0f);
+  uint32_t* w = reinterpret_cast<uint32_t*>(out->data());
+  int ti = 0;
+  for (int kt = 0; kt < 8; ++kt)
+    for (int mt = kt / 2; mt < 4; ++mt, ++ti)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, c = lane & 3;
+        const int rows[4] = {16 * mt + g, 16 * mt + g + 8, 16 * mt + g, 16 * mt + g + 8};
+        const int cols[4] = {8 * kt + c, 8 * kt + c, 8 * kt + c + 4, 8 * kt + c + 4};
+        for (int e = 0; e < 4; ++e) {
+          const int i = rows[e], j = cols[e];
+          const float v = (j <= i && i < dim) ? static_cast<float>(chol[static_cast<size_t>(i) * dim + j])
+                                              : 0.0f;
+          const uint32_t hb = tf32_round_bits(v);
+          float hf;
+          std::memcpy(&hf, &hb, 4);
+          w[((ti * 2 + 0) * 32 + lane) * 4 + e] = hb;
+          w[((ti * 2 + 1) * 32 + lane) * 4 + e] = tf32_round_bits(v - hf);
+        }
+      }
+  for (int i = 0; i < dim; ++i) {
+    (*out)[kMmaFragWords + i] = static_cast<float>(mu[i]);
+    (*out)[kMmaFragWords + kMvDim + i] = static_cast<float>(sigma[i]);
+  }
+}
+
+__global__ void __launch_bounds__(kMmaWarps * 32, 4)
+mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
+  // per staged dimension 8 words: hi ^ (warp bits) for the 4 warps, then the
+  // direction words of index bits 0..3
+  __shared__ uint4 s_sob[kMmaTileDims * 2];
+  __shared__ uint4 s_frag[kMmaFragWords / 4];
+  __shared__ double s_acc[kMmaWarps][TQF_MAX_PAYOFFS * 3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  const float* tabp = P.lsplit + kMvParts * kMvSplitStride;
+  for (int i = tid; i < kMmaFragWords / 4; i += blockDim.x)
+    s_frag[i] = __ldg(reinterpret_cast<const uint4*>(tabp) + i);
+  for (int i = tid; i < kMmaWarps * TQF_MAX_PAYOFFS * 3; i += blockDim.x) (&s_acc[0][0])[i] = 0.0;
+  // rows of this thread in the C layout: 16 mt + g (h = 0), 16 mt + 8 + g (h = 1)
+  float mu[8], sg[8], x0[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = 16 * (r >> 1) + 8 * (r & 1) + g;
+    mu[r] = __ldg(tabp + kMmaFragWords + i);
+    sg[r] = __ldg(tabp + kMmaFragWords + kMvDim + i);
+    x0[r] = P.x0[i];
+  }
+  __syncthreads();
+
+  // index of the path this thread DRAWS for, n-tile 0: warp * 16 + g (bit 3 = n-tile)
+  uint32_t lowmask[3];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    lowmask[b] = 0u - ((static_cast<uint32_t>(g) >> b) & 1u);
+    asm volatile("" : "+r"(lowmask[b]));
+  }
+  const int dim = P.dim;
+  const int tile_steps = kMmaTileDims / dim;   // dim <= 64 -> >= 4
+  const uint64_t chunk_base = P.first_index & ~static_cast<uint64_t>(kMmaPaths - 1);
+  const uint64_t num_chunks =
+      (P.first_index + P.path_count - chunk_base + kMmaPaths - 1) / kMmaPaths;
+  const uint32_t sob_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_sob));
+  const uint32_t frag_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_frag)) + lane * 16;
+  const uint32_t sob_lane = sob_addr + c * 32;
+
+  for (uint64_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
+    // paths of this thread in the C layout: warp * 16 + nt * 8 + 2 c + e
+    bool valid[2][2];
+    uint64_t local[2][2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const uint64_t index = chunk_base + chunk * kMmaPaths + warp * 16 + nt * 8 + 2 * c + e;
+        valid[nt][e] = index >= P.first_index && index < P.first_index + P.path_count;
+        local[nt][e] = index - P.first_index;
+      }
+    float x[4][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[mt][nt][e] = x0[mt * 2 + (e >> 1)];
+
+    auto record = [&](int step_index, int slot) {
+      if (P.mode != MODE_PRICE) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 16 * mt + 8 * (e >> 1) + g;
+              if (valid[nt][e & 1] && i < dim) {
+                const float v = x[mt][nt][e];
+                P.out[static_cast<int64_t>(local[nt][e & 1]) * P.stride_path + slot * P.stride_time +
+                      i * P.stride_dim] = P.store_exp ? expf(v) : v;
+              }
+            }
+        return;
+      }
+      for (int pq = 0; pq < P.num_payoffs; ++pq) {
+        const PayoffK& d = P.pay[pq];
+        if (d.step != step_index) continue;
+        // basket sum (component < 0) or one component: own rows, then the 8 lanes
+        // that share c (shuffles over the g bits)
+        float part[2][2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float sacc = 0;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int i = 16 * mt + 8 * h + g;
+                const bool take = d.component < 0 ? i < dim : i == d.component;
+                sacc += take ? x[mt][nt][2 * h + e] : 0.0f;
+              }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) sacc += __shfl_xor_sync(0xFFFFFFFFu, sacc, o);
+            part[nt][e] = sacc;
+          }
+        double sum = 0.0, sq = 0.0, bad = 0.0;
+        if (g == 0) {
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float m = part[nt][e];
+              if (d.component < 0) m = m / static_cast<float>(dim);
+              if (valid[nt][e]) {
+                const double v = eval_payoff(d, static_cast<double>(m), 0.0, 0.0);
+                if (isfinite(v)) {
+                  sum += v;
+                  sq += v * v;
+                } else {
+                  bad += 1.0;
+                }
+              }
+            }
+        }
+        sum = warp_sum(sum);
+        sq = warp_sum(sq);
+        bad = warp_sum(bad);
+        if (lane == 0) {
+          s_acc[warp][pq * 3 + 0] += sum;
+          s_acc[warp][pq * 3 + 1] += sq;
+          s_acc[warp][pq * 3 + 2] += bad;
+        }
+      }
+    };
+    if (P.record_slot[0] >= 0) record(0, P.record_slot[0]);
+
+    for (int s0 = 0; s0 < P.num_steps; s0 += tile_steps) {
+      const int s1 = min(P.num_steps, s0 + tile_steps);
+      __syncthreads();
+      {
+        const uint32_t high_bits =
+            static_cast<uint32_t>((chunk_base + chunk * kMmaPaths) >> kMmaIdxBits);
+        for (int dd = tid; dd < (s1 - s0) * dim; dd += blockDim.x) {
+          const uint4* v4 = reinterpret_cast<const uint4*>(
+              P.sobol_v + (static_cast<size_t>(s0) * dim + dd) * 32);
+          uint4 w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) w[q] = __ldg(v4 + q);
+          const uint32_t* wv = reinterpret_cast<const uint32_t*>(w);
+          uint32_t h = 0;
+#pragma unroll
+          for (int b = kMmaIdxBits; b < 32; ++b)
+            h ^= wv[b] & (0u - ((high_bits >> (b - kMmaIdxBits)) & 1u));
+          s_sob[2 * dd] = make_uint4(h, h ^ wv[4], h ^ wv[5], h ^ wv[4] ^ wv[5]);
+          s_sob[2 * dd + 1] = w[0];
+        }
+      }
+      __syncthreads();
+      for (int s = s0; s < s1; ++s) {
+        float acc[4][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.0f;
+        const uint32_t sa = sob_lane + (s - s0) * dim * 32;
+        int ti = 0;   // compile-time after unrolling
+#pragma unroll
+        for (int kt = 0; kt < 8; ++kt) {
+          // this thread's entries of the B fragments of k-tile kt, both n-tiles
+          uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = 8 * kt + 4 * h;           // + c
+            float z0 = 0.0f, z1 = 0.0f;
+            if (j + c < dim) {
+              const uint4 v = lds_u4(sa + j * 32 + 16);
+              uint32_t xb = lds_u32(sa + j * 32 + warp * 4);
+              xb ^= v.x & lowmask[0];
+              xb ^= v.y & lowmask[1];
+              xb ^= v.z & lowmask[2];
+              z0 = sobol_normal_f32(xb);
+              z1 = sobol_normal_f32(xb ^ v.w);       // index bit 3 = n-tile
+            }
+            bh[0][h] = __float_as_uint(z0) & 0xffffe000u;
+            bh[1][h] = __float_as_uint(z1) & 0xffffe000u;
+            bl[0][h] = __float_as_uint(z0 - __uint_as_float(bh[0][h]));
+            bl[1][h] = __float_as_uint(z1 - __uint_as_float(bh[1][h]));
+          }
+          uint4 ah[4], al[4];
+#pragma unroll
+          for (int mt = kt / 2; mt < 4; ++mt) {
+            ah[mt] = lds_u4(frag_addr + ((ti + mt - kt / 2) * 2 + 0) * 512);
+            al[mt] = lds_u4(frag_addr + ((ti + mt - kt / 2) * 2 + 1) * 512);
+          }
+          // small terms first; the three products of one accumulator are spaced
+          // by the other accumulators
+#pragma unroll
+          for (int mt = kt / 2; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], al[mt], bh[nt][0], bh[nt][1]);
+#pragma unroll
+          for (int mt = kt / 2; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], ah[mt], bl[nt][0], bl[nt][1]);
+#pragma unroll
+          for (int mt = kt / 2; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
+          ti += 4 - kt / 2;
+        }
+        const float dt = P.coef[2 * s], sq = P.coef[2 * s + 1];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int r = mt * 2 + (e >> 1);
+              const float xv = x[mt][nt][e], a = acc[mt][nt][e];
+              if (P.exact_log) {
+                x[mt][nt][e] = xv + (mu[r] * dt + (sq * sg[r]) * a);
+              } else {
+                const float dt_inc = dt * (mu[r] * xv);
+                const float dw_inc = (sg[r] * xv) * (a * sq);
+                x[mt][nt][e] = (xv + dt_inc) + dw_inc;
+              }
+            }
+        const int flag = P.record_slot[s + 1];
+        if (flag >= 0) record(s + 1, flag);
+      }
+    }
+  }
+  if (P.mode == MODE_PRICE) {
+    __syncthreads();
+    for (int i = tid; i < TQF_MAX_PAYOFFS * 3; i += blockDim.x) {
+      const int q = i / 3, k = i - q * 3;
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kMmaWarps; ++w) v += s_acc[w][i];
+      P.partials[(static_cast<size_t>(blockIdx.x) * TQF_MAX_PAYOFFS + q) * 4 + k] = v;
+    }
+  }
+}
+
+static bool mma_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("TQF_MVGBM_MMA");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <typename Real, int DMAX>
 static void launch_split(const MvParams<Real, DMAX>& P, int grid, cudaStream_t stream) {
   if constexpr (DMAX == kMvDim) {
@@ -689,6 +1021,13 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
                                     ? chunks32 : static_cast<uint64_t>(a.max_grid));
     if (grid < 1) grid = 1;
     *grid_out = grid;
+    if constexpr (sizeof(Real) == 4 && DMAX == kMvDim) {
+      if (a.rngk == RNGK_SOBOL && mma_enabled()) {
+        mvgbm_mma_kernel<<<grid, kMmaWarps * 32, 0, stream>>>(P);
+        TQF_CUDA_OK(cudaGetLastError());
+        return TQF_OK;
+      }
+    }
     launch_split(P, grid, stream);
     TQF_CUDA_OK(cudaGetLastError());
     return TQF_OK;
