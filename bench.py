@@ -459,13 +459,14 @@ def run_gpu_c5(args):
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record(stream)
     # [rows, 50, 1] time-major view of exp(log-price), exponentiated on store
-    paths = plan.paths(record_slot, 50, lo, hi - lo, exp_transform=True)
+    # (the kernel that writes the paths also sums every column: the LSM basis means)
+    paths, csums = plan.paths(record_slot, 50, lo, hi - lo, exp_transform=True, column_sums=True)
     e1.record(stream)
     # antithetic shard rows: [+ partners of units lo..hi) | - partners]; the global
     # index only matters for num_calibration_samples (unused here)
     price = lsm.least_square_mc(paths, np.arange(50), put, basis, discount_factors=df,
                                 dtype=np.float64, global_path_offset=2 * lo,
-                                all_reduce=reduce_fn)
+                                all_reduce=reduce_fn, column_sums=csums)
     e2.record(stream)
     if timed:
       torch.cuda.synchronize()
@@ -523,7 +524,7 @@ def run_gpu_c5(args):
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved / hbm_peak, 'traffic': None,
                      'note': 'LSM passes: 32 algorithmic bytes per path per exercise date (SURVEY 8d) '
-                             '/ time between the device events around least_square_mc (column means, 49 streaming '
+                             '/ time between the device events around least_square_mc (49 streaming '
                              'passes, 49 device solves); peak = MEASURED_PEAKS.json hbm_gbs'},
         'cpu_baseline': {'value': cv, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                          'sample': '%d paths x %d steps + LSM, single process numpy oracle (%.1f s)' % (cn, csteps, cdt)},

@@ -232,6 +232,17 @@ int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                    int64_t stride_path, int64_t stride_time, int64_t stride_dim,
                    int transform, void* stream);
 
+/* tqf_plan_paths that also returns, in column_sums_dev (double
+ * [num_slots][dim], fully overwritten), the sum over this shard's paths of
+ * every stored value (after `transform`): the basis-centring means of the
+ * Longstaff-Schwartz passes (lsm.py:110-111) without a second pass over the
+ * paths.  Slots that no step records receive 0.  Not for TQF_MODEL_MVGBM.  */
+int tqf_plan_paths_sums(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                        const int32_t* record_slot, void* out_dev,
+                        int64_t stride_path, int64_t stride_time, int64_t stride_dim,
+                        int transform, int num_slots, double* column_sums_dev,
+                        void* stream);
+
 /* ------------------------------------------------------------------------
  * Longstaff-Schwartz regression passes on materialised paths: replaces the
  * device work of models/longstaff_schwartz/lsm.py:231-436 (payoff_fn, basis_fn,

@@ -131,3 +131,38 @@ def test_lsm_tabulated_payoff_and_per_path_discounting():
       discount_factors=df, dtype=np.float64)
   assert got.shape == (b,)
   np.testing.assert_allclose(got, want, rtol=1e-10)
+
+
+def test_column_sums_from_the_path_kernel():
+  # engine.Plan.paths(column_sums=True): the sums the LSM basis means need,
+  # accumulated by the kernel that stores the paths (lsm.py:110-111)
+  import torch
+  import tff_b200 as tff
+  from tff_b200 import engine
+  from tff_b200.models import closures, utils
+  lsm = _lsm()
+  r, sigma, n = 0.1, 1.0, 50_002
+  times = np.linspace(0.0, 1.0, 13)
+  drift, vol = closures.affine_closures(r - sigma**2 / 2, 0.0, sigma)
+  spec = closures.resolve_spec(drift, vol)
+  all_times, mask, _ = utils.prepare_grid(times=times, time_step=np.float64(0.05), dtype=np.float64)
+  steps, record_slot = engine.record_plan(mask, 13)
+  for rtype in (tff.math.random.RandomType.STATELESS_ANTITHETIC, tff.math.random.RandomType.SOBOL):
+    rng = engine.RngSpec(rtype, [4, 2], 0)
+    plan = engine.Plan(spec, all_times, steps, np.array([0.0]), rng, n, np.float64)
+    try:
+      ref = plan.paths(record_slot, 13, exp_transform=True)
+      paths, sums = plan.paths(record_slot, 13, exp_transform=True, column_sums=True)
+      assert torch.equal(ref, paths)
+      np.testing.assert_allclose(sums.cpu().numpy(), paths.sum(dim=0).cpu().numpy(), rtol=1e-13)
+      # a shard of the units
+      p2, s2 = plan.paths(record_slot, 13, 1000, 3000, exp_transform=True, column_sums=True)
+      np.testing.assert_allclose(s2.cpu().numpy(), p2.sum(dim=0).cpu().numpy(), rtol=1e-13)
+      df = np.exp(-r * times)
+      put, basis = lsm.make_basket_put_payoff([1.1], dtype=np.float64), lsm.make_polynomial_basis(3)
+      a = lsm.least_square_mc(paths, np.arange(13), put, basis, discount_factors=df, dtype=np.float64)
+      b = lsm.least_square_mc(paths, np.arange(13), put, basis, discount_factors=df, dtype=np.float64,
+                              column_sums=sums)
+      np.testing.assert_allclose(a, b, rtol=1e-12)
+    finally:
+      plan.close()

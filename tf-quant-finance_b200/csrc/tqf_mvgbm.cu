@@ -675,6 +675,60 @@ __device__ __forceinline__ float sobol_normal_f32(uint32_t x32) {
   return fm::ndtri_t_f32(t);
 }
 
+// Round to nearest TF32: the remainder z - zh then has a sign independent of
+// z, so the tensor core's truncation of it does not bias |z| (a truncating
+// split measurably lowers the C4 price by 4e-7 relative).
+__device__ __forceinline__ uint32_t tf32_rna(float v) {
+  // (cvt.rna.tf32.f32 is emulated with ~5 instructions on sm_100a)
+  return (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+}
+
+// N Sobol integer points -> standard normals, float32, the same arithmetic as
+// fm::ndtri_t_f32 per draw but evaluated side by side: the central polynomial
+// runs unconditionally for all N (independent Horner chains, no branch between
+// them) and ONE rarely taken branch per batch patches the draws in the tails
+// (|z| > 3.1, 0.2 % of them).
+template <int N>
+__device__ __forceinline__ void sobol_normals_f32(const uint32_t (&xb)[N], float (&z)[N]) {
+  float t[N], w[N], p[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    t[k] = fmaf(__uint2float_rn(xb[k]), 4.656612873077393e-10f, -1.0f);
+    const float a = fmaf(-t[k], t[k], 1.0f);
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(a));   // a is never subnormal
+    w[k] = l2 * -0.693147182f;
+  }
+  const float cc[TQF_NDTRI_F32_C_N] = {TQF_NDTRI_F32_C_LIST};
+  float y[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    y[k] = w[k] - TQF_NDTRI_F32_C_MID;
+    p[k] = cc[0];
+  }
+#pragma unroll
+  for (int i = 1; i < TQF_NDTRI_F32_C_N; ++i)
+#pragma unroll
+    for (int k = 0; k < N; ++k) p[k] = fmaf(p[k], y[k], cc[i]);
+  float wmax = w[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) wmax = fmaxf(wmax, w[k]);
+  if (!(wmax < 6.25f)) {
+    const float ct[TQF_NDTRI_F32_T_N] = {TQF_NDTRI_F32_T_LIST};
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (!(w[k] < 6.25f)) {
+        const float yt = sqrtf(w[k]) - TQF_NDTRI_F32_T_MID;
+        float q = ct[0];
+#pragma unroll
+        for (int i = 1; i < TQF_NDTRI_F32_T_N; ++i) q = fmaf(q, yt, ct[i]);
+        p[k] = q;
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) z[k] = t[k] * p[k];
+}
+
 static uint32_t tf32_round_bits(float f) {
   uint32_t b;
   std::memcpy(&b, &f, 4);
@@ -697,8 +751,11 @@ static void build_mma(const double* chol, const double* mu, const double* sigma,
         const int cols[4] = {8 * kt + c, 8 * kt + c, 8 * kt + c + 4, 8 * kt + c + 4};
         for (int e = 0; e < 4; ++e) {
           const int i = rows[e], j = cols[e];
-          const float v = (j <= i && i < dim) ? static_cast<float>(chol[static_cast<size_t>(i) * dim + j])
-                                              : 0.0f;
+          // row i of the factor scaled by sigma_i: the kernel applies
+          // x_i' = x_i (1 + mu_i dt + sqrt_dt sum_j (sigma_i L_ij) z_j)
+          const float v = (j <= i && i < dim)
+                              ? static_cast<float>(sigma[i] * chol[static_cast<size_t>(i) * dim + j])
+                              : 0.0f;
           const uint32_t hb = tf32_round_bits(v);
           float hf;
           std::memcpy(&hf, &hb, 4);
@@ -712,6 +769,8 @@ static void build_mma(const double* chol, const double* mu, const double* sigma,
   }
 }
 
+// FULL: dim == 64 (no padding checks in the draw loop).
+template <bool FULL>
 __global__ void __launch_bounds__(kMmaWarps * 32, 4)
 mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
   // per staged dimension 8 words: hi ^ (warp bits) for the 4 warps, then the
@@ -726,12 +785,11 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
     s_frag[i] = __ldg(reinterpret_cast<const uint4*>(tabp) + i);
   for (int i = tid; i < kMmaWarps * TQF_MAX_PAYOFFS * 3; i += blockDim.x) (&s_acc[0][0])[i] = 0.0;
   // rows of this thread in the C layout: 16 mt + g (h = 0), 16 mt + 8 + g (h = 1)
-  float mu[8], sg[8], x0[8];
+  float mu[8], x0[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int i = 16 * (r >> 1) + 8 * (r & 1) + g;
     mu[r] = __ldg(tabp + kMmaFragWords + i);
-    sg[r] = __ldg(tabp + kMmaFragWords + kMvDim + i);
     x0[r] = P.x0[i];
   }
   __syncthreads();
@@ -750,7 +808,8 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
       (P.first_index + P.path_count - chunk_base + kMmaPaths - 1) / kMmaPaths;
   const uint32_t sob_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_sob));
   const uint32_t frag_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_frag)) + lane * 16;
-  const uint32_t sob_lane = sob_addr + c * 32;
+  // this lane's first dimension: direction words at +16, the warp's high word at + 4 warp
+  const uint32_t sob_v = sob_addr + c * 32 + 16, sob_h = sob_addr + c * 32 + warp * 4;
 
   for (uint64_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
     // paths of this thread in the C layout: warp * 16 + nt * 8 + 2 c + e
@@ -873,30 +932,38 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
           for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.0f;
-        const uint32_t sa = sob_lane + (s - s0) * dim * 32;
+        const uint32_t soff = (s - s0) * dim * 32;
         int ti = 0;   // compile-time after unrolling
 #pragma unroll
         for (int kt = 0; kt < 8; ++kt) {
-          // this thread's entries of the B fragments of k-tile kt, both n-tiles
-          uint32_t bh[2][2], bl[2][2];
+          // this thread's entries of the B fragments of k-tile kt: dimensions
+          // 8 kt + c (h = 0) and 8 kt + 4 + c (h = 1) of both n-tiles, drawn side by side
+          uint32_t xb[4];
+          bool live[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int j = 8 * kt + 4 * h;           // + c
-            float z0 = 0.0f, z1 = 0.0f;
-            if (j + c < dim) {
-              const uint4 v = lds_u4(sa + j * 32 + 16);
-              uint32_t xb = lds_u32(sa + j * 32 + warp * 4);
-              xb ^= v.x & lowmask[0];
-              xb ^= v.y & lowmask[1];
-              xb ^= v.z & lowmask[2];
-              z0 = sobol_normal_f32(xb);
-              z1 = sobol_normal_f32(xb ^ v.w);       // index bit 3 = n-tile
-            }
-            bh[0][h] = __float_as_uint(z0) & 0xffffe000u;
-            bh[1][h] = __float_as_uint(z1) & 0xffffe000u;
-            bl[0][h] = __float_as_uint(z0 - __uint_as_float(bh[0][h]));
-            bl[1][h] = __float_as_uint(z1 - __uint_as_float(bh[1][h]));
+            live[h] = FULL || j + c < dim;
+            const uint32_t jo = (FULL || live[h]) ? j * 32 : 0;   // stay inside the staged tile
+            const uint4 v = lds_u4(sob_v + soff + jo);
+            uint32_t x = lds_u32(sob_h + soff + jo);
+            x ^= v.x & lowmask[0];
+            x ^= v.y & lowmask[1];
+            x ^= v.z & lowmask[2];
+            xb[2 * h] = x;
+            xb[2 * h + 1] = x ^ v.w;                 // index bit 3 = n-tile
           }
+          float z[4];
+          sobol_normals_f32<4>(xb, z);
+          uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              const float zz = (FULL || live[h]) ? z[2 * h + nt] : 0.0f;
+              bh[nt][h] = tf32_rna(zz);
+              bl[nt][h] = __float_as_uint(zz - __uint_as_float(bh[nt][h]));
+            }
           uint4 ah[4], al[4];
 #pragma unroll
           for (int mt = kt / 2; mt < 4; ++mt) {
@@ -919,22 +986,20 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
             for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
           ti += 4 - kt / 2;
         }
+        // acc_i = sum_j sigma_i L_ij z_j.  Euler: x_i' = x_i (1 + mu_i dt + sqrt_dt acc_i);
+        // exact log-normal increment: x_i' = x_i + (mu_i dt + sqrt_dt acc_i), mu = means - vols^2 / 2
         const float dt = P.coef[2 * s], sq = P.coef[2 * s + 1];
+        float c1[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) c1[r] = P.exact_log ? mu[r] * dt : fmaf(mu[r], dt, 1.0f);
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int r = mt * 2 + (e >> 1);
-              const float xv = x[mt][nt][e], a = acc[mt][nt][e];
-              if (P.exact_log) {
-                x[mt][nt][e] = xv + (mu[r] * dt + (sq * sg[r]) * a);
-              } else {
-                const float dt_inc = dt * (mu[r] * xv);
-                const float dw_inc = (sg[r] * xv) * (a * sq);
-                x[mt][nt][e] = (xv + dt_inc) + dw_inc;
-              }
+              const float f = fmaf(sq, acc[mt][nt][e], c1[mt * 2 + (e >> 1)]);
+              x[mt][nt][e] = P.exact_log ? x[mt][nt][e] + f : x[mt][nt][e] * f;
             }
         const int flag = P.record_slot[s + 1];
         if (flag >= 0) record(s + 1, flag);
@@ -1023,7 +1088,10 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
     *grid_out = grid;
     if constexpr (sizeof(Real) == 4 && DMAX == kMvDim) {
       if (a.rngk == RNGK_SOBOL && mma_enabled()) {
-        mvgbm_mma_kernel<<<grid, kMmaWarps * 32, 0, stream>>>(P);
+        if (a.dim == kMvDim)
+          mvgbm_mma_kernel<true><<<grid, kMmaWarps * 32, 0, stream>>>(P);
+        else
+          mvgbm_mma_kernel<false><<<grid, kMmaWarps * 32, 0, stream>>>(P);
         TQF_CUDA_OK(cudaGetLastError());
         return TQF_OK;
       }

@@ -80,6 +80,8 @@ struct tqf_plan {
   uint32_t* sobol_dev;      // [S_total*nf][32]
   const double* logtab_dev; // shared per-device log table (not owned)
   void* lsplit_dev;         // MVGBM dim > 8: factor in the split kernel's order
+  double* colsum_dev;       // [max_grid][slots * dim] column-sum partials (lazily allocated)
+  size_t colsum_doubles;
   double* partials_dev;     // [max_grid][TQF_MAX_PAYOFFS][4]
   int* record_dev;          // [num_steps+1]
   SwaptionK* swaptions_dev; // [TQF_MAX_PAYOFFS]
@@ -288,13 +290,42 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   return TQF_OK;
 }
 
+// sums[m] = sum_blocks partials[block][m]: one warp per column, lanes stride
+// over the CTAs, fixed order -> reproducible.
+__global__ void colsum_reduce_kernel(const double* __restrict__ partials, int num_blocks, int M,
+                                     double* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  double v = 0.0;
+  for (int bk = lane; bk < num_blocks; bk += 32) v += partials[static_cast<size_t>(bk) * M + m];
+  v = warp_sum(v);
+  if (lane == 0) sums[m] = v;
+}
+
 template <typename Real>
 static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                      const int32_t* record_slot, void* out_dev, int64_t stride_path,
                      int64_t stride_time, int64_t stride_dim, int transform,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int num_slots = 0, double* column_sums_dev = nullptr) {
   KParams<Real> P;
   fill_common(plan, path_offset, path_count, &P);
+  if (column_sums_dev) {
+    TQF_REQUIRE(plan->model.kind != TQF_MODEL_MVGBM,
+                "column sums are not available for the multi-asset kernel");
+    const int cols = num_slots * plan->info.dim;
+    TQF_REQUIRE(num_slots >= 1 && cols <= 2048, "column sums: 1 <= num_slots * dim <= 2048");
+    const size_t need = static_cast<size_t>(plan->max_grid) * cols;
+    if (need > plan->colsum_doubles) {
+      cudaFree(plan->colsum_dev);
+      plan->colsum_dev = nullptr;
+      plan->colsum_doubles = 0;
+      TQF_CUDA_OK(cudaMalloc(&plan->colsum_dev, need * sizeof(double)));
+      plan->colsum_doubles = need;
+    }
+    P.colsum_partials = plan->colsum_dev;
+    P.colsum_cols = cols;
+  }
   const size_t nrec = static_cast<size_t>(plan->model.num_steps) + 1;
   TQF_CUDA_OK(cudaMemcpyAsync(plan->record_dev, record_slot, nrec * sizeof(int),
                               cudaMemcpyHostToDevice, stream));
@@ -349,7 +380,13 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PATHS, false);
   }
   P.tables_in_smem = in_smem ? 1 : 0;
-  return dispatch<Real>(plan, MODE_PATHS, plan->max_grid, smem, P, stream, &grid);
+  int rc = dispatch<Real>(plan, MODE_PATHS, plan->max_grid, smem, P, stream, &grid);
+  if (rc == TQF_OK && column_sums_dev) {
+    colsum_reduce_kernel<<<(P.colsum_cols + 3) / 4, 128, 0, stream>>>(
+        plan->colsum_dev, grid, P.colsum_cols, column_sums_dev);
+    TQF_CUDA_OK(cudaGetLastError());
+  }
+  return rc;
 }
 
 extern "C" {
@@ -463,6 +500,7 @@ int tqf_plan_destroy(tqf_plan* plan) {
   cudaFree(plan->coef_dev);
   cudaFree(plan->sobol_dev);
   cudaFree(plan->lsplit_dev);
+  cudaFree(plan->colsum_dev);
   cudaFree(plan->partials_dev);
   cudaFree(plan->record_dev);
   cudaFree(plan->swaptions_dev);
@@ -498,6 +536,24 @@ int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                                  stride_time, stride_dim, transform, s)
              : run_paths<float>(plan, path_offset, path_count, record_slot, out_dev, stride_path,
                                 stride_time, stride_dim, transform, s);
+}
+
+int tqf_plan_paths_sums(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                        const int32_t* record_slot, void* out_dev, int64_t stride_path,
+                        int64_t stride_time, int64_t stride_dim, int transform, int num_slots,
+                        double* column_sums_dev, void* stream) {
+  TQF_REQUIRE(plan && record_slot && column_sums_dev, "null argument");
+  const uint64_t units = plan->rng.antithetic ? plan->num_paths_total / 2 : plan->num_paths_total;
+  TQF_REQUIRE(path_offset + path_count <= units, "shard exceeds the number of paths");
+  TQF_REQUIRE(path_count > 0 && out_dev, "empty shard or null output");
+  for (int i = 0; i <= plan->model.num_steps; ++i)
+    TQF_REQUIRE(record_slot[i] < num_slots, "record_slot entry exceeds num_slots");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return plan->model.dtype == TQF_F64
+             ? run_paths<double>(plan, path_offset, path_count, record_slot, out_dev, stride_path,
+                                 stride_time, stride_dim, transform, s, num_slots, column_sums_dev)
+             : run_paths<float>(plan, path_offset, path_count, record_slot, out_dev, stride_path,
+                                stride_time, stride_dim, transform, s, num_slots, column_sums_dev);
 }
 
 }  // extern "C"

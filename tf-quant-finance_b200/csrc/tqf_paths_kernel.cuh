@@ -90,6 +90,10 @@ struct KParams {
   Real* out;
   int64_t stride_path, stride_time, stride_dim;
   int store_exp;             // store exp(state) (log-space models feeding LSM)
+  // optional column sums of the stored values (the basis-centring means of the
+  // Longstaff-Schwartz passes, lsm.py:110-111, for free while the paths are written)
+  double* colsum_partials;   // device [gridDim.x][colsum_cols] or null
+  int colsum_cols;           // number of time slots * DIM
 };
 
 // ------------------------------------------------------------- models -----
@@ -491,6 +495,7 @@ path_kernel(const KParams<typename Model::Real> P) {
   uint4* s_low = reinterpret_cast<uint4*>(smem_raw + off);
   if (RNGK == RNGK_SOBOL) off += static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   double* s_acc = reinterpret_cast<double*>(smem_raw + off);
+  double* s_col = s_acc + kWarps * TQF_MAX_PAYOFFS * 3;   // [kWarps][colsum_cols]
 
   const int tid = threadIdx.x;
   if (kLogTab) fm::fill_smem_logtab(s_logtab, P.logtab, tid, kBlock);
@@ -505,6 +510,8 @@ path_kernel(const KParams<typename Model::Real> P) {
   }
   if (MODE == MODE_PRICE) {
     for (int i = tid; i < kWarps * TQF_MAX_PAYOFFS * 3; i += kBlock) s_acc[i] = 0.0;
+  } else if (P.colsum_partials) {
+    for (int i = tid; i < kWarps * P.colsum_cols; i += kBlock) s_col[i] = 0.0;
   }
   __syncthreads();
 
@@ -558,21 +565,36 @@ path_kernel(const KParams<typename Model::Real> P) {
     PhiloxStreamV<Real, PPT> stream;
     if (RNGK == RNGK_PHILOX) stream.init(P.key, P.ctr, tab, first_element);
 
+    // Stores the state of every path of this thread into time slot `slot`.
+    auto store_slot = [&](int slot) {
+      double cs[DIM];
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) cs[j] = 0.0;
+#pragma unroll
+      for (int a = 0; a < PPT; ++a)
+        if (valid[a]) {
+#pragma unroll
+          for (int h = 0; h < NPATH; ++h)
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) {
+              const Real v = P.store_exp ? static_cast<Real>(exp(x[a][h][j])) : x[a][h][j];
+              P.out[static_cast<int64_t>(local[a] + h * P.anti_half) * P.stride_path +
+                    slot * P.stride_time + j * P.stride_dim] = v;
+              cs[j] += static_cast<double>(v);
+            }
+        }
+      if (P.colsum_partials) {
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) {
+          const double t = warp_sum(cs[j]);
+          if (lane == 0) s_col[warp * P.colsum_cols + slot * DIM + j] += t;
+        }
+      }
+    };
     if (MODE == MODE_PATHS) {
       const int slot = rec_tab[0];
-      if (slot >= 0) {
-#pragma unroll
-        for (int a = 0; a < PPT; ++a)
-          if (valid[a]) {
-#pragma unroll
-            for (int h = 0; h < NPATH; ++h)
-#pragma unroll
-              for (int j = 0; j < DIM; ++j)
-                P.out[static_cast<int64_t>(local[a] + h * P.anti_half) * P.stride_path +
-                      slot * P.stride_time + j * P.stride_dim] =
-                    P.store_exp ? static_cast<Real>(exp(x[a][h][j])) : x[a][h][j];
-          }
-      }
+      if (slot >= 0) store_slot(slot);
     }
 
     // Evaluates and reduces the payoffs attached to `step_index`.
@@ -738,20 +760,7 @@ path_kernel(const KParams<typename Model::Real> P) {
           }
           if (rec_next >= 0) eval_payoffs(s + 1);
         } else {
-          const int slot = rec_next;
-          if (slot >= 0) {
-#pragma unroll
-            for (int a = 0; a < PPT; ++a)
-              if (valid[a]) {
-#pragma unroll
-                for (int h = 0; h < NPATH; ++h)
-#pragma unroll
-                  for (int j = 0; j < DIM; ++j)
-                    P.out[static_cast<int64_t>(local[a] + h * P.anti_half) * P.stride_path +
-                          slot * P.stride_time + j * P.stride_dim] =
-                        P.store_exp ? static_cast<Real>(exp(x[a][h][j])) : x[a][h][j];
-              }
-          }
+          if (rec_next >= 0) store_slot(rec_next);
         }
       }
     }
@@ -767,6 +776,14 @@ path_kernel(const KParams<typename Model::Real> P) {
       const int q = i / 3, k = i - q * 3;
       P.partials[(static_cast<size_t>(blockIdx.x) * TQF_MAX_PAYOFFS + q) * 4 + k] = v;
     }
+  } else if (P.colsum_partials) {
+    __syncthreads();
+    for (int i = tid; i < P.colsum_cols; i += kBlock) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) v += s_col[w * P.colsum_cols + i];
+      P.colsum_partials[static_cast<size_t>(blockIdx.x) * P.colsum_cols + i] = v;
+    }
   }
 }
 
@@ -776,7 +793,7 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
 
 template <typename Real>
 size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool tables_in_smem,
-                        int ppt = kMaxPPT) {
+                        int ppt = kMaxPPT, int colsum_cols = 0) {
   size_t off = 0;
   if (tables_in_smem) {
     off = static_cast<size_t>(num_steps) * ncoef * sizeof(Real);
@@ -785,6 +802,7 @@ size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool table
   }
   if (rngk == RNGK_SOBOL) off += static_cast<size_t>(ppt) * kSobolTileDims * sizeof(uint32_t) + static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   off += static_cast<size_t>(kWarps) * TQF_MAX_PAYOFFS * 3 * sizeof(double);
+  off += static_cast<size_t>(kWarps) * colsum_cols * sizeof(double);
   if (rngk == RNGK_SOBOL && sizeof(Real) == 8)
     off += static_cast<size_t>(TQF_LOGTAB_COUNT) * 2 * sizeof(double);
   return off;
@@ -801,7 +819,8 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
     auto kern = path_kernel<Model, RK, AN, MD>;                                        \
     constexpr int ppt = PathsPerThread<Model, RK>::value;                              \
     const size_t smem = path_kernel_smem<typename Model::Real>(                        \
-        Model::NCOEF, P.num_steps, RK, MD, P.tables_in_smem != 0, ppt);                \
+        Model::NCOEF, P.num_steps, RK, MD, P.tables_in_smem != 0, ppt,                 \
+        P.colsum_partials ? P.colsum_cols : 0);                                        \
     const uint64_t num_super = (P.num_chunks + ppt - 1) / ppt;                         \
     int grid = static_cast<int>(num_super < static_cast<uint64_t>(max_grid)            \
                                     ? num_super : static_cast<uint64_t>(max_grid));    \

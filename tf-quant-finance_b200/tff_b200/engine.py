@@ -427,17 +427,29 @@ class Plan:
       pass
 
   def paths(self, record_slot, num_times, unit_offset=0, unit_count=None,
-            exp_transform=False, out=None):
+            exp_transform=False, out=None, column_sums=False):
     """States at the recorded steps: a `[rows, num_times, dim]` VIEW of a
     time-major `[num_times, dim, rows]` buffer (coalesced stores, no
     transpose).  rows = units (x2 for antithetic: partners follow).
-    `exp_transform` stores exp(state) (log-space models)."""
+    `exp_transform` stores exp(state) (log-space models).  `column_sums=True`
+    returns `(paths, sums)` with `sums` a float64 device tensor
+    `[num_times, dim]`, the sum over the rows of every stored value
+    (accumulated by the kernel that writes them); `least_square_mc(...,
+    column_sums=sums)` then skips its own pass over the paths."""
     unit_count = self.units - unit_offset if unit_count is None else unit_count
     rows = unit_count * (2 if self.rng.antithetic else 1)
     dim = self.spec.dim
     buf = _tensor.empty((num_times, dim, rows), self.dtype) if out is None else out
     assert tuple(buf.shape) == (num_times, dim, rows) and buf.is_contiguous()
     rec = np.ascontiguousarray(record_slot, dtype=np.int32)
+    if column_sums:
+      sums = torch.empty((num_times, dim), dtype=torch.float64, device=buf.device)
+      _lib.check(_lib.lib().tqf_plan_paths_sums(
+          self._handle, unit_offset, unit_count, rec.ctypes.data, buf.data_ptr(),
+          1, dim * rows, rows,
+          _lib.TRANSFORM_EXP if exp_transform else _lib.TRANSFORM_NONE,
+          num_times, sums.data_ptr(), _tensor.current_stream_ptr()))
+      return buf.permute(2, 0, 1), sums
     _lib.check(_lib.lib().tqf_plan_paths(
         self._handle, unit_offset, unit_count, rec.ctypes.data, buf.data_ptr(),
         1, dim * rows, rows,

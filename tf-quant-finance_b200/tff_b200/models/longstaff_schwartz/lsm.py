@@ -65,7 +65,7 @@ def _unpack_sums(sums, K, packed):
 def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
                     discount_factors=None, num_calibration_samples=None,
                     dtype=None, name=None, *, global_path_offset=0,
-                    all_reduce=None):
+                    all_reduce=None, column_sums=None):
   """Values Amercian style options using the LSM algorithm (`lsm.py:128-295`).
 
   Args are those of the reference; `exercise_times` are indices into the time
@@ -77,7 +77,10 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
 
   Extension for sharded paths: `global_path_offset` is the global index of the
   first local path and `all_reduce(tensor)` sums a device tensor in place over
-  the ranks (e.g. `torch.distributed.all_reduce`).
+  the ranks (e.g. `torch.distributed.all_reduce`).  `column_sums`: optional
+  float64 device tensor `[num_times, dim]` with the sums of `sample_paths` over
+  the (local) samples, as `engine.Plan.paths(..., column_sums=True)` returns
+  them; the pass that forms the basis-centring means is then skipped.
 
   Returns a numpy array `[batch_size]`.
   """
@@ -194,9 +197,15 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
     dev = x.device
     # column means over ALL samples (lsm.py:110-111)
     tidx = np.ascontiguousarray(ex_times, dtype=np.int32)
-    colsum = torch.zeros((B, T, dim), dtype=torch.float64, device=dev)
-    _lib.check(lib.tqf_lsm_column_sums(handle, tidx.ctypes.data, T,
-                                       colsum.data_ptr(), stream))
+    if column_sums is not None and not batched:
+      cs = column_sums.to(device=dev, dtype=torch.float64)
+      if cs.dim() != 2 or int(cs.shape[0]) != int(x.shape[-2]) or int(cs.shape[1]) != dim:
+        raise ValueError('column_sums must have shape [num_times, dim] of sample_paths')
+      colsum = cs[torch.as_tensor(ex_times, device=dev)].unsqueeze(0).expand(B, T, dim).contiguous()
+    else:
+      colsum = torch.zeros((B, T, dim), dtype=torch.float64, device=dev)
+      _lib.check(lib.tqf_lsm_column_sums(handle, tidx.ctypes.data, T,
+                                         colsum.data_ptr(), stream))
     count = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
     if all_reduce is not None:
       all_reduce(colsum)
