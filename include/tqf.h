@@ -321,6 +321,17 @@ int tqf_lsm_step(tqf_lsm* lsm, int do_update, int t_update, const double* mean_u
  * layout (K <= 6) only; TQF_ERR_UNSUPPORTED otherwise (solve on the host). */
 int tqf_lsm_solve(tqf_lsm* lsm, double* sums_dev, int reduce_partials, double rcond,
                   double* beta_dev, void* stream);
+/* Fused regression solve for the single-asset vectorised pass (dim 1,
+ * K <= 6, contiguous time-major paths, even path count): once set, every
+ * tqf_lsm_step that accumulates also reduces its per-CTA partials into
+ * sums_dev [B][27] and writes beta [B][K] for the accumulated date, from the
+ * last CTA to finish; the tqf_lsm_solve call that follows (same beta_dev)
+ * then returns without launching anything.  Steps served by the other kernels
+ * are unaffected.  ticket_dev: one zero-initialised uint32 in device memory.
+ * Single GPU only (the sums are not all-reduced).                          */
+int tqf_lsm_set_fused_solve(tqf_lsm* h, double rcond, double* sums_dev, double* beta_dev,
+                            uint32_t* ticket_dev);
+
 /* num_sums doubles per payoff.  Packed (K <= 6): the upper triangle of a 6 x 6
  * X'X row by row (21 entries) followed by 6 entries of X'y; otherwise X'X
  * [K][K] row-major followed by X'y [K]. */

@@ -61,6 +61,22 @@ def test_basket_price_matches_oracle(dtype):
   np.testing.assert_allclose(got, want, rtol=2e-5 if dtype == np.float32 else 1e-12)
 
 
+def test_c4_shape_252_steps_has_no_systematic_error():
+  # the C4 grid (252 steps, 64 assets, float32, Sobol): elementwise within the
+  # float32 tolerance AND the per-asset means within 2e-6 -- a rounding error
+  # common to all paths and steps (e.g. forming 1 + mu dt in float32) passes a
+  # 10-step test and shows up here as a 1e-4 shift of the means
+  dtype, dim, n = np.float32, 64, 512
+  tff, model, (odrift, ovol), x0 = _setup(dim, dtype)
+  kw = dict(num_samples=n, initial_state=x0, num_time_steps=252)
+  got = model.sample_paths_euler([1.0], random_type=tff.math.random.RandomType.SOBOL,
+                                 **kw).cpu().numpy()[:, 0, :].astype(np.float64)
+  want = oeuler.sample(dim, odrift, ovol, [1.0], random_type=odraws.RandomType.SOBOL,
+                       dtype=dtype, **kw)[:, 0, :].astype(np.float64)
+  np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6 * 100)
+  np.testing.assert_allclose(got.mean(axis=0), want.mean(axis=0), rtol=2e-6)
+
+
 def test_fp32_sobol_uniform_equal_to_one_gives_inf():
   # beyond 2^24 points a float32 Sobol uniform can round to 1.0 and
   # the reference's erfinv returns +inf; the engine reproduces and counts it.

@@ -55,6 +55,13 @@ struct LsmArgs {
   const Real* ev_tab;
   const Real* ratio_path;
   int slot_update, slot_acc;  // exercise-date slots of t_update / t_acc
+  // fused regression solve (vectorised single-asset kernel): the last CTA to
+  // finish reduces the partials into `sums_out` and writes beta for `t_acc`
+  unsigned int* ticket;       // device counter, zero between launches (null: not fused)
+  double* sums_out;           // [B][kLsmFastNS]
+  double* beta_out;           // [B][K]
+  double rcond;
+  int round_to_float;
 };
 
 template <typename Real>
@@ -348,6 +355,10 @@ template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
+template <int K>
+__device__ void lsm_solve_one(const double* __restrict__ sp, double rcond, int round_to_float,
+                              double* __restrict__ beta);
+
 // L2 residency: the merged state W (8 B per path) is read and written by every
 // pass while each path column is read by two consecutive passes only.  W is
 // tagged evict_last and the columns evict_first (streaming), so that for sample
@@ -498,6 +509,45 @@ __global__ void __launch_bounds__(kLsmBlock, 3) lsm_step_dim1_vec_kernel(const L
       if (src >= 0)
         for (int wi = 0; wi < kLsmBlock / 32; ++wi) v += s_red[wi][src];
       A.partials[(static_cast<size_t>(blockIdx.x) * A.batch + b) * kLsmFastNS + slot] = v;
+    }
+    if (A.ticket != nullptr) {
+      // last CTA done: reduce the per-CTA rows in a fixed order and solve -- the
+      // separate solve launch (and its launch latency) disappears from the
+      // date-to-date critical path
+      __shared__ bool s_last;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(A.ticket, 1u);
+        s_last = t == gridDim.x * gridDim.y - 1;
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        const int M = A.batch * kLsmFastNS, num_blocks = gridDim.x;
+        const volatile double* part = A.partials;
+        for (int m = warp; m < M; m += kLsmBlock / 32) {
+          double a8[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) a8[u] = 0.0;
+          int bk = lane;
+          for (; bk + 7 * 32 < num_blocks; bk += 8 * 32) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a8[u] += part[static_cast<size_t>(bk + u * 32) * M + m];
+          }
+          double tail = 0.0;
+          for (; bk < num_blocks; bk += 32) tail += part[static_cast<size_t>(bk) * M + m];
+          double v = (((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]))) + tail;
+          v = warp_sum(v);
+          if (lane == 0) A.sums_out[m] = v;
+        }
+        __syncthreads();
+        for (int bb = threadIdx.x; bb < A.batch; bb += kLsmBlock) {
+          lsm_solve_one<KT>(A.sums_out + static_cast<size_t>(bb) * kLsmFastNS, A.rcond,
+                            A.round_to_float, A.beta_out + static_cast<size_t>(bb) * KT);
+        }
+        if (threadIdx.x == 0) *A.ticket = 0u;
+      }
     }
   }
 }
@@ -865,6 +915,12 @@ struct tqf_lsm {
   int times_cap;
   bool external_w, external_partials;
   bool tabulated;                   // exercise values and / or per-path ratios given
+  // fused solve (tqf_lsm_set_fused_solve)
+  unsigned int* ticket_dev;
+  double* fused_sums_dev;
+  double* fused_beta_dev;
+  double fused_rcond;
+  bool last_step_solved;
   std::vector<int>* exercise_times; // slot -> time index (tabulated mode)
 };
 
@@ -949,6 +1005,15 @@ static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* 
       d.num_paths < (1ull << 32) && (reinterpret_cast<uintptr_t>(d.paths_dev) % (2 * esz)) == 0 &&
       (reinterpret_cast<uintptr_t>(h->w_dev) % (2 * esz)) == 0 && (d.stride_time % 2) == 0 &&
       (d.stride_batch % 2) == 0;
+  h->last_step_solved = false;
+  if (vec_ok && do_acc && h->ticket_dev != nullptr) {
+    A.ticket = h->ticket_dev;
+    A.sums_out = h->fused_sums_dev;
+    A.beta_out = h->fused_beta_dev;
+    A.rcond = h->fused_rcond;
+    A.round_to_float = d.dtype == TQF_F32 ? 1 : 0;
+    h->last_step_solved = true;
+  }
   if (vec_ok) {
     switch (K) {
       case 1: lsm_step_dim1_vec_kernel<Real, 1><<<grid, kLsmBlock, 0, s>>>(A); break;
@@ -1169,6 +1234,10 @@ int tqf_lsm_solve(tqf_lsm* h, double* sums_dev, int reduce_partials, double rcon
     set_error("device solve is implemented for basis sizes <= 6; solve on the host");
     return TQF_ERR_UNSUPPORTED;
   }
+  if (h->last_step_solved && beta_dev == h->fused_beta_dev) {
+    h->last_step_solved = false;   // the step kernel's last CTA already wrote beta
+    return TQF_OK;
+  }
   const int B = h->desc.batch;
   TQF_REQUIRE(!reduce_partials || B <= 128, "fused reduction supports up to 128 payoffs");
   if (reduce_partials) {
@@ -1180,6 +1249,20 @@ int tqf_lsm_solve(tqf_lsm* h, double* sums_dev, int reduce_partials, double rcon
         nullptr, 0, sums_dev, B, h->K, rcond, h->desc.dtype == TQF_F32 ? 1 : 0, beta_dev);
   }
   TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
+}
+
+int tqf_lsm_set_fused_solve(tqf_lsm* h, double rcond, double* sums_dev, double* beta_dev,
+                            uint32_t* ticket_dev) {
+  TQF_REQUIRE(h && sums_dev && beta_dev && ticket_dev, "null argument");
+  if (!h->fast) {
+    set_error("the fused solve is implemented for basis sizes <= 6");
+    return TQF_ERR_UNSUPPORTED;
+  }
+  h->ticket_dev = ticket_dev;
+  h->fused_sums_dev = sums_dev;
+  h->fused_beta_dev = beta_dev;
+  h->fused_rcond = rcond;
   return TQF_OK;
 }
 

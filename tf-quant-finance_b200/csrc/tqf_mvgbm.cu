@@ -986,12 +986,14 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
             for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
           ti += 4 - kt / 2;
         }
-        // acc_i = sum_j sigma_i L_ij z_j.  Euler: x_i' = x_i (1 + mu_i dt + sqrt_dt acc_i);
-        // exact log-normal increment: x_i' = x_i + (mu_i dt + sqrt_dt acc_i), mu = means - vols^2 / 2
+        // acc_i = sum_j sigma_i L_ij z_j.  Euler: x_i' = x_i + x_i (mu_i dt + sqrt_dt acc_i);
+        // exact log-normal increment: x_i' = x_i + (mu_i dt + sqrt_dt acc_i), mu = means - vols^2 / 2.
+        // (The relative increment is NOT merged into 1 + ...: rounding 1 + mu dt to
+        // float32 is the same error for every path and step, a 1e-4 bias of the price.)
         const float dt = P.coef[2 * s], sq = P.coef[2 * s + 1];
         float c1[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) c1[r] = P.exact_log ? mu[r] * dt : fmaf(mu[r], dt, 1.0f);
+        for (int r = 0; r < 8; ++r) c1[r] = mu[r] * dt;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -999,7 +1001,7 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float f = fmaf(sq, acc[mt][nt][e], c1[mt * 2 + (e >> 1)]);
-              x[mt][nt][e] = P.exact_log ? x[mt][nt][e] + f : x[mt][nt][e] * f;
+              x[mt][nt][e] = P.exact_log ? x[mt][nt][e] + f : fmaf(x[mt][nt][e], f, x[mt][nt][e]);
             }
         const int flag = P.record_slot[s + 1];
         if (flag >= 0) record(s + 1, flag);

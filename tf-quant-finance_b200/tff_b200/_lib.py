@@ -170,6 +170,8 @@ _SIGNATURES = {
     'tqf_lsm_destroy': (C.c_int, [C.c_void_p]),
     'tqf_lsm_column_sums':
         (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'tqf_lsm_set_fused_solve':
+        (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     'tqf_lsm_init': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'tqf_lsm_step':
         (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -233,6 +233,11 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
     # solve kernel (one launch less per date)
     fused = device_solve and all_reduce is None and B <= 128
     sums_arg = None if fused else sums.data_ptr()
+    if fused:
+      # the last CTA of each streaming pass reduces and solves (no solve launch)
+      ticket = torch.zeros((1,), dtype=torch.int32, device=dev)
+      _lib.check(lib.tqf_lsm_set_fused_solve(handle, rcond, sums.data_ptr(),
+                                             beta_dev.data_ptr(), ticket.data_ptr()))
     if e > 0:
       _lib.check(lib.tqf_lsm_step(handle, 0, 0, None, None, None, 1,
                                   int(ex_times[e - 1]), mean_ptr(e), ratio_ptr(e),
