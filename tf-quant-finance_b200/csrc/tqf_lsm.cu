@@ -359,6 +359,51 @@ template <int K>
 __device__ void lsm_solve_one(const double* __restrict__ sp, double rcond, int round_to_float,
                               double* __restrict__ beta);
 
+// Run by the last CTA of a fused pass: fixed-order reduction of the per-CTA
+// partial rows, then the K x K solve of every payoff.  Not inlined, so that the
+// solver's registers do not weigh on the streaming loop of the caller.
+template <int KT>
+__device__ __noinline__ void lsm_fused_tail(const double* partials, int batch, int num_blocks,
+                                            double* sums_out, double rcond, int round_to_float,
+                                            double* beta_out) {
+  // Thread t sums column m = t % 32 (m < M) of the rows r = t / 32, t / 32 + 8, ...
+  // with 14 independent L2 loads in flight (the rows were written by other SMs
+  // in this launch: read through L2), then the 8 row groups are combined in a
+  // fixed order -> reproducible sums.
+  const int M = batch * kLsmFastNS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ double s_part[kLsmBlock / 32][32];
+  constexpr int W = kLsmBlock / 32, U = 14;
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    const int m = m0 + lane;
+    double acc = 0.0;
+    if (m < M) {
+      int r = warp;
+      for (; r + (U - 1) * W < num_blocks; r += U * W) {
+        double ld[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) ld[u] = __ldcg(partials + static_cast<size_t>(r + u * W) * M + m);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += ld[u];
+      }
+      for (; r < num_blocks; r += W) acc += __ldcg(partials + static_cast<size_t>(r) * M + m);
+    }
+    s_part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && m < M) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) v += s_part[w][lane];
+      sums_out[m] = v;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int bb = threadIdx.x; bb < batch; bb += kLsmBlock)
+    lsm_solve_one<KT>(sums_out + static_cast<size_t>(bb) * kLsmFastNS, rcond, round_to_float,
+                      beta_out + static_cast<size_t>(bb) * KT);
+}
+
 // L2 residency: the merged state W (8 B per path) is read and written by every
 // pass while each path column is read by two consecutive passes only.  W is
 // tagged evict_last and the columns evict_first (streaming), so that for sample
@@ -524,28 +569,8 @@ __global__ void __launch_bounds__(kLsmBlock, 3) lsm_step_dim1_vec_kernel(const L
       __syncthreads();
       if (s_last) {
         __threadfence();
-        const int M = A.batch * kLsmFastNS, num_blocks = gridDim.x;
-        const volatile double* part = A.partials;
-        for (int m = warp; m < M; m += kLsmBlock / 32) {
-          double a8[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) a8[u] = 0.0;
-          int bk = lane;
-          for (; bk + 7 * 32 < num_blocks; bk += 8 * 32) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a8[u] += part[static_cast<size_t>(bk + u * 32) * M + m];
-          }
-          double tail = 0.0;
-          for (; bk < num_blocks; bk += 32) tail += part[static_cast<size_t>(bk) * M + m];
-          double v = (((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]))) + tail;
-          v = warp_sum(v);
-          if (lane == 0) A.sums_out[m] = v;
-        }
-        __syncthreads();
-        for (int bb = threadIdx.x; bb < A.batch; bb += kLsmBlock) {
-          lsm_solve_one<KT>(A.sums_out + static_cast<size_t>(bb) * kLsmFastNS, A.rcond,
-                            A.round_to_float, A.beta_out + static_cast<size_t>(bb) * KT);
-        }
+        lsm_fused_tail<KT>(A.partials, A.batch, gridDim.x, A.sums_out, A.rcond, A.round_to_float,
+                           A.beta_out);
         if (threadIdx.x == 0) *A.ticket = 0u;
       }
     }
@@ -904,7 +929,7 @@ using namespace tqf;
 
 struct tqf_lsm {
   tqf_lsm_desc desc;
-  int K, NS, grid;
+  int K, NS, grid, grid_aux;
   bool fast;
   void* w_dev;           // Real [B][N]
   int* exponents_dev;    // [K][dim]
@@ -1094,9 +1119,12 @@ int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
   int sms = kSMs;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   uint64_t blocks = (desc->num_paths + kLsmBlock - 1) / kLsmBlock;
-  // fast kernels: 3 CTAs of 256 threads resident per SM -> two full waves
-  const uint64_t cap = static_cast<uint64_t>(sms) * (h->fast ? 6 : 2);
+  // fast kernels: 3 CTAs of 256 threads resident per SM -> one full wave (and few partial rows)
+  const uint64_t cap = static_cast<uint64_t>(sms) * (h->fast ? 3 : 2);
   h->grid = static_cast<int>(blocks < cap ? (blocks ? blocks : 1) : cap);
+  // the one-load-per-iteration kernels (initial payoff, value sum) want more CTAs in flight
+  const uint64_t cap_aux = static_cast<uint64_t>(sms) * 8;
+  h->grid_aux = static_cast<int>(blocks < cap_aux ? (blocks ? blocks : 1) : cap_aux);
   const size_t esize = desc->dtype == TQF_F64 ? 8 : 4;
   cudaError_t e = cudaSuccess;
   if (desc->w_dev) {               // caller-owned workspace (framework allocator)
@@ -1189,7 +1217,7 @@ int tqf_lsm_column_sums(tqf_lsm* h, const int32_t* time_indices, int num_times, 
 int tqf_lsm_init(tqf_lsm* h, int time_index, void* stream) {
   TQF_REQUIRE(h, "null handle");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const dim3 grid(h->grid, h->desc.batch);
+  const dim3 grid(h->grid_aux, h->desc.batch);
   const int slot = h->tabulated ? slot_of(h, time_index) : 0;
   TQF_REQUIRE(slot >= 0, "time index is not one of exercise_time_indices");
   if (h->desc.dtype == TQF_F64) {
@@ -1277,9 +1305,9 @@ int tqf_lsm_value_sum(tqf_lsm* h, uint64_t skip_below, double* sums_dev, void* s
   TQF_REQUIRE(h && sums_dev, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const tqf_lsm_desc& d = h->desc;
-  int rc = ensure_partials(h, static_cast<size_t>(h->grid) * d.batch * 2);
+  int rc = ensure_partials(h, static_cast<size_t>(h->grid_aux) * d.batch * 2);
   if (rc != TQF_OK) return rc;
-  const dim3 grid(h->grid, d.batch);
+  const dim3 grid(h->grid_aux, d.batch);
   if (d.dtype == TQF_F64) {
     LsmArgs<double> A;
     fill_args(h, &A);
@@ -1291,7 +1319,7 @@ int tqf_lsm_value_sum(tqf_lsm* h, uint64_t skip_below, double* sums_dev, void* s
   }
   TQF_CUDA_OK(cudaGetLastError());
   const int M = d.batch * 2;
-  lsm_reduce_kernel<<<1, 128, 0, s>>>(h->partials_dev, h->grid, M, sums_dev);
+  lsm_reduce_kernel<<<1, 128, 0, s>>>(h->partials_dev, h->grid_aux, M, sums_dev);
   TQF_CUDA_OK(cudaGetLastError());
   return TQF_OK;
 }

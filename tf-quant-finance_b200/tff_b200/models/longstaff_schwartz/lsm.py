@@ -10,6 +10,8 @@ sums, after the all-reduce when paths are sharded over GPUs.
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 
@@ -233,7 +235,7 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
     # solve kernel (one launch less per date)
     fused = device_solve and all_reduce is None and B <= 128
     sums_arg = None if fused else sums.data_ptr()
-    if fused:
+    if fused and os.environ.get('TQF_LSM_FUSED_SOLVE', '1') != '0':
       # the last CTA of each streaming pass reduces and solves (no solve launch)
       ticket = torch.zeros((1,), dtype=torch.int32, device=dev)
       _lib.check(lib.tqf_lsm_set_fused_solve(handle, rcond, sums.data_ptr(),

@@ -21,8 +21,9 @@ df = np.exp(-r * times)
 put = lsm.make_basket_put_payoff([1.1], dtype=np.float64)
 basis = lsm.make_polynomial_basis(3)
 def one():
-  paths = plan.paths(record_slot, 50, 0, plan.units, exp_transform=True)
-  return lsm.least_square_mc(paths, np.arange(50), put, basis, discount_factors=df, dtype=np.float64)
+  paths, sums = plan.paths(record_slot, 50, 0, plan.units, exp_transform=True, column_sums=True)
+  return lsm.least_square_mc(paths, np.arange(50), put, basis, discount_factors=df, dtype=np.float64,
+                             column_sums=sums)
 for _ in range(3): one()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
