@@ -514,18 +514,18 @@ def run_gpu_c5(args):
         'config': {'workload': w['name'] if args.paths is None else w['name'] + ' [paths=%d]' % n,
                    'paths': n, 'euler_steps': steps, 'exercise_dates': 50,
                    'l2': 'inputs (3.2 GB of paths) exceed L2',
-                   'timing': 'wall clock around generation + LSM (49 dates: streaming pass + device '
-                             'pseudo-inverse each; device events: generation %.2f ms, LSM %.2f ms)'
+                   'timing': 'wall clock around generation + LSM (49 dates: one streaming pass each, the '
+                             'regression solved by its last CTA; device events: generation %.2f ms, LSM %.2f ms)'
                              % (gen, lsm_ms)},
         'prices': [float(price[0])], 'clocks': clocks,
         'e2e': {'value': n * steps / (wall_ms * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': 50 * 8 * 2 + 148 * 6 * 8, 'd2h_bytes_per_step': 16},
-        'gpu_launches': args.steps * (1 + 2 + 1 + 49 * 2 + 2),
+        'gpu_launches': args.steps * (2 + 1 + 50 + 2),   # paths + column-sum reduce, init, passes, value sum + reduce
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved / hbm_peak, 'traffic': None,
                      'note': 'LSM passes: 32 algorithmic bytes per path per exercise date (SURVEY 8d) '
-                             '/ time between the device events around least_square_mc (49 streaming '
-                             'passes, 49 device solves); peak = MEASURED_PEAKS.json hbm_gbs'},
+                             '/ time between the device events around least_square_mc (initial payoff, 50 streaming '
+                             'passes with fused solves, value sum); peak = MEASURED_PEAKS.json hbm_gbs'},
         'cpu_baseline': {'value': cv, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                          'sample': '%d paths x %d steps + LSM, single process numpy oracle (%.1f s)' % (cn, csteps, cdt)},
     }

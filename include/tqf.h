@@ -54,6 +54,12 @@ extern "C" {
 #define TQF_MODEL_LINEAR_1F 6     /* x' = A x + B + C z                      */
 #define TQF_MODEL_HW1F 7          /* HW exact OU step + short-rate integral  */
 #define TQF_MODEL_AFFINE_ND 8     /* a = a0 + A1 x, S = B, dim 2..4          */
+/* TQF_MODEL_AFFINE_1F with the pathwise tangents carried alongside the path
+ * (the forward-mode Jacobians of euler_sampling.py:393-402, 467-510 /
+ * math/custom_loops.py:20-215): state = [x, dx/dx0, dx/dtheta], coef columns
+ * dt, sqrt_dt, a0, a1, b0, b1, da0/dtheta, da1/dtheta, db0/dtheta, db1/dtheta;
+ * x0 = [x0, 1, 0].                                                          */
+#define TQF_MODEL_AFFINE_1F_TANGENT 9
 
 /* payoff kinds (reduced in-kernel; callers: e.g. hull_white/swaption.py:310) */
 #define TQF_PAYOFF_CALL 1          /* max(f(X_T) - K, 0)                    */
@@ -64,6 +70,10 @@ extern "C" {
 #define TQF_PAYOFF_DOWN_OUT_CALL 6
 #define TQF_PAYOFF_IDENTITY 7      /* f(X_T) (moments)                      */
 #define TQF_PAYOFF_HW_SWAPTION 8   /* hull_white/swaption.py:291-312        */
+/* pathwise derivative of the call / put payoff: 1{f > K} f'(X_T) T_T resp.
+ * -1{K > f} f'(X_T) T_T with T = state[tangent_component]                  */
+#define TQF_PAYOFF_CALL_TANGENT 9
+#define TQF_PAYOFF_PUT_TANGENT 10
 
 /* state transform applied before the payoff */
 #define TQF_TRANSFORM_NONE 0
@@ -178,7 +188,7 @@ typedef struct tqf_payoff_desc {
   int32_t kind;       /* TQF_PAYOFF_*                                       */
   int32_t component;  /* state component; -1 = arithmetic mean over dim     */
   int32_t transform;  /* TQF_TRANSFORM_*                                    */
-  int32_t reserved;
+  int32_t tangent_component; /* TQF_PAYOFF_*_TANGENT: state component of T   */
   double strike;
   double barrier;
   double scale;       /* multiplies the payoff (discount factor, notional)  */

@@ -53,6 +53,7 @@ static bool model_info(int kind, int dim, ModelInfo* info) {
   switch (kind) {
     case TQF_MODEL_MVGBM: *info = {dim, dim, 2}; return dim >= 1 && dim <= 64;
     case TQF_MODEL_AFFINE_1F: *info = {1, 1, 6}; return true;
+    case TQF_MODEL_AFFINE_1F_TANGENT: *info = {3, 1, 10}; return true;
     case TQF_MODEL_AFFINE_ND:
       *info = {dim, dim, 2 + dim + 2 * dim * dim};
       return dim >= 2 && dim <= 4;
@@ -149,6 +150,9 @@ static int dispatch(const tqf_plan* plan, int mode, int grid, size_t smem, const
   switch (plan->model.kind) {
     case TQF_MODEL_AFFINE_1F:
       return launch_path_kernel<AffineModel1F<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+    case TQF_MODEL_AFFINE_1F_TANGENT:
+      return launch_path_kernel<TangentAffine1FModel<Real>>(rk, anti, mode, grid, smem, P, stream,
+                                                            grid_out);
     case TQF_MODEL_GBM_1F:
       return launch_path_kernel<GbmModel1F<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     case TQF_MODEL_LINEAR_1F:
@@ -184,7 +188,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   std::vector<SwaptionK> swaptions;
   for (int q = 0; q < num_payoffs; ++q) {
     const tqf_payoff_desc& d = payoffs[q];
-    TQF_REQUIRE(d.kind >= TQF_PAYOFF_CALL && d.kind <= TQF_PAYOFF_HW_SWAPTION,
+    TQF_REQUIRE(d.kind >= TQF_PAYOFF_CALL && d.kind <= TQF_PAYOFF_PUT_TANGENT,
                 "unknown payoff kind");
     const int step = d.expiry_step > 0 ? d.expiry_step : S;
     TQF_REQUIRE(step <= S, "payoff expiry_step exceeds the number of steps");
@@ -217,7 +221,12 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
       TQF_REQUIRE(d.component >= 0 && d.component < plan->info.dim,
                   "payoff component out of range");
     }
-    P.pay[q] = PayoffK{d.kind, d.component, d.transform, step, d.strike, d.barrier, d.scale};
+    const bool is_tangent = d.kind == TQF_PAYOFF_CALL_TANGENT || d.kind == TQF_PAYOFF_PUT_TANGENT;
+    TQF_REQUIRE(!is_tangent || (plan->model.kind != TQF_MODEL_MVGBM && d.tangent_component >= 0 &&
+                                d.tangent_component < plan->info.dim),
+                "tangent_component out of range");
+    P.pay[q] = PayoffK{d.kind, d.component, d.transform, step, d.strike, d.barrier, d.scale,
+                       is_tangent ? d.tangent_component : 0};
     if (d.kind >= TQF_PAYOFF_UP_OUT_CALL && d.kind <= TQF_PAYOFF_DOWN_OUT_CALL) {
       TQF_REQUIRE(monitor < 0 || monitor == d.component,
                   "all barrier payoffs of one call must watch the same state component");

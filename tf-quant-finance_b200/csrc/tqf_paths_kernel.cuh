@@ -42,6 +42,7 @@ struct PayoffK {
   double strike;
   double barrier;
   double scale;
+  int32_t tangent;   // TQF_PAYOFF_*_TANGENT: state component of the tangent
 };
 
 // Device-side table of one Hull-White swaption payoff (TQF_PAYOFF_HW_SWAPTION):
@@ -144,6 +145,28 @@ struct AffineModelND {
 template <typename R> using AffineModel2D = AffineModelND<R, 2>;
 template <typename R> using AffineModel3D = AffineModelND<R, 3>;
 template <typename R> using AffineModel4D = AffineModelND<R, 4>;
+
+// AffineModel1F with its pathwise tangents (forward-mode sensitivities, the
+// Jacobian-carrying loop of euler_sampling.py:393-402 / custom_loops.py:20-215):
+//   y = dx/dx0:      y' = y + y (dt a1 + b1 dw)
+//   v = dx/dtheta:   v' = v + v (dt a1 + b1 dw) + dt (da0 + da1 x) + (db0 + db1 x) dw
+// with the PRE-step x on the right-hand sides (differentiating _euler_step).
+template <typename R>
+struct TangentAffine1FModel {
+  using Real = R;
+  static constexpr int DIM = 3, NF = 1, NCOEF = 10;
+  __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
+                                              const Real (&c)[NCOEF]) {
+    const Real dw = z[0] * c[1];
+    const Real xs = x[0];
+    const Real g = fma(c[5], dw, c[0] * c[3]);           // d(increment)/dx
+    const Real dt_inc = c[0] * (c[2] + c[3] * xs);
+    const Real dw_inc = (c[4] + c[5] * xs) * dw;
+    x[0] = (xs + dt_inc) + dw_inc;
+    x[2] = fma(x[2], g, x[2]) + (c[0] * (c[6] + c[7] * xs) + (c[8] + c[9] * xs) * dw);
+    x[1] = fma(x[1], g, x[1]);
+  }
+};
 
 template <typename R>
 struct GbmModel1F {  // a = mu x, S = sigma x  (univariate_geometric_brownian_motion.py:127-153)
@@ -393,15 +416,23 @@ __device__ __forceinline__ Real select_component(const Real (&v)[DIM], int comp)
 
 // ------------------------------------------------------------ payoffs -----
 __device__ __forceinline__ double eval_payoff(const PayoffK& d, double x_final, double x_max,
-                                              double x_min) {
+                                              double x_min, double tangent = 0.0) {
   double f = x_final, fmax = x_max, fmin = x_min;
   if (d.transform == TQF_TRANSFORM_EXP) {
     f = exp(f);
     fmax = exp(fmax);
     fmin = exp(fmin);
   }
+  // d f / d state: f itself for the exponential transform
+  const double fprime = d.transform == TQF_TRANSFORM_EXP ? f : 1.0;
   double v;
   switch (d.kind) {
+    case TQF_PAYOFF_CALL_TANGENT:
+      v = f - d.strike > 0.0 ? fprime * tangent : 0.0;
+      break;
+    case TQF_PAYOFF_PUT_TANGENT:
+      v = d.strike - f > 0.0 ? -(fprime * tangent) : 0.0;
+      break;
     case TQF_PAYOFF_CALL:
       v = f - d.strike > 0.0 ? f - d.strike : 0.0;
       break;
@@ -624,7 +655,10 @@ path_kernel(const KParams<typename Model::Real> P) {
                 const double xa = static_cast<double>(xmax[a][h]);
                 const double xi = static_cast<double>(xmin[a][h]);
                 const double xf = static_cast<double>(select_component<Real, DIM>(x[a][h], d.component));
-                v = eval_payoff(d, xf, xa, xi);
+                const double tg = (d.kind == TQF_PAYOFF_CALL_TANGENT || d.kind == TQF_PAYOFF_PUT_TANGENT)
+                                      ? static_cast<double>(select_component<Real, DIM>(x[a][h], d.tangent))
+                                      : 0.0;
+                v = eval_payoff(d, xf, xa, xi, tg);
               }
               if (isfinite(v)) {
                 sum += v;

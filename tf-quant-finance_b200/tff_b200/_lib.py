@@ -28,6 +28,7 @@ MODEL_MVGBM = 5
 MODEL_LINEAR_1F = 6
 MODEL_HW1F = 7
 MODEL_AFFINE_ND = 8
+MODEL_AFFINE_1F_TANGENT = 9
 PAYOFF_CALL = 1
 PAYOFF_PUT = 2
 PAYOFF_UP_OUT_CALL = 3
@@ -36,6 +37,8 @@ PAYOFF_UP_OUT_PUT = 5
 PAYOFF_DOWN_OUT_CALL = 6
 PAYOFF_IDENTITY = 7
 PAYOFF_HW_SWAPTION = 8
+PAYOFF_CALL_TANGENT = 9
+PAYOFF_PUT_TANGENT = 10
 TRANSFORM_NONE, TRANSFORM_EXP = 0, 1
 MAX_PAYOFFS = 8
 MAX_SWAPTION_PAYMENTS = 64
@@ -77,7 +80,7 @@ class PayoffDesc(C.Structure):
       ('kind', C.c_int32),
       ('component', C.c_int32),
       ('transform', C.c_int32),
-      ('reserved', C.c_int32),
+      ('tangent_component', C.c_int32),
       ('strike', C.c_double),
       ('barrier', C.c_double),
       ('scale', C.c_double),

@@ -60,6 +60,32 @@ class AffineSpec1F(ModelSpec):
     return np.stack(cols, -1).astype(np.float64)
 
 
+class TangentAffineSpec1F(ModelSpec):
+  """`AffineSpec1F` carrying the pathwise tangents `dX/dX0` and `dX/dtheta`
+  alongside the path: the forward-mode Jacobians the reference obtains with
+  `watch_params` (`euler_sampling.py:393-402, 467-510`,
+  `math/custom_loops.py:20-215`).  `theta` is one scalar parameter; `da0`,
+  `da1`, `db`, `db1` are the derivatives of the four coefficient functions with
+  respect to it (scalars or callables of an array of times).  The device state
+  is `[X, dX/dX0, dX/dtheta]`; the user-facing dimension stays 1 and the draws
+  are those of the plain 1-d process."""
+  kind, dim, num_factors, num_coef = _lib.MODEL_AFFINE_1F_TANGENT, 3, 1, 10
+  user_dim = 1
+  X, D_INITIAL, D_THETA = 0, 1, 2      # state components
+
+  def __init__(self, a0, a1, b, b1=0.0, da0=0.0, da1=0.0, db=0.0, db1=0.0):
+    self.p = (a0, a1, b, b1, da0, da1, db, db1)
+
+  def coef_table(self, all_times, dtype):
+    t, dt, sq = self._dt_columns(all_times, dtype)
+    cols = [dt, sq] + [_eval_param(q, t, dtype) for q in self.p]
+    return np.stack(cols, -1).astype(np.float64)
+
+  @staticmethod
+  def extend_initial_state(x0):
+    return np.concatenate([np.asarray(x0).reshape(-1)[:1], [1.0, 0.0]])
+
+
 class ProbedAffineSpec(ModelSpec):
   """An arbitrary Python (drift_fn, volatility_fn) pair that turns out to be
   affine: a(t, x) = a0(t) + A1(t) x and S(t, x) = B0(t) (+ B1(t) x for dim 1).
@@ -243,13 +269,15 @@ class Payoff:
   of the reference's callers, e.g. `hull_white/swaption.py:310-311`)."""
 
   def __init__(self, kind, strike=0.0, barrier=0.0, component=0, log_state=False,
-               scale=1.0):
+               scale=1.0, tangent=0):
     self.kind, self.strike, self.barrier = kind, float(strike), float(barrier)
     self.component, self.log_state, self.scale = int(component), bool(log_state), float(scale)
+    self.tangent = int(tangent)
 
   def desc(self):
     d = _lib.PayoffDesc()
     d.kind, d.component = self.kind, self.component
+    d.tangent_component = self.tangent
     d.transform = _lib.TRANSFORM_EXP if self.log_state else _lib.TRANSFORM_NONE
     d.strike, d.barrier, d.scale = self.strike, self.barrier, self.scale
     return d
@@ -281,6 +309,18 @@ def down_and_out_call(strike, barrier, **kw):
 
 def identity(**kw):
   return Payoff(_lib.PAYOFF_IDENTITY, **kw)
+
+
+def european_call_tangent(strike, tangent, **kw):
+  """Pathwise derivative of `european_call`: `1{f > K} f'(X_T) T_T`, with `T`
+  the state component `tangent` of a tangent-carrying model
+  (`TangentAffineSpec1F.D_INITIAL` -> delta-like, `.D_THETA` -> vega-like)."""
+  return Payoff(_lib.PAYOFF_CALL_TANGENT, strike=strike, tangent=tangent, **kw)
+
+
+def european_put_tangent(strike, tangent, **kw):
+  """Pathwise derivative of `european_put`: `-1{K > f} f'(X_T) T_T`."""
+  return Payoff(_lib.PAYOFF_PUT_TANGENT, strike=strike, tangent=tangent, **kw)
 
 
 # ----------------------------------------------------------- record plan ----

@@ -87,6 +87,27 @@ def affine_closures(a0, a1, b, b1=0.0):
   return DeviceClosure(spec, 'drift', drift), DeviceClosure(spec, 'volatility', vol)
 
 
+def affine_tangent_closures(a0, a1, b, b1=0.0, da0=0.0, da1=0.0, db=0.0, db1=0.0):
+  """`affine_closures` whose sampler also carries the pathwise tangents
+  `dX/dX0` and `dX/dtheta` (the reference's `watch_params` route,
+  `euler_sampling.py:393-402`): `sample` then returns `[N, k, 3]` with the
+  components `[X, dX/dX0, dX/dtheta]`, `price` accepts the `*_tangent` payoffs.
+  `da0 .. db1` are the derivatives of `a0 .. b1` with respect to the watched
+  scalar parameter `theta`.  Log-space GBM of the Monte-Carlo notebook
+  (`Monte_Carlo_Euler_Scheme.ipynb` cells 22-28), theta = sigma:
+  `affine_tangent_closures(r - sigma**2 / 2, 0, sigma, da0=-sigma, db=1)`."""
+  spec = engine.TangentAffineSpec1F(a0, a1, b, b1, da0, da1, db, db1)
+
+  def drift(t, x):
+    x = _as_tensor(x)
+    return _p(a0, t, x) + _p(a1, t, x) * x
+
+  def vol(t, x):
+    x = _as_tensor(x)
+    return (_p(b, t, x) + _p(b1, t, x) * x).unsqueeze(-1)
+  return DeviceClosure(spec, 'drift', drift), DeviceClosure(spec, 'volatility', vol)
+
+
 def gbm_closures(mean, volatility):
   """(drift_fn, volatility_fn) of dX = mean(t) X dt + volatility(t) X dW."""
   spec = engine.GbmSpec1F(mean, volatility)

@@ -27,8 +27,11 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
   """Argument normalisation of `sample` (`euler_sampling.py:232-310`)."""
   if watch_params is not None:
     raise NotImplementedError(
-        '`watch_params` (pathwise Greeks through custom_loops.for_loop) is not '
-        'implemented by the B200 engine yet (SURVEY 8f-3).')
+        '`watch_params` relies on TensorFlow differentiating Python closures. The '
+        'B200 engine carries the pathwise tangents in-kernel for the 1-d affine '
+        'family instead: build the closures with '
+        'closures.affine_tangent_closures(..., da0=, da1=, db=, db1=) and read '
+        'dX/dX0, dX/dtheta from the extra state components (SURVEY 8f-3).')
   dtype = _tensor.infer_dtype(times, dtype)
   times = _tensor.to_numpy(times, dtype).reshape(-1)
   if tolerance is None:
@@ -81,9 +84,12 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
     raise NotImplementedError(
         'batched `normal_draws` are not implemented by the B200 engine yet.')
   spec = closures.resolve_spec(drift_fn, volatility_fn, dim)
-  if spec.dim != dim:
+  if getattr(spec, 'user_dim', spec.dim) != dim:
     raise ValueError('`dim` is {} but the model has dimension {}'.format(
-        dim, spec.dim))
+        dim, getattr(spec, 'user_dim', spec.dim)))
+  if hasattr(spec, 'extend_initial_state') and (batch_shape or normal_draws is not None):
+    raise NotImplementedError(
+        'tangent-carrying closures support neither batched processes nor normal_draws yet')
   num_steps, record_slot = engine.record_plan(keep_mask, times.shape[0])
   num_samples = int(num_samples)
   # one plan per element of the batch of processes (a single one without batch)
@@ -104,7 +110,8 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
     stride, offset = (batch_size, bi) if antithetic else (1, bi * num_samples)
     rng = engine.RngSpec(random_type, seed, skip, normal_draws, unit_stride=stride,
                          unit_offset=offset)
-    plans.append(engine.Plan(spec_b, all_times, num_steps, x0[0], rng, num_samples, dtype))
+    x0_plan = spec_b.extend_initial_state(x0[0]) if hasattr(spec_b, 'extend_initial_state') else x0[0]
+    plans.append(engine.Plan(spec_b, all_times, num_steps, x0_plan, rng, num_samples, dtype))
   return plans, record_slot, times.shape[0], batch_shape
 
 
