@@ -452,6 +452,13 @@ def run_gpu_c5(args):
   put = lsm.make_basket_put_payoff([1.1], dtype=np.float64)
   basis = lsm.make_polynomial_basis(3)
   reduce_fn = (lambda t: dist.all_reduce(t)) if world > 1 else None
+  # several GPUs: the per-date normal equations are summed over the ranks inside
+  # the streaming kernel through peer memory (NVLink); NCCL only carries the
+  # column sums and the final value sum
+  px = None
+  if world > 1:
+    from tff_b200 import distributed
+    px = distributed.PeerExchange()
   stream = torch.cuda.current_stream()
   times_ms = {'gen': 0.0, 'lsm': 0.0}
 
@@ -466,7 +473,7 @@ def run_gpu_c5(args):
     # index only matters for num_calibration_samples (unused here)
     price = lsm.least_square_mc(paths, np.arange(50), put, basis, discount_factors=df,
                                 dtype=np.float64, global_path_offset=2 * lo,
-                                all_reduce=reduce_fn, column_sums=csums)
+                                all_reduce=reduce_fn, column_sums=csums, peer_exchange=px)
     e2.record(stream)
     if timed:
       torch.cuda.synchronize()
@@ -531,6 +538,8 @@ def run_gpu_c5(args):
     }
     print(json.dumps(line))
   plan.close()
+  if px is not None:
+    px.close()
   if world > 1:
     dist.destroy_process_group()
 

@@ -342,6 +342,36 @@ int tqf_lsm_solve(tqf_lsm* lsm, double* sums_dev, int reduce_partials, double rc
 int tqf_lsm_set_fused_solve(tqf_lsm* h, double rcond, double* sums_dev, double* beta_dev,
                             uint32_t* ticket_dev);
 
+/* 1 when the fused pass (tqf_lsm_set_fused_solve) applies to this handle. */
+int tqf_lsm_fused_eligible(const tqf_lsm* h, int* eligible);
+
+/* Multi-GPU (one process per GPU of ONE box): the reduced normal equations of
+ * every exercise date are summed over the ranks INSIDE the tail of the fused
+ * pass, by peer stores / flags over NVLink -- replaces the per-date
+ * ncclAllReduce of K^2 + K doubles (lsm.py:369-377 computes lhs and
+ * rhs per date).  Every rank adds the contributions in rank order, so all ranks
+ * solve from bit-identical sums.
+ *   bufs[r]: the exchange buffer of rank r (tqf_lsm_peer_bytes() bytes, zeroed
+ *     once, allocated with tqf_peer_alloc by its owner and mapped here with
+ *     tqf_peer_open), r = 0 .. world-1, world <= 8, batch <= 16;
+ *   epoch_base: number of exchanges already performed on these buffers -- the
+ *     same on every rank; read it back with tqf_lsm_peer_epoch after the call.
+ * Requires tqf_lsm_set_fused_solve and tqf_lsm_fused_eligible on EVERY rank
+ * (all ranks must take the same route).  A peer that does not arrive within
+ * ~10 s poisons the sums with NaN instead of hanging the device.           */
+int tqf_lsm_peer_bytes(uint64_t* bytes);
+int tqf_lsm_set_peer_exchange(tqf_lsm* h, int rank, int world, void* const* bufs,
+                              uint64_t epoch_base);
+int tqf_lsm_peer_epoch(const tqf_lsm* h, uint64_t* epoch);
+
+/* Peer-visible device memory (CUDA IPC): alloc + export on the owner, open /
+ * close on the other processes of the box, free on the owner.              */
+int tqf_peer_alloc(uint64_t bytes, void** dev_ptr, uint8_t ipc_handle[64]);
+int tqf_peer_open(const uint8_t ipc_handle[64], void** dev_ptr);
+int tqf_peer_close(void* dev_ptr);
+int tqf_peer_free(void* dev_ptr);
+
+
 /* num_sums doubles per payoff.  Packed (K <= 6): the upper triangle of a 6 x 6
  * X'X row by row (21 entries) followed by 6 entries of X'y; otherwise X'X
  * [K][K] row-major followed by X'y [K]. */

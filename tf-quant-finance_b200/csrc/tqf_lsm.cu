@@ -27,6 +27,14 @@ constexpr int kLsmFastNS = kLsmFastK * (kLsmFastK + 1) / 2 + kLsmFastK;  // 27
 constexpr int kLsmMaxDim = 8;
 constexpr int kLsmMaxK = 128;
 constexpr int kLsmTile = 32;   // paths per tile of the generic path
+// Peer exchange buffer of one rank: flags uint64 [2][kLsmMaxPeers] (a 128-byte
+// line per parity), then sums double [2][kLsmMaxPeers][kLsmPeerMaxSums].
+constexpr int kLsmMaxPeers = 8;
+constexpr int kLsmPeerMaxBatch = 16;
+constexpr int kLsmPeerMaxSums = kLsmPeerMaxBatch * 27;
+constexpr size_t kLsmPeerFlagBytes = 2 * 128;
+constexpr size_t kLsmPeerBytes =
+    kLsmPeerFlagBytes + 2ull * kLsmMaxPeers * kLsmPeerMaxSums * sizeof(double);
 
 template <typename Real>
 struct LsmArgs {
@@ -62,6 +70,11 @@ struct LsmArgs {
   double* beta_out;           // [B][K]
   double rcond;
   int round_to_float;
+  // exchange of the reduced sums between the GPUs of one box through peer
+  // memory (NVLink), inside the same tail -- no NCCL call per exercise date
+  int peer_rank, peer_world;            // peer_world <= 1: single GPU
+  unsigned long long peer_epoch;        // strictly increasing launch number, equal on all ranks
+  unsigned char* peer_bufs[kLsmMaxPeers];  // exchange buffer of every rank, mapped here
 };
 
 template <typename Real>
@@ -362,10 +375,66 @@ __device__ void lsm_solve_one(const double* __restrict__ sp, double rcond, int r
 // Run by the last CTA of a fused pass: fixed-order reduction of the per-CTA
 // partial rows, then the K x K solve of every payoff.  Not inlined, so that the
 // solver's registers do not weigh on the streaming loop of the caller.
-template <int KT>
-__device__ __noinline__ void lsm_fused_tail(const double* partials, int batch, int num_blocks,
-                                            double* sums_out, double rcond, int round_to_float,
-                                            double* beta_out) {
+__device__ __forceinline__ unsigned long long* peer_flag(unsigned char* buf, int parity, int src) {
+  return reinterpret_cast<unsigned long long*>(buf + parity * 128) + src;
+}
+__device__ __forceinline__ double* peer_sums(unsigned char* buf, int parity, int src) {
+  return reinterpret_cast<double*>(buf + kLsmPeerFlagBytes) +
+         (static_cast<size_t>(parity) * kLsmMaxPeers + src) * kLsmPeerMaxSums;
+}
+
+// All-reduce of the M local sums over the ranks of one box, executed by the
+// tail CTA of every rank: each rank stores its sums into slot [parity][rank] of
+// EVERY rank's buffer (peer stores over NVLink), fences, raises its flag there
+// (st.release.sys) and waits for the flags of all ranks in its own buffer
+// (ld.acquire.sys); then every rank adds the slots in rank order -- the same
+// order everywhere, so all ranks solve from bit-identical sums.  Slots are
+// double-buffered by the parity of the epoch: a rank cannot run two exchanges
+// ahead of another one, because each exchange needs every rank's flag.
+// Returns false when a peer did not arrive within ~10 s (the sums are then
+// poisoned with NaN instead of hanging the GPU).
+template <typename Args>
+__device__ __forceinline__ bool lsm_peer_all_reduce(const Args& A, double* sums, int M) {
+  __shared__ int s_timeout;
+  const int parity = static_cast<int>(A.peer_epoch & 1ull);
+  if (threadIdx.x == 0) s_timeout = 0;
+  for (int i = threadIdx.x; i < A.peer_world * M; i += blockDim.x) {
+    const int r = i / M, m = i - r * M;
+    peer_sums(A.peer_bufs[r], parity, A.peer_rank)[m] = sums[m];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < A.peer_world) {
+    unsigned long long* remote = peer_flag(A.peer_bufs[threadIdx.x], parity, A.peer_rank);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(remote), "l"(A.peer_epoch) : "memory");
+    const unsigned long long* mine = peer_flag(A.peer_bufs[A.peer_rank], parity, threadIdx.x);
+    const long long t0 = clock64();
+    unsigned long long seen = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+      if (seen >= A.peer_epoch) break;
+      if (clock64() - t0 > 20000000000ll) {
+        s_timeout = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const bool ok = s_timeout == 0;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    double v = 0.0;
+    for (int r = 0; r < A.peer_world; ++r)
+      v += *reinterpret_cast<volatile double*>(peer_sums(A.peer_bufs[A.peer_rank], parity, r) + m);
+    sums[m] = ok ? v : __longlong_as_double(0x7ff8000000000000ll);
+  }
+  __syncthreads();
+  return ok;
+}
+
+template <int KT, typename Args>
+__device__ __noinline__ void lsm_fused_tail(const Args& A, const double* partials, int batch,
+                                            int num_blocks, double* sums_out, double rcond,
+                                            int round_to_float, double* beta_out) {
   // Thread t sums column m = t % 32 (m < M) of the rows r = t / 32, t / 32 + 8, ...
   // with 14 independent L2 loads in flight (the rows were written by other SMs
   // in this launch: read through L2), then the 8 row groups are combined in a
@@ -399,6 +468,7 @@ __device__ __noinline__ void lsm_fused_tail(const double* partials, int batch, i
     __syncthreads();
   }
   __syncthreads();
+  if (A.peer_world > 1) lsm_peer_all_reduce(A, sums_out, M);
   for (int bb = threadIdx.x; bb < batch; bb += kLsmBlock)
     lsm_solve_one<KT>(sums_out + static_cast<size_t>(bb) * kLsmFastNS, rcond, round_to_float,
                       beta_out + static_cast<size_t>(bb) * KT);
@@ -569,8 +639,8 @@ __global__ void __launch_bounds__(kLsmBlock, 3) lsm_step_dim1_vec_kernel(const L
       __syncthreads();
       if (s_last) {
         __threadfence();
-        lsm_fused_tail<KT>(A.partials, A.batch, gridDim.x, A.sums_out, A.rcond, A.round_to_float,
-                           A.beta_out);
+        lsm_fused_tail<KT>(A, A.partials, A.batch, gridDim.x, A.sums_out, A.rcond,
+                           A.round_to_float, A.beta_out);
         if (threadIdx.x == 0) *A.ticket = 0u;
       }
     }
@@ -946,6 +1016,10 @@ struct tqf_lsm {
   double* fused_beta_dev;
   double fused_rcond;
   bool last_step_solved;
+  // peer exchange (tqf_lsm_set_peer_exchange)
+  int peer_rank, peer_world;
+  unsigned long long peer_epoch;
+  unsigned char* peer_bufs[kLsmMaxPeers];
   std::vector<int>* exercise_times; // slot -> time index (tabulated mode)
 };
 
@@ -995,6 +1069,17 @@ static int ensure_partials(tqf_lsm* h, size_t doubles) {
   return TQF_OK;
 }
 
+// The vectorised single-asset kernel (the one with the fused solve) applies.
+static bool lsm_vec_ok(const tqf_lsm* h) {
+  const tqf_lsm_desc& d = h->desc;
+  const size_t esz = d.dtype == TQF_F64 ? 8 : 4;
+  return !h->tabulated && h->fast && d.dim == 1 && d.stride_path == 1 && (d.num_paths % 2) == 0 &&
+         d.num_paths > 0 && d.num_paths < (1ull << 32) &&
+         (reinterpret_cast<uintptr_t>(d.paths_dev) % (2 * esz)) == 0 &&
+         (reinterpret_cast<uintptr_t>(h->w_dev) % (2 * esz)) == 0 && (d.stride_time % 2) == 0 &&
+         (d.stride_batch % 2) == 0;
+}
+
 template <typename Real>
 static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* mean_update,
                          const double* beta, const double* ratio_update, int do_acc, int t_acc,
@@ -1024,12 +1109,7 @@ static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* 
   if (rc != TQF_OK) return rc;
   A.partials = h->partials_dev;
   const dim3 grid(h->grid, B);
-  const size_t esz = sizeof(Real);
-  const bool vec_ok =
-      !h->tabulated && h->fast && d.dim == 1 && d.stride_path == 1 && (d.num_paths % 2) == 0 &&
-      d.num_paths < (1ull << 32) && (reinterpret_cast<uintptr_t>(d.paths_dev) % (2 * esz)) == 0 &&
-      (reinterpret_cast<uintptr_t>(h->w_dev) % (2 * esz)) == 0 && (d.stride_time % 2) == 0 &&
-      (d.stride_batch % 2) == 0;
+  const bool vec_ok = lsm_vec_ok(h);
   h->last_step_solved = false;
   if (vec_ok && do_acc && h->ticket_dev != nullptr) {
     A.ticket = h->ticket_dev;
@@ -1038,6 +1118,12 @@ static int lsm_step_impl(tqf_lsm* h, int do_update, int t_update, const double* 
     A.rcond = h->fused_rcond;
     A.round_to_float = d.dtype == TQF_F32 ? 1 : 0;
     h->last_step_solved = true;
+    A.peer_rank = h->peer_rank;
+    A.peer_world = h->peer_world;
+    if (h->peer_world > 1) {
+      A.peer_epoch = ++h->peer_epoch;
+      for (int r = 0; r < h->peer_world; ++r) A.peer_bufs[r] = h->peer_bufs[r];
+    }
   }
   if (vec_ok) {
     switch (K) {
@@ -1291,6 +1377,78 @@ int tqf_lsm_set_fused_solve(tqf_lsm* h, double rcond, double* sums_dev, double* 
   h->fused_sums_dev = sums_dev;
   h->fused_beta_dev = beta_dev;
   h->fused_rcond = rcond;
+  return TQF_OK;
+}
+
+int tqf_lsm_fused_eligible(const tqf_lsm* h, int* eligible) {
+  TQF_REQUIRE(h && eligible, "null argument");
+  *eligible = lsm_vec_ok(h) ? 1 : 0;
+  return TQF_OK;
+}
+
+int tqf_lsm_peer_bytes(uint64_t* bytes) {
+  TQF_REQUIRE(bytes, "null argument");
+  *bytes = kLsmPeerBytes;
+  return TQF_OK;
+}
+
+int tqf_lsm_set_peer_exchange(tqf_lsm* h, int rank, int world, void* const* bufs,
+                              uint64_t epoch_base) {
+  TQF_REQUIRE(h && bufs, "null argument");
+  TQF_REQUIRE(world >= 1 && world <= kLsmMaxPeers && rank >= 0 && rank < world,
+              "peer exchange supports up to 8 ranks");
+  TQF_REQUIRE(h->desc.batch <= kLsmPeerMaxBatch, "peer exchange supports up to 16 payoffs");
+  TQF_REQUIRE(h->ticket_dev != nullptr, "call tqf_lsm_set_fused_solve first");
+  TQF_REQUIRE(lsm_vec_ok(h), "the fused pass does not apply to this problem (tqf_lsm_fused_eligible)");
+  h->peer_rank = rank;
+  h->peer_world = world;
+  h->peer_epoch = epoch_base;
+  for (int r = 0; r < world; ++r) {
+    TQF_REQUIRE(bufs[r] != nullptr, "null peer buffer");
+    h->peer_bufs[r] = static_cast<unsigned char*>(bufs[r]);
+  }
+  return TQF_OK;
+}
+
+int tqf_lsm_peer_epoch(const tqf_lsm* h, uint64_t* epoch) {
+  TQF_REQUIRE(h && epoch, "null argument");
+  *epoch = h->peer_epoch;
+  return TQF_OK;
+}
+
+/* Peer-visible device memory of one box (CUDA IPC). */
+int tqf_peer_alloc(uint64_t bytes, void** dev_ptr, uint8_t ipc_handle[64]) {
+  TQF_REQUIRE(dev_ptr && ipc_handle && bytes > 0, "bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  void* p = nullptr;
+  TQF_CUDA_OK(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t hnd;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hnd, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return cuda_fail(e, "tqf_peer_alloc");
+  }
+  std::memcpy(ipc_handle, &hnd, 64);
+  *dev_ptr = p;
+  return TQF_OK;
+}
+
+int tqf_peer_open(const uint8_t ipc_handle[64], void** dev_ptr) {
+  TQF_REQUIRE(dev_ptr && ipc_handle, "null argument");
+  cudaIpcMemHandle_t hnd;
+  std::memcpy(&hnd, ipc_handle, 64);
+  TQF_CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+  return TQF_OK;
+}
+
+int tqf_peer_close(void* dev_ptr) {
+  if (dev_ptr) TQF_CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+  return TQF_OK;
+}
+
+int tqf_peer_free(void* dev_ptr) {
+  if (dev_ptr) TQF_CUDA_OK(cudaFree(dev_ptr));
   return TQF_OK;
 }
 

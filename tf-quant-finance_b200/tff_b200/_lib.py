@@ -175,6 +175,15 @@ _SIGNATURES = {
         (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'tqf_lsm_set_fused_solve':
         (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'tqf_lsm_fused_eligible': (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    'tqf_lsm_peer_bytes': (C.c_int, [C.POINTER(C.c_uint64)]),
+    'tqf_lsm_set_peer_exchange':
+        (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_uint64]),
+    'tqf_lsm_peer_epoch': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    'tqf_peer_alloc': (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]),
+    'tqf_peer_open': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    'tqf_peer_close': (C.c_int, [C.c_void_p]),
+    'tqf_peer_free': (C.c_int, [C.c_void_p]),
     'tqf_lsm_init': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'tqf_lsm_step':
         (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

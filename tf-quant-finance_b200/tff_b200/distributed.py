@@ -9,9 +9,13 @@ anything from another one until the reduction: one all-reduce of the
 `torch.distributed`), plus, for Longstaff-Schwartz, the column sums and one
 `K^2 + K` block per exercise date.
 """
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+from tff_b200 import _lib
 
 
 def world():
@@ -57,3 +61,56 @@ def paths_sharded(plan, record_slot, num_times, exp_transform=False):
   the global index of its first unit."""
   lo, count = shard_units(plan.units)
   return plan.paths(record_slot, num_times, lo, count, exp_transform), lo
+
+
+class PeerExchange:
+  """Exchange buffers of the ranks of one box, mapped into every process (CUDA
+  IPC over NVLink peer access).  `least_square_mc(..., peer_exchange=px)` then
+  sums the per-date normal equations over the ranks inside the tail of its
+  streaming kernel instead of calling NCCL once per exercise date.
+
+  Collective: construct and `close()` on all ranks of `group` together, after
+  `torch.cuda.set_device`.  At most 8 ranks, one per GPU (or several processes
+  sharing a GPU, which time-slice)."""
+
+  def __init__(self, group=None):
+    self.group = group
+    self.rank = dist.get_rank(group)
+    self.world = dist.get_world_size(group)
+    if self.world > 8:
+      raise ValueError('PeerExchange supports at most 8 ranks (one box)')
+    lib = _lib.lib()
+    _lib.require_cuda()
+    nbytes = C.c_uint64()
+    _lib.check(lib.tqf_lsm_peer_bytes(C.byref(nbytes)))
+    own = C.c_void_p()
+    handle = C.create_string_buffer(64)
+    _lib.check(lib.tqf_peer_alloc(nbytes.value, C.byref(own), handle))
+    self._own = own
+    handles = [None] * self.world
+    dist.all_gather_object(handles, handle.raw, group=group)
+    self._opened = []
+    ptrs = []
+    for r, h in enumerate(handles):
+      if r == self.rank:
+        ptrs.append(own.value)
+        continue
+      p = C.c_void_p()
+      _lib.check(lib.tqf_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
+      self._opened.append(p)
+      ptrs.append(p.value)
+    self.ptrs = (C.c_void_p * self.world)(*ptrs)
+    self.epoch = 0          # exchanges performed so far (equal on all ranks)
+    dist.barrier(group=group)
+
+  def close(self):
+    if getattr(self, '_own', None) is None:
+      return
+    torch.cuda.synchronize()
+    dist.barrier(group=self.group)       # nobody still writes into a peer
+    lib = _lib.lib()
+    for p in self._opened:
+      lib.tqf_peer_close(p)
+    dist.barrier(group=self.group)
+    lib.tqf_peer_free(self._own)
+    self._own, self._opened = None, []

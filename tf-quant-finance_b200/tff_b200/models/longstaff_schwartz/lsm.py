@@ -67,7 +67,7 @@ def _unpack_sums(sums, K, packed):
 def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
                     discount_factors=None, num_calibration_samples=None,
                     dtype=None, name=None, *, global_path_offset=0,
-                    all_reduce=None, column_sums=None):
+                    all_reduce=None, column_sums=None, peer_exchange=None):
   """Values Amercian style options using the LSM algorithm (`lsm.py:128-295`).
 
   Args are those of the reference; `exercise_times` are indices into the time
@@ -83,6 +83,10 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
   float64 device tensor `[num_times, dim]` with the sums of `sample_paths` over
   the (local) samples, as `engine.Plan.paths(..., column_sums=True)` returns
   them; the pass that forms the basis-centring means is then skipped.
+  `peer_exchange`: a `tff_b200.distributed.PeerExchange` of the ranks that
+  `all_reduce` spans; the per-date normal equations are then summed over the
+  ranks inside the streaming kernel (peer memory over NVLink) and `all_reduce`
+  is only called for the column sums and the final value sum.
 
   Returns a numpy array `[batch_size]`.
   """
@@ -234,18 +238,31 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
     # single rank + device solve: the per-CTA partials are reduced inside the
     # solve kernel (one launch less per date)
     fused = device_solve and all_reduce is None and B <= 128
+    use_peers = False
+    if (device_solve and all_reduce is not None and peer_exchange is not None and B <= 16
+        and os.environ.get('TQF_LSM_PEER_EXCHANGE', '1') != '0'):
+      # every rank must take the same route: the fused pass has to apply everywhere
+      ok = C.c_int()
+      _lib.check(lib.tqf_lsm_fused_eligible(handle, C.byref(ok)))
+      flag = torch.tensor([float(ok.value)], dtype=torch.float64, device=dev)
+      all_reduce(flag)
+      use_peers = float(flag.item()) == float(peer_exchange.world)
+      fused = use_peers
     sums_arg = None if fused else sums.data_ptr()
-    if fused and os.environ.get('TQF_LSM_FUSED_SOLVE', '1') != '0':
+    if fused and (use_peers or os.environ.get('TQF_LSM_FUSED_SOLVE', '1') != '0'):
       # the last CTA of each streaming pass reduces and solves (no solve launch)
       ticket = torch.zeros((1,), dtype=torch.int32, device=dev)
       _lib.check(lib.tqf_lsm_set_fused_solve(handle, rcond, sums.data_ptr(),
                                              beta_dev.data_ptr(), ticket.data_ptr()))
+      if use_peers:
+        _lib.check(lib.tqf_lsm_set_peer_exchange(handle, peer_exchange.rank, peer_exchange.world,
+                                                 peer_exchange.ptrs, peer_exchange.epoch))
     if e > 0:
       _lib.check(lib.tqf_lsm_step(handle, 0, 0, None, None, None, 1,
                                   int(ex_times[e - 1]), mean_ptr(e), ratio_ptr(e),
                                   mean_stride, sums_arg, stream))
     while e > 0:
-      if all_reduce is not None:
+      if all_reduce is not None and not use_peers:
         all_reduce(sums)
       if device_solve:
         _lib.check(lib.tqf_lsm_solve(handle, sums.data_ptr(), 1 if fused else 0, rcond,
@@ -268,6 +285,10 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
                                      vs.data_ptr(), stream))
     if all_reduce is not None:
       all_reduce(vs)
+    if use_peers:
+      ep = C.c_uint64()
+      _lib.check(lib.tqf_lsm_peer_epoch(handle, C.byref(ep)))
+      peer_exchange.epoch = int(ep.value)
     vs = vs.cpu().numpy()
   finally:
     lib.tqf_lsm_destroy(handle)
