@@ -345,6 +345,19 @@ int tqf_lsm_set_fused_solve(tqf_lsm* h, double rcond, double* sums_dev, double* 
 /* 1 when the fused pass (tqf_lsm_set_fused_solve) applies to this handle. */
 int tqf_lsm_fused_eligible(const tqf_lsm* h, int* eligible);
 
+/* The whole backward induction of lsm.py:296-330 after tqf_lsm_init, for a
+ * handle with the fused solve set: one accumulate-only pass for the last
+ * exercise date, then one update + accumulate pass per earlier date, launched
+ * back to back from native code (the per-date host work of a Python loop,
+ * ~50 us, is longer than a pass at a few million paths).
+ *   exercise_times: host int32 [num_times] time indices;
+ *   means_dev: device double, the basis means of exercise index e at
+ *     means_dev + (e - 1) * dim (+ payoff * mean_stride);
+ *   ratio_dev: device double [num_times][batch], row e = df[e + 1] / df[e].  */
+int tqf_lsm_run_fused(tqf_lsm* h, const int32_t* exercise_times, int num_times,
+                      const double* means_dev, int64_t mean_stride, const double* ratio_dev,
+                      double* beta_dev, void* stream);
+
 /* Multi-GPU (one process per GPU of ONE box): the reduced normal equations of
  * every exercise date are summed over the ranks INSIDE the tail of the fused
  * pass, by peer stores / flags over NVLink -- replaces the per-date

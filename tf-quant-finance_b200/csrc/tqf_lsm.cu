@@ -375,6 +375,15 @@ __device__ void lsm_solve_one(const double* __restrict__ sp, double rcond, int r
 // Run by the last CTA of a fused pass: fixed-order reduction of the per-CTA
 // partial rows, then the K x K solve of every payoff.  Not inlined, so that the
 // solver's registers do not weigh on the streaming loop of the caller.
+// What the tail needs of the peer exchange, passed BY VALUE (taking the address
+// of the kernel parameter struct would move all of it to local memory, hot loop
+// included: measured +14 us per pass).
+struct PeerK {
+  int peer_rank, peer_world;
+  unsigned long long peer_epoch;
+  unsigned char* peer_bufs[kLsmMaxPeers];
+};
+
 __device__ __forceinline__ unsigned long long* peer_flag(unsigned char* buf, int parity, int src) {
   return reinterpret_cast<unsigned long long*>(buf + parity * 128) + src;
 }
@@ -393,8 +402,7 @@ __device__ __forceinline__ double* peer_sums(unsigned char* buf, int parity, int
 // ahead of another one, because each exchange needs every rank's flag.
 // Returns false when a peer did not arrive within ~10 s (the sums are then
 // poisoned with NaN instead of hanging the GPU).
-template <typename Args>
-__device__ __forceinline__ bool lsm_peer_all_reduce(const Args& A, double* sums, int M) {
+__device__ __forceinline__ bool lsm_peer_all_reduce(const PeerK& A, double* sums, int M) {
   __shared__ int s_timeout;
   const int parity = static_cast<int>(A.peer_epoch & 1ull);
   if (threadIdx.x == 0) s_timeout = 0;
@@ -431,8 +439,8 @@ __device__ __forceinline__ bool lsm_peer_all_reduce(const Args& A, double* sums,
   return ok;
 }
 
-template <int KT, typename Args>
-__device__ __noinline__ void lsm_fused_tail(const Args& A, const double* partials, int batch,
+template <int KT>
+__device__ __noinline__ void lsm_fused_tail(const PeerK A, const double* partials, int batch,
                                             int num_blocks, double* sums_out, double rcond,
                                             int round_to_float, double* beta_out) {
   // Thread t sums column m = t % 32 (m < M) of the rows r = t / 32, t / 32 + 8, ...
@@ -639,7 +647,13 @@ __global__ void __launch_bounds__(kLsmBlock, 3) lsm_step_dim1_vec_kernel(const L
       __syncthreads();
       if (s_last) {
         __threadfence();
-        lsm_fused_tail<KT>(A, A.partials, A.batch, gridDim.x, A.sums_out, A.rcond,
+        PeerK pk;
+        pk.peer_rank = A.peer_rank;
+        pk.peer_world = A.peer_world;
+        pk.peer_epoch = A.peer_epoch;
+#pragma unroll
+        for (int r = 0; r < kLsmMaxPeers; ++r) pk.peer_bufs[r] = A.peer_bufs[r];
+        lsm_fused_tail<KT>(pk, A.partials, A.batch, gridDim.x, A.sums_out, A.rcond,
                            A.round_to_float, A.beta_out);
         if (threadIdx.x == 0) *A.ticket = 0u;
       }
@@ -1378,6 +1392,33 @@ int tqf_lsm_set_fused_solve(tqf_lsm* h, double rcond, double* sums_dev, double* 
   h->fused_beta_dev = beta_dev;
   h->fused_rcond = rcond;
   return TQF_OK;
+}
+
+int tqf_lsm_run_fused(tqf_lsm* h, const int32_t* exercise_times, int num_times,
+                      const double* means_dev, int64_t mean_stride, const double* ratio_dev,
+                      double* beta_dev, void* stream) {
+  TQF_REQUIRE(h && exercise_times && means_dev && ratio_dev && beta_dev && num_times >= 1,
+              "bad arguments");
+  TQF_REQUIRE(h->ticket_dev != nullptr && beta_dev == h->fused_beta_dev && lsm_vec_ok(h),
+              "tqf_lsm_run_fused needs tqf_lsm_set_fused_solve on an eligible handle");
+  const int dim = h->desc.dim, B = h->desc.batch;
+  // exercise index e uses the means of time slot e - 1 and the ratio row e
+  auto mean_of = [&](int e) { return means_dev + static_cast<int64_t>(e - 1) * dim; };
+  auto ratio_of = [&](int e) { return ratio_dev + static_cast<int64_t>(e) * B; };
+  int e = num_times - 1;
+  int rc = TQF_OK;
+  if (e > 0)
+    rc = tqf_lsm_step(h, 0, 0, nullptr, nullptr, nullptr, 1, exercise_times[e - 1], mean_of(e),
+                      ratio_of(e), mean_stride, nullptr, stream);
+  while (rc == TQF_OK && e > 0) {
+    const int do_acc = e - 1 > 0 ? 1 : 0;
+    rc = tqf_lsm_step(h, 1, exercise_times[e - 1], mean_of(e), beta_dev, ratio_of(e), do_acc,
+                      do_acc ? exercise_times[e - 2] : 0, do_acc ? mean_of(e - 1) : nullptr,
+                      do_acc ? ratio_of(e - 1) : nullptr, mean_stride, nullptr, stream);
+    --e;
+  }
+  h->last_step_solved = false;
+  return rc;
 }
 
 int tqf_lsm_fused_eligible(const tqf_lsm* h, int* eligible) {

@@ -175,6 +175,9 @@ _SIGNATURES = {
         (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'tqf_lsm_set_fused_solve':
         (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'tqf_lsm_run_fused':
+        (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                   C.c_void_p, C.c_void_p]),
     'tqf_lsm_fused_eligible': (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     'tqf_lsm_peer_bytes': (C.c_int, [C.POINTER(C.c_uint64)]),
     'tqf_lsm_set_peer_exchange':

@@ -249,7 +249,8 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
       use_peers = float(flag.item()) == float(peer_exchange.world)
       fused = use_peers
     sums_arg = None if fused else sums.data_ptr()
-    if fused and (use_peers or os.environ.get('TQF_LSM_FUSED_SOLVE', '1') != '0'):
+    fused_set = fused and (use_peers or os.environ.get('TQF_LSM_FUSED_SOLVE', '1') != '0')
+    if fused_set:
       # the last CTA of each streaming pass reduces and solves (no solve launch)
       ticket = torch.zeros((1,), dtype=torch.int32, device=dev)
       _lib.check(lib.tqf_lsm_set_fused_solve(handle, rcond, sums.data_ptr(),
@@ -257,6 +258,18 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
       if use_peers:
         _lib.check(lib.tqf_lsm_set_peer_exchange(handle, peer_exchange.rank, peer_exchange.world,
                                                  peer_exchange.ptrs, peer_exchange.epoch))
+    native_loop = False
+    if fused_set:
+      ok = C.c_int()
+      _lib.check(lib.tqf_lsm_fused_eligible(handle, C.byref(ok)))
+      native_loop = bool(ok.value)
+    if native_loop:
+      # every pass reduces and solves in its own tail: the whole backward
+      # induction is launched back to back from native code
+      _lib.check(lib.tqf_lsm_run_fused(handle, ex_i32.ctypes.data, T, means.data_ptr(),
+                                       mean_stride, ratio_dev.data_ptr(), beta_dev.data_ptr(),
+                                       stream))
+      e = 0
     if e > 0:
       _lib.check(lib.tqf_lsm_step(handle, 0, 0, None, None, None, 1,
                                   int(ex_times[e - 1]), mean_ptr(e), ratio_ptr(e),
