@@ -383,7 +383,13 @@ def run_gpu(args):
     peak = (ffma if fp32 else dfma) / 1e9
     roofline = {'bound': 'fp32' if fp32 else 'fp64', 'achieved': achieved, 'peak': peak,
                 'unit': 'G %s-pipe instr/s' % ('FP32' if fp32 else 'FP64'),
-                'frac': achieved / peak, 'traffic': None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full at a
+                # reduced path count; the kernel only reads its tables, so the figure does not
+                # grow with the path count): profiles/r1i_c2_table_log.txt, r1e_c3_hw_swaption.txt,
+                # r1r_c4_mvgbm_mma.txt
+                'traffic': {'c2': 196608.0, 'c3': 105984.0, 'c4': 2203392.0}.get(args.workload),
+                'traffic_unit': 'bytes per launch (ncu, reduced path count)',
+                'frac': achieved / peak,
                 'note': 'achieved = path-steps/s/GPU x %d algorithmic %s instr per path-step; '
                         'peak = %s issue rate measured live by tqf_measure_fp64_peak '
                         '(MEASURED_PEAKS.json has no FP64/FP32 entry); kernel has no HBM traffic'

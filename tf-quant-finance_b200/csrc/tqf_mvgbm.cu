@@ -933,6 +933,9 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.0f;
         const uint32_t soff = (s - s0) * dim * 32;
+        // (A rolled loop over k-tile pairs with the row tiles predicated -- 9 KB of
+        // code instead of 21 KB -- measured 767 ms against 730 ms: the fetch stalls
+        // it removes cost less than the scheduling freedom it takes away.)
         int ti = 0;   // compile-time after unrolling
 #pragma unroll
         for (int kt = 0; kt < 8; ++kt) {
