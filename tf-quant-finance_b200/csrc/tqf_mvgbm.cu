@@ -667,66 +667,12 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint4& a, uint32_t
       : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 
-// Sobol integer point -> standard normal, float32: the reference's
-// (float(x) 2^-32 - 0.5) 2 equals RN(float(x) 2^-31 - 1) (the scaling by two
-// commutes with the rounding), one FFMA.
-__device__ __forceinline__ float sobol_normal_f32(uint32_t x32) {
-  const float t = fmaf(__uint2float_rn(x32), 4.656612873077393e-10f, -1.0f);
-  return fm::ndtri_t_f32(t);
-}
-
 // Round to nearest TF32: the remainder z - zh then has a sign independent of
 // z, so the tensor core's truncation of it does not bias |z| (a truncating
 // split measurably lowers the C4 price by 4e-7 relative).
 __device__ __forceinline__ uint32_t tf32_rna(float v) {
   // (cvt.rna.tf32.f32 is emulated with ~5 instructions on sm_100a)
   return (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
-}
-
-// N Sobol integer points -> standard normals, float32, the same arithmetic as
-// fm::ndtri_t_f32 per draw but evaluated side by side: the central polynomial
-// runs unconditionally for all N (independent Horner chains, no branch between
-// them) and ONE rarely taken branch per batch patches the draws in the tails
-// (|z| > 3.1, 0.2 % of them).
-template <int N>
-__device__ __forceinline__ void sobol_normals_f32(const uint32_t (&xb)[N], float (&z)[N]) {
-  float t[N], w[N], p[N];
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    t[k] = fmaf(__uint2float_rn(xb[k]), 4.656612873077393e-10f, -1.0f);
-    const float a = fmaf(-t[k], t[k], 1.0f);
-    float l2;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(a));   // a is never subnormal
-    w[k] = l2 * -0.693147182f;
-  }
-  const float cc[TQF_NDTRI_F32_C_N] = {TQF_NDTRI_F32_C_LIST};
-  float y[N];
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    y[k] = w[k] - TQF_NDTRI_F32_C_MID;
-    p[k] = cc[0];
-  }
-#pragma unroll
-  for (int i = 1; i < TQF_NDTRI_F32_C_N; ++i)
-#pragma unroll
-    for (int k = 0; k < N; ++k) p[k] = fmaf(p[k], y[k], cc[i]);
-  float wmax = w[0];
-#pragma unroll
-  for (int k = 1; k < N; ++k) wmax = fmaxf(wmax, w[k]);
-  if (!(wmax < 6.25f)) {
-    const float ct[TQF_NDTRI_F32_T_N] = {TQF_NDTRI_F32_T_LIST};
-#pragma unroll
-    for (int k = 0; k < N; ++k)
-      if (!(w[k] < 6.25f)) {
-        const float yt = sqrtf(w[k]) - TQF_NDTRI_F32_T_MID;
-        float q = ct[0];
-#pragma unroll
-        for (int i = 1; i < TQF_NDTRI_F32_T_N; ++i) q = fmaf(q, yt, ct[i]);
-        p[k] = q;
-      }
-  }
-#pragma unroll
-  for (int k = 0; k < N; ++k) z[k] = t[k] * p[k];
 }
 
 static uint32_t tf32_round_bits(float f) {

@@ -378,11 +378,59 @@ __device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&x
   fm::ndtri_t_v<K>(tab, t, z);
 }
 
+// N Sobol integer points -> standard normals, float32, the same arithmetic as
+// fm::ndtri_t_f32 per draw but evaluated side by side: the central polynomial
+// runs unconditionally for all N (independent Horner chains, no branch between
+// them) and ONE rarely taken branch per batch patches the draws in the tails
+// (|z| > 3.1, 0.2 % of them).
+template <int N>
+__device__ __forceinline__ void sobol_normals_f32(const uint32_t (&xb)[N], float (&z)[N]) {
+  float t[N], w[N], p[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    t[k] = fmaf(__uint2float_rn(xb[k]), 4.656612873077393e-10f, -1.0f);
+    const float a = fmaf(-t[k], t[k], 1.0f);
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(a));   // a is never subnormal
+    w[k] = l2 * -0.693147182f;
+  }
+  const float cc[TQF_NDTRI_F32_C_N] = {TQF_NDTRI_F32_C_LIST};
+  float y[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    y[k] = w[k] - TQF_NDTRI_F32_C_MID;
+    p[k] = cc[0];
+  }
+#pragma unroll
+  for (int i = 1; i < TQF_NDTRI_F32_C_N; ++i)
+#pragma unroll
+    for (int k = 0; k < N; ++k) p[k] = fmaf(p[k], y[k], cc[i]);
+  float wmax = w[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) wmax = fmaxf(wmax, w[k]);
+  if (!(wmax < 6.25f)) {
+    const float ct[TQF_NDTRI_F32_T_N] = {TQF_NDTRI_F32_T_LIST};
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (!(w[k] < 6.25f)) {
+        const float yt = sqrtf(w[k]) - TQF_NDTRI_F32_T_MID;
+        float q = ct[0];
+#pragma unroll
+        for (int i = 1; i < TQF_NDTRI_F32_T_N; ++i) q = fmaf(q, yt, ct[i]);
+        p[k] = q;
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) z[k] = t[k] * p[k];
+}
+
 template <int K, class Tab>
 __device__ __forceinline__ void sobol_normals(const Tab&, const uint32_t (&xb)[K],
                                               float (&z)[K]) {
-#pragma unroll
-  for (int k = 0; k < K; ++k) z[k] = ndtri(sobol_uniform_f32(xb[k]));
+  // bit-identical to z[k] = ndtri(sobol_uniform_f32(xb[k])): (u - 0.5) 2 with
+  // u = RN(x) 2^-32 equals RN(RN(x) 2^-31 - 1), the scaling by two commutes
+  // with the rounding
+  sobol_normals_f32<K>(xb, z);
 }
 template <int K, class Tab>
 __device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&xb)[K],
