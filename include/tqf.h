@@ -116,6 +116,13 @@ int tqf_philox_normal_fill(const uint32_t key[2], const uint32_t counter[4],
                            uint64_t first_element, uint64_t num_elements,
                            int dtype, void* out_dev, void* stream);
 
+/* The same for the uniform stream on [0, 1) of tf.random.stateless_uniform /
+ * tf.random.uniform (math/random_ops/uniform.py:92-101): fp32 Uint32ToFloat,
+ * four per group; fp64 Uint64ToDouble, two per group.                      */
+int tqf_philox_uniform_fill(const uint32_t key[2], const uint32_t counter[4],
+                            uint64_t first_element, uint64_t num_elements,
+                            int dtype, void* out_dev, void* stream);
+
 /* Direction numbers m[dim][32] (int32) from the Joe-Kuo table: replaces
  * `load_data` + `_compute_direction_numbers`
  * (math/random_ops/sobol/sobol_impl.py:171-197, 237-261).

@@ -137,6 +137,43 @@ def normals_from_words(words, dtype):
   raise ValueError(dtype)
 
 
+def uniforms_from_words(words, dtype):
+  """`UniformDistribution::operator()` (random_distributions.h) on uint32 [G, 4]
+  -> [G * k] uniforms on [0, 1): float32 four Uint32ToFloat per group, float64
+  two Uint64ToDouble.  This is what `tf.random.stateless_uniform` /
+  `tf.random.uniform` return for minval 0, maxval 1
+  (`math/random_ops/uniform.py:92-101`)."""
+  dtype = np.dtype(dtype)
+  w = np.ascontiguousarray(words, dtype=np.uint32)
+  if dtype == np.float64:
+    return np.stack([uint64_to_double(w[:, 0], w[:, 1]), uint64_to_double(w[:, 2], w[:, 3])],
+                    axis=-1).reshape(-1)
+  if dtype == np.float32:
+    return uint32_to_float(w).reshape(-1)
+  raise ValueError(dtype)
+
+
+def uniform_fill(key, counter, num_elements, dtype, first_element=0):
+  k = 2 if np.dtype(dtype) == np.float64 else 4
+  g0 = first_element // k
+  g1 = (first_element + num_elements + k - 1) // k
+  flat = uniforms_from_words(raw_words(key, counter, g0, g1 - g0), dtype)
+  off = first_element - g0 * k
+  return flat[off:off + num_elements]
+
+
+def stateless_uniform(shape, seed, dtype=np.float32):
+  """`tf.random.stateless_uniform(shape, seed, dtype=dtype, alg='philox')`."""
+  key, counter = stateless_key_counter(seed)
+  return uniform_fill(key, counter, int(np.prod(shape)), dtype).reshape(shape)
+
+
+def stateful_uniform(shape, seed, dtype=np.float32):
+  """First call of `tf.random.uniform(shape, dtype=dtype, seed=seed)`."""
+  key, counter = stateful_key_counter(seed)
+  return uniform_fill(key, counter, int(np.prod(shape)), dtype).reshape(shape)
+
+
 def normal_fill(key, counter, num_elements, dtype, first_element=0):
   """Elements [first_element, first_element + num_elements) of the flat stream."""
   k = 2 if np.dtype(dtype) == np.float64 else 4

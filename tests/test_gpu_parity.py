@@ -503,3 +503,41 @@ def test_batch_of_gbm_parameters():
                        random_type=odraws.RandomType.STATELESS, **kw)
   assert got.shape == want.shape == (2, n, 1, 1)
   _close(got, want, dtype, scale=np.abs(want).max())
+
+
+# ----- tff.math.random.uniform (math/random_ops/uniform.py; uniform_test.py:31-73)
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_uniform_stateless_and_pseudo_bit_exact(dtype):
+  tff = _tff()
+  rt = tff.math.random.RandomType
+  got = _np(tff.math.random.uniform(10, [2, 3, 5000], random_type=rt.STATELESS, seed=[2, 2], dtype=dtype))
+  want = ophilox.stateless_uniform([2, 3, 5000, 10], [2, 2], dtype)
+  assert got.dtype == dtype and got.shape == (2, 3, 5000, 10)
+  np.testing.assert_array_equal(got, want)          # pure bit manipulation + one exact subtraction
+  assert got.min() >= 0.0 and got.max() < 1.0
+  np.testing.assert_array_almost_equal(got.mean(axis=2), 0.5 * np.ones((2, 3, 10)), decimal=2)
+  got = _np(tff.math.random.uniform(10, [2, 3, 5000], seed=101, dtype=dtype))
+  np.testing.assert_array_equal(got, ophilox.stateful_uniform([2, 3, 5000, 10], 101, dtype))
+  np.testing.assert_array_almost_equal(got.mean(axis=2), 0.5 * np.ones((2, 3, 10)), decimal=2)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_uniform_sobol_equals_sobol_sample(dtype):
+  # uniform_test.py:58-73
+  tff = _tff()
+  got = _np(tff.math.random.uniform(5, [100], random_type=tff.math.random.RandomType.SOBOL,
+                                    skip=1000, dtype=dtype))
+  want = _np(tff.math.random.sobol.sample(dim=5, num_results=100, skip=1000, dtype=dtype))
+  assert got.dtype == dtype
+  np.testing.assert_array_equal(got, want)
+
+
+def test_uniform_argument_errors():
+  tff = _tff()
+  rt = tff.math.random.RandomType
+  with pytest.raises(ValueError):
+    tff.math.random.uniform(2, [4], random_type=rt.STATELESS)
+  with pytest.raises(NotImplementedError):
+    tff.math.random.uniform(2, [4], random_type=rt.PSEUDO_ANTITHETIC, seed=1)
+  with pytest.raises(NotImplementedError):
+    tff.math.random.uniform(2, [4], random_type=rt.HALTON)

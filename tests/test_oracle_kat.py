@@ -364,3 +364,17 @@ def test_lsm_basket_degree_10():
   b = lsm.least_square_mc(_LS_SAMPLES, [1, 2, 3], put, basis, _LS_DF, dtype=np.float64)
   assert a.shape == (3,)
   np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-4)
+
+
+def test_philox_uniform_conversions():
+  # random_distributions.h Uint32ToFloat / Uint64ToDouble: [0, 1), extremes exact
+  from oracle import philox as ophilox
+  w = np.array([[0, 0, 0xFFFFFFFF, 0xFFFFFFFF], [0x00800000, 0x007FFFFF, 0x000FFFFF, 0]], np.uint32)
+  f = ophilox.uniforms_from_words(w, np.float32)
+  np.testing.assert_array_equal(f[:4], np.array([0.0, 0.0, 1 - 2.0**-23, 1 - 2.0**-23], np.float32))
+  assert f[4] == 0.0 and f[5] == np.float32(1 - 2.0**-23)      # only the low 23 bits are used
+  d = ophilox.uniforms_from_words(w, np.float64)
+  np.testing.assert_array_equal(d, np.array([0.0, 1 - 2.0**-52, (0x7FFFFF) * 2.0**-52 + 0.0,
+                                             1 - 2.0**-20]))
+  u = ophilox.stateless_uniform([4096, 3], [2, 2], np.float64)
+  assert u.min() >= 0 and u.max() < 1 and abs(u.mean() - 0.5) < 0.01

@@ -97,6 +97,42 @@ __global__ void philox_normal_f32_kernel(PhiloxKey key, PhiloxCtr ctr,
   }
 }
 
+// tf.random.stateless_uniform / tf.random.uniform on [0, 1)
+// (random_distributions.h: UniformDistribution<PhiloxRandom, T>): float32 takes
+// four Uint32ToFloat per group, float64 two Uint64ToDouble.
+__global__ void philox_uniform_f64_kernel(PhiloxKey key, PhiloxCtr ctr, uint64_t first_element,
+                                          uint64_t n, double* __restrict__ out) {
+  const uint64_t g0 = first_element >> 1;
+  const uint64_t g1 = (first_element + n + 1) >> 1;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t g = g0 + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       g < g1; g += stride) {
+    const uint4 w = philox_group(ctr, key, g);
+    const double a = uint64_to_double(w.x, w.y), b = uint64_to_double(w.z, w.w);
+    const uint64_t e = g << 1;
+    if (e >= first_element && e < first_element + n) out[e - first_element] = a;
+    if (e + 1 >= first_element && e + 1 < first_element + n) out[e + 1 - first_element] = b;
+  }
+}
+
+__global__ void philox_uniform_f32_kernel(PhiloxKey key, PhiloxCtr ctr, uint64_t first_element,
+                                          uint64_t n, float* __restrict__ out) {
+  const uint64_t g0 = first_element >> 2;
+  const uint64_t g1 = (first_element + n + 3) >> 2;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t g = g0 + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       g < g1; g += stride) {
+    const uint4 w = philox_group(ctr, key, g);
+    const float v[4] = {uint32_to_float(w.x), uint32_to_float(w.y), uint32_to_float(w.z),
+                        uint32_to_float(w.w)};
+    const uint64_t e = g << 2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (e + k >= first_element && e + k < first_element + n) out[e + k - first_element] = v[k];
+    }
+  }
+}
+
 // Sobol fill: one thread per (row, dim) element, rows fastest within a warp
 // would make stores strided, so threads run over the flattened [count][dim]
 // output (coalesced stores); the XOR walks the set bits of the index.
@@ -275,6 +311,27 @@ int tqf_philox_normal_fill(const uint32_t key[2], const uint32_t counter[4],
         k, c, first_element, num_elements, static_cast<double*>(out_dev));
   } else {
     philox_normal_f32_kernel<<<grid_for(num_elements / 4 + 1, 256), 256, 0, s>>>(
+        k, c, first_element, num_elements, static_cast<float*>(out_dev));
+  }
+  TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
+}
+
+int tqf_philox_uniform_fill(const uint32_t key[2], const uint32_t counter[4],
+                            uint64_t first_element, uint64_t num_elements, int dtype,
+                            void* out_dev, void* stream) {
+  TQF_REQUIRE(key && counter, "null key/counter");
+  TQF_REQUIRE(dtype == TQF_F32 || dtype == TQF_F64, "dtype must be TQF_F32 or TQF_F64");
+  if (num_elements == 0) return TQF_OK;
+  TQF_REQUIRE(out_dev, "null output");
+  const PhiloxKey k{key[0], key[1]};
+  const PhiloxCtr c{counter[0], counter[1], counter[2], counter[3]};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == TQF_F64) {
+    philox_uniform_f64_kernel<<<grid_for(num_elements / 2 + 1, 256), 256, 0, s>>>(
+        k, c, first_element, num_elements, static_cast<double*>(out_dev));
+  } else {
+    philox_uniform_f32_kernel<<<grid_for(num_elements / 4 + 1, 256), 256, 0, s>>>(
         k, c, first_element, num_elements, static_cast<float*>(out_dev));
   }
   TQF_CUDA_OK(cudaGetLastError());

@@ -147,6 +147,9 @@ _SIGNATURES = {
     'tqf_philox_normal_fill':
         (C.c_int, [_u32p, _u32p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p,
                    C.c_void_p]),
+    'tqf_philox_uniform_fill':
+        (C.c_int, [_u32p, _u32p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p,
+                   C.c_void_p]),
     'tqf_sobol_direction_numbers':
         (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                    C.c_void_p]),

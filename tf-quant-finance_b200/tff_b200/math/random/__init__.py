@@ -6,6 +6,8 @@ from tff_b200.math.random.multivariate_normal import multivariate_normal as mv_n
 from tff_b200.math.random.multivariate_normal import RandomType
 from tff_b200.math.random.philox import normal
 from tff_b200.math.random.philox import stateless_normal
+from tff_b200.math.random.philox import stateless_uniform
+from tff_b200.math.random.uniform import uniform
 
 __all__ = ['RandomType', 'mv_normal_sample', 'sobol', 'stateless_normal',
-           'normal']
+           'normal', 'uniform', 'stateless_uniform']

@@ -37,12 +37,13 @@ def stateful_key_counter(seed):
   return key, ctr
 
 
-def _fill(key, ctr, shape, dtype, first_element=0):
+def _fill(key, ctr, shape, dtype, first_element=0, uniform=False):
   dtype = _tensor.np_dtype(dtype)
   shape = tuple(int(s) for s in np.asarray(shape).reshape(-1))
   n = int(np.prod(shape)) if shape else 1
   out = _tensor.empty((n,), dtype)
-  _lib.check(_lib.lib().tqf_philox_normal_fill(
+  fill = _lib.lib().tqf_philox_uniform_fill if uniform else _lib.lib().tqf_philox_normal_fill
+  _lib.check(fill(
       key, ctr, first_element, n, _tensor.tqf_dtype(dtype), out.data_ptr(),
       _tensor.current_stream_ptr()))
   return out.reshape(shape)
@@ -58,6 +59,18 @@ def normal(shape, dtype=np.float32, seed=None):
   """First invocation of `tf.random.normal(shape, dtype=dtype, seed=seed)`."""
   key, ctr = stateful_key_counter(seed)
   return _fill(key, ctr, shape, dtype)
+
+
+def stateless_uniform(shape, seed, dtype=np.float32):
+  """`tf.random.stateless_uniform(shape, seed=seed, dtype=dtype, alg='philox')` on [0, 1)."""
+  key, ctr = stateless_key_counter(seed)
+  return _fill(key, ctr, shape, dtype, uniform=True)
+
+
+def uniform(shape, dtype=np.float32, seed=None):
+  """First invocation of `tf.random.uniform(shape, dtype=dtype, seed=seed)` on [0, 1)."""
+  key, ctr = stateful_key_counter(seed)
+  return _fill(key, ctr, shape, dtype, uniform=True)
 
 
 def raw_words(key, counter, first_group, num_groups):
