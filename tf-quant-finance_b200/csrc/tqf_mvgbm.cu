@@ -1,7 +1,15 @@
 // Correlated multi-asset geometric Brownian motion, Euler scheme (config C4:
-// 64 assets, float32, Sobol).  One thread carries one path with all `dim`
-// asset prices in registers; per step it draws `dim` normals in-kernel,
-// applies the Cholesky factor and updates the state.
+// 64 assets, float32, Sobol).  Three kernels:
+//   mvgbm_kernel        dim <= 8: one thread carries one path, the factor in the
+//                       kernel parameter space;
+//   mvgbm_mma_kernel    8 < dim <= 64, float32, Sobol: a warp carries 16 paths,
+//                       the triangular mat-vec runs on the tensor cores
+//                       (mma.sync TF32 with split operands), normals are drawn
+//                       directly in the B-fragment layout;
+//   mvgbm_split_kernel  8 < dim <= 64 otherwise (float64, Philox): four threads
+//                       per path, factor rows streamed from shared memory.
+// Per step they draw `dim` normals in-kernel, apply the Cholesky factor and
+// update the state.
 //
 // Replaces, for the closures of
 // models/geometric_brownian_motion/multivariate_geometric_brownian_motion.py:130-151,
@@ -9,12 +17,6 @@
 // step for dim = 64, with tf.linalg.cholesky re-run every step, line 147) and
 // the tf.linalg.matvec over it (models/euler_sampling.py:529):
 //   x_i' = (x_i + dt mu_i x_i) + (sigma_i x_i) sqrt_dt sum_{j<=i} L_ij z_j.
-//
-// The Cholesky factor lives in the kernel parameter space (constant bank): the
-// fully unrolled lower-triangular mat-vec reads every L_ij as an FFMA / DFMA
-// constant operand -- no shared-memory traffic, no per-path matrix.  CUDA-core
-// FP32; a tensor-core formulation would need the [paths x dim] normal tile in
-// shared memory and only pays for the 48 % of the step that is the mat-vec.
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
