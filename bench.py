@@ -276,7 +276,7 @@ def run_reference(args):
       'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
   }
-  print(json.dumps(line))
+  emit(line)
 
 
 # -------------------------------------------------------------- GPU arm ----
@@ -418,7 +418,7 @@ def run_gpu(args):
         'cpu_baseline': {'value': cv, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d paths x %d steps, single process numpy oracle (%.1f s)' % (cn, csteps, cdt)},
     }
-    print(json.dumps(line))
+    emit(line)
   plan.close()
   if world > 1:
     dist.destroy_process_group()
@@ -542,7 +542,7 @@ def run_gpu_c5(args):
         'cpu_baseline': {'value': cv, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                          'sample': '%d paths x %d steps + LSM, single process numpy oracle (%.1f s)' % (cn, csteps, cdt)},
     }
-    print(json.dumps(line))
+    emit(line)
   plan.close()
   if px is not None:
     px.close()
@@ -550,7 +550,26 @@ def run_gpu_c5(args):
     dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+  """Writes the ONE JSON line of the run to the process's original stdout."""
+  data = (json.dumps(line) + '\n').encode()
+  if _JSON_FD is None:
+    sys.stdout.write(data.decode())
+    sys.stdout.flush()
+  else:
+    os.write(_JSON_FD, data)
+
+
 def main():
+  # stdout carries exactly one JSON line: anything else written to fd 1 during the
+  # run (NCCL prints its version banner there) is sent to stderr instead
+  global _JSON_FD
+  sys.stdout.flush()
+  _JSON_FD = os.dup(1)
+  os.dup2(2, 1)
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=5)

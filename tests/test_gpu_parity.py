@@ -541,3 +541,35 @@ def test_uniform_argument_errors():
     tff.math.random.uniform(2, [4], random_type=rt.PSEUDO_ANTITHETIC, seed=1)
   with pytest.raises(NotImplementedError):
     tff.math.random.uniform(2, [4], random_type=rt.HALTON)
+
+
+# ----- stateless_random_shuffle (math/random_ops/stateless.py:24-52; stateless_test.py:29-125)
+def test_stateless_random_shuffle_matches_reference_construction():
+  import torch
+  tff = _tff()
+  shuffles = {}
+  for dtype in (np.int32, np.int64, np.float32, np.float64):
+    ident = np.arange(10, dtype=dtype)
+    s1 = _np(tff.math.random.stateless_random_shuffle(ident, seed=(1, 42)))
+    s2 = _np(tff.math.random.stateless_random_shuffle(ident, seed=(2, 42)))
+    assert s1.dtype == dtype and s2.dtype == dtype
+    assert np.abs(s1 - s2).max() > 0                               # different seeds differ
+    assert set(s1.tolist()) == set(ident.tolist()) == set(s2.tolist())   # permutations
+    # the permutation is argsort(stable) of the float64 stateless uniforms
+    want = ident[np.argsort(ophilox.stateless_uniform([10], [1, 42], np.float64), kind='stable')]
+    np.testing.assert_array_equal(s1, want)
+    shuffles[dtype] = _np(tff.math.random.stateless_random_shuffle(ident, seed=(100, 42)))
+    np.testing.assert_array_equal(                                  # stateless
+        shuffles[dtype], _np(tff.math.random.stateless_random_shuffle(ident, seed=(100, 42))))
+  for dtype in shuffles:                                            # same across dtypes
+    np.testing.assert_array_equal(shuffles[dtype], shuffles[np.int32].astype(dtype))
+  # independent of the input values
+  rs = np.random.RandomState(25)
+  random_input = np.sort(rs.normal(size=[10]))
+  control = _np(tff.math.random.stateless_random_shuffle(random_input, seed=(100, 42)))
+  np.testing.assert_array_equal(np.argsort(shuffles[np.int64]), np.argsort(control))
+  # multi-dimensional input: rows are shuffled
+  x = np.array([[[1], [2], [3]], [[4], [5], [6]]], dtype=np.float32)
+  got = _np(tff.math.random.stateless_random_shuffle(torch.as_tensor(x), seed=(1, 42)))
+  assert got.shape == x.shape and got.dtype == x.dtype
+  assert sorted(got.reshape(2, 3).tolist()) == sorted(x.reshape(2, 3).tolist())

@@ -7,7 +7,8 @@ from tff_b200.math.random.multivariate_normal import RandomType
 from tff_b200.math.random.philox import normal
 from tff_b200.math.random.philox import stateless_normal
 from tff_b200.math.random.philox import stateless_uniform
+from tff_b200.math.random.stateless import stateless_random_shuffle
 from tff_b200.math.random.uniform import uniform
 
 __all__ = ['RandomType', 'mv_normal_sample', 'sobol', 'stateless_normal',
-           'normal', 'uniform', 'stateless_uniform']
+           'normal', 'uniform', 'stateless_uniform', 'stateless_random_shuffle']
