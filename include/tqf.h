@@ -123,6 +123,19 @@ int tqf_philox_uniform_fill(const uint32_t key[2], const uint32_t counter[4],
                             uint64_t first_element, uint64_t num_elements,
                             int dtype, void* out_dev, void* stream);
 
+/* Non-randomized Halton points `halton.sample(dim, sequence_indices =
+ * first_index .. first_index + count - 1, randomized=False)` in the reference's
+ * floating-point arithmetic (math/random_ops/halton/halton_impl.py:250-288).
+ *   radixes: host int32 [dim], the first `dim` primes (440-526);
+ *   sizes:   host int32 [dim], digits kept per axis (_MAX_SIZES_BY_AXES, 530-534);
+ *   weights: host double [dim][max_size], round(radix^j) in `dtype` (265-273);
+ *   kind 1: uniforms, kind 2: normals sqrt(2) erfinv(2u - 1)
+ *   (multivariate_normal.py:420).  out_dev is dtype [count][dim] row-major.
+ * Synchronises `stream` before returning.                                   */
+int tqf_halton_fill(const double* weights, const int32_t* sizes, const int32_t* radixes,
+                    int dim, int max_size, uint64_t first_index, uint64_t count,
+                    int kind, int dtype, void* out_dev, void* stream);
+
 /* Direction numbers m[dim][32] (int32) from the Joe-Kuo table: replaces
  * `load_data` + `_compute_direction_numbers`
  * (math/random_ops/sobol/sobol_impl.py:171-197, 237-261).

@@ -83,6 +83,26 @@ def _mvnormal_sobol(sample_shape, mean, skip, dtype):
   return mean + _erfinv_times_sqrt2(seq, dtype)
 
 
+def _mvnormal_halton(sample_shape, mean, skip, dtype):
+  """`multivariate_normal.py:356-424` for HALTON (randomized = False):
+  `halton.sample(dim, sequence_indices=range(skip, skip + n))`, then the same
+  transpose / reshape / erfinv as the Sobol branch."""
+  from oracle import halton  # pylint: disable=g-import-not-at-top
+  batch_shape = tuple(mean.shape)
+  dim = batch_shape[-1]
+  sample_shape = tuple(int(s) for s in sample_shape)
+  output_shape_t = tuple(reversed(batch_shape)) + sample_shape
+  num_samples = int(np.prod(output_shape_t)) // dim
+  seq = halton.sample(dim, sequence_indices=np.arange(skip, skip + num_samples), dtype=dtype)
+  seq = seq.T
+  size_sample = len(sample_shape)
+  size_batch = len(batch_shape)
+  perm = (list(range(size_batch, size_batch + size_sample)) +
+          list(range(size_batch - 1, -1, -1)))
+  seq = np.transpose(seq.reshape(output_shape_t), perm)
+  return mean + _erfinv_times_sqrt2(seq, dtype)
+
+
 def mv_normal_sample(sample_shape, mean, random_type=None, seed=None,
                      dtype=None, skip=0):
   """`multivariate_normal` restricted to `mean` only (identity scale)."""
@@ -98,6 +118,8 @@ def mv_normal_sample(sample_shape, mean, random_type=None, seed=None,
                                        dtype)
   if random_type == RandomType.SOBOL:
     return _mvnormal_sobol(sample_shape, mean, skip, dtype)
+  if random_type == RandomType.HALTON:
+    return _mvnormal_halton(sample_shape, mean, skip, dtype)
   raise NotImplementedError(
       'Only STATELESS, PSEUDO, PSEUDO_ANTITHETIC, STATELESS_ANTITHETIC and '
       'SOBOL are restated by the oracle. Supplied: {}'.format(random_type))

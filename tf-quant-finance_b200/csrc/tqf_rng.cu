@@ -165,6 +165,42 @@ __global__ void sobol_fill_kernel(const uint32_t* __restrict__ v_table, int dim,
   }
 }
 
+// Non-randomized Halton sequence in the reference's floating-point arithmetic
+// (halton_impl.py:250-288): digit j of index i in base p is
+// floor(i / p^j) mod p, the point is sum_j (digit_j / p) / p^j, everything in
+// `Real`.  One thread per (row, dim) element of the [count][dim] output.
+template <int KIND, typename Real>
+__global__ void halton_fill_kernel(const Real* __restrict__ weights, const int* __restrict__ sizes,
+                                   const Real* __restrict__ radixes, int dim, int max_size,
+                                   uint64_t first_index, uint64_t count,
+                                   const double* __restrict__ logtab, Real* __restrict__ out) {
+  const uint64_t total = count * static_cast<uint64_t>(dim);
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       e < total; e += stride) {
+    const uint64_t row = e / dim;
+    const int d = static_cast<int>(e - row * dim);
+    // indices = cast(sequence_indices, dtype) + 1   (halton_impl.py:404-411)
+    const Real idx = static_cast<Real>(first_index + row) + Real(1);
+    const Real p = radixes[d];
+    const Real* w = weights + static_cast<size_t>(d) * max_size;
+    const int n = sizes[d];
+    Real sum = 0;
+    for (int j = 0; j < n; ++j) {
+      const Real wj = w[j];
+      Real c = floor(idx / wj);
+      c = fmod(c, p);
+      c = c / p;
+      sum += c / wj;
+    }
+    if constexpr (KIND == 1) {
+      out[e] = sum;
+    } else {
+      out[e] = ndtri(sum, logtab);
+    }
+  }
+}
+
 __global__ void math_eval_kernel(int fn, const double* __restrict__ in, double* __restrict__ out,
                                  uint64_t n, const double* __restrict__ logtab) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
@@ -315,6 +351,70 @@ int tqf_philox_normal_fill(const uint32_t key[2], const uint32_t counter[4],
   }
   TQF_CUDA_OK(cudaGetLastError());
   return TQF_OK;
+}
+
+}  // extern "C"
+
+template <typename Real>
+static int halton_fill_impl(const double* weights, const int32_t* sizes, const int32_t* radixes,
+                            int dim, int max_size, uint64_t first_index, uint64_t count, int kind,
+                            void* out_dev, cudaStream_t s) {
+  std::vector<Real> w(static_cast<size_t>(dim) * max_size), r(dim);
+  for (size_t i = 0; i < w.size(); ++i) w[i] = static_cast<Real>(weights[i]);
+  for (int d = 0; d < dim; ++d) r[d] = static_cast<Real>(radixes[d]);
+  Real *w_dev = nullptr, *r_dev = nullptr;
+  int* n_dev = nullptr;
+  const double* logtab = nullptr;
+  int rc = device_logtab(&logtab);
+  if (rc != TQF_OK) return rc;
+  cudaError_t e = cudaMalloc(&w_dev, w.size() * sizeof(Real));
+  if (e == cudaSuccess) e = cudaMalloc(&r_dev, r.size() * sizeof(Real));
+  if (e == cudaSuccess) e = cudaMalloc(&n_dev, dim * sizeof(int));
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(w_dev, w.data(), w.size() * sizeof(Real), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(r_dev, r.data(), r.size() * sizeof(Real), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(n_dev, sizes, dim * sizeof(int), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    const int grid = grid_for(count * static_cast<uint64_t>(dim), 256);
+    if (kind == 1)
+      halton_fill_kernel<1, Real><<<grid, 256, 0, s>>>(w_dev, n_dev, r_dev, dim, max_size,
+                                                       first_index, count, logtab,
+                                                       static_cast<Real*>(out_dev));
+    else
+      halton_fill_kernel<2, Real><<<grid, 256, 0, s>>>(w_dev, n_dev, r_dev, dim, max_size,
+                                                       first_index, count, logtab,
+                                                       static_cast<Real*>(out_dev));
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // the host staging buffers go away
+  }
+  cudaFree(w_dev);
+  cudaFree(r_dev);
+  cudaFree(n_dev);
+  if (e != cudaSuccess) return cuda_fail(e, "tqf_halton_fill");
+  return TQF_OK;
+}
+
+extern "C" {
+
+int tqf_halton_fill(const double* weights, const int32_t* sizes, const int32_t* radixes, int dim,
+                    int max_size, uint64_t first_index, uint64_t count, int kind, int dtype,
+                    void* out_dev, void* stream) {
+  TQF_REQUIRE(weights && sizes && radixes, "null table");
+  TQF_REQUIRE(dim >= 1 && dim <= 1000 && max_size >= 1 && max_size <= 64, "bad dim / max_size");
+  TQF_REQUIRE(kind == 1 || kind == 2, "kind must be 1 (uniform) or 2 (normal)");
+  TQF_REQUIRE(dtype == TQF_F32 || dtype == TQF_F64, "dtype must be TQF_F32 or TQF_F64");
+  for (int d = 0; d < dim; ++d)
+    TQF_REQUIRE(sizes[d] >= 1 && sizes[d] <= max_size && radixes[d] >= 2, "bad sizes / radixes");
+  if (count == 0) return TQF_OK;
+  TQF_REQUIRE(out_dev, "null output");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dtype == TQF_F64
+             ? halton_fill_impl<double>(weights, sizes, radixes, dim, max_size, first_index,
+                                        count, kind, out_dev, s)
+             : halton_fill_impl<float>(weights, sizes, radixes, dim, max_size, first_index, count,
+                                       kind, out_dev, s);
 }
 
 int tqf_philox_uniform_fill(const uint32_t key[2], const uint32_t counter[4],

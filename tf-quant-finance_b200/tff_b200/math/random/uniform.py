@@ -13,8 +13,8 @@ def uniform(dim, sample_shape, random_type=None, dtype=None, seed=None, name=Non
   Same contract as the reference: PSEUDO -> `tf.random.uniform(seed=)` (first
   invocation of a fresh op), STATELESS -> `tf.random.stateless_uniform(seed=[a, b],
   alg='philox')`, SOBOL -> `sobol.sample(dim, prod(sample_shape), skip)`;
-  PSEUDO_ANTITHETIC raises as in the reference (`uniform.py:102-105`); the
-  Halton types are not implemented by the B200 engine.
+  PSEUDO_ANTITHETIC raises as in the reference (`uniform.py:102-105`); HALTON is
+  the non-randomized sequence, HALTON_RANDOMIZED is not implemented.
   """
   del name
   random_type = RandomType.PSEUDO if random_type is None else random_type
@@ -35,6 +35,13 @@ def uniform(dim, sample_shape, random_type=None, dtype=None, seed=None, name=Non
     num = int(np.prod(sample_shape)) if sample_shape else 1
     seq = sobol.sample(dim=int(dim), num_results=num, skip=int(kwargs.get('skip', 0)), dtype=dtype)
     return seq.reshape(shape)
+  if random_type.value == RandomType.HALTON.value:
+    from tff_b200.math.random import halton  # pylint: disable=g-import-not-at-top
+    num = int(np.prod(sample_shape)) if sample_shape else 1
+    skip = int(kwargs.get('skip', 0))
+    seq, _ = halton.sample(dim=int(dim), sequence_indices=np.arange(skip, skip + num),
+                           randomized=False, dtype=dtype)
+    return seq.reshape(shape)
   raise NotImplementedError(
-      'uniform: {} is not implemented by the B200 engine (Philox and Sobol only).'.format(
-          random_type))
+      'uniform: {} is not implemented by the B200 engine (Philox, Sobol and the '
+      'non-randomized Halton sequence only).'.format(random_type))
