@@ -60,6 +60,9 @@ extern "C" {
  * dt, sqrt_dt, a0, a1, b0, b1, da0/dtheta, da1/dtheta, db0/dtheta, db1/dtheta;
  * x0 = [x0, 1, 0].                                                          */
 #define TQF_MODEL_AFFINE_1F_TANGENT 9
+/* Milstein scheme of the 1-d affine process (milstein_sampling.py:565-575):
+ * coef columns dt, sqrt_dt, a0, a1, b0, b1; dS/dx = b1.                     */
+#define TQF_MODEL_MILSTEIN_1F 10
 
 /* payoff kinds (reduced in-kernel; callers: e.g. hull_white/swaption.py:310) */
 #define TQF_PAYOFF_CALL 1          /* max(f(X_T) - K, 0)                    */

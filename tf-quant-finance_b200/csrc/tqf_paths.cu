@@ -54,6 +54,7 @@ static bool model_info(int kind, int dim, ModelInfo* info) {
     case TQF_MODEL_MVGBM: *info = {dim, dim, 2}; return dim >= 1 && dim <= 64;
     case TQF_MODEL_AFFINE_1F: *info = {1, 1, 6}; return true;
     case TQF_MODEL_AFFINE_1F_TANGENT: *info = {3, 1, 10}; return true;
+    case TQF_MODEL_MILSTEIN_1F: *info = {1, 1, 6}; return true;
     case TQF_MODEL_AFFINE_ND:
       *info = {dim, dim, 2 + dim + 2 * dim * dim};
       return dim >= 2 && dim <= 4;
@@ -153,6 +154,9 @@ static int dispatch(const tqf_plan* plan, int mode, int grid, size_t smem, const
     case TQF_MODEL_AFFINE_1F_TANGENT:
       return launch_path_kernel<TangentAffine1FModel<Real>>(rk, anti, mode, grid, smem, P, stream,
                                                             grid_out);
+    case TQF_MODEL_MILSTEIN_1F:
+      return launch_path_kernel<MilsteinAffine1FModel<Real>>(rk, anti, mode, grid, smem, P, stream,
+                                                             grid_out);
     case TQF_MODEL_GBM_1F:
       return launch_path_kernel<GbmModel1F<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     case TQF_MODEL_LINEAR_1F:

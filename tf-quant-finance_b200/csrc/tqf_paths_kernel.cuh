@@ -168,6 +168,24 @@ struct TangentAffine1FModel {
   }
 };
 
+// Milstein step in one dimension (_milstein_1d, milstein_sampling.py:565-575):
+//   x' = x + dt a + b dw + (b b') (dw^2 - dt) / 2,  a = a0 + a1 x, b = b0 + b1 x, b' = b1,
+// with the reference's grouping ((x + dt_inc) + dw_inc) + hot_inc.
+template <typename R>
+struct MilsteinAffine1FModel {
+  using Real = R;
+  static constexpr int DIM = 1, NF = 1, NCOEF = 6;
+  __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
+                                              const Real (&c)[NCOEF]) {
+    const Real dw = z[0] * c[1];
+    const Real vol = c[4] + c[5] * x[0];
+    const Real dt_inc = c[0] * (c[2] + c[3] * x[0]);
+    const Real dw_inc = vol * dw;
+    const Real hot_inc = ((vol * c[5]) * (dw * dw - c[0])) / Real(2);
+    x[0] = ((x[0] + dt_inc) + dw_inc) + hot_inc;
+  }
+};
+
 template <typename R>
 struct GbmModel1F {  // a = mu x, S = sigma x  (univariate_geometric_brownian_motion.py:127-153)
   using Real = R;

@@ -29,6 +29,7 @@ MODEL_LINEAR_1F = 6
 MODEL_HW1F = 7
 MODEL_AFFINE_ND = 8
 MODEL_AFFINE_1F_TANGENT = 9
+MODEL_MILSTEIN_1F = 10
 PAYOFF_CALL = 1
 PAYOFF_PUT = 2
 PAYOFF_UP_OUT_CALL = 3

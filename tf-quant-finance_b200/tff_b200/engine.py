@@ -86,6 +86,28 @@ class TangentAffineSpec1F(ModelSpec):
     return np.concatenate([np.asarray(x0).reshape(-1)[:1], [1.0, 0.0]])
 
 
+class MilsteinSpec1F(ModelSpec):
+  """The Milstein scheme (`models/milstein_sampling.py:565-575`) of a 1-d process
+  whose Euler spec is affine (`AffineSpec1F`, `GbmSpec1F` or a probed pair of
+  plain callables): the volatility gradient of `b0(t) + b1(t) x` is `b1(t)`."""
+  kind, dim, num_factors, num_coef = _lib.MODEL_MILSTEIN_1F, 1, 1, 6
+
+  def __init__(self, euler_spec):
+    if euler_spec.dim != 1 or euler_spec.kind not in (_lib.MODEL_AFFINE_1F, _lib.MODEL_GBM_1F):
+      raise NotImplementedError(
+          'The B200 Milstein kernel covers 1-d processes with affine drift and '
+          'volatility (affine_closures, gbm_closures, GeometricBrownianMotion, or '
+          'plain callables that are affine in the state). There is no CPU fallback.')
+    self.euler_spec = euler_spec
+
+  def coef_table(self, all_times, dtype):
+    tab = self.euler_spec.coef_table(all_times, dtype)
+    if self.euler_spec.kind == _lib.MODEL_GBM_1F:      # dt, sqrt_dt, mu, sigma
+      zero = np.zeros_like(tab[:, 0])
+      tab = np.stack([tab[:, 0], tab[:, 1], zero, tab[:, 2], zero, tab[:, 3]], -1)
+    return np.ascontiguousarray(tab, dtype=np.float64)
+
+
 class ProbedAffineSpec(ModelSpec):
   """An arbitrary Python (drift_fn, volatility_fn) pair that turns out to be
   affine: a(t, x) = a0(t) + A1(t) x and S(t, x) = B0(t) (+ B1(t) x for dim 1).
