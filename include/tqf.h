@@ -205,6 +205,11 @@ typedef struct tqf_model_desc {
   const double* x0;        /* host double [dim] initial state               */
   const double* matrix;    /* MVGBM: host double [dim][dim] Cholesky factor */
   const double* vector;    /* MVGBM: host double [2][dim] means, vols       */
+  /* Optional per-path initial states (`initial_state` of shape
+   * [num_samples, dim], euler_sampling.py:357): DEVICE pointer, model dtype,
+   * [num_paths_total][dim] row-major; NULL = every path starts at x0.  The
+   * buffer must stay alive while the plan is used.  Not for TQF_MODEL_MVGBM. */
+  const void* x0_paths_dev;
 } tqf_model_desc;
 
 typedef struct tqf_payoff_desc {

@@ -447,8 +447,8 @@ def test_limits_are_reported():
   with pytest.raises(ValueError):          # STATELESS needs a seed
     sample(dim, drift, vol, [1.0], num_samples=8, initial_state=x0, num_time_steps=4,
            random_type=rt.STATELESS, dtype=dtype)
-  with pytest.raises(NotImplementedError):  # per-path initial states
-    sample(dim, drift, vol, [1.0], num_samples=8,
+  with pytest.raises(ValueError):          # per-path initial states: one row per sample
+    sample(dim, drift, vol, [1.0], num_samples=6,
            initial_state=np.arange(16.0).reshape(8, 2), num_time_steps=4, seed=1, dtype=dtype)
 
 
@@ -573,3 +573,40 @@ def test_stateless_random_shuffle_matches_reference_construction():
   got = _np(tff.math.random.stateless_random_shuffle(torch.as_tensor(x), seed=(1, 42)))
   assert got.shape == x.shape and got.dtype == x.dtype
   assert sorted(got.reshape(2, 3).tolist()) == sorted(x.reshape(2, 3).tolist())
+
+
+# ----- one initial state per path (`initial_state` of shape [num_samples, dim],
+# euler_sampling.py:357: `initial_state + zeros([num_samples, dim])`)
+@pytest.mark.parametrize('rt', ['STATELESS_ANTITHETIC', 'SOBOL', 'STATELESS'])
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_per_path_initial_states(rt, dtype):
+  tff = _tff()
+  from tff_b200.models import closures
+  from oracle import euler as oeuler
+  n = 3002
+  rs = np.random.RandomState(3)
+  x0 = rs.uniform(0.5, 2.0, size=(n, 1)).astype(dtype)
+  mu, sigma = 0.05, 0.3
+  drift, vol = closures.gbm_closures(mu, sigma)
+  kw = dict(num_samples=n, initial_state=x0, seed=[4, 2], time_step=0.05, dtype=dtype)
+  got = _np(tff.models.euler_sampling.sample(1, drift, vol, [0.0, 0.5, 1.0],
+                                             random_type=tff.math.random.RandomType[rt], **kw))
+  want = oeuler.sample(1, lambda t, x: dtype(mu) * x, lambda t, x: (dtype(sigma) * x)[..., None],
+                       [0.0, 0.5, 1.0], random_type=odraws.RandomType[rt], **kw)
+  assert got.shape == want.shape == (n, 3, 1)
+  np.testing.assert_array_equal(got[:, 0, :], x0)
+  _close(got, want, dtype)
+  # Heston (dim 2), per-path spot and variance
+  x02 = np.stack([rs.uniform(4.0, 5.0, n), rs.uniform(0.02, 0.08, n)], -1).astype(dtype)
+  heston = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=0.5, rho=-0.7, dtype=dtype)
+  got = _np(heston.sample_paths_euler([0.5, 1.0], x02, num_samples=n, num_time_steps=20,
+                                      random_type=tff.math.random.RandomType[rt], seed=[4, 2]))
+  from oracle import models as omodels
+  od, ov = omodels.heston_closures(2.0, 0.04, 0.5, -0.7, dtype)
+  want = oeuler.sample(2, od, ov, [0.5, 1.0], num_samples=n, initial_state=x02, num_time_steps=20,
+                       random_type=odraws.RandomType[rt], seed=[4, 2], dtype=dtype)
+  _close(got, want, dtype)
+  with pytest.raises(ValueError):
+    tff.models.euler_sampling.sample(1, drift, vol, [1.0], num_samples=n + 2, initial_state=x0,
+                                     seed=[4, 2], time_step=0.05, dtype=dtype,
+                                     random_type=tff.math.random.RandomType[rt])

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
   # sizes implied by include/tqf.h on LP64
   assert C.sizeof(_lib.RngDesc) == 4 + 4 + 8 + 16 + 8 + 8 + 8 + 8 + 8
-  assert C.sizeof(_lib.ModelDesc) == 8 * 4 + 4 * 8
+  assert C.sizeof(_lib.ModelDesc) == 8 * 4 + 5 * 8
   assert C.sizeof(_lib.PayoffDesc) == 16 + 24 + 16 + 16 + 3 * 64 * 8
 
 

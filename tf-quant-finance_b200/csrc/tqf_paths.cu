@@ -116,6 +116,8 @@ static void fill_common(const tqf_plan* plan, uint64_t path_offset, uint64_t pat
   P->num_steps = plan->model.num_steps;
   P->num_steps_total = plan->model.num_steps_total;
   for (int j = 0; j < 4; ++j) P->x0[j] = static_cast<Real>(plan->x0[j]);
+  P->x0_paths = static_cast<const Real*>(plan->model.x0_paths_dev);
+  P->x0_half = plan->num_paths_total / 2;
   P->key = PhiloxKey{plan->rng.key[0], plan->rng.key[1]};
   P->ctr = PhiloxCtr{plan->rng.counter[0], plan->rng.counter[1], plan->rng.counter[2],
                      plan->rng.counter[3]};
@@ -421,6 +423,8 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
               "num_steps must be in [0, num_steps_total]");
   TQF_REQUIRE(model->num_steps == 0 || model->coef, "null coefficient table");
   TQF_REQUIRE(model->x0, "null initial state");
+  TQF_REQUIRE(model->x0_paths_dev == nullptr || model->kind != TQF_MODEL_MVGBM,
+              "per-path initial states are not supported by the multi-asset kernels");
   TQF_REQUIRE(rng->type == TQF_RNG_PHILOX || rng->type == TQF_RNG_SOBOL ||
                   rng->type == TQF_RNG_DRAWS,
               "unknown rng type");

@@ -63,6 +63,8 @@ struct KParams {
   int num_steps;
   int num_steps_total;
   Real x0[4];
+  const Real* x0_paths;      // device [N][DIM] per-path initial states, or null
+  uint64_t x0_half;          // antithetic plans: row of the partner = row + x0_half (N / 2)
   // rng
   PhiloxKey key;
   PhiloxCtr ctr;
@@ -652,10 +654,13 @@ path_kernel(const KParams<typename Model::Real> P) {
       for (int h = 0; h < NPATH; ++h)
 #pragma unroll
         for (int j = 0; j < DIM; ++j) {
-          x[a][h][j] = P.x0[j];
+          Real x0j = P.x0[j];
+          if (P.x0_paths != nullptr && valid[a])
+            x0j = P.x0_paths[(P.path_offset + local[a] + h * P.x0_half) * DIM + j];
+          x[a][h][j] = x0j;
           if (j == 0 || j == P.monitor) {
-            xmax[a][h] = P.x0[j];
-            xmin[a][h] = P.x0[j];
+            xmax[a][h] = x0j;
+            xmin[a][h] = x0j;
           }
         }
 

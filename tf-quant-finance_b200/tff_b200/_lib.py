@@ -73,6 +73,7 @@ class ModelDesc(C.Structure):
       ('x0', C.c_void_p),
       ('matrix', C.c_void_p),
       ('vector', C.c_void_p),
+      ('x0_paths_dev', C.c_void_p),
   ]
 
 

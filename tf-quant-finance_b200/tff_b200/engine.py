@@ -416,7 +416,9 @@ class RngSpec:
 class Plan:
   """Device-resident tables of one (model, grid, rng) configuration."""
 
-  def __init__(self, spec, all_times, num_steps, x0, rng, num_samples, dtype):
+  def __init__(self, spec, all_times, num_steps, x0, rng, num_samples, dtype, x0_paths=None):
+    """`x0_paths`: optional per-path initial states `[num_samples, dim]`
+    (anything convertible to a tensor); `x0` is then only a placeholder."""
     self.spec, self.rng = spec, rng
     self.dtype = np.dtype(dtype)
     self.num_samples = int(num_samples)
@@ -444,6 +446,14 @@ class Plan:
     m.reserved = int(getattr(spec, 'exact_log', False))
     m.coef = table.ctypes.data
     m.x0 = x0.ctypes.data
+    if x0_paths is not None:
+      xp = torch.as_tensor(np.array(_tensor.to_numpy(x0_paths, self.dtype), order='C', copy=True),
+                           device=_tensor.device()).contiguous()
+      if tuple(xp.shape) != (self.num_samples, spec.dim):
+        raise ValueError('per-path initial states must have shape {} but have {}'.format(
+            (self.num_samples, spec.dim), tuple(xp.shape)))
+      self._keep.append(xp)
+      m.x0_paths_dev = xp.data_ptr()
     extra = getattr(spec, 'device_arrays', None)
     if extra is not None:
       mat, vec = extra(self.dtype)

@@ -10,6 +10,7 @@ reduces payoffs in-kernel (no path leaves the registers).
 """
 import numpy as np
 
+from tff_b200 import _lib
 from tff_b200 import _tensor
 from tff_b200 import engine
 from tff_b200.math import random
@@ -111,9 +112,16 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
   plans = []
   for bi, index in enumerate(np.ndindex(*batch_shape)):
     x0 = np.asarray(x0_full[index]).reshape(-1, dim)
+    x0_paths = None
     if x0.shape[0] != 1 and not np.all(x0 == x0[0]):
-      raise NotImplementedError(
-          'per-path initial states are not implemented by the B200 engine yet.')
+      # one initial state per path (`initial_state` of shape [num_samples, dim])
+      if x0.shape[0] != int(num_samples):
+        raise ValueError('`initial_state` has {} rows but `num_samples` is {}'.format(
+            x0.shape[0], int(num_samples)))
+      if hasattr(spec, 'extend_initial_state') or spec.kind == _lib.MODEL_MVGBM:
+        raise NotImplementedError(
+            'per-path initial states are not implemented for this model yet.')
+      x0_paths = x0
     spec_b = spec.for_batch(index, batch_shape) if (
         batch_shape and hasattr(spec, 'for_batch')) else spec
     # draw units of a batch (models/utils.py:98-107): [batch, N] row-major, or
@@ -122,7 +130,8 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
     rng = engine.RngSpec(random_type, seed, skip, normal_draws, unit_stride=stride,
                          unit_offset=offset)
     x0_plan = spec_b.extend_initial_state(x0[0]) if hasattr(spec_b, 'extend_initial_state') else x0[0]
-    plans.append(engine.Plan(spec_b, all_times, num_steps, x0_plan, rng, num_samples, dtype))
+    plans.append(engine.Plan(spec_b, all_times, num_steps, x0_plan, rng, num_samples, dtype,
+                             x0_paths=x0_paths))
   return plans, record_slot, times.shape[0], batch_shape
 
 
