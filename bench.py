@@ -535,7 +535,12 @@ def run_gpu_c5(args):
                 'h2d_bytes_per_step': 50 * 8 * 2 + 148 * 6 * 8, 'd2h_bytes_per_step': 16},
         'gpu_launches': args.steps * (2 + 1 + 50 + 2),   # paths + column-sum reduce, init, passes, value sum + reduce
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': achieved / hbm_peak, 'traffic': None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE streaming pass at 8 M paths
+                     # (ncu --set full, cache flushed before the launch: 192.1 MB read + 9.8 MB written
+                     # against 256 MB algorithmic -- most of W's 64 MB store is still in L2 when the
+                     # kernel ends): profiles/r1z_c5_lsm_step_fused.txt
+                     'frac': achieved / hbm_peak, 'traffic': 201859840.0 if n == 8_000_000 else None,
+                     'traffic_unit': 'bytes per streaming pass (ncu, 8M paths, cold L2)',
                      'note': 'LSM passes: 32 algorithmic bytes per path per exercise date (SURVEY 8d) '
                              '/ time between the device events around least_square_mc (initial payoff, 50 streaming '
                              'passes with fused solves, value sum); peak = MEASURED_PEAKS.json hbm_gbs'},
