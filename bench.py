@@ -301,9 +301,18 @@ def run_gpu(args):
   lo, hi = min(rank * per, units), min((rank + 1) * per, units)
   stream = torch.cuda.current_stream()
 
+  # several GPUs: the payoff sums of the ranks are added inside the reduction
+  # kernel over NVLink peer memory (no NCCL call in the step);
+  # TQF_PRICE_PEER_EXCHANGE=0 selects the NCCL all-reduce instead
+  px = None
+  if world > 1 and os.environ.get('TQF_PRICE_PEER_EXCHANGE', '1') != '0':
+    from tff_b200 import distributed
+    px = distributed.PeerExchange()
+    plan.set_peer_exchange(px)
+
   def one_step():
     sums = plan.price_sums(payoffs, lo, hi - lo)
-    if world > 1:
+    if world > 1 and px is None:
       dist.all_reduce(sums)
     return sums
 
@@ -351,8 +360,10 @@ def run_gpu(args):
 
   def e2e_step():
     p = engine.Plan(spec, all_times, steps, x0, engine.RngSpec(**rngkw), n, wdtype)
+    if px is not None:
+      p.set_peer_exchange(px)
     s = p.price_sums(payoffs, lo, hi - lo)
-    if world > 1:
+    if world > 1 and px is None:
       dist.all_reduce(s)
     out = s.cpu().numpy()[:, 0] / n
     p.close()
@@ -405,7 +416,7 @@ def run_gpu(args):
         'dtype': w['dtype'], 'data': 'synthetic',
         'config': {'workload': w['name'] if args.paths is None else w['name'] + ' [paths=%d]' % n,
                    'paths': n, 'euler_steps': steps, 'payoffs': len(payoffs),
-                   'sharding': 'disjoint path ranges per rank; all-reduce of payoff sums',
+                   'sharding': 'disjoint path ranges per rank; payoff sums added over NVLink peer memory inside the reduction kernel (1 GPU: no exchange)',
                    'l2': 'flushed (256 MiB memset) between timed iterations; the kernel reads <100 KB of tables'},
         'prices': prices,
         'clocks': clocks,
@@ -420,6 +431,8 @@ def run_gpu(args):
     }
     emit(line)
   plan.close()
+  if px is not None:
+    px.close()
   if world > 1:
     dist.destroy_process_group()
 

@@ -270,6 +270,16 @@ int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                    int64_t stride_path, int64_t stride_time, int64_t stride_dim,
                    int transform, void* stream);
 
+/* Multi-GPU pricing (one process per GPU of ONE box): once set, every
+ * tqf_plan_price adds the sums of all ranks inside its reduction kernel, over
+ * NVLink peer memory and in rank order (bit-identical sums on every rank), so
+ * sums_dev comes back globally reduced -- replaces the ncclAllReduce of the
+ * payoff sums.  bufs / epoch_base as tqf_lsm_set_peer_exchange; all
+ * ranks must issue the same sequence of tqf_plan_price calls.               */
+int tqf_plan_set_peer_exchange(tqf_plan* plan, int rank, int world, void* const* bufs,
+                               uint64_t epoch_base);
+int tqf_plan_peer_epoch(const tqf_plan* plan, uint64_t* epoch);
+
 /* tqf_plan_paths that also returns, in column_sums_dev (double
  * [num_slots][dim], fully overwritten), the sum over this shard's paths of
  * every stored value (after `transform`): the basis-centring means of the

@@ -55,6 +55,12 @@ def _worker(rank, world, port, out_path):
     # the NCCL-style route (one all-reduce per date) on the same shards
     res.append(lsm.least_square_mc(paths, np.arange(T), put, basis, global_path_offset=lo,
                                    all_reduce=reduce_fn, column_sums=sums, **kw))
+    # fused pricing: the payoff sums of both ranks are added inside the reduction kernel
+    from tff_b200 import engine
+    payoffs = [engine.european_call(1.0, log_state=True), engine.european_put(1.2, log_state=True)]
+    plan.set_peer_exchange(px)
+    fused = [plan.price_sums(payoffs, lo, count).cpu().numpy() for _ in range(3)]
+    np.save(out_path % (10 + rank), np.stack(fused))
     px.close()
     plan.close()
     np.save(out_path % rank, np.stack(res))
@@ -85,6 +91,17 @@ def test_two_ranks_peer_exchange_matches_single_process(tmp_path):
     p.kill()
   assert not hung, 'peer exchange worker did not finish'
   assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+  # fused pricing: both ranks hold the global sums, equal to a single-process run
+  from tff_b200 import engine
+  plan, _, _, _, _, _ = _setup()
+  payoffs = [engine.european_call(1.0, log_state=True), engine.european_put(1.2, log_state=True)]
+  whole = plan.price_sums(payoffs).cpu().numpy()
+  plan.close()
+  fused = [np.load(out % (10 + r)) for r in range(2)]
+  np.testing.assert_array_equal(fused[0], fused[1])
+  for row in fused[0]:
+    np.testing.assert_allclose(row[:, :2], whole[:, :2], rtol=1e-13)
+    np.testing.assert_array_equal(row[:, 2], whole[:, 2])
   got = [np.load(out % r) for r in range(2)]
   # every rank solved from bit-identical sums -> identical prices on both ranks
   np.testing.assert_array_equal(got[0], got[1])

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "tqf_paths_kernel.cuh"
+#include "tqf_peer.cuh"
 
 namespace tqf {
 
@@ -29,7 +30,7 @@ TQF_EXTERN_MODEL(AffineModel4D)
 #undef TQF_EXTERN_MODEL
 
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_blocks,
-                                       int num_payoffs, double* __restrict__ sums) {
+                                       int num_payoffs, double* __restrict__ sums, const PeerK pk) {
   // One warp per (payoff, statistic); fixed summation order -> reproducible.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -42,6 +43,12 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
     }
     v = warp_sum(v);
     if (lane == 0) sums[q * 4 + k] = v;
+  }
+  // several GPUs: the sums of all ranks are added here, over NVLink peer memory
+  // and in rank order (bit-identical on every rank) -- no NCCL call per pricing
+  if (pk.peer_world > 1) {
+    __syncthreads();
+    peer_all_reduce(pk, sums, num_payoffs * 4);
   }
 }
 
@@ -82,6 +89,7 @@ struct tqf_plan {
   uint32_t* sobol_dev;      // [S_total*nf][32]
   const double* logtab_dev; // shared per-device log table (not owned)
   void* lsplit_dev;         // MVGBM dim > 8: factor in the split kernel's order
+  PeerHost peer;            // tqf_plan_set_peer_exchange (world <= 1: single GPU)
   double* colsum_dev;       // [max_grid][slots * dim] column-sum partials (lazily allocated)
   size_t colsum_doubles;
   double* partials_dev;     // [max_grid][TQF_MAX_PAYOFFS][4]
@@ -143,6 +151,19 @@ static int rng_kind(const tqf_plan* plan) {
     case TQF_RNG_SOBOL: return RNGK_SOBOL;
     default: return RNGK_DRAWS;
   }
+}
+
+// Kernel-side descriptor of the next exchange of this plan (advances the epoch).
+static PeerK next_peer_exchange(tqf_plan* plan) {
+  PeerK pk;
+  std::memset(&pk, 0, sizeof(pk));
+  if (plan->peer.world > 1) {
+    pk.peer_rank = plan->peer.rank;
+    pk.peer_world = plan->peer.world;
+    pk.peer_epoch = ++plan->peer.epoch;
+    for (int r = 0; r < plan->peer.world; ++r) pk.peer_bufs[r] = plan->peer.bufs[r];
+  }
+  return pk;
 }
 
 template <typename Real>
@@ -286,7 +307,8 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.exact_log = plan->model.reserved;
     int rc = launch_mvgbm(a, stream, &grid);
     if (rc != TQF_OK) return rc;
-    reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev);
+    reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev,
+                                                  next_peer_exchange(plan));
     TQF_CUDA_OK(cudaGetLastError());
     return TQF_OK;
   }
@@ -300,7 +322,8 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   P.tables_in_smem = in_smem ? 1 : 0;
   int rc = dispatch<Real>(plan, MODE_PRICE, plan->max_grid, smem, P, stream, &grid);
   if (rc != TQF_OK) return rc;
-  reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev);
+  reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev,
+                                                  next_peer_exchange(plan));
   TQF_CUDA_OK(cudaGetLastError());
   return TQF_OK;
 }
@@ -553,6 +576,27 @@ int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                                  stride_time, stride_dim, transform, s)
              : run_paths<float>(plan, path_offset, path_count, record_slot, out_dev, stride_path,
                                 stride_time, stride_dim, transform, s);
+}
+
+int tqf_plan_set_peer_exchange(tqf_plan* plan, int rank, int world, void* const* bufs,
+                               uint64_t epoch_base) {
+  TQF_REQUIRE(plan && bufs, "null argument");
+  TQF_REQUIRE(world >= 1 && world <= kLsmMaxPeers && rank >= 0 && rank < world,
+              "peer exchange supports up to 8 ranks");
+  plan->peer.rank = rank;
+  plan->peer.world = world;
+  plan->peer.epoch = epoch_base;
+  for (int r = 0; r < world; ++r) {
+    TQF_REQUIRE(bufs[r] != nullptr, "null peer buffer");
+    plan->peer.bufs[r] = static_cast<unsigned char*>(bufs[r]);
+  }
+  return TQF_OK;
+}
+
+int tqf_plan_peer_epoch(const tqf_plan* plan, uint64_t* epoch) {
+  TQF_REQUIRE(plan && epoch, "null argument");
+  *epoch = plan->peer.epoch;
+  return TQF_OK;
 }
 
 int tqf_plan_paths_sums(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,

@@ -893,8 +893,9 @@ path_kernel(const KParams<typename Model::Real> P) {
 }
 
 // Deterministic final reduction of the per-CTA partials.
+struct PeerK;
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_blocks,
-                                       int num_payoffs, double* __restrict__ sums);
+                                       int num_payoffs, double* __restrict__ sums, const PeerK pk);
 
 template <typename Real>
 size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool tables_in_smem,

@@ -43,12 +43,18 @@ def all_reduce_(tensor):
   return tensor
 
 
-def price_sharded(plan, payoffs):
+def price_sharded(plan, payoffs, peer_exchange=None):
   """Monte-Carlo means of `payoffs` with the plan's units sharded over the
-  ranks of the default process group.  Returns (mean, stderr) numpy arrays."""
+  ranks of the default process group.  Returns (mean, stderr) numpy arrays.
+  With a `PeerExchange` the sums are added inside the reduction kernel over
+  NVLink peer memory instead of by an NCCL all-reduce."""
   lo, count = shard_units(plan.units)
-  sums = plan.price_sums(list(payoffs), lo, count)
-  all_reduce_(sums)
+  if peer_exchange is not None and peer_exchange.world > 1:
+    plan.set_peer_exchange(peer_exchange)
+    sums = plan.price_sums(list(payoffs), lo, count)
+  else:
+    sums = plan.price_sums(list(payoffs), lo, count)
+    all_reduce_(sums)
   s = sums.cpu().numpy()
   n = float(plan.num_samples)
   mean = s[:, 0] / n

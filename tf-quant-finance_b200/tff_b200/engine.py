@@ -529,9 +529,25 @@ class Plan:
         _tensor.current_stream_ptr()))
     return buf.permute(2, 0, 1)
 
+  def set_peer_exchange(self, peer_exchange):
+    """Several GPUs of one box: every `price_sums` then returns the sums of ALL
+    ranks, added inside the reduction kernel over NVLink peer memory
+    (`tff_b200.distributed.PeerExchange`) -- no NCCL call per pricing.  All ranks
+    must issue the same sequence of `price_sums` calls."""
+    self._peer_exchange = peer_exchange
+    _lib.check(_lib.lib().tqf_plan_set_peer_exchange(
+        self._handle, peer_exchange.rank, peer_exchange.world, peer_exchange.ptrs,
+        peer_exchange.epoch))
+
   def price_sums(self, payoffs, unit_offset=0, unit_count=None):
     """Unnormalised per-payoff sums as a device tensor [num_payoffs, 4]:
     (sum, sum of squares, number of non-finite payoffs, 0)."""
+    px = getattr(self, '_peer_exchange', None)
+    if px is not None:
+      # the buffers may have been used by another plan / the LSM passes meanwhile
+      _lib.check(_lib.lib().tqf_plan_set_peer_exchange(
+          self._handle, px.rank, px.world, px.ptrs, px.epoch))
+      px.epoch += 1
     unit_count = self.units - unit_offset if unit_count is None else unit_count
     descs = (_lib.PayoffDesc * len(payoffs))(*[p.desc() for p in payoffs])
     sums = torch.zeros((len(payoffs), 4), dtype=torch.float64,
