@@ -307,8 +307,12 @@ def run_gpu(args):
   px = None
   if world > 1 and os.environ.get('TQF_PRICE_PEER_EXCHANGE', '1') != '0':
     from tff_b200 import distributed
-    px = distributed.PeerExchange()
-    plan.set_peer_exchange(px)
+    try:
+      px = distributed.PeerExchange()       # fails on ALL ranks together or on none
+      plan.set_peer_exchange(px)
+    except RuntimeError as e:
+      sys.stderr.write('peer exchange unavailable (%s): NCCL all-reduce of the sums\n' % e)
+      px = None
 
   def one_step():
     sums = plan.price_sums(payoffs, lo, hi - lo)
@@ -416,7 +420,7 @@ def run_gpu(args):
         'dtype': w['dtype'], 'data': 'synthetic',
         'config': {'workload': w['name'] if args.paths is None else w['name'] + ' [paths=%d]' % n,
                    'paths': n, 'euler_steps': steps, 'payoffs': len(payoffs),
-                   'sharding': 'disjoint path ranges per rank; payoff sums added over NVLink peer memory inside the reduction kernel (1 GPU: no exchange)',
+                   'sharding': 'disjoint path ranges per rank; ' + ('payoff sums added over NVLink peer memory inside the reduction kernel' if px is not None else ('NCCL all-reduce of the payoff sums' if world > 1 else 'single GPU, no exchange')),
                    'l2': 'flushed (256 MiB memset) between timed iterations; the kernel reads <100 KB of tables'},
         'prices': prices,
         'clocks': clocks,
@@ -477,7 +481,11 @@ def run_gpu_c5(args):
   px = None
   if world > 1:
     from tff_b200 import distributed
-    px = distributed.PeerExchange()
+    try:
+      px = distributed.PeerExchange()       # fails on ALL ranks together or on none
+    except RuntimeError as e:
+      sys.stderr.write('peer exchange unavailable (%s): one NCCL all-reduce per date\n' % e)
+      px = None
   stream = torch.cuda.current_stream()
   times_ms = {'gen': 0.0, 'lsm': 0.0}
 

@@ -107,3 +107,31 @@ def test_shard_units_is_a_partition(units, world):
     prev_end = lo + cnt
     covered += cnt
   assert covered == units and prev_end == units
+
+
+def _peer_worker(rank, world_size, port, out):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world_size)
+  try:
+    from tff_b200 import distributed
+    try:
+      distributed.PeerExchange()
+      result = 'constructed'
+    except RuntimeError as e:
+      result = 'RuntimeError: %s' % e
+    with open(out % rank, 'w') as f:
+      f.write(result)
+  finally:
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_fails_on_all_ranks_together_without_a_gpu(tmp_path):
+  # no CUDA device here: the set-up must fail collectively (RuntimeError on every
+  # rank, nobody left waiting in a barrier) so that callers can fall back to NCCL
+  if torch.cuda.is_available():
+    pytest.skip('needs a machine without a GPU')
+  out = str(tmp_path / 'peer%d.txt')
+  mp.spawn(_peer_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+  for r in range(2):
+    assert open(out % r).read().startswith('RuntimeError: PeerExchange could not be set up')

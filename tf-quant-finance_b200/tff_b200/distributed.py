@@ -86,25 +86,48 @@ class PeerExchange:
     if self.world > 8:
       raise ValueError('PeerExchange supports at most 8 ranks (one box)')
     lib = _lib.lib()
-    _lib.require_cuda()
-    nbytes = C.c_uint64()
-    _lib.check(lib.tqf_lsm_peer_bytes(C.byref(nbytes)))
-    own = C.c_void_p()
-    handle = C.create_string_buffer(64)
-    _lib.check(lib.tqf_peer_alloc(nbytes.value, C.byref(own), handle))
-    self._own = own
+    self._own, self._opened, error = None, [], None
+    handle_bytes = None
+    try:
+      _lib.require_cuda()
+      nbytes = C.c_uint64()
+      _lib.check(lib.tqf_lsm_peer_bytes(C.byref(nbytes)))
+      own = C.c_void_p()
+      handle = C.create_string_buffer(64)
+      _lib.check(lib.tqf_peer_alloc(nbytes.value, C.byref(own), handle))
+      self._own = own
+      handle_bytes = handle.raw
+    except Exception as e:  # pylint: disable=broad-except
+      error = e
+    # every rank takes part in both gathers whatever happened locally, so that a
+    # failure on one rank (no IPC in this container, ...) fails ALL ranks together
     handles = [None] * self.world
-    dist.all_gather_object(handles, handle.raw, group=group)
-    self._opened = []
+    dist.all_gather_object(handles, handle_bytes, group=group)
     ptrs = []
-    for r, h in enumerate(handles):
-      if r == self.rank:
-        ptrs.append(own.value)
-        continue
-      p = C.c_void_p()
-      _lib.check(lib.tqf_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
-      self._opened.append(p)
-      ptrs.append(p.value)
+    if error is None and all(h is not None for h in handles):
+      try:
+        for r, h in enumerate(handles):
+          if r == self.rank:
+            ptrs.append(self._own.value)
+            continue
+          p = C.c_void_p()
+          _lib.check(lib.tqf_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
+          self._opened.append(p)
+          ptrs.append(p.value)
+      except Exception as e:  # pylint: disable=broad-except
+        error = e
+    elif error is None:
+      error = RuntimeError('a peer could not allocate its exchange buffer')
+    oks = [None] * self.world
+    dist.all_gather_object(oks, error is None, group=group)
+    if not all(oks):
+      for p in self._opened:
+        lib.tqf_peer_close(p)
+      if self._own is not None:
+        lib.tqf_peer_free(self._own)
+      self._own, self._opened = None, []
+      raise RuntimeError('PeerExchange could not be set up on every rank: {}'.format(
+          error if error is not None else 'failure on another rank'))
     self.ptrs = (C.c_void_p * self.world)(*ptrs)
     self.epoch = 0          # exchanges performed so far (equal on all ranks)
     dist.barrier(group=group)
