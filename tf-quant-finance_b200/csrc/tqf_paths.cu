@@ -94,6 +94,10 @@ struct tqf_plan {
   size_t colsum_doubles;
   double* partials_dev;     // [max_grid][TQF_MAX_PAYOFFS][4]
   int* record_dev;          // [num_steps+1]
+  // what record_dev holds (and the stream it was uploaded on): a pricing loop
+  // re-sends identical flags every call, a pageable 1 KB copy in front of the kernel
+  std::vector<int>* record_cache;
+  cudaStream_t record_stream;
   SwaptionK* swaptions_dev; // [TQF_MAX_PAYOFFS]
   double x0[64];
   double mu[64], sigma[64];
@@ -151,6 +155,22 @@ static int rng_kind(const tqf_plan* plan) {
     case TQF_RNG_SOBOL: return RNGK_SOBOL;
     default: return RNGK_DRAWS;
   }
+}
+
+// record_dev <- table, unless it already holds exactly that (uploaded on the same stream).
+static cudaError_t upload_record(tqf_plan* plan, const int* table, size_t n, cudaStream_t stream) {
+  if (plan->record_cache && plan->record_stream == stream && plan->record_cache->size() == n &&
+      std::memcmp(plan->record_cache->data(), table, n * sizeof(int)) == 0)
+    return cudaSuccess;
+  const cudaError_t e =
+      cudaMemcpyAsync(plan->record_dev, table, n * sizeof(int), cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  if (!plan->record_cache) plan->record_cache = new (std::nothrow) std::vector<int>();
+  if (plan->record_cache) {
+    plan->record_cache->assign(table, table + n);
+    plan->record_stream = stream;
+  }
+  return cudaSuccess;
 }
 
 // Kernel-side descriptor of the next exchange of this plan (advances the epoch).
@@ -263,8 +283,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     }
   }
   P.monitor = monitor < 0 ? 0 : monitor;
-  TQF_CUDA_OK(cudaMemcpyAsync(plan->record_dev, flags.data(), flags.size() * sizeof(int),
-                              cudaMemcpyHostToDevice, stream));
+  TQF_CUDA_OK(upload_record(plan, flags.data(), flags.size(), stream));
   P.record_slot = plan->record_dev;
   if (!swaptions.empty()) {
     TQF_CUDA_OK(cudaMemcpyAsync(plan->swaptions_dev, swaptions.data(),
@@ -365,8 +384,7 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     P.colsum_cols = cols;
   }
   const size_t nrec = static_cast<size_t>(plan->model.num_steps) + 1;
-  TQF_CUDA_OK(cudaMemcpyAsync(plan->record_dev, record_slot, nrec * sizeof(int),
-                              cudaMemcpyHostToDevice, stream));
+  TQF_CUDA_OK(upload_record(plan, record_slot, nrec, stream));
   P.record_slot = plan->record_dev;
   P.out = static_cast<Real*>(out_dev);
   P.stride_path = stride_path;
@@ -543,6 +561,7 @@ int tqf_plan_destroy(tqf_plan* plan) {
   cudaFree(plan->colsum_dev);
   cudaFree(plan->partials_dev);
   cudaFree(plan->record_dev);
+  delete plan->record_cache;
   cudaFree(plan->swaptions_dev);
   delete plan;
   return TQF_OK;

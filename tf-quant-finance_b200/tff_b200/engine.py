@@ -550,7 +550,8 @@ class Plan:
       px.epoch += 1
     unit_count = self.units - unit_offset if unit_count is None else unit_count
     descs = (_lib.PayoffDesc * len(payoffs))(*[p.desc() for p in payoffs])
-    sums = torch.zeros((len(payoffs), 4), dtype=torch.float64,
+    # (fully overwritten by the reduction kernel)
+    sums = torch.empty((len(payoffs), 4), dtype=torch.float64,
                        device=_tensor.device())
     _lib.check(_lib.lib().tqf_plan_price(
         self._handle, unit_offset, unit_count, descs, len(payoffs),
