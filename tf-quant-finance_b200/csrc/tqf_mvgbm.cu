@@ -660,7 +660,10 @@ constexpr int kMmaIdxBits = 6;
 constexpr int kMmaTiles = 20;                                    // (mt, kt) with kt <= 2 mt + 1
 constexpr int kMmaFragWords = kMmaTiles * 2 * 32 * 4;           // hi / lo fragments
 constexpr int kMmaTabWords = kMmaFragWords + 2 * kMvDim;        // + mu[64], sigma[64]
-constexpr int kMmaTileDims = 256;                                // Sobol dimensions staged at once
+#ifndef TQF_MMA_TILE_DIMS
+#define TQF_MMA_TILE_DIMS 512
+#endif
+constexpr int kMmaTileDims = TQF_MMA_TILE_DIMS;   // Sobol dimensions staged at once (8 steps of 64; 256: +0.8 % time)
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
