@@ -32,10 +32,15 @@ METRIC = 'euler_path_steps_per_sec'
 UNIT = 'path-steps/s'
 
 # Algorithmic FP64-pipe instructions per path-step (DESIGN.md section 4.1,
-# SURVEY.md 8(d)).  C2 = 2 Sobol normals x 32 (t, 1-t^2, table log 8, degree-21
-# polynomial, t*P) + Heston Euler update 14 (sqrt 6, state 8) + barrier compare 1;
-# it was 96 before the table logarithm replaced the 18-instruction log.
-ALGO_FP64_INSTR = {'c1': 26, 'c2': 79, 'c3': 47, 'c4': 3616, 'c5': 25}
+# SURVEY.md 8(d); frozen in roofline.json).  C2 = 2 Sobol normals x 32 (t, 1-t^2,
+# table log 8, degree-21 polynomial, t*P) + Heston Euler update 14 (sqrt 6, state 8)
+# + barrier compare 1; it was 96 before the table logarithm replaced the
+# 18-instruction log.  C3 / C1 were 47 / 26 (SURVEY's budget of 44 per Philox +
+# Box-Muller normal); the hand-written log / sqrt / sincos need 25 per normal (a
+# Box-Muller evaluation of ~50 yields TWO normals), so A = 25 + 4 (C3) and
+# 25 / 2 + 3.5 (C1, antithetic: one normal serves two paths): SURVEY allows A to be
+# tightened only downward, and ncu shows the C3 kernel executing 29.7 per path-step.
+ALGO_FP64_INSTR = {'c1': 16, 'c2': 79, 'c3': 29, 'c4': 3616, 'c5': 22}
 
 WORKLOADS = {
     'c1': dict(name='C1 GBM call (log-space affine), 100k paths x 100 steps, fp64, PSEUDO_ANTITHETIC seed 42',
