@@ -413,7 +413,10 @@ def run_gpu(args):
                 'note': 'achieved = path-steps/s/GPU x %d algorithmic %s instr per path-step; '
                         'peak = %s issue rate measured live by tqf_measure_fp64_peak '
                         '(MEASURED_PEAKS.json has no FP64/FP32 entry); kernel has no HBM traffic'
-                        % (algo, 'FP32' if fp32 else 'FP64', 'FFMA' if fp32 else 'DFMA')}
+                        % (algo, 'FP32' if fp32 else 'FP64', 'FFMA' if fp32 else 'DFMA')
+                        + ('; C3 is bound by the dispatch port, not by the FP64 pipe: 30 FP64 + 59 other '
+                           'instructions per path-step, 47 of them the Philox rounds (roofline.json)'
+                           if args.workload == 'c3' else '')}
     cores = 1
     csample = {'c1': 100_000, 'c2': 32768, 'c3': 65536, 'c4': 1024, 'c5': 65536}[args.workload]
     cv, cdt, csteps, cn = cpu_run(args.workload, csample, cores)
