@@ -190,3 +190,67 @@ def test_hw_exact_tables_match_oracle():
   fwd, fwd_grad = _exact.forward_rate_fns(lambda t: 0.01 + 0.002 * t, np.float64)
   np.testing.assert_allclose(fwd(np.array([0.0, 1.0])), [0.01, 0.014], rtol=1e-14)
   np.testing.assert_allclose(fwd_grad(np.array([0.0, 1.0])), [0.004, 0.004], rtol=1e-9)
+
+
+# ----- host tables of the generators / model specs added for SURVEY 8f (no GPU needed)
+def test_halton_host_tables_equal_the_oracle():
+  from oracle import halton as ohalton
+  from tff_b200.math.random import halton
+  for dtype in (np.float32, np.float64):
+    for dim in (1, 2, 40, 1000):
+      radixes, sizes, weights, max_size = halton._tables(dim, np.dtype(dtype))
+      np.testing.assert_array_equal(radixes, ohalton.primes(dim))
+      np.testing.assert_array_equal(sizes, ohalton.max_sizes_by_axes(dim, dtype).reshape(-1).astype(np.int32))
+      assert max_size == int(sizes.max()) and weights.shape == (dim, max_size)
+      # weights = round(radix ** j) in dtype, exactly representable, 1 beyond an axis' own digits
+      for d in (0, dim - 1):
+        p = int(radixes[d])
+        np.testing.assert_array_equal(weights[d, :sizes[d]], [float(p**j) for j in range(sizes[d])])
+        assert np.all(weights[d, sizes[d]:] == 1.0)
+  assert halton._first_primes(1000)[-1] == 7919
+  with pytest.raises(NotImplementedError):
+    halton.sample(3, num_results=4)                       # randomized=True is the reference's default
+  with pytest.raises(ValueError):
+    halton.sample(3, randomized=False)
+  with pytest.raises(NotImplementedError):
+    halton._range_of(None, np.array([0, 2, 5]))           # non-contiguous indices
+
+
+def test_milstein_and_tangent_specs_build_the_documented_tables():
+  from tff_b200 import engine
+  all_times = np.array([0.0, 0.25, 0.5, 1.0])
+  gbm = engine.GbmSpec1F(0.05, lambda t: 0.2 + 0.1 * np.asarray(t))
+  tab = engine.MilsteinSpec1F(gbm).coef_table(all_times, np.float64)
+  assert tab.shape == (3, 6)
+  np.testing.assert_allclose(tab[:, 0], [0.25, 0.25, 0.5])
+  np.testing.assert_allclose(tab[:, 1], np.sqrt([0.25, 0.25, 0.5]))
+  np.testing.assert_array_equal(tab[:, 2], 0.0)                       # a0
+  np.testing.assert_allclose(tab[:, 3], 0.05)                         # a1 = mu
+  np.testing.assert_array_equal(tab[:, 4], 0.0)                       # b0
+  np.testing.assert_allclose(tab[:, 5], [0.225, 0.25, 0.3])           # b1 = sigma(times[i + 1])
+  aff = engine.AffineSpec1F(0.1, -0.2, 0.3, 0.4)
+  np.testing.assert_array_equal(engine.MilsteinSpec1F(aff).coef_table(all_times, np.float64),
+                                aff.coef_table(all_times, np.float64))
+  with pytest.raises(NotImplementedError):
+    engine.MilsteinSpec1F(engine.HestonEulerSpec(2.0, 0.04, 0.5, -0.7))
+  tan = engine.TangentAffineSpec1F(0.1, -0.2, 0.3, 0.4, da0=1.0, db=2.0)
+  tab = tan.coef_table(all_times, np.float64)
+  assert tab.shape == (3, 10) and tan.dim == 3 and tan.user_dim == 1
+  np.testing.assert_allclose(tab[0], [0.25, 0.5, 0.1, -0.2, 0.3, 0.4, 1.0, 0.0, 2.0, 0.0])
+  np.testing.assert_array_equal(tan.extend_initial_state(np.array([1.5])), [1.5, 1.0, 0.0])
+
+
+def test_uniform_and_milstein_argument_errors_need_no_gpu():
+  import tff_b200 as tff
+  rt = tff.math.random.RandomType
+  with pytest.raises(ValueError):
+    tff.math.random.uniform(2, [4], random_type=rt.STATELESS)                 # no seed
+  with pytest.raises(NotImplementedError):
+    tff.math.random.uniform(2, [4], random_type=rt.PSEUDO_ANTITHETIC, seed=1)
+  from tff_b200.models import closures
+  drift, vol = closures.gbm_closures(0.1, 0.2)
+  with pytest.raises(NotImplementedError):
+    tff.models.milstein_sampling.sample(dim=2, drift_fn=drift, volatility_fn=vol, times=[1.0],
+                                        time_step=0.1)
+  with pytest.raises(ValueError):
+    tff.models.milstein_sampling.sample(dim=1, drift_fn=drift, volatility_fn=vol, times=[1.0])
