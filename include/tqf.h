@@ -369,7 +369,9 @@ int tqf_lsm_step(tqf_lsm* lsm, int do_update, int t_update, const double* mean_u
  * layout (K <= 6) only; TQF_ERR_UNSUPPORTED otherwise (solve on the host). */
 int tqf_lsm_solve(tqf_lsm* lsm, double* sums_dev, int reduce_partials, double rcond,
                   double* beta_dev, void* stream);
-/* Fused regression solve for the single-asset vectorised pass (dim 1,
+/* Fused regression solve -- `beta = pinv(X'X) X'y` of lsm.py:369-377, which the
+ * reference evaluates as separate matmul / pinv ops per exercise date -- for
+ * the single-asset vectorised pass (dim 1,
  * K <= 6, contiguous time-major paths, even path count): once set, every
  * tqf_lsm_step that accumulates also reduces its per-CTA partials into
  * sums_dev [B][27] and writes beta [B][K] for the accumulated date, from the
