@@ -18,12 +18,20 @@ Pinning status
   prices are pinned by the reference's own known-answer tests
   (tests/test_oracle_kat.py lists each with its file:line).
 * The Philox4x32-10 core is pinned by the Random123 known-answer vectors.
-* **parity unpinned**: the TensorFlow-specific part of the pseudo-random
-  stream (seed -> key/counter scrambling of `tf.random.stateless_normal`, the
-  op-seed pair of `tf.random.normal`, uint32 -> float conversion and the
-  Box-Muller constants) lives in TensorFlow's C++ sources, which are neither
-  under /root/reference nor installed here, and no reference test holds an
-  output value of that stream.  It is restated from the published TensorFlow
-  algorithm (tensorflow==2.12.0rc1 is the version pinned by the reference's
-  ci_build/Dockerfile:17) -- see oracle/philox.py.
+* The TensorFlow-specific part of the float32 pseudo-random stream (seed ->
+  key/counter scrambling of `tf.random.stateless_normal`, the group / counter
+  layout, `Uint32ToFloat`, `BoxMullerFloat`) is pinned by the two vectors
+  TensorFlow publishes in its own documentation (`tf.random.stateless_normal(
+  [2, 3], seed=[1, 2])` and `tf.random.Generator.from_seed(1).normal([2, 3])`),
+  tests/test_oracle_kat.py::test_philox_tensorflow_published_*.
+* **parity unpinned** (only this): the float64 conversion `Uint64ToDouble` /
+  `BoxMullerDouble` and the op-seed pair `(87654321, s)` of the stateful
+  `tf.random.normal(seed=s)`.  TensorFlow cannot be installed in this image and
+  neither its documentation nor any test of the reference prints a float64
+  value of the stream.  They are restated from the published TensorFlow source
+  (tensorflow==2.12.0rc1, the version pinned by the reference's
+  ci_build/Dockerfile:17) in oracle/philox.py and held to what CAN be checked
+  without TensorFlow: the float64 stream consumes the same (pinned) raw words,
+  its uniforms have the documented bit layout and its normals invert back to
+  those uniforms (z0^2 + z1^2 = -2 ln u1, atan2(z0, z1) = 2 pi u2).
 """

@@ -19,10 +19,14 @@ version pinned in the reference's `ci_build/Dockerfile:17`):
 * `tensorflow/python/framework/random_seed.py` -- `get_seed`: with no global
   seed an op seed s becomes the pair (87654321, s).
 
-PARITY UNPINNED for everything in this list except the Philox core: no test
-of the reference contains an output value of these streams and TensorFlow
-cannot be run in this image.  The core is pinned by the Random123 known-answer
-vectors (tests/test_oracle_kat.py).
+Pinned: the Philox core by the Random123 known-answer vectors; the float32
+stream end to end (GenerateKey, counter layout, Uint32ToFloat, BoxMullerFloat)
+by the two vectors TensorFlow prints in its documentation
+(tests/test_oracle_kat.py::test_philox_tensorflow_published_*).
+PARITY UNPINNED: `Uint64ToDouble` / `BoxMullerDouble` (float64) and the
+stateful op-seed pair -- no published float64 value exists and TensorFlow
+cannot be run in this image; they are held to internal consistency with the
+pinned words only.
 """
 import numpy as np
 

@@ -64,6 +64,39 @@ def test_stateful_normal_first_call(dtype):
   _close(got, want, dtype)
 
 
+def test_philox_tensorflow_published_vectors_on_the_device():
+  # The values TensorFlow prints in its own documentation
+  # (tests/test_oracle_kat.py::test_philox_tensorflow_published_*), produced by the
+  # CUDA generator through the C ABI.
+  tff = _tff()
+  from tff_b200.math.random import philox
+  got = _np(tff.math.random.stateless_normal([2, 3], [1, 2], np.float32))
+  np.testing.assert_allclose(
+      got, [[0.5441101, 0.20738031, 0.07356433], [0.04643455, -1.3015898, -0.95385665]],
+      rtol=1e-5, atol=1e-7)
+  import ctypes as C
+  got = _np(philox._fill((C.c_uint32 * 2)(0, 0), (C.c_uint32 * 4)(1, 0, 0, 0),
+                         [2, 3], np.float32))
+  np.testing.assert_allclose(
+      got, [[0.43842277, -0.53439844, -0.07710262], [1.5658046, -0.1012345, -0.2744976]],
+      rtol=1e-5, atol=1e-7)
+
+
+def test_philox_fp64_box_muller_identities_on_the_device():
+  # float64: same raw words (bit-exact above), Uint64ToDouble + BoxMullerDouble:
+  # z0^2 + z1^2 = -2 ln u1, atan2(z0, z1) = 2 pi u2
+  from tff_b200.math.random import philox
+  key, ctr = philox.stateless_key_counter([1, 2])
+  z = _np(philox._fill(key, ctr, [8192], np.float64)).reshape(-1, 2)
+  okey, octr = ophilox.stateless_key_counter([1, 2])
+  words = ophilox.raw_words(okey, octr, 0, 4096)
+  u1 = np.maximum(ophilox.uint64_to_double(words[:, 0], words[:, 1]), 1e-7)
+  u2 = ophilox.uint64_to_double(words[:, 2], words[:, 3])
+  np.testing.assert_allclose((z**2).sum(axis=1), -2 * np.log(u1), rtol=1e-12)
+  ang = np.arctan2(z[:, 0], z[:, 1]) % (2 * np.pi)
+  np.testing.assert_allclose(ang, 2 * np.pi * u2, rtol=0, atol=1e-11)
+
+
 @pytest.mark.parametrize('dtype', [np.float64, np.float32])
 @pytest.mark.parametrize('first', [1, 2, 3, 1000003])
 def test_normal_fill_offsets(dtype, first):

@@ -165,6 +165,55 @@ def test_philox_counter_add_carries():
                           [0, 0, 8, 1], [1, 0, 8, 1]]
 
 
+# Values TensorFlow itself publishes for these streams (TensorFlow "Random number
+# generation" guide and the API docs of tf.random.stateless_normal): the seed
+# scrambling (GenerateKey), the group / counter layout, Uint32ToFloat and
+# BoxMullerFloat of oracle/philox.py are pinned by them.
+TF_STATELESS_NORMAL_2x3_SEED_1_2 = np.array(
+    [[0.5441101, 0.20738031, 0.07356433], [0.04643455, -1.3015898, -0.95385665]], np.float32)
+TF_GENERATOR_FROM_SEED_1_NORMAL_2x3 = np.array(
+    [[0.43842277, -0.53439844, -0.07710262], [1.5658046, -0.1012345, -0.2744976]], np.float32)
+
+
+def test_philox_tensorflow_published_stateless_normal():
+  # tf.random.stateless_normal([2, 3], seed=[1, 2]) as printed in TensorFlow's docs
+  got = philox.stateless_normal([2, 3], [1, 2], np.float32)
+  np.testing.assert_allclose(got, TF_STATELESS_NORMAL_2x3_SEED_1_2, rtol=2e-7, atol=1e-8)
+
+
+def test_philox_tensorflow_published_generator_normal():
+  # tf.random.Generator.from_seed(1).normal([2, 3]) (RNG guide): state = [1, 0, 0]
+  # -> counter = [1, 0, 0, 0], key = [0, 0]; same Philox / Box-Muller kernels
+  got = philox.normal_fill(np.array([0, 0], np.uint32), np.array([1, 0, 0, 0], np.uint32),
+                           6, np.float32).reshape(2, 3)
+  np.testing.assert_allclose(got, TF_GENERATOR_FROM_SEED_1_NORMAL_2x3, rtol=2e-7, atol=1e-8)
+
+
+def test_philox_fp64_stream_is_consistent_with_the_pinned_fp32_one():
+  # No TensorFlow publication holds float64 values.  What can be pinned without
+  # TF: (i) float64 consumes the SAME raw words, two groups of two words per pair
+  # of normals; (ii) Uint64ToDouble is the bit layout of random_distributions.h
+  # (mantissa = low 20 bits of word 0 | word 1); (iii) BoxMullerDouble inverts:
+  # z0^2 + z1^2 = -2 ln u1 and atan2(z0, z1) = 2 pi u2 for the uniforms of (ii).
+  key, ctr = philox.stateless_key_counter([1, 2])
+  words = philox.raw_words(key, ctr, 0, 4096)
+  z = philox.normal_fill(key, ctr, 8192, np.float64).reshape(-1, 2)
+  u1 = philox.uint64_to_double(words[:, 0], words[:, 1])
+  u2 = philox.uint64_to_double(words[:, 2], words[:, 3])
+  bits = (u1 + 1.0).view(np.uint64)
+  np.testing.assert_array_equal(bits >> np.uint64(52), 1023)
+  np.testing.assert_array_equal(
+      bits & np.uint64((1 << 52) - 1),
+      ((words[:, 0].astype(np.uint64) & np.uint64(0xFFFFF)) << np.uint64(32))
+      | words[:, 1].astype(np.uint64))
+  np.testing.assert_allclose((z**2).sum(axis=1), -2 * np.log(np.maximum(u1, 1e-7)), rtol=1e-13)
+  ang = np.arctan2(z[:, 0], z[:, 1]) % (2 * np.pi)
+  np.testing.assert_allclose(ang, 2 * np.pi * u2, rtol=0, atol=1e-12)
+  # the float32 stream of the same seed starts from the same first group
+  f = philox.normals_from_words(words[:1], np.float32)
+  np.testing.assert_allclose(f[:3], TF_STATELESS_NORMAL_2x3_SEED_1_2[0], rtol=2e-7)
+
+
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
 def test_stateless_prefix_stability_and_moments(dtype):
   # math/random_ops/multivariate_normal_test.py:342-380 (structure only)
