@@ -270,6 +270,14 @@ int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                    int64_t stride_path, int64_t stride_time, int64_t stride_dim,
                    int transform, void* stream);
 
+/* float32 Sobol draws beyond 2^24 points: the uniform RN(x) 2^-32 can be exactly
+ * 1.0 and the reference's `erfinv((u - 0.5) * 2)` (multivariate_normal.py:420)
+ * returns +inf (config C4 at 20 M paths).  Strict mode (default,
+ * clamp = 0) reproduces that: the path's payoff is non-finite and is COUNTED in
+ * sums[.][2] instead of summed.  clamp = 1 is a documented non-reference mode:
+ * such a draw uses the largest float32 below one.  float64 is unaffected.   */
+int tqf_plan_set_sobol_clamp(tqf_plan* plan, int clamp);
+
 /* Multi-GPU pricing (one process per GPU of ONE box): once set, every
  * tqf_plan_price adds the sums of all ranks inside its reduction kernel, over
  * NVLink peer memory and in rank order (bit-identical sums on every rank), so

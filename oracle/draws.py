@@ -125,15 +125,56 @@ def mv_normal_sample(sample_shape, mean, random_type=None, seed=None,
       'SOBOL are restated by the oracle. Supplied: {}'.format(random_type))
 
 
+def _draws_of_path_range(num_normal_draws, num_time_steps, num_sample_paths,
+                         random_type, skip, seed, dtype, path_range):
+  """Rows [lo, hi) of the `[num_sample_paths, steps * draws]` matrix that
+  `generate_mc_normal_draws` builds, WITHOUT building the rest (chunked /
+  multi-process oracle runs at the BASELINE sizes).  Row p of the Philox matrix
+  is elements [p D, (p + 1) D) of the flat stream, row p of the Sobol matrix is
+  point skip + 1 + p (its value does not depend on `num_digits`).  For the
+  antithetic types [lo, hi) addresses the first half and the partners
+  `2 mean - r = -r` follow, like `_mvnormal_pseudo_antithetic`."""
+  lo, hi = int(path_range[0]), int(path_range[1])
+  d = num_time_steps * num_normal_draws
+  anti = random_type in (RandomType.PSEUDO_ANTITHETIC, RandomType.STATELESS_ANTITHETIC)
+  limit = num_sample_paths // 2 if anti else num_sample_paths
+  if not 0 <= lo <= hi <= limit:
+    raise ValueError('path_range outside the run')
+  if random_type == RandomType.SOBOL:
+    u = sobol.sample(d, hi - lo, skip=skip + lo, dtype=dtype)
+    rows = _erfinv_times_sqrt2(u, dtype)
+  elif random_type in (RandomType.PSEUDO, RandomType.PSEUDO_ANTITHETIC):
+    key, ctr = philox.stateful_key_counter(seed)
+    rows = philox.normal_fill(key, ctr, (hi - lo) * d, dtype, first_element=lo * d)
+  elif random_type in (RandomType.STATELESS, RandomType.STATELESS_ANTITHETIC):
+    key, ctr = philox.stateless_key_counter(seed)
+    rows = philox.normal_fill(key, ctr, (hi - lo) * d, dtype, first_element=lo * d)
+  else:
+    raise NotImplementedError(random_type)
+  rows = rows.reshape(hi - lo, num_time_steps, num_normal_draws)
+  if anti:
+    rows = np.concatenate([rows, -rows], axis=0)
+  return np.transpose(rows, [1, 0, 2])
+
+
 def generate_mc_normal_draws(num_normal_draws, num_time_steps,
                              num_sample_paths, random_type, batch_shape=None,
-                             skip=0, seed=None, dtype=None):
-  """`models/utils.py:20-128` -> [steps] + batch_shape + [paths, draws]."""
+                             skip=0, seed=None, dtype=None, path_range=None):
+  """`models/utils.py:20-128` -> [steps] + batch_shape + [paths, draws].
+
+  `path_range=(lo, hi)` (oracle extension, no batch): only the paths lo..hi-1 of
+  the `num_sample_paths`-path call (for the antithetic types: of its first
+  half, partners appended) -- see `_draws_of_path_range`."""
   if skip is None:
     skip = 0
   dtype = np.dtype(np.float32 if dtype is None else dtype)
   batch_shape = tuple(batch_shape or ())
   random_type = RandomType(random_type.value)
+  if path_range is not None:
+    if batch_shape:
+      raise NotImplementedError('path_range with a batch')
+    return _draws_of_path_range(num_normal_draws, num_time_steps, num_sample_paths,
+                                random_type, skip, seed, dtype, path_range)
   total_dimension = np.zeros(num_time_steps * num_normal_draws, dtype=dtype)
   if random_type in (RandomType.PSEUDO_ANTITHETIC,
                      RandomType.STATELESS_ANTITHETIC):

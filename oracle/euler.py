@@ -18,8 +18,14 @@ from oracle import grid as grid_lib
 def sample(dim, drift_fn, volatility_fn, times, time_step=None,
            num_time_steps=None, num_samples=1, initial_state=None,
            random_type=None, seed=None, skip=0, times_grid=None,
-           normal_draws=None, tolerance=None, dtype=None, return_grid=False):
-  """`euler_sampling.sample` -> batch_shape + [num_samples, k, dim]."""
+           normal_draws=None, tolerance=None, dtype=None, return_grid=False,
+           path_range=None, return_extrema=False):
+  """`euler_sampling.sample` -> batch_shape + [num_samples, k, dim].
+
+  Oracle extensions: `path_range` (a slice of the paths, see
+  `draws.generate_mc_normal_draws`); `return_extrema` also returns the running
+  maximum and minimum of state component 0 over the initial state and every
+  executed step (what a barrier monitored on all grid points sees)."""
   if dtype is None:
     dtype = np.asarray(times).dtype
     if dtype.kind != 'f':
@@ -56,7 +62,10 @@ def sample(dim, drift_fn, volatility_fn, times, time_step=None,
         num_sample_paths=num_samples, batch_shape=batch_shape,
         random_type=(draws_lib.RandomType.PSEUDO if random_type is None
                      else random_type),
-        dtype=dtype, seed=seed, skip=skip)
+        dtype=dtype, seed=seed, skip=skip, path_range=path_range)
+    if path_range is not None:         # oracle extension: a slice of the paths
+      num_samples = normal_draws.shape[-2]
+      state = initial_state + np.zeros([num_samples, dim], dtype=dtype)
 
   record = k != 1
   written = 0
@@ -65,6 +74,8 @@ def sample(dim, drift_fn, volatility_fn, times, time_step=None,
     slots[0] = state
   written += int(keep_mask[0])
   i = 0
+  xmax = np.array(state[..., 0])
+  xmin = np.array(state[..., 0])
   while i < steps_num and written < k:                       # cond_fn :426-431
     t = all_times[i + 1]
     dw = normal_draws[i] * sqrt_dt[i]
@@ -72,6 +83,9 @@ def sample(dim, drift_fn, volatility_fn, times, time_step=None,
     vol = volatility_fn(t, state)
     dw_inc = np.einsum('...ij,...j->...i', vol, dw).astype(dtype)
     state = (state + dt_inc + dw_inc).astype(dtype)
+    if return_extrema:
+      xmax = np.maximum(xmax, state[..., 0])
+      xmin = np.minimum(xmin, state[..., 0])
     if record:
       slots[written] = state
     written += int(keep_mask[i + 1])
@@ -82,6 +96,8 @@ def sample(dim, drift_fn, volatility_fn, times, time_step=None,
     res = np.stack(slots, axis=0)                 # [k] + batch + [N, dim]
     n = res.ndim
     out = np.transpose(res, list(range(1, n - 1)) + [0, n - 1])
+  if return_extrema:
+    return out, xmax, xmin
   if return_grid:
     return out, (all_times, keep_mask, time_indices)
   return out

@@ -65,7 +65,8 @@ def _update_log_spot(kappa, theta, volvol, rho, v, v_next, x, dt, z, g1=0.5, g2=
 def sample_paths(mean_reversion, theta, volvol, rho, times, initial_state,
                  num_samples=1, random_type=None, seed=None, time_step=None,
                  skip=0, tolerance=1e-6, num_time_steps=None, times_grid=None,
-                 normal_draws=None, dtype=np.float64):
+                 normal_draws=None, dtype=np.float64, path_range=None,
+                 return_extrema=False):
   """`HestonModel.sample_paths` -> [num_samples, k, 2] (log-spot, variance)."""
   dtype = np.dtype(dtype)
   times = np.asarray(times, dtype=dtype)
@@ -94,7 +95,8 @@ def sample_paths(mean_reversion, theta, volvol, rho, times, initial_state,
     normal_draws = draws_lib.generate_mc_normal_draws(
         2, steps, num_samples,
         draws_lib.RandomType.PSEUDO if random_type is None else random_type,
-        dtype=dtype, seed=seed, skip=skip)
+        dtype=dtype, seed=seed, skip=skip, path_range=path_range)
+    num_samples = normal_draws.shape[1]
   else:
     normal_draws = np.transpose(np.asarray(normal_draws, dtype), [1, 0, 2])
     num_samples = normal_draws.shape[1]
@@ -106,6 +108,7 @@ def sample_paths(mean_reversion, theta, volvol, rho, times, initial_state,
     xs[0], vs[0] = x, v
   written = int(keep_mask[0])
   i = 0
+  xmax, xmin = np.array(x), np.array(x)      # oracle extension (return_extrema)
   while i < steps and written < k:
     z = normal_draws[i]
     if dt[i] > tolerance:
@@ -113,13 +116,16 @@ def sample_paths(mean_reversion, theta, volvol, rho, times, initial_state,
       x = _update_log_spot(kap[i], th[i], vv[i], rh[i], v, v_next, x, dt[i],
                            z[..., 1]).astype(dtype)
       v = v_next
+    xmax, xmin = np.maximum(xmax, x), np.minimum(xmin, x)
     if record:
       xs[written], vs[written] = x, v
     written += int(keep_mask[i + 1])
     i += 1
   if not record:
-    return np.stack([x[:, None], v[:, None]], -1)
+    out = np.stack([x[:, None], v[:, None]], -1)
+    return (out, xmax, xmin) if return_extrema else out
   zeros = np.zeros(num_samples, dtype)
   xs = [zeros if a is None else a for a in xs]
   vs = [zeros if a is None else a for a in vs]
-  return np.stack([np.stack(xs, 0).T, np.stack(vs, 0).T], -1)
+  out = np.stack([np.stack(xs, 0).T, np.stack(vs, 0).T], -1)
+  return (out, xmax, xmin) if return_extrema else out

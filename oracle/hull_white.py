@@ -110,7 +110,7 @@ class HullWhiteModel1F:
     return all_times, mask
 
   def sample_paths(self, times, num_samples, random_type=None, seed=None,
-                   skip=0, times_grid=None, normal_draws=None):
+                   skip=0, times_grid=None, normal_draws=None, path_range=None):
     """Short-rate paths [num_samples, k, 1] (`_sample_paths` 641-781).
 
     PSEUDO types are given the precomputed-draws layout of the STATELESS types
@@ -125,7 +125,8 @@ class HullWhiteModel1F:
       normal_draws = draws_lib.generate_mc_normal_draws(
           1, steps, num_samples,
           draws_lib.RandomType.PSEUDO if random_type is None else random_type,
-          seed=seed, dtype=self.dtype, skip=skip)
+          seed=seed, dtype=self.dtype, skip=skip, path_range=path_range)
+      num_samples = normal_draws.shape[1]
     else:
       normal_draws = np.transpose(np.asarray(normal_draws, self.dtype), [1, 0, 2])
     exp_x_t = self.conditional_mean_x(all_times)
@@ -173,12 +174,13 @@ class HullWhiteModel1F:
     return self.bond_reconstitution(times, maturities, r, y_t)[..., None]
 
   def sample_discount_curve_paths(self, times, curve_times, num_samples,
-                                  random_type=None, seed=None, skip=0):
+                                  random_type=None, seed=None, skip=0, path_range=None):
     """(P(t, t+tau) [N, m, k, 1], r_t [N, k, 1]) (`...py:451-592`)."""
     times = np.asarray(times, dtype=self.dtype)
     curve_times = np.asarray(curve_times, dtype=self.dtype)
     y_t = self.compute_yt(times)
-    rates = self.sample_paths(times, num_samples, random_type, seed, skip)
+    rates = self.sample_paths(times, num_samples, random_type, seed, skip,
+                              path_range=path_range)
     r = rates[:, None, :, 0]                                 # [N, 1, k]
     t = times[None, None, :]
     tau = curve_times[None, :, None]
@@ -191,7 +193,7 @@ def swaption_price_mc(*, expiries, fixed_leg_payment_times,
                       reference_rate_fn, mean_reversion, volatility,
                       notional=1.0, is_payer_swaption=True, num_samples=100,
                       random_type=None, seed=None, skip=0, time_step=None,
-                      dtype=np.float64, return_payoffs=False):
+                      dtype=np.float64, return_payoffs=False, path_range=None):
   """`swaption_price(use_analytic_pricing=False)` (`swaption.py:216-312`) with
   `discount_factors_and_bond_prices_from_samples` (`hjm/swaption_util.py:28-170`).
 
@@ -215,7 +217,8 @@ def swaption_price_mc(*, expiries, fixed_leg_payment_times,
   tau = pay_t - exp_b
   curve_times = np.unique(tau.reshape(-1))
   p_t_tau, r_t = model.sample_discount_curve_paths(
-      sim_times, curve_times, num_samples, random_type, seed, skip)
+      sim_times, curve_times, num_samples, random_type, seed, skip, path_range=path_range)
+  num_samples = r_t.shape[0]           # path_range (oracle extension): a slice of the paths
   # path discount factors: dt_0 = 0 (the first interval is not discounted)
   dt = np.concatenate([[0.0], sim_times[1:] - sim_times[:-1]]).astype(dtype)
   cumul = np.cumsum(r_t[:, :, 0] * dt[None, :], axis=1)       # [N, k]

@@ -15,8 +15,9 @@ KEYS = ['metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step',
         'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline']
 
 
-@pytest.mark.parametrize('workload,paths', [('c1', 20000), ('c2', 200000), ('c3', 200000),
-                                            ('c4', 20000), ('c5', 100000)])
+@pytest.mark.parametrize('workload,paths', [('c1', 20000), ('c2', 200000), ('c2_qe', 200000),
+                                            ('c3', 200000), ('c4', 20000), ('c5', 100000),
+                                            ('materialise', 100000)])
 def test_bench_workload_runs(workload, paths):
   out = subprocess.run(
       [sys.executable, os.path.join(ROOT, 'bench.py'), '--workload', workload,

@@ -89,3 +89,34 @@ def test_fp32_sobol_uniform_equal_to_one_gives_inf():
       random_type=tff.math.random.RandomType.SOBOL, skip=18684944 - 100,
       num_time_steps=1, return_stats=True)
   assert bad[0] >= 1
+
+
+def test_fp32_sobol_clamped_mode_keeps_the_hazard_paths_finite():
+  # tqf_plan_set_sobol_clamp: u == 1.0 -> largest float32 below one (z = ndtri(1 - 2^-24)
+  # = 5.42); every other draw, hence every other path, is unchanged.
+  import tff_b200 as tff
+  from tff_b200 import engine
+  from tff_b200.models import closures
+  from tff_b200.models import utils
+  tff_, model, _, x0 = _setup(16, np.float32)
+  spec = closures.resolve_spec(model.drift_fn(), model.volatility_fn())
+  all_times, mask, _ = utils.prepare_grid(times=np.array([1.0], np.float32),
+                                          time_step=np.float32(1.0), num_time_steps=1,
+                                          dtype=np.float32)
+  steps, _ = engine.record_plan(mask, 1)
+  rng = engine.RngSpec(tff.math.random.RandomType.SOBOL, None, 18684944 - 100)
+  plan = engine.Plan(spec, all_times, steps, x0, rng, 256, np.float32)
+  try:
+    pay = [engine.identity(component=12), engine.european_call(100.0, component=-1)]
+    strict = plan.price_sums(pay).cpu().numpy()
+    plan.set_sobol_clamp(True)
+    clamped = plan.price_sums(pay).cpu().numpy()
+    plan.set_sobol_clamp(False)
+    again = plan.price_sums(pay).cpu().numpy()
+  finally:
+    plan.close()
+  assert strict[0, 2] >= 1 and np.all(clamped[:, 2] == 0)
+  np.testing.assert_array_equal(strict, again)
+  # the hazard path now contributes a finite value: asset 12 moved by +5.42 sigma sqrt(dt)
+  extra = clamped[0, 0] - strict[0, 0]
+  assert 100.0 < extra / strict[0, 2] < 2000.0

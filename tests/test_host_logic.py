@@ -254,3 +254,37 @@ def test_uniform_and_milstein_argument_errors_need_no_gpu():
                                         time_step=0.1)
   with pytest.raises(ValueError):
     tff.models.milstein_sampling.sample(dim=1, drift_fn=drift, volatility_fn=vol, times=[1.0])
+
+
+# ProbedAffineSpec (engine.py): plain Python callables are accepted only when they
+# are affine on the WHOLE state space; the probing runs on the host.
+@pytest.mark.parametrize('name', ['relu', 'abs', 'clamp', 'cutoff', 'reciprocal', 'log'])
+def test_probed_affine_spec_rejects_piecewise_and_singular_callables(name):
+  import torch
+  from tff_b200 import engine
+  drifts = {
+      'relu': lambda t, x: torch.relu(x),
+      'abs': lambda t, x: torch.abs(x),
+      'clamp': lambda t, x: torch.clamp(x, -50.0, 50.0),
+      'cutoff': lambda t, x: torch.where(x > 130.0, torch.zeros_like(x), 0.1 * x),
+      'reciprocal': lambda t, x: 1.0 / x,
+      'log': lambda t, x: torch.log(x),
+  }
+  vol = lambda t, x: 0.2 * torch.ones_like(x).unsqueeze(-1)
+  spec = engine.ProbedAffineSpec(1, drifts[name], vol)
+  spec.initial_state_hint = np.array([100.0])
+  with pytest.raises(NotImplementedError):
+    spec.coef_table(np.linspace(0.0, 1.0, 5), np.float64)
+
+
+def test_probed_affine_spec_accepts_affine_callables():
+  import torch
+  from tff_b200 import engine
+  spec = engine.ProbedAffineSpec(
+      2, lambda t, x: torch.stack([0.1 * t + 0.5 * x[..., 1], -0.3 * x[..., 0] + 1.0], -1),
+      lambda t, x: torch.eye(2, dtype=x.dtype).expand(x.shape[0], 2, 2) * (1.0 + t))
+  spec.initial_state_hint = np.array([1.0, -2.0])
+  tab = spec.coef_table(np.linspace(0.0, 1.0, 5), np.float64)
+  assert tab.shape == (4, spec.num_coef)
+  np.testing.assert_allclose(tab[:, 2:4], np.stack([0.1 * np.linspace(0.25, 1, 4), np.ones(4)], -1))
+  np.testing.assert_allclose(tab[0, 4:8], [0.0, 0.5, -0.3, 0.0], atol=1e-12)

@@ -19,7 +19,8 @@
 //   x_i' = (x_i + dt mu_i x_i) + (sigma_i x_i) sqrt_dt sum_{j<=i} L_ij z_j.
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
+#include <memory>
+#include <new>
 #include <vector>
 
 #include "tqf_paths_kernel.cuh"
@@ -44,6 +45,7 @@ struct MvParams {
   int64_t stride_path, stride_time, stride_dim;
   int store_exp;
   int exact_log;  // additive log-space step (exact sampler) instead of the Euler step
+  int sobol_clamp;  // float32 Sobol: u == 1.0 -> largest float below 1 (tqf_plan_set_sobol_clamp)
   Real x0[DMAX], mu[DMAX], sigma[DMAX];
   Real L[DMAX * (DMAX + 1) / 2];  // packed rows of the lower-triangular factor
 };
@@ -173,7 +175,7 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
             xb ^= l1.z & lowmask[6];
             const uint32_t xin[1] = {xb};
             Real zo[1];
-            sobol_normals<1>(tab, xin, zo);
+            sobol_normals<1>(tab, xin, zo, P.sobol_clamp);
             s_z[j * kBlock + tid] = zo[0];
           }
         } else {
@@ -597,7 +599,7 @@ mvgbm_split_kernel(const __grid_constant__ MvParams<Real, kMvDim> P) {
               xb[0] ^= l1.x & lowmask[4];
               if (NP == 2) xb[NP - 1] = xb[0] ^ l1.y;      // index bit 5 set
               Real zo[NP];
-              sobol_normals<NP>(tab, xb, zo);
+              sobol_normals<NP>(tab, xb, zo, P.sobol_clamp);
 #pragma unroll
               for (int q = 0; q < NP; ++q)
                 sts_real(zw + (jj >> 2) * kZg + q * kZq + (jj & 3) * sizeof(Real), zo[q]);
@@ -908,7 +910,7 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
             xb[2 * h + 1] = x ^ v.w;                 // index bit 3 = n-tile
           }
           float z[4];
-          sobol_normals_f32<4>(xb, z);
+          sobol_normals_f32<4>(xb, z, P.sobol_clamp);
           uint32_t bh[2][2], bl[2][2];
 #pragma unroll
           for (int h = 0; h < 2; ++h)
@@ -995,9 +997,11 @@ static void launch_split(const MvParams<Real, DMAX>& P, int grid, cudaStream_t s
 
 template <typename Real, int DMAX>
 static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
-  static MvParams<Real, DMAX> P;   // large (up to 19 KB): keep off the stack
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
+  // large (up to 19 KB): on the heap, one per call -- no shared state between
+  // threads / streams / devices of one process (the launch copies it)
+  std::unique_ptr<MvParams<Real, DMAX>> holder(new (std::nothrow) MvParams<Real, DMAX>);
+  TQF_REQUIRE(holder, "out of memory");
+  MvParams<Real, DMAX>& P = *holder;
   std::memset(&P, 0, sizeof(P));
   P.dim = a.dim;
   P.num_steps = a.num_steps;
@@ -1025,6 +1029,7 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
   P.stride_dim = a.stride_dim;
   P.store_exp = a.store_exp;
   P.exact_log = a.exact_log;
+  P.sobol_clamp = a.sobol_clamp;
   for (int i = 0; i < DMAX; ++i) {
     const bool in = i < a.dim;
     P.x0[i] = in ? static_cast<Real>(a.x0[i]) : Real(0);

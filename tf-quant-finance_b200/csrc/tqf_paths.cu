@@ -90,6 +90,7 @@ struct tqf_plan {
   const double* logtab_dev; // shared per-device log table (not owned)
   void* lsplit_dev;         // MVGBM dim > 8: factor in the split kernel's order
   PeerHost peer;            // tqf_plan_set_peer_exchange (world <= 1: single GPU)
+  int sobol_clamp;          // tqf_plan_set_sobol_clamp
   double* colsum_dev;       // [max_grid][slots * dim] column-sum partials (lazily allocated)
   size_t colsum_doubles;
   double* partials_dev;     // [max_grid][TQF_MAX_PAYOFFS][4]
@@ -134,6 +135,7 @@ static void fill_common(const tqf_plan* plan, uint64_t path_offset, uint64_t pat
   P->ctr = PhiloxCtr{plan->rng.counter[0], plan->rng.counter[1], plan->rng.counter[2],
                      plan->rng.counter[3]};
   P->sobol_v = plan->sobol_dev;
+  P->sobol_clamp = plan->sobol_clamp;
   P->logtab = plan->logtab_dev;
   for (int k = 0; k < 8; ++k) P->sobol_hi[k] = 0x41400000;
   P->draws = static_cast<const Real*>(plan->rng.draws_dev);
@@ -324,6 +326,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.partials = plan->partials_dev;
     a.record_dev = plan->record_dev;
     a.exact_log = plan->model.reserved;
+    a.sobol_clamp = plan->sobol_clamp;
     int rc = launch_mvgbm(a, stream, &grid);
     if (rc != TQF_OK) return rc;
     reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev,
@@ -423,6 +426,7 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.stride_dim = stride_dim;
     a.store_exp = transform == TQF_TRANSFORM_EXP ? 1 : 0;
     a.exact_log = plan->model.reserved;
+    a.sobol_clamp = plan->sobol_clamp;
     int g = 1;
     return launch_mvgbm(a, stream, &g);
   }
@@ -609,6 +613,12 @@ int tqf_plan_set_peer_exchange(tqf_plan* plan, int rank, int world, void* const*
     TQF_REQUIRE(bufs[r] != nullptr, "null peer buffer");
     plan->peer.bufs[r] = static_cast<unsigned char*>(bufs[r]);
   }
+  return TQF_OK;
+}
+
+int tqf_plan_set_sobol_clamp(tqf_plan* plan, int clamp) {
+  TQF_REQUIRE(plan, "null argument");
+  plan->sobol_clamp = clamp ? 1 : 0;
   return TQF_OK;
 }
 

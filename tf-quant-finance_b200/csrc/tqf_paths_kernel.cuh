@@ -73,6 +73,7 @@ struct KParams {
   const double* logtab;      // device-global log table (tqf_math.cuh), double Sobol only
   int sobol_hi[8];           // 8 x 0x41400000 (see sobol_normals): separate params so that
                              // each lives in its own register
+  int sobol_clamp;           // float32 Sobol: u == 1.0 -> largest float below 1 (non-reference mode)
   uint64_t first_index;      // Sobol: skip + 1 + path_offset ; else path_offset
   const Real* draws;         // device [N][S_total][NF]
   // work
@@ -378,7 +379,7 @@ struct PhiloxStreamV<float, PPT> {
 // Inverse-CDF transform of K Sobol integer points.
 template <int K, class Tab>
 __device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&xb)[K],
-                                              double (&z)[K]) {
+                                              double (&z)[K], int = 0) {
   double t[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) t[k] = sobol_centered_f64(xb[k]);
@@ -390,7 +391,7 @@ __device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&x
 // already in place, instead of costing one MOV per draw.
 template <int K, class Tab>
 __device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&xb)[K],
-                                              const int (&hi)[K], double (&z)[K]) {
+                                              const int (&hi)[K], double (&z)[K], int = 0) {
   double t[K];
 #pragma unroll
   for (int k = 0; k < K; ++k)
@@ -403,8 +404,14 @@ __device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&x
 // runs unconditionally for all N (independent Horner chains, no branch between
 // them) and ONE rarely taken branch per batch patches the draws in the tails
 // (|z| > 3.1, 0.2 % of them).
+// `clamp` (documented non-reference mode, tqf_plan_set_sobol_clamp): beyond 2^24
+// points RN(x) 2^-32 can be exactly 1.0 and the reference's own
+// erfinv returns +inf; with clamp != 0 such a draw uses the largest float32
+// below one instead (t = 1 - 2^-23).  Handled inside the rare tail branch: the
+// strict hot path is unchanged.
 template <int N>
-__device__ __forceinline__ void sobol_normals_f32(const uint32_t (&xb)[N], float (&z)[N]) {
+__device__ __forceinline__ void sobol_normals_f32(const uint32_t (&xb)[N], float (&z)[N],
+                                                  int clamp = 0) {
   float t[N], w[N], p[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -433,6 +440,10 @@ __device__ __forceinline__ void sobol_normals_f32(const uint32_t (&xb)[N], float
 #pragma unroll
     for (int k = 0; k < N; ++k)
       if (!(w[k] < 6.25f)) {
+        if (clamp && t[k] == 1.0f) {
+          t[k] = 0.99999988079071044921875f;             // 2 (1 - 2^-24) - 1
+          w[k] = -__logf(fmaf(-t[k], t[k], 1.0f));
+        }
         const float yt = sqrtf(w[k]) - TQF_NDTRI_F32_T_MID;
         float q = ct[0];
 #pragma unroll
@@ -446,16 +457,16 @@ __device__ __forceinline__ void sobol_normals_f32(const uint32_t (&xb)[N], float
 
 template <int K, class Tab>
 __device__ __forceinline__ void sobol_normals(const Tab&, const uint32_t (&xb)[K],
-                                              float (&z)[K]) {
+                                              float (&z)[K], int clamp = 0) {
   // bit-identical to z[k] = ndtri(sobol_uniform_f32(xb[k])): (u - 0.5) 2 with
   // u = RN(x) 2^-32 equals RN(RN(x) 2^-31 - 1), the scaling by two commutes
   // with the rounding
-  sobol_normals_f32<K>(xb, z);
+  sobol_normals_f32<K>(xb, z, clamp);
 }
 template <int K, class Tab>
 __device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&xb)[K],
-                                              const int (&)[K], float (&z)[K]) {
-  sobol_normals<K>(tab, xb, z);
+                                              const int (&)[K], float (&z)[K], int clamp = 0) {
+  sobol_normals<K>(tab, xb, z, clamp);
 }
 
 // v[comp] for a register-resident state vector.  Written with opaque `selp`s:
@@ -811,7 +822,7 @@ path_kernel(const KParams<typename Model::Real> P) {
             for (int a = 0; a < PPT; ++a) xb[a * NF + j] = lowx ^ s_high[a * kSobolTileDims + dd];
           }
           Real zz[PPT * NF];
-          sobol_normals<PPT * NF>(tab, xb, t_hi, zz);
+          sobol_normals<PPT * NF>(tab, xb, t_hi, zz, P.sobol_clamp);
 #pragma unroll
           for (int a = 0; a < PPT; ++a)
 #pragma unroll
@@ -977,6 +988,7 @@ struct MvLaunch {
   int64_t stride_path, stride_time, stride_dim;
   int store_exp;
   int exact_log;
+  int sobol_clamp;
 };
 
 int launch_mvgbm(const MvLaunch& a, cudaStream_t stream, int* grid_out);

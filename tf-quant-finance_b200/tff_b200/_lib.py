@@ -173,6 +173,7 @@ _SIGNATURES = {
     'tqf_plan_set_peer_exchange':
         (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_uint64]),
     'tqf_plan_peer_epoch': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    'tqf_plan_set_sobol_clamp': (C.c_int, [C.c_void_p, C.c_int]),
     'tqf_plan_paths_sums':
         (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                    C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -9,6 +9,7 @@ anything from another one until the reduction: one all-reduce of the
 `torch.distributed`), plus, for Longstaff-Schwartz, the column sums and one
 `K^2 + K` block per exercise date.
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -41,6 +42,40 @@ def all_reduce_(tensor):
   if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
     dist.all_reduce(tensor)
   return tensor
+
+
+_SHARDED = None       # (peer_exchange or None) while a `sharded()` context is active
+
+
+@contextlib.contextmanager
+def sharded(peer_exchange=None):
+  """Inside this context the pricing entry points of the package
+  (`euler_sampling.price`, `GenericItoProcess.price`, `HestonModel.price`,
+  `swaption_price`, `bond_option_price`, `cap_floor_price`) shard their paths over
+  the ranks of the default process group and return GLOBAL prices on every rank:
+  each rank simulates `shard_units(units)` and the `[num_payoffs, 4]` sums are
+  added over NVLink peer memory (`peer_exchange`) or by one NCCL all-reduce.
+  Collective: every rank must make the same calls."""
+  global _SHARDED
+  previous = _SHARDED
+  _SHARDED = (peer_exchange,)
+  try:
+    yield
+  finally:
+    _SHARDED = previous
+
+
+def price_sums(plan, payoffs):
+  """`plan.price_sums(payoffs)` -- sharded over the ranks and globally reduced
+  inside a `sharded()` context, the whole run on this GPU otherwise."""
+  if _SHARDED is None or world()[1] == 1:
+    return plan.price_sums(list(payoffs))
+  px = _SHARDED[0]
+  lo, count = shard_units(plan.units)
+  if px is not None and px.world > 1:
+    plan.set_peer_exchange(px)
+    return plan.price_sums(list(payoffs), lo, count)
+  return all_reduce_(plan.price_sums(list(payoffs), lo, count))
 
 
 def price_sharded(plan, payoffs, peer_exchange=None):

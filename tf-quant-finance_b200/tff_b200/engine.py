@@ -113,8 +113,10 @@ class ProbedAffineSpec(ModelSpec):
   affine: a(t, x) = a0(t) + A1(t) x and S(t, x) = B0(t) (+ B1(t) x for dim 1).
 
   The callables are evaluated ON THE HOST at every grid time for a few probe
-  states; the coefficients are solved from the probes and verified on two
-  further random states.  A pair that is not affine is rejected -- the CUDA
+  states; the coefficients are solved from the origin and the unit vectors and
+  verified on check points of both signs, of magnitudes 1e-3 .. 1e3 and around
+  the initial state.  A pair that is not affine there, or that is not finite on
+  a probe (1 / x, log x), is rejected -- the CUDA
   kernels cannot run Python, and there is no CPU fallback."""
 
   def __init__(self, dim, drift_fn, volatility_fn):
@@ -154,17 +156,36 @@ class ProbedAffineSpec(ModelSpec):
     d = self.dim
     t, dt, sq = self._dt_columns(all_times, dtype)
     rs = np.random.RandomState(12345)
-    # probes: origin, unit vectors, two random check points
-    probes = np.concatenate([np.zeros((1, d)), np.eye(d), rs.uniform(0.5, 2.0, (2, d))])
+    # probes: origin and unit vectors (the coefficients are solved from these), then
+    # check points on which the affine form must reproduce the callable: both signs,
+    # small and large magnitudes, and a cloud around the initial state -- a callable
+    # that is only affine on part of the state space (relu, abs, clamp, a local-vol
+    # cut-off) must not pass
+    checks = [rs.uniform(0.5, 2.0, (2, d)), rs.uniform(-2.0, -0.5, (2, d)),
+              rs.uniform(-1.0, 1.0, (2, d)) * 1e-3, rs.uniform(-1.0, 1.0, (2, d)) * 1e3]
+    x0 = getattr(self, 'initial_state_hint', None)
+    if x0 is not None:
+      x0 = np.asarray(x0, dtype=np.float64).reshape(-1)[:d]
+      if x0.shape[0] == d and np.all(np.isfinite(x0)):
+        spread = np.maximum(np.abs(x0), 1.0)
+        checks.append(x0 + spread * rs.uniform(-1.0, 1.0, (4, d)))
+    probes = np.concatenate([np.zeros((1, d)), np.eye(d)] + checks)
     rows = []
     for i in range(t.shape[0]):
       a = self._call(self.drift_fn, t[i], probes, dtype, False)          # [P, d]
       s_ = self._call(self.volatility_fn, t[i], probes, dtype, True)     # [P, d, d]
+      if not (np.all(np.isfinite(a)) and np.all(np.isfinite(s_))):
+        raise NotImplementedError(
+            'The drift/volatility callable returns non-finite values on the probe states '
+            '(origin, unit vectors, points of both signs) at t={}: it is not an affine '
+            'function of the state on the whole state space, which is what the B200 path '
+            'engine runs for plain Python callables. There is no CPU fallback.'.format(
+                float(t[i])))
       a0 = a[0]
       a1 = (a[1:1 + d] - a0).T                                           # A1[i][j]
       b0 = s_[0]
       b1 = s_[1:1 + d] - b0                                              # [j][., .]
-      for c in (d + 1, d + 2):
+      for c in range(d + 1, probes.shape[0]):
         x = probes[c]
         pred_a = a0 + a1 @ x
         pred_s = b0 + np.tensordot(x, b1, axes=(0, 0))
@@ -529,6 +550,13 @@ class Plan:
         _tensor.current_stream_ptr()))
     return buf.permute(2, 0, 1)
 
+  def set_sobol_clamp(self, clamp=True):
+    """float32 Sobol draws whose uniform rounds to exactly 1.0 (possible beyond
+    2^24 points): strict mode (default) reproduces the reference's +inf
+    normal and the path is counted as non-finite; the clamped mode uses the largest
+    float32 below one instead (documented non-reference mode)."""
+    _lib.check(_lib.lib().tqf_plan_set_sobol_clamp(self._handle, int(bool(clamp))))
+
   def set_peer_exchange(self, peer_exchange):
     """Several GPUs of one box: every `price_sums` then returns the sums of ALL
     ranks, added inside the reduction kernel over NVLink peer memory
@@ -547,7 +575,6 @@ class Plan:
       # the buffers may have been used by another plan / the LSM passes meanwhile
       _lib.check(_lib.lib().tqf_plan_set_peer_exchange(
           self._handle, px.rank, px.world, px.ptrs, px.epoch))
-      px.epoch += 1
     unit_count = self.units - unit_offset if unit_count is None else unit_count
     descs = (_lib.PayoffDesc * len(payoffs))(*[p.desc() for p in payoffs])
     # (fully overwritten by the reduction kernel)
@@ -556,6 +583,12 @@ class Plan:
     _lib.check(_lib.lib().tqf_plan_price(
         self._handle, unit_offset, unit_count, descs, len(payoffs),
         sums.data_ptr(), _tensor.current_stream_ptr()))
+    if px is not None:
+      # the library advances the epoch only once the exchange kernel is launched: a
+      # call that failed validation leaves every rank's count untouched
+      ep = C.c_uint64()
+      _lib.check(_lib.lib().tqf_plan_peer_epoch(self._handle, C.byref(ep)))
+      px.epoch = int(ep.value)
     return sums
 
 

@@ -12,6 +12,7 @@ import numpy as np
 
 from tff_b200 import _lib
 from tff_b200 import _tensor
+from tff_b200 import distributed
 from tff_b200 import engine
 from tff_b200.math import random
 from tff_b200.models import closures
@@ -96,6 +97,8 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
     raise NotImplementedError(
         'batched `normal_draws` are not implemented by the B200 engine yet.')
   spec = closures.resolve_spec(drift_fn, volatility_fn, dim)
+  if isinstance(spec, engine.ProbedAffineSpec):
+    spec.initial_state_hint = np.asarray(initial_state, dtype=np.float64).reshape(-1, dim)[0]
   if getattr(spec, 'user_dim', spec.dim) != dim:
     raise ValueError('`dim` is {} but the model has dimension {}'.format(
         dim, getattr(spec, 'user_dim', spec.dim)))
@@ -208,7 +211,7 @@ def price(dim, drift_fn, volatility_fn, times, payoffs, time_step=None,
     raise NotImplementedError('batched processes are not supported by `price` yet')
   plan = plans[0]
   try:
-    sums = plan.price_sums(list(payoffs)).cpu().numpy()
+    sums = distributed.price_sums(plan, payoffs).cpu().numpy()
   finally:
     plan.close()
   n = float(plan.num_samples)

@@ -63,6 +63,29 @@ class HestonModel(generic_ito_process.GenericItoProcess):
         tolerance=tolerance, num_time_steps=num_time_steps,
         times_grid=times_grid, normal_draws=normal_draws)
 
+  def price(self, times, payoffs, num_samples=1, initial_state=None,
+            random_type=None, seed=None, time_step=None, num_time_steps=None,
+            skip=0, times_grid=None, normal_draws=None, return_stats=False,
+            scheme='euler', tolerance=1e-6):
+    """Fused simulation + payoff reduction (engine extension; nothing stored).
+    `scheme='euler'`: the Euler closures, as `GenericItoProcess.price`;
+    `scheme='qe'`: the QE scheme of `sample_paths` (what the reference's
+    `HestonModel.sample_paths` runs)."""
+    if scheme == 'euler':
+      return generic_ito_process.GenericItoProcess.price(
+          self, times, payoffs, num_samples=num_samples, initial_state=initial_state,
+          random_type=random_type, seed=seed, time_step=time_step,
+          num_time_steps=num_time_steps, skip=skip, times_grid=times_grid,
+          normal_draws=normal_draws, return_stats=return_stats)
+    if scheme != 'qe':
+      raise ValueError("scheme must be 'euler' or 'qe'")
+    from tff_b200.models.heston import qe  # pylint: disable=g-import-not-at-top
+    return qe.price(self, times, payoffs, initial_state, num_samples=num_samples,
+                    random_type=random_type, seed=seed, time_step=time_step, skip=skip,
+                    tolerance=tolerance, num_time_steps=num_time_steps,
+                    times_grid=times_grid, normal_draws=normal_draws,
+                    return_stats=return_stats)
+
   def expected_total_variance(self, future_times, initial_var, name=None):
     """`heston_model.py:462-509` (host, numpy)."""
     del name

@@ -12,6 +12,7 @@ import numpy as np
 
 from tff_b200 import _lib
 from tff_b200 import _tensor
+from tff_b200 import distributed
 from tff_b200 import engine
 from tff_b200.math import piecewise
 from tff_b200.models import utils
@@ -68,10 +69,9 @@ class HestonQeSpec(engine.ModelSpec):
     return np.nan_to_num(np.stack(cols, -1).astype(np.float64))
 
 
-def sample_paths(model, times, initial_state, num_samples=1, random_type=None,
-                 seed=None, time_step=None, skip=0, tolerance=1e-6,
-                 num_time_steps=None, times_grid=None, normal_draws=None):
-  """`[num_samples, k, 2]` = (log-spot, variance) QE paths on the device."""
+def _plan(model, times, initial_state, num_samples, random_type, seed, time_step, skip,
+          tolerance, num_time_steps, times_grid, normal_draws):
+  """(plan, record_slot, k) of one QE sampling call (`heston_model.py:177-340`)."""
   dt_ = model.dtype()
   times = _tensor.to_numpy(times, dt_).reshape(-1)
   x0 = _tensor.to_numpy(initial_state, dt_)
@@ -103,7 +103,38 @@ def sample_paths(model, times, initial_state, num_samples=1, random_type=None,
   rng = engine.RngSpec(random_type, seed, skip, normal_draws)
   plan = engine.Plan(spec, all_times, num_steps, x0.reshape(-1), rng,
                      int(num_samples), dt_)
+  return plan, record_slot, times.shape[0]
+
+
+def sample_paths(model, times, initial_state, num_samples=1, random_type=None,
+                 seed=None, time_step=None, skip=0, tolerance=1e-6,
+                 num_time_steps=None, times_grid=None, normal_draws=None):
+  """`[num_samples, k, 2]` = (log-spot, variance) QE paths on the device."""
+  plan, record_slot, k = _plan(model, times, initial_state, num_samples, random_type, seed,
+                               time_step, skip, tolerance, num_time_steps, times_grid,
+                               normal_draws)
   try:
-    return plan.paths(record_slot, times.shape[0])
+    return plan.paths(record_slot, k)
   finally:
     plan.close()
+
+
+def price(model, times, payoffs, initial_state, num_samples=1, random_type=None,
+          seed=None, time_step=None, skip=0, tolerance=1e-6, num_time_steps=None,
+          times_grid=None, normal_draws=None, return_stats=False):
+  """Fused mode of the QE scheme: Monte-Carlo means of `payoffs` on the state at
+  `times[-1]` of `sample_paths(...)` with the same arguments (barrier payoffs
+  monitored on every grid point), no path stored.  Engine extension -- the
+  reference would take `mean(payoff(sample_paths(...)))`."""
+  plan, _, _ = _plan(model, times, initial_state, num_samples, random_type, seed,
+                     time_step, skip, tolerance, num_time_steps, times_grid, normal_draws)
+  try:
+    sums = distributed.price_sums(plan, payoffs).cpu().numpy()
+  finally:
+    plan.close()
+  n = float(plan.num_samples)
+  mean = sums[:, 0] / n
+  if not return_stats:
+    return mean
+  var = np.maximum(sums[:, 1] / n - mean**2, 0.0)
+  return mean, np.sqrt(var / n), sums[:, 2]

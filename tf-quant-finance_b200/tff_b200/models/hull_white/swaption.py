@@ -17,6 +17,7 @@ import numpy as np
 
 from tff_b200 import _lib
 from tff_b200 import _tensor
+from tff_b200 import distributed
 from tff_b200.models import utils
 from tff_b200.models.hull_white import _exact
 from tff_b200.models.hull_white import one_factor
@@ -55,10 +56,34 @@ class _RawPayoff:
     return self._d
 
 
-def _price_on_grid(model, sim_times, expiries, make_desc, num_samples,
-                   random_type, seed, skip):
-  """Runs the fused HW1F price kernel over `sim_times` and returns the payoff
-  sums `[len(expiries), 4]` and the number of simulated paths.
+class _GridPricing:
+  """The fused HW1F pricing plan of a batch of claims over one simulation grid:
+  `plan` (device tables), `payoffs` (one descriptor per claim, evaluated when the
+  path reaches the claim's expiry step), `num_steps`.  `sums()` runs the fused
+  kernel and returns the payoff sums `[len(payoffs), 4]` (host); it may be called
+  repeatedly (benchmarks re-price on the same plan)."""
+
+  def __init__(self, plan, payoffs, num_steps):
+    self.plan, self.payoffs, self.num_steps = plan, payoffs, num_steps
+    self.num_samples = float(plan.num_samples)
+
+  def sums_dev(self, chunk=0):
+    c0 = chunk * _lib.MAX_PAYOFFS
+    return distributed.price_sums(self.plan, self.payoffs[c0:c0 + _lib.MAX_PAYOFFS])
+
+  def sums(self):
+    out = []
+    for c in range((len(self.payoffs) + _lib.MAX_PAYOFFS - 1) // _lib.MAX_PAYOFFS):
+      out.append(self.sums_dev(c).cpu().numpy())
+    return np.concatenate(out, axis=0)
+
+  def close(self):
+    self.plan.close()
+
+
+def _plan_on_grid(model, sim_times, expiries, make_desc, num_samples,
+                  random_type, seed, skip):
+  """Builds the fused HW1F pricing plan over `sim_times` (`_GridPricing`).
 
   `make_desc(b, step)` builds the payoff descriptor of claim `b`, which is
   evaluated when its path reaches simulation step `step` (the step that lands
@@ -92,13 +117,23 @@ def _price_on_grid(model, sim_times, expiries, make_desc, num_samples,
           raise ValueError('expiries must be non-negative.')
         step = 1
       descs.append(_RawPayoff(make_desc(b, step)))
-    sums = []
-    for c0 in range(0, len(descs), _lib.MAX_PAYOFFS):
-      sums.append(plan.price_sums(descs[c0:c0 + _lib.MAX_PAYOFFS]).cpu().numpy())
-    sums = np.concatenate(sums, axis=0)
-  finally:
+  except Exception:
     plan.close()
-  return sums, float(plan.num_samples)
+    raise
+  return _GridPricing(plan, descs, plan.num_steps)
+
+
+def _price_on_grid(model, sim_times, expiries, make_desc, num_samples,
+                   random_type, seed, skip):
+  """Payoff sums `[len(expiries), 4]` of the fused HW1F price kernel over
+  `sim_times` and the number of simulated paths (see `_plan_on_grid`)."""
+  gp = _plan_on_grid(model, sim_times, expiries, make_desc, num_samples,
+                     random_type, seed, skip)
+  try:
+    sums = gp.sums()
+  finally:
+    gp.close()
+  return sums, gp.num_samples
 
 
 def swaption_price(*,
@@ -122,7 +157,8 @@ def swaption_price(*,
                    time_step=None,
                    dtype=None,
                    name=None,
-                   return_stats=False):
+                   return_stats=False,
+                   _plan_only=False):
   """European swaption prices of shape `expiries.shape` (numpy float array).
 
   Same arguments as the reference.  `use_analytic_pricing=True` (Jamshidian
@@ -174,6 +210,9 @@ def swaption_price(*,
   def make_desc(b, step):
     return _swaption_desc(model, step, exp_flat[b], pay_flat[b], cpn_flat[b],
                           dcf_flat[b], payer_flat[b], ntl_flat[b])
+  if _plan_only:
+    return _plan_on_grid(model, sim_times, exp_flat, make_desc, num_samples,
+                         random_type, seed, skip)
   sums, n = _price_on_grid(model, sim_times, exp_flat, make_desc, num_samples,
                            random_type, seed, skip)
   price = (sums[:, 0] / n).astype(dt_).reshape(batch_shape)
