@@ -406,6 +406,34 @@ int tqf_lsm_run_fused(tqf_lsm* h, const int32_t* exercise_times, int num_times,
                       const double* means_dev, int64_t mean_stride, const double* ratio_dev,
                       double* beta_dev, void* stream);
 
+/* The whole backward induction of lsm.py:231-330 -- terminal cashflow
+ * (lsm.py:266-276), one regression + exercise sweep per earlier date
+ * (`_lsm_loop_body`, 403-436) and the sum of the discounted values (284-291) --
+ * in ONE persistent cooperative launch: one CTA per SM owns a fixed set of path
+ * tiles, streams the two path columns of every date through a TMA-fed
+ * shared-memory ring, keeps W in L2, and the per-date regression is a grid
+ * barrier whose last arriver reduces (and, with tqf_lsm_set_peer_exchange,
+ * exchanges over NVLink), solves and releases.  Applies when
+ * tqf_lsm_persistent_eligible (one payoff, dim 1, K <= 6, contiguous time-major
+ * paths, 16-byte aligned columns, path count a multiple of 16 / sizeof(dtype)).
+ *   means_dev / ratio_dev: as tqf_lsm_run_fused;
+ *   skip_below: global paths below it do not count in the value sum
+ *     (num_calibration_samples, lsm.py:286-289);
+ *   value_sums_dev: double [2] = {sum of W over the counted paths, their count}
+ *     -- over ALL ranks when the peer exchange is set;
+ *   beta_dev: double [K] scratch (regression coefficients of the current date);
+ *   history_dev: NULL, or double [num_times - 1][27 + 6]: row j = the reduced
+ *     normal equations (tqf_lsm_sums_layout, packed) and beta of exercise index
+ *     num_times - 1 - j (diagnostics / parity tests).
+ * Nothing synchronises with the host; tqf_lsm_status reads back (and waits for)
+ * a non-zero code when a grid barrier or peer timed out.                    */
+int tqf_lsm_persistent_eligible(const tqf_lsm* h, int* eligible);
+int tqf_lsm_run_persistent(tqf_lsm* h, const int32_t* exercise_times, int num_times,
+                           const double* means_dev, int64_t mean_stride, const double* ratio_dev,
+                           double rcond, uint64_t skip_below, double* value_sums_dev,
+                           double* beta_dev, double* history_dev, void* stream);
+int tqf_lsm_status(const tqf_lsm* h, uint64_t* status);
+
 /* Multi-GPU (one process per GPU of ONE box): the reduced normal equations of
  * every exercise date are summed over the ranks INSIDE the tail of the fused
  * pass, by peer stores / flags over NVLink -- replaces the per-date
@@ -417,8 +445,8 @@ int tqf_lsm_run_fused(tqf_lsm* h, const int32_t* exercise_times, int num_times,
  *     tqf_peer_open), r = 0 .. world-1, world <= 8, batch <= 16;
  *   epoch_base: number of exchanges already performed on these buffers -- the
  *     same on every rank; read it back with tqf_lsm_peer_epoch after the call.
- * Requires tqf_lsm_set_fused_solve and tqf_lsm_fused_eligible on EVERY rank
- * (all ranks must take the same route).  A peer that does not arrive within
+ * Requires tqf_lsm_fused_eligible (and, for the one-launch-per-date route,
+ * tqf_lsm_set_fused_solve) on EVERY rank: all ranks must take the same route.  A peer that does not arrive within
  * ~10 s poisons the sums with NaN instead of hanging the device.           */
 int tqf_lsm_peer_bytes(uint64_t* bytes);
 int tqf_lsm_set_peer_exchange(tqf_lsm* h, int rank, int world, void* const* bufs,

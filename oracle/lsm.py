@@ -46,8 +46,12 @@ def _apply_discount(values, df, e):
 
 def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
                     discount_factors=None, num_calibration_samples=None,
-                    dtype=None):
-  """`least_square_mc` (`lsm.py:128-295`) -> [batch_size] prices."""
+                    dtype=None, diagnostics=None):
+  """`least_square_mc` (`lsm.py:128-295`) -> [batch_size] prices.
+
+  `diagnostics` (oracle extension): a dict that receives, per exercise index e,
+  the normal equations `lhs[e]` [B, K, K], `rhs[e]` [B, K] and `beta[e]`, and the
+  final merged state `w` = cashflow + values [N, B]."""
   x = np.asarray(sample_paths, dtype=dtype)
   dtype = x.dtype
   exercise_times = np.asarray(exercise_times)
@@ -83,12 +87,18 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
     pinv = np.stack([np.linalg.pinv(m, rcond=10 * K * np.finfo(dtype).eps) for m in lhs])
     rhs = np.matmul(np.transpose(sub, [0, 2, 1]), y.T[..., None])
     beta = np.matmul(pinv, rhs)
+    if diagnostics is not None:
+      diagnostics.setdefault('lhs', {})[e] = lhs
+      diagnostics.setdefault('rhs', {})[e] = rhs[..., 0]
+      diagnostics.setdefault('beta', {})[e] = beta[..., 0]
     expected = np.maximum(np.matmul(design_t, beta)[..., 0].T, 0)   # [N, B]
     upd = ev > expected
     new_values = np.where(upd, 0, cashflow + values)
     cashflow = np.where(upd, ev, 0).astype(dtype)
     values = _apply_discount(new_values, df, e).astype(dtype)
     e -= 1
+  if diagnostics is not None:
+    diagnostics['w'] = cashflow + values
   pv = _apply_discount(cashflow + values, df, 0)
   if num_calibration_samples is not None:
     pv = pv[num_calibration_samples:]

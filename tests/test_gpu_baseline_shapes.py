@@ -86,3 +86,73 @@ def test_c3_swaption_price_time_step_1_360_stateless():
   want = 100.0 * payoff.mean()
   np.testing.assert_allclose(got, want, rtol=1e-12)
   np.testing.assert_allclose(got, 0.71632434, rtol=0, atol=3e-3)      # 3 standard errors
+
+
+def _unpack27(row, K):
+  lhs = np.zeros((K, K))
+  idx = 0
+  for i in range(6):
+    for j in range(i, 6):
+      if i < K and j < K:
+        lhs[i, j] = lhs[j, i] = row[idx]
+      idx += 1
+  return lhs, row[21:21 + K]
+
+
+def test_c5_american_put_148_steps_50_dates_cubic_basis():
+  # lsm.py:145-183 at the C5 shape: time_step 0.01 (148 Euler steps), 50 exercise dates,
+  # STATELESS_ANTITHETIC seed [4, 2], cubic basis; N = 2^17.  The device path is the
+  # persistent single-launch backward induction.
+  import tff_b200 as tff
+  from tff_b200 import engine
+  from tff_b200.models import closures
+  from tff_b200.models import utils
+  from oracle import lsm as olsm
+  lsm = tff.models.longstaff_schwartz
+  n, r, sigma = 1 << 17, 0.1, 1.0
+  times = np.linspace(0.0, 1.0, 50)
+  drift, vol = closures.affine_closures(r - sigma**2 / 2, 0.0, sigma)
+  all_times, mask, _ = utils.prepare_grid(times=times, time_step=np.float64(0.01), dtype=np.float64)
+  nsteps, record_slot = engine.record_plan(mask, 50)
+  assert nsteps == 148
+  rng = engine.RngSpec(tff.math.random.RandomType.STATELESS_ANTITHETIC, [4, 2], 0)
+  plan = engine.Plan(closures.resolve_spec(drift, vol), all_times, nsteps, np.array([0.0]), rng, n,
+                     np.float64)
+  try:
+    paths, csums = plan.paths(record_slot, 50, exp_transform=True, column_sums=True)
+  finally:
+    plan.close()
+  df = np.exp(-r * times)
+  diag = {}
+  got = lsm.least_square_mc(paths, np.arange(50), lsm.make_basket_put_payoff([1.1], dtype=np.float64),
+                            lsm.make_polynomial_basis(3), discount_factors=df, dtype=np.float64,
+                            column_sums=csums, diagnostics=diag)
+  assert diag['route'] == 'persistent'
+
+  jobs = [dict(lo=lo, hi=hi, n=n, r=r, sigma=sigma, times=times.tolist(), time_step=0.01,
+               random_type='STATELESS_ANTITHETIC', seed=[4, 2]) for lo, hi in chunked.slices(n // 2, 1 << 12)]
+  parts = chunked.run('gbm_log_paths', jobs)
+  half = [p.shape[0] // 2 for p in parts]
+  olog = np.concatenate([p[:h] for p, h in zip(parts, half)] + [p[h:] for p, h in zip(parts, half)])
+  opaths = np.exp(olog)                                            # [N, 50, 1]
+  np.testing.assert_allclose(paths.cpu().numpy(), opaths, rtol=1e-12)   # 148-step Euler paths
+  odiag = {}
+  want = olsm.least_square_mc(opaths, np.arange(50), olsm.make_basket_put_payoff([1.1]),
+                              olsm.make_polynomial_basis(3), df, dtype=np.float64, diagnostics=odiag)
+  # exercise decisions: paths whose final cashflow differs (a decision flipped on the way)
+  w_got = diag['w'].cpu().numpy()
+  w_want = odiag['w'][:, 0]
+  flips = int(np.sum(np.abs(w_got - w_want) > 1e-9 * np.maximum(np.abs(w_want), 1e-3)))
+  assert flips <= 2, flips
+  # per-date normal equations X'X, X'y of the 49 regressions
+  worst = 0.0
+  for j in range(49):
+    e = 49 - j
+    lhs, rhs = _unpack27(diag['sums'][j], 4)
+    for g, w in ((lhs, odiag['lhs'][e][0]), (rhs, odiag['rhs'][e][0])):
+      err = np.abs(g - w).max() / np.abs(w).max()
+      worst = max(worst, err)
+  tol = 1e-13 if flips == 0 else 1e-4
+  assert worst < tol, (worst, flips)
+  np.testing.assert_allclose(got, want, rtol=1e-12 if flips == 0 else 1e-6)
+  assert abs(float(got[0]) - 0.397) < 5e-3                          # docstring value at N = 1e5

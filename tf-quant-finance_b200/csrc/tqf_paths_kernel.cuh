@@ -504,6 +504,11 @@ __device__ __forceinline__ double eval_payoff(const PayoffK& d, double x_final, 
   }
   // d f / d state: f itself for the exponential transform
   const double fprime = d.transform == TQF_TRANSFORM_EXP ? f : 1.0;
+  // A non-finite state (e.g. the +inf normal of a float32 Sobol uniform equal to
+  // 1.0, SURVEY F7, or inf - inf = NaN one step later) makes the reference's
+  // relu(...) NaN; `NaN > 0` is false, so without this test such a path would be
+  // priced as 0 instead of being counted as non-finite by the caller.
+  if (!isfinite(f)) return f - f;
   double v;
   switch (d.kind) {
     case TQF_PAYOFF_CALL_TANGENT:

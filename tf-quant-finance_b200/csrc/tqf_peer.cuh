@@ -46,16 +46,28 @@ __device__ __forceinline__ double* peer_sums(unsigned char* buf, int parity, int
 // ahead of another one, because each exchange needs every rank's flag.
 // Returns false when a peer did not arrive within ~10 s (the sums are then
 // poisoned with NaN instead of hanging the GPU).
-__device__ __forceinline__ bool peer_all_reduce(const PeerK& A, double* sums, int M) {
+// `nthreads` / `bar_id`: the threads of the CTA that call this together.  bar_id
+// < 0: the whole CTA (__syncthreads); otherwise the first `nthreads` threads,
+// synchronised on named barrier `bar_id` (warp-specialised kernels whose other
+// warps do not take part).
+__device__ __forceinline__ void peer_sync(int nthreads, int bar_id) {
+  if (bar_id < 0)
+    __syncthreads();
+  else
+    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool peer_all_reduce(const PeerK& A, double* sums, int M,
+                                                int nthreads = 0, int bar_id = -1) {
   __shared__ int s_timeout;
+  if (bar_id < 0) nthreads = blockDim.x;
   const int parity = static_cast<int>(A.peer_epoch & 1ull);
   if (threadIdx.x == 0) s_timeout = 0;
-  for (int i = threadIdx.x; i < A.peer_world * M; i += blockDim.x) {
+  for (int i = threadIdx.x; i < A.peer_world * M; i += nthreads) {
     const int r = i / M, m = i - r * M;
     peer_sums(A.peer_bufs[r], parity, A.peer_rank)[m] = sums[m];
   }
   __threadfence_system();
-  __syncthreads();
+  peer_sync(nthreads, bar_id);
   if (threadIdx.x < A.peer_world) {
     unsigned long long* remote = peer_flag(A.peer_bufs[threadIdx.x], parity, A.peer_rank);
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(remote), "l"(A.peer_epoch) : "memory");
@@ -71,15 +83,15 @@ __device__ __forceinline__ bool peer_all_reduce(const PeerK& A, double* sums, in
       }
     }
   }
-  __syncthreads();
+  peer_sync(nthreads, bar_id);
   const bool ok = s_timeout == 0;
-  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+  for (int m = threadIdx.x; m < M; m += nthreads) {
     double v = 0.0;
     for (int r = 0; r < A.peer_world; ++r)
       v += *reinterpret_cast<volatile double*>(peer_sums(A.peer_bufs[A.peer_rank], parity, r) + m);
     sums[m] = ok ? v : __longlong_as_double(0x7ff8000000000000ll);
   }
-  __syncthreads();
+  peer_sync(nthreads, bar_id);
   return ok;
 }
 

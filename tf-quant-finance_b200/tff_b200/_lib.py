@@ -174,6 +174,11 @@ _SIGNATURES = {
         (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_uint64]),
     'tqf_plan_peer_epoch': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     'tqf_plan_set_sobol_clamp': (C.c_int, [C.c_void_p, C.c_int]),
+    'tqf_lsm_persistent_eligible': (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    'tqf_lsm_run_persistent':
+        (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_double,
+                   C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'tqf_lsm_status': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     'tqf_plan_paths_sums':
         (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                    C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

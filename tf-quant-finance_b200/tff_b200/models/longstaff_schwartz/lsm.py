@@ -67,7 +67,8 @@ def _unpack_sums(sums, K, packed):
 def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
                     discount_factors=None, num_calibration_samples=None,
                     dtype=None, name=None, *, global_path_offset=0,
-                    all_reduce=None, column_sums=None, peer_exchange=None):
+                    all_reduce=None, column_sums=None, peer_exchange=None,
+                    diagnostics=None):
   """Values Amercian style options using the LSM algorithm (`lsm.py:128-295`).
 
   Args are those of the reference; `exercise_times` are indices into the time
@@ -87,6 +88,12 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
   `all_reduce` spans; the per-date normal equations are then summed over the
   ranks inside the streaming kernel (peer memory over NVLink) and `all_reduce`
   is only called for the column sums and the final value sum.
+
+  `diagnostics`: optional dict; when the persistent single-launch route runs it
+  receives `sums` (`[T - 1, 27]`, row j = the reduced normal equations of
+  exercise index `T - 1 - j` in the packed layout of `tqf_lsm_sums_layout`),
+  `beta` (`[T - 1, 6]`), `w` (the final merged state `cashflow + values` of the
+  local paths, a device tensor) and `route`.
 
   Returns a numpy array `[batch_size]`.
   """
@@ -229,24 +236,72 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
     def ratio_ptr(e):
       return ratio_dev.data_ptr() + e * B * 8
 
-    _lib.check(lib.tqf_lsm_init(handle, int(ex_times[T - 1]), stream))
     sums = torch.zeros((B, ns.value), dtype=torch.float64, device=dev)
-    beta_dev = torch.zeros((B, K), dtype=torch.float64, device=dev)
     rcond = 10 * K * float(np.finfo(dt).eps)
-    e = T - 1
     device_solve = bool(packed.value)
+    multi = all_reduce is not None
+    peers_possible = (multi and peer_exchange is not None and B <= 16
+                      and os.environ.get('TQF_LSM_PEER_EXCHANGE', '1') != '0')
+
+    def all_ranks_agree(ok):
+      if not multi:
+        return bool(ok)
+      flag = torch.tensor([float(bool(ok))], dtype=torch.float64, device=dev)
+      all_reduce(flag)
+      return float(flag.item()) == float(peer_exchange.world)
+
+    # Route 1: the whole backward induction in ONE persistent cooperative launch
+    # (single asset, one payoff, K <= 6, contiguous time-major paths); several GPUs
+    # exchange the per-date sums over NVLink peer memory inside it.
+    persistent = False
+    if (device_solve and B == 1 and not batched and (not multi or peers_possible)
+        and os.environ.get('TQF_LSM_PERSISTENT', '1') != '0'):
+      ok = C.c_int()
+      _lib.check(lib.tqf_lsm_persistent_eligible(handle, C.byref(ok)))
+      persistent = all_ranks_agree(ok.value) if multi else bool(ok.value)
+    if persistent:
+      if multi:
+        _lib.check(lib.tqf_lsm_set_peer_exchange(handle, peer_exchange.rank, peer_exchange.world,
+                                                 peer_exchange.ptrs, peer_exchange.epoch))
+      history = None
+      if diagnostics is not None:
+        history = torch.zeros((max(T - 1, 1), 33), dtype=torch.float64, device=dev)
+      vs = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+      beta_dev = torch.zeros((6,), dtype=torch.float64, device=dev)
+      _lib.check(lib.tqf_lsm_run_persistent(
+          handle, ex_i32.ctypes.data, T, means.data_ptr(), mean_stride, ratio_dev.data_ptr(),
+          rcond, int(num_calibration_samples or 0), vs.data_ptr(), beta_dev.data_ptr(),
+          None if history is None else history.data_ptr(), stream))
+      if multi:
+        ep = C.c_uint64()
+        _lib.check(lib.tqf_lsm_peer_epoch(handle, C.byref(ep)))
+        peer_exchange.epoch = int(ep.value)
+      vs = vs.cpu().numpy()
+      st = C.c_uint64()
+      _lib.check(lib.tqf_lsm_status(handle, C.byref(st)))
+      if st.value != 0:
+        raise RuntimeError(
+            'the persistent Longstaff-Schwartz kernel reported status {} (1: a CTA did not reach '
+            'the grid barrier in time, 2 / 4: a tile never arrived, 3: a peer rank did not take '
+            'part in the exchange within its time-out)'.format(st.value))
+      if diagnostics is not None:
+        h = history.cpu().numpy()
+        diagnostics.update(route='persistent', sums=h[:T - 1, :27], beta=h[:T - 1, 27:],
+                           w=w_buf[0])
+      return (ratio[0] * vs[:, 0] / vs[:, 1]).astype(dt)
+
+    _lib.check(lib.tqf_lsm_init(handle, int(ex_times[T - 1]), stream))
+    beta_dev = torch.zeros((B, K), dtype=torch.float64, device=dev)
+    e = T - 1
     # single rank + device solve: the per-CTA partials are reduced inside the
     # solve kernel (one launch less per date)
     fused = device_solve and all_reduce is None and B <= 128
     use_peers = False
-    if (device_solve and all_reduce is not None and peer_exchange is not None and B <= 16
-        and os.environ.get('TQF_LSM_PEER_EXCHANGE', '1') != '0'):
+    if device_solve and peers_possible:
       # every rank must take the same route: the fused pass has to apply everywhere
       ok = C.c_int()
       _lib.check(lib.tqf_lsm_fused_eligible(handle, C.byref(ok)))
-      flag = torch.tensor([float(ok.value)], dtype=torch.float64, device=dev)
-      all_reduce(flag)
-      use_peers = float(flag.item()) == float(peer_exchange.world)
+      use_peers = all_ranks_agree(ok.value)
       fused = use_peers
     sums_arg = None if fused else sums.data_ptr()
     fused_set = fused and (use_peers or os.environ.get('TQF_LSM_FUSED_SOLVE', '1') != '0')
@@ -303,6 +358,12 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
       _lib.check(lib.tqf_lsm_peer_epoch(handle, C.byref(ep)))
       peer_exchange.epoch = int(ep.value)
     vs = vs.cpu().numpy()
+    if diagnostics is not None:
+      diagnostics.update(route='per-date launches', w=w_buf[0])
+    if use_peers and not np.all(np.isfinite(vs)):
+      raise RuntimeError('non-finite Longstaff-Schwartz value sums after a peer exchange: a peer '
+                         'rank did not take part within the time-out (rank skew or a failure on '
+                         'another rank), or the paths hold non-finite values')
   finally:
     lib.tqf_lsm_destroy(handle)
   # per-sample discounting: the value sum already carries df[1] / df[0] per path
