@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 R, SIGMA, N, T = 0.1, 1.0, 40_000, 13
 
 
-def _setup():
+def _setup(strikes=(1.1, 1.2)):
   sys.path.insert(0, os.path.join(ROOT, 'tf-quant-finance_b200'))
   import tff_b200 as tff
   from tff_b200 import engine
@@ -30,18 +30,18 @@ def _setup():
   plan = engine.Plan(spec, all_times, steps, np.array([0.0]), rng, N, np.float64)
   lsm = tff.models.longstaff_schwartz
   kw = dict(discount_factors=np.exp(-R * times), dtype=np.float64)
-  put = lsm.make_basket_put_payoff([1.1, 1.2], dtype=np.float64)
+  put = lsm.make_basket_put_payoff(list(strikes), dtype=np.float64)
   return plan, record_slot, lsm, put, lsm.make_polynomial_basis(3), kw
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, strikes=(1.1, 1.2)):
   try:
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank % torch.cuda.device_count())
     dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank,
                             world_size=world)
-    plan, record_slot, lsm, put, basis, kw = _setup()
+    plan, record_slot, lsm, put, basis, kw = _setup(strikes)
     from tff_b200 import distributed
     lo, count = distributed.shard_units(plan.units, rank, world)
     paths, sums = plan.paths(record_slot, T, lo, count, exp_transform=True, column_sums=True)
@@ -51,7 +51,9 @@ def _worker(rank, world, port, out_path):
     for _ in range(2):   # twice on the same buffers: the epochs continue
       res.append(lsm.least_square_mc(paths, np.arange(T), put, basis, global_path_offset=lo,
                                      all_reduce=reduce_fn, column_sums=sums, peer_exchange=px, **kw))
-    assert px.epoch == 2 * (T - 1), px.epoch
+    # one payoff: the persistent single-launch induction (T exchanges: T - 1 regressions
+    # and the value sum); several payoffs: one launch per date (T - 1 exchanges)
+    assert px.epoch == (2 * T if len(strikes) == 1 else 2 * (T - 1)), px.epoch
     # the NCCL-style route (one all-reduce per date) on the same shards
     res.append(lsm.least_square_mc(paths, np.arange(T), put, basis, global_path_offset=lo,
                                    all_reduce=reduce_fn, column_sums=sums, **kw))
@@ -70,10 +72,11 @@ def _worker(rank, world, port, out_path):
     os._exit(1)
 
 
-def test_two_ranks_peer_exchange_matches_single_process(tmp_path):
+@pytest.mark.parametrize('strikes', [(1.1, 1.2), (1.1,)], ids=['per_date_launches', 'persistent'])
+def test_two_ranks_peer_exchange_matches_single_process(tmp_path, strikes):
   import torch
   import torch.multiprocessing as mp
-  plan, record_slot, lsm, put, basis, kw = _setup()
+  plan, record_slot, lsm, put, basis, kw = _setup(strikes)
   paths = plan.paths(record_slot, T, exp_transform=True)
   want = lsm.least_square_mc(paths, np.arange(T), put, basis, **kw)
   plan.close()
@@ -81,7 +84,7 @@ def test_two_ranks_peer_exchange_matches_single_process(tmp_path):
   ctx = mp.get_context('spawn')
   out = str(tmp_path / 'rank%d.npy')
   port = 29600 + os.getpid() % 300
-  procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, out, strikes)) for r in range(2)]
   for p in procs:
     p.start()
   for p in procs:

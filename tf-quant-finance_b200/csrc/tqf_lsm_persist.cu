@@ -30,6 +30,7 @@
 // write of W), of which W is served by L2.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -37,12 +38,12 @@
 
 namespace tqf {
 
-constexpr int kPConsumers = 480;                  // 15 consumer warps (16 warps per CTA: 128 registers each)
+constexpr int kPConsumers = 352;                  // 11 consumer warps (12 warps per CTA: 168 registers each)
 constexpr int kPThreads = kPConsumers + 32;       // + one producer warp
 constexpr int kPVecPerThread = 2;                 // 16-byte vectors per thread and tile
-constexpr int kPTileVecs = kPConsumers * kPVecPerThread;   // 960 vectors = 15 KB per column
+constexpr int kPTileVecs = kPConsumers * kPVecPerThread;   // 704 vectors = 11 KB per column
 constexpr int kPTileBytes = kPTileVecs * 16;
-constexpr int kPStages = 6;                       // 6 x 2 x 15 KB = 180 KB of columns in flight
+constexpr int kPStages = 8;                       // 8 x 2 x 11 KB = 176 KB of columns in flight
 constexpr size_t kPSmemBytes = static_cast<size_t>(kPStages) * 2 * kPTileBytes + 1024;
 constexpr long long kPTimeoutCycles = 8000000000ll;   // ~4 s: a lost CTA must not hang the GPU
 
@@ -66,6 +67,7 @@ struct PersistArgs {
   double* history;            // optional [T - 1][27 + 6]: sums and beta of every date
   double* value_sums;         // [2]: sum of W over the pricing paths, their count
   unsigned long long* ctrl;   // [0] arrivals, [1] release flag, [2] status
+  int tune;                   // TQF_LSM_TUNE experiment bits (0 = the shipped configuration)
   PeerK peer;
 };
 
@@ -91,11 +93,13 @@ __device__ __forceinline__ bool p_mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a barrier that never completes (a bug, a lost peer) must not hang the box.
-__device__ __forceinline__ bool p_mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool p_mbar_wait(uint32_t bar, uint32_t parity, unsigned sleep_ns = 0) {
   if (p_mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
-  while (!p_mbar_try_wait(bar, parity))
+  while (!p_mbar_try_wait(bar, parity)) {
+    if (sleep_ns) __nanosleep(sleep_ns);       // producer: do not compete for issue slots
     if (clock64() - t0 > kPTimeoutCycles) return false;
+  }
   return true;
 }
 __device__ __forceinline__ void p_bulk_load(uint32_t dst, const void* src, uint32_t bytes,
@@ -159,6 +163,167 @@ __device__ __noinline__ void p_solve(const double* sums, double rcond, int round
   lsm_solve_one<KT>(sums, rcond, round_to_float, beta);
 }
 
+// W' = (pv > 0 and pv > cont) ? pv : rw -- two compares chained through the
+// predicate and one select (the plain C++ form compiles to two selects per path)
+__device__ __forceinline__ double p_exercise(double pv, double cont, double rw) {
+  double r;
+  asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f64 q, %1, 0d0000000000000000;\n\t"
+      "setp.gt.and.f64 p, %1, %2, q;\n\tselp.f64 %0, %1, %3, p;\n\t}"
+      : "=d"(r) : "d"(pv), "d"(cont), "d"(rw));
+  return r;
+}
+__device__ __forceinline__ float p_exercise(float pv, float cont, float rw) {
+  float r;
+  asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f32 q, %1, 0f00000000;\n\t"
+      "setp.gt.and.f32 p, %1, %2, q;\n\tselp.f32 %0, %1, %3, p;\n\t}"
+      : "=f"(r) : "f"(pv), "f"(cont), "f"(rw));
+  return r;
+}
+
+struct SweepState {
+  uint32_t stage, phase;     // position in the shared-memory ring (continues across dates)
+  bool failed;
+};
+template <typename Real, int KT>
+struct SweepParams {
+  Real beta[KT];
+  Real strike, mean_u, ratio_u, mean_a, ratio_a;
+  bool descending;
+};
+
+// One date of the backward induction over this CTA's tiles (consumer threads).
+// MID = true: the common sweep (update + accumulate, every path calibrates),
+// straight-line code per tile; MID = false: the first / last sweep and
+// num_calibration_samples, with run-time flags.  Leaves the K (K + 1) / 2 + K
+// regression sums (or, on the last sweep, {value sum, count}) in `acc`.
+template <typename Real, int KT, bool MID>
+__device__ __forceinline__ void p_sweep(const PersistArgs<Real>& A, const SweepParams<Real, KT>& sp,
+                                        SweepState& st, double (&acc)[KT * (KT + 1) / 2 + KT],
+                                        uint32_t ring, uint32_t fullb, uint32_t emptyb,
+                                        uint32_t tile_lo, uint32_t tile_hi, int tid, int lane,
+                                        uint64_t keep, bool first, bool last) {
+  constexpr int VN = PVec<Real>::N;
+  constexpr int NX = KT * (KT + 1) / 2;
+  uint4* wv = reinterpret_cast<uint4*>(A.w);
+  const uint32_t num_my = tile_hi - tile_lo;
+  const bool calib_all = A.num_calib == ~0ull;
+  uint32_t count = 0;                           // sum of phi_0 phi_0: an integer
+  double vsum = 0.0, vcnt = 0.0;
+  uint32_t tile = sp.descending ? tile_hi - 1 : tile_lo;
+  const int step = sp.descending ? -1 : 1;
+  uint4 wreg[kPVecPerThread];
+  if ((MID || !first) && num_my > 0) {
+#pragma unroll
+    for (int u = 0; u < kPVecPerThread; ++u) {
+      const uint32_t v = tile * kPTileVecs + u * kPConsumers + tid;
+      if (v < A.num_vecs) wreg[u] = p_ld_keep(wv + v, keep);
+    }
+  }
+  for (uint32_t i = 0; i < num_my; ++i, tile += step) {
+    if (!p_mbar_wait(fullb + 8 * st.stage, st.phase)) st.failed = true;
+    const uint32_t src = ring + st.stage * (2 * kPTileBytes);
+    uint4 xu_raw[kPVecPerThread], xa_raw[kPVecPerThread];
+#pragma unroll
+    for (int u = 0; u < kPVecPerThread; ++u) {
+      xu_raw[u] = p_lds(src + u * kPConsumers * 16);
+      if (MID || !last) xa_raw[u] = p_lds(src + kPTileBytes + u * kPConsumers * 16);
+    }
+    __syncwarp();
+    if (lane == 0) p_mbar_arrive(emptyb + 8 * st.stage);     // the stage is free again
+    if (++st.stage == kPStages) {
+      st.stage = 0;
+      st.phase ^= 1u;
+    }
+    const uint32_t vbase = tile * kPTileVecs + tid;
+    Real wn[kPVecPerThread][VN];
+    // ---- exercise decision: W' = (pv > 0 and pv > X beta) ? pv : ratio W, which is
+    // `ev > relu(X beta) ? ev : ratio W` with ev = relu(pv) (lsm.py:391-399)
+#pragma unroll
+    for (int u = 0; u < kPVecPerThread; ++u) {
+      const uint32_t v = vbase + u * kPConsumers;
+      // (lanes beyond the last vector of a partial tile compute on stale shared
+      // memory; only their store and their sums are masked)
+      Real xu[VN], wo[VN];
+      PVec<Real>::unpack(xu_raw[u], xu);
+      if (MID || !first) PVec<Real>::unpack(wreg[u], wo);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        const Real pv = sp.strike - xu[e];
+        if (!MID && first) {
+          wn[u][e] = pv > Real(0) ? pv : Real(0);              // the terminal cashflow
+        } else {
+          const Real c = xu[e] - sp.mean_u;
+          Real cont = sp.beta[KT - 1];
+#pragma unroll
+          for (int k = KT - 2; k >= 0; --k) cont = fma(cont, c, sp.beta[k]);
+          wn[u][e] = p_exercise(pv, cont, sp.ratio_u * wo[e]);
+        }
+      }
+      if (v < A.num_vecs) p_st_keep(wv + v, PVec<Real>::pack(wn[u]), keep);
+    }
+    // W of the next tile, into the registers just consumed
+    if ((MID || !first) && i + 1 < num_my) {
+#pragma unroll
+      for (int u = 0; u < kPVecPerThread; ++u) {
+        const uint32_t v = (tile + step) * kPTileVecs + u * kPConsumers + tid;
+        if (v < A.num_vecs) wreg[u] = p_ld_keep(wv + v, keep);
+      }
+    }
+    // ---- normal equations of the next (earlier) date, branch-free: a path that does
+    // not take part (out of the money) contributes c = 0, y = 0 and no count
+#pragma unroll
+    for (int u = 0; u < kPVecPerThread; ++u) {
+      const uint32_t v = vbase + u * kPConsumers;
+      const bool active = v < A.num_vecs;
+      if (MID || !last) {
+        Real xa[VN];
+        PVec<Real>::unpack(xa_raw[u], xa);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          const Real pa = sp.strike - xa[e];
+          bool use = active && pa > Real(0);
+          if (!MID && !calib_all)
+            use = use && (A.path_offset + static_cast<uint64_t>(v) * VN + e) < A.num_calib;
+          const Real cr = use ? xa[e] - sp.mean_a : Real(0);
+          const double y = use ? static_cast<double>(sp.ratio_a * wn[u][e]) : 0.0;
+          count += use ? 1u : 0u;
+          double phi[KT];
+          Real pw = 1;
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            phi[k] = static_cast<double>(pw);
+            pw *= cr;
+          }
+          int idx = 0;
+#pragma unroll
+          for (int a = 0; a < KT; ++a)
+#pragma unroll
+            for (int b = a; b < KT; ++b) {
+              if (idx > 0) acc[idx] = fma(phi[a], phi[b], acc[idx]);    // phi_0 = 1: additions
+              ++idx;
+            }
+          acc[NX] += y;
+#pragma unroll
+          for (int a = 1; a < KT; ++a) acc[NX + a] = fma(phi[a], y, acc[NX + a]);
+        }
+      } else if (active) {
+#pragma unroll
+        for (int e = 0; e < VN; ++e)
+          if (A.path_offset + static_cast<uint64_t>(v) * VN + e >= A.skip_below) {
+            vsum += static_cast<double>(wn[u][e]);
+            vcnt += 1.0;
+          }
+      }
+    }
+  }
+  if (MID || !last) {
+    acc[0] = static_cast<double>(count);
+  } else {
+    acc[0] = vsum;
+    acc[1] = vcnt;
+  }
+}
+
 template <typename Real, int KT>
 __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const PersistArgs<Real> A) {
   constexpr int VN = PVec<Real>::N;                   // paths per 16-byte vector
@@ -195,6 +360,8 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
       uint64_t pol_first, pol_normal;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
       asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_normal));
+      if (A.tune & 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_normal));
+      if (A.tune & 8) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_first));
       uint32_t it = 0;
       for (int j = 0; j < T; ++j) {
         const bool last = j == T - 1;
@@ -202,9 +369,9 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
         const Real* cola = last ? colu
                                 : A.paths + static_cast<int64_t>(A.ex_times[T - 2 - j]) * A.stride_time;
         for (uint32_t i = 0; i < num_my; ++i, ++it) {
-          const uint32_t tile = (j & 1) ? tile_hi - 1 - i : tile_lo + i;
+          const uint32_t tile = ((j & 1) && !(A.tune & 4)) ? tile_hi - 1 - i : tile_lo + i;
           const uint32_t s = it % kPStages, ph = (it / kPStages) & 1u;
-          if (!p_mbar_wait(empty0 + 8 * s, ph ^ 1u)) {
+          if (!p_mbar_wait(empty0 + 8 * s, ph ^ 1u, 200)) {
             atomicExch(A.ctrl + 2, 2ull);
             return;
           }
@@ -230,131 +397,43 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
   // ---------------------------------------------------------------- consumers
   uint64_t keep;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+  if (A.tune & 1) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(keep));
   const int warp = tid >> 5, lane = tid & 31;
-  const Real strike = static_cast<Real>(A.strike);
+  SweepState st;
+  st.stage = 0;
+  st.phase = 0;
+  st.failed = false;
+  // shared-memory addresses computed once (opaque to the compiler, which would
+  // otherwise rematerialise the shared-window arithmetic in every iteration)
+  uint32_t ring = smem_base + tid * 16, fullb = full0, emptyb = empty0;
+  asm volatile("" : "+r"(ring), "+r"(fullb), "+r"(emptyb));
   const bool calib_all = A.num_calib == ~0ull;
-  uint4* wv = reinterpret_cast<uint4*>(A.w);
-  uint32_t it = 0;
-  bool failed = false;
 
   for (int j = 0; j < T; ++j) {
     const bool first = j == 0, last = j == T - 1;
     // update of exercise index e_u = T - j on column slot e_u - 1; accumulation for
     // e_a = T - j - 1 on column slot e_a - 1 (lsm.py:403-436)
-    Real beta[KT];
+    SweepParams<Real, KT> sp;
 #pragma unroll
-    for (int k = 0; k < KT; ++k) beta[k] = first ? Real(0) : static_cast<Real>(s_beta[k]);
-    const Real mean_u = first ? Real(0) : static_cast<Real>(A.means[T - 1 - j]);
-    const Real ratio_u = first ? Real(1) : static_cast<Real>(A.ratio[T - j]);
-    const Real mean_a = last ? Real(0) : static_cast<Real>(A.means[T - 2 - j]);
-    const Real ratio_a = last ? static_cast<Real>(1) : static_cast<Real>(A.ratio[T - 1 - j]);
+    for (int k = 0; k < KT; ++k) sp.beta[k] = first ? Real(0) : static_cast<Real>(s_beta[k]);
+    sp.strike = static_cast<Real>(A.strike);
+    sp.mean_u = first ? Real(0) : static_cast<Real>(A.means[T - 1 - j]);
+    sp.ratio_u = first ? Real(1) : static_cast<Real>(A.ratio[T - j]);
+    sp.mean_a = last ? Real(0) : static_cast<Real>(A.means[T - 2 - j]);
+    sp.ratio_a = last ? Real(1) : static_cast<Real>(A.ratio[T - 1 - j]);
+    sp.descending = (j & 1) != 0 && !(A.tune & 4);
     double acc[NA];
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.0;
-    double vsum = 0.0, vcnt = 0.0;
-
-    // W of the first tile (later tiles are fetched one tile ahead)
-    uint4 wnext[kPVecPerThread];
-    if (!first && num_my > 0) {
-      const uint32_t tile = (j & 1) ? tile_hi - 1 : tile_lo;
-#pragma unroll
-      for (int u = 0; u < kPVecPerThread; ++u) {
-        const uint32_t v = tile * kPTileVecs + u * kPConsumers + tid;
-        if (v < A.num_vecs) wnext[u] = p_ld_keep(wv + v, keep);
-      }
-    }
-    for (uint32_t i = 0; i < num_my; ++i, ++it) {
-      const uint32_t tile = (j & 1) ? tile_hi - 1 - i : tile_lo + i;
-      const uint32_t s = it % kPStages, ph = (it / kPStages) & 1u;
-      if (!p_mbar_wait(full0 + 8 * s, ph)) failed = true;
-      const uint32_t src = smem_base + s * (2 * kPTileBytes) + tid * 16;
-      uint4 xu_raw[kPVecPerThread], xa_raw[kPVecPerThread], w_raw[kPVecPerThread];
-#pragma unroll
-      for (int u = 0; u < kPVecPerThread; ++u) {
-        xu_raw[u] = p_lds(src + u * kPConsumers * 16);
-        xa_raw[u] = last ? xu_raw[u] : p_lds(src + kPTileBytes + u * kPConsumers * 16);
-        w_raw[u] = wnext[u];
-      }
-      __syncwarp();
-      if (lane == 0) p_mbar_arrive(empty0 + 8 * s);     // the stage is free again
-      if (!first && i + 1 < num_my) {
-        const uint32_t tn = (j & 1) ? tile - 1 : tile + 1;
-#pragma unroll
-        for (int u = 0; u < kPVecPerThread; ++u) {
-          const uint32_t v = tn * kPTileVecs + u * kPConsumers + tid;
-          if (v < A.num_vecs) wnext[u] = p_ld_keep(wv + v, keep);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kPVecPerThread; ++u) {
-        const uint32_t v = tile * kPTileVecs + u * kPConsumers + tid;
-        if (v >= A.num_vecs) continue;
-        Real xu[VN], xa[VN], wn[VN];
-        PVec<Real>::unpack(xu_raw[u], xu);
-        PVec<Real>::unpack(xa_raw[u], xa);
-        if (!first) PVec<Real>::unpack(w_raw[u], wn);
-#pragma unroll
-        for (int e = 0; e < VN; ++e) {
-          const Real pv = strike - xu[e];
-          const Real ev = pv > Real(0) ? pv : Real(0);
-          if (first) {
-            wn[e] = ev;                                  // the terminal cashflow
-          } else {
-            const Real c = xu[e] - mean_u;
-            Real cont = beta[KT - 1];
-#pragma unroll
-            for (int k = KT - 2; k >= 0; --k) cont = fma(cont, c, beta[k]);
-            cont = cont > Real(0) ? cont : Real(0);
-            wn[e] = ev > cont ? ev : ratio_u * wn[e];
-          }
-        }
-        p_st_keep(wv + v, PVec<Real>::pack(wn), keep);
-        const uint64_t n0 = A.path_offset + static_cast<uint64_t>(v) * VN;
-        if (!last) {
-#pragma unroll
-          for (int e = 0; e < VN; ++e) {
-            const Real pa = strike - xa[e];
-            const bool use = pa > Real(0) && (calib_all || (n0 + e) < A.num_calib);
-            if (use) {
-              double phi[KT];
-              const Real cr = xa[e] - mean_a;
-              Real pw = 1;
-#pragma unroll
-              for (int k = 0; k < KT; ++k) {
-                phi[k] = static_cast<double>(pw);
-                pw *= cr;
-              }
-              const double y = static_cast<double>(ratio_a * wn[e]);
-              int idx = 0;
-#pragma unroll
-              for (int a = 0; a < KT; ++a)
-#pragma unroll
-                for (int b = a; b < KT; ++b) {
-                  acc[idx] = fma(phi[a], phi[b], acc[idx]);
-                  ++idx;
-                }
-#pragma unroll
-              for (int a = 0; a < KT; ++a)
-                acc[KT * (KT + 1) / 2 + a] = fma(phi[a], y, acc[KT * (KT + 1) / 2 + a]);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < VN; ++e)
-            if (n0 + e >= A.skip_below) {
-              vsum += static_cast<double>(wn[e]);
-              vcnt += 1.0;
-            }
-        }
-      }
-    }
+    if (!first && !last && calib_all)
+      p_sweep<Real, KT, true>(A, sp, st, acc, ring, fullb, emptyb, tile_lo, tile_hi, tid, lane, keep,
+                              false, false);
+    else
+      p_sweep<Real, KT, false>(A, sp, st, acc, ring, fullb, emptyb, tile_lo, tile_hi, tid, lane, keep,
+                               first, last);
 
     // ---- CTA partial sums -> global row (packed 6 x 6 layout), fixed order
     const int M = last ? 2 : kLsmFastNS;
-    if (last) {                            // NA >= 2 for every K
-      acc[0] = vsum;
-      acc[1] = vcnt;
-    }
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
       const double v = warp_sum(acc[i]);
@@ -452,7 +531,7 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
     }
     p_bar_consumers();
   }
-  if (failed && tid == 0) atomicExch(A.ctrl + 2, 4ull);
+  if (st.failed && tid == 0) atomicExch(A.ctrl + 2, 4ull);
 }
 
 bool lsm_persistent_ok(const tqf_lsm* h) {
@@ -513,6 +592,7 @@ static int run_persistent_t(tqf_lsm* h, int num_times, const double* means_dev,
   A.history = history_dev;
   A.value_sums = value_sums_dev;
   A.ctrl = h->ctrl_dev;
+  if (const char* t = std::getenv("TQF_LSM_TUNE")) A.tune = std::atoi(t);
   A.peer.peer_rank = h->peer_rank;
   A.peer.peer_world = h->peer_world;
   A.peer.peer_epoch = h->peer_epoch;
