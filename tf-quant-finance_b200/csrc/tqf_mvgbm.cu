@@ -64,6 +64,8 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
   Real* s_z = reinterpret_cast<Real*>(s_dyn);
   const int tid = threadIdx.x;
   const fm::ConstTab tab(P.logtab);
+  // the Philox stream's Box-Muller logarithm reads the MID-free table stored behind it
+  const fm::ConstTab tab0(P.logtab + 2 * TQF_LOGTAB_COUNT);
   for (int i = tid; i < kWarps * TQF_MAX_PAYOFFS * 3; i += kBlock) s_acc[i] = 0.0;
   __syncthreads();
 
@@ -87,7 +89,7 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
     PhiloxStreamV<Real, 1> stream;
     if (P.rngk == RNGK_PHILOX) {
       const uint64_t fe[1] = {valid ? (P.path_offset + local) * stream_stride : 0};
-      stream.init(P.key, P.ctr, tab, fe);
+      stream.init(P.key, P.ctr, tab0, fe);
     }
 
     auto eval_payoffs = [&](int step_index) {
@@ -181,7 +183,7 @@ mvgbm_kernel(const __grid_constant__ MvParams<Real, DMAX> P) {
         } else {
           for (int j = 0; j < dim; ++j) {
             Real zo[1];
-            stream.next(P.key, P.ctr, tab, zo);
+            stream.next(P.key, P.ctr, tab0, zo);
             s_z[j * kBlock + tid] = zo[0];
           }
         }
@@ -445,6 +447,8 @@ mvgbm_split_kernel(const __grid_constant__ MvParams<Real, kMvDim> P) {
   const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
   for (int i = tid; i < kMvParts * kMvSplitStride; i += blockDim.x) s_split[i] = P.lsplit[i];
   const fm::ConstTab tab(P.logtab);
+  // the Philox stream's Box-Muller logarithm reads the MID-free table stored behind it
+  const fm::ConstTab tab0(P.logtab + 2 * TQF_LOGTAB_COUNT);
   for (int i = tid; i < TQF_MAX_PAYOFFS * 3; i += blockDim.x) s_acc[i] = 0.0;
   __syncthreads();
 
@@ -614,10 +618,10 @@ mvgbm_split_kernel(const __grid_constant__ MvParams<Real, kMvDim> P) {
           for (int q = 0; q < NP; ++q) {
             PhiloxStreamV<Real, 1> stream;
             const uint64_t fe[1] = {elem_base[q] + static_cast<uint64_t>(s) * dim + j_begin};
-            if (j_count > 0) stream.init(P.key, P.ctr, tab, fe);
+            if (j_count > 0) stream.init(P.key, P.ctr, tab0, fe);
             for (int jj = 0; jj < kMvRows; ++jj) {
               Real zo[1] = {0};
-              if (jj < j_count) stream.next(P.key, P.ctr, tab, zo);
+              if (jj < j_count) stream.next(P.key, P.ctr, tab0, zo);
               sts_real(zw + (jj >> 2) * kZg + q * kZq + (jj & 3) * sizeof(Real), zo[0]);
             }
           }

@@ -1,6 +1,7 @@
 // Host side of the path engine: plans (device-resident tables), the fused
 // pricing launch and the path-materialising launch.  C ABI in include/tqf.h.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -31,18 +32,39 @@ TQF_EXTERN_MODEL(AffineModel4D)
 
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_blocks,
                                        int num_payoffs, double* __restrict__ sums, const PeerK pk) {
-  // One warp per (payoff, statistic); fixed summation order -> reproducible.
+  // Thread t sums the rows t, t + 256, ... (independent loads), then every
+  // (payoff, statistic) is combined by a shuffle tree and across the 8 warps in a
+  // fixed order -> reproducible for a given grid.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
-  for (int item = warp; item < num_payoffs * 4; item += nwarps) {
-    const int q = item >> 2, k = item & 3;
-    double v = 0.0;
-    if (k < 3) {
-      for (int b = lane; b < num_blocks; b += 32)
-        v += partials[(static_cast<size_t>(b) * TQF_MAX_PAYOFFS + q) * 4 + k];
+  __shared__ double s_w[8][TQF_MAX_PAYOFFS * 3];
+  double acc[TQF_MAX_PAYOFFS * 3];
+#pragma unroll
+  for (int i = 0; i < TQF_MAX_PAYOFFS * 3; ++i) acc[i] = 0.0;
+  for (int b = threadIdx.x; b < num_blocks; b += blockDim.x) {
+    const double* row = partials + static_cast<size_t>(b) * TQF_MAX_PAYOFFS * 4;
+#pragma unroll
+    for (int q = 0; q < TQF_MAX_PAYOFFS; ++q)
+      if (q < num_payoffs) {
+        const double4 v = *reinterpret_cast<const double4*>(row + q * 4);
+        acc[q * 3] += v.x;
+        acc[q * 3 + 1] += v.y;
+        acc[q * 3 + 2] += v.z;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < TQF_MAX_PAYOFFS * 3; ++i)
+    if (i < num_payoffs * 3) {
+      const double v = warp_sum(acc[i]);
+      if (lane == 0) s_w[warp][i] = v;
     }
-    v = warp_sum(v);
-    if (lane == 0) sums[q * 4 + k] = v;
+  __syncthreads();
+  if (threadIdx.x < num_payoffs * 4) {
+    const int q = threadIdx.x >> 2, k = threadIdx.x & 3;
+    double v = 0.0;
+    if (k < 3)
+      for (int w = 0; w < nwarps; ++w) v += s_w[w][q * 3 + k];
+    sums[q * 4 + k] = v;
   }
   // several GPUs: the sums of all ranks are added here, over NVLink peer memory
   // and in rank order (bit-identical on every rank) -- no NCCL call per pricing
@@ -50,6 +72,19 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
     __syncthreads();
     peer_all_reduce(pk, sums, num_payoffs * 4);
   }
+}
+
+int resident_grid(const void* kernel, size_t smem) {
+  int per_sm = 0, dev = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem) != cudaSuccess ||
+      cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int mult = 1;
+  if (const char* e = std::getenv("TQF_GRID_WAVES")) mult = std::atoi(e) > 0 ? std::atoi(e) : 1;
+  return per_sm * sms * mult;
 }
 
 struct ModelInfo {
@@ -342,7 +377,8 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PRICE, false);
   }
   P.tables_in_smem = in_smem ? 1 : 0;
-  int rc = dispatch<Real>(plan, MODE_PRICE, plan->max_grid, smem, P, stream, &grid);
+  int rc = dispatch<Real>(plan, P.need_extrema ? MODE_PRICE_EXTREMA : MODE_PRICE, plan->max_grid, smem,
+                          P, stream, &grid);
   if (rc != TQF_OK) return rc;
   reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev,
                                                   next_peer_exchange(plan));
@@ -523,7 +559,9 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
   int sms = kSMs;
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device);
   if (e != cudaSuccess) rc = cuda_fail(e, "cudaGetDevice");
-  plan->max_grid = sms * 16;
+  plan->max_grid = sms * 32;
+  if (const char* e = std::getenv("TQF_GRID_PER_SM"))
+    if (std::atoi(e) > 0) plan->max_grid = sms * std::atoi(e);
   if (rc == TQF_OK) {
     rc = model->dtype == TQF_F64 ? upload_coef<double>(model, info.ncoef, &plan->coef_dev)
                                  : upload_coef<float>(model, info.ncoef, &plan->coef_dev);

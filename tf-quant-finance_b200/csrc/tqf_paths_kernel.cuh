@@ -31,7 +31,10 @@ constexpr int kSobolTileDims = TQF_SOBOL_TILE;  // Sobol dimensions staged in sm
 constexpr int kWarps = kBlock / 32;
 constexpr int kMaxPPT = 8;      // most paths carried by one thread
 
-enum { MODE_PRICE = 0, MODE_PATHS = 1 };
+// MODE_PRICE_EXTREMA: MODE_PRICE that also tracks the running extrema of the monitored
+// component (barrier payoffs); a mode of its own so that the plain pricing kernels carry
+// neither the registers nor the per-step test.
+enum { MODE_PRICE = 0, MODE_PATHS = 1, MODE_PRICE_EXTREMA = 2 };
 enum { RNGK_PHILOX = 0, RNGK_SOBOL = 1, RNGK_DRAWS = 2 };
 
 struct PayoffK {
@@ -291,6 +294,44 @@ struct HestonQeModel {
 template <typename Real, int PPT>
 struct PhiloxStreamV;
 
+// BoxMullerDouble (random_distributions.h) of PPT Philox groups side by side:
+//   u1 = max(U(x0, x1), 1e-7), v = 2 pi U(x2, x3), r = sqrt(-2 ln u1) -> (r sin v, r cos v).
+// -ln u1 comes from the table logarithm (tqf_logtab0.inc, MID-free: 8 FP64
+// instructions instead of 18 + MUFU + I2F); its absolute error of a few 1e-19 near
+// u1 = 1 and 1e-15 near 2^-14 keeps r within 1e-14 relative wherever r > 1e-5.
+// Arguments below 2^-14 (6e-5 of the draws, u1 = 0 and the 1e-7 clamp included)
+// take the full-precision logarithm in a rarely entered branch.
+template <int PPT, class Tab>
+__device__ __forceinline__ void philox_box_muller_v(const PhiloxKey& key, const PhiloxCtr& ctr,
+                                                    const Tab& tab, uint64_t (&group)[PPT],
+                                                    double (&z0)[PPT], double (&z1)[PPT]) {
+  double u1[PPT], v1[PPT], w[PPT], sn[PPT], cs[PPT];
+#pragma unroll
+  for (int a = 0; a < PPT; ++a) {
+    const uint4 q = philox_group(ctr, key, group[a]);
+    ++group[a];
+    u1[a] = uint64_to_double(q.x, q.y);
+    v1[a] = 6.283185307179586476925286766559 * uint64_to_double(q.z, q.w);
+  }
+  uint32_t hmin;
+  fm::neg_log_mid_tab_v<PPT>(tab, u1, w, &hmin);
+  if (hmin < 0x3f100000u) {                       // some u1 < 2^-14: outside the table
+#pragma unroll
+    for (int a = 0; a < PPT; ++a)
+      if (static_cast<uint32_t>(__double2hiint(u1[a])) < 0x3f100000u) {
+        const double u = u1[a] < 1.0e-7 ? 1.0e-7 : u1[a];
+        w[a] = -fm::log_pos(u);
+      }
+  }
+  fm::sincos_2pi_v<PPT>(tab, v1, sn, cs);
+#pragma unroll
+  for (int a = 0; a < PPT; ++a) {
+    const double r = fm::sqrt_pos(w[a] + w[a]);
+    z0[a] = sn[a] * r;
+    z1[a] = cs[a] * r;
+  }
+}
+
 template <int PPT>
 struct PhiloxStreamV<double, PPT> {
   uint64_t group[PPT];
@@ -299,23 +340,7 @@ struct PhiloxStreamV<double, PPT> {
   template <class Tab>
   __device__ __forceinline__ void refill(const PhiloxKey& key, const PhiloxCtr& ctr,
                                          const Tab& tab) {
-    double u1[PPT], v1[PPT], lg[PPT], sn[PPT], cs[PPT];
-#pragma unroll
-    for (int a = 0; a < PPT; ++a) {
-      const uint4 w = philox_group(ctr, key, group[a]);
-      ++group[a];
-      const double u = uint64_to_double(w.x, w.y);
-      u1[a] = u < 1.0e-7 ? 1.0e-7 : u;
-      v1[a] = 6.283185307179586476925286766559 * uint64_to_double(w.z, w.w);
-    }
-    fm::log_pos_v<PPT>(tab, u1, lg);
-    fm::sincos_2pi_v<PPT>(tab, v1, sn, cs);
-#pragma unroll
-    for (int a = 0; a < PPT; ++a) {
-      const double r = fm::sqrt_pos(-2.0 * lg[a]);
-      b0[a] = sn[a] * r;
-      b1[a] = cs[a] * r;
-    }
+    philox_box_muller_v<PPT>(key, ctr, tab, group, b0, b1);
   }
   template <class Tab>
   __device__ __forceinline__ void init(const PhiloxKey& key, const PhiloxCtr& ctr,
@@ -587,6 +612,8 @@ path_kernel(const KParams<typename Model::Real> P) {
   constexpr int DIM = Model::DIM, NF = Model::NF, NCOEF = Model::NCOEF;
   constexpr int NPATH = ANTI ? 2 : 1;
   constexpr int PPT = PathsPerThread<Model, RNGK>::value;
+  constexpr bool kPrice = MODE != MODE_PATHS;
+  constexpr bool kExtrema = MODE == MODE_PRICE_EXTREMA;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: log table (double Sobol only) | coef [S][NCOEF] Real | record_slot
@@ -594,7 +621,9 @@ path_kernel(const KParams<typename Model::Real> P) {
   //         accumulators [kWarps][8][3] double
   // {T, s} table of the table logarithm behind the FP64 inverse CDF: first, so
   // that its shared address is a compile-time constant in the LDS
-  constexpr bool kLogTab = RNGK == RNGK_SOBOL && sizeof(Real) == 8;
+  // (double Sobol: the ndtri table; double Philox: the MID-free table of the
+  // Box-Muller logarithm, stored behind the first one in the device buffer)
+  constexpr bool kLogTab = (RNGK == RNGK_SOBOL || RNGK == RNGK_PHILOX) && sizeof(Real) == 8;
   double* s_logtab = reinterpret_cast<double*>(smem_raw);
   size_t off = kLogTab ? static_cast<size_t>(TQF_LOGTAB_COUNT) * 2 * sizeof(double) : 0;
   Real* s_coef = reinterpret_cast<Real*>(smem_raw + off);
@@ -613,7 +642,9 @@ path_kernel(const KParams<typename Model::Real> P) {
   double* s_col = s_acc + kWarps * TQF_MAX_PAYOFFS * 3;   // [kWarps][colsum_cols]
 
   const int tid = threadIdx.x;
-  if (kLogTab) fm::fill_smem_logtab(s_logtab, P.logtab, tid, kBlock);
+  if (kLogTab)
+    fm::fill_smem_logtab(s_logtab, P.logtab + (RNGK == RNGK_PHILOX ? 2 * TQF_LOGTAB_COUNT : 0), tid,
+                         kBlock);
   const fm::SmemTab tab = kLogTab ? fm::SmemTab(s_logtab) : fm::SmemTab();
   const Real* coef_tab = P.coef;
   const int* rec_tab = P.record_slot;
@@ -623,7 +654,7 @@ path_kernel(const KParams<typename Model::Real> P) {
     for (int i = tid; i <= P.num_steps; i += kBlock) s_rec[i] = P.record_slot[i];
     rec_tab = s_rec;
   }
-  if (MODE == MODE_PRICE) {
+  if (kPrice) {
     for (int i = tid; i < kWarps * TQF_MAX_PAYOFFS * 3; i += kBlock) s_acc[i] = 0.0;
   } else if (P.colsum_partials) {
     for (int i = tid; i < kWarps * P.colsum_cols; i += kBlock) s_col[i] = 0.0;
@@ -674,14 +705,11 @@ path_kernel(const KParams<typename Model::Real> P) {
           if (P.x0_paths != nullptr && valid[a])
             x0j = P.x0_paths[(P.path_offset + local[a] + h * P.x0_half) * DIM + j];
           x[a][h][j] = x0j;
-          if (j == 0 || j == P.monitor) {
+          if (kExtrema && (j == 0 || j == P.monitor)) {
             xmax[a][h] = x0j;
             xmin[a][h] = x0j;
           }
         }
-
-    PhiloxStreamV<Real, PPT> stream;
-    if (RNGK == RNGK_PHILOX) stream.init(P.key, P.ctr, tab, first_element);
 
     // Stores the state of every path of this thread into time slot `slot`.
     auto store_slot = [&](int slot) {
@@ -739,9 +767,9 @@ path_kernel(const KParams<typename Model::Real> P) {
                 swap = sw.is_payer ? swap : -swap;
                 v = (swap > 0.0 ? swap : 0.0) * d.scale;
               } else {
-                const double xa = static_cast<double>(xmax[a][h]);
-                const double xi = static_cast<double>(xmin[a][h]);
                 const double xf = static_cast<double>(select_component<Real, DIM>(x[a][h], d.component));
+                const double xa = kExtrema ? static_cast<double>(xmax[a][h]) : xf;
+                const double xi = kExtrema ? static_cast<double>(xmin[a][h]) : xf;
                 const double tg = (d.kind == TQF_PAYOFF_CALL_TANGENT || d.kind == TQF_PAYOFF_PUT_TANGENT)
                                       ? static_cast<double>(select_component<Real, DIM>(x[a][h], d.tangent))
                                       : 0.0;
@@ -767,7 +795,107 @@ path_kernel(const KParams<typename Model::Real> P) {
         }
       }
     };
-    if (MODE == MODE_PRICE && rec_tab[0] >= 0) eval_payoffs(0);
+    if (kPrice && rec_tab[0] >= 0) eval_payoffs(0);
+
+    // One Euler step of every path of this thread with the normals z, then the
+    // running extrema and the payoffs / stores attached to the step.
+    auto step_body = [&](int s, const Real (&z)[PPT][NF]) {
+      const int rec_next = rec_tab[s + 1];
+      Real cc[NCOEF];
+      load_step_coef<Real, NCOEF>(coef_tab + static_cast<size_t>(s) * NCOEF, cc);
+#pragma unroll
+      for (int a = 0; a < PPT; ++a) {
+        Model::step(x[a][0], z[a], cc);
+        if (ANTI) {
+          Real zm[NF];
+#pragma unroll
+          for (int j = 0; j < NF; ++j) zm[j] = -z[a][j];
+          Model::step(x[a][NPATH - 1], zm, cc);
+        }
+      }
+      if (kPrice) {
+        if (kExtrema) {
+          // running extrema of the ONE monitored state component; the flags are
+          // uniform, so each block is a branch around straight-line code
+          if (DIM == 1 || P.monitor == 0) {
+            if (P.need_extrema & 1) {
+#pragma unroll
+              for (int a = 0; a < PPT; ++a)
+#pragma unroll
+                for (int h = 0; h < NPATH; ++h)
+                  xmax[a][h] = x[a][h][0] > xmax[a][h] ? x[a][h][0] : xmax[a][h];
+            }
+            if (P.need_extrema & 2) {
+#pragma unroll
+              for (int a = 0; a < PPT; ++a)
+#pragma unroll
+                for (int h = 0; h < NPATH; ++h)
+                  xmin[a][h] = x[a][h][0] < xmin[a][h] ? x[a][h][0] : xmin[a][h];
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < PPT; ++a)
+#pragma unroll
+              for (int h = 0; h < NPATH; ++h) {
+                const Real xm = select_component<Real, DIM>(x[a][h], P.monitor);
+                if (P.need_extrema & 1) xmax[a][h] = xm > xmax[a][h] ? xm : xmax[a][h];
+                if (P.need_extrema & 2) xmin[a][h] = xm < xmin[a][h] ? xm : xmin[a][h];
+              }
+          }
+        }
+        if (rec_next >= 0) eval_payoffs(s + 1);
+      } else {
+        if (rec_next >= 0) store_slot(rec_next);
+      }
+    };
+
+    // float64 Philox with one or two factors: a Philox group yields the normals of
+    // two consecutive steps (NF = 1) or of the two factors of one step (NF = 2), so
+    // the loop consumes whole groups and nothing selects between buffered halves.
+    constexpr bool kPhiloxPairs = RNGK == RNGK_PHILOX && sizeof(Real) == 8 && NF <= 2;
+    if (kPhiloxPairs) {
+      uint64_t group[PPT];
+#pragma unroll
+      for (int a = 0; a < PPT; ++a) group[a] = first_element[a] >> 1;
+      double g0[PPT], g1[PPT];
+      Real z[PPT][NF];
+      int s = 0;
+      if (NF == 1) {
+        // A path whose first element is odd (odd number of steps per path) starts in
+        // the middle of a group -- same parity for all paths of a thread: its loop
+        // starts at s = -1 and skips that half.  Two step bodies per group, each
+        // guarded by a compare (the payoff code inside is instantiated twice, not
+        // once per special case).
+        s = (first_element[0] & 1) ? -1 : 0;
+        for (; s < P.num_steps; s += 2) {
+          philox_box_muller_v<PPT>(P.key, P.ctr, tab, group, g0, g1);
+          if (s >= 0) {
+#pragma unroll
+            for (int a = 0; a < PPT; ++a) z[a][0] = static_cast<Real>(g0[a]);
+            step_body(s, z);
+          }
+          if (s + 1 < P.num_steps) {
+#pragma unroll
+            for (int a = 0; a < PPT; ++a) z[a][0] = static_cast<Real>(g1[a]);
+            step_body(s + 1, z);
+          }
+        }
+      } else {
+        for (; s < P.num_steps; ++s) {
+          philox_box_muller_v<PPT>(P.key, P.ctr, tab, group, g0, g1);
+#pragma unroll
+          for (int a = 0; a < PPT; ++a) {
+            z[a][0] = static_cast<Real>(g0[a]);
+            z[a][NF - 1] = static_cast<Real>(g1[a]);
+          }
+          step_body(s, z);
+        }
+      }
+      continue;                                   // next super-chunk
+    }
+
+    PhiloxStreamV<Real, PPT> stream;
+    if (RNGK == RNGK_PHILOX) stream.init(P.key, P.ctr, tab, first_element);
 
     for (int s0 = 0; s0 < P.num_steps; s0 += TILE_STEPS) {
       const int s1 = min(P.num_steps, s0 + TILE_STEPS);
@@ -795,11 +923,6 @@ path_kernel(const KParams<typename Model::Real> P) {
         __syncthreads();
       }
       for (int s = s0; s < s1; ++s) {
-        // step constants and record flag: loaded here, consumed after the draws
-        // (the loads' latency hides behind the inverse CDFs)
-        const int rec_next = rec_tab[s + 1];
-        Real cc[NCOEF];
-        load_step_coef<Real, NCOEF>(coef_tab + static_cast<size_t>(s) * NCOEF, cc);
         Real z[PPT][NF];
         if (RNGK == RNGK_PHILOX) {
 #pragma unroll
@@ -839,56 +962,13 @@ path_kernel(const KParams<typename Model::Real> P) {
             for (int j = 0; j < NF; ++j)
               z[a][j] = P.draws[first_element[a] + static_cast<size_t>(s) * NF + j];
         }
-#pragma unroll
-        for (int a = 0; a < PPT; ++a) {
-          Model::step(x[a][0], z[a], cc);
-          if (ANTI) {
-            Real zm[NF];
-#pragma unroll
-            for (int j = 0; j < NF; ++j) zm[j] = -z[a][j];
-            Model::step(x[a][NPATH - 1], zm, cc);
-          }
-        }
-        if (MODE == MODE_PRICE) {
-          if (P.need_extrema) {
-            // running extrema of the ONE monitored state component; the flags are
-            // uniform, so each block is a branch around straight-line code
-            if (DIM == 1 || P.monitor == 0) {
-              if (P.need_extrema & 1) {
-#pragma unroll
-                for (int a = 0; a < PPT; ++a)
-#pragma unroll
-                  for (int h = 0; h < NPATH; ++h)
-                    xmax[a][h] = x[a][h][0] > xmax[a][h] ? x[a][h][0] : xmax[a][h];
-              }
-              if (P.need_extrema & 2) {
-#pragma unroll
-                for (int a = 0; a < PPT; ++a)
-#pragma unroll
-                  for (int h = 0; h < NPATH; ++h)
-                    xmin[a][h] = x[a][h][0] < xmin[a][h] ? x[a][h][0] : xmin[a][h];
-              }
-            } else {
-#pragma unroll
-              for (int a = 0; a < PPT; ++a)
-#pragma unroll
-                for (int h = 0; h < NPATH; ++h) {
-                  const Real xm = select_component<Real, DIM>(x[a][h], P.monitor);
-                  if (P.need_extrema & 1) xmax[a][h] = xm > xmax[a][h] ? xm : xmax[a][h];
-                  if (P.need_extrema & 2) xmin[a][h] = xm < xmin[a][h] ? xm : xmin[a][h];
-                }
-            }
-          }
-          if (rec_next >= 0) eval_payoffs(s + 1);
-        } else {
-          if (rec_next >= 0) store_slot(rec_next);
-        }
+        step_body(s, z);
       }
     }
 
   }
 
-  if (MODE == MODE_PRICE) {
+  if (kPrice) {
     __syncthreads();
     for (int i = tid; i < TQF_MAX_PAYOFFS * 3; i += kBlock) {
       double v = 0.0;
@@ -925,10 +1005,14 @@ size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool table
   if (rngk == RNGK_SOBOL) off += static_cast<size_t>(ppt) * kSobolTileDims * sizeof(uint32_t) + static_cast<size_t>(kSobolTileDims) * 8 * sizeof(uint32_t);
   off += static_cast<size_t>(kWarps) * TQF_MAX_PAYOFFS * 3 * sizeof(double);
   off += static_cast<size_t>(kWarps) * colsum_cols * sizeof(double);
-  if (rngk == RNGK_SOBOL && sizeof(Real) == 8)
+  if ((rngk == RNGK_SOBOL || rngk == RNGK_PHILOX) && sizeof(Real) == 8)
     off += static_cast<size_t>(TQF_LOGTAB_COUNT) * 2 * sizeof(double);
   return off;
 }
+
+// CTAs of `kernel` (kBlock threads, `smem` dynamic bytes) that are resident at the
+// same time on the current device; 0 when the query fails.  tqf_paths.cu.
+int resident_grid(const void* kernel, size_t smem);
 
 // Launches the right instantiation for (rng kind, antithetic, mode).
 template <class Model>
@@ -944,13 +1028,21 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
         Model::NCOEF, P.num_steps, RK, MD, P.tables_in_smem != 0, ppt,                 \
         P.colsum_partials ? P.colsum_cols : 0);                                        \
     const uint64_t num_super = (P.num_chunks + ppt - 1) / ppt;                         \
-    int grid = static_cast<int>(num_super < static_cast<uint64_t>(max_grid)            \
-                                    ? num_super : static_cast<uint64_t>(max_grid));    \
-    if (grid < 1) grid = 1;                                                            \
-    *grid_out = grid;                                                                  \
     if (smem > 48 * 1024)                                                              \
       TQF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        static_cast<int>(smem)));                       \
+    /* Many more CTAs than are resident (max_grid = 32 per SM, ~11 waves): the    */   \
+    /* CTAs of an SM drift out of phase, so the table staging of one overlaps the */   \
+    /* arithmetic of the others (a grid of exactly the resident CTAs, which run   */   \
+    /* in lock step, measured 8% slower on C2), and the last partial wave is      */   \
+    /* short.  Each CTA walks its chunks with a grid stride: the per-CTA partial  */   \
+    /* sums and their fixed-order reduction stay reproducible.                    */   \
+    (void)&resident_grid;                                                              \
+    const int cap = max_grid;                                                          \
+    int grid = static_cast<int>(num_super < static_cast<uint64_t>(cap)                 \
+                                    ? num_super : static_cast<uint64_t>(cap));         \
+    if (grid < 1) grid = 1;                                                            \
+    *grid_out = grid;                                                                  \
     kern<<<grid, kBlock, smem, stream>>>(P);                                           \
     TQF_CUDA_OK(cudaGetLastError());                                                   \
     return TQF_OK;                                                                     \
@@ -960,6 +1052,11 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
     if (rngk == RNGK_PHILOX) TQF_LAUNCH(RNGK_PHILOX, false, MODE_PRICE);
     if (rngk == RNGK_SOBOL) TQF_LAUNCH(RNGK_SOBOL, false, MODE_PRICE);
     if (rngk == RNGK_DRAWS) TQF_LAUNCH(RNGK_DRAWS, false, MODE_PRICE);
+  } else if (mode == MODE_PRICE_EXTREMA) {
+    if (rngk == RNGK_PHILOX && anti) TQF_LAUNCH(RNGK_PHILOX, true, MODE_PRICE_EXTREMA);
+    if (rngk == RNGK_PHILOX) TQF_LAUNCH(RNGK_PHILOX, false, MODE_PRICE_EXTREMA);
+    if (rngk == RNGK_SOBOL) TQF_LAUNCH(RNGK_SOBOL, false, MODE_PRICE_EXTREMA);
+    if (rngk == RNGK_DRAWS) TQF_LAUNCH(RNGK_DRAWS, false, MODE_PRICE_EXTREMA);
   } else {
     if (rngk == RNGK_PHILOX && anti) TQF_LAUNCH(RNGK_PHILOX, true, MODE_PATHS);
     if (rngk == RNGK_PHILOX) TQF_LAUNCH(RNGK_PHILOX, false, MODE_PATHS);

@@ -23,8 +23,12 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 // Device-global copy of the {T, 1/c} table of the table logarithm
 // (tqf_math.cuh); uploaded once per device and kept for the process lifetime.
-static const double kLogTabHost[2 * TQF_LOGTAB_COUNT] = {
+// Two tables back to back: the one of the central ndtri branch (T carries the
+// -MID offset) and the MID-free one behind the Box-Muller logarithm of the Philox
+// path (kernels address it at +2 * TQF_LOGTAB_COUNT doubles).
+static const double kLogTabHost[4 * TQF_LOGTAB_COUNT] = {
 #include "tqf_logtab.inc"
+#include "tqf_logtab0.inc"
 };
 
 int device_logtab(const double** out) {
