@@ -74,19 +74,6 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
   }
 }
 
-int resident_grid(const void* kernel, size_t smem) {
-  int per_sm = 0, dev = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem) != cudaSuccess ||
-      cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  int mult = 1;
-  if (const char* e = std::getenv("TQF_GRID_WAVES")) mult = std::atoi(e) > 0 ? std::atoi(e) : 1;
-  return per_sm * sms * mult;
-}
-
 struct ModelInfo {
   int dim, nf, ncoef;
 };

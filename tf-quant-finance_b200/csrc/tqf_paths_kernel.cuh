@@ -103,6 +103,22 @@ struct KParams {
   int colsum_cols;           // number of time slots * DIM
 };
 
+// v[comp] for a register-resident state vector.  Written with opaque `selp`s:
+// a plain `j == comp ? v[j] : r` chain is turned into an indexed load by the
+// compiler, which moves the whole state array to local memory (an LDL/STL pair
+// per path and step in the hot loop).
+__device__ __forceinline__ double selp_real(double a, double b, int take_a) {
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}"
+      : "=d"(r) : "d"(a), "d"(b), "r"(take_a));
+  return r;
+}
+__device__ __forceinline__ float selp_real(float a, float b, int take_a) {
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}"
+      : "=f"(r) : "f"(a), "f"(b), "r"(take_a));
+  return r;
+}
 // ------------------------------------------------------------- models -----
 // coef columns: 0 = dt, 1 = sqrt(dt), then model specific.  Every step mirrors
 // _euler_step (euler_sampling.py:513-537): dw = z sqrt_dt;
@@ -265,26 +281,126 @@ struct HestonQeModel {
   __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
                                               const Real (&c)[NCOEF]) {
     if (c[0] == Real(0)) return;  // zero-length step: consumes its draws only
-    const Real v = x[1];
-    const Real m = c[2] + (v - c[2]) * c[1];
-    const Real s2 = fma(v, c[3], c[4]);
-    const Real psi = s2 / (m * m);
-    Real vn;
-    if (psi < Real(1.5)) {
-      const Real psi_inv = Real(2) / psi;
-      const Real b2 = psi_inv - Real(1) + sqrt(psi_inv * (psi_inv - Real(1)));
-      const Real a = m / (Real(1) + b2);
-      const Real t = sqrt(b2) + z[0];
+    step_impl(x, z, c);
+  }
+  // Reference arithmetic op for op (IEEE divisions and square roots of libdevice).
+  template <typename T>
+  __device__ static __forceinline__ void step_reference(T (&x)[DIM], const T (&z)[NF],
+                                                        const T (&c)[NCOEF]) {
+    const T v = x[1];
+    const T m = c[2] + (v - c[2]) * c[1];
+    const T s2 = fma(v, c[3], c[4]);
+    const T psi = s2 / (m * m);
+    T vn;
+    if (psi < T(1.5)) {
+      const T psi_inv = T(2) / psi;
+      const T b2 = psi_inv - T(1) + sqrt(psi_inv * (psi_inv - T(1)));
+      const T a = m / (T(1) + b2);
+      const T t = sqrt(b2) + z[0];
       vn = a * (t * t);
     } else {
-      const Real p = (psi - Real(1)) / (psi + Real(1));
-      const Real beta = (Real(1) - p) / m;
-      const Real u = Real(0.5) * (Real(1) + erf(z[0] * Real(0.70710678118654752440)));
-      vn = u > p ? (log(Real(1) - p) - log(Real(1) - u)) / beta : Real(0);
+      const T p = (psi - T(1)) / (psi + T(1));
+      const T beta = (T(1) - p) / m;
+      const T u = T(0.5) * (T(1) + erf(z[0] * T(0.70710678118654752440)));
+      vn = u > p ? (log(T(1) - p) - log(T(1) - u)) / beta : T(0);
     }
     x[0] = (((x[0] + c[5]) + c[6] * v) + c[7] * vn) + sqrt(c[8] * v + c[9] * vn) * z[1];
     x[1] = vn;
   }
+  __device__ static __forceinline__ void step_impl(float (&x)[DIM], const float (&z)[NF],
+                                                   const float (&c)[NCOEF]) {
+    step_reference<float>(x, z, c);
+  }
+  // float64 (see step_batch): the quadratic branch for one path.
+  __device__ static __forceinline__ void step_impl(double (&x)[DIM], const double (&z)[NF],
+                                                   const double (&c)[NCOEF]) {
+    double xs[1][1][DIM] = {{{x[0], x[1]}}};
+    const double zs[1][NF] = {{z[0], z[1]}};
+    step_batch<1, 1, 0>(xs, zs, c, 1.0);
+    x[0] = xs[0][0][0];
+    x[1] = xs[0][0][1];
+  }
+
+  // The QE step of the N paths a thread carries (float64), half H of each
+  // antithetic pair, normals sign * z:
+  //  * the quadratic branch (psi < 1.5, ~97% of the path-steps of config C2) runs for
+  //    all N side by side on the hand-written reciprocal / square root (5-6 FP64
+  //    instructions each, <= 1 ulp, no special-case code): two reciprocals and three
+  //    square roots per step instead of three IEEE divisions and square roots;
+  //  * the paths that need the exponential branch (psi >= 1.5: variance near zero) or
+  //    have degenerate inputs are then served ONE PER ITERATION of a compacting loop
+  //    (a lane with one such path runs the ~300-instruction reference arithmetic once;
+  //    a branch per path would run it once per path for the whole warp).
+  static constexpr bool kBatchStep = sizeof(R) == 8;
+  template <int N, int NP, int H>
+  __device__ static __forceinline__ void step_batch(double (&x)[N][NP][DIM],
+                                                    const double (&z)[N][NF],
+                                                    const double (&c)[NCOEF], double sign) {
+    if (c[0] == 0.0) return;
+    double v[N], m[N], s2[N], vn[N];
+    unsigned slow = 0;
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+      v[a] = x[a][H][1];
+      m[a] = c[2] + (v[a] - c[2]) * c[1];
+      s2[a] = fma(v[a], c[3], c[4]);
+      const double m2 = m[a] * m[a];
+      // psi = s2 / m2 < 1.5  <=>  s2 < 1.5 m2 for positive m2
+      const bool quad = m[a] > 1e-150 && s2[a] > 1e-300 && s2[a] < 1.5 * m2 && m2 < 1e150;
+      slow |= quad ? 0u : (1u << a);
+      const double q = (m2 + m2) * fm::rcp_pos(quad ? s2[a] : 1.0);     // 2 / psi  (> 4/3)
+      const double t1 = q - 1.0;
+      const double b2 = t1 + fm::sqrt_pos(q * t1);
+      const double al = m[a] * fm::rcp_pos(1.0 + b2);
+      const double t = fm::sqrt_pos(b2) + sign * z[a][0];
+      vn[a] = al * (t * t);
+    }
+    while (slow) {
+      const int a = __ffs(slow) - 1;
+      slow &= slow - 1;
+      double ms = m[0], ss = s2[0], zs = z[0][0];
+#pragma unroll
+      for (int k = 1; k < N; ++k) {
+        ms = selp_real(m[k], ms, k == a ? 1 : 0);
+        ss = selp_real(s2[k], ss, k == a ? 1 : 0);
+        zs = selp_real(z[k][0], zs, k == a ? 1 : 0);
+      }
+      // reference arithmetic (heston_model.py:522-551)
+      const double psi = ss / (ms * ms);
+      double r;
+      if (psi < 1.5) {
+        const double psi_inv = 2.0 / psi;
+        const double b2 = psi_inv - 1.0 + sqrt(psi_inv * (psi_inv - 1.0));
+        const double t = sqrt(b2) + sign * zs;
+        r = ms / (1.0 + b2) * (t * t);
+      } else {
+        const double p = (psi - 1.0) / (psi + 1.0);
+        const double beta = (1.0 - p) / ms;
+        const double u = 0.5 * (1.0 + erf(sign * zs * 0.70710678118654752440));
+        r = u > p ? (log(1.0 - p) - log(1.0 - u)) / beta : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < N; ++k) vn[k] = selp_real(r, vn[k], k == a ? 1 : 0);
+    }
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+      const double arg = fma(c[8], v[a], c[9] * vn[a]);
+      // (the addend keeps rsqrt finite when v = vn = 0 and is absorbed otherwise)
+      const double sq = arg > 0.0 ? fm::sqrt_pos(arg + 1e-300) : sqrt(arg);
+      x[a][H][0] = (((x[a][H][0] + c[5]) + c[6] * v[a]) + c[7] * vn[a]) + sq * (sign * z[a][1]);
+      x[a][H][1] = vn[a];
+    }
+  }
+};
+
+// Models that step all the paths of a thread at once define kBatchStep = true.
+template <class M, class = void>
+struct HasBatchStep {
+  static constexpr bool value = false;
+};
+template <class M>
+struct HasBatchStep<M, decltype(void(M::kBatchStep))> {
+  static constexpr bool value = M::kBatchStep;
 };
 
 // ------------------------------------------------------- normal streams ---
@@ -494,22 +610,6 @@ __device__ __forceinline__ void sobol_normals(const Tab& tab, const uint32_t (&x
   sobol_normals<K>(tab, xb, z, clamp);
 }
 
-// v[comp] for a register-resident state vector.  Written with opaque `selp`s:
-// a plain `j == comp ? v[j] : r` chain is turned into an indexed load by the
-// compiler, which moves the whole state array to local memory (an LDL/STL pair
-// per path and step in the hot loop).
-__device__ __forceinline__ double selp_real(double a, double b, int take_a) {
-  double r;
-  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}"
-      : "=d"(r) : "d"(a), "d"(b), "r"(take_a));
-  return r;
-}
-__device__ __forceinline__ float selp_real(float a, float b, int take_a) {
-  float r;
-  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}"
-      : "=f"(r) : "f"(a), "f"(b), "r"(take_a));
-  return r;
-}
 template <typename Real, int DIM>
 __device__ __forceinline__ Real select_component(const Real (&v)[DIM], int comp) {
   Real r = v[0];
@@ -605,13 +705,18 @@ struct PathsPerThread {
       (RNGK == RNGK_SOBOL) ? (Model::NF >= TQF_SOBOL_DRAWS ? 1 : TQF_SOBOL_DRAWS / Model::NF) : 4;
 };
 
-template <class Model, int RNGK, bool ANTI, int MODE>
+// PPT_: paths (antithetic pairs) carried by one thread.  The default suits runs that
+// fill the machine; the Philox kernels also exist with PPT_ = 1 for small runs
+// (config C1: 50 000 pairs), where four times as many CTAs -- ten warps per SM
+// instead of less than three -- hide the latency of the dependent Philox /
+// Box-Muller chain that a handful of warps per SM cannot.
+template <class Model, int RNGK, bool ANTI, int MODE, int PPT_ = PathsPerThread<Model, RNGK>::value>
 __global__ void __launch_bounds__(kBlock, TQF_MIN_BLOCKS)
 path_kernel(const KParams<typename Model::Real> P) {
   using Real = typename Model::Real;
   constexpr int DIM = Model::DIM, NF = Model::NF, NCOEF = Model::NCOEF;
   constexpr int NPATH = ANTI ? 2 : 1;
-  constexpr int PPT = PathsPerThread<Model, RNGK>::value;
+  constexpr int PPT = PPT_;
   constexpr bool kPrice = MODE != MODE_PATHS;
   constexpr bool kExtrema = MODE == MODE_PRICE_EXTREMA;
 
@@ -803,14 +908,19 @@ path_kernel(const KParams<typename Model::Real> P) {
       const int rec_next = rec_tab[s + 1];
       Real cc[NCOEF];
       load_step_coef<Real, NCOEF>(coef_tab + static_cast<size_t>(s) * NCOEF, cc);
+      if constexpr (HasBatchStep<Model>::value) {
+        Model::template step_batch<PPT, NPATH, 0>(x, z, cc, Real(1));
+        if (ANTI) Model::template step_batch<PPT, NPATH, NPATH - 1>(x, z, cc, Real(-1));
+      } else {
 #pragma unroll
-      for (int a = 0; a < PPT; ++a) {
-        Model::step(x[a][0], z[a], cc);
-        if (ANTI) {
-          Real zm[NF];
+        for (int a = 0; a < PPT; ++a) {
+          Model::step(x[a][0], z[a], cc);
+          if (ANTI) {
+            Real zm[NF];
 #pragma unroll
-          for (int j = 0; j < NF; ++j) zm[j] = -z[a][j];
-          Model::step(x[a][NPATH - 1], zm, cc);
+            for (int j = 0; j < NF; ++j) zm[j] = -z[a][j];
+            Model::step(x[a][NPATH - 1], zm, cc);
+          }
         }
       }
       if (kPrice) {
@@ -1010,9 +1120,12 @@ size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool table
   return off;
 }
 
-// CTAs of `kernel` (kBlock threads, `smem` dynamic bytes) that are resident at the
-// same time on the current device; 0 when the query fails.  tqf_paths.cu.
-int resident_grid(const void* kernel, size_t smem);
+// A run whose chunks, grouped `ppt` per CTA, leave most of the machine empty (fewer
+// CTAs than three per SM; max_grid = 32 per SM): such runs take the one-path-per-
+// thread Philox kernels.
+inline bool small_run(uint64_t num_chunks, int ppt, int max_grid) {
+  return (num_chunks + ppt - 1) / ppt < static_cast<uint64_t>(max_grid / 32 * 3);
+}
 
 // Launches the right instantiation for (rng kind, antithetic, mode).
 template <class Model>
@@ -1020,10 +1133,10 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
                        const KParams<typename Model::Real>& P, cudaStream_t stream,
                        int* grid_out) {
   (void)smem_unused;
-#define TQF_LAUNCH(RK, AN, MD)                                                         \
+#define TQF_LAUNCH_PPT(RK, AN, MD, PPTV)                                               \
   do {                                                                                 \
-    auto kern = path_kernel<Model, RK, AN, MD>;                                        \
-    constexpr int ppt = PathsPerThread<Model, RK>::value;                              \
+    auto kern = path_kernel<Model, RK, AN, MD, PPTV>;                                  \
+    constexpr int ppt = PPTV;                                                          \
     const size_t smem = path_kernel_smem<typename Model::Real>(                        \
         Model::NCOEF, P.num_steps, RK, MD, P.tables_in_smem != 0, ppt,                 \
         P.colsum_partials ? P.colsum_cols : 0);                                        \
@@ -1037,7 +1150,6 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
     /* in lock step, measured 8% slower on C2), and the last partial wave is      */   \
     /* short.  Each CTA walks its chunks with a grid stride: the per-CTA partial  */   \
     /* sums and their fixed-order reduction stay reproducible.                    */   \
-    (void)&resident_grid;                                                              \
     const int cap = max_grid;                                                          \
     int grid = static_cast<int>(num_super < static_cast<uint64_t>(cap)                 \
                                     ? num_super : static_cast<uint64_t>(cap));         \
@@ -1046,6 +1158,13 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
     kern<<<grid, kBlock, smem, stream>>>(P);                                           \
     TQF_CUDA_OK(cudaGetLastError());                                                   \
     return TQF_OK;                                                                     \
+  } while (0)
+#define TQF_LAUNCH(RK, AN, MD)                                                         \
+  do {                                                                                 \
+    constexpr int dflt = PathsPerThread<Model, RK>::value;                             \
+    if (RK == RNGK_PHILOX && dflt > 1 && small_run(P.num_chunks, dflt, max_grid))      \
+      TQF_LAUNCH_PPT(RK, AN, MD, 1);                                                   \
+    TQF_LAUNCH_PPT(RK, AN, MD, dflt);                                                  \
   } while (0)
   if (mode == MODE_PRICE) {
     if (rngk == RNGK_PHILOX && anti) TQF_LAUNCH(RNGK_PHILOX, true, MODE_PRICE);
@@ -1064,6 +1183,7 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
     if (rngk == RNGK_DRAWS) TQF_LAUNCH(RNGK_DRAWS, false, MODE_PATHS);
   }
 #undef TQF_LAUNCH
+#undef TQF_LAUNCH_PPT
   set_error("unsupported rng / mode combination");
   return TQF_ERR_UNSUPPORTED;
 }

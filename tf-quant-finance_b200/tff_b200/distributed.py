@@ -69,12 +69,14 @@ def price_sums(plan, payoffs):
   """`plan.price_sums(payoffs)` -- sharded over the ranks and globally reduced
   inside a `sharded()` context, the whole run on this GPU otherwise."""
   if _SHARDED is None or world()[1] == 1:
+    plan.clear_peer_exchange()
     return plan.price_sums(list(payoffs))
   px = _SHARDED[0]
   lo, count = shard_units(plan.units)
   if px is not None and px.world > 1:
     plan.set_peer_exchange(px)
     return plan.price_sums(list(payoffs), lo, count)
+  plan.clear_peer_exchange()
   return all_reduce_(plan.price_sums(list(payoffs), lo, count))
 
 

@@ -437,10 +437,13 @@ class RngSpec:
 class Plan:
   """Device-resident tables of one (model, grid, rng) configuration."""
 
-  def __init__(self, spec, all_times, num_steps, x0, rng, num_samples, dtype, x0_paths=None):
+  def __init__(self, spec, all_times, num_steps, x0, rng, num_samples, dtype, x0_paths=None,
+               table=None):
     """`x0_paths`: optional per-path initial states `[num_samples, dim]`
-    (anything convertible to a tensor); `x0` is then only a placeholder."""
+    (anything convertible to a tensor); `x0` is then only a placeholder.
+    `table`: the precomputed `spec.coef_table(all_times, dtype)[:num_steps]`."""
     self.spec, self.rng = spec, rng
+    self.cached = False
     self.dtype = np.dtype(dtype)
     self.num_samples = int(num_samples)
     self.num_steps = int(num_steps)
@@ -451,8 +454,9 @@ class Plan:
                        'PSEUDO_ANTITHETIC random type')
     self.units = self.num_samples // 2 if rng.antithetic else self.num_samples
 
-    table = np.ascontiguousarray(
-        spec.coef_table(all_times, self.dtype)[:self.num_steps], dtype=np.float64)
+    if table is None:
+      table = spec.coef_table(all_times, self.dtype)[:self.num_steps]
+    table = np.ascontiguousarray(table, dtype=np.float64)
     x0 = np.ascontiguousarray(np.asarray(x0, dtype=self.dtype).reshape(-1),
                               dtype=np.float64)
     if x0.shape[0] != spec.dim:
@@ -507,6 +511,11 @@ class Plan:
     _lib.check(_lib.lib().tqf_plan_create(C.byref(m), C.byref(r),
                                           self.num_samples, C.byref(handle)))
     self._handle = handle
+
+  def release(self):
+    """`close()` unless the plan lives in the plan cache (`cached_plan`)."""
+    if not self.cached:
+      self.close()
 
   def close(self):
     if getattr(self, '_handle', None):
@@ -567,6 +576,14 @@ class Plan:
         self._handle, peer_exchange.rank, peer_exchange.world, peer_exchange.ptrs,
         peer_exchange.epoch))
 
+  def clear_peer_exchange(self):
+    """Back to single-GPU pricing (a cached plan may have been used sharded before)."""
+    px = getattr(self, '_peer_exchange', None)
+    if px is not None:
+      own = (C.c_void_p * 1)(px.ptrs[px.rank])
+      _lib.check(_lib.lib().tqf_plan_set_peer_exchange(self._handle, 0, 1, own, 0))
+      self._peer_exchange = None
+
   def price_sums(self, payoffs, unit_offset=0, unit_count=None):
     """Unnormalised per-payoff sums as a device tensor [num_payoffs, 4]:
     (sum, sum of squares, number of non-finite payoffs, 0)."""
@@ -590,6 +607,50 @@ class Plan:
       _lib.check(_lib.lib().tqf_plan_peer_epoch(self._handle, C.byref(ep)))
       px.epoch = int(ep.value)
     return sums
+
+
+# ------------------------------------------------------------ plan cache ----
+# Repeated pricing calls with identical inputs (a calibration loop re-pricing on the
+# same grid, a benchmark) re-use the device-resident tables instead of allocating,
+# uploading and freeing them per call: plans are keyed by the CONTENT of everything
+# that goes to the device ("copied by the library into its own device
+# cache keyed by content hash").  Least recently used plans are destroyed.
+_PLAN_CACHE = {}
+_PLAN_CACHE_SIZE = 8
+
+
+def cached_plan(spec, all_times, num_steps, x0, rng, num_samples, dtype):
+  """A `Plan` for these inputs from the cache, built on a miss.  Callers use
+  `plan.release()` instead of `close()`.  Plans that reference caller-owned device
+  memory (per-path initial states, `normal_draws=`) are never cached."""
+  dtype = np.dtype(dtype)
+  if rng.type == _lib.RNG_DRAWS:
+    return Plan(spec, all_times, num_steps, x0, rng, num_samples, dtype)
+  all_times = np.asarray(all_times, dtype=dtype)
+  table = np.ascontiguousarray(spec.coef_table(all_times, dtype)[:int(num_steps)], dtype=np.float64)
+  x0 = np.ascontiguousarray(np.asarray(x0, dtype=dtype).reshape(-1), dtype=np.float64)
+  extra = getattr(spec, 'device_arrays', None)
+  extra_bytes = b''.join(a.tobytes() for a in extra(dtype)) if extra is not None else b''
+  rkey = (tuple(rng.key), tuple(rng.counter)) if rng.type == _lib.RNG_PHILOX else ()
+  key = (torch.cuda.current_device() if torch.cuda.is_available() else -1,
+         spec.kind, spec.dim, spec.num_factors, int(num_steps), all_times.shape[0] - 1, dtype.str,
+         int(num_samples), rng.type, rng.antithetic, rkey, rng.skip, rng.unit_stride,
+         rng.unit_offset, int(getattr(spec, 'exact_log', False)), table.tobytes(), x0.tobytes(),
+         extra_bytes)
+  plan = _PLAN_CACHE.pop(key, None)
+  if plan is None or getattr(plan, '_handle', None) is None:
+    plan = Plan(spec, all_times, num_steps, x0, rng, num_samples, dtype, table=table)
+    plan.cached = True
+  _PLAN_CACHE[key] = plan                 # most recently used last
+  while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+    old = _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    old.close()
+  return plan
+
+
+def clear_plan_cache():
+  while _PLAN_CACHE:
+    _PLAN_CACHE.popitem()[1].close()
 
 
 def measure_fma_peaks():

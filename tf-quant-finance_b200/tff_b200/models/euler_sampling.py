@@ -25,7 +25,7 @@ class InvalidArgumentError(ValueError):
 
 def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
              num_samples, initial_state, random_type, seed, skip, times_grid,
-             normal_draws, watch_params, validate_args, tolerance, dtype):
+             normal_draws, watch_params, validate_args, tolerance, dtype, use_cache=False):
   """Argument normalisation of `sample` (`euler_sampling.py:232-310`)."""
   if watch_params is not None:
     raise NotImplementedError(
@@ -133,8 +133,11 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
     rng = engine.RngSpec(random_type, seed, skip, normal_draws, unit_stride=stride,
                          unit_offset=offset)
     x0_plan = spec_b.extend_initial_state(x0[0]) if hasattr(spec_b, 'extend_initial_state') else x0[0]
-    plans.append(engine.Plan(spec_b, all_times, num_steps, x0_plan, rng, num_samples, dtype,
-                             x0_paths=x0_paths))
+    if use_cache and x0_paths is None:
+      plans.append(engine.cached_plan(spec_b, all_times, num_steps, x0_plan, rng, num_samples, dtype))
+    else:
+      plans.append(engine.Plan(spec_b, all_times, num_steps, x0_plan, rng, num_samples, dtype,
+                               x0_paths=x0_paths))
   return plans, record_slot, times.shape[0], batch_shape
 
 
@@ -204,16 +207,16 @@ def price(dim, drift_fn, volatility_fn, times, payoffs, time_step=None,
   plans, _, _, batch_shape = _prepare(
       dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
       num_samples, initial_state, random_type, seed, skip, times_grid,
-      normal_draws, None, validate_args, tolerance, dtype)
+      normal_draws, None, validate_args, tolerance, dtype, use_cache=True)
   if batch_shape:
     for plan in plans:
-      plan.close()
+      plan.release()
     raise NotImplementedError('batched processes are not supported by `price` yet')
   plan = plans[0]
   try:
     sums = distributed.price_sums(plan, payoffs).cpu().numpy()
   finally:
-    plan.close()
+    plan.release()
   n = float(plan.num_samples)
   mean = sums[:, 0] / n
   if not return_stats:

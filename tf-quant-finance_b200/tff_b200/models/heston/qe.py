@@ -70,7 +70,7 @@ class HestonQeSpec(engine.ModelSpec):
 
 
 def _plan(model, times, initial_state, num_samples, random_type, seed, time_step, skip,
-          tolerance, num_time_steps, times_grid, normal_draws):
+          tolerance, num_time_steps, times_grid, normal_draws, use_cache=False):
   """(plan, record_slot, k) of one QE sampling call (`heston_model.py:177-340`)."""
   dt_ = model.dtype()
   times = _tensor.to_numpy(times, dt_).reshape(-1)
@@ -101,8 +101,8 @@ def _plan(model, times, initial_state, num_samples, random_type, seed, time_step
   num_steps, record_slot = engine.record_plan(mask, times.shape[0])
   spec = HestonQeSpec(*params, tolerance)
   rng = engine.RngSpec(random_type, seed, skip, normal_draws)
-  plan = engine.Plan(spec, all_times, num_steps, x0.reshape(-1), rng,
-                     int(num_samples), dt_)
+  make = engine.cached_plan if use_cache else engine.Plan
+  plan = make(spec, all_times, num_steps, x0.reshape(-1), rng, int(num_samples), dt_)
   return plan, record_slot, times.shape[0]
 
 
@@ -127,11 +127,12 @@ def price(model, times, payoffs, initial_state, num_samples=1, random_type=None,
   monitored on every grid point), no path stored.  Engine extension -- the
   reference would take `mean(payoff(sample_paths(...)))`."""
   plan, _, _ = _plan(model, times, initial_state, num_samples, random_type, seed,
-                     time_step, skip, tolerance, num_time_steps, times_grid, normal_draws)
+                     time_step, skip, tolerance, num_time_steps, times_grid, normal_draws,
+                     use_cache=True)
   try:
     sums = distributed.price_sums(plan, payoffs).cpu().numpy()
   finally:
-    plan.close()
+    plan.release()
   n = float(plan.num_samples)
   mean = sums[:, 0] / n
   if not return_stats:
