@@ -229,7 +229,17 @@ typedef struct tqf_payoff_desc {
    * I = the path integral of the short rate carried by TQF_MODEL_HW1F.     */
   int32_t num_payments;
   int32_t is_payer;
-  int32_t reserved2;
+  /* Barrier payoffs (TQF_PAYOFF_*_OUT_*): 1 = continuous monitoring by the
+   * Brownian-bridge correction of black_scholes/brownian_bridge.py:118-196
+   * (`brownian_bridge_single`): the payoff is multiplied by
+   *   prod_steps [1 - exp(-2 (x_s - b)(x_e - b) / var_step)]
+   * over the steps whose two ends lie on the inner side of the barrier b (0 as soon
+   * as a grid point is beyond it), var_step = the variance of the monitored
+   * component's increment given the state at the start of the step.  State
+   * component 0 of TQF_MODEL_AFFINE_1F / LINEAR_1F / HESTON_EULER; with
+   * TQF_TRANSFORM_EXP the barrier refers to exp(state) and the bridge runs on the
+   * state (log-price) itself.                                               */
+  int32_t brownian_bridge;
   double reserved3;
   double reserved4;
   double pay_g[TQF_MAX_SWAPTION_PAYMENTS];     /* G(tau_j)=(1-e^{-k tau})/k */

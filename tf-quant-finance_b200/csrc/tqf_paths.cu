@@ -279,7 +279,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
         sw.k[j] = d.pay_k[j];
         sw.coef[j] = d.pay_coef[j];
       }
-      P.pay[q] = PayoffK{d.kind, 0, 0, step, 0.0, 0.0, d.scale};
+      P.pay[q] = PayoffK{d.kind, 0, 0, step, 0.0, 0.0, d.scale, 0, 0};
       continue;
     }
     if (plan->model.kind == TQF_MODEL_MVGBM) {
@@ -296,14 +296,32 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     TQF_REQUIRE(!is_tangent || (plan->model.kind != TQF_MODEL_MVGBM && d.tangent_component >= 0 &&
                                 d.tangent_component < plan->info.dim),
                 "tangent_component out of range");
+    const bool is_barrier = d.kind >= TQF_PAYOFF_UP_OUT_CALL && d.kind <= TQF_PAYOFF_DOWN_OUT_CALL;
+    const int bridge = is_barrier && d.brownian_bridge ? 1 : 0;
     P.pay[q] = PayoffK{d.kind, d.component, d.transform, step, d.strike, d.barrier, d.scale,
-                       is_tangent ? d.tangent_component : 0};
-    if (d.kind >= TQF_PAYOFF_UP_OUT_CALL && d.kind <= TQF_PAYOFF_DOWN_OUT_CALL) {
+                       is_tangent ? d.tangent_component : 0, bridge};
+    if (is_barrier) {
       TQF_REQUIRE(monitor < 0 || monitor == d.component,
                   "all barrier payoffs of one call must watch the same state component");
       monitor = d.component;
       const bool up = d.kind == TQF_PAYOFF_UP_OUT_CALL || d.kind == TQF_PAYOFF_UP_OUT_PUT;
       P.need_extrema |= up ? 1 : 2;
+      if (bridge) {
+        TQF_REQUIRE(d.component == 0, "the Brownian-bridge correction monitors state component 0");
+        TQF_REQUIRE(plan->model.kind == TQF_MODEL_AFFINE_1F || plan->model.kind == TQF_MODEL_LINEAR_1F ||
+                        plan->model.kind == TQF_MODEL_HESTON_EULER,
+                    "the Brownian-bridge correction is implemented for the 1-d affine / additive "
+                    "models and the Heston Euler scheme (state component 0)");
+        TQF_REQUIRE(d.barrier > 0.0 || d.transform != TQF_TRANSFORM_EXP,
+                    "a barrier on exp(state) must be positive");
+        // the bridge lives in state space: a barrier on exp(X) is log(barrier) on X
+        const double level = d.transform == TQF_TRANSFORM_EXP ? std::log(d.barrier) : d.barrier;
+        double* slot = up ? &P.bridge_up : &P.bridge_dn;
+        TQF_REQUIRE(!(P.bridge & (up ? 1 : 2)) || *slot == level,
+                    "all bridged barrier payoffs of one direction must share one barrier level");
+        *slot = level;
+        P.bridge |= up ? 1 : 2;
+      }
     }
   }
   P.monitor = monitor < 0 ? 0 : monitor;
@@ -364,8 +382,8 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     smem = path_kernel_smem<Real>(plan->info.ncoef, P.num_steps, rk, MODE_PRICE, false);
   }
   P.tables_in_smem = in_smem ? 1 : 0;
-  int rc = dispatch<Real>(plan, P.need_extrema ? MODE_PRICE_EXTREMA : MODE_PRICE, plan->max_grid, smem,
-                          P, stream, &grid);
+  const int mode = P.bridge ? MODE_PRICE_BRIDGE : (P.need_extrema ? MODE_PRICE_EXTREMA : MODE_PRICE);
+  int rc = dispatch<Real>(plan, mode, plan->max_grid, smem, P, stream, &grid);
   if (rc != TQF_OK) return rc;
   reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev,
                                                   next_peer_exchange(plan));

@@ -34,7 +34,8 @@ constexpr int kMaxPPT = 8;      // most paths carried by one thread
 // MODE_PRICE_EXTREMA: MODE_PRICE that also tracks the running extrema of the monitored
 // component (barrier payoffs); a mode of its own so that the plain pricing kernels carry
 // neither the registers nor the per-step test.
-enum { MODE_PRICE = 0, MODE_PATHS = 1, MODE_PRICE_EXTREMA = 2 };
+// MODE_PRICE_BRIDGE: MODE_PRICE_EXTREMA plus the Brownian-bridge no-touch products.
+enum { MODE_PRICE = 0, MODE_PATHS = 1, MODE_PRICE_EXTREMA = 2, MODE_PRICE_BRIDGE = 3 };
 enum { RNGK_PHILOX = 0, RNGK_SOBOL = 1, RNGK_DRAWS = 2 };
 
 struct PayoffK {
@@ -46,6 +47,7 @@ struct PayoffK {
   double barrier;
   double scale;
   int32_t tangent;   // TQF_PAYOFF_*_TANGENT: state component of the tangent
+  int32_t bridge;    // barrier payoffs: multiply by the bridge no-touch probability
 };
 
 // Device-side table of one Hull-White swaption payoff (TQF_PAYOFF_HW_SWAPTION):
@@ -89,6 +91,11 @@ struct KParams {
   int num_payoffs;
   int need_extrema;          // bit 0: running max, bit 1: running min of `monitor`
   int monitor;               // state component the barrier payoffs watch
+  // Brownian-bridge correction of the barrier payoffs (continuous monitoring,
+  // black_scholes/brownian_bridge.py:118-196): bit 0 = an upper, bit 1 = a lower
+  // barrier at bridge_up / bridge_dn (state space, component 0)
+  int bridge;
+  double bridge_up, bridge_dn;
   PayoffK pay[TQF_MAX_PAYOFFS];
   double* partials;          // device [gridDim.x][TQF_MAX_PAYOFFS][4]
   const SwaptionK* swaptions; // device [num_payoffs] (HW swaption payoffs only)
@@ -134,6 +141,10 @@ struct AffineModel1F {  // a = a0 + a1 x, S = b0 + b1 x
     const Real dt_inc = c[0] * (c[2] + c[3] * x[0]);
     const Real dw_inc = (c[4] + c[5] * x[0]) * dw;
     x[0] = (x[0] + dt_inc) + dw_inc;
+  }
+  __device__ static __forceinline__ Real bridge_var(const Real (&x)[DIM], const Real (&c)[NCOEF]) {
+    const Real vol = c[4] + c[5] * x[0];
+    return vol * vol * c[0];
   }
 };
 
@@ -229,6 +240,9 @@ struct LinearModel1F {  // x' = A x + B + C z  (HW exact OU step, vector_hull_wh
                                               const Real (&c)[NCOEF]) {
     x[0] = (c[2] * x[0] + c[3]) + c[4] * z[0];
   }
+  __device__ static __forceinline__ Real bridge_var(const Real (&)[DIM], const Real (&c)[NCOEF]) {
+    return c[4] * c[4];
+  }
 };
 
 template <typename R>
@@ -262,6 +276,10 @@ struct HestonEulerModel {  // heston/heston_model.py:143-173; state [X = log S, 
     const Real vol = sqrt_abs(var);
     x[0] = fma(vol, z[0] * c[0], fma(c[1], var, x[0]));
     x[1] = fma(vol, fma(c[5], z[1], c[4] * z[0]), fma(c[2], c[3] - var, var));
+  }
+  // log-spot increment: sqrt|V| sqrt_dt z0
+  __device__ static __forceinline__ Real bridge_var(const Real (&x)[DIM], const Real (&c)[NCOEF]) {
+    return (x[1] < Real(0) ? -x[1] : x[1]) * (c[0] * c[0]);
   }
   __device__ static __forceinline__ double sqrt_abs(double v) {
     // |V| == 0 would make rsqrt infinite: nudge it (the addend is absorbed otherwise).
@@ -391,6 +409,19 @@ struct HestonQeModel {
       x[a][H][1] = vn[a];
     }
   }
+};
+
+// Variance of the increment of state component 0 over one step, given the state
+// BEFORE the step: the `variance` argument of brownian_bridge_single
+// (black_scholes/brownian_bridge.py:118-196).  Models that define bridge_var can
+// price continuously monitored barriers (TQF payoff flag `brownian_bridge`).
+template <class M, class = void>
+struct HasBridgeVar {
+  static constexpr bool value = false;
+};
+template <class M>
+struct HasBridgeVar<M, decltype(void(&M::bridge_var))> {
+  static constexpr bool value = true;
 };
 
 // Models that step all the paths of a thread at once define kBatchStep = true.
@@ -620,7 +651,8 @@ __device__ __forceinline__ Real select_component(const Real (&v)[DIM], int comp)
 
 // ------------------------------------------------------------ payoffs -----
 __device__ __forceinline__ double eval_payoff(const PayoffK& d, double x_final, double x_max,
-                                              double x_min, double tangent = 0.0) {
+                                              double x_min, double tangent = 0.0,
+                                              double surv_up = 1.0, double surv_dn = 1.0) {
   double f = x_final, fmax = x_max, fmin = x_min;
   if (d.transform == TQF_TRANSFORM_EXP) {
     f = exp(f);
@@ -648,17 +680,23 @@ __device__ __forceinline__ double eval_payoff(const PayoffK& d, double x_final, 
     case TQF_PAYOFF_PUT:
       v = d.strike - f > 0.0 ? d.strike - f : 0.0;
       break;
+    // (with the bridge flag the payoff is weighted by the probability that the
+    // continuous path between the grid points did not touch the barrier either)
     case TQF_PAYOFF_UP_OUT_CALL:
       v = (f - d.strike > 0.0 && !(fmax > d.barrier)) ? f - d.strike : 0.0;
+      if (d.bridge) v *= surv_up;
       break;
     case TQF_PAYOFF_UP_OUT_PUT:
       v = (d.strike - f > 0.0 && !(fmax > d.barrier)) ? d.strike - f : 0.0;
+      if (d.bridge) v *= surv_up;
       break;
     case TQF_PAYOFF_DOWN_OUT_PUT:
       v = (d.strike - f > 0.0 && !(fmin < d.barrier)) ? d.strike - f : 0.0;
+      if (d.bridge) v *= surv_dn;
       break;
     case TQF_PAYOFF_DOWN_OUT_CALL:
       v = (f - d.strike > 0.0 && !(fmin < d.barrier)) ? f - d.strike : 0.0;
+      if (d.bridge) v *= surv_dn;
       break;
     default:  // TQF_PAYOFF_IDENTITY
       v = f;
@@ -718,7 +756,8 @@ path_kernel(const KParams<typename Model::Real> P) {
   constexpr int NPATH = ANTI ? 2 : 1;
   constexpr int PPT = PPT_;
   constexpr bool kPrice = MODE != MODE_PATHS;
-  constexpr bool kExtrema = MODE == MODE_PRICE_EXTREMA;
+  constexpr bool kExtrema = MODE == MODE_PRICE_EXTREMA || MODE == MODE_PRICE_BRIDGE;
+  constexpr bool kBridge = MODE == MODE_PRICE_BRIDGE;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: log table (double Sobol only) | coef [S][NCOEF] Real | record_slot
@@ -800,6 +839,15 @@ path_kernel(const KParams<typename Model::Real> P) {
     }
 
     Real x[PPT][NPATH][DIM], xmax[PPT][NPATH], xmin[PPT][NPATH];
+    // bridge no-touch probabilities of the upper / lower barrier (MODE_PRICE_EXTREMA)
+    double surv_up[PPT][NPATH], surv_dn[PPT][NPATH];
+#pragma unroll
+    for (int a = 0; a < PPT; ++a)
+#pragma unroll
+      for (int h = 0; h < NPATH; ++h) {
+        surv_up[a][h] = 1.0;
+        surv_dn[a][h] = 1.0;
+      }
 #pragma unroll
     for (int a = 0; a < PPT; ++a)
 #pragma unroll
@@ -878,7 +926,8 @@ path_kernel(const KParams<typename Model::Real> P) {
                 const double tg = (d.kind == TQF_PAYOFF_CALL_TANGENT || d.kind == TQF_PAYOFF_PUT_TANGENT)
                                       ? static_cast<double>(select_component<Real, DIM>(x[a][h], d.tangent))
                                       : 0.0;
-                v = eval_payoff(d, xf, xa, xi, tg);
+                v = eval_payoff(d, xf, xa, xi, tg, kBridge ? surv_up[a][h] : 1.0,
+                                kBridge ? surv_dn[a][h] : 1.0);
               }
               if (isfinite(v)) {
                 sum += v;
@@ -908,6 +957,18 @@ path_kernel(const KParams<typename Model::Real> P) {
       const int rec_next = rec_tab[s + 1];
       Real cc[NCOEF];
       load_step_coef<Real, NCOEF>(coef_tab + static_cast<size_t>(s) * NCOEF, cc);
+      Real xpre[PPT][NPATH], bvar[PPT][NPATH];
+      if constexpr (HasBridgeVar<Model>::value && kBridge) {
+        {
+#pragma unroll
+          for (int a = 0; a < PPT; ++a)
+#pragma unroll
+            for (int h = 0; h < NPATH; ++h) {
+              xpre[a][h] = x[a][h][0];
+              bvar[a][h] = Model::bridge_var(x[a][h], cc);
+            }
+        }
+      }
       if constexpr (HasBatchStep<Model>::value) {
         Model::template step_batch<PPT, NPATH, 0>(x, z, cc, Real(1));
         if (ANTI) Model::template step_batch<PPT, NPATH, NPATH - 1>(x, z, cc, Real(-1));
@@ -921,6 +982,32 @@ path_kernel(const KParams<typename Model::Real> P) {
             for (int j = 0; j < NF; ++j) zm[j] = -z[a][j];
             Model::step(x[a][NPATH - 1], zm, cc);
           }
+        }
+      }
+      if constexpr (HasBridgeVar<Model>::value && kBridge) {
+        {
+          // brownian_bridge_single: P(no touch) = 1 - exp(-2 (x_s - b)(x_e - b) / var) when
+          // both ends are on the inner side of the barrier, 0 otherwise
+#pragma unroll
+          for (int a = 0; a < PPT; ++a)
+#pragma unroll
+            for (int h = 0; h < NPATH; ++h) {
+              const double xs = static_cast<double>(xpre[a][h]);
+              const double xe = static_cast<double>(x[a][h][0]);
+              const double var = static_cast<double>(bvar[a][h]);
+              if (P.bridge & 1) {
+                const double ds = P.bridge_up - xs, de = P.bridge_up - xe;
+                const double p = (ds > 0.0 && de > 0.0)
+                                     ? (var > 0.0 ? 1.0 - exp(-2.0 * (ds * de) / var) : 1.0) : 0.0;
+                surv_up[a][h] *= p;
+              }
+              if (P.bridge & 2) {
+                const double ds = xs - P.bridge_dn, de = xe - P.bridge_dn;
+                const double p = (ds > 0.0 && de > 0.0)
+                                     ? (var > 0.0 ? 1.0 - exp(-2.0 * (ds * de) / var) : 1.0) : 0.0;
+                surv_dn[a][h] *= p;
+              }
+            }
         }
       }
       if (kPrice) {
@@ -1162,8 +1249,9 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
 #define TQF_LAUNCH(RK, AN, MD)                                                         \
   do {                                                                                 \
     constexpr int dflt = PathsPerThread<Model, RK>::value;                             \
-    if (RK == RNGK_PHILOX && dflt > 1 && small_run(P.num_chunks, dflt, max_grid))      \
-      TQF_LAUNCH_PPT(RK, AN, MD, 1);                                                   \
+    if constexpr (RK == RNGK_PHILOX && dflt > 1) {                                     \
+      if (small_run(P.num_chunks, dflt, max_grid)) TQF_LAUNCH_PPT(RK, AN, MD, 1);      \
+    }                                                                                  \
     TQF_LAUNCH_PPT(RK, AN, MD, dflt);                                                  \
   } while (0)
   if (mode == MODE_PRICE) {
@@ -1176,6 +1264,13 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
     if (rngk == RNGK_PHILOX) TQF_LAUNCH(RNGK_PHILOX, false, MODE_PRICE_EXTREMA);
     if (rngk == RNGK_SOBOL) TQF_LAUNCH(RNGK_SOBOL, false, MODE_PRICE_EXTREMA);
     if (rngk == RNGK_DRAWS) TQF_LAUNCH(RNGK_DRAWS, false, MODE_PRICE_EXTREMA);
+  } else if (mode == MODE_PRICE_BRIDGE) {
+    if constexpr (HasBridgeVar<Model>::value) {
+      if (rngk == RNGK_PHILOX && anti) TQF_LAUNCH(RNGK_PHILOX, true, MODE_PRICE_BRIDGE);
+      if (rngk == RNGK_PHILOX) TQF_LAUNCH(RNGK_PHILOX, false, MODE_PRICE_BRIDGE);
+      if (rngk == RNGK_SOBOL) TQF_LAUNCH(RNGK_SOBOL, false, MODE_PRICE_BRIDGE);
+      if (rngk == RNGK_DRAWS) TQF_LAUNCH(RNGK_DRAWS, false, MODE_PRICE_BRIDGE);
+    }
   } else {
     if (rngk == RNGK_PHILOX && anti) TQF_LAUNCH(RNGK_PHILOX, true, MODE_PATHS);
     if (rngk == RNGK_PHILOX) TQF_LAUNCH(RNGK_PHILOX, false, MODE_PATHS);

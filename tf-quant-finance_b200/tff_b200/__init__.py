@@ -11,7 +11,8 @@ Heston / Hull-White model classes, `swaption_price` and Longstaff-Schwartz.
 All device work runs in libtqf.so (hand-written CUDA for sm_100a); there is no
 CPU fallback.
 """
+from tff_b200 import black_scholes
 from tff_b200 import math
 from tff_b200 import models
 
-__all__ = ['math', 'models']
+__all__ = ['black_scholes', 'math', 'models']

@@ -89,7 +89,7 @@ class PayoffDesc(C.Structure):
       ('expiry_step', C.c_int32),
       ('num_payments', C.c_int32),
       ('is_payer', C.c_int32),
-      ('reserved2', C.c_int32),
+      ('brownian_bridge', C.c_int32),
       ('reserved3', C.c_double),
       ('reserved4', C.c_double),
       ('pay_g', C.c_double * MAX_SWAPTION_PAYMENTS),

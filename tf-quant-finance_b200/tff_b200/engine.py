@@ -47,16 +47,38 @@ class ModelSpec:
 
 
 class AffineSpec1F(ModelSpec):
-  """dX = (a0(t) + a1(t) X) dt + (b0(t) + b1(t) X) dW."""
-  kind, dim, num_factors, num_coef = _lib.MODEL_AFFINE_1F, 1, 1, 6
+  """dX = (a0(t) + a1(t) X) dt + (b0(t) + b1(t) X) dW.
+
+  When both state coefficients are the constant 0 (additive noise: the log-space
+  GBM of the Monte-Carlo notebook, configs C1 / C5) the Euler step
+  `(x + dt a0) + b0 (z sqrt_dt)` does not read the state in its increments; it then
+  runs as `x' = (x + B) + C z` with the per-step constants `B = dt a0`,
+  `C = b0 sqrt_dt` formed once on the host (TQF_MODEL_LINEAR_1F: 2 fused
+  multiply-adds per path-step instead of 7 FP64 instructions; the result differs
+  from the reference grouping by one rounding of `b0 sqrt_dt z`)."""
+  dim, num_factors = 1, 1
 
   def __init__(self, a0, a1, b, b1=0.0):
     self.a0, self.a1, self.b, self.b1 = a0, a1, b, b1
+    self.additive = all(
+        not callable(p) and np.ndim(p) == 0 and float(p) == 0.0 for p in (a1, b1))
+    self.kind = _lib.MODEL_LINEAR_1F if self.additive else _lib.MODEL_AFFINE_1F
+    self.num_coef = 5 if self.additive else 6
 
-  def coef_table(self, all_times, dtype):
+  def general_table(self, all_times, dtype):
+    """The six columns dt, sqrt_dt, a0, a1, b0, b1 of TQF_MODEL_AFFINE_1F."""
     t, dt, sq = self._dt_columns(all_times, dtype)
     cols = [dt, sq, _eval_param(self.a0, t, dtype), _eval_param(self.a1, t, dtype),
             _eval_param(self.b, t, dtype), _eval_param(self.b1, t, dtype)]
+    return np.stack(cols, -1).astype(np.float64)
+
+  def coef_table(self, all_times, dtype):
+    if not self.additive:
+      return self.general_table(all_times, dtype)
+    t, dt, sq = self._dt_columns(all_times, dtype)
+    a0 = _eval_param(self.a0, t, dtype)
+    b0 = _eval_param(self.b, t, dtype)
+    cols = [dt, sq, np.ones_like(dt), (dt * a0).astype(dtype), (b0 * sq).astype(dtype)]
     return np.stack(cols, -1).astype(np.float64)
 
 
@@ -93,7 +115,8 @@ class MilsteinSpec1F(ModelSpec):
   kind, dim, num_factors, num_coef = _lib.MODEL_MILSTEIN_1F, 1, 1, 6
 
   def __init__(self, euler_spec):
-    if euler_spec.dim != 1 or euler_spec.kind not in (_lib.MODEL_AFFINE_1F, _lib.MODEL_GBM_1F):
+    if euler_spec.dim != 1 or not (isinstance(euler_spec, AffineSpec1F) or euler_spec.kind in (
+        _lib.MODEL_AFFINE_1F, _lib.MODEL_GBM_1F)):
       raise NotImplementedError(
           'The B200 Milstein kernel covers 1-d processes with affine drift and '
           'volatility (affine_closures, gbm_closures, GeometricBrownianMotion, or '
@@ -101,7 +124,10 @@ class MilsteinSpec1F(ModelSpec):
     self.euler_spec = euler_spec
 
   def coef_table(self, all_times, dtype):
-    tab = self.euler_spec.coef_table(all_times, dtype)
+    if isinstance(self.euler_spec, AffineSpec1F):
+      tab = self.euler_spec.general_table(all_times, dtype)
+    else:
+      tab = self.euler_spec.coef_table(all_times, dtype)
     if self.euler_spec.kind == _lib.MODEL_GBM_1F:      # dt, sqrt_dt, mu, sigma
       zero = np.zeros_like(tab[:, 0])
       tab = np.stack([tab[:, 0], tab[:, 1], zero, tab[:, 2], zero, tab[:, 3]], -1)
@@ -312,15 +338,22 @@ class Payoff:
   of the reference's callers, e.g. `hull_white/swaption.py:310-311`)."""
 
   def __init__(self, kind, strike=0.0, barrier=0.0, component=0, log_state=False,
-               scale=1.0, tangent=0):
+               scale=1.0, tangent=0, brownian_bridge=False):
+    """`brownian_bridge` (barrier payoffs): continuous monitoring -- the payoff is
+    weighted by the probability that the Brownian bridge between consecutive grid
+    points did not touch the barrier (`tff.black_scholes.brownian_bridge_single`,
+    `black_scholes/brownian_bridge.py:118-196`), accumulated step by step in the
+    fused kernel."""
     self.kind, self.strike, self.barrier = kind, float(strike), float(barrier)
     self.component, self.log_state, self.scale = int(component), bool(log_state), float(scale)
     self.tangent = int(tangent)
+    self.brownian_bridge = bool(brownian_bridge)
 
   def desc(self):
     d = _lib.PayoffDesc()
     d.kind, d.component = self.kind, self.component
     d.tangent_component = self.tangent
+    d.brownian_bridge = int(self.brownian_bridge)
     d.transform = _lib.TRANSFORM_EXP if self.log_state else _lib.TRANSFORM_NONE
     d.strike, d.barrier, d.scale = self.strike, self.barrier, self.scale
     return d
