@@ -309,6 +309,37 @@ int tqf_plan_paths_sums(tqf_plan* plan, uint64_t path_offset, uint64_t path_coun
                         int transform, int num_slots, double* column_sums_dev,
                         void* stream);
 
+/* Hull-White discount curves along simulated short-rate paths: replaces the
+ * device work of `sample_discount_curve_paths` / `_bond_reconstitution`
+ * (models/hull_white/vector_hull_white.py:451-592, 783-814),
+ *   out[n][i][j][d] = coef_a[i][j][d] exp(-(rates[n, j, d] - f0[j][d]) coef_g[i][j][d]),
+ * with the path-independent factors folded into the tables by the caller:
+ *   coef_g = (1 - e^{-a_d tau_i}) / a_d,
+ *   coef_a = P0_d(t_j + tau_i) / P0_d(t_j) exp(-y_d(t_j) coef_g^2 / 2).
+ *   rates_dev: model dtype, element (n, j, d) at n*rs_path + j*rs_time + d*rs_dim
+ *     (strides in elements; the time-major view of tqf_plan_paths has rs_path = 1);
+ *   f0_dev [k][dim], coef_a_dev / coef_g_dev [m][k][dim]: DEVICE doubles;
+ *   out_dev: model dtype [num_paths][m][k][dim], contiguous.                 */
+int tqf_hw_discount_curves(const void* rates_dev, int64_t rs_path, int64_t rs_time,
+                           int64_t rs_dim, const double* f0_dev, const double* coef_a_dev,
+                           const double* coef_g_dev, uint64_t num_paths, int m, int k, int dim,
+                           int dtype, void* out_dev, void* stream);
+
+/* Exercise values of Bermudan swaptions on Hull-White paths: replaces the bond
+ * gather / weighted sum / scatter of hull_white/swaption.py:608-724
+ * (`_map_payoff_to_sim_times`):
+ *   values[u][n][b] = relu(1 - sum_j coef[b][e][j] exp(k[b][e][j] - g[b][e][j] x[n][u])),
+ *   u = ex_slot[b][e] (slot of the e-th exercise date of swaption b among the unique
+ *   exercise dates); x = r - f(0, t) at those dates, element (n, u) at
+ *   n*xs_path + u*xs_slot; g / k / coef: DEVICE doubles [B][E][m] (coef carries the
+ *   +1 of the float leg on its last entry); values_dev: model dtype [U][N][B],
+ *   zero-filled by the caller (dates without exercise stay 0).               */
+int tqf_hw_exercise_values(const void* x_dev, int64_t xs_path, int64_t xs_slot,
+                           const double* g_dev, const double* k_dev, const double* coef_dev,
+                           const int32_t* ex_slot_dev, uint64_t num_paths, int num_swaptions,
+                           int num_exercise, int num_payments, int dtype, void* values_dev,
+                           void* stream);
+
 /* ------------------------------------------------------------------------
  * Longstaff-Schwartz regression passes on materialised paths: replaces the
  * device work of models/longstaff_schwartz/lsm.py:231-436 (payoff_fn, basis_fn,

@@ -393,6 +393,23 @@ class VectorHullWhiteModel:
     return np.transpose(np.stack(slots, 0), [1, 0, 2])
 
 
+def vector_sample_discount_curve_paths(model, times, curve_times, num_samples, random_type=None,
+                                       seed=None, skip=0):
+  """`VectorHullWhiteModel.sample_discount_curve_paths` (`vector_hull_white.py:451-592`):
+  (P(t, t + tau) [N, m, k, dim], short rates [N, k, dim]); factor d uses its own
+  curve, mean reversion and y_d(t) in `_bond_reconstitution` (783-814)."""
+  times = np.asarray(times, dtype=model.dtype)
+  curve_times = np.asarray(curve_times, dtype=model.dtype)
+  rates = model.sample_paths(times, num_samples, random_type, seed, skip)      # [N, k, dim]
+  t = times[None, None, :]
+  tau = curve_times[None, :, None]
+  out = []
+  for d, f in enumerate(model.factors):
+    y_t = f.compute_yt(times)
+    out.append(f.bond_reconstitution(t, t + tau, rates[:, None, :, d], y_t[None, None, :]))
+  return np.stack(out, axis=-1), rates
+
+
 def _unique_in_order(a):
   """`tf.unique`: distinct values in order of first appearance + inverse index."""
   _, first, inv = np.unique(a, return_index=True, return_inverse=True)

@@ -348,6 +348,41 @@ def test_vector_hw_paths_match_oracle(rng, corr_kind):
   np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize('corr_kind', ['none', 'piecewise'])
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_vector_hw_discount_curve_paths_match_oracle(corr_kind, dtype):
+  # vector_hull_white.py:451-592, 783-814: [N, m, k, dim] bond prices from the kernel
+  import tff_b200 as tff
+  model, omodel = _vector_models(_curve2, corr_kind, dtype)
+  times, curve_times = [0.1, 0.5, 1.0, 2.5], [0.25, 0.5, 1.0]
+  n = 1531                      # not a multiple of the 32-path tile
+  p, r = model.sample_discount_curve_paths(
+      times, curve_times, num_samples=n, random_type=tff.math.random.RandomType.STATELESS,
+      seed=[5, 6])
+  op, orr = ohw.vector_sample_discount_curve_paths(
+      omodel, times, curve_times, n, odraws.RandomType.STATELESS, seed=[5, 6])
+  assert tuple(p.shape) == op.shape == (n, 3, 4, 2) and tuple(r.shape) == (n, 4, 2)
+  tol = 1e-12 if dtype == np.float64 else 1e-5
+  np.testing.assert_allclose(_np(r), orr, rtol=tol, atol=tol * 1e-2)
+  np.testing.assert_allclose(_np(p), op, rtol=tol)
+
+
+def test_hw_discount_curve_paths_many_times_and_strided_rates():
+  # 1-factor: 40 simulation times x 5 maturities (several 32-column tiles)
+  import tff_b200 as tff
+  dtype = np.float64
+  model = tff.models.HullWhiteModel1F(0.03, 0.02, _curve, dtype=dtype)
+  omodel = ohw.HullWhiteModel1F(0.03, 0.02, _curve, dtype)
+  times = np.linspace(0.05, 2.0, 40)
+  curve_times = [0.25, 0.5, 1.0, 2.0, 5.0]
+  p, r = model.sample_discount_curve_paths(
+      times, curve_times, num_samples=333, random_type=tff.math.random.RandomType.SOBOL, skip=7)
+  op, orr = omodel.sample_discount_curve_paths(times, curve_times, 333, odraws.RandomType.SOBOL,
+                                               skip=7)
+  assert tuple(p.shape) == op.shape == (333, 5, 40, 1)
+  np.testing.assert_allclose(_np(p), op, rtol=1e-12)
+
+
 def test_vector_hw_reference_moments_kat():
   # hull_white_test.py:223-270: mean / variance (1e-4) and correlation (1e-2)
   # at t = 1 with 50k STATELESS_ANTITHETIC paths, seed [1, 2]

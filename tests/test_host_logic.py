@@ -288,3 +288,45 @@ def test_probed_affine_spec_accepts_affine_callables():
   assert tab.shape == (4, spec.num_coef)
   np.testing.assert_allclose(tab[:, 2:4], np.stack([0.1 * np.linspace(0.25, 1, 4), np.ones(4)], -1))
   np.testing.assert_allclose(tab[0, 4:8], [0.0, 0.5, -0.3, 0.0], atol=1e-12)
+
+
+# Closed-form Hull-White valuations (host): the reference's analytic known answers
+def _flat_rate(t):
+  import torch
+  return 0.01 + 0 * t if isinstance(t, torch.Tensor) else 0.01 * np.ones_like(np.asarray(t, dtype=np.float64))
+
+
+def test_analytic_swaption_reference_kats():
+  # hull_white/swaption_test.py:85-125 (0.71632434), :160-205 (time-dependent volatility,
+  # 0.5593057004094042), :127-158 (receiver, 0.813482544626056).  The reference's values
+  # come out of a Brent search stopped at its default root tolerance of 2e-7
+  # (math/root_search/brent.py), and the price moves by ~30 per unit of break-even rate:
+  # they are good to ~1e-6, which is the tolerance here (the root below is solved to 1e-14).
+  import tff_b200 as tff
+  from tff_b200.math import piecewise
+  kw = dict(expiries=np.array(1.0), floating_leg_start_times=np.array([1.0, 1.25, 1.5, 1.75]),
+            floating_leg_end_times=np.array([1.25, 1.5, 1.75, 2.0]),
+            fixed_leg_payment_times=np.array([1.25, 1.5, 1.75, 2.0]),
+            floating_leg_daycount_fractions=0.25 * np.ones(4),
+            fixed_leg_daycount_fractions=0.25 * np.ones(4), fixed_leg_coupon=0.011 * np.ones(4),
+            reference_rate_fn=_flat_rate, notional=100., mean_reversion=0.03, dtype=np.float64)
+  price = tff.models.hull_white.swaption_price(volatility=0.02, **kw)
+  assert price.shape == () and price.dtype == np.float64
+  np.testing.assert_allclose(price, 0.71632434, rtol=0, atol=2e-6)
+  price = tff.models.hull_white.swaption_price(volatility=0.02, is_payer_swaption=False, **kw)
+  np.testing.assert_allclose(price, 0.813482544626056, rtol=0, atol=2e-6)
+  vol = piecewise.PiecewiseConstantFunc([0.5], [0.01, 0.02], dtype=np.float64)
+  price = tff.models.hull_white.swaption_price(volatility=vol, **kw)
+  np.testing.assert_allclose(price, 0.5593057004094042, rtol=0, atol=2e-6)
+
+
+def test_analytic_bond_option_reference_kat():
+  # hull_white/zero_coupon_bond_option_test.py:49-73
+  import tff_b200 as tff
+  expiries, maturities = np.array(1.0), np.array(5.0)
+  strikes = np.exp(-0.01 * maturities) / np.exp(-0.01 * expiries)
+  price = tff.models.hull_white.bond_option_price(
+      strikes=strikes, expiries=expiries, maturities=maturities, mean_reversion=0.03,
+      volatility=0.02, discount_rate_fn=_flat_rate, dtype=np.float64)
+  assert price.shape == ()
+  np.testing.assert_allclose(price, 0.02817777, rtol=1e-8, atol=1e-8)

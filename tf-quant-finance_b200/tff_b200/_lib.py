@@ -179,6 +179,12 @@ _SIGNATURES = {
         (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_double,
                    C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'tqf_lsm_status': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    'tqf_hw_exercise_values':
+        (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'tqf_hw_discount_curves':
+        (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'tqf_plan_paths_sums':
         (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                    C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

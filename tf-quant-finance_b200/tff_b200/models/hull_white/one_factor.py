@@ -43,6 +43,47 @@ def _input_type(param, dtype, name):
   return piecewise.PiecewiseConstantFunc([], value, dtype=dtype), False, True
 
 
+def discount_curves_on_device(rates, times, curve_times, mean_reversions, y_t, rate_fns, fwd_fns,
+                              dtype):
+  """P(t_j, t_j + tau_i) `[N, m, k, dim]` along the short-rate paths `rates`
+  (`[N, k, dim]` device tensor, any strides): the path-independent factors of
+  `_bond_reconstitution` (`vector_hull_white.py:783-814`) are tabulated on the host
+  per factor d,
+    G[i, j, d] = (1 - e^{-a_d tau_i}) / a_d,
+    A[i, j, d] = P0_d(t_j + tau_i) / P0_d(t_j) exp(-y_d(t_j) G^2 / 2),
+  and `tqf_hw_discount_curves` writes A exp(-(r - f0) G) in one pass."""
+  import ctypes as C  # pylint: disable=g-import-not-at-top
+  k, m, dim = times.shape[0], curve_times.shape[0], len(mean_reversions)
+  t = times[None, :]
+  big_t = t + curve_times[:, None]                                       # [m, k]
+  a_tab = np.empty((m, k, dim), dtype=np.float64)
+  g_tab = np.empty((m, k, dim), dtype=np.float64)
+  f0 = np.empty((k, dim), dtype=np.float64)
+  for d in range(dim):
+    kap = dtype.type(mean_reversions[d])
+    g = ((1. - np.exp(-kap * (big_t - t))) / kap).astype(dtype)
+    p0t = np.exp(-rate_fns[d](times) * times).astype(dtype)
+    p0T = np.exp(-rate_fns[d](big_t) * big_t).astype(dtype)
+    y = np.asarray(y_t[d], dtype=dtype)[None, :]
+    # the reference multiplies p_0_t_tau by exp(-term1 - 0.5 term2); exp(a + b) is
+    # split here into exp(a) exp(b): one rounding apart
+    a_tab[:, :, d] = (p0T / p0t[None, :]) * np.exp(-0.5 * (y * g**2))
+    g_tab[:, :, d] = g
+    f0[:, d] = np.asarray(fwd_fns[d](times), dtype=dtype)
+  dev = rates.device
+  f0_d = torch.as_tensor(f0, device=dev)
+  a_d = torch.as_tensor(np.ascontiguousarray(a_tab), device=dev)
+  g_d = torch.as_tensor(np.ascontiguousarray(g_tab), device=dev)
+  n = int(rates.shape[0])
+  out = torch.empty((n, m, k, dim), dtype=rates.dtype, device=dev)
+  _lib.require_cuda()
+  sp, st, sd = rates.stride()
+  _lib.check(_lib.lib().tqf_hw_discount_curves(
+      rates.data_ptr(), sp, st, sd, f0_d.data_ptr(), a_d.data_ptr(), g_d.data_ptr(), n, m, k,
+      dim, _tensor.tqf_dtype(dtype), out.data_ptr(), _tensor.current_stream_ptr()))
+  return out
+
+
 class HullWhite1FSpec(engine.ModelSpec):
   """Per-step table of TQF_MODEL_HW1F: A, B, C, W, W f(0, t_{i+1}); state [x, I]."""
   kind, dim, num_factors, num_coef = _lib.MODEL_HW1F, 2, 1, 5
@@ -221,13 +262,11 @@ class HullWhiteModel1F(generic_ito_process.GenericItoProcess):
     curve_times = _tensor.to_numpy(curve_times, self._dtype)
     rates = self.sample_paths(times, num_samples, random_type, seed, skip,
                               time_step, times_grid, normal_draws, validate_args)
-    y_t = self._tables.y_t(times)
-    t = times[None, None, :]
-    tau = curve_times[None, :, None]
-    p = self._bond_reconstitution(np.broadcast_to(t, (1, curve_times.shape[0], times.shape[0])),
-                                  t + tau, rates[:, None, :, 0],
-                                  np.broadcast_to(y_t[None, None, :], (1, curve_times.shape[0], times.shape[0])))
-    return p[..., None], rates
+    rate = lambda t: _exact.discount_rate(self._initial_discount_rate_fn, t, self._dtype)
+    curves = discount_curves_on_device(
+        rates, times, curve_times, [self._tables.k], [self._tables.y_t(times)], [rate],
+        [self._fwd], self._dtype)
+    return curves, rates
 
   def discount_bond_price(self, short_rate, times, maturities, name=None):
     """P(t, T) given r(t) (`vector_hull_white.py:594-636`); numpy in, numpy out."""

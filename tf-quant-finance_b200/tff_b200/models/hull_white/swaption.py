@@ -161,9 +161,9 @@ def swaption_price(*,
                    _plan_only=False):
   """European swaption prices of shape `expiries.shape` (numpy float array).
 
-  Same arguments as the reference.  `use_analytic_pricing=True` (Jamshidian
-  decomposition, a closed form outside the Monte-Carlo hot path) is not
-  implemented by the B200 engine; pass `use_analytic_pricing=False`.
+  Same arguments as the reference.  `use_analytic_pricing=True` (the default, as in
+  the reference) evaluates the Jamshidian closed form on the host;
+  `use_analytic_pricing=False` runs the fused Monte-Carlo kernel.
   """
   del floating_leg_daycount_fractions, floating_leg_start_times
   del floating_leg_end_times, name
@@ -178,15 +178,19 @@ def swaption_price(*,
                          pay_t.ndim - 1, expiries.ndim))
   notional = np.asarray(1.0 if notional is None else _tensor.to_numpy(notional, dt_), dtype=dt_)
   is_payer = np.asarray(_tensor.to_numpy(is_payer_swaption), dtype=bool)
+  model = one_factor.HullWhiteModel1F(mean_reversion, volatility,
+                                      reference_rate_fn, dtype=dt_)
   if use_analytic_pricing:
-    raise NotImplementedError(
-        'Analytic (Jamshidian) swaption valuation is a closed form outside the '
-        'B200 Monte-Carlo hot path; call with use_analytic_pricing=False.')
+    # Jamshidian decomposition: a closed form evaluated on the host (swaption.py:726-814)
+    if model._tables is None:
+      raise ValueError('The paramerization of `mean_reversion` and/or `volatility` does not '
+                       'support analytic computation of bond option variance.')
+    from tff_b200.models.hull_white import _analytic  # pylint: disable=g-import-not-at-top
+    price = _analytic.swaption_price(model, expiries, pay_t, dcf, coupon, notional, is_payer)
+    return price.astype(dt_)
   if time_step is None:
     raise ValueError('`time_step` must be provided for simulation '
                      'based bond option valuation.')
-  model = one_factor.HullWhiteModel1F(mean_reversion, volatility,
-                                      reference_rate_fn, dtype=dt_)
   if model._tables is None:
     raise NotImplementedError(
         'swaption_price needs constant mean reversion and constant or '
@@ -346,19 +350,20 @@ def bermudan_swaption_price(*,
   g = (1. - np.exp(-kconst * (pay_flat - t_e))) / kconst
   y = model._tables.y_t(t_e.reshape(-1)).reshape(t_e.shape)
   kk = -(rate(pay_flat) * pay_flat) + rate(t_e) * t_e - 0.5 * y * g**2
-  gd = torch.as_tensor(g, device=dev, dtype=td)
-  kd = torch.as_tensor(kk, device=dev, dtype=td)
-  cd = torch.as_tensor(coef, device=dev, dtype=td)
   u_count = uniq.shape[0]
+  # exercise values of every (swaption, exercise date) on every path: one kernel
+  # (tqf_hw_exercise_values) instead of a gather / sum / scatter per pair
+  g_d = torch.as_tensor(np.ascontiguousarray(g, dtype=np.float64), device=dev)
+  k_d = torch.as_tensor(np.ascontiguousarray(kk, dtype=np.float64), device=dev)
+  c_d = torch.as_tensor(np.ascontiguousarray(coef, dtype=np.float64), device=dev)
+  slot_d = torch.as_tensor(np.ascontiguousarray(ex_index, dtype=np.int32), device=dev)
   values = torch.zeros((u_count, n, nb), device=dev, dtype=td)
-  for b in range(nb):
-    for e in range(n_ex):
-      u = int(ex_index[b, e])
-      bonds = torch.exp(kd[b, e][None, :] - gd[b, e][None, :] * x_u[:, u:u + 1])   # [N, m]
-      swap = 1.0 - (cd[b, e][None, :] * bonds).sum(dim=-1)
-      # duplicates of an exercise date overwrite, as the scatter in
-      # `_map_payoff_to_sim_times` does
-      values[u, :, b] = torch.relu(swap)
+  x_u = x_u.contiguous()                                      # [N, U]
+  _lib.require_cuda()
+  _lib.check(_lib.lib().tqf_hw_exercise_values(
+      x_u.data_ptr(), x_u.stride(0), x_u.stride(1), g_d.data_ptr(), k_d.data_ptr(),
+      c_d.data_ptr(), slot_d.data_ptr(), n, nb, n_ex, m, _tensor.tqf_dtype(dt_),
+      values.data_ptr(), _tensor.current_stream_ptr()))
   price = lsm.least_square_mc(
       short_rate, np.arange(u_count), payoff_utils.make_tabulated_payoff(values),
       basis_fn, discount_factors=df_u, dtype=dt_)

@@ -317,3 +317,29 @@ class VectorHullWhiteModel:
       plan.close()
     f0 = torch.as_tensor(self.instant_forward_rate(times), device=x.device, dtype=x.dtype)
     return x + f0[None, :, :]
+
+  def sample_discount_curve_paths(self, times, curve_times, num_samples=1, random_type=None,
+                                  seed=None, skip=0, time_step=None, times_grid=None,
+                                  normal_draws=None, validate_args=False, name=None):
+    """Simulated discount curves (`vector_hull_white.py:451-592`):
+    `(P(t, t + tau) [num_samples, m, k, dim], short rates [num_samples, k, dim])`,
+    factor d discounting on its own curve.  Needs piecewise-constant (or constant)
+    parameters, as the reference."""
+    if self._one_factor:
+      return self._one_factor.sample_discount_curve_paths(
+          times, curve_times, num_samples, random_type, seed, skip, time_step, times_grid,
+          normal_draws, validate_args, name)
+    del name
+    if not self._is_piecewise_constant or self._sample_with_generic:
+      raise ValueError('All paramaters `mean_reversion`, `volatility`, and '
+                       '`corr_matrix`must be piecewise constant functions.')
+    dt_ = self._dtype
+    times = _tensor.to_numpy(times, dt_)
+    curve_times = _tensor.to_numpy(curve_times, dt_)
+    rates = self.sample_paths(times, num_samples, random_type, seed, skip, time_step,
+                              times_grid, normal_draws, validate_args)
+    rate_fns = [(lambda t, f=f: _exact.discount_rate(f, t, dt_)) for f in self._rate_fns]
+    curves = one_factor.discount_curves_on_device(
+        rates, times, curve_times, [tab.k for tab in self._tables],
+        [tab.y_t(times) for tab in self._tables], rate_fns, self._fwd, dt_)
+    return curves, rates

@@ -62,9 +62,8 @@ def bond_option_price(*,
                       return_stats=False):
   """Zero-coupon bond option prices of shape `strikes.shape` (numpy array).
 
-  Same arguments as the reference.  The analytic branch is a closed form
-  outside the Monte-Carlo hot path and is not provided; pass
-  `use_analytic_pricing=False`.  Options whose expiry is negative are worth 0
+  Same arguments as the reference.  `use_analytic_pricing=True` (the default)
+  evaluates the closed form on the host; `False` runs the fused kernel.  Options whose expiry is negative are worth 0
   and are left out of the simulation grid.
   """
   del name
@@ -73,15 +72,19 @@ def bond_option_price(*,
   expiries = _tensor.to_numpy(expiries, dt_)
   maturities = _tensor.to_numpy(maturities, dt_)
   is_call = np.asarray(_tensor.to_numpy(is_call_options), dtype=bool)
+  model = one_factor.HullWhiteModel1F(mean_reversion, volatility,
+                                      discount_rate_fn, dtype=dt_)
   if use_analytic_pricing:
-    raise NotImplementedError(
-        'Analytic bond option valuation is a closed form outside the B200 '
-        'Monte-Carlo hot path; call with use_analytic_pricing=False.')
+    # Black formula on the forward bond price: a closed form evaluated on the host
+    # (zero_coupon_bond_option.py:210-304)
+    if model._tables is None:
+      raise ValueError('The paramerization of `mean_reversion` and/or `volatility` does not '
+                       'support analytic computation of bond option variance.')
+    from tff_b200.models.hull_white import _analytic  # pylint: disable=g-import-not-at-top
+    return _analytic.bond_option_price(model, strikes, expiries, maturities, is_call).astype(dt_)
   if time_step is None:
     raise ValueError('`time_step` must be provided for simulation '
                      'based bond option valuation.')
-  model = one_factor.HullWhiteModel1F(mean_reversion, volatility,
-                                      discount_rate_fn, dtype=dt_)
   if model._tables is None:
     raise NotImplementedError(
         'bond_option_price needs constant mean reversion and constant or '
