@@ -230,8 +230,12 @@ def test_bond_option_errors():
             dtype=np.float64)
   with pytest.raises(ValueError, match='time_step'):
     tff.models.hull_white.bond_option_price(use_analytic_pricing=False, **kw)
-  with pytest.raises(NotImplementedError):
-    tff.models.hull_white.bond_option_price(use_analytic_pricing=True, **kw)
+  # the default (analytic) valuation is a host-side closed form: MC at 1e-3 of it
+  analytic = tff.models.hull_white.bond_option_price(use_analytic_pricing=True, **kw)
+  mc = tff.models.hull_white.bond_option_price(
+      use_analytic_pricing=False, num_samples=400000, time_step=0.1, seed=[1, 2],
+      random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, **kw)
+  np.testing.assert_allclose(mc, analytic, rtol=0, atol=2e-4)
 
 
 # ----------------------------------------------------------------- caps/floors

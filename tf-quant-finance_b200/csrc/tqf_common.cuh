@@ -18,6 +18,8 @@ void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
 // Device-global {T, 1/c} table of the table logarithm (tqf_rng.cu).
 int device_logtab(const double** out);
+// Device-global cubic table of the float32 inverse normal CDF (tqf_ndtri_f32_tab.inc).
+int device_ndtri_f32_tab(const float** out);
 
 #define TQF_CUDA_OK(expr)                                        \
   do {                                                           \

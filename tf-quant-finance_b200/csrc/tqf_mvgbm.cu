@@ -35,6 +35,7 @@ struct MvParams {
   PhiloxCtr ctr;
   const uint32_t* sobol_v;
   const double* logtab;  // device-global log table (read through L1)
+  const float* ndtab;    // device-global cubic table of the float32 inverse CDF (mma kernel)
   const Real* lsplit;    // device: factor / mu / sigma in the split kernel's order (dim > 8)
   uint64_t first_index, path_offset, path_count, num_chunks, chunk_base;
   int mode, num_payoffs;
@@ -667,7 +668,7 @@ constexpr int kMmaTiles = 20;                                    // (mt, kt) wit
 constexpr int kMmaFragWords = kMmaTiles * 2 * 32 * 4;           // hi / lo fragments
 constexpr int kMmaTabWords = kMmaFragWords + 2 * kMvDim;        // + mu[64], sigma[64]
 #ifndef TQF_MMA_TILE_DIMS
-#define TQF_MMA_TILE_DIMS 512
+#define TQF_MMA_TILE_DIMS 256
 #endif
 constexpr int kMmaTileDims = TQF_MMA_TILE_DIMS;   // Sobol dimensions staged at once (8 steps of 64; 256: +0.8 % time)
 
@@ -726,10 +727,39 @@ static void build_mma(const double* chol, const double* mu, const double* sigma,
   }
 }
 
-// FULL: dim == 64 (no padding checks in the draw loop).
-template <bool FULL>
-__global__ void __launch_bounds__(kMmaWarps * 32, 4)
+// float32 inverse normal CDF by table (tools/fit_ndtri_f32_table.py):
+//   z = t f(a), a = 1 - t^2; the top 11 bits of a (8 exponent + 3 mantissa bits) select a
+//   cubic in r = a - centre: 14 instructions per draw against 27 for the logarithm +
+//   degree-10 polynomial, no tail branch; max relative error 2e-7 (mean 4e-8).
+// The table lives in shared memory as EIGHT interleaved copies, copy k in the 16-byte
+// bank group k: lane l reads copy l % 8, so the eight lanes that a 128-bit shared load
+// serves per cycle never collide, whatever rows they ask for (a single copy would
+// serialise ~2.7x on random rows and make the LSU the bottleneck).
+constexpr int kNdTabRows = 186, kNdTabBase = 831;
+constexpr int kNdTabSmemBytes = kNdTabRows * 8 * 16;
+template <int N>
+__device__ __forceinline__ void sobol_normals_f32_tab(const uint32_t (&xb)[N], float (&z)[N],
+                                                      uint32_t tab_lane) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const float t = fmaf(__uint2float_rn(xb[k]), 4.656612873077393e-10f, -1.0f);
+    const float a = fmaf(-t, t, 1.0f);
+    const uint32_t bits = __float_as_uint(a);
+    const uint32_t idx = max(bits >> 20, static_cast<uint32_t>(kNdTabBase));
+    const uint4 row = lds_u4(tab_lane + idx * 128u);          // tab_lane is pre-offset by -base
+    const float r = a - __uint_as_float((bits & 0xFFF00000u) | 0x00080000u);
+    const float q = fmaf(fmaf(fmaf(__uint_as_float(row.w), r, __uint_as_float(row.z)), r,
+                              __uint_as_float(row.y)), r, __uint_as_float(row.x));
+    z[k] = t * q;
+  }
+}
+
+// FULL: dim == 64 (no padding checks in the draw loop).  TAB: table-driven draws.
+// NS: steps whose accumulators are formed together (they share the A-fragment loads).
+template <bool FULL, bool TAB, int NS>
+__global__ void __launch_bounds__(kMmaWarps * 32, NS == 1 ? 4 : 3)
 mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
+  extern __shared__ __align__(16) unsigned char s_ndt[];   // TAB: [rows][8 copies][4 floats]
   // per staged dimension 8 words: hi ^ (warp bits) for the 4 warps, then the
   // direction words of index bits 0..3
   __shared__ uint4 s_sob[kMmaTileDims * 2];
@@ -741,6 +771,18 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
   for (int i = tid; i < kMmaFragWords / 4; i += blockDim.x)
     s_frag[i] = __ldg(reinterpret_cast<const uint4*>(tabp) + i);
   for (int i = tid; i < kMmaWarps * TQF_MAX_PAYOFFS * 3; i += blockDim.x) (&s_acc[0][0])[i] = 0.0;
+  if (TAB) {
+    uint4* dst = reinterpret_cast<uint4*>(s_ndt);
+    for (int i = tid; i < kNdTabRows * 8; i += blockDim.x) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(P.ndtab) + (i >> 3));
+      // row 0 = the draws with t = +-1 (float32 uniform rounded to 0 or 1): +-inf
+      // like the reference, or +-ndtri(1 - 2^-24) in the clamped mode
+      if ((i >> 3) == 0 && P.sobol_clamp) v.x = __float_as_uint(5.4199314f);
+      dst[i] = v;
+    }
+  }
+  const uint32_t tab_lane = static_cast<uint32_t>(__cvta_generic_to_shared(s_ndt)) + (lane & 7) * 16 -
+                            kNdTabBase * 128u;
   // rows of this thread in the C layout: 16 mt + g (h = 0), 16 mt + 8 + g (h = 1)
   float mu[8], x0[8];
 #pragma unroll
@@ -865,31 +907,55 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
       {
         const uint32_t high_bits =
             static_cast<uint32_t>((chunk_base + chunk * kMmaPaths) >> kMmaIdxBits);
-        for (int dd = tid; dd < (s1 - s0) * dim; dd += blockDim.x) {
-          const uint4* v4 = reinterpret_cast<const uint4*>(
-              P.sobol_v + (static_cast<size_t>(s0) * dim + dd) * 32);
-          uint4 w[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) w[q] = __ldg(v4 + q);
-          const uint32_t* wv = reinterpret_cast<const uint32_t*>(w);
+        // Eight lanes per dimension, one 16-byte quad of its 32 direction words each:
+        // consecutive lanes read consecutive 16 bytes (fully coalesced; one thread per
+        // dimension reading 128 bytes cost 8x the LSU wavefronts, a quarter of the
+        // kernel's LSU budget).  The XOR over the chunk's high index bits is combined
+        // with three shuffles.
+        const int q = tid & 7;
+        const int ndims = (s1 - s0) * dim;
+        for (int base = 0; base < ndims; base += blockDim.x / 8) {
+          const int dd = base + (tid >> 3);
+          const bool live_dd = dd < ndims;
+          uint4 w = make_uint4(0u, 0u, 0u, 0u);
+          if (live_dd)
+            w = __ldg(reinterpret_cast<const uint4*>(
+                          P.sobol_v + (static_cast<size_t>(s0) * dim + dd) * 32) + q);
+          const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
           uint32_t h = 0;
 #pragma unroll
-          for (int b = kMmaIdxBits; b < 32; ++b)
-            h ^= wv[b] & (0u - ((high_bits >> (b - kMmaIdxBits)) & 1u));
-          s_sob[2 * dd] = make_uint4(h, h ^ wv[4], h ^ wv[5], h ^ wv[4] ^ wv[5]);
-          s_sob[2 * dd + 1] = w[0];
+          for (int j = 0; j < 4; ++j) {
+            const int b = 4 * q + j;                 // index bit of this word
+            const uint32_t bit = b >= kMmaIdxBits ? (high_bits >> (b - kMmaIdxBits)) & 1u : 0u;
+            h ^= wv[j] & (0u - bit);
+          }
+          h ^= __shfl_xor_sync(0xFFFFFFFFu, h, 1);
+          h ^= __shfl_xor_sync(0xFFFFFFFFu, h, 2);
+          h ^= __shfl_xor_sync(0xFFFFFFFFu, h, 4);
+          if (live_dd && q == 1) s_sob[2 * dd] = make_uint4(h, h ^ w.x, h ^ w.y, h ^ w.x ^ w.y);
+          if (live_dd && q == 0) s_sob[2 * dd + 1] = w;
         }
       }
       __syncthreads();
-      for (int s = s0; s < s1; ++s) {
-        float acc[4][2][4];
+      // NS consecutive steps share every load of the factor's A fragments: sigma L z is
+      // state-independent, so the accumulators of step s + 1 can be formed next to those
+      // of step s before either update runs.  (The A fragments are 41% of the kernel's
+      // shared-memory wavefronts, and the LSU data pipe is what bounds it: ncu
+      // l1tex__data_pipe_lsu_wavefronts 91%.)
+      for (int s = s0; s < s1; s += NS) {
+        float acc[NS][4][2][4];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int u = 0; u < NS; ++u)
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt)
+          for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.0f;
-        const uint32_t soff = (s - s0) * dim * 32;
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[u][mt][nt][e] = 0.0f;
+        uint32_t soff[NS];
+#pragma unroll
+        for (int u = 0; u < NS; ++u)        // a step beyond the tile re-reads the last one (discarded)
+          soff[u] = (min(s + u, s1 - 1) - s0) * dim * 32;
         // (A rolled loop over k-tile pairs with the row tiles predicated -- 9 KB of
         // code instead of 21 KB -- measured 767 ms against 730 ms: the fetch stalls
         // it removes cost less than the scheduling freedom it takes away.)
@@ -898,73 +964,82 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
         for (int kt = 0; kt < 8; ++kt) {
           // this thread's entries of the B fragments of k-tile kt: dimensions
           // 8 kt + c (h = 0) and 8 kt + 4 + c (h = 1) of both n-tiles, drawn side by side
-          uint32_t xb[4];
-          bool live[2];
+          uint32_t bh[NS][2][2], bl[NS][2][2];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int j = 8 * kt + 4 * h;           // + c
-            live[h] = FULL || j + c < dim;
-            const uint32_t jo = (FULL || live[h]) ? j * 32 : 0;   // stay inside the staged tile
-            const uint4 v = lds_u4(sob_v + soff + jo);
-            uint32_t x = lds_u32(sob_h + soff + jo);
-            x ^= v.x & lowmask[0];
-            x ^= v.y & lowmask[1];
-            x ^= v.z & lowmask[2];
-            xb[2 * h] = x;
-            xb[2 * h + 1] = x ^ v.w;                 // index bit 3 = n-tile
-          }
-          float z[4];
-          sobol_normals_f32<4>(xb, z, P.sobol_clamp);
-          uint32_t bh[2][2], bl[2][2];
+          for (int u = 0; u < NS; ++u) {
+            uint32_t xb[4];
+            bool live[2];
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              const float zz = (FULL || live[h]) ? z[2 * h + nt] : 0.0f;
-              bh[nt][h] = tf32_rna(zz);
-              bl[nt][h] = __float_as_uint(zz - __uint_as_float(bh[nt][h]));
+            for (int h = 0; h < 2; ++h) {
+              const int j = 8 * kt + 4 * h;           // + c
+              live[h] = FULL || j + c < dim;
+              const uint32_t jo = (FULL || live[h]) ? j * 32 : 0;   // stay inside the staged tile
+              const uint4 v = lds_u4(sob_v + soff[u] + jo);
+              uint32_t x = lds_u32(sob_h + soff[u] + jo);
+              x ^= v.x & lowmask[0];
+              x ^= v.y & lowmask[1];
+              x ^= v.z & lowmask[2];
+              xb[2 * h] = x;
+              xb[2 * h + 1] = x ^ v.w;                 // index bit 3 = n-tile
             }
-          uint4 ah[4], al[4];
+            float z[4];
+            if (TAB)
+              sobol_normals_f32_tab<4>(xb, z, tab_lane);
+            else
+              sobol_normals_f32<4>(xb, z, P.sobol_clamp);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                const float zz = (FULL || live[h]) ? z[2 * h + nt] : 0.0f;
+                bh[u][nt][h] = tf32_rna(zz);
+                bl[u][nt][h] = __float_as_uint(zz - __uint_as_float(bh[u][nt][h]));
+              }
+          }
 #pragma unroll
           for (int mt = kt / 2; mt < 4; ++mt) {
-            ah[mt] = lds_u4(frag_addr + ((ti + mt - kt / 2) * 2 + 0) * 512);
-            al[mt] = lds_u4(frag_addr + ((ti + mt - kt / 2) * 2 + 1) * 512);
+            const uint4 ah = lds_u4(frag_addr + ((ti + mt - kt / 2) * 2 + 0) * 512);
+            const uint4 al = lds_u4(frag_addr + ((ti + mt - kt / 2) * 2 + 1) * 512);
+            // small terms first; the three products of one accumulator are spaced
+            // by the other accumulators
+#pragma unroll
+            for (int u = 0; u < NS; ++u)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[u][mt][nt], al, bh[u][nt][0], bh[u][nt][1]);
+#pragma unroll
+            for (int u = 0; u < NS; ++u)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[u][mt][nt], ah, bl[u][nt][0], bl[u][nt][1]);
+#pragma unroll
+            for (int u = 0; u < NS; ++u)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[u][mt][nt], ah, bh[u][nt][0], bh[u][nt][1]);
           }
-          // small terms first; the three products of one accumulator are spaced
-          // by the other accumulators
-#pragma unroll
-          for (int mt = kt / 2; mt < 4; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], al[mt], bh[nt][0], bh[nt][1]);
-#pragma unroll
-          for (int mt = kt / 2; mt < 4; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], ah[mt], bl[nt][0], bl[nt][1]);
-#pragma unroll
-          for (int mt = kt / 2; mt < 4; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
           ti += 4 - kt / 2;
         }
         // acc_i = sum_j sigma_i L_ij z_j.  Euler: x_i' = x_i + x_i (mu_i dt + sqrt_dt acc_i);
         // exact log-normal increment: x_i' = x_i + (mu_i dt + sqrt_dt acc_i), mu = means - vols^2 / 2.
         // (The relative increment is NOT merged into 1 + ...: rounding 1 + mu dt to
         // float32 is the same error for every path and step, a 1e-4 bias of the price.)
-        const float dt = P.coef[2 * s], sq = P.coef[2 * s + 1];
-        float c1[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) c1[r] = mu[r] * dt;
+        for (int u = 0; u < NS; ++u) {
+          if (s + u >= s1) break;
+          const float dt = P.coef[2 * (s + u)], sq = P.coef[2 * (s + u) + 1];
+          float c1[8];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+          for (int r = 0; r < 8; ++r) c1[r] = mu[r] * dt;
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt)
+          for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float f = fmaf(sq, acc[mt][nt][e], c1[mt * 2 + (e >> 1)]);
-              x[mt][nt][e] = P.exact_log ? x[mt][nt][e] + f : fmaf(x[mt][nt][e], f, x[mt][nt][e]);
-            }
-        const int flag = P.record_slot[s + 1];
-        if (flag >= 0) record(s + 1, flag);
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float f = fmaf(sq, acc[u][mt][nt][e], c1[mt * 2 + (e >> 1)]);
+                x[mt][nt][e] = P.exact_log ? x[mt][nt][e] + f : fmaf(x[mt][nt][e], f, x[mt][nt][e]);
+              }
+          const int flag = P.record_slot[s + u + 1];
+          if (flag >= 0) record(s + u + 1, flag);
+        }
       }
     }
   }
@@ -1053,10 +1128,34 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
     *grid_out = grid;
     if constexpr (sizeof(Real) == 4 && DMAX == kMvDim) {
       if (a.rngk == RNGK_SOBOL && mma_enabled()) {
-        if (a.dim == kMvDim)
-          mvgbm_mma_kernel<true><<<grid, kMmaWarps * 32, 0, stream>>>(P);
-        else
-          mvgbm_mma_kernel<false><<<grid, kMmaWarps * 32, 0, stream>>>(P);
+        static const bool tab = [] {
+          const char* e = std::getenv("TQF_MVGBM_NDTRI_TAB");
+          return !(e && e[0] == '0');
+        }();
+        // two steps per A-fragment load (NS = 2): fewer shared-memory wavefronts but 168
+        // registers -> 3 CTAs per SM; measured 676 ms against 646 ms for NS = 1 on C4, so
+        // it stays an experiment (TQF_MVGBM_STEP_PAIRS=1)
+        static const bool pair = [] {
+          const char* e = std::getenv("TQF_MVGBM_STEP_PAIRS");
+          return e && e[0] == '1';
+        }();
+        if (tab && a.ndtab != nullptr) {
+          P.ndtab = a.ndtab;
+          auto k_full = pair ? mvgbm_mma_kernel<true, true, 2> : mvgbm_mma_kernel<true, true, 1>;
+          auto k_part = mvgbm_mma_kernel<false, true, 1>;
+          TQF_CUDA_OK(cudaFuncSetAttribute(k_full, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kNdTabSmemBytes));
+          TQF_CUDA_OK(cudaFuncSetAttribute(k_part, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kNdTabSmemBytes));
+          if (a.dim == kMvDim)
+            k_full<<<grid, kMmaWarps * 32, kNdTabSmemBytes, stream>>>(P);
+          else
+            k_part<<<grid, kMmaWarps * 32, kNdTabSmemBytes, stream>>>(P);
+        } else if (a.dim == kMvDim) {
+          mvgbm_mma_kernel<true, false, 1><<<grid, kMmaWarps * 32, 0, stream>>>(P);
+        } else {
+          mvgbm_mma_kernel<false, false, 1><<<grid, kMmaWarps * 32, 0, stream>>>(P);
+        }
         TQF_CUDA_OK(cudaGetLastError());
         return TQF_OK;
       }

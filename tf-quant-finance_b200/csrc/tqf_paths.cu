@@ -110,6 +110,7 @@ struct tqf_plan {
   void* coef_dev;           // Real [num_steps][ncoef]
   uint32_t* sobol_dev;      // [S_total*nf][32]
   const double* logtab_dev; // shared per-device log table (not owned)
+  const float* ndtab_dev;   // shared per-device float32 ndtri table (not owned; MVGBM)
   void* lsplit_dev;         // MVGBM dim > 8: factor in the split kernel's order
   PeerHost peer;            // tqf_plan_set_peer_exchange (world <= 1: single GPU)
   int sobol_clamp;          // tqf_plan_set_sobol_clamp
@@ -357,6 +358,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.ctr = P.ctr;
     a.sobol_v = plan->sobol_dev;
     a.logtab = plan->logtab_dev;
+    a.ndtab = plan->ndtab_dev;
     a.lsplit_dev = plan->lsplit_dev;
     a.first_index = P.first_index;
     a.path_offset = path_offset;
@@ -456,6 +458,7 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.ctr = P.ctr;
     a.sobol_v = plan->sobol_dev;
     a.logtab = plan->logtab_dev;
+    a.ndtab = plan->ndtab_dev;
     a.lsplit_dev = plan->lsplit_dev;
     a.first_index = P.first_index;
     a.path_offset = path_offset;
@@ -574,6 +577,7 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
   if (rc == TQF_OK && rng->type == TQF_RNG_SOBOL)
     rc = upload_sobol_table(rng->direction_numbers, static_cast<int>(dims), &plan->sobol_dev, 0);
   if (rc == TQF_OK) rc = device_logtab(&plan->logtab_dev);
+  if (rc == TQF_OK && model->kind == TQF_MODEL_MVGBM) rc = device_ndtri_f32_tab(&plan->ndtab_dev);
   if (rc == TQF_OK && model->kind == TQF_MODEL_MVGBM && info.dim > 8)
     rc = mvgbm_upload_split(plan->chol, plan->mu, plan->sigma, info.dim, model->dtype,
                             &plan->lsplit_dev);

@@ -1295,6 +1295,7 @@ struct MvLaunch {
   PhiloxCtr ctr;
   const uint32_t* sobol_v;
   const double* logtab;
+  const float* ndtab;        // device_ndtri_f32_tab(): cubic table of the float32 inverse CDF
   const void* lsplit_dev;    // mvgbm_upload_split() table (dim > 8)
   uint64_t first_index, path_offset, path_count;
   int num_payoffs;

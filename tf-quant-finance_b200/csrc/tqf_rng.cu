@@ -8,6 +8,7 @@
 #include <mutex>
 #include <vector>
 
+#include <cmath>
 #include "tqf_common.cuh"
 
 namespace tqf {
@@ -45,6 +46,31 @@ int device_logtab(const double** out) {
     if (e != cudaSuccess) {
       cudaFree(d);
       return cuda_fail(e, "cudaMemcpy(log table)");
+    }
+    tables[dev] = d;
+  }
+  *out = tables[dev];
+  return TQF_OK;
+}
+
+static const float kNdtriF32TabHost[] = {
+#include "tqf_ndtri_f32_tab.inc"
+};
+
+int device_ndtri_f32_tab(const float** out) {
+  static std::mutex mu;
+  static const float* tables[64] = {nullptr};
+  int dev = 0;
+  TQF_CUDA_OK(cudaGetDevice(&dev));
+  TQF_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
+  std::lock_guard<std::mutex> lock(mu);
+  if (!tables[dev]) {
+    float* d = nullptr;
+    TQF_CUDA_OK(cudaMalloc(&d, sizeof(kNdtriF32TabHost)));
+    cudaError_t e = cudaMemcpy(d, kNdtriF32TabHost, sizeof(kNdtriF32TabHost), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(d);
+      return cuda_fail(e, "cudaMemcpy(ndtri table)");
     }
     tables[dev] = d;
   }
