@@ -8,12 +8,13 @@
 // payoff.  tqf_lsm.cu runs the same algorithm with one launch per date; here
 //   * one CTA per SM owns a fixed, contiguous set of path tiles for the whole
 //     induction; per date it streams the two path columns the date needs
-//     through a 6-stage shared-memory ring filled by TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx; a dedicated producer warp runs
-//     ahead of the 16 consumer warps, across date boundaries as well, because
-//     the columns are read-only), and reads / writes the merged state
-//     W = cashflow + values with 16-byte vector accesses tagged evict_last so
-//     that it stays in the 126 MB L2 between dates;
+//     and the merged state W = cashflow + values through a 6-stage
+//     shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier
+//     complete_tx; a producer warp runs ahead of the 11 consumer warps -- for
+//     the read-only columns across date boundaries as well, for W up to the
+//     date boundary, where it waits for the consumers' stores), and writes W
+//     back with 16-byte stores tagged evict_last so that it stays in the
+//     126 MB L2 between dates;
 //   * consecutive dates sweep the tiles in opposite directions: the column a
 //     date accumulates on is the column the next date updates with, and its
 //     most recently read tail is still in L2 when the sweep turns around;
@@ -43,8 +44,9 @@ constexpr int kPThreads = kPConsumers + 32;       // + one producer warp
 constexpr int kPVecPerThread = 2;                 // 16-byte vectors per thread and tile
 constexpr int kPTileVecs = kPConsumers * kPVecPerThread;   // 704 vectors = 11 KB per column
 constexpr int kPTileBytes = kPTileVecs * 16;
-constexpr int kPStages = 8;                       // 8 x 2 x 11 KB = 176 KB of columns in flight
-constexpr size_t kPSmemBytes = static_cast<size_t>(kPStages) * 2 * kPTileBytes + 1024;
+constexpr int kPStages = 6;                       // 6 x 3 x 11 KB = 198 KB of columns and W in flight
+constexpr int kPSlots = 3;                        // update column | accumulation column | W
+constexpr size_t kPSmemBytes = static_cast<size_t>(kPStages) * kPSlots * kPTileBytes + 1024;
 constexpr long long kPTimeoutCycles = 8000000000ll;   // ~4 s: a lost CTA must not hang the GPU
 
 template <typename Real>
@@ -182,6 +184,7 @@ __device__ __forceinline__ float p_exercise(float pv, float cont, float rw) {
 
 struct SweepState {
   uint32_t stage, phase;     // position in the shared-memory ring (continues across dates)
+  uint32_t wpar;             // per stage: parity of its W barrier (unused on the first date)
   bool failed;
 };
 template <typename Real, int KT>
@@ -200,6 +203,7 @@ template <typename Real, int KT, bool MID>
 __device__ __forceinline__ void p_sweep(const PersistArgs<Real>& A, const SweepParams<Real, KT>& sp,
                                         SweepState& st, double (&acc)[KT * (KT + 1) / 2 + KT],
                                         uint32_t ring, uint32_t fullb, uint32_t emptyb,
+                                        uint32_t fullwb, uint32_t passdone,
                                         uint32_t tile_lo, uint32_t tile_hi, int tid, int lane,
                                         uint64_t keep, bool first, bool last) {
   constexpr int VN = PVec<Real>::N;
@@ -211,22 +215,19 @@ __device__ __forceinline__ void p_sweep(const PersistArgs<Real>& A, const SweepP
   double vsum = 0.0, vcnt = 0.0;
   uint32_t tile = sp.descending ? tile_hi - 1 : tile_lo;
   const int step = sp.descending ? -1 : 1;
-  uint4 wreg[kPVecPerThread];
-  if ((MID || !first) && num_my > 0) {
-#pragma unroll
-    for (int u = 0; u < kPVecPerThread; ++u) {
-      const uint32_t v = tile * kPTileVecs + u * kPConsumers + tid;
-      if (v < A.num_vecs) wreg[u] = p_ld_keep(wv + v, keep);
-    }
-  }
   for (uint32_t i = 0; i < num_my; ++i, tile += step) {
     if (!p_mbar_wait(fullb + 8 * st.stage, st.phase)) st.failed = true;
-    const uint32_t src = ring + st.stage * (2 * kPTileBytes);
-    uint4 xu_raw[kPVecPerThread], xa_raw[kPVecPerThread];
+    if (MID || !first) {
+      if (!p_mbar_wait(fullwb + 8 * st.stage, (st.wpar >> st.stage) & 1u)) st.failed = true;
+      st.wpar ^= 1u << st.stage;
+    }
+    const uint32_t src = ring + st.stage * (kPSlots * kPTileBytes);
+    uint4 xu_raw[kPVecPerThread], xa_raw[kPVecPerThread], wreg[kPVecPerThread];
 #pragma unroll
     for (int u = 0; u < kPVecPerThread; ++u) {
       xu_raw[u] = p_lds(src + u * kPConsumers * 16);
       if (MID || !last) xa_raw[u] = p_lds(src + kPTileBytes + u * kPConsumers * 16);
+      if (MID || !first) wreg[u] = p_lds(src + 2 * kPTileBytes + u * kPConsumers * 16);
     }
     __syncwarp();
     if (lane == 0) p_mbar_arrive(emptyb + 8 * st.stage);     // the stage is free again
@@ -260,14 +261,6 @@ __device__ __forceinline__ void p_sweep(const PersistArgs<Real>& A, const SweepP
         }
       }
       if (v < A.num_vecs) p_st_keep(wv + v, PVec<Real>::pack(wn[u]), keep);
-    }
-    // W of the next tile, into the registers just consumed
-    if ((MID || !first) && i + 1 < num_my) {
-#pragma unroll
-      for (int u = 0; u < kPVecPerThread; ++u) {
-        const uint32_t v = (tile + step) * kPTileVecs + u * kPConsumers + tid;
-        if (v < A.num_vecs) wreg[u] = p_ld_keep(wv + v, keep);
-      }
     }
     // ---- normal equations of the next (earlier) date, branch-free: a path that does
     // not take part (out of the money) contributes c = 0, y = 0 and no count
@@ -322,6 +315,12 @@ __device__ __forceinline__ void p_sweep(const PersistArgs<Real>& A, const SweepP
     acc[0] = vsum;
     acc[1] = vcnt;
   }
+  // this warp's W stores of the date are complete: make them visible to the bulk
+  // copies (async proxy) that fetch W for the next date, then tell the W producer
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) p_mbar_arrive(passdone);
 }
 
 template <typename Real, int KT>
@@ -330,9 +329,13 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
   constexpr int NA = KT * (KT + 1) / 2 + KT;
   extern __shared__ __align__(128) unsigned char p_smem[];
   // layout: [stages][2 columns][16 KB] | full barriers | empty barriers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + static_cast<size_t>(kPStages) * 2 * kPTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + static_cast<size_t>(kPStages) * kPSlots * kPTileBytes);
   const uint32_t smem_base = p_smem_u32(p_smem);
+  // full0[s]: the two path columns of stage s have landed; fullw0[s]: its W tile has;
+  // empty0[s]: every consumer warp has copied the stage into registers; passdone: every
+  // consumer warp has stored (and fenced) its last W of the current date
   const uint32_t full0 = p_smem_u32(bars), empty0 = p_smem_u32(bars + kPStages);
+  const uint32_t fullw0 = p_smem_u32(bars + 2 * kPStages), passdone = p_smem_u32(bars + 3 * kPStages);
   __shared__ double s_red[kPConsumers / 32][32];
   __shared__ double s_beta[kLsmFastK];
   __shared__ int s_flag;
@@ -348,8 +351,10 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
   if (tid == 0) {
     for (int s = 0; s < kPStages; ++s) {
       p_mbar_init(full0 + 8 * s, 1);
+      p_mbar_init(fullw0 + 8 * s, 1);
       p_mbar_init(empty0 + 8 * s, kPConsumers / 32);
     }
+    p_mbar_init(passdone, kPConsumers / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -357,6 +362,8 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
   if (tid >= kPConsumers) {
     // ------------------------------------------------------------ producer
     if (tid == kPConsumers) {
+      // lane 0: the two path columns of every tile, free-running across dates (the
+      // columns are read-only), bounded only by the ring
       uint64_t pol_first, pol_normal;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
       asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_normal));
@@ -378,7 +385,7 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
           const uint32_t v0 = tile * kPTileVecs;
           const uint32_t nv = min(static_cast<uint32_t>(kPTileVecs), A.num_vecs - v0);
           const uint32_t bytes = nv * 16u;
-          const uint32_t dst = smem_base + s * (2 * kPTileBytes);
+          const uint32_t dst = smem_base + s * (kPSlots * kPTileBytes);
           p_mbar_expect_tx(full0 + 8 * s, last ? bytes : 2 * bytes);
           // the update column is read for the last time: evict_first; the column that
           // is accumulated on comes back as the update column of the next date
@@ -388,6 +395,36 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
             p_bulk_load(dst + kPTileBytes,
                         reinterpret_cast<const unsigned char*>(cola) + static_cast<size_t>(v0) * 16,
                         bytes, full0 + 8 * s, pol_normal);
+        }
+      }
+    } else if (tid == kPConsumers + 1) {
+      // lane 1: the W tiles (none on the first date, whose W is the terminal payoff).  W
+      // of date j + 1 is what the consumers stored on date j -- and the sweep turns
+      // around, so the first tiles wanted are the last ones written: this lane waits at
+      // every date boundary until all consumer warps have stored and fenced
+      // (`passdone`); within a date the tiles are distinct and it runs ahead like lane 0.
+      uint64_t pol_keep;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      if (A.tune & 1) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+      uint32_t it = num_my;                     // ring position of the first tile of date 1
+      for (int j = 1; j < T; ++j) {
+        if (!p_mbar_wait(passdone, static_cast<uint32_t>(j - 1) & 1u, 200)) {
+          atomicExch(A.ctrl + 2, 5ull);
+          return;
+        }
+        for (uint32_t i = 0; i < num_my; ++i, ++it) {
+          const uint32_t tile = ((j & 1) && !(A.tune & 4)) ? tile_hi - 1 - i : tile_lo + i;
+          const uint32_t s = it % kPStages, ph = (it / kPStages) & 1u;
+          if (!p_mbar_wait(empty0 + 8 * s, ph ^ 1u, 200)) {
+            atomicExch(A.ctrl + 2, 2ull);
+            return;
+          }
+          const uint32_t v0 = tile * kPTileVecs;
+          const uint32_t nv = min(static_cast<uint32_t>(kPTileVecs), A.num_vecs - v0);
+          const uint32_t dst = smem_base + s * (kPSlots * kPTileBytes) + 2 * kPTileBytes;
+          p_mbar_expect_tx(fullw0 + 8 * s, nv * 16u);
+          p_bulk_load(dst, reinterpret_cast<const unsigned char*>(A.w) + static_cast<size_t>(v0) * 16,
+                      nv * 16u, fullw0 + 8 * s, pol_keep);
         }
       }
     }
@@ -402,11 +439,12 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
   SweepState st;
   st.stage = 0;
   st.phase = 0;
+  st.wpar = 0;
   st.failed = false;
   // shared-memory addresses computed once (opaque to the compiler, which would
   // otherwise rematerialise the shared-window arithmetic in every iteration)
-  uint32_t ring = smem_base + tid * 16, fullb = full0, emptyb = empty0;
-  asm volatile("" : "+r"(ring), "+r"(fullb), "+r"(emptyb));
+  uint32_t ring = smem_base + tid * 16, fullb = full0, emptyb = empty0, fullwb = fullw0;
+  asm volatile("" : "+r"(ring), "+r"(fullb), "+r"(emptyb), "+r"(fullwb));
   const bool calib_all = A.num_calib == ~0ull;
 
   for (int j = 0; j < T; ++j) {
@@ -426,11 +464,11 @@ __global__ void __launch_bounds__(kPThreads, 1) lsm_persistent_kernel(const Pers
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.0;
     if (!first && !last && calib_all)
-      p_sweep<Real, KT, true>(A, sp, st, acc, ring, fullb, emptyb, tile_lo, tile_hi, tid, lane, keep,
-                              false, false);
+      p_sweep<Real, KT, true>(A, sp, st, acc, ring, fullb, emptyb, fullwb, passdone, tile_lo, tile_hi,
+                              tid, lane, keep, false, false);
     else
-      p_sweep<Real, KT, false>(A, sp, st, acc, ring, fullb, emptyb, tile_lo, tile_hi, tid, lane, keep,
-                               first, last);
+      p_sweep<Real, KT, false>(A, sp, st, acc, ring, fullb, emptyb, fullwb, passdone, tile_lo, tile_hi,
+                               tid, lane, keep, first, last);
 
     // ---- CTA partial sums -> global row (packed 6 x 6 layout), fixed order
     const int M = last ? 2 : kLsmFastNS;

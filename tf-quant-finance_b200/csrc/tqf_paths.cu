@@ -32,15 +32,17 @@ TQF_EXTERN_MODEL(AffineModel4D)
 
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_blocks,
                                        int num_payoffs, double* __restrict__ sums, const PeerK pk) {
-  // Thread t sums the rows t, t + 256, ... (independent loads), then every
-  // (payoff, statistic) is combined by a shuffle tree and across the 8 warps in a
-  // fixed order -> reproducible for a given grid.
+  // Thread t sums the rows t, t + 1024, ... (independent loads: at most 5 rounds of
+  // L2 latency for the 4736-CTA grid), then every (payoff, statistic) is combined by a
+  // shuffle tree and across the 32 warps in a fixed order -> reproducible for a given
+  // grid.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
-  __shared__ double s_w[8][TQF_MAX_PAYOFFS * 3];
+  __shared__ double s_w[32][TQF_MAX_PAYOFFS * 3];
   double acc[TQF_MAX_PAYOFFS * 3];
 #pragma unroll
   for (int i = 0; i < TQF_MAX_PAYOFFS * 3; ++i) acc[i] = 0.0;
+#pragma unroll 2
   for (int b = threadIdx.x; b < num_blocks; b += blockDim.x) {
     const double* row = partials + static_cast<size_t>(b) * TQF_MAX_PAYOFFS * 4;
 #pragma unroll
@@ -371,7 +373,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     a.sobol_clamp = plan->sobol_clamp;
     int rc = launch_mvgbm(a, stream, &grid);
     if (rc != TQF_OK) return rc;
-    reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev,
+    reduce_partials_kernel<<<1, 1024, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev,
                                                   next_peer_exchange(plan));
     TQF_CUDA_OK(cudaGetLastError());
     return TQF_OK;
@@ -387,7 +389,7 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   const int mode = P.bridge ? MODE_PRICE_BRIDGE : (P.need_extrema ? MODE_PRICE_EXTREMA : MODE_PRICE);
   int rc = dispatch<Real>(plan, mode, plan->max_grid, smem, P, stream, &grid);
   if (rc != TQF_OK) return rc;
-  reduce_partials_kernel<<<1, 256, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev,
+  reduce_partials_kernel<<<1, 1024, 0, stream>>>(plan->partials_dev, grid, num_payoffs, sums_dev,
                                                   next_peer_exchange(plan));
   TQF_CUDA_OK(cudaGetLastError());
   return TQF_OK;
