@@ -299,10 +299,14 @@ class Ctx:
     out = None
     for _ in range(max(warmup, 3)):
       out = step_fn()
-    self.barrier()
+    # (the clock sampler spawns nvidia-smi: start it BEFORE the barrier, or rank 0 enters
+    # the timed region ~0.5 ms after the others and every other rank waits for it inside
+    # the first step's in-kernel exchange)
     sampler = ClockSampler(self.local) if (sample_clocks and self.rank == 0) else None
     if sampler:
       sampler.start()
+      time.sleep(0.3)
+    self.barrier()
     evs = []
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -317,6 +321,9 @@ class Ctx:
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
     ms = sum(a.elapsed_time(b) for a, b in evs)
+    if os.environ.get('TQF_BENCH_DEBUG'):
+      sys.stderr.write('rank %d: per-step ms %s\n' % (
+          self.rank, ' '.join('%.3f' % a.elapsed_time(b) for a, b in evs)))
     ms, = self.max_over_ranks([ms])
     return ms / steps, wall, clocks, out
 

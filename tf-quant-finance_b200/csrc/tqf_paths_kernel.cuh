@@ -15,6 +15,8 @@
 // point skip + 1 + p.
 #pragma once
 
+#include <cstdlib>
+
 #include "tqf_common.cuh"
 
 namespace tqf {
@@ -1213,6 +1215,18 @@ size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool table
 inline bool small_run(uint64_t num_chunks, int ppt, int max_grid) {
   return (num_chunks + ppt - 1) / ppt < static_cast<uint64_t>(max_grid / 32 * 3);
 }
+// A Sobol run with fewer than eight waves of CTAs (three resident per SM): the last,
+// partly filled wave would cost up to a sixth of the run (C2 sharded over 8 GPUs:
+// 2442 chunks of 512 paths on 444 resident CTAs = 5.5 waves, measured efficiency
+// 0.82).  Such runs carry half as many paths per thread -- twice the CTAs, half
+// the quantum.
+inline bool few_waves(uint64_t num_chunks, int ppt, int max_grid) {
+  static const bool off = [] {
+    const char* e = std::getenv("TQF_FEW_WAVES");      // "0": always the default kernels (A/B)
+    return e && e[0] == '0';
+  }();
+  return !off && (num_chunks + ppt - 1) / ppt < static_cast<uint64_t>(max_grid / 32 * 3) * 8;
+}
 
 // Launches the right instantiation for (rng kind, antithetic, mode).
 template <class Model>
@@ -1251,6 +1265,9 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
     constexpr int dflt = PathsPerThread<Model, RK>::value;                             \
     if constexpr (RK == RNGK_PHILOX && dflt > 1) {                                     \
       if (small_run(P.num_chunks, dflt, max_grid)) TQF_LAUNCH_PPT(RK, AN, MD, 1);      \
+    }                                                                                  \
+    if constexpr (RK == RNGK_SOBOL && dflt >= 4) {                                     \
+      if (few_waves(P.num_chunks, dflt, max_grid)) TQF_LAUNCH_PPT(RK, AN, MD, dflt / 2); \
     }                                                                                  \
     TQF_LAUNCH_PPT(RK, AN, MD, dflt);                                                  \
   } while (0)
