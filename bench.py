@@ -250,6 +250,7 @@ class Ctx:
       dist.init_process_group('nccl', device_id=torch.device('cuda', self.local))
     self.stream = torch.cuda.current_stream()
     self.flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device='cuda')
+    self._align = torch.zeros(1, dtype=torch.float32, device='cuda')
     self.px = None
     if self.world > 1 and os.environ.get('TQF_PRICE_PEER_EXCHANGE', '1') != '0':
       from tff_b200 import distributed
@@ -307,6 +308,11 @@ class Ctx:
       sampler.start()
       time.sleep(0.3)
     self.barrier()
+    if self.world > 1:
+      # device-side alignment: ranks leave the host barrier some 100 us apart; this
+      # all-reduce is enqueued without blocking the host, so every GPU passes it at the
+      # same moment with its first timed step already queued behind it
+      self.dist.all_reduce(self._align)
     evs = []
     t0 = time.perf_counter()
     for _ in range(steps):

@@ -500,6 +500,11 @@ int tqf_peer_alloc(uint64_t bytes, void** dev_ptr, uint8_t ipc_handle[64]);
 int tqf_peer_open(const uint8_t ipc_handle[64], void** dev_ptr);
 int tqf_peer_close(void* dev_ptr);
 int tqf_peer_free(void* dev_ptr);
+/* Status words of a rank's OWN exchange buffer: how many in-kernel exchanges
+ * gave up waiting for a peer (their sums were poisoned with NaN) and the epoch
+ * of the last one.  Synchronous 16-byte copy; the host calls it when a result
+ * that went through an exchange is not finite.                              */
+int tqf_peer_status(const void* own_buf, uint64_t* timeouts, uint64_t* last_epoch);
 
 
 /* num_sums doubles per payoff.  Packed (K <= 6): the upper triangle of a 6 x 6

@@ -49,6 +49,21 @@ def test_ctypes_structs_match_the_compiled_abi():
                          C.sizeof(_lib.PayoffDesc), C.sizeof(_lib.LsmDesc)]
 
 
+def test_integration_md_struct_sketch_matches_the_abi():
+  # the `_Rng` / `_Model` classes INTEGRATION.md shows a maintainer are executed as written
+  text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+  ns = {'C': C}
+  for cls in ('_Rng', '_Model'):
+    m = re.search(r'^class %s\(C\.Structure\):\n(?:  .*\n)+' % cls, text, re.M)
+    assert m, cls
+    exec(m.group(0), ns)  # pylint: disable=exec-used
+  sizes = (C.c_int32 * 4)()
+  _lib.check(_lib.lib().tqf_abi_sizes(sizes))
+  assert [C.sizeof(ns['_Rng']), C.sizeof(ns['_Model'])] == list(sizes)[:2]
+  assert [f[0] for f in ns['_Rng']._fields_] == [f[0] for f in _lib.RngDesc._fields_]
+  assert [f[0] for f in ns['_Model']._fields_] == [f[0] for f in _lib.ModelDesc._fields_]
+
+
 def test_product_does_not_import_oracle():
   pkg = os.path.join(ROOT, 'tf-quant-finance_b200')
   for base, _, files in os.walk(pkg):

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <string>
@@ -34,6 +35,16 @@ int device_ndtri_f32_tab(const float** out);
       return TQF_ERR_INVALID_ARGUMENT;    \
     }                                     \
   } while (0)
+
+// NVTX range around a C-ABI entry point (header-only NVTX 3: a no-op function
+// pointer check unless a profiler injected itself into the process).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define TQF_NVTX(name) ::tqf::NvtxRange nvtx_range__(name)
 
 constexpr int kSMs = 148;  // B200
 

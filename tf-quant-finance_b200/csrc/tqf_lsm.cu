@@ -921,6 +921,7 @@ int tqf_lsm_workspace(const tqf_lsm_desc* desc, int num_times, uint64_t* partial
 }
 
 int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
+  TQF_NVTX("tqf_lsm_create");
   TQF_REQUIRE(desc && out, "null argument");
   *out = nullptr;
   TQF_REQUIRE(desc->dtype == TQF_F32 || desc->dtype == TQF_F64, "bad dtype");
@@ -1013,6 +1014,7 @@ int tqf_lsm_destroy(tqf_lsm* h) {
 
 int tqf_lsm_column_sums(tqf_lsm* h, const int32_t* time_indices, int num_times, double* sums_dev,
                         void* stream) {
+  TQF_NVTX("tqf_lsm_column_sums");
   TQF_REQUIRE(h && time_indices && sums_dev && num_times >= 1, "bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const tqf_lsm_desc& d = h->desc;
@@ -1046,6 +1048,7 @@ int tqf_lsm_column_sums(tqf_lsm* h, const int32_t* time_indices, int num_times, 
 }
 
 int tqf_lsm_init(tqf_lsm* h, int time_index, void* stream) {
+  TQF_NVTX("tqf_lsm_init");
   TQF_REQUIRE(h, "null handle");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const dim3 grid(h->grid_aux, h->desc.batch);
@@ -1070,6 +1073,7 @@ int tqf_lsm_step(tqf_lsm* h, int do_update, int t_update, const double* mean_upd
                  const double* beta_dev, const double* ratio_update_dev, int do_accumulate,
                  int t_acc, const double* mean_acc_dev, const double* ratio_acc_dev,
                  int64_t mean_stride, double* sums_dev, void* stream) {
+  TQF_NVTX("tqf_lsm_step");
   TQF_REQUIRE(h, "null handle");
   TQF_REQUIRE(!do_update || (mean_update_dev && beta_dev && ratio_update_dev),
               "null update argument");
@@ -1088,6 +1092,7 @@ int tqf_lsm_step(tqf_lsm* h, int do_update, int t_update, const double* mean_upd
 
 int tqf_lsm_solve(tqf_lsm* h, double* sums_dev, int reduce_partials, double rcond,
                   double* beta_dev, void* stream) {
+  TQF_NVTX("tqf_lsm_solve");
   TQF_REQUIRE(h && sums_dev && beta_dev, "null argument");
   if (!h->fast) {
     set_error("device solve is implemented for basis sizes <= 6; solve on the host");
@@ -1128,6 +1133,7 @@ int tqf_lsm_set_fused_solve(tqf_lsm* h, double rcond, double* sums_dev, double* 
 int tqf_lsm_run_fused(tqf_lsm* h, const int32_t* exercise_times, int num_times,
                       const double* means_dev, int64_t mean_stride, const double* ratio_dev,
                       double* beta_dev, void* stream) {
+  TQF_NVTX("tqf_lsm_run_fused");
   TQF_REQUIRE(h && exercise_times && means_dev && ratio_dev && beta_dev && num_times >= 1,
               "bad arguments");
   TQF_REQUIRE(h->ticket_dev != nullptr && beta_dev == h->fused_beta_dev && lsm_vec_ok(h),
@@ -1162,6 +1168,7 @@ int tqf_lsm_run_persistent(tqf_lsm* h, const int32_t* exercise_times, int num_ti
                            const double* means_dev, int64_t mean_stride, const double* ratio_dev,
                            double rcond, uint64_t skip_below, double* value_sums_dev,
                            double* beta_dev, double* history_dev, void* stream) {
+  TQF_NVTX("tqf_lsm_run_persistent");
   TQF_REQUIRE(h && exercise_times && means_dev && ratio_dev && value_sums_dev && beta_dev &&
                   num_times >= 1,
               "bad arguments");
@@ -1246,6 +1253,16 @@ int tqf_peer_close(void* dev_ptr) {
   return TQF_OK;
 }
 
+int tqf_peer_status(const void* own_buf, uint64_t* timeouts, uint64_t* last_epoch) {
+  TQF_REQUIRE(own_buf && timeouts && last_epoch, "null argument");
+  unsigned long long w[2] = {0, 0};
+  TQF_CUDA_OK(cudaMemcpy(w, static_cast<const unsigned char*>(own_buf) + kLsmMaxPeers * 8, sizeof(w),
+                         cudaMemcpyDeviceToHost));
+  *timeouts = w[0];
+  *last_epoch = w[1];
+  return TQF_OK;
+}
+
 int tqf_peer_free(void* dev_ptr) {
   if (dev_ptr) TQF_CUDA_OK(cudaFree(dev_ptr));
   return TQF_OK;
@@ -1259,6 +1276,7 @@ int tqf_lsm_sums_layout(const tqf_lsm* h, int* num_sums, int* is_packed_symmetri
 }
 
 int tqf_lsm_value_sum(tqf_lsm* h, uint64_t skip_below, double* sums_dev, void* stream) {
+  TQF_NVTX("tqf_lsm_value_sum");
   TQF_REQUIRE(h && sums_dev, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const tqf_lsm_desc& d = h->desc;

@@ -499,6 +499,7 @@ extern "C" {
 
 int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
                     uint64_t num_paths_total, tqf_plan** out_plan) {
+  TQF_NVTX("tqf_plan_create");
   TQF_REQUIRE(model && rng && out_plan, "null argument");
   *out_plan = nullptr;
   ModelInfo info;
@@ -623,6 +624,7 @@ int tqf_plan_destroy(tqf_plan* plan) {
 int tqf_plan_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                    const tqf_payoff_desc* payoffs, int num_payoffs, double* sums_dev,
                    void* stream) {
+  TQF_NVTX("tqf_plan_price");
   TQF_REQUIRE(plan && sums_dev, "null argument");
   TQF_REQUIRE(num_payoffs >= 1 && num_payoffs <= TQF_MAX_PAYOFFS && payoffs,
               "num_payoffs must be in [1, TQF_MAX_PAYOFFS]");
@@ -637,6 +639,7 @@ int tqf_plan_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
 int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                    const int32_t* record_slot, void* out_dev, int64_t stride_path,
                    int64_t stride_time, int64_t stride_dim, int transform, void* stream) {
+  TQF_NVTX("tqf_plan_paths");
   TQF_REQUIRE(plan && record_slot, "null argument");
   const uint64_t units = plan->rng.antithetic ? plan->num_paths_total / 2 : plan->num_paths_total;
   TQF_REQUIRE(path_offset + path_count <= units, "shard exceeds the number of paths");
@@ -681,6 +684,7 @@ int tqf_plan_paths_sums(tqf_plan* plan, uint64_t path_offset, uint64_t path_coun
                         const int32_t* record_slot, void* out_dev, int64_t stride_path,
                         int64_t stride_time, int64_t stride_dim, int transform, int num_slots,
                         double* column_sums_dev, void* stream) {
+  TQF_NVTX("tqf_plan_paths_sums");
   TQF_REQUIRE(plan && record_slot && column_sums_dev, "null argument");
   const uint64_t units = plan->rng.antithetic ? plan->num_paths_total / 2 : plan->num_paths_total;
   TQF_REQUIRE(path_offset + path_count <= units, "shard exceeds the number of paths");

@@ -31,6 +31,10 @@ struct PeerK {
 __device__ __forceinline__ unsigned long long* peer_flag(unsigned char* buf, int parity, int src) {
   return reinterpret_cast<unsigned long long*>(buf + parity * 128) + src;
 }
+// Two status words behind the eight flags of parity 0 (the flag line is 128 bytes).
+__device__ __forceinline__ unsigned long long* peer_status_words(unsigned char* buf) {
+  return reinterpret_cast<unsigned long long*>(buf) + kLsmMaxPeers;
+}
 __device__ __forceinline__ double* peer_sums(unsigned char* buf, int parity, int src) {
   return reinterpret_cast<double*>(buf + kLsmPeerFlagBytes) +
          (static_cast<size_t>(parity) * kLsmMaxPeers + src) * kLsmPeerMaxSums;
@@ -44,8 +48,10 @@ __device__ __forceinline__ double* peer_sums(unsigned char* buf, int parity, int
 // order everywhere, so all ranks solve from bit-identical sums.  Slots are
 // double-buffered by the parity of the epoch: a rank cannot run two exchanges
 // ahead of another one, because each exchange needs every rank's flag.
-// Returns false when a peer did not arrive within ~10 s (the sums are then
-// poisoned with NaN instead of hanging the GPU).
+// Returns false when a peer did not arrive within ~10 s: the sums are then
+// poisoned with NaN instead of hanging the GPU, and the time-out is counted in
+// the status words of the rank's own buffer, which the host reads with
+// tqf_peer_status to tell this cause of a NaN from any other.
 // `nthreads` / `bar_id`: the threads of the CTA that call this together.  bar_id
 // < 0: the whole CTA (__syncthreads); otherwise the first `nthreads` threads,
 // synchronised on named barrier `bar_id` (warp-specialised kernels whose other
@@ -79,6 +85,11 @@ __device__ __forceinline__ bool peer_all_reduce(const PeerK& A, double* sums, in
       if (seen >= A.peer_epoch) break;
       if (clock64() - t0 > 20000000000ll) {
         s_timeout = 1;
+        // status words of this rank's own buffer (tqf_peer_status): number of
+        // exchanges that timed out, and the epoch of the last one
+        unsigned long long* status = peer_status_words(A.peer_bufs[A.peer_rank]);
+        atomicAdd(status, 1ull);
+        atomicExch(status + 1, A.peer_epoch);
         break;
       }
     }

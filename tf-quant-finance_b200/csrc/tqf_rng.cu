@@ -351,6 +351,7 @@ int tqf_philox_stateful_key_counter(int64_t op_seed, uint32_t key[2], uint32_t c
 int tqf_philox_raw_fill(const uint32_t key[2], const uint32_t counter[4],
                         uint64_t first_group, uint64_t num_groups, uint32_t* out_dev,
                         void* stream) {
+  TQF_NVTX("tqf_philox_raw_fill");
   TQF_REQUIRE(key && counter, "null key/counter");
   if (num_groups == 0) return TQF_OK;
   TQF_REQUIRE(out_dev, "null output");
@@ -365,6 +366,7 @@ int tqf_philox_raw_fill(const uint32_t key[2], const uint32_t counter[4],
 int tqf_philox_normal_fill(const uint32_t key[2], const uint32_t counter[4],
                            uint64_t first_element, uint64_t num_elements, int dtype,
                            void* out_dev, void* stream) {
+  TQF_NVTX("tqf_philox_normal_fill");
   TQF_REQUIRE(key && counter, "null key/counter");
   TQF_REQUIRE(dtype == TQF_F32 || dtype == TQF_F64, "dtype must be TQF_F32 or TQF_F64");
   if (num_elements == 0) return TQF_OK;
@@ -431,6 +433,7 @@ extern "C" {
 int tqf_halton_fill(const double* weights, const int32_t* sizes, const int32_t* radixes, int dim,
                     int max_size, uint64_t first_index, uint64_t count, int kind, int dtype,
                     void* out_dev, void* stream) {
+  TQF_NVTX("tqf_halton_fill");
   TQF_REQUIRE(weights && sizes && radixes, "null table");
   TQF_REQUIRE(dim >= 1 && dim <= 1000 && max_size >= 1 && max_size <= 64, "bad dim / max_size");
   TQF_REQUIRE(kind == 1 || kind == 2, "kind must be 1 (uniform) or 2 (normal)");
@@ -450,6 +453,7 @@ int tqf_halton_fill(const double* weights, const int32_t* sizes, const int32_t* 
 int tqf_philox_uniform_fill(const uint32_t key[2], const uint32_t counter[4],
                             uint64_t first_element, uint64_t num_elements, int dtype,
                             void* out_dev, void* stream) {
+  TQF_NVTX("tqf_philox_uniform_fill");
   TQF_REQUIRE(key && counter, "null key/counter");
   TQF_REQUIRE(dtype == TQF_F32 || dtype == TQF_F64, "dtype must be TQF_F32 or TQF_F64");
   if (num_elements == 0) return TQF_OK;
@@ -471,6 +475,7 @@ int tqf_philox_uniform_fill(const uint32_t key[2], const uint32_t counter[4],
 int tqf_sobol_direction_numbers(const uint32_t* poly_a, const uint8_t* degree,
                                 const uint32_t* m_init, int num_rows, int dim,
                                 int32_t* out) {
+  TQF_NVTX("tqf_sobol_direction_numbers");
   TQF_REQUIRE(out && dim >= 1, "bad output / dim");
   TQF_REQUIRE(dim - 1 <= num_rows, "dim exceeds the direction-number table");
   TQF_REQUIRE(dim == 1 || (poly_a && degree && m_init), "null table");
@@ -550,6 +555,7 @@ int tqf_math_eval(int fn, const double* in_dev, double* out_dev, uint64_t n, voi
 int tqf_sobol_fill(const int32_t* direction_numbers, int dim, uint64_t num_results,
                    uint64_t skip, uint64_t first_result, uint64_t count, int kind, int dtype,
                    void* out_dev, void* stream) {
+  TQF_NVTX("tqf_sobol_fill");
   TQF_REQUIRE(direction_numbers && dim >= 1, "null direction numbers / bad dim");
   TQF_REQUIRE(kind >= 0 && kind <= 2, "kind must be 0, 1 or 2");
   TQF_REQUIRE(dtype == TQF_F32 || dtype == TQF_F64, "dtype must be TQF_F32 or TQF_F64");

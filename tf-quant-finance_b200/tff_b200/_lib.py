@@ -210,6 +210,7 @@ _SIGNATURES = {
     'tqf_peer_open': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     'tqf_peer_close': (C.c_int, [C.c_void_p]),
     'tqf_peer_free': (C.c_int, [C.c_void_p]),
+    'tqf_peer_status': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     'tqf_lsm_init': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'tqf_lsm_step':
         (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

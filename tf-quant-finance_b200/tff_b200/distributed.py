@@ -80,6 +80,17 @@ def price_sums(plan, payoffs):
   return all_reduce_(plan.price_sums(list(payoffs), lo, count))
 
 
+def price_sums_host(plan, payoffs):
+  """`price_sums` read back to the host.  Sums that came through a peer exchange and
+  are not finite are traced to the exchange's status words first: a time-out there
+  raises instead of being returned as a NaN price."""
+  s = price_sums(plan, payoffs).cpu().numpy()
+  px = _SHARDED[0] if _SHARDED is not None else None
+  if px is not None and px.world > 1 and not np.all(np.isfinite(s)):
+    px.check('payoff sums')
+  return s
+
+
 def price_sharded(plan, payoffs, peer_exchange=None):
   """Monte-Carlo means of `payoffs` with the plan's units sharded over the
   ranks of the default process group.  Returns (mean, stderr) numpy arrays.
@@ -93,6 +104,8 @@ def price_sharded(plan, payoffs, peer_exchange=None):
     sums = plan.price_sums(list(payoffs), lo, count)
     all_reduce_(sums)
   s = sums.cpu().numpy()
+  if peer_exchange is not None and peer_exchange.world > 1 and not np.all(np.isfinite(s)):
+    peer_exchange.check('payoff sums')
   n = float(plan.num_samples)
   mean = s[:, 0] / n
   var = np.maximum(s[:, 1] / n - mean**2, 0.0)
@@ -103,7 +116,13 @@ def paths_sharded(plan, record_slot, num_times, exp_transform=False):
   """This rank's rows of the path tensor (time-major view `[rows, k, dim]`) and
   the global index of its first unit."""
   lo, count = shard_units(plan.units)
-  return plan.paths(record_slot, num_times, lo, count, exp_transform), lo
+  x = plan.paths(record_slot, num_times, lo, count, exp_transform)
+  if plan.rng.antithetic and world()[1] > 1:
+    # rows are [count units | their count partners]: row r >= count is global path
+    # N/2 + lo + (r - count), not lo + r.  `least_square_mc(num_calibration_samples=)`
+    # selects by global index lo + r and refuses tensors carrying this mark.
+    x._tqf_antithetic_shard = True
+  return x, lo
 
 
 class PeerExchange:
@@ -168,6 +187,19 @@ class PeerExchange:
     self.ptrs = (C.c_void_p * self.world)(*ptrs)
     self.epoch = 0          # exchanges performed so far (equal on all ranks)
     dist.barrier(group=group)
+
+  def check(self, what='result'):
+    """Raises if an in-kernel exchange on this rank's buffer gave up waiting for a
+    peer (its sums were poisoned with NaN).  Called by the pricing entry points
+    when a `what` that went through the exchange is not finite."""
+    n, ep = C.c_uint64(), C.c_uint64()
+    _lib.check(_lib.lib().tqf_peer_status(self._own, C.byref(n), C.byref(ep)))
+    if n.value:
+      raise RuntimeError(
+          'non-finite {}: {} peer exchange(s) on rank {} timed out waiting for another rank '
+          '(last at epoch {}); the ranks did not all reach the same exchange -- a failed or '
+          'skipped call on one rank, or a rank more than ~10 s behind'.format(
+              what, n.value, self.rank, ep.value))
 
   def close(self):
     if getattr(self, '_own', None) is None:

@@ -214,7 +214,7 @@ def price(dim, drift_fn, volatility_fn, times, payoffs, time_step=None,
     raise NotImplementedError('batched processes are not supported by `price` yet')
   plan = plans[0]
   try:
-    sums = distributed.price_sums(plan, payoffs).cpu().numpy()
+    sums = distributed.price_sums_host(plan, payoffs)
   finally:
     plan.release()
   n = float(plan.num_samples)

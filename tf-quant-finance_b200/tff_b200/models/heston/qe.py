@@ -130,7 +130,7 @@ def price(model, times, payoffs, initial_state, num_samples=1, random_type=None,
                      time_step, skip, tolerance, num_time_steps, times_grid, normal_draws,
                      use_cache=True)
   try:
-    sums = distributed.price_sums(plan, payoffs).cpu().numpy()
+    sums = distributed.price_sums_host(plan, payoffs)
   finally:
     plan.release()
   n = float(plan.num_samples)

@@ -74,7 +74,8 @@ class _GridPricing:
   def sums(self):
     out = []
     for c in range((len(self.payoffs) + _lib.MAX_PAYOFFS - 1) // _lib.MAX_PAYOFFS):
-      out.append(self.sums_dev(c).cpu().numpy())
+      c0 = c * _lib.MAX_PAYOFFS
+      out.append(distributed.price_sums_host(self.plan, self.payoffs[c0:c0 + _lib.MAX_PAYOFFS]))
     return np.concatenate(out, axis=0)
 
   def close(self):

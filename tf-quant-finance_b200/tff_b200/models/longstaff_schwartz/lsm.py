@@ -106,6 +106,12 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
         'kernels: use make_basket_put_payoff(strikes) or '
         'make_tabulated_payoff(values), and make_polynomial_basis(degree). '
         'There is no CPU fallback.')
+  if num_calibration_samples and getattr(sample_paths, '_tqf_antithetic_shard', False):
+    raise ValueError(
+        'num_calibration_samples with a shard of antithetic paths: the rows of the shard are '
+        '[units | partners], so "the first num_calibration_samples paths" would depend on the '
+        'number of ranks.  Draw the paths with a non-antithetic random type, or calibrate on '
+        'all paths.')
   if isinstance(sample_paths, torch.Tensor) or hasattr(sample_paths, '__dlpack__'):
     x = _tensor.from_dlpack(sample_paths)
     if dtype is not None:
@@ -121,6 +127,11 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
   n_local, dim = int(x.shape[-3]), int(x.shape[-1])
   ex_times = np.asarray(_tensor.to_numpy(exercise_times)).astype(np.int64).reshape(-1)
   T = ex_times.shape[0]
+  num_times = int(x.shape[-2])
+  if T == 0 or ex_times.min() < 0 or ex_times.max() >= num_times:
+    # the kernels index the time axis with these: the reference's tf.gather raises too
+    raise ValueError('exercise_times must be indices into the time axis of sample_paths '
+                     '(0 <= index < {}); got {}'.format(num_times, ex_times.tolist()))
   ev_tab = None
   if tabulated:
     vals = payoff_fn.values.to(device=x.device, dtype=x.dtype)        # [times, N, B]
@@ -361,6 +372,7 @@ def least_square_mc(sample_paths, exercise_times, payoff_fn, basis_fn,
     if diagnostics is not None:
       diagnostics.update(route='per-date launches', w=w_buf[0])
     if use_peers and not np.all(np.isfinite(vs)):
+      peer_exchange.check('Longstaff-Schwartz value sums')
       raise RuntimeError('non-finite Longstaff-Schwartz value sums after a peer exchange: a peer '
                          'rank did not take part within the time-out (rank skew or a failure on '
                          'another rank), or the paths hold non-finite values')
