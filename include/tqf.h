@@ -139,6 +139,25 @@ int tqf_halton_fill(const double* weights, const int32_t* sizes, const int32_t* 
                     int dim, int max_size, uint64_t first_index, uint64_t count,
                     int kind, int dtype, void* out_dev, void* stream);
 
+/* Owen-randomized Halton points (halton_impl.py:290-322, `randomized=True`).
+ * tqf_halton_permutations builds, ON THE HOST, the digit permutations of
+ * `_get_permutations` (342-379): for axis d (radix p_d) and digit position
+ * i < num_coeffs the stable argsort of `tf.random.stateless_uniform([p_d],
+ * seed=(seed + i, p_d), float64)` (math/random_ops/stateless.py:24-52);
+ * perms is int32 [num_coeffs][sum_d p_d], axis d at column offset sum_{e<d} p_e
+ * -- the flattened `perms` of the reference's HaltonParams.
+ * tqf_halton_randomized_fill: as tqf_halton_fill with every digit looked up in
+ * its permutation (perms_dev: the table above in DEVICE memory) and
+ * zero_correction[d] (host double [dim], `stateless_uniform([dim,1], (seed,
+ * seed), dtype) / p_d^size_d`, 303-322) added.  Synchronises `stream`.        */
+int tqf_halton_permutations(int64_t seed, const int32_t* radixes, int dim, int num_coeffs,
+                            int32_t* perms);
+int tqf_halton_randomized_fill(const double* weights, const int32_t* sizes,
+                               const int32_t* radixes, int dim, int max_size,
+                               const int32_t* perms_dev, const double* zero_correction,
+                               uint64_t first_index, uint64_t count, int kind, int dtype,
+                               void* out_dev, void* stream);
+
 /* Direction numbers m[dim][32] (int32) from the Joe-Kuo table: replaces
  * `load_data` + `_compute_direction_numbers`
  * (math/random_ops/sobol/sobol_impl.py:171-197, 237-261).

@@ -83,8 +83,8 @@ def _mvnormal_sobol(sample_shape, mean, skip, dtype):
   return mean + _erfinv_times_sqrt2(seq, dtype)
 
 
-def _mvnormal_halton(sample_shape, mean, skip, dtype):
-  """`multivariate_normal.py:356-424` for HALTON (randomized = False):
+def _mvnormal_halton(sample_shape, mean, skip, dtype, randomized=False, seed=None):
+  """`multivariate_normal.py:356-424` for HALTON / HALTON_RANDOMIZED:
   `halton.sample(dim, sequence_indices=range(skip, skip + n))`, then the same
   transpose / reshape / erfinv as the Sobol branch."""
   from oracle import halton  # pylint: disable=g-import-not-at-top
@@ -93,7 +93,8 @@ def _mvnormal_halton(sample_shape, mean, skip, dtype):
   sample_shape = tuple(int(s) for s in sample_shape)
   output_shape_t = tuple(reversed(batch_shape)) + sample_shape
   num_samples = int(np.prod(output_shape_t)) // dim
-  seq = halton.sample(dim, sequence_indices=np.arange(skip, skip + num_samples), dtype=dtype)
+  seq = halton.sample(dim, sequence_indices=np.arange(skip, skip + num_samples), dtype=dtype,
+                      randomized=randomized, seed=seed)
   seq = seq.T
   size_sample = len(sample_shape)
   size_batch = len(batch_shape)
@@ -120,6 +121,8 @@ def mv_normal_sample(sample_shape, mean, random_type=None, seed=None,
     return _mvnormal_sobol(sample_shape, mean, skip, dtype)
   if random_type == RandomType.HALTON:
     return _mvnormal_halton(sample_shape, mean, skip, dtype)
+  if random_type == RandomType.HALTON_RANDOMIZED:
+    return _mvnormal_halton(sample_shape, mean, skip, dtype, randomized=True, seed=seed)
   raise NotImplementedError(
       'Only STATELESS, PSEUDO, PSEUDO_ANTITHETIC, STATELESS_ANTITHETIC and '
       'SOBOL are restated by the oracle. Supplied: {}'.format(random_type))

@@ -3,6 +3,7 @@
 // the oracle, and they back `tff_b200.math.random` (stateless_normal,
 // sobol.sample, mv_normal_sample).  The path kernels use the same device
 // functions (tqf_common.cuh) in registers.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -231,6 +232,49 @@ __global__ void halton_fill_kernel(const Real* __restrict__ weights, const int* 
   }
 }
 
+// Owen-randomized Halton point (halton_impl.py:290-322): digit j of axis d goes
+// through permutation `perms[j][offset_d ..]` of range(p_d) before it is scaled; all
+// `num_coeffs` digit positions are looked up as the reference does, the ones beyond
+// the axis' own size are then masked, and the random tail `zero_correction[d]` is added.
+template <int KIND, typename Real>
+__global__ void halton_randomized_kernel(const Real* __restrict__ weights,
+                                         const int* __restrict__ sizes,
+                                         const Real* __restrict__ radixes,
+                                         const int* __restrict__ radix_offsets,
+                                         const int* __restrict__ perms, int radix_sum,
+                                         const Real* __restrict__ zero_correction, int dim,
+                                         int max_size, uint64_t first_index, uint64_t count,
+                                         const double* __restrict__ logtab,
+                                         Real* __restrict__ out) {
+  const uint64_t total = count * static_cast<uint64_t>(dim);
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       e < total; e += stride) {
+    const uint64_t row = e / dim;
+    const int d = static_cast<int>(e - row * dim);
+    const Real idx = static_cast<Real>(first_index + row) + Real(1);
+    const Real p = radixes[d];
+    const Real* w = weights + static_cast<size_t>(d) * max_size;
+    const int n = sizes[d];
+    const int* perm = perms + radix_offsets[d];
+    Real sum = 0;
+    for (int j = 0; j < n; ++j) {
+      const Real wj = w[j];
+      Real c = floor(idx / wj);
+      c = fmod(c, p);
+      c = static_cast<Real>(perm[static_cast<size_t>(j) * radix_sum + static_cast<int>(c)]);
+      c = c / p;
+      sum += c / wj;
+    }
+    sum += zero_correction[d];
+    if constexpr (KIND == 1) {
+      out[e] = sum;
+    } else {
+      out[e] = ndtri(sum, logtab);
+    }
+  }
+}
+
 __global__ void math_eval_kernel(int fn, const double* __restrict__ in, double* __restrict__ out,
                                  uint64_t n, const double* __restrict__ logtab) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
@@ -428,7 +472,133 @@ static int halton_fill_impl(const double* weights, const int32_t* sizes, const i
   return TQF_OK;
 }
 
+template <typename Real>
+static int halton_randomized_impl(const double* weights, const int32_t* sizes,
+                                  const int32_t* radixes, int dim, int max_size,
+                                  const int32_t* perms_dev, const double* zero_correction,
+                                  uint64_t first_index, uint64_t count, int kind, void* out_dev,
+                                  cudaStream_t s) {
+  std::vector<Real> w(static_cast<size_t>(dim) * max_size), r(dim), z(dim);
+  std::vector<int> offs(dim);
+  int radix_sum = 0;
+  for (size_t i = 0; i < w.size(); ++i) w[i] = static_cast<Real>(weights[i]);
+  for (int d = 0; d < dim; ++d) {
+    r[d] = static_cast<Real>(radixes[d]);
+    z[d] = static_cast<Real>(zero_correction[d]);
+    offs[d] = radix_sum;
+    radix_sum += radixes[d];
+  }
+  const double* logtab = nullptr;
+  int rc = device_logtab(&logtab);
+  if (rc != TQF_OK) return rc;
+  // one staging allocation: weights | radixes | zero correction | sizes | offsets
+  const size_t nreal = w.size() + 2 * static_cast<size_t>(dim);
+  const size_t bytes = nreal * sizeof(Real) + 2 * static_cast<size_t>(dim) * sizeof(int);
+  unsigned char* dev = nullptr;
+  cudaError_t e = cudaMalloc(&dev, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "tqf_halton_randomized_fill");
+  Real* w_dev = reinterpret_cast<Real*>(dev);
+  Real* r_dev = w_dev + w.size();
+  Real* z_dev = r_dev + dim;
+  int* n_dev = reinterpret_cast<int*>(z_dev + dim);
+  int* o_dev = n_dev + dim;
+  e = cudaMemcpyAsync(w_dev, w.data(), w.size() * sizeof(Real), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(r_dev, r.data(), dim * sizeof(Real), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(z_dev, z.data(), dim * sizeof(Real), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(n_dev, sizes, dim * sizeof(int), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(o_dev, offs.data(), dim * sizeof(int), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    const int grid = grid_for(count * static_cast<uint64_t>(dim), 256);
+    if (kind == 1)
+      halton_randomized_kernel<1, Real><<<grid, 256, 0, s>>>(
+          w_dev, n_dev, r_dev, o_dev, perms_dev, radix_sum, z_dev, dim, max_size, first_index,
+          count, logtab, static_cast<Real*>(out_dev));
+    else
+      halton_randomized_kernel<2, Real><<<grid, 256, 0, s>>>(
+          w_dev, n_dev, r_dev, o_dev, perms_dev, radix_sum, z_dev, dim, max_size, first_index,
+          count, logtab, static_cast<Real*>(out_dev));
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // the host staging buffers go away
+  }
+  cudaFree(dev);
+  if (e != cudaSuccess) return cuda_fail(e, "tqf_halton_randomized_fill");
+  return TQF_OK;
+}
+
+// Uint64ToDouble on the host (the device twin is uint64_to_double).
+static double host_uint64_to_double(uint32_t x0, uint32_t x1) {
+  const uint64_t bits = (static_cast<uint64_t>((x0 & 0xFFFFFu) | 0x3FF00000u) << 32) | x1;
+  double d;
+  std::memcpy(&d, &bits, sizeof(d));
+  return d - 1.0;
+}
+
 extern "C" {
+
+int tqf_halton_permutations(int64_t seed, const int32_t* radixes, int dim, int num_coeffs,
+                            int32_t* perms) {
+  TQF_NVTX("tqf_halton_permutations");
+  TQF_REQUIRE(radixes && perms && dim >= 1 && dim <= 1000, "bad radixes / dim");
+  TQF_REQUIRE(num_coeffs >= 1 && num_coeffs <= 64, "bad num_coeffs");
+  size_t radix_sum = 0;
+  for (int d = 0; d < dim; ++d) {
+    TQF_REQUIRE(radixes[d] >= 2, "bad radix");
+    radix_sum += radixes[d];
+  }
+  std::vector<double> u;
+  std::vector<int32_t> order;
+  size_t offset = 0;
+  for (int d = 0; d < dim; ++d) {
+    const int p = radixes[d];
+    u.resize(p);
+    order.resize(p);
+    for (int i = 0; i < num_coeffs; ++i) {
+      // stateless_random_shuffle(range(p), seed=(seed + i, p)): float64 stateless
+      // uniforms (two per Philox group) and a stable argsort
+      const int64_t sd[2] = {seed + i, p};
+      uint32_t key[2], ctr[4];
+      tqf_philox_stateless_key_counter(sd, key, ctr);
+      const PhiloxKey k{key[0], key[1]};
+      const PhiloxCtr c{ctr[0], ctr[1], ctr[2], ctr[3]};
+      for (int g = 0; 2 * g < p; ++g) {
+        const uint4 w = philox_group(c, k, static_cast<uint64_t>(g));
+        u[2 * g] = host_uint64_to_double(w.x, w.y);
+        if (2 * g + 1 < p) u[2 * g + 1] = host_uint64_to_double(w.z, w.w);
+      }
+      for (int q = 0; q < p; ++q) order[q] = q;
+      std::stable_sort(order.begin(), order.end(),
+                       [&u](int32_t a, int32_t b) { return u[a] < u[b]; });
+      std::memcpy(perms + static_cast<size_t>(i) * radix_sum + offset, order.data(),
+                  static_cast<size_t>(p) * sizeof(int32_t));
+    }
+    offset += p;
+  }
+  return TQF_OK;
+}
+
+int tqf_halton_randomized_fill(const double* weights, const int32_t* sizes,
+                               const int32_t* radixes, int dim, int max_size,
+                               const int32_t* perms_dev, const double* zero_correction,
+                               uint64_t first_index, uint64_t count, int kind, int dtype,
+                               void* out_dev, void* stream) {
+  TQF_NVTX("tqf_halton_randomized_fill");
+  TQF_REQUIRE(weights && sizes && radixes && perms_dev && zero_correction, "null table");
+  TQF_REQUIRE(dim >= 1 && dim <= 1000 && max_size >= 1 && max_size <= 64, "bad dim / max_size");
+  TQF_REQUIRE(kind == 1 || kind == 2, "kind must be 1 (uniform) or 2 (normal)");
+  TQF_REQUIRE(dtype == TQF_F32 || dtype == TQF_F64, "dtype must be TQF_F32 or TQF_F64");
+  for (int d = 0; d < dim; ++d)
+    TQF_REQUIRE(sizes[d] >= 1 && sizes[d] <= max_size && radixes[d] >= 2, "bad sizes / radixes");
+  if (count == 0) return TQF_OK;
+  TQF_REQUIRE(out_dev, "null output");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dtype == TQF_F64
+             ? halton_randomized_impl<double>(weights, sizes, radixes, dim, max_size, perms_dev,
+                                              zero_correction, first_index, count, kind,
+                                              out_dev, s)
+             : halton_randomized_impl<float>(weights, sizes, radixes, dim, max_size, perms_dev,
+                                             zero_correction, first_index, count, kind, out_dev,
+                                             s);
+}
 
 int tqf_halton_fill(const double* weights, const int32_t* sizes, const int32_t* radixes, int dim,
                     int max_size, uint64_t first_index, uint64_t count, int kind, int dtype,

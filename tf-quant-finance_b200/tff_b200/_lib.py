@@ -191,6 +191,11 @@ _SIGNATURES = {
     'tqf_halton_fill':
         (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                    C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'tqf_halton_permutations':
+        (C.c_int, [C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'tqf_halton_randomized_fill':
+        (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                   C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'tqf_lsm_workspace': (C.c_int, [C.POINTER(LsmDesc), C.c_int, C.POINTER(C.c_uint64)]),
     'tqf_lsm_create': (C.c_int, [C.POINTER(LsmDesc), C.POINTER(C.c_void_p)]),
     'tqf_lsm_destroy': (C.c_int, [C.c_void_p]),

@@ -101,23 +101,20 @@ def multivariate_normal(sample_shape, mean=None, covariance_matrix=None,
     z = z.t().reshape(out_shape_t).permute(perm)
     return _finish(z, mean_t, scale_t)
 
-  if rt == RandomType.HALTON:
-    # multivariate_normal.py:386-424 with randomized = False
+  if rt in (RandomType.HALTON, RandomType.HALTON_RANDOMIZED):
+    # multivariate_normal.py:391-424
     from tff_b200.math.random import halton  # pylint: disable=g-import-not-at-top
     skip = int(kwargs.get('skip', 0) or 0)
     out_shape_t = tuple(reversed(batch_shape)) + sample_shape
     num_samples = int(np.prod(out_shape_t)) // dim
-    z = halton.sample_normal(dim, num_samples, skip=skip, dtype=dt)   # [n, dim]
+    z = halton.sample_normal(dim, num_samples, skip=skip, dtype=dt,
+                             randomized=rt == RandomType.HALTON_RANDOMIZED, seed=seed,
+                             randomization_params=kwargs.get('randomization_params'))
     nb, ns = len(batch_shape), len(sample_shape)
     perm = list(range(nb, nb + ns)) + list(range(nb - 1, -1, -1))
     z = z.t().reshape(out_shape_t).permute(perm)
     return _finish(z, mean_t, scale_t)
 
-  if rt == RandomType.HALTON_RANDOMIZED:
-    raise NotImplementedError(
-        'HALTON_RANDOMIZED (Owen scrambling through TensorFlow\'s random shuffle) is not '
-        'implemented by the B200 engine (SURVEY 8f-4); supported: PSEUDO, STATELESS, '
-        'PSEUDO_ANTITHETIC, STATELESS_ANTITHETIC, SOBOL, HALTON.')
   raise NotImplementedError(
       'Only STATELESS, PSEUDO, PSEUDO_ANTITHETIC, STATELESS_ANTITHETIC,  '
       'HALTON, HALTON_RANDOMIZED, and SOBOL random types are currently '

@@ -35,13 +35,15 @@ def uniform(dim, sample_shape, random_type=None, dtype=None, seed=None, name=Non
     num = int(np.prod(sample_shape)) if sample_shape else 1
     seq = sobol.sample(dim=int(dim), num_results=num, skip=int(kwargs.get('skip', 0)), dtype=dtype)
     return seq.reshape(shape)
-  if random_type.value == RandomType.HALTON.value:
+  if random_type.value in (RandomType.HALTON.value, RandomType.HALTON_RANDOMIZED.value):
+    # uniform.py:135-150
     from tff_b200.math.random import halton  # pylint: disable=g-import-not-at-top
     num = int(np.prod(sample_shape)) if sample_shape else 1
     skip = int(kwargs.get('skip', 0))
     seq, _ = halton.sample(dim=int(dim), sequence_indices=np.arange(skip, skip + num),
-                           randomized=False, dtype=dtype)
+                           randomized=random_type.value == RandomType.HALTON_RANDOMIZED.value,
+                           randomization_params=kwargs.get('randomization_params'), seed=seed,
+                           dtype=dtype)
     return seq.reshape(shape)
   raise NotImplementedError(
-      'uniform: {} is not implemented by the B200 engine (Philox, Sobol and the '
-      'non-randomized Halton sequence only).'.format(random_type))
+      'uniform: {} is not implemented by the B200 engine.'.format(random_type))

@@ -71,15 +71,17 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
       times_grid=times_grid, tolerance=tolerance, dtype=dtype)
 
   if (normal_draws is None and random_type is not None
-      and random_type.value == random.RandomType.HALTON.value):
-    # The non-randomized Halton sequence has no in-kernel generator: its normals
+      and random_type.value in (random.RandomType.HALTON.value,
+                                random.RandomType.HALTON_RANDOMIZED.value)):
+    # The Halton sequences have no in-kernel generator: their normals
     # are materialised like the reference does for every random type
     # (euler_sampling.py:365-374, utils.py:20-128) and fed as `normal_draws`.
     if batch_shape:
       raise NotImplementedError('batched processes with HALTON draws are not implemented yet')
     draws = utils.generate_mc_normal_draws(
         num_normal_draws=dim, num_time_steps=all_times.shape[0] - 1,
-        num_sample_paths=int(num_samples), random_type=random_type, skip=skip, dtype=dtype)
+        num_sample_paths=int(num_samples), random_type=random_type, skip=skip, seed=seed,
+        dtype=dtype)
     normal_draws = draws.permute(1, 0, 2).contiguous()           # [N, steps, dim]
   if normal_draws is not None:
     normal_draws = _tensor.from_dlpack(normal_draws)
