@@ -63,6 +63,20 @@ extern "C" {
 /* Milstein scheme of the 1-d affine process (milstein_sampling.py:565-575):
  * coef columns dt, sqrt_dt, a0, a1, b0, b1; dS/dx = b1.                     */
 #define TQF_MODEL_MILSTEIN_1F 10
+/* Gaussian / quasi-Gaussian HJM with deterministic volatility
+ * (hjm/gaussian_hjm.py:203-228, hjm/quasi_gaussian_hjm.py:232-289): F = dim - 1
+ * Markov factors x_i and the path integral I of the short rate r = sum_i x_i +
+ * f(0, t) that the models' discount factors are made of (gaussian_hjm.py:451-456
+ * left-point rule, quasi_gaussian_hjm.py:486-490 right-point rule):
+ *   x_i' = (x_i + dt (a0_i - k_i x_i)) + sum_j B_ij z_j sqrt_dt,
+ *   I'   = I + cL sum_i x_i + cR sum_i x_i' + cF.
+ * coef columns: dt, sqrt_dt, a0[F] (= sum_j y_ij, the deterministic state y of the
+ * model), k[F], B[F][F] row-major (sqrt_rho_ij sigma_i), cL, cR, cF.  F = 1..3;
+ * num_factors = the normals one step CONSUMES: F (Gaussian HJM) or F + F^2
+ * (quasi-Gaussian: the reference simulates vec(y) next to x with zero volatility
+ * rows, so its Wiener process has F + F^2 components of which the first F act);
+ * supported (F, num_factors): (1,1) (1,2) (2,2) (2,6) (3,3).  x0 = 0.         */
+#define TQF_MODEL_HJM 11
 
 /* payoff kinds (reduced in-kernel; callers: e.g. hull_white/swaption.py:310) */
 #define TQF_PAYOFF_CALL 1          /* max(f(X_T) - K, 0)                    */
@@ -259,7 +273,11 @@ typedef struct tqf_payoff_desc {
    * TQF_TRANSFORM_EXP the barrier refers to exp(state) and the bridge runs on the
    * state (log-price) itself.                                               */
   int32_t brownian_bridge;
-  double reserved3;
+  /* TQF_PAYOFF_HW_SWAPTION on TQF_MODEL_HJM: number of factors F (0 is read as
+   * 1); P(t_e, T_j) = exp(pay_k[j] - sum_i pay_g[j * F + i] x_i)
+   * (quasi_gaussian_hjm.py:499-525), num_payments * F <= 64.                 */
+  int32_t num_factors;
+  int32_t reserved3;
   double reserved4;
   double pay_g[TQF_MAX_SWAPTION_PAYMENTS];     /* G(tau_j)=(1-e^{-k tau})/k */
   /* ln(P0(T_j)/P0(t_e)) - y(t_e) G_j^2 / 2 (vector_hull_white.py:783-814)  */
@@ -343,6 +361,20 @@ int tqf_hw_discount_curves(const void* rates_dev, int64_t rs_path, int64_t rs_ti
                            int64_t rs_dim, const double* f0_dev, const double* coef_a_dev,
                            const double* coef_g_dev, uint64_t num_paths, int m, int k, int dim,
                            int dtype, void* out_dev, void* stream);
+
+/* HJM discount curves along simulated factor paths (`_bond_reconstitution`,
+ * models/hjm/quasi_gaussian_hjm.py:499-525, behind `sample_discount_curve_paths`
+ * 365-449):  out[n][i][j] = coef_a[i][j] exp(-sum_d coef_g[i][j][d] x[n, j, d]),
+ *   coef_g = (1 - e^{-k_d tau_i}) / k_d,
+ *   coef_a = P0(t_j + tau_i) / P0(t_j) exp(-coef_g' y(t_j) coef_g / 2)
+ * (y is deterministic for deterministic volatility).  x_dev: model dtype, element
+ * (n, j, d) at n*xs_path + j*xs_time + d*xs_dim; coef_a_dev [m][k], coef_g_dev
+ * [m][k][num_factors]: DEVICE doubles; out_dev: model dtype [num_paths][m][k].
+ * num_factors <= 3.                                                           */
+int tqf_hjm_discount_curves(const void* x_dev, int64_t xs_path, int64_t xs_time,
+                            int64_t xs_dim, const double* coef_a_dev,
+                            const double* coef_g_dev, uint64_t num_paths, int m, int k,
+                            int num_factors, int dtype, void* out_dev, void* stream);
 
 /* Exercise values of Bermudan swaptions on Hull-White paths: replaces the bond
  * gather / weighted sum / scatter of hull_white/swaption.py:608-724

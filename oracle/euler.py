@@ -93,6 +93,9 @@ def sample(dim, drift_fn, volatility_fn, times, time_step=None,
   if not record:
     out = np.expand_dims(state, axis=-2)
   else:
+    # duplicate request times leave trailing TensorArray slots unwritten: TensorFlow's
+    # stack() returns zeros there (element shape known)
+    slots = [np.zeros_like(state) if s is None else s for s in slots]
     res = np.stack(slots, axis=0)                 # [k] + batch + [N, dim]
     n = res.ndim
     out = np.transpose(res, list(range(1, n - 1)) + [0, n - 1])

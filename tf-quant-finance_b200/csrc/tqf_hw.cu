@@ -57,6 +57,49 @@ hw_discount_curves_kernel(const Real* __restrict__ rates, int64_t rs_path, int64
   }
 }
 
+// HJM discount curves (`_bond_reconstitution`, hjm/quasi_gaussian_hjm.py:499-525)
+// along simulated factor paths: the factors act TOGETHER inside one exponential,
+//   P(t_j, t_j + tau_i) = A_ij exp(-sum_d G_ijd x_d(t_j)),
+//   A = P0(t + tau) / P0(t) exp(-G' y(t) G / 2)  (y deterministic: folded on the host).
+// Same tile transpose as above; out is [num_paths][m][k].
+template <typename Real>
+__global__ void __launch_bounds__(kHwTile * 8)
+hjm_discount_curves_kernel(const Real* __restrict__ x, int64_t xs_path, int64_t xs_time,
+                           int64_t xs_dim, const double* __restrict__ coef_a,
+                           const double* __restrict__ coef_g, uint64_t num_paths, int m, int k,
+                           int nf, Real* __restrict__ out) {
+  __shared__ double s_x[3][kHwTile][kHwTile + 1];       // [factor][time column][path]
+  const uint64_t n0 = static_cast<uint64_t>(blockIdx.x) * kHwTile;
+  const int c0 = blockIdx.y * kHwTile;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < kHwTile; r += 8) {
+    const int j = c0 + r;
+    const uint64_t n = n0 + tx;
+    for (int d = 0; d < nf; ++d) {
+      double v = 0.0;
+      if (j < k && n < num_paths)
+        v = static_cast<double>(x[static_cast<int64_t>(n) * xs_path + j * xs_time + d * xs_dim]);
+      s_x[d][r][tx] = v;
+    }
+  }
+  __syncthreads();
+  const int j = c0 + tx;
+  if (j >= k) return;
+  for (int i = 0; i < m; ++i) {
+    const double a = coef_a[static_cast<size_t>(i) * k + j];
+    double g[3];
+    for (int d = 0; d < nf; ++d) g[d] = coef_g[(static_cast<size_t>(i) * k + j) * nf + d];
+    for (int r = ty; r < kHwTile; r += 8) {
+      const uint64_t n = n0 + r;
+      if (n < num_paths) {
+        double e = 0.0;
+        for (int d = 0; d < nf; ++d) e = fma(-s_x[d][tx][r], g[d], e);
+        out[(n * m + i) * static_cast<uint64_t>(k) + j] = static_cast<Real>(a * exp(e));
+      }
+    }
+  }
+}
+
 // Exercise values of Bermudan swaptions on Hull-White paths: the tabulated
 // payoff that hull_white/swaption.py:608-724 builds with a gather of the
 // [N, m, k] bond tensor, a weighted sum over the payments and a scatter to the
@@ -144,6 +187,40 @@ extern "C" int tqf_hw_discount_curves(const void* rates_dev, int64_t rs_path, in
     hw_discount_curves_kernel<float><<<grid, block, 0, s>>>(
         static_cast<const float*>(rates_dev), rs_path, rs_time, rs_dim, f0_dev, coef_a_dev,
         coef_g_dev, num_paths, m, k, dim, static_cast<float*>(out_dev));
+  TQF_CUDA_OK(cudaGetLastError());
+  return TQF_OK;
+}
+
+extern "C" int tqf_hjm_discount_curves(const void* x_dev, int64_t xs_path, int64_t xs_time,
+                                       int64_t xs_dim, const double* coef_a_dev,
+                                       const double* coef_g_dev, uint64_t num_paths, int m,
+                                       int k, int num_factors, int dtype, void* out_dev,
+                                       void* stream) {
+  TQF_NVTX("tqf_hjm_discount_curves");
+  TQF_REQUIRE(x_dev && coef_a_dev && coef_g_dev && out_dev, "null argument");
+  TQF_REQUIRE(m >= 1 && k >= 1 && num_factors >= 1 && num_factors <= 3,
+              "empty curve / time axis or more than 3 factors");
+  TQF_REQUIRE(dtype == TQF_F32 || dtype == TQF_F64, "bad dtype");
+  if (num_paths == 0) return TQF_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: libtqf has no CPU fallback");
+    return TQF_ERR_CUDA;
+  }
+  const uint64_t bx = (num_paths + kHwTile - 1) / kHwTile;
+  TQF_REQUIRE(bx < (1ull << 31), "too many paths for one launch");
+  const dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>((k + kHwTile - 1) / kHwTile));
+  const dim3 block(kHwTile, 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == TQF_F64)
+    hjm_discount_curves_kernel<double><<<grid, block, 0, s>>>(
+        static_cast<const double*>(x_dev), xs_path, xs_time, xs_dim, coef_a_dev, coef_g_dev,
+        num_paths, m, k, num_factors, static_cast<double*>(out_dev));
+  else
+    hjm_discount_curves_kernel<float><<<grid, block, 0, s>>>(
+        static_cast<const float*>(x_dev), xs_path, xs_time, xs_dim, coef_a_dev, coef_g_dev,
+        num_paths, m, k, num_factors, static_cast<float*>(out_dev));
   TQF_CUDA_OK(cudaGetLastError());
   return TQF_OK;
 }

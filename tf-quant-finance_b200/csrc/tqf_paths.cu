@@ -28,6 +28,11 @@ TQF_EXTERN_MODEL(HestonQeModel)
 TQF_EXTERN_MODEL(AffineModel2D)
 TQF_EXTERN_MODEL(AffineModel3D)
 TQF_EXTERN_MODEL(AffineModel4D)
+TQF_EXTERN_MODEL(HjmModel11)
+TQF_EXTERN_MODEL(HjmModel12)
+TQF_EXTERN_MODEL(HjmModel22)
+TQF_EXTERN_MODEL(HjmModel26)
+TQF_EXTERN_MODEL(HjmModel33)
 #undef TQF_EXTERN_MODEL
 
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_blocks,
@@ -80,8 +85,14 @@ struct ModelInfo {
   int dim, nf, ncoef;
 };
 
-static bool model_info(int kind, int dim, ModelInfo* info) {
+static bool model_info(int kind, int dim, int num_factors, ModelInfo* info) {
   switch (kind) {
+    case TQF_MODEL_HJM: {
+      const int f = dim - 1;
+      *info = {dim, num_factors, 5 + 2 * f + f * f};
+      return (f == 1 && (num_factors == 1 || num_factors == 2)) ||
+             (f == 2 && (num_factors == 2 || num_factors == 6)) || (f == 3 && num_factors == 3);
+    }
     case TQF_MODEL_MVGBM: *info = {dim, dim, 2}; return dim >= 1 && dim <= 64;
     case TQF_MODEL_AFFINE_1F: *info = {1, 1, 6}; return true;
     case TQF_MODEL_AFFINE_1F_TANGENT: *info = {3, 1, 10}; return true;
@@ -243,6 +254,18 @@ static int dispatch(const tqf_plan* plan, int mode, int grid, size_t smem, const
       if (plan->info.dim == 3)
         return launch_path_kernel<AffineModel3D<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
       return launch_path_kernel<AffineModel4D<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+    case TQF_MODEL_HJM: {
+      const int f = plan->info.dim - 1, nfs = plan->info.nf;
+      if (f == 1 && nfs == 1)
+        return launch_path_kernel<HjmModel11<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+      if (f == 1)
+        return launch_path_kernel<HjmModel12<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+      if (f == 2 && nfs == 2)
+        return launch_path_kernel<HjmModel22<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+      if (f == 2)
+        return launch_path_kernel<HjmModel26<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+      return launch_path_kernel<HjmModel33<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+    }
     default:
       set_error("model kind not supported by the generic path kernel");
       return TQF_ERR_UNSUPPORTED;
@@ -268,17 +291,21 @@ static int run_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     TQF_REQUIRE(step <= S, "payoff expiry_step exceeds the number of steps");
     flags[step] = 1;
     if (d.kind == TQF_PAYOFF_HW_SWAPTION) {
-      TQF_REQUIRE(plan->model.kind == TQF_MODEL_HW1F,
-                  "TQF_PAYOFF_HW_SWAPTION needs the TQF_MODEL_HW1F model");
-      TQF_REQUIRE(d.num_payments >= 1 && d.num_payments <= TQF_MAX_SWAPTION_PAYMENTS,
+      TQF_REQUIRE(plan->model.kind == TQF_MODEL_HW1F || plan->model.kind == TQF_MODEL_HJM,
+                  "TQF_PAYOFF_HW_SWAPTION needs the TQF_MODEL_HW1F or TQF_MODEL_HJM model");
+      const int nf = d.num_factors > 0 ? d.num_factors : 1;
+      TQF_REQUIRE(nf == (plan->model.kind == TQF_MODEL_HJM ? plan->info.dim - 1 : 1),
+                  "payoff num_factors does not match the model");
+      TQF_REQUIRE(d.num_payments >= 1 && d.num_payments * nf <= TQF_MAX_SWAPTION_PAYMENTS,
                   "num_payments out of range");
       if (swaptions.empty()) swaptions.resize(TQF_MAX_PAYOFFS);
       SwaptionK& sw = swaptions[q];
       std::memset(&sw, 0, sizeof(sw));
       sw.num_payments = d.num_payments;
       sw.is_payer = d.is_payer;
+      sw.num_factors = nf;
+      for (int j = 0; j < d.num_payments * nf; ++j) sw.g[j] = d.pay_g[j];
       for (int j = 0; j < d.num_payments; ++j) {
-        sw.g[j] = d.pay_g[j];
         sw.k[j] = d.pay_k[j];
         sw.coef[j] = d.pay_coef[j];
       }
@@ -503,7 +530,7 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
   TQF_REQUIRE(model && rng && out_plan, "null argument");
   *out_plan = nullptr;
   ModelInfo info;
-  if (!model_info(model->kind, model->dim, &info)) {
+  if (!model_info(model->kind, model->dim, model->num_factors, &info)) {
     set_error("unknown model kind");
     return TQF_ERR_UNSUPPORTED;
   }

@@ -57,6 +57,8 @@ struct PayoffK {
 struct SwaptionK {
   int32_t num_payments;
   int32_t is_payer;
+  int32_t num_factors;   // g[j * num_factors + i] multiplies state component i
+  int32_t pad;
   double g[TQF_MAX_SWAPTION_PAYMENTS];
   double k[TQF_MAX_SWAPTION_PAYMENTS];
   double coef[TQF_MAX_SWAPTION_PAYMENTS];
@@ -261,6 +263,41 @@ struct HullWhite1FModel {
     x[1] = fma(c[3], x[0], x[1] + c[4]);
   }
 };
+
+// Gaussian / quasi-Gaussian HJM with deterministic volatility (TQF_MODEL_HJM, see
+// tqf.h): F Markov factors and the short-rate integral; NFS normals are consumed
+// per step (the reference's Wiener process also drives the zero-volatility vec(y)
+// components of the quasi-Gaussian state), the first F act.
+template <typename R, int F, int NFS>
+struct HjmModel {
+  using Real = R;
+  static constexpr int DIM = F + 1, NF = NFS, NCOEF = 5 + 2 * F + F * F;
+  __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
+                                              const Real (&c)[NCOEF]) {
+    Real dw[F], xn[F];
+    Real pre = 0, post = 0;
+#pragma unroll
+    for (int j = 0; j < F; ++j) dw[j] = z[j] * c[1];
+#pragma unroll
+    for (int i = 0; i < F; ++i) {
+      const Real drift = c[2 + i] - c[2 + F + i] * x[i];
+      Real diff = 0;
+#pragma unroll
+      for (int j = 0; j < F; ++j) diff = fma(c[2 + 2 * F + i * F + j], dw[j], diff);
+      xn[i] = (x[i] + c[0] * drift) + diff;
+      pre += x[i];
+      post += xn[i];
+    }
+#pragma unroll
+    for (int i = 0; i < F; ++i) x[i] = xn[i];
+    x[F] = x[F] + (c[2 + 2 * F + F * F] * pre + c[3 + 2 * F + F * F] * post + c[4 + 2 * F + F * F]);
+  }
+};
+template <typename R> using HjmModel11 = HjmModel<R, 1, 1>;
+template <typename R> using HjmModel12 = HjmModel<R, 1, 2>;
+template <typename R> using HjmModel22 = HjmModel<R, 2, 2>;
+template <typename R> using HjmModel26 = HjmModel<R, 2, 6>;
+template <typename R> using HjmModel33 = HjmModel<R, 3, 3>;
 
 template <typename R>
 struct HestonEulerModel {  // heston/heston_model.py:143-173; state [X = log S, V]
@@ -913,11 +950,23 @@ path_kernel(const KParams<typename Model::Real> P) {
               double v;
               if (d.kind == TQF_PAYOFF_HW_SWAPTION) {
                 const SwaptionK& sw = P.swaptions[q];
-                const double xs = static_cast<double>(x[a][h][0]);
                 const double integral = static_cast<double>(x[a][h][DIM - 1]);
                 double acc = 0.0;
-                for (int j = 0; j < sw.num_payments; ++j)
-                  acc = fma(sw.coef[j], exp(fma(-sw.g[j], xs, sw.k[j])), acc);
+                if (DIM <= 2 || sw.num_factors == 1) {
+                  const double xs = static_cast<double>(x[a][h][0]);
+                  for (int j = 0; j < sw.num_payments; ++j)
+                    acc = fma(sw.coef[j], exp(fma(-sw.g[j], xs, sw.k[j])), acc);
+                } else {
+                  // several factors (TQF_MODEL_HJM): log P_j = k_j - sum_i g_ji x_i
+                  const int nf = sw.num_factors;
+                  for (int j = 0; j < sw.num_payments; ++j) {
+                    double e = sw.k[j];
+#pragma unroll
+                    for (int i = 0; i < DIM - 1; ++i)
+                      if (i < nf) e = fma(-sw.g[j * nf + i], static_cast<double>(x[a][h][i]), e);
+                    acc = fma(sw.coef[j], exp(e), acc);
+                  }
+                }
                 double swap = exp(-integral) * (1.0 - acc);
                 swap = sw.is_payer ? swap : -swap;
                 v = (swap > 0.0 ? swap : 0.0) * d.scale;

@@ -30,6 +30,7 @@ MODEL_HW1F = 7
 MODEL_AFFINE_ND = 8
 MODEL_AFFINE_1F_TANGENT = 9
 MODEL_MILSTEIN_1F = 10
+MODEL_HJM = 11
 PAYOFF_CALL = 1
 PAYOFF_PUT = 2
 PAYOFF_UP_OUT_CALL = 3
@@ -90,7 +91,8 @@ class PayoffDesc(C.Structure):
       ('num_payments', C.c_int32),
       ('is_payer', C.c_int32),
       ('brownian_bridge', C.c_int32),
-      ('reserved3', C.c_double),
+      ('num_factors', C.c_int32),
+      ('reserved3', C.c_int32),
       ('reserved4', C.c_double),
       ('pay_g', C.c_double * MAX_SWAPTION_PAYMENTS),
       ('pay_k', C.c_double * MAX_SWAPTION_PAYMENTS),
@@ -184,6 +186,9 @@ _SIGNATURES = {
                    C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'tqf_hw_discount_curves':
         (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'tqf_hjm_discount_curves':
+        (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                    C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'tqf_plan_paths_sums':
         (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,

@@ -1,6 +1,7 @@
 """Mirror of `tf_quant_finance.models` for the Monte-Carlo hot path."""
 from tff_b200.models import closures
 from tff_b200.models import euler_sampling
+from tff_b200.models import hjm
 from tff_b200.models import hull_white
 from tff_b200.models import longstaff_schwartz
 from tff_b200.models import milstein_sampling
@@ -15,4 +16,4 @@ from tff_b200.models.ito_process import ItoProcess
 
 __all__ = ['closures', 'euler_sampling', 'milstein_sampling', 'utils', 'GenericItoProcess',
            'GeometricBrownianMotion', 'MultivariateGeometricBrownianMotion', 'HestonModel', 'HullWhiteModel1F', 'VectorHullWhiteModel', 'ItoProcess',
-           'hull_white', 'longstaff_schwartz']
+           'hull_white', 'hjm', 'longstaff_schwartz']
