@@ -223,8 +223,6 @@ def test_halton_host_tables_equal_the_oracle():
         np.testing.assert_array_equal(weights[d, :sizes[d]], [float(p**j) for j in range(sizes[d])])
         assert np.all(weights[d, sizes[d]:] == 1.0)
   assert halton._first_primes(1000)[-1] == 7919
-  with pytest.raises(NotImplementedError):
-    halton.sample(3, num_results=4)                       # randomized=True is the reference's default
   with pytest.raises(ValueError):
     halton.sample(3, randomized=False)
   with pytest.raises(NotImplementedError):
