@@ -339,10 +339,18 @@ class Ctx:
     fn()
     self.barrier()
     t0 = time.perf_counter()
+    per_call = []
     for _ in range(steps):
-      fn()
+      c0 = time.perf_counter()
+      fn()                                   # returns host values: the call is synchronous
+      per_call.append(time.perf_counter() - c0)
     self.barrier()
     dt, = self.max_over_ranks([time.perf_counter() - t0])
+    if max(per_call) > 2.0 * min(per_call) + 1e-3:
+      # one call far off the others (allocator growth, a host hiccup): say so instead of
+      # folding it silently into the mean
+      sys.stderr.write('e2e: uneven calls on rank %d: %s ms\n' % (
+          self.rank, ' '.join('%.3f' % (1e3 * t) for t in per_call)))
     return dt / steps
 
   def peaks(self):
