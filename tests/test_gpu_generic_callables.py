@@ -161,9 +161,6 @@ def test_argument_errors():
   with pytest.raises(ValueError):                                        # odd antithetic count
     sample(1, drift, vol, [1.0], num_samples=11, time_step=0.5, seed=1,
            random_type=tff.math.random.RandomType.PSEUDO_ANTITHETIC, dtype=np.float64)
-  with pytest.raises(NotImplementedError):
-    sample(1, drift, vol, [1.0], time_step=0.5, seed=1, dtype=np.float64,
-           random_type=tff.math.random.RandomType.HALTON_RANDOMIZED)
   with pytest.raises(NotImplementedError):                               # not affine
     sample(1, lambda t, x: torch.sin(x), vol, [1.0], time_step=0.5, seed=1, dtype=np.float64)
   with pytest.raises(NotImplementedError):
