@@ -572,8 +572,6 @@ def test_uniform_argument_errors():
     tff.math.random.uniform(2, [4], random_type=rt.STATELESS)
   with pytest.raises(NotImplementedError):
     tff.math.random.uniform(2, [4], random_type=rt.PSEUDO_ANTITHETIC, seed=1)
-  with pytest.raises(NotImplementedError):
-    tff.math.random.uniform(2, [4], random_type=rt.HALTON_RANDOMIZED, seed=1)
 
 
 # ----- stateless_random_shuffle (math/random_ops/stateless.py:24-52; stateless_test.py:29-125)
