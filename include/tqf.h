@@ -198,6 +198,62 @@ int tqf_sobol_fill(const int32_t* direction_numbers, int dim,
                    void* stream);
 
 /* ------------------------------------------------------------------------
+ * tff.math.qmc: digital nets, Sobol generating matrices, lattice rules.
+ * ---------------------------------------------------------------------- */
+
+/* tf.random.stateless_uniform(shape, seed, minval, maxval, dtype=int32|int64)
+ * as `_random_stateless_uniform` calls it (math/qmc/digital_net.py:155-202,
+ * behind random_digital_shift 45-95 and random_scrambling_matrices 98-152):
+ * `minval + x % (maxval - minval)` on the uint32 words (int_bits 32, four per
+ * Philox call) or on uint64 pairs of words (int_bits 64).  out_dev is
+ * int32 / int64 [num_elements].                                             */
+int tqf_philox_uniform_int_fill(const uint32_t key[2], const uint32_t counter[4],
+                                int64_t minval, int64_t maxval, uint64_t num_elements,
+                                int int_bits, void* out_dev, void* stream);
+
+/* `sobol_generating_matrices(dim, num_results, num_digits)`
+ * (math/qmc/sobol.py:132-218, 221-243, 246-395) from the Joe-Kuo table in the
+ * layout of tqf_sobol_direction_numbers; out is host int64
+ * [dim][log_num_results], row 0 the identity.  Host only.                    */
+int tqf_qmc_sobol_generating_matrices(const uint32_t* poly_a, const uint8_t* degree,
+                                      const uint32_t* m_init, int num_rows, int dim,
+                                      int log_num_results, int num_digits, int64_t* out);
+
+/* `scramble_generating_matrices` (math/qmc/digital_net.py:422-527): column c of
+ * coordinate d becomes XOR over the set bits (num_digits-1-shift) of G[d][c] of
+ * S[d][shift] >> shift.  Host int64 [dim][num_columns] / [dim][scrambling_columns]
+ * in, [dim][num_columns] out.  Host only.                                    */
+int tqf_qmc_scramble_generating_matrices(const int64_t* generating_matrices,
+                                         const int64_t* scrambling_matrices, int dim,
+                                         int num_columns, int scrambling_columns, int num_digits,
+                                         int64_t* out);
+
+/* `digital_net_sample` (math/qmc/digital_net.py:205-419): point i, coordinate d
+ * = real(shift[d] XOR_{bit b of index_i set, b < log_num_results} G[d][b]) /
+ * real(1 << num_digits), optionally tent-transformed (utils.py:94-117).
+ *   generating_matrices: host int64 [dim][num_columns] (already scrambled);
+ *   digital_shift: host int64 [dim] or NULL;
+ *   sequence_indices_dev: DEVICE int64 [count] or NULL for first_index + i;
+ *   int_bits: 32 / 64 = the reference's int_dtype (integer wrap-around and the
+ *   integer -> real cast follow it); dtype: TQF_F32 / TQF_F64.
+ * out_dev is dtype [count][dim] row-major.  Synchronises `stream`.           */
+int tqf_qmc_digital_net_fill(const int64_t* generating_matrices, int dim, int num_columns,
+                             int log_num_results, const int64_t* digital_shift,
+                             const int64_t* sequence_indices_dev, uint64_t first_index,
+                             uint64_t count, int num_digits, int int_bits,
+                             int apply_tent_transform, int dtype, void* out_dev, void* stream);
+
+/* `lattice_rule_sample` (math/qmc/lattice_rule.py:99-229): floormod(real(i) *
+ * floormod(z_d / n, 1) + shift_d, 1) with every product and sum rounded on its
+ * own, as TensorFlow's element-wise ops are.  generating_vectors: host int64
+ * [dim]; additive_shift: host double [dim] or NULL; indices as above.
+ * Synchronises `stream`.                                                    */
+int tqf_qmc_lattice_rule_fill(const int64_t* generating_vectors, int dim, int64_t num_results,
+                              const double* additive_shift, const int64_t* sequence_indices_dev,
+                              uint64_t first_index, uint64_t count, int int_bits,
+                              int apply_tent_transform, int dtype, void* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------
  * The path engine: replaces the device work of
  *   models/euler_sampling.py:335-537  (_sample, _while_loop, _euler_step)
  *   models/utils.py:20-128            (generate_mc_normal_draws)

@@ -162,6 +162,19 @@ _SIGNATURES = {
     'tqf_sobol_fill':
         (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
                    C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'tqf_philox_uniform_int_fill':
+        (C.c_int, [_u32p, _u32p, C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
+    'tqf_qmc_sobol_generating_matrices':
+        (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                   C.c_void_p]),
+    'tqf_qmc_scramble_generating_matrices':
+        (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'tqf_qmc_digital_net_fill':
+        (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
+                   C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'tqf_qmc_lattice_rule_fill':
+        (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'tqf_plan_create':
         (C.c_int, [C.POINTER(ModelDesc), C.POINTER(RngDesc), C.c_uint64,
                    C.POINTER(C.c_void_p)]),
