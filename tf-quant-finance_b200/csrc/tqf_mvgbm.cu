@@ -396,6 +396,8 @@ static void build_split(const double* chol, const double* mu, const double* sigm
 
 static void build_mma(const double* chol, const double* mu, const double* sigma, int dim,
                       std::vector<float>* out);
+static void build_tc5(const double* chol, const double* mu, const double* sigma, int dim,
+                      std::vector<float>* out);
 
 int mvgbm_upload_split(const double* chol, const double* mu, const double* sigma, int dim,
                        int dtype, void** out_dev) {
@@ -409,7 +411,9 @@ int mvgbm_upload_split(const double* chol, const double* mu, const double* sigma
   } else {
     std::vector<float> host, mma;
     build_split<float>(chol, mu, sigma, dim, &host);
-    build_mma(chol, mu, sigma, dim, &mma);   // tensor-core kernel's tables follow
+    build_mma(chol, mu, sigma, dim, &mma);   // tensor-core kernels' tables follow
+    host.insert(host.end(), mma.begin(), mma.end());
+    build_tc5(chol, mu, sigma, dim, &mma);
     host.insert(host.end(), mma.begin(), mma.end());
     TQF_CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(float)));
     e = cudaMemcpy(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -1055,6 +1059,369 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// float32, Sobol, dim == 64, fused price: the same contraction on the 5th-generation
+// tensor cores (tcgen05.mma.kind::tf32, accumulator in tensor memory).
+//
+//   * a CTA of 128 threads owns a tile of 128 consecutive Sobol indices; thread t
+//     IS path t: TMEM lane t holds row t of the A operand (its 64 scaled normals)
+//     and row t of the accumulator (its 64 increments); the state x[64] stays in
+//     the thread's registers for all steps -- no fragment layouts, no shuffles;
+//   * per step a thread draws its 64 normals (16 side by side), scales them by
+//     sqrt(dt), splits them into TF32 hi / lo parts and writes them to TMEM with
+//     tcgen05.st (32x32b.x16); column 64 of A carries dt (hi / lo), so that the
+//     drift mu_i dt comes out of the same contraction (row 64 of B = mu);
+//   * B = (diag(sigma) L)^T, hi and lo parts, sits in shared memory for the whole
+//     kernel in the canonical K-major no-swizzle UMMA layout (8 x 16-byte core
+//     matrices, LBO = 1024 B between K chunks, SBO = 128 B between row groups);
+//   * one thread issues 27 MMAs (128 x 64 x 8 each): A_lo B_hi, A_hi B_lo, A_hi B_hi
+//     (9 K slices each), tcgen05.commit -> mbarrier; every thread then reads its row of
+//     the accumulator with tcgen05.ld and applies x += x f (or x += f);
+//   * the Sobol integers are T[d][lane] ^ H[d][warp]: T = the 32 combinations of the
+//     direction words of index bits 0-4, H = index bits 5-6 (the warp) and the tile's
+//     high bits, both staged in shared memory one step ahead (double buffered).
+// Two CTAs per SM (256 of the 512 TMEM columns each): while one waits for its
+// MMAs the other draws.
+constexpr int kT5Threads = 128;
+constexpr int kT5K = 72;                              // 64 factors + dt column, padded to 8
+constexpr int kT5PartBytes = (kT5K / 4) * 1024;       // one part (hi or lo) of B
+constexpr int kT5BWords = 2 * kT5PartBytes / 4;
+constexpr int kT5TmemCols = 256;
+constexpr uint32_t kT5ColD = 0, kT5ColAh = 64, kT5ColAl = 64 + kT5K;
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1),
+// A = B = TF32 (bits 7-9, 10-12 = 2), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kT5Idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int kT5SmemB = 0;
+constexpr int kT5SmemTab = kT5SmemB + 2 * kT5PartBytes;
+constexpr int kT5SmemT = kT5SmemTab + kNdTabSmemBytes;             // 2 x [64][32] words
+constexpr int kT5SmemH = kT5SmemT + 2 * 64 * 32 * 4;               // 2 x [4][64] words
+constexpr int kT5SmemAcc = kT5SmemH + 2 * 4 * 64 * 4;              // [4][MAX_PAYOFFS * 3] doubles
+constexpr int kT5SmemBar = kT5SmemAcc + 4 * TQF_MAX_PAYOFFS * 3 * 8;
+constexpr int kT5SmemBytes = kT5SmemBar + 16;
+
+// Host: B[k][n] = sigma_n L_nk (k < 64), mu_n (k = 64), 0 beyond; element (n, k) of a part at
+// float index (k / 4) * 256 + n * 4 + k % 4.
+static void build_tc5(const double* chol, const double* mu, const double* sigma, int dim,
+                      std::vector<float>* out) {
+  out->assign(kT5BWords, 0.0f);
+  uint32_t* w = reinterpret_cast<uint32_t*>(out->data());
+  for (int n = 0; n < kMvDim; ++n)
+    for (int k = 0; k < kT5K; ++k) {
+      float v = 0.0f;
+      if (n < dim && k < dim && k <= n) v = static_cast<float>(sigma[n] * chol[static_cast<size_t>(n) * dim + k]);
+      if (n < dim && k == kMvDim) v = static_cast<float>(mu[n]);
+      const uint32_t hb = tf32_round_bits(v);
+      float hf;
+      std::memcpy(&hf, &hb, 4);
+      const int at = (k / 4) * 256 + n * 4 + (k % 4);
+      w[at] = hb;
+      w[kT5PartBytes / 4 + at] = tf32_round_bits(v - hf);
+    }
+}
+
+__device__ __forceinline__ void t5_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kT5Idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void t5_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15, %16};\n"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+        "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+        "r"(v[15])
+      : "memory");
+}
+
+__device__ __forceinline__ void t5_st8(uint32_t taddr, uint32_t v0) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %2, %2, %2, %2, %2, %2};\n"
+               :
+               : "r"(taddr), "r"(v0), "r"(z)
+               : "memory");
+}
+
+__device__ __forceinline__ void t5_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Bounded wait: a protocol error traps (the launch fails) instead of hanging the device.
+__device__ __forceinline__ void t5_mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+// Stages step s of the tile whose paths have index >> 7 == high_bits: sT[d][l] = XOR of the
+// direction words of the set bits of l (index bits 0-4), sH[w][d] = index bits 5-6 = w and the
+// high bits.  Eight lanes per dimension read its 32 direction words as one coalesced 128 bytes.
+__device__ __forceinline__ void t5_stage(const uint32_t* __restrict__ sobol_v, int s,
+                                         uint32_t high_bits, uint32_t* sT, uint32_t* sH, int tid) {
+  const int q = tid & 7, lane = tid & 31, base_lane = lane & ~7;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int dd = it * 16 + (tid >> 3);
+    const uint4 w =
+        __ldg(reinterpret_cast<const uint4*>(sobol_v + (static_cast<size_t>(s) * kMvDim + dd) * 32) + q);
+    const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
+    uint32_t h = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = 4 * q + j;                 // index bit of this word
+      const uint32_t bit = b >= 7 ? (high_bits >> (b - 7)) & 1u : 0u;
+      h ^= wv[j] & (0u - bit);
+    }
+    h ^= __shfl_xor_sync(0xFFFFFFFFu, h, 1);
+    h ^= __shfl_xor_sync(0xFFFFFFFFu, h, 2);
+    h ^= __shfl_xor_sync(0xFFFFFFFFu, h, 4);
+    const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, w.x, base_lane);
+    const uint32_t v1 = __shfl_sync(0xFFFFFFFFu, w.y, base_lane);
+    const uint32_t v2 = __shfl_sync(0xFFFFFFFFu, w.z, base_lane);
+    const uint32_t v3 = __shfl_sync(0xFFFFFFFFu, w.w, base_lane);
+    const uint32_t v4 = __shfl_sync(0xFFFFFFFFu, w.x, base_lane + 1);
+    const uint32_t v5 = __shfl_sync(0xFFFFFFFFu, w.y, base_lane + 1);
+    const uint32_t v6 = __shfl_sync(0xFFFFFFFFu, w.z, base_lane + 1);
+    // entries l = 4 q + {0, 1, 2, 3}: bits 2, 3, 4 of l are the bits of q
+    const uint32_t e = (v2 & (0u - (q & 1u))) ^ (v3 & (0u - ((q >> 1) & 1u))) ^ (v4 & (0u - ((q >> 2) & 1u)));
+    *reinterpret_cast<uint4*>(sT + dd * 32 + 4 * q) = make_uint4(e, e ^ v0, e ^ v1, e ^ v0 ^ v1);
+    if (q < 4) sH[q * kMvDim + dd] = h ^ (v5 & (0u - (q & 1u))) ^ (v6 & (0u - ((q >> 1) & 1u)));
+  }
+}
+
+__global__ void __launch_bounds__(kT5Threads, 2)
+mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
+  extern __shared__ __align__(1024) unsigned char t5_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* sB = reinterpret_cast<uint32_t*>(t5_smem + kT5SmemB);
+  uint32_t* sT = reinterpret_cast<uint32_t*>(t5_smem + kT5SmemT);
+  uint32_t* sH = reinterpret_cast<uint32_t*>(t5_smem + kT5SmemH);
+  double* s_acc = reinterpret_cast<double*>(t5_smem + kT5SmemAcc);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(t5_smem + kT5SmemBar);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t5_smem + kT5SmemBar + 8);
+  const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(t5_smem));
+  const uint32_t bar = smem_base + kT5SmemBar;
+
+  // ---- one-time set-up: B, the inverse-CDF table, the barrier, tensor memory
+  const float* tabp = P.lsplit + kMvParts * kMvSplitStride + kMmaTabWords;
+  for (int i = tid; i < kT5BWords / 4; i += kT5Threads)
+    reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(tabp) + i);
+  {
+    uint4* dst = reinterpret_cast<uint4*>(t5_smem + kT5SmemTab);
+    for (int i = tid; i < kNdTabRows * 8; i += kT5Threads) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(P.ndtab) + (i >> 3));
+      if ((i >> 3) == 0 && P.sobol_clamp) v.x = __float_as_uint(5.4199314f);
+      dst[i] = v;
+    }
+  }
+  for (int i = tid; i < 4 * TQF_MAX_PAYOFFS * 3; i += kT5Threads) s_acc[i] = 0.0;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                 :
+                 : "r"(smem_base + kT5SmemBar + 8), "r"(kT5TmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  // B was written through the generic proxy; the tensor core reads it through the async proxy
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *s_tmem;
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);   // this warp's lanes
+  const uint32_t tab_lane = smem_base + kT5SmemTab + (lane & 7) * 16 - kNdTabBase * 128u;
+  // shared-memory matrix descriptor of B (cute::UMMA::SmemDescriptor): start >> 4,
+  // LBO = 1024 B (K chunks) at bit 16, SBO = 128 B (8-row groups) at bit 32, version 1 at bit 46
+  const uint64_t b_desc = static_cast<uint64_t>(((smem_base + kT5SmemB) & 0x3FFFFu) >> 4) |
+                          (static_cast<uint64_t>(1024 >> 4) << 16) |
+                          (static_cast<uint64_t>(128 >> 4) << 32) | (1ull << 46);
+
+  const uint64_t chunk_base = P.first_index & ~static_cast<uint64_t>(kT5Threads - 1);
+  const uint64_t num_chunks =
+      (P.first_index + P.path_count - chunk_base + kT5Threads - 1) / kT5Threads;
+  uint32_t phase = 0;
+
+  for (uint64_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
+    const uint64_t tile_index = chunk_base + chunk * kT5Threads;
+    const uint64_t index = tile_index + tid;
+    const bool valid = index >= P.first_index && index < P.first_index + P.path_count;
+    const uint32_t high_bits = static_cast<uint32_t>(tile_index >> 7);
+    float x[kMvDim];
+#pragma unroll
+    for (int i = 0; i < kMvDim; ++i) x[i] = P.x0[i];
+
+    auto record = [&](int step_index) {
+      const int dim = P.dim;
+      for (int pq = 0; pq < P.num_payoffs; ++pq) {
+        const PayoffK& d = P.pay[pq];
+        if (d.step != step_index) continue;
+        float m = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kMvDim; ++i) {
+          const bool take = d.component < 0 ? i < dim : i == d.component;
+          m += take ? x[i] : 0.0f;
+        }
+        if (d.component < 0) m = m / static_cast<float>(dim);
+        double sum = 0.0, sq = 0.0, bad = 0.0;
+        if (valid) {
+          const double v = eval_payoff(d, static_cast<double>(m), 0.0, 0.0);
+          if (isfinite(v)) {
+            sum = v;
+            sq = v * v;
+          } else {
+            bad = 1.0;
+          }
+        }
+        sum = warp_sum(sum);
+        sq = warp_sum(sq);
+        bad = warp_sum(bad);
+        if (lane == 0) {
+          double* acc = s_acc + (warp * TQF_MAX_PAYOFFS + pq) * 3;
+          acc[0] += sum;
+          acc[1] += sq;
+          acc[2] += bad;
+        }
+      }
+    };
+    if (P.record_slot[0] >= 0) record(0);
+
+    __syncthreads();                       // every reader of the staging buffers is done
+    t5_stage(P.sobol_v, 0, high_bits, sT, sH, tid);
+    __syncthreads();
+
+#pragma unroll 1
+    for (int s = 0; s < P.num_steps; ++s) {
+      const int buf = s & 1;
+      const uint32_t* sTb = sT + buf * (kMvDim * 32);
+      const uint32_t* sHb = sH + buf * (4 * kMvDim) + warp * kMvDim;
+      const float dt = P.coef[2 * s], sqdt = P.coef[2 * s + 1];
+      // ---- the 64 scaled normals of this path -> A (hi / lo) in tensor memory
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t xb[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const uint4 hw = *reinterpret_cast<const uint4*>(sHb + c * 16 + i4 * 4);
+          xb[i4 * 4 + 0] = sTb[(c * 16 + i4 * 4 + 0) * 32 + lane] ^ hw.x;
+          xb[i4 * 4 + 1] = sTb[(c * 16 + i4 * 4 + 1) * 32 + lane] ^ hw.y;
+          xb[i4 * 4 + 2] = sTb[(c * 16 + i4 * 4 + 2) * 32 + lane] ^ hw.z;
+          xb[i4 * 4 + 3] = sTb[(c * 16 + i4 * 4 + 3) * 32 + lane] ^ hw.w;
+        }
+        float z[16];
+        sobol_normals_f32_tab<16>(xb, z, tab_lane);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float zs = z[i] * sqdt;
+          hi[i] = tf32_rna(zs);
+          lo[i] = __float_as_uint(zs - __uint_as_float(hi[i]));
+        }
+        t5_st16(t_lane + kT5ColAh + c * 16, hi);
+        t5_st16(t_lane + kT5ColAl + c * 16, lo);
+      }
+      {
+        const uint32_t dh = tf32_rna(dt);
+        t5_st8(t_lane + kT5ColAh + kMvDim, dh);
+        t5_st8(t_lane + kT5ColAl + kMvDim, __float_as_uint(dt - __uint_as_float(dh)));
+      }
+      // ---- the tables of the next step, while this step's stores drain
+      if (s + 1 < P.num_steps)
+        t5_stage(P.sobol_v, s + 1, high_bits, sT + (buf ^ 1) * (kMvDim * 32),
+                 sH + (buf ^ 1) * (4 * kMvDim), tid);
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        // small terms first: A_lo B_hi, A_hi B_lo, A_hi B_hi (one K = 8 slice = 2 chunks = 2 KB of B)
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+          t5_mma(tmem + kT5ColD, tmem + kT5ColAl + 8 * j, b_desc + ((j * 2048) >> 4), j > 0);
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+          t5_mma(tmem + kT5ColD, tmem + kT5ColAh + 8 * j, b_desc + ((kT5PartBytes + j * 2048) >> 4), 1u);
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+          t5_mma(tmem + kT5ColD, tmem + kT5ColAh + 8 * j, b_desc + ((j * 2048) >> 4), 1u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                     :
+                     : "r"(bar)
+                     : "memory");
+      }
+      t5_mbar_wait(bar, phase);
+      phase ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      // ---- f_i = sqrt_dt sum_k sigma_i L_ik z_k + mu_i dt; Euler x += x f, exact log step x += f
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float f[16];
+        t5_ld16(t_lane + kT5ColD + c * 16, f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          x[c * 16 + i] = P.exact_log ? x[c * 16 + i] + f[i] : fmaf(x[c * 16 + i], f[i], x[c * 16 + i]);
+      }
+      if (P.record_slot[s + 1] >= 0) record(s + 1);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kT5TmemCols)
+                 : "memory");
+  }
+  for (int i = tid; i < TQF_MAX_PAYOFFS * 3; i += kT5Threads) {
+    const int q = i / 3, k = i - q * 3;
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) v += s_acc[w * TQF_MAX_PAYOFFS * 3 + i];
+    P.partials[(static_cast<size_t>(blockIdx.x) * TQF_MAX_PAYOFFS + q) * 4 + k] = v;
+  }
+}
+
+// TQF_MVGBM_TC5=0 falls back to the mma.sync kernel (kept for the A/B and for dim < 64,
+// path materialisation and non-Sobol draws, which the tcgen05 kernel does not cover).
+static bool tc5_enabled() {
+  const char* e = std::getenv("TQF_MVGBM_TC5");   // read per launch: tests toggle it
+  return e && e[0] == '1';
+}
+
 static bool mma_enabled() {
   static const bool on = [] {
     const char* e = std::getenv("TQF_MVGBM_MMA");
@@ -1127,6 +1494,22 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
     if (grid < 1) grid = 1;
     *grid_out = grid;
     if constexpr (sizeof(Real) == 4 && DMAX == kMvDim) {
+      if (a.rngk == RNGK_SOBOL && a.dim == kMvDim && a.mode == MODE_PRICE && a.ndtab != nullptr &&
+          tc5_enabled()) {
+        P.ndtab = a.ndtab;
+        const uint64_t base128 = a.first_index & ~static_cast<uint64_t>(kT5Threads - 1);
+        const uint64_t chunks128 =
+            (a.first_index + a.path_count - base128 + kT5Threads - 1) / kT5Threads;
+        int g5 = static_cast<int>(chunks128 < static_cast<uint64_t>(2 * kSMs) ? chunks128 : 2 * kSMs);
+        if (g5 < 1) g5 = 1;
+        if (g5 > a.max_grid) g5 = a.max_grid;      // partials hold max_grid rows
+        *grid_out = g5;
+        TQF_CUDA_OK(cudaFuncSetAttribute(mvgbm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kT5SmemBytes));
+        mvgbm_tc5_kernel<<<g5, kT5Threads, kT5SmemBytes, stream>>>(P);
+        TQF_CUDA_OK(cudaGetLastError());
+        return TQF_OK;
+      }
       if (a.rngk == RNGK_SOBOL && mma_enabled()) {
         static const bool tab = [] {
           const char* e = std::getenv("TQF_MVGBM_NDTRI_TAB");
