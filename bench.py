@@ -40,7 +40,13 @@ UNIT = 'path-steps/s'
 
 # Algorithmic FP-pipe instructions per path-step (SURVEY.md 8(d);
 # frozen in roofline.json -- SURVEY allows them to be tightened only downward).
-ALGO_INSTR = {'c1': 16, 'c2': 79, 'c2_qe': 79, 'c3': 29, 'c4': 3616, 'c5': 22}
+ALGO_INSTR = {'c1': 16, 'c2': 79, 'c2_qe': 79, 'c3': 29, 'c4': 1408, 'c5': 22}
+# C4 is bound by the issue slots (and, next to them, the shared-memory pipe), not by one
+# FP pipe: its contraction runs on the tensor cores.  A(C4) = 64 draws x 22 thread-instructions
+# of ANY pipe (Sobol word 2.25, table inverse CDF 14, scale 1, TF32 split 3, update 1, staging
+# 0.75), tightened down from SURVEY's 3616 FP32-pipe instructions (2080 of them were the
+# mat-vec FMAs, 64 x 6 the polynomial inverse CDF); peak = issue rate = the FFMA rate.
+ISSUE_BOUND = ('c4',)
 
 WORKLOADS = {
     'c1': dict(name='C1 GBM call (log-space affine), 100k paths x 100 steps, fp64, PSEUDO_ANTITHETIC seed 42',
@@ -371,6 +377,16 @@ def _fp_roofline(ctx, name, per_gpu_rate, note=''):
     traffic = json.load(open(os.path.join(ROOT, 'roofline.json'))).get(name, {}).get('ncu', {}).get('dram_bytes')
   except Exception:  # pylint: disable=broad-except
     pass
+  if name in ISSUE_BOUND:
+    return {'bound': 'issue', 'achieved': achieved, 'peak': peak,
+            'unit': 'G thread-instr/s (all pipes)', 'frac': achieved / peak,
+            'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu capture named in roofline.json)',
+            'note': 'achieved = path-steps/s/GPU x %d algorithmic thread-instructions per path-step '
+                    '(roofline.json: draws, TF32 split and update; the [128 x 72] x [72 x 64] '
+                    'contraction per tile and step runs on the tensor pipe: tcgen05.mma.kind::tf32, '
+                    'ncu sm__pipe_tensor_cycles_active 20 %%); peak = issue slots = 128 lanes/clk/SM, '
+                    'measured live as the FFMA rate by tqf_measure_fp64_peak; no per-path HBM '
+                    'traffic%s' % (algo, note)}
   return {'bound': 'fp32' if fp32 else 'fp64', 'achieved': achieved, 'peak': peak,
           'unit': 'G %s-pipe instr/s' % ('FP32' if fp32 else 'FP64'), 'frac': achieved / peak,
           'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu capture named in roofline.json)',
@@ -536,6 +552,25 @@ def run_fused(ctx, name, steps, warmup, with_e2e=True, sample_clocks=False):
                           'ms_per_step': ms_c}
       except (AttributeError, RuntimeError) as e:
         res['clamped'] = {'unavailable': str(e)}
+      finally:
+        try:
+          w.plan.set_sobol_clamp(False)
+        except (AttributeError, RuntimeError):
+          pass
+      # A/B: the same plan on the mma.sync (legacy HMMA) kernel the tcgen05 kernel replaced
+      res['kernel'] = 'mvgbm_tc5_kernel (tcgen05.mma.kind::tf32, A and accumulator in tensor memory)'
+      old_env = os.environ.get('TQF_MVGBM_TC5')
+      os.environ['TQF_MVGBM_TC5'] = '0'
+      try:
+        ms_l, _, _, sums_l = ctx.timed(w.step, max(1, min(steps, 2)), 1)
+        sl = sums_l.cpu().numpy()
+        res['mma_sync_kernel'] = {'ms_per_step': ms_l, 'price': float(sl[0, 0] / w.n),
+                                  'non_finite_paths': float(sl[0, 2])}
+      finally:
+        if old_env is None:
+          del os.environ['TQF_MVGBM_TC5']
+        else:
+          os.environ['TQF_MVGBM_TC5'] = old_env
     res['wall_s_timed_region'] = wall
     if clocks is not None:
       res['clocks'] = clocks

@@ -1063,11 +1063,13 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
 // float32, Sobol, dim == 64, fused price: the same contraction on the 5th-generation
 // tensor cores (tcgen05.mma.kind::tf32, accumulator in tensor memory).
 //
-//   * a CTA of 128 threads owns a tile of 128 consecutive Sobol indices; thread t
-//     IS path t: TMEM lane t holds row t of the A operand (its 64 scaled normals)
-//     and row t of the accumulator (its 64 increments); the state x[64] stays in
-//     the thread's registers for all steps -- no fragment layouts, no shuffles;
-//   * per step a thread draws its 64 normals (16 side by side), scales them by
+//   * a CTA owns a tile of 128 consecutive Sobol indices; path p IS TMEM lane p: it
+//     holds row p of the A operand (the 64 scaled normals) and row p of the
+//     accumulator (the 64 increments).  Two threads carry a path -- warps 0-3 its
+//     factors / assets 0-31, warps 4-7 the other 32 (both reach lanes 32 (w % 4) ..)
+//     -- with their half of the state in registers for all steps: no fragment
+//     layouts, no shuffles, 8 warps per CTA for the same tensor memory;
+//   * per step a thread draws its 32 normals (16 side by side), scales them by
 //     sqrt(dt), splits them into TF32 hi / lo parts and writes them to TMEM with
 //     tcgen05.st (32x32b.x16); column 64 of A carries dt (hi / lo), so that the
 //     drift mu_i dt comes out of the same contraction (row 64 of B = mu);
@@ -1082,7 +1084,9 @@ mvgbm_mma_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
 //     high bits, both staged in shared memory one step ahead (double buffered).
 // Two CTAs per SM (256 of the 512 TMEM columns each): while one waits for its
 // MMAs the other draws.
-constexpr int kT5Threads = 128;
+constexpr int kT5Paths = 128;                         // paths per tile = TMEM lanes
+constexpr int kT5Threads = 256;                       // two threads per path, 32 factors each
+constexpr int kT5Half = kMvDim / 2;
 constexpr int kT5K = 72;                              // 64 factors + dt column, padded to 8
 constexpr int kT5PartBytes = (kT5K / 4) * 1024;       // one part (hi or lo) of B
 constexpr int kT5BWords = 2 * kT5PartBytes / 4;
@@ -1094,9 +1098,11 @@ constexpr uint32_t kT5Idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) <
 constexpr int kT5SmemB = 0;
 constexpr int kT5SmemTab = kT5SmemB + 2 * kT5PartBytes;
 constexpr int kT5SmemT = kT5SmemTab + kNdTabSmemBytes;             // 2 x [64][32] words
-constexpr int kT5SmemH = kT5SmemT + 2 * 64 * 32 * 4;               // 2 x [4][64] words
-constexpr int kT5SmemAcc = kT5SmemH + 2 * 4 * 64 * 4;              // [4][MAX_PAYOFFS * 3] doubles
-constexpr int kT5SmemBar = kT5SmemAcc + 4 * TQF_MAX_PAYOFFS * 3 * 8;
+constexpr int kT5HStride = kMvDim + 8;                // +8: the four warp variants of a dimension land in different banks
+constexpr int kT5SmemH = kT5SmemT + 2 * 64 * 32 * 4;               // 2 x [4][72] words
+constexpr int kT5SmemAcc = kT5SmemH + 2 * 4 * kT5HStride * 4;              // [4][MAX_PAYOFFS * 3] doubles
+constexpr int kT5SmemPart = kT5SmemAcc + 4 * TQF_MAX_PAYOFFS * 3 * 8;   // [128] floats
+constexpr int kT5SmemBar = kT5SmemPart + kT5Paths * 4;
 constexpr int kT5SmemBytes = kT5SmemBar + 16;
 
 // Host: B[k][n] = sigma_n L_nk (k < 64), mu_n (k = 64), 0 beyond; element (n, k) of a part at
@@ -1120,7 +1126,7 @@ static void build_tc5(const double* chol, const double* mu, const double* sigma,
 }
 
 __device__ __forceinline__ void t5_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                       uint32_t accumulate) {
+                                       uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -1128,8 +1134,24 @@ __device__ __forceinline__ void t5_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}\n"
       :
-      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kT5Idesc), "r"(accumulate)
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// One term (A part at a_col, B part at byte offset b_off) of a step: K slices 0..7 of the
+// factors and slice 8 = the dt column.  The factor is lower triangular: slice j (factors
+// 8 j .. 8 j + 7) only moves assets n >= 8 j, so it runs on the columns 16 (j / 2) .. 63 of
+// the accumulator (N = 64, 64, 48, 48, 32, 32, 16, 16: 5/8 of the tensor-pipe time; N must be
+// a multiple of 16 at M = 128).  `fresh`: the first slice overwrites the accumulator.
+__device__ __forceinline__ void t5_term(uint32_t tmem, uint32_t a_col, uint64_t b_desc, uint32_t b_off,
+                                        bool fresh) {
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const int n0 = j < 8 ? 16 * (j / 2) : 0;
+    const uint32_t idesc = (kT5Idesc & ~(0x3Fu << 17)) | (static_cast<uint32_t>((kMvDim - n0) >> 3) << 17);
+    t5_mma(tmem + kT5ColD + n0, tmem + a_col + 8 * j, b_desc + ((b_off + j * 2048 + n0 * 16) >> 4), idesc,
+           (fresh && j == 0) ? 0u : 1u);
+  }
 }
 
 __device__ __forceinline__ void t5_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -1187,15 +1209,29 @@ __device__ __forceinline__ void t5_mbar_wait(uint32_t bar, uint32_t parity) {
 
 // Stages step s of the tile whose paths have index >> 7 == high_bits: sT[d][l] = XOR of the
 // direction words of the set bits of l (index bits 0-4), sH[w][d] = index bits 5-6 = w and the
-// high bits.  Eight lanes per dimension read its 32 direction words as one coalesced 128 bytes.
-__device__ __forceinline__ void t5_stage(const uint32_t* __restrict__ sobol_v, int s,
-                                         uint32_t high_bits, uint32_t* sT, uint32_t* sH, int tid) {
+// high bits.  Eight lanes per dimension read its 32 direction words as one coalesced 128 bytes
+// (t5_stage_load, issued early: the words come from L2) and combine them with shuffles.
+constexpr int kT5StageIters = kMvDim * 8 / kT5Threads;
+struct T5Words {
+  uint4 w[kT5StageIters];
+};
+__device__ __forceinline__ T5Words t5_stage_load(const uint32_t* __restrict__ sobol_v, int s, int tid) {
+  T5Words r;
+#pragma unroll
+  for (int it = 0; it < kT5StageIters; ++it) {
+    const int dd = it * (kT5Threads / 8) + (tid >> 3);
+    r.w[it] = __ldg(reinterpret_cast<const uint4*>(sobol_v + (static_cast<size_t>(s) * kMvDim + dd) * 32) +
+                    (tid & 7));
+  }
+  return r;
+}
+__device__ __forceinline__ void t5_stage_write(const T5Words& r, uint32_t high_bits, uint32_t* sT,
+                                               uint32_t* sH, int tid) {
   const int q = tid & 7, lane = tid & 31, base_lane = lane & ~7;
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int dd = it * 16 + (tid >> 3);
-    const uint4 w =
-        __ldg(reinterpret_cast<const uint4*>(sobol_v + (static_cast<size_t>(s) * kMvDim + dd) * 32) + q);
+  for (int it = 0; it < kT5StageIters; ++it) {
+    const int dd = it * (kT5Threads / 8) + (tid >> 3);
+    const uint4 w = r.w[it];
     const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
     uint32_t h = 0;
 #pragma unroll
@@ -1217,19 +1253,26 @@ __device__ __forceinline__ void t5_stage(const uint32_t* __restrict__ sobol_v, i
     // entries l = 4 q + {0, 1, 2, 3}: bits 2, 3, 4 of l are the bits of q
     const uint32_t e = (v2 & (0u - (q & 1u))) ^ (v3 & (0u - ((q >> 1) & 1u))) ^ (v4 & (0u - ((q >> 2) & 1u)));
     *reinterpret_cast<uint4*>(sT + dd * 32 + 4 * q) = make_uint4(e, e ^ v0, e ^ v1, e ^ v0 ^ v1);
-    if (q < 4) sH[q * kMvDim + dd] = h ^ (v5 & (0u - (q & 1u))) ^ (v6 & (0u - ((q >> 1) & 1u)));
+    if (q < 4) sH[q * kT5HStride + dd] = h ^ (v5 & (0u - (q & 1u))) ^ (v6 & (0u - ((q >> 1) & 1u)));
   }
+}
+__device__ __forceinline__ void t5_stage(const uint32_t* __restrict__ sobol_v, int s,
+                                         uint32_t high_bits, uint32_t* sT, uint32_t* sH, int tid) {
+  t5_stage_write(t5_stage_load(sobol_v, s, tid), high_bits, sT, sH, tid);
 }
 
 __global__ void __launch_bounds__(kT5Threads, 2)
 mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
   extern __shared__ __align__(1024) unsigned char t5_smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // thread = (path p of the tile, half h of its factors / assets): warps 0-3 are half 0,
+  // warps 4-7 half 1; warp w reaches TMEM lanes 32 (w % 4) .. + 31 = its paths
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pw = warp & 3, half = warp >> 2;
+  const int p = tid & (kT5Paths - 1);
   uint32_t* sB = reinterpret_cast<uint32_t*>(t5_smem + kT5SmemB);
   uint32_t* sT = reinterpret_cast<uint32_t*>(t5_smem + kT5SmemT);
   uint32_t* sH = reinterpret_cast<uint32_t*>(t5_smem + kT5SmemH);
   double* s_acc = reinterpret_cast<double*>(t5_smem + kT5SmemAcc);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(t5_smem + kT5SmemBar);
+  float* s_part = reinterpret_cast<float*>(t5_smem + kT5SmemPart);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t5_smem + kT5SmemBar + 8);
   const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(t5_smem));
   const uint32_t bar = smem_base + kT5SmemBar;
@@ -1264,7 +1307,7 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = *s_tmem;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);   // this warp's lanes
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(pw * 32) << 16);   // this warp's lanes
   const uint32_t tab_lane = smem_base + kT5SmemTab + (lane & 7) * 16 - kNdTabBase * 128u;
   // shared-memory matrix descriptor of B (cute::UMMA::SmemDescriptor): start >> 4,
   // LBO = 1024 B (K chunks) at bit 16, SBO = 128 B (8-row groups) at bit 32, version 1 at bit 46
@@ -1272,20 +1315,20 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
                           (static_cast<uint64_t>(1024 >> 4) << 16) |
                           (static_cast<uint64_t>(128 >> 4) << 32) | (1ull << 46);
 
-  const uint64_t chunk_base = P.first_index & ~static_cast<uint64_t>(kT5Threads - 1);
-  const uint64_t num_chunks =
-      (P.first_index + P.path_count - chunk_base + kT5Threads - 1) / kT5Threads;
+  const uint64_t chunk_base = P.first_index & ~static_cast<uint64_t>(kT5Paths - 1);
+  const uint64_t num_chunks = (P.first_index + P.path_count - chunk_base + kT5Paths - 1) / kT5Paths;
   uint32_t phase = 0;
 
   for (uint64_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
-    const uint64_t tile_index = chunk_base + chunk * kT5Threads;
-    const uint64_t index = tile_index + tid;
+    const uint64_t tile_index = chunk_base + chunk * kT5Paths;
+    const uint64_t index = tile_index + p;
     const bool valid = index >= P.first_index && index < P.first_index + P.path_count;
     const uint32_t high_bits = static_cast<uint32_t>(tile_index >> 7);
-    float x[kMvDim];
+    float x[kT5Half];                       // assets 32 half .. 32 half + 31 of path p
 #pragma unroll
-    for (int i = 0; i < kMvDim; ++i) x[i] = P.x0[i];
+    for (int i = 0; i < kT5Half; ++i) x[i] = P.x0[half * kT5Half + i];
 
+    // (called by all threads together: d.step and the payoff list are uniform)
     auto record = [&](int step_index) {
       const int dim = P.dim;
       for (int pq = 0; pq < P.num_payoffs; ++pq) {
@@ -1293,29 +1336,36 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
         if (d.step != step_index) continue;
         float m = 0.0f;
 #pragma unroll
-        for (int i = 0; i < kMvDim; ++i) {
-          const bool take = d.component < 0 ? i < dim : i == d.component;
+        for (int i = 0; i < kT5Half; ++i) {
+          const int a = half * kT5Half + i;
+          const bool take = d.component < 0 ? a < dim : a == d.component;
           m += take ? x[i] : 0.0f;
         }
-        if (d.component < 0) m = m / static_cast<float>(dim);
+        __syncthreads();
+        if (half == 1) s_part[p] = m;
+        __syncthreads();
         double sum = 0.0, sq = 0.0, bad = 0.0;
-        if (valid) {
-          const double v = eval_payoff(d, static_cast<double>(m), 0.0, 0.0);
-          if (isfinite(v)) {
-            sum = v;
-            sq = v * v;
-          } else {
-            bad = 1.0;
+        if (half == 0) {
+          m += s_part[p];
+          if (d.component < 0) m = m / static_cast<float>(dim);
+          if (valid) {
+            const double v = eval_payoff(d, static_cast<double>(m), 0.0, 0.0);
+            if (isfinite(v)) {
+              sum = v;
+              sq = v * v;
+            } else {
+              bad = 1.0;
+            }
           }
-        }
-        sum = warp_sum(sum);
-        sq = warp_sum(sq);
-        bad = warp_sum(bad);
-        if (lane == 0) {
-          double* acc = s_acc + (warp * TQF_MAX_PAYOFFS + pq) * 3;
-          acc[0] += sum;
-          acc[1] += sq;
-          acc[2] += bad;
+          sum = warp_sum(sum);
+          sq = warp_sum(sq);
+          bad = warp_sum(bad);
+          if (lane == 0) {
+            double* acc = s_acc + (pw * TQF_MAX_PAYOFFS + pq) * 3;
+            acc[0] += sum;
+            acc[1] += sq;
+            acc[2] += bad;
+          }
         }
       }
     };
@@ -1328,20 +1378,22 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
 #pragma unroll 1
     for (int s = 0; s < P.num_steps; ++s) {
       const int buf = s & 1;
-      const uint32_t* sTb = sT + buf * (kMvDim * 32);
-      const uint32_t* sHb = sH + buf * (4 * kMvDim) + warp * kMvDim;
+      const uint32_t* sTb = sT + buf * (kMvDim * 32) + half * (kT5Half * 32) + lane;
+      const uint32_t* sHb = sH + buf * (4 * kT5HStride) + pw * kT5HStride + half * kT5Half;
       const float dt = P.coef[2 * s], sqdt = P.coef[2 * s + 1];
-      // ---- the 64 scaled normals of this path -> A (hi / lo) in tensor memory
+      T5Words next;
+      if (s + 1 < P.num_steps) next = t5_stage_load(P.sobol_v, s + 1, tid);
+      // ---- the 32 scaled normals of this half of the path -> A (hi / lo) in tensor memory
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t xb[16];
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const uint4 hw = *reinterpret_cast<const uint4*>(sHb + c * 16 + i4 * 4);
-          xb[i4 * 4 + 0] = sTb[(c * 16 + i4 * 4 + 0) * 32 + lane] ^ hw.x;
-          xb[i4 * 4 + 1] = sTb[(c * 16 + i4 * 4 + 1) * 32 + lane] ^ hw.y;
-          xb[i4 * 4 + 2] = sTb[(c * 16 + i4 * 4 + 2) * 32 + lane] ^ hw.z;
-          xb[i4 * 4 + 3] = sTb[(c * 16 + i4 * 4 + 3) * 32 + lane] ^ hw.w;
+          xb[i4 * 4 + 0] = sTb[(c * 16 + i4 * 4 + 0) * 32] ^ hw.x;
+          xb[i4 * 4 + 1] = sTb[(c * 16 + i4 * 4 + 1) * 32] ^ hw.y;
+          xb[i4 * 4 + 2] = sTb[(c * 16 + i4 * 4 + 2) * 32] ^ hw.z;
+          xb[i4 * 4 + 3] = sTb[(c * 16 + i4 * 4 + 3) * 32] ^ hw.w;
         }
         float z[16];
         sobol_normals_f32_tab<16>(xb, z, tab_lane);
@@ -1352,33 +1404,26 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
           hi[i] = tf32_rna(zs);
           lo[i] = __float_as_uint(zs - __uint_as_float(hi[i]));
         }
-        t5_st16(t_lane + kT5ColAh + c * 16, hi);
-        t5_st16(t_lane + kT5ColAl + c * 16, lo);
+        t5_st16(t_lane + kT5ColAh + half * kT5Half + c * 16, hi);
+        t5_st16(t_lane + kT5ColAl + half * kT5Half + c * 16, lo);
       }
-      {
+      if (half == 1) {
         const uint32_t dh = tf32_rna(dt);
         t5_st8(t_lane + kT5ColAh + kMvDim, dh);
         t5_st8(t_lane + kT5ColAl + kMvDim, __float_as_uint(dt - __uint_as_float(dh)));
       }
       // ---- the tables of the next step, while this step's stores drain
       if (s + 1 < P.num_steps)
-        t5_stage(P.sobol_v, s + 1, high_bits, sT + (buf ^ 1) * (kMvDim * 32),
-                 sH + (buf ^ 1) * (4 * kMvDim), tid);
+        t5_stage_write(next, high_bits, sT + (buf ^ 1) * (kMvDim * 32), sH + (buf ^ 1) * (4 * kT5HStride), tid);
       asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncthreads();
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         // small terms first: A_lo B_hi, A_hi B_lo, A_hi B_hi (one K = 8 slice = 2 chunks = 2 KB of B)
-#pragma unroll
-        for (int j = 0; j < 9; ++j)
-          t5_mma(tmem + kT5ColD, tmem + kT5ColAl + 8 * j, b_desc + ((j * 2048) >> 4), j > 0);
-#pragma unroll
-        for (int j = 0; j < 9; ++j)
-          t5_mma(tmem + kT5ColD, tmem + kT5ColAh + 8 * j, b_desc + ((kT5PartBytes + j * 2048) >> 4), 1u);
-#pragma unroll
-        for (int j = 0; j < 9; ++j)
-          t5_mma(tmem + kT5ColD, tmem + kT5ColAh + 8 * j, b_desc + ((j * 2048) >> 4), 1u);
+        t5_term(tmem, kT5ColAl, b_desc, 0, true);
+        t5_term(tmem, kT5ColAh, b_desc, kT5PartBytes, false);
+        t5_term(tmem, kT5ColAh, b_desc, 0, false);
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
                      :
                      : "r"(bar)
@@ -1389,9 +1434,9 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       // ---- f_i = sqrt_dt sum_k sigma_i L_ik z_k + mu_i dt; Euler x += x f, exact log step x += f
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float f[16];
-        t5_ld16(t_lane + kT5ColD + c * 16, f);
+        t5_ld16(t_lane + kT5ColD + half * kT5Half + c * 16, f);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           x[c * 16 + i] = P.exact_log ? x[c * 16 + i] + f[i] : fmaf(x[c * 16 + i], f[i], x[c * 16 + i]);
@@ -1419,7 +1464,7 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
 // path materialisation and non-Sobol draws, which the tcgen05 kernel does not cover).
 static bool tc5_enabled() {
   const char* e = std::getenv("TQF_MVGBM_TC5");   // read per launch: tests toggle it
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }
 
 static bool mma_enabled() {
@@ -1497,9 +1542,8 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
       if (a.rngk == RNGK_SOBOL && a.dim == kMvDim && a.mode == MODE_PRICE && a.ndtab != nullptr &&
           tc5_enabled()) {
         P.ndtab = a.ndtab;
-        const uint64_t base128 = a.first_index & ~static_cast<uint64_t>(kT5Threads - 1);
-        const uint64_t chunks128 =
-            (a.first_index + a.path_count - base128 + kT5Threads - 1) / kT5Threads;
+        const uint64_t base128 = a.first_index & ~static_cast<uint64_t>(kT5Paths - 1);
+        const uint64_t chunks128 = (a.first_index + a.path_count - base128 + kT5Paths - 1) / kT5Paths;
         int g5 = static_cast<int>(chunks128 < static_cast<uint64_t>(2 * kSMs) ? chunks128 : 2 * kSMs);
         if (g5 < 1) g5 = 1;
         if (g5 > a.max_grid) g5 = a.max_grid;      // partials hold max_grid rows

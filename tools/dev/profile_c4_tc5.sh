@@ -12,4 +12,5 @@ ncu --set full --clock-control none --import-source on -k regex:mvgbm_tc5 -s 3 -
   python tools/dev/ncu_extra.py < /tmp/c4tc5.raw.csv
   ncu -i /tmp/c4tc5.ncu-rep --page source --csv --print-source sass > /tmp/c4tc5.src.csv
   python tools/ncu_hot.py /tmp/c4tc5.src.csv 40
+  python tools/dev/ncu_smem.py /tmp/c4tc5.src.csv 14
 } > $O/${TAG}_c4_tc5.txt 2>&1
