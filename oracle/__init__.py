@@ -24,6 +24,10 @@ Pinning status
   TensorFlow publishes in its own documentation (`tf.random.stateless_normal(
   [2, 3], seed=[1, 2])` and `tf.random.Generator.from_seed(1).normal([2, 3])`),
   tests/test_oracle_kat.py::test_philox_tensorflow_published_*.
+* TensorFlow's stateless INTEGER uniform (`lo + x mod range`) is pinned by the
+  reference's documented `random_digital_shift(2, 10, seed=(2, 3)) == [586, 1011]`
+  (math/qmc/digital_net.py:58-68), tests/test_qmc.py; `tff.math.qmc` as a whole
+  by every known value of its three test files.
 * **parity unpinned** (only this): the float64 conversion `Uint64ToDouble` /
   `BoxMullerDouble` and the op-seed pair `(87654321, s)` of the stateful
   `tf.random.normal(seed=s)`.  TensorFlow cannot be installed in this image and
