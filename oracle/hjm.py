@@ -262,3 +262,57 @@ def swaption_price_mc(*, expiries, fixed_leg_payment_times, fixed_leg_daycount_f
   payoff = np.maximum(swap, 0.0)
   price = np.asarray(notional, dtype=dtype) * payoff.mean(0)
   return (price, payoff) if return_payoffs else price
+
+
+def bond_option_price_mc(*, strikes, expiries, maturities, discount_rate_fn, dim, mean_reversion,
+                         volatility, corr_matrix=None, is_call_options=True, num_samples=1,
+                         random_type=None, seed=None, skip=0, time_step=None, dtype=np.float64):
+  """`hjm.bond_option_price` (`zero_coupon_bond_option.py:30-195`) with
+  `options_price_from_samples` (`zero_coupon_bond_option_util.py:29-153`):
+  sim_times = unique(expiries U range(time_step, longest, time_step)); the discount
+  factor is cumprod(exp(-r(sim_i) (sim_i - sim_{i-1}))) over the SIM times with
+  dt_0 = 0 (the model's own discount factors are dropped, line 170)."""
+  if time_step is None:
+    raise ValueError('`time_step` must be provided for simulation based bond option valuation.')
+  dtype = np.dtype(dtype)
+  strikes = np.asarray(strikes, dtype=dtype)
+  expiries = np.broadcast_to(np.asarray(expiries, dtype=dtype), strikes.shape)
+  maturities = np.broadcast_to(np.asarray(maturities, dtype=dtype), strikes.shape)
+  is_call = np.broadcast_to(np.asarray(is_call_options, dtype=bool), strikes.shape)
+  model = QuasiGaussianHJM(dim, mean_reversion, volatility, discount_rate_fn, corr_matrix, dtype)
+  sim_times = np.unique(expiries.reshape(-1))
+  longest = sim_times.max()
+  sim_times = np.unique(np.concatenate(
+      [sim_times, grid_lib.tf_range(dtype.type(time_step), longest, dtype.type(time_step), dtype)]))
+  tau = maturities - expiries
+  curve_times = np.unique(tau.reshape(-1))
+  p_t_tau, r_t, _ = model.sample_discount_curve_paths(
+      sim_times, curve_times, num_samples, time_step=time_step, random_type=random_type,
+      seed=seed, skip=skip)
+  dt = np.concatenate([[0.0], sim_times[1:] - sim_times[:-1]]).astype(dtype)
+  df = np.cumprod(np.exp(-r_t * dt[None, :]), axis=1)
+  sim_idx = np.searchsorted(sim_times, expiries.reshape(-1))
+  cur_idx = np.searchsorted(curve_times, tau.reshape(-1))
+  bond = p_t_tau[:, cur_idx, sim_idx].reshape((num_samples,) + strikes.shape)
+  dfs = df[:, sim_idx].reshape((num_samples,) + strikes.shape)
+  payoff = np.where(is_call, np.maximum(bond - strikes, 0.0), np.maximum(strikes - bond, 0.0))
+  return (dfs * payoff).mean(0)
+
+
+def cap_floor_price_mc(*, strikes, expiries, maturities, daycount_fractions, reference_rate_fn, dim,
+                       mean_reversion, volatility, corr_matrix=None, notional=1.0, is_cap=True,
+                       num_samples=1, random_type=None, seed=None, skip=0, time_step=None,
+                       dtype=np.float64):
+  """`hjm.cap_floor_price` (`cap_floor.py:27-229`)."""
+  dtype = np.dtype(dtype)
+  strikes = np.asarray(strikes, dtype=dtype)
+  expiries = np.asarray(expiries, dtype=dtype)
+  dcf = np.asarray(daycount_fractions, dtype=dtype)
+  caplets = bond_option_price_mc(
+      strikes=1.0 / (1.0 + dcf * strikes), expiries=expiries, maturities=maturities,
+      discount_rate_fn=reference_rate_fn, dim=dim, mean_reversion=mean_reversion,
+      volatility=volatility, corr_matrix=corr_matrix,
+      is_call_options=~np.asarray(is_cap, dtype=bool), num_samples=num_samples,
+      random_type=random_type, seed=seed, skip=skip, time_step=time_step, dtype=dtype)
+  caplets = np.where(np.broadcast_to(expiries, caplets.shape) < 0.0, 0.0, caplets)
+  return (np.asarray(notional, dtype=dtype) * (1.0 + dcf * strikes) * caplets).sum(-1)

@@ -1,5 +1,6 @@
-"""Gaussian / quasi-Gaussian HJM and the Monte-Carlo HJM swaption price (SURVEY 8f-2;
-`models/hjm/{quasi_gaussian_hjm,gaussian_hjm,swaption_pricing,swaption_util}.py`).
+"""Gaussian / quasi-Gaussian HJM and the Monte-Carlo HJM swaption, bond-option and cap / floor
+prices (`models/hjm/{quasi_gaussian_hjm,gaussian_hjm,swaption_pricing,swaption_util,
+zero_coupon_bond_option,zero_coupon_bond_option_util,cap_floor}.py`).
 
 CPU: the oracle against the reference's own values (`gaussian_hjm_test.py:224-283`,
 `swaption_pricing_test.py:46-165, 321-356`), and the product's HOST tables (grid,
@@ -52,16 +53,20 @@ def test_oracle_swaption_reference_values():
 
 
 def _replay(model, times, num_samples, random_type, seed, skip=0, time_step=None,
-            num_time_steps=None):
+            num_time_steps=None, integral_weights_fn=None):
   """numpy twin of HjmModel::step (csrc/tqf_paths_kernel.cuh) over the product's host
   tables with the oracle's draws: (state at the requested times [N, k, F + 1], y)."""
   dt_ = model._dtype
   times = np.asarray(times, dtype=dt_)
   f = model._factors
   grid, idx, all_times, keep_mask = model._grids(times, time_step, num_time_steps)
-  table, y_entries = model._tables(all_times)
   from tff_b200 import engine
   num_steps, grid_slot = engine.record_plan(keep_mask, grid.shape[0])
+  weights = None
+  if integral_weights_fn is not None:
+    entries = [max(e for e, g in enumerate(grid_slot) if g == i) for i in idx]
+    weights = integral_weights_fn(all_times, entries)
+  table, y_entries = model._tables(all_times, weights)
   nfs = model._draws_per_step()
   z = odraws.generate_mc_normal_draws(nfs, all_times.shape[0] - 1, num_samples, random_type,
                                       seed=seed, skip=skip, dtype=dt_)           # [S, N, nfs]
@@ -159,6 +164,73 @@ def test_swaption_descriptor_replay_matches_oracle_price(factors):
   want = ohjm.swaption_price_mc(num_hjm_factors=factors, mean_reversion=mr, volatility=vol,
                                 time_step=0.1, num_samples=n, random_type=rt, **SWAPTION)
   np.testing.assert_allclose(price, want[0], rtol=1e-11)
+
+
+def test_oracle_bond_option_and_cap_reference_values():
+  rt = odraws.RandomType.STATELESS_ANTITHETIC
+  # zero_coupon_bond_option_test.py:37-61 (tolerance 1e-2 there), 63-96 (time-dependent vol)
+  exp, mat = np.array([1.0]), np.array([5.0])
+  strikes = np.exp(-0.01 * mat) / np.exp(-0.01 * exp)
+  kw = dict(strikes=strikes, expiries=exp, maturities=mat, discount_rate_fn=RATE, time_step=0.1,
+            random_type=rt, seed=[1, 2])
+  got = ohjm.bond_option_price_mc(dim=1, mean_reversion=[0.03], volatility=[0.02],
+                                  num_samples=100_000, **kw)
+  assert got.shape == (1,) and abs(got[0] - 0.02817777) < 1e-2
+  # :183-209 two factors
+  got = ohjm.bond_option_price_mc(dim=2, mean_reversion=[0.03, 0.06], volatility=[0.02, 0.01],
+                                  num_samples=50_000, **kw)
+  assert abs(got[0] - 0.03111126) < 1e-2
+  # cap_floor_test.py:41-68: the analytic Hull-White value 0.4072088 (tolerance 1e-3 + 1e-3 rel
+  # there; a single seed scatters by ~1e-3, the mean over seeds sits within 5e-4)
+  cap = dict(strikes=0.01 * np.ones(4), expiries=np.array([0.0, 0.25, 0.5, 0.75]),
+             maturities=np.array([0.25, 0.5, 0.75, 1.0]), daycount_fractions=0.25 * np.ones(4),
+             notional=100.0, dim=1, mean_reversion=[0.03], volatility=[0.02], reference_rate_fn=RATE,
+             num_samples=100_000, time_step=0.1, random_type=rt)
+  prices = [ohjm.cap_floor_price_mc(seed=seed, **cap) for seed in ([42, 42], [1, 2], [3, 4], [5, 6])]
+  assert abs(prices[0] - 0.4072088281493774) < 2.5e-3
+  assert abs(np.mean(prices) - 0.4072088281493774) < 5e-4
+  # :70-103 piecewise-constant volatility
+  pw = omodels.PiecewiseConstantFunc([0.5], [0.01, 0.02], dtype=np.float64)
+  got = ohjm.cap_floor_price_mc(seed=[42, 42], **dict(cap, volatility=lambda t, r: pw(np.asarray([t]))))
+  assert abs(got - 0.2394242699989869) < 2.5e-3
+
+
+@pytest.mark.parametrize('factors', [1, 2])
+def test_bond_option_descriptor_replay_matches_oracle_price(factors):
+  """The bond-option route on the host: simulation grid, the reference's discounting weights
+  (dt_0 = 0 over the SIMULATION times) and the one-payment payoff descriptors, evaluated in numpy
+  on the replayed state exactly as the kernel does, against the oracle's price."""
+  from tff_b200.models import hjm
+  from tff_b200.models.hjm import zero_coupon_bond_option as zcb
+  from tff_b200 import engine
+  mr, vol = [0.03, 0.06][:factors], [0.02, 0.01][:factors]
+  rt = odraws.RandomType.STATELESS_ANTITHETIC
+  n = 4000
+  strikes = np.array([0.96, 0.97, 0.99, 0.95])
+  expiries = np.array([1.0, 0.55, 0.25, 1.0])
+  maturities = np.array([5.0, 2.0, 0.5, 3.0])
+  is_call = np.array([True, False, True, False])
+  model = hjm.QuasiGaussianHJM(factors, mr, vol, RATE, dtype=np.float64)
+  sim_times, wfn = zcb._simulation_grid(expiries, np.float64(0.1), np.dtype(np.float64))
+  state, _ = _replay(model, sim_times, n, rt, [1, 2], time_step=np.float64(0.1), integral_weights_fn=wfn)
+  grid, idx, all_times, keep_mask = model._grids(sim_times, np.float64(0.1), None)
+  _, grid_slot = engine.record_plan(keep_mask, grid.shape[0])
+  _, y_entries = model._tables(all_times)
+  got = []
+  for b in range(4):
+    j = int(np.searchsorted(sim_times, expiries[b]))
+    entry = max(e for e, g in enumerate(grid_slot) if g == idx[j])
+    d = zcb._bond_option_desc(model, entry, y_entries[entry], expiries[b], maturities[b], strikes[b],
+                              is_call[b])
+    x, integ = state[:, j, :factors], state[:, j, factors]
+    p = d.pay_coef[0] * np.exp(d.pay_k[0] - sum(d.pay_g[i] * x[:, i] for i in range(factors)))
+    sign = 1.0 if d.is_payer else -1.0
+    got.append(d.scale * np.maximum(sign * np.exp(-integ) * (1.0 - p), 0.0).mean())
+  want = ohjm.bond_option_price_mc(strikes=strikes, expiries=expiries, maturities=maturities,
+                                   discount_rate_fn=RATE, dim=factors, mean_reversion=mr,
+                                   volatility=vol, is_call_options=is_call, num_samples=n,
+                                   random_type=rt, seed=[1, 2], time_step=0.1)
+  np.testing.assert_allclose(got, want, rtol=1e-10)
 
 
 def test_interior_duplicate_times_with_num_time_steps_are_refused():
@@ -287,3 +359,57 @@ def test_gpu_hjm_swaption_matches_oracle_and_reference_values():
                                 random_type=ort, time_step=0.1, **SWAPTION)
   np.testing.assert_allclose(got, want, rtol=1e-10)
   assert abs(got[0] - 0.5593057004094042) < 1e-3
+
+
+@pytest.mark.gpu
+def test_gpu_hjm_bond_option_and_cap_floor_match_oracle_and_reference_values():
+  import tff_b200 as tff
+  rt, ort = tff.math.random.RandomType.STATELESS_ANTITHETIC, odraws.RandomType.STATELESS_ANTITHETIC
+  one = dict(dim=1, mean_reversion=[0.03], volatility=[0.02])
+  two = dict(dim=2, mean_reversion=[0.03, 0.06], volatility=[0.02, 0.01])
+  exp, mat = np.array([1.0]), np.array([5.0])
+  strikes = np.exp(-0.01 * mat) / np.exp(-0.01 * exp)
+  # zero_coupon_bond_option_test.py:37-61, 183-209 (tolerance 1e-2 there)
+  for model_kw, n, ref in ((one, 100_000, 0.02817777), (two, 50_000, 0.03111126),
+                           (dict(two, corr_matrix=[[1.0, 0.5], [0.5, 1.0]]), 20_000, None)):
+    kw = dict(strikes=strikes, expiries=exp, maturities=mat, discount_rate_fn=RATE, time_step=0.1,
+              seed=[1, 2], num_samples=n, **model_kw)
+    got = tff.models.hjm.bond_option_price(random_type=rt, dtype=np.float64, **kw)
+    want = ohjm.bond_option_price_mc(random_type=ort, **kw)
+    assert got.shape == (1,) and got.dtype == np.float64
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    if ref is not None:
+      assert abs(got[0] - ref) < 1e-2
+  # a batch: calls and puts, several expiries (one off the uniform grid), a 2-d batch shape
+  kw = dict(strikes=np.array([[0.96, 0.97], [0.99, 0.95]]), expiries=np.array([[1.0, 0.55], [0.25, 1.0]]),
+            maturities=np.array([[5.0, 2.0], [0.5, 3.0]]), discount_rate_fn=RATE, time_step=0.1,
+            is_call_options=np.array([[True, False], [True, False]]), seed=[4, 2], num_samples=20_000)
+  got, stderr, bad = tff.models.hjm.bond_option_price(random_type=rt, dtype=np.float64,
+                                                      return_stats=True, **one, **kw)
+  want = ohjm.bond_option_price_mc(random_type=ort, **one, **kw)
+  assert got.shape == (2, 2) and np.all(bad == 0) and np.all(stderr > 0)
+  np.testing.assert_allclose(got, want, rtol=1e-10)
+  # cap_floor_test.py:41-68 (expiry 0 included: a deterministic caplet), :70-103, floors
+  cap = dict(strikes=0.01 * np.ones(4), expiries=np.array([0.0, 0.25, 0.5, 0.75]),
+             maturities=np.array([0.25, 0.5, 0.75, 1.0]), daycount_fractions=0.25 * np.ones(4),
+             notional=100.0, reference_rate_fn=RATE, num_samples=100_000, time_step=0.1, seed=[42, 42])
+  got = tff.models.hjm.cap_floor_price(random_type=rt, dtype=np.float64, **one, **cap)
+  want = ohjm.cap_floor_price_mc(random_type=ort, **one, **cap)
+  assert got.shape == () and got.dtype == np.float64
+  np.testing.assert_allclose(got, want, rtol=1e-10)
+  assert abs(got - 0.4072088281493774) < 2.5e-3
+  got = tff.models.hjm.cap_floor_price(random_type=rt, dtype=np.float64, is_cap=False, **two, **cap)
+  want = ohjm.cap_floor_price_mc(random_type=ort, is_cap=False, **two, **cap)
+  np.testing.assert_allclose(got, want, rtol=1e-10)
+  from tff_b200.math import piecewise
+  pw = piecewise.PiecewiseConstantFunc([0.5], [0.01, 0.02], dtype=np.float64)
+  opw = omodels.PiecewiseConstantFunc([0.5], [0.01, 0.02], dtype=np.float64)
+  got = tff.models.hjm.cap_floor_price(random_type=rt, dtype=np.float64, dim=1, mean_reversion=[0.03],
+                                       volatility=lambda t, r: pw([float(t)]), **cap)
+  want = ohjm.cap_floor_price_mc(random_type=ort, dim=1, mean_reversion=[0.03],
+                                 volatility=lambda t, r: opw(np.asarray([t])), **cap)
+  np.testing.assert_allclose(got, want, rtol=1e-10)
+  assert abs(got - 0.2394242699989869) < 2.5e-3
+  with pytest.raises(ValueError):
+    tff.models.hjm.bond_option_price(strikes=strikes, expiries=exp, maturities=mat,
+                                     discount_rate_fn=RATE, random_type=rt, **one)

@@ -171,8 +171,12 @@ class QuasiGaussianHJM:
     out[steps] = y
     return out
 
-  def _tables(self, all_times):
-    """(coef table [S, NCOEF] float64, y at every Euler grid entry [S + 1, F, F])."""
+  def _tables(self, all_times, integral_weights=None):
+    """(coef table [S, NCOEF] float64, y at every Euler grid entry [S + 1, F, F]).
+
+    `integral_weights` [S] replaces the model's own discounting rule: step s adds
+    `w_s r(all_times[s + 1])` to the short-rate integral (the rule of
+    `options_price_from_samples`, hjm/zero_coupon_bond_option_util.py:102-113)."""
     dt_ = self._dtype
     f = self._factors
     steps = all_times.shape[0] - 1
@@ -184,7 +188,10 @@ class QuasiGaussianHJM:
     a0 = self._drift_a0(all_times, y_entries)                       # [S, F]
     b = (self._sqrt_rho[None, :, :] * sigma[:, :, None]).astype(dt_)       # [S, F, F]
     f0 = np.asarray(self._fwd(all_times), dtype=dt_)
-    if self._RIGHT_POINT_DISCOUNTING:
+    if integral_weights is not None:
+      w = np.asarray(integral_weights, dtype=dt_)
+      c_l, c_r, c_f = np.zeros_like(dts), w, (f0[1:] * w).astype(dt_)
+    elif self._RIGHT_POINT_DISCOUNTING:
       c_l, c_r, c_f = np.zeros_like(dts), dts, (f0[1:] * dts).astype(dt_)
     else:
       c_l, c_r, c_f = dts, np.zeros_like(dts), (f0[:-1] * dts).astype(dt_)
@@ -199,9 +206,12 @@ class QuasiGaussianHJM:
   def _draws_per_step(self):
     return self._dim if self._DRAWS_PER_STEP_IS_STATE_DIM else self._factors
 
-  def _plan(self, times, time_step, num_time_steps, num_samples, random_type, seed, skip):
+  def _plan(self, times, time_step, num_time_steps, num_samples, random_type, seed, skip,
+            integral_weights_fn=None):
     """The device plan over the Euler grid, which Euler entry each requested time is
-    read at, the y tables at those entries, and the gather of duplicate times."""
+    read at, the y tables at those entries, and the gather of duplicate times.
+    `integral_weights_fn(all_times, entries)` (entries = Euler entry of every requested
+    time) may replace the discounting rule, see `_tables`."""
     dt_ = self._dtype
     times = _tensor.to_numpy(times, dt_)
     if times.ndim != 1:
@@ -226,7 +236,10 @@ class QuasiGaussianHJM:
           entry_of[pos] = entry
     if np.any(entry_of < 0):
       raise ValueError('a requested time is not reached by the simulation grid')
-    table, y_entries = self._tables(all_times)
+    weights = None
+    if integral_weights_fn is not None:
+      weights = integral_weights_fn(all_times, entry_of[inverse])
+    table, y_entries = self._tables(all_times, weights)
     spec = _HjmSpec(f, self._draws_per_step(), table[:num_steps])
     rng = engine.RngSpec(random_type, seed, skip, None)
     plan = engine.Plan(spec, all_times, num_steps, np.zeros(f + 1, dt_), rng, int(num_samples),

@@ -1,5 +1,6 @@
 """Mirror of `tf_quant_finance.models.milstein_sampling` (`milstein_sampling.py:35-256`)
-for one-dimensional processes on the B200 path engine.
+on the B200 path engine: one-dimensional processes with affine coefficients, and
+multi-dimensional processes whose volatility does not depend on the state.
 
 Same skeleton as the Euler sampler (`utils.prepare_grid`, coefficients at
 `times[i + 1]`, the `_while_loop` recording rule); the step is `_milstein_1d`
@@ -7,9 +8,20 @@ Same skeleton as the Euler sampler (`utils.prepare_grid`, coefficients at
 normals per step even in one dimension (282-290) and uses the first `dim` of
 them: the draw layout is reproduced by generating that tensor on the device and
 feeding its first column to the kernel as `normal_draws`.
+
+Multi-dimensional scheme (`_milstein_nd`, 578-595): the higher-order term and the
+Stratonovich drift correction are contractions with the volatility GRADIENT
+(530-562).  For every multi-dimensional process the engine can run besides the
+multi-asset GBM -- drift affine in the state, volatility `B(t)` (`AffineModelND`) --
+that gradient is identically zero, the auxiliary `3 * dim * stratonovich_order`
+normals multiply zero and the step is `x + dt a + B dW`: the Euler kernel, fed
+with the first `dim` columns of the reference's Milstein draw tensor.  Processes
+with a state-dependent volatility matrix (SABR, multi-asset GBM) would need the
+Stratonovich integrals in the kernel and are refused.
 """
 import numpy as np
 
+from tff_b200 import _lib
 from tff_b200 import _tensor
 from tff_b200 import engine
 from tff_b200.math import random
@@ -24,17 +36,15 @@ def sample(*, dim, drift_fn, volatility_fn, times, time_step=None, num_time_step
   """Returns sample paths from the process using the Milstein method:
   CUDA tensor `[num_samples, k, dim]`.
 
-  `dim` must be 1 and the (drift, volatility) pair affine in the state (model
+  `dim == 1`: the (drift, volatility) pair must be affine in the state (model
   closures or plain Python callables, probed on the host); the volatility
   gradient is then exact and `grad_volatility_fn` is not needed (it is ignored).
+  `dim > 1`: drift affine in the state and a state-independent volatility matrix.
   `swap_memory`, `precompute_normal_draws` and `name` only steer TensorFlow's
   execution: the result is defined to equal the reference's precomputed-draws path.
   """
   del swap_memory, precompute_normal_draws, name, grad_volatility_fn
-  if dim != 1:
-    raise NotImplementedError(
-        'The B200 Milstein kernel covers dim == 1; the multi-dimensional scheme needs the '
-        'Stratonovich integrals of milstein_sampling.py:481-553 (SURVEY 8f-4).')
+  dim = int(dim)
   if watch_params is not None:
     raise NotImplementedError('`watch_params` is not implemented by the B200 Milstein sampler')
   dtype = _tensor.infer_dtype(times, dtype)
@@ -54,9 +64,18 @@ def sample(*, dim, drift_fn, volatility_fn, times, time_step=None, num_time_step
   if initial_state is None:
     initial_state = np.zeros(dim, dtype=dtype)
   x0 = _tensor.to_numpy(initial_state, dtype).reshape(-1)
-  if x0.shape[0] != 1:
+  if x0.shape[0] != dim:
     raise NotImplementedError('per-path / batched initial states are not implemented yet')
-  spec = engine.MilsteinSpec1F(closures.resolve_spec(drift_fn, volatility_fn, dim))
+  euler_spec = closures.resolve_spec(drift_fn, volatility_fn, dim)
+  if dim == 1:
+    spec = engine.MilsteinSpec1F(euler_spec)
+  elif euler_spec.kind == _lib.MODEL_AFFINE_ND:
+    spec = euler_spec        # B(t) does not depend on the state: every gradient term is zero
+  else:
+    raise NotImplementedError(
+        'The multi-dimensional B200 Milstein sampler covers processes with affine drift and a '
+        'state-independent volatility matrix; a state-dependent volatility needs the Stratonovich '
+        'integrals of milstein_sampling.py:481-553 in the kernel. There is no CPU fallback.')
   num_samples = int(num_samples)
   steps_total = all_times.shape[0] - 1
   rt = random.RandomType.PSEUDO if random_type is None else random_type
