@@ -362,6 +362,14 @@ int tqf_plan_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
                    const tqf_payoff_desc* payoffs, int num_payoffs,
                    double* sums_dev, void* stream);
 
+/* tqf_plan_price followed by the read-back of the sums into HOST memory
+ * (sums_host: double [num_payoffs][4]) and a synchronisation of `stream`: the whole
+ * device side of one pricing call of the reference API (`tf.reduce_mean(payoff(...))`
+ * evaluated to a host value) behind a single FFI call.                       */
+int tqf_plan_price_host(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                        const tqf_payoff_desc* payoffs, int num_payoffs,
+                        double* sums_dev, double* sums_host, void* stream);
+
 /* Materialising mode: writes the state at the recorded steps.
  *   record_slot: host int32 [num_steps+1]; entry 0 refers to the initial
  *   state, entry s+1 to the state after step s; value = output time slot or -1.

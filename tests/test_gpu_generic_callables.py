@@ -165,3 +165,46 @@ def test_argument_errors():
     sample(1, lambda t, x: torch.sin(x), vol, [1.0], time_step=0.5, seed=1, dtype=np.float64)
   with pytest.raises(NotImplementedError):
     sample(1, drift, vol, [1.0], time_step=0.5, seed=1, watch_params=[1.0], dtype=np.float64)
+
+
+def test_repeated_price_calls_are_bound_by_content():
+  # euler_sampling.price recognises a repeated call by the CONTENT of its arguments and runs it
+  # as one FFI call (tqf_plan_price_host); any changed number must give the new answer
+  tff = _tff()
+  from tff_b200 import engine
+  from tff_b200.models import closures
+  from tff_b200.models import euler_sampling as es
+  r, sigma = 0.03, 0.1
+  d, v = closures.affine_closures(r - sigma**2 / 2, 0.0, sigma)
+  process = tff.models.GenericItoProcess(1, d, v, dtype=np.float64)
+  x0 = np.array([np.log(700.0)])
+  rt = tff.math.random.RandomType.PSEUDO_ANTITHETIC
+
+  def call(strike, seed=42, n=20000, stats=False):
+    return process.price([1.0], [engine.european_call(strike, log_state=True, scale=np.exp(-r))],
+                         num_samples=n, initial_state=x0, random_type=rt, seed=seed, time_step=0.01,
+                         return_stats=stats)
+  es._CALLS.clear()
+  first = call(650.0)
+  assert len(es._CALLS) == 1
+  again = call(650.0)
+  np.testing.assert_array_equal(first, again)
+  other = call(680.0)
+  assert len(es._CALLS) == 2 and other[0] < first[0]
+  np.testing.assert_array_equal(call(650.0), first)
+  assert call(650.0, seed=43)[0] != first[0]
+  mean, stderr, bad = call(650.0, stats=True)
+  kept = bad.copy()
+  call(680.0, stats=True)
+  np.testing.assert_array_equal(bad, kept)                 # results do not alias the bound buffers
+  np.testing.assert_array_equal(mean, first)
+  # a destroyed plan is rebuilt, not reused
+  engine.clear_plan_cache()
+  np.testing.assert_array_equal(call(650.0), first)
+  # callables of time are never bound
+  d2, v2 = closures.affine_closures(lambda t: 0.02 + 0 * t, 0.0, sigma)
+  p2 = tff.models.GenericItoProcess(1, d2, v2, dtype=np.float64)
+  before = len(es._CALLS)
+  p2.price([1.0], [engine.european_call(650.0, log_state=True)], num_samples=1000, initial_state=x0,
+           random_type=rt, seed=1, time_step=0.1)
+  assert len(es._CALLS) == before

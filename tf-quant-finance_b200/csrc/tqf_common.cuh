@@ -21,6 +21,13 @@ int cuda_fail(cudaError_t e, const char* what);
 int device_logtab(const double** out);
 // Device-global cubic table of the float32 inverse normal CDF (tqf_ndtri_f32_tab.inc).
 int device_ndtri_f32_tab(const float** out);
+// Device buffers of plans (coefficient tables, direction numbers, partial sums): served
+// from a per-device free list of power-of-two blocks, so that a pricing call with new
+// parameters -- a new plan -- costs no cudaMalloc / cudaFree once the process is warm
+// (tqf_rng.cu).  dev_free_all_sync(): one device synchronisation, then every block goes
+// back to the list (the semantics cudaFree had: nothing in flight can still read them).
+int dev_alloc(void** out, size_t bytes);
+void dev_release(void* const* ptrs, int count);
 
 #define TQF_CUDA_OK(expr)                                        \
   do {                                                           \

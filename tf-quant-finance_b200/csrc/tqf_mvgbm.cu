@@ -406,7 +406,8 @@ int mvgbm_upload_split(const double* chol, const double* mu, const double* sigma
   if (dtype == TQF_F64) {
     std::vector<double> host;
     build_split<double>(chol, mu, sigma, dim, &host);
-    TQF_CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(double)));
+    const int rc = dev_alloc(&dev, host.size() * sizeof(double));
+    if (rc != TQF_OK) return rc;
     e = cudaMemcpy(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice);
   } else {
     std::vector<float> host, mma;
@@ -415,11 +416,12 @@ int mvgbm_upload_split(const double* chol, const double* mu, const double* sigma
     host.insert(host.end(), mma.begin(), mma.end());
     build_tc5(chol, mu, sigma, dim, &mma);
     host.insert(host.end(), mma.begin(), mma.end());
-    TQF_CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(float)));
+    const int rc = dev_alloc(&dev, host.size() * sizeof(float));
+    if (rc != TQF_OK) return rc;
     e = cudaMemcpy(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) {
-    cudaFree(dev);
+    dev_release(&dev, 1);
     return cuda_fail(e, "mvgbm_upload_split");
   }
   *out_dev = dev;

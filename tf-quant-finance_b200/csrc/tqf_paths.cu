@@ -147,10 +147,11 @@ static int upload_coef(const tqf_model_desc* m, int ncoef, void** out) {
   std::vector<Real> host(n > 0 ? n : 1);
   for (size_t i = 0; i < n; ++i) host[i] = static_cast<Real>(m->coef[i]);
   void* dev = nullptr;
-  TQF_CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(Real)));
+  const int rc = dev_alloc(&dev, host.size() * sizeof(Real));
+  if (rc != TQF_OK) return rc;
   cudaError_t e = cudaMemcpy(dev, host.data(), host.size() * sizeof(Real), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
-    cudaFree(dev);
+    dev_release(&dev, 1);
     return cuda_fail(e, "upload_coef");
   }
   *out = dev;
@@ -612,13 +613,19 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
     rc = mvgbm_upload_split(plan->chol, plan->mu, plan->sigma, info.dim, model->dtype,
                             &plan->lsplit_dev);
   if (rc == TQF_OK) {
-    e = cudaMalloc(&plan->partials_dev,
-                   static_cast<size_t>(plan->max_grid) * TQF_MAX_PAYOFFS * 4 * sizeof(double));
-    if (e == cudaSuccess)
-      e = cudaMalloc(&plan->record_dev, (static_cast<size_t>(model->num_steps) + 1) * sizeof(int));
-    if (e == cudaSuccess)
-      e = cudaMalloc(&plan->swaptions_dev, TQF_MAX_PAYOFFS * sizeof(SwaptionK));
-    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(plan scratch)");
+    void* p = nullptr;
+    rc = dev_alloc(&p, static_cast<size_t>(plan->max_grid) * TQF_MAX_PAYOFFS * 4 * sizeof(double));
+    plan->partials_dev = static_cast<double*>(p);
+    if (rc == TQF_OK) {
+      p = nullptr;
+      rc = dev_alloc(&p, (static_cast<size_t>(model->num_steps) + 1) * sizeof(int));
+      plan->record_dev = static_cast<int*>(p);
+    }
+    if (rc == TQF_OK) {
+      p = nullptr;
+      rc = dev_alloc(&p, TQF_MAX_PAYOFFS * sizeof(SwaptionK));
+      plan->swaptions_dev = static_cast<SwaptionK*>(p);
+    }
   }
   // the descriptors' host pointers are not kept
   plan->model.coef = nullptr;
@@ -636,14 +643,10 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
 
 int tqf_plan_destroy(tqf_plan* plan) {
   if (!plan) return TQF_OK;
-  cudaFree(plan->coef_dev);
-  cudaFree(plan->sobol_dev);
-  cudaFree(plan->lsplit_dev);
-  cudaFree(plan->colsum_dev);
-  cudaFree(plan->partials_dev);
-  cudaFree(plan->record_dev);
+  void* blocks[7] = {plan->coef_dev,     plan->sobol_dev,  plan->lsplit_dev,   plan->colsum_dev,
+                     plan->partials_dev, plan->record_dev, plan->swaptions_dev};
+  dev_release(blocks, 7);
   delete plan->record_cache;
-  cudaFree(plan->swaptions_dev);
   delete plan;
   return TQF_OK;
 }
@@ -661,6 +664,20 @@ int tqf_plan_price(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
   return plan->model.dtype == TQF_F64
              ? run_price<double>(plan, path_offset, path_count, payoffs, num_payoffs, sums_dev, s)
              : run_price<float>(plan, path_offset, path_count, payoffs, num_payoffs, sums_dev, s);
+}
+
+int tqf_plan_price_host(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
+                        const tqf_payoff_desc* payoffs, int num_payoffs, double* sums_dev,
+                        double* sums_host, void* stream) {
+  TQF_NVTX("tqf_plan_price_host");
+  TQF_REQUIRE(sums_host, "null host buffer");
+  const int rc = tqf_plan_price(plan, path_offset, path_count, payoffs, num_payoffs, sums_dev, stream);
+  if (rc != TQF_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  TQF_CUDA_OK(cudaMemcpyAsync(sums_host, sums_dev, sizeof(double) * 4 * num_payoffs,
+                              cudaMemcpyDeviceToHost, s));
+  TQF_CUDA_OK(cudaStreamSynchronize(s));
+  return TQF_OK;
 }
 
 int tqf_plan_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,

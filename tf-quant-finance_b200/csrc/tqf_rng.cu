@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <set>
 #include <vector>
 
 #include <cmath>
@@ -21,6 +23,97 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 int cuda_fail(cudaError_t e, const char* what) {
   g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
   return TQF_ERR_CUDA;
+}
+
+namespace {
+struct DevBlockCache {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_blocks;      // (device, bytes) -> block
+  std::map<void*, std::pair<int, size_t>> live;                  // block -> (device, bytes)
+  size_t cached_bytes = 0;
+  // blocks up to kSlabBlockMax are carved out of 16 MB slabs (one cudaMalloc per slab):
+  // the first plans of a process do not pay one cudaMalloc (~0.3-1 ms) per buffer either
+  struct Slab {
+    char* base;
+    size_t used;
+  };
+  std::map<int, Slab> slab;                                      // device -> current slab
+  std::set<void*> carved;                                        // blocks that live inside a slab
+};
+constexpr size_t kSlabBytes = 16ull << 20, kSlabBlockMax = 4ull << 20;
+DevBlockCache& dev_cache() {
+  static DevBlockCache* c = new DevBlockCache();   // never destroyed: outlives the CUDA context teardown
+  return *c;
+}
+constexpr size_t kDevCacheLimit = 256ull << 20;
+}  // namespace
+
+int dev_alloc(void** out, size_t bytes) {
+  size_t size = 512;
+  while (size < bytes) size <<= 1;
+  int dev = 0;
+  TQF_CUDA_OK(cudaGetDevice(&dev));
+  DevBlockCache& c = dev_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.free_blocks.find({dev, size});
+    if (it != c.free_blocks.end()) {
+      *out = it->second;
+      c.free_blocks.erase(it);
+      c.cached_bytes -= size;
+      c.live[*out] = {dev, size | (c.carved.count(*out) ? 1 : 0)};
+      return TQF_OK;
+    }
+  }
+  if (size <= kSlabBlockMax) {
+    std::lock_guard<std::mutex> lock(c.mu);
+    DevBlockCache::Slab& sl = c.slab[dev];
+    if (sl.base == nullptr || sl.used + size > kSlabBytes) {
+      void* base = nullptr;
+      TQF_CUDA_OK(cudaMalloc(&base, kSlabBytes));     // the rest of an old slab stays with its blocks
+      sl.base = static_cast<char*>(base);
+      sl.used = 0;
+    }
+    *out = sl.base + sl.used;
+    sl.used += size;
+    c.carved.insert(*out);
+    c.live[*out] = {dev, size | 1};                   // bit 0: carved from a slab, never cudaFree'd
+    return TQF_OK;
+  }
+  void* p = nullptr;
+  TQF_CUDA_OK(cudaMalloc(&p, size));
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.live[p] = {dev, size};
+  *out = p;
+  return TQF_OK;
+}
+
+void dev_release(void* const* ptrs, int count) {
+  bool any = false;
+  for (int i = 0; i < count; ++i) any = any || ptrs[i] != nullptr;
+  if (!any) return;
+  // what cudaFree did implicitly: nothing in flight may still read the blocks
+  cudaDeviceSynchronize();
+  DevBlockCache& c = dev_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (int i = 0; i < count; ++i) {
+    void* p = ptrs[i];
+    if (!p) continue;
+    auto it = c.live.find(p);
+    if (it == c.live.end()) {          // not one of ours (allocated with cudaMalloc)
+      cudaFree(p);
+      continue;
+    }
+    const bool carved = (it->second.second & 1) != 0;
+    const std::pair<int, size_t> key = {it->second.first, it->second.second & ~static_cast<size_t>(1)};
+    c.live.erase(it);
+    if (!carved && c.cached_bytes + key.second > kDevCacheLimit) {
+      cudaFree(p);
+    } else {
+      c.free_blocks.insert({key, p});
+      c.cached_bytes += key.second;
+    }
+  }
 }
 
 // Device-global copy of the {T, 1/c} table of the table logarithm
@@ -312,12 +405,18 @@ int upload_sobol_table(const int32_t* direction_numbers, int dim, uint32_t** out
     }
   }
   uint32_t* dev = nullptr;
-  TQF_CUDA_OK(cudaMalloc(&dev, v.size() * sizeof(uint32_t)));
+  {
+    void* p = nullptr;
+    const int rc = dev_alloc(&p, v.size() * sizeof(uint32_t));
+    if (rc != TQF_OK) return rc;
+    dev = static_cast<uint32_t*>(p);
+  }
   cudaError_t e = cudaMemcpyAsync(dev, v.data(), v.size() * sizeof(uint32_t),
                                   cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // v is a local
   if (e != cudaSuccess) {
-    cudaFree(dev);
+    void* p = dev;
+    dev_release(&p, 1);
     return cuda_fail(e, "upload_sobol_table");
   }
   *out_dev = dev;
@@ -761,8 +860,11 @@ int tqf_sobol_fill(const int32_t* direction_numbers, int dim, uint64_t num_resul
                                                       static_cast<float*>(out_dev));
   }
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the table is freed below
-  cudaFree(table);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the table is released below
+  {
+    void* p = table;
+    dev_release(&p, 1);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "sobol_fill_kernel");
   return TQF_OK;
 }

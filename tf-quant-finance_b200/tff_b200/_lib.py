@@ -182,6 +182,9 @@ _SIGNATURES = {
     'tqf_plan_price':
         (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(PayoffDesc),
                    C.c_int, C.c_void_p, C.c_void_p]),
+    'tqf_plan_price_host':
+        (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(PayoffDesc),
+                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'tqf_plan_paths':
         (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                    C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),

@@ -39,6 +39,12 @@ class ModelSpec:
     """float64 [S, num_coef]; values exactly representable in `dtype`."""
     raise NotImplementedError
 
+  def constant_key(self):
+    """A hashable description of the model when ALL its parameters are plain numbers
+    (nothing a later call could evaluate differently), else None.  Lets a pricing
+    entry point recognise a repeated call without rebuilding the tables."""
+    return None
+
   @staticmethod
   def _dt_columns(all_times, dtype):
     t = np.asarray(all_times, dtype=dtype)
@@ -64,6 +70,12 @@ class AffineSpec1F(ModelSpec):
         not callable(p) and np.ndim(p) == 0 and float(p) == 0.0 for p in (a1, b1))
     self.kind = _lib.MODEL_LINEAR_1F if self.additive else _lib.MODEL_AFFINE_1F
     self.num_coef = 5 if self.additive else 6
+
+  def constant_key(self):
+    ps = (self.a0, self.a1, self.b, self.b1)
+    if any(callable(p) or np.ndim(p) != 0 for p in ps):
+      return None
+    return ('affine1f',) + tuple(float(p) for p in ps)
 
   def general_table(self, all_times, dtype):
     """The six columns dt, sqrt_dt, a0, a1, b0, b1 of TQF_MODEL_AFFINE_1F."""
@@ -348,6 +360,10 @@ class Payoff:
     self.component, self.log_state, self.scale = int(component), bool(log_state), float(scale)
     self.tangent = int(tangent)
     self.brownian_bridge = bool(brownian_bridge)
+
+  def key(self):
+    return (self.kind, self.strike, self.barrier, self.component, self.log_state, self.scale,
+            self.tangent, self.brownian_bridge)
 
   def desc(self):
     d = _lib.PayoffDesc()
@@ -640,6 +656,32 @@ class Plan:
       _lib.check(_lib.lib().tqf_plan_peer_epoch(self._handle, C.byref(ep)))
       px.epoch = int(ep.value)
     return sums
+
+
+class HostPricing:
+  """A plan with its payoff descriptors and result buffers bound once: `sums()` is a
+  single FFI call (`tqf_plan_price_host`: kernels, read-back, synchronisation).  What a
+  repeated pricing call with identical arguments runs (`euler_sampling.price`)."""
+
+  def __init__(self, plan, payoffs):
+    self.plan = plan
+    self.count = len(payoffs)
+    self.descs = (_lib.PayoffDesc * self.count)(*[p.desc() for p in payoffs])
+    self.sums_dev = torch.empty((self.count, 4), dtype=torch.float64, device=_tensor.device())
+    self.sums_host = np.empty((self.count, 4), dtype=np.float64)
+    self._fn = _lib.lib().tqf_plan_price_host
+    self._args = (plan._handle, 0, plan.units, self.descs, self.count, self.sums_dev.data_ptr(),
+                  self.sums_host.ctypes.data)
+
+  def sums(self):
+    plan = self.plan
+    if getattr(plan, '_peer_exchange', None) is not None:
+      plan.clear_peer_exchange()
+    _lib.check(self._fn(*self._args, torch.cuda.current_stream().cuda_stream))
+    return self.sums_host
+
+  def alive(self):
+    return getattr(self.plan, '_handle', None) is not None
 
 
 # ------------------------------------------------------------ plan cache ----

@@ -8,7 +8,10 @@ draws tensor of the reference is never built: normals are generated in the
 kernel that steps the paths.  `price` is the fused extension that also
 reduces payoffs in-kernel (no path leaves the registers).
 """
+import collections
+
 import numpy as np
+import torch
 
 from tff_b200 import _lib
 from tff_b200 import _tensor
@@ -194,6 +197,45 @@ def sample(dim,
       plan.close()
 
 
+# A pricing call whose arguments are all plain numbers / small arrays is recognised by
+# their CONTENT the second time it is made (a calibration loop, a risk run re-pricing the
+# same book): the plan, the payoff descriptors and the result buffers stay bound and the
+# call is one FFI call.  Models with callable parameters, `normal_draws=`, sharded runs
+# and anything large are never bound (`_call_key` returns None).
+_CALLS = collections.OrderedDict()
+_CALLS_SIZE = 8
+
+
+def _small(a):
+  if a is None:
+    return None
+  a = np.asarray(_tensor.to_numpy(a))
+  if a.size > 64 or a.dtype == object:
+    raise OverflowError
+  return (a.dtype.str, a.shape, a.tobytes())
+
+
+def _call_key(dim, drift_fn, volatility_fn, times, payoffs, time_step, num_time_steps,
+              num_samples, initial_state, random_type, seed, skip, times_grid, normal_draws,
+              tolerance, dtype):
+  if normal_draws is not None or distributed._SHARDED is not None:   # pylint: disable=protected-access
+    return None
+  spec = getattr(drift_fn, 'tqf_spec', None)
+  if spec is None or spec is not getattr(volatility_fn, 'tqf_spec', None):
+    return None
+  model = spec.constant_key()
+  if model is None or not all(isinstance(p, engine.Payoff) for p in payoffs):
+    return None
+  try:
+    return (torch.cuda.current_device(), int(dim), model, _small(times), tuple(p.key() for p in payoffs),
+            _small(time_step), None if num_time_steps is None else int(num_time_steps),
+            int(num_samples), _small(initial_state),
+            None if random_type is None else random_type.value, _small(seed), int(skip),
+            _small(times_grid), tolerance, None if dtype is None else np.dtype(_tensor.np_dtype(dtype)).str)
+  except (OverflowError, TypeError, ValueError):
+    return None
+
+
 def price(dim, drift_fn, volatility_fn, times, payoffs, time_step=None,
           num_time_steps=None, num_samples=1, initial_state=None,
           random_type=None, seed=None, skip=0, times_grid=None,
@@ -206,25 +248,37 @@ def price(dim, drift_fn, volatility_fn, times, payoffs, time_step=None,
   Returns a float64 numpy array `[len(payoffs)]`; with `return_stats` also the
   standard errors and the number of non-finite payoffs.
   """
-  plans, _, _, batch_shape = _prepare(
-      dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
-      num_samples, initial_state, random_type, seed, skip, times_grid,
-      normal_draws, None, validate_args, tolerance, dtype, use_cache=True)
-  if batch_shape:
-    for plan in plans:
+  key = _call_key(dim, drift_fn, volatility_fn, times, payoffs, time_step, num_time_steps,
+                  num_samples, initial_state, random_type, seed, skip, times_grid, normal_draws,
+                  tolerance, dtype)
+  bound = _CALLS.get(key) if key is not None else None
+  if bound is not None and bound.alive():
+    _CALLS.move_to_end(key)
+    plan, sums = bound.plan, bound.sums()
+  else:
+    plans, _, _, batch_shape = _prepare(
+        dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
+        num_samples, initial_state, random_type, seed, skip, times_grid,
+        normal_draws, None, validate_args, tolerance, dtype, use_cache=True)
+    if batch_shape:
+      for plan in plans:
+        plan.release()
+      raise NotImplementedError('batched processes are not supported by `price` yet')
+    plan = plans[0]
+    try:
+      sums = distributed.price_sums_host(plan, payoffs)
+      if key is not None and plan.cached:
+        _CALLS[key] = engine.HostPricing(plan, payoffs)
+        while len(_CALLS) > _CALLS_SIZE:
+          _CALLS.popitem(last=False)
+    finally:
       plan.release()
-    raise NotImplementedError('batched processes are not supported by `price` yet')
-  plan = plans[0]
-  try:
-    sums = distributed.price_sums_host(plan, payoffs)
-  finally:
-    plan.release()
   n = float(plan.num_samples)
   mean = sums[:, 0] / n
   if not return_stats:
     return mean
   var = np.maximum(sums[:, 1] / n - mean**2, 0.0)
-  return mean, np.sqrt(var / n), sums[:, 2]
+  return mean, np.sqrt(var / n), sums[:, 2].copy()
 
 
 __all__ = ['sample', 'price']
