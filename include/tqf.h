@@ -77,6 +77,7 @@ extern "C" {
  * rows, so its Wiener process has F + F^2 components of which the first F act);
  * supported (F, num_factors): (1,1) (1,2) (2,2) (2,6) (3,3).  x0 = 0.         */
 #define TQF_MODEL_HJM 11
+#define TQF_MODEL_HESTON_TANGENT 12 /* Heston Euler + tangents of (X, V) wrt one parameter: state [X, V, dX, dV] */
 
 /* payoff kinds (reduced in-kernel; callers: e.g. hull_white/swaption.py:310) */
 #define TQF_PAYOFF_CALL 1          /* max(f(X_T) - K, 0)                    */

@@ -113,3 +113,112 @@ def test_gpu_fused_delta_vega_notebook_setup():
     delta, vega = _bs(SPOT, k, SIGMA, R, expiry)
     assert abs(got[3 * i + 1] - delta) < 5e-3 * delta
     assert abs(got[3 * i + 2] - vega) < 0.1 * vega
+
+
+# ------------------------------------------------------------------ Heston ----
+HESTON = dict(mean_reversion=2.0, theta=0.04, volvol=0.5, rho=-0.7)
+H_X0 = np.array([np.log(100.0), 0.04])
+
+
+def _oracle_heston(params, x0, times, **kw):
+  from oracle import models as omodels
+  d, v = omodels.heston_closures(params['mean_reversion'], params['theta'], params['volvol'],
+                                 params['rho'], np.float64)
+  return oeuler.sample(2, d, v, times, initial_state=np.asarray(x0, dtype=np.float64),
+                       dtype=np.float64, **kw)
+
+
+@pytest.mark.parametrize('rt', ['STATELESS_ANTITHETIC', 'SOBOL'])
+def test_oracle_heston_tangents_equal_finite_differences(rt):
+  kw = dict(num_samples=256, random_type=odraws.RandomType[rt], seed=[4, 2], num_time_steps=24)
+  times = [0.5, 1.0]
+  zero = dict(d_mean_reversion=0.0, d_theta=0.0, d_volvol=0.0, d_rho=0.0, d_initial_state=(0.0, 0.0))
+  base = _oracle_heston(HESTON, H_X0, times, **kw)
+  h = 1e-6
+  cases = [('mean_reversion', 'd_mean_reversion'), ('theta', 'd_theta'), ('volvol', 'd_volvol'),
+           ('rho', 'd_rho'), ('x0', None), ('v0', None)]
+  for name, dname in cases:
+    d = dict(zero)
+    if name == 'x0':
+      d['d_initial_state'] = (1.0, 0.0)
+      up, dn = (_oracle_heston(HESTON, H_X0 + s * np.array([h, 0.0]), times, **kw) for s in (1, -1))
+    elif name == 'v0':
+      d['d_initial_state'] = (0.0, 1.0)
+      up, dn = (_oracle_heston(HESTON, H_X0 + s * np.array([0.0, h]), times, **kw) for s in (1, -1))
+    else:
+      d[dname] = 1.0
+      up, dn = (_oracle_heston(dict(HESTON, **{name: HESTON[name] + s * h}), H_X0, times, **kw)
+                for s in (1, -1))
+    got = otangent.heston_with_tangents(**HESTON, **d, times=times, initial_state=H_X0, **kw)
+    np.testing.assert_array_equal(got[..., :2], base)          # the path itself is untouched
+    fd = (up - dn) / (2 * h)
+    # paths whose variance crosses zero inside the step have a kink in |V|: compare the bulk
+    ok = np.abs(got[..., 2:] - fd) <= 1e-5 + 1e-5 * np.abs(fd)
+    assert ok.mean() > 0.97, (name, ok.mean())
+    np.testing.assert_allclose(np.median(got[..., 2:], axis=0), np.median(fd, axis=0), rtol=1e-5,
+                               atol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('rt', ['STATELESS_ANTITHETIC', 'SOBOL', 'STATELESS'])
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_gpu_heston_tangent_paths_match_oracle(rt, dtype):
+  import tff_b200 as tff
+  from tff_b200.models import closures
+  d = dict(d_mean_reversion=0.3, d_theta=-0.2, d_volvol=1.0, d_rho=0.5, d_initial_state=(0.25, 1.0))
+  kw = dict(num_samples=3000, seed=[4, 2], time_step=0.04)
+  drift, vol = closures.heston_tangent_closures(**HESTON, **d)
+  got = tff.models.euler_sampling.sample(
+      2, drift, vol, [0.4, 1.0], initial_state=H_X0.astype(dtype),
+      random_type=tff.math.random.RandomType[rt], dtype=dtype, **kw).cpu().numpy()
+  want = otangent.heston_with_tangents(**HESTON, **d, times=[0.4, 1.0], initial_state=H_X0,
+                                       random_type=odraws.RandomType[rt], dtype=dtype, **kw)
+  assert got.shape == want.shape == (3000, 2, 4) and got.dtype == dtype
+  if dtype == np.float64:
+    np.testing.assert_allclose(got[..., :2], want[..., :2], rtol=1e-12, atol=1e-14)
+    # the tangents carry 1 / (2 sqrt|V|): rounding differences of V at the 1e-16 level are
+    # amplified where a path's variance comes close to zero
+    np.testing.assert_allclose(got[..., 2:], want[..., 2:], rtol=1e-8, atol=1e-9)
+  else:
+    np.testing.assert_allclose(got[..., :2], want[..., :2], rtol=1e-5, atol=5e-6)
+    ok = np.abs(got - want) <= 2e-4 * np.maximum(1.0, np.abs(want))
+    assert ok.mean() > 0.995          # float32 tangents amplify the rounding of 1 / sqrt|V| near 0
+
+
+@pytest.mark.gpu
+def test_gpu_heston_fused_vega_and_delta():
+  # d price / d V_0 and d price / d S_0 of a call, fused, against the same estimators on the
+  # oracle's materialised tangent paths and against a finite difference of fused prices
+  import tff_b200 as tff
+  from tff_b200 import engine
+  from tff_b200.models import closures
+  T = engine.TangentHestonSpec
+  n, steps, strike = 1 << 17, 50, 100.0
+  rt = tff.math.random.RandomType.SOBOL
+  kw = dict(num_samples=n, initial_state=H_X0, num_time_steps=steps, dtype=np.float64)
+  # vol-of-vol 0.3 satisfies the Feller condition: with 0.5 the Euler variance hits zero on
+  # many paths, where d sqrt|V| / dV is unbounded -- the pathwise estimator is then heavy-tailed
+  # and sits 3% away from a finite difference at 2^17 paths
+  HESTON = dict(mean_reversion=2.0, theta=0.04, volvol=0.3, rho=-0.7)
+  out = {}
+  for name, d0 in (('vega_v0', (0.0, 1.0)), ('delta_log', (1.0, 0.0))):
+    drift, vol = closures.heston_tangent_closures(**HESTON, d_initial_state=d0)
+    pay = [engine.european_call(strike, log_state=True),
+           engine.european_call_tangent(strike, T.D_X, log_state=True)]
+    got = tff.models.euler_sampling.price(2, drift, vol, [1.0], pay, random_type=rt, **kw)
+    o = otangent.heston_with_tangents(**HESTON, d_mean_reversion=0.0, d_theta=0.0, d_volvol=0.0,
+                                      d_rho=0.0, d_initial_state=d0, times=[1.0], initial_state=H_X0,
+                                      num_samples=n, random_type=odraws.RandomType.SOBOL,
+                                      num_time_steps=steps)[:, 0, :]
+    s = np.exp(o[:, 0])
+    want = [np.maximum(s - strike, 0).mean(), ((s > strike) * s * o[:, 2]).mean()]
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    out[name] = got
+  # finite difference of the fused price in V_0 (same Sobol points): the pathwise vega
+  model = tff.models.HestonModel(dtype=np.float64, **HESTON)
+  h = 1e-4
+  up, dn = (model.price([1.0], [engine.european_call(strike, log_state=True)], num_samples=n,
+                        initial_state=H_X0 + s * np.array([0.0, h]), random_type=rt,
+                        num_time_steps=steps)[0] for s in (1, -1))
+  np.testing.assert_allclose(out['vega_v0'][1], (up - dn) / (2 * h), rtol=1e-2)
+  assert 0.4 < out['delta_log'][1] / 100.0 < 0.9          # d price / d S_0 = (d price / d log S_0) / S_0

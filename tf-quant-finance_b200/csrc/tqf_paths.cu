@@ -96,6 +96,7 @@ static bool model_info(int kind, int dim, int num_factors, ModelInfo* info) {
     case TQF_MODEL_MVGBM: *info = {dim, dim, 2}; return dim >= 1 && dim <= 64;
     case TQF_MODEL_AFFINE_1F: *info = {1, 1, 6}; return true;
     case TQF_MODEL_AFFINE_1F_TANGENT: *info = {3, 1, 10}; return true;
+    case TQF_MODEL_HESTON_TANGENT: *info = {4, 2, 12}; return true;
     case TQF_MODEL_MILSTEIN_1F: *info = {1, 1, 6}; return true;
     case TQF_MODEL_AFFINE_ND:
       *info = {dim, dim, 2 + dim + 2 * dim * dim};
@@ -245,6 +246,9 @@ static int dispatch(const tqf_plan* plan, int mode, int grid, size_t smem, const
       return launch_path_kernel<LinearModel1F<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     case TQF_MODEL_HESTON_EULER:
       return launch_path_kernel<HestonEulerModel<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
+    case TQF_MODEL_HESTON_TANGENT:
+      return launch_path_kernel<TangentHestonModel<Real>>(rk, anti, mode, grid, smem, P, stream,
+                                                          grid_out);
     case TQF_MODEL_HW1F:
       return launch_path_kernel<HullWhite1FModel<Real>>(rk, anti, mode, grid, smem, P, stream, grid_out);
     case TQF_MODEL_HESTON_QE:

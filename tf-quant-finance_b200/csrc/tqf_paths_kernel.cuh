@@ -327,6 +327,39 @@ struct HestonEulerModel {  // heston/heston_model.py:143-173; state [X = log S, 
   __device__ static __forceinline__ float sqrt_abs(float v) { return sqrtf(fabsf(v)); }
 };
 
+// HestonEulerModel with the pathwise tangents of (X, V) with respect to ONE scalar
+// parameter p (forward-mode sensitivities: what the reference obtains by differentiating
+// the Euler loop with `watch_params`, euler_sampling.py:393-402).  State
+// [X, V, dX/dp, dV/dp]; with s = sqrt|V|, ds = sign(V) (dV/dp) / (2 s) and the PRE-step
+// state on the right-hand sides (differentiating _euler_step with the closures of
+// heston/heston_model.py:143-173):
+//   dX/dp' = dX/dp - dt (dV/dp) / 2 + ds dw0
+//   dV/dp' = dV/dp + dt (dkappa (theta - V) + kappa (dtheta - dV/dp))
+//            + (dxi s + xi ds) (rho dw0 + rhobar dw1) + xi s (drho dw0 + drhobar dw1).
+// c: dt, sqrt_dt, kappa, theta, xi, rho, rhobar, dkappa, dtheta, dxi, drho, drhobar.
+// The primal follows the reference grouping (x + dt drift) + vol . dw.
+template <typename R>
+struct TangentHestonModel {
+  using Real = R;
+  static constexpr int DIM = 4, NF = 2, NCOEF = 12;
+  __device__ static __forceinline__ void step(Real (&x)[DIM], const Real (&z)[NF],
+                                              const Real (&c)[NCOEF]) {
+    const Real dw0 = z[0] * c[1], dw1 = z[1] * c[1];
+    const Real v = x[1], vt = x[3];
+    const Real s = sqrt(v < Real(0) ? -v : v);
+    const Real ds = s > Real(0) ? (v < Real(0) ? -vt : vt) / (Real(2) * s) : Real(0);
+    const Real w = c[5] * dw0 + c[6] * dw1;
+    const Real wp = c[9 + 1] * dw0 + c[9 + 2] * dw1;
+    const Real xt = (x[2] + c[0] * (Real(-0.5) * vt)) + ds * dw0;
+    const Real vtn = (vt + c[0] * (c[7] * (c[3] - v) + c[2] * (c[8] - vt))) +
+                     ((c[9] * s + c[4] * ds) * w + (c[4] * s) * wp);
+    x[0] = (x[0] + c[0] * (Real(-0.5) * v)) + s * dw0;
+    x[1] = (v + c[0] * (c[2] * (c[3] - v))) + (c[4] * s) * w;
+    x[2] = xt;
+    x[3] = vtn;
+  }
+};
+
 template <typename R>
 struct HestonQeModel {
   // Andersen's Quadratic-Exponential step (heston/heston_model.py:402-431,

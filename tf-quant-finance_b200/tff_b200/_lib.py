@@ -31,6 +31,7 @@ MODEL_AFFINE_ND = 8
 MODEL_AFFINE_1F_TANGENT = 9
 MODEL_MILSTEIN_1F = 10
 MODEL_HJM = 11
+MODEL_HESTON_TANGENT = 12
 PAYOFF_CALL = 1
 PAYOFF_PUT = 2
 PAYOFF_UP_OUT_CALL = 3

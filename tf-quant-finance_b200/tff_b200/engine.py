@@ -310,6 +310,40 @@ class HestonEulerSpec(ModelSpec):
     return np.stack(cols, -1).astype(np.float64)
 
 
+class TangentHestonSpec(ModelSpec):
+  """`HestonEulerSpec` carrying the pathwise tangents of `(X, V)` with respect to ONE
+  scalar `p` alongside the path (the forward-mode sensitivities the reference obtains by
+  differentiating the Euler loop with `watch_params`, `euler_sampling.py:393-402`).
+  `d_mean_reversion`, `d_theta`, `d_volvol`, `d_rho` are the derivatives of the four
+  parameters with respect to `p`, `d_initial_state` those of `[X_0, V_0]` (so vega-type
+  sensitivities to `V_0` and delta come from the same kernel).  Device state
+  `[X, V, dX/dp, dV/dp]`; the user-facing dimension stays 2 and the draws are those of
+  the plain Heston process."""
+  kind, dim, num_factors, num_coef = _lib.MODEL_HESTON_TANGENT, 4, 2, 12
+  user_dim = 2
+  X, V, D_X, D_V = 0, 1, 2, 3          # state components
+
+  def __init__(self, mean_reversion, theta, volvol, rho, d_mean_reversion=0.0, d_theta=0.0,
+               d_volvol=0.0, d_rho=0.0, d_initial_state=(0.0, 0.0)):
+    self.p = (mean_reversion, theta, volvol, rho)
+    self.d = (d_mean_reversion, d_theta, d_volvol, d_rho)
+    self.d_initial_state = tuple(float(v) for v in d_initial_state)
+
+  def coef_table(self, all_times, dtype):
+    t, dt, sq = self._dt_columns(all_times, dtype)
+    ty = np.dtype(dtype).type
+    kappa, theta, volvol, rho = (_eval_param(q, t, dtype) for q in self.p)
+    dk, dth, dxi, drho = (_eval_param(q, t, dtype) for q in self.d)
+    rhobar = np.sqrt(ty(1) - rho**2).astype(dtype)
+    drhobar = (-(rho * drho) / rhobar).astype(dtype)
+    cols = [dt, sq, kappa, theta, volvol, rho, rhobar, dk, dth, dxi, drho, drhobar]
+    return np.stack(cols, -1).astype(np.float64)
+
+  def extend_initial_state(self, x0):
+    x0 = np.asarray(x0).reshape(-1)[:2]
+    return np.concatenate([x0, np.asarray(self.d_initial_state, dtype=x0.dtype)])
+
+
 class MvGbmSpec(ModelSpec):
   """Correlated multi-asset GBM closures
   (`geometric_brownian_motion/multivariate_geometric_brownian_motion.py:130-151`):

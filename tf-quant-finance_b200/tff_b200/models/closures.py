@@ -143,6 +143,21 @@ def heston_closures(mean_reversion, theta, volvol, rho):
   return DeviceClosure(spec, 'drift', drift), DeviceClosure(spec, 'volatility', vol)
 
 
+def heston_tangent_closures(mean_reversion, theta, volvol, rho, d_mean_reversion=0.0, d_theta=0.0,
+                            d_volvol=0.0, d_rho=0.0, d_initial_state=(0.0, 0.0)):
+  """`heston_closures` whose sampler also carries the pathwise tangents of `(X, V)` with
+  respect to one scalar `p`: `sample` returns `[N, k, 4]` with the components
+  `[X, V, dX/dp, dV/dp]`, `price` accepts the `*_tangent` payoffs on component
+  `TangentHestonSpec.D_X`.  `d_*` are the derivatives of the parameters / of the initial
+  state with respect to `p`: vega to the initial variance is `d_initial_state=(0, 1)`,
+  the sensitivity to the vol-of-vol `d_volvol=1`, delta `d_initial_state=(1, 0)`."""
+  spec = engine.TangentHestonSpec(mean_reversion, theta, volvol, rho, d_mean_reversion, d_theta,
+                                  d_volvol, d_rho, d_initial_state)
+  drift, vol = heston_closures(mean_reversion, theta, volvol, rho)
+  return (DeviceClosure(spec, 'drift', drift._host_fn),   # pylint: disable=protected-access
+          DeviceClosure(spec, 'volatility', vol._host_fn))   # pylint: disable=protected-access
+
+
 def mvgbm_closures(means, volatilities, corr_matrix, dim):
   """(drift_fn, volatility_fn) of the correlated multi-asset GBM
   (`multivariate_geometric_brownian_motion.py:130-151`)."""
