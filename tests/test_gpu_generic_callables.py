@@ -163,8 +163,13 @@ def test_argument_errors():
            random_type=tff.math.random.RandomType.PSEUDO_ANTITHETIC, dtype=np.float64)
   with pytest.raises(NotImplementedError):                               # not affine
     sample(1, lambda t, x: torch.sin(x), vol, [1.0], time_step=0.5, seed=1, dtype=np.float64)
-  with pytest.raises(NotImplementedError):
-    sample(1, drift, vol, [1.0], time_step=0.5, seed=1, watch_params=[1.0], dtype=np.float64)
+  # `watch_params` only steers how TensorFlow differentiates the loop: same forward paths
+  rt = tff.math.random.RandomType.STATELESS
+  a = sample(1, drift, vol, [1.0], time_step=0.5, seed=[1, 2], random_type=rt, num_samples=64,
+             watch_params=[1.0], dtype=np.float64)
+  b = sample(1, drift, vol, [1.0], time_step=0.5, seed=[1, 2], random_type=rt, num_samples=64,
+             dtype=np.float64)
+  assert torch.equal(a, b)
 
 
 def test_repeated_price_calls_are_bound_by_content():

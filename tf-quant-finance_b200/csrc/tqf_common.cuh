@@ -101,6 +101,19 @@ __host__ __device__ __forceinline__ uint4 philox_group(const PhiloxCtr& base,
                        key.k0, key.k1);
 }
 
+// The same for kernels that carry `lo` = low 64 counter bits + group number themselves
+// (one 64-bit increment per refill instead of a 128-bit add with carry detection: 7
+// instructions per Philox call).  Valid while the low half cannot wrap: plans require a
+// base below 2^63 (TensorFlow's seed derivations start it at 0), groups stay below 2^62.
+__device__ __forceinline__ uint64_t philox_base_lo(const PhiloxCtr& base) {
+  return (static_cast<uint64_t>(base.c1) << 32) | base.c0;
+}
+__device__ __forceinline__ uint4 philox_group_nowrap(const PhiloxCtr& base, const PhiloxKey& key,
+                                                     uint64_t lo) {
+  return philox4x32_10(static_cast<uint32_t>(lo), static_cast<uint32_t>(lo >> 32), base.c2, base.c3,
+                       key.k0, key.k1);
+}
+
 // tensorflow/core/lib/random/random_distributions.h: Uint64ToDouble.
 __device__ __forceinline__ double uint64_to_double(uint32_t x0, uint32_t x1) {
   const uint32_t hi = (x0 & 0xFFFFFu) | 0x3FF00000u;

@@ -552,6 +552,10 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
   TQF_REQUIRE(rng->type == TQF_RNG_PHILOX || rng->type == TQF_RNG_SOBOL ||
                   rng->type == TQF_RNG_DRAWS,
               "unknown rng type");
+  if (rng->type == TQF_RNG_PHILOX)
+    TQF_REQUIRE((rng->counter[1] >> 31) == 0,
+                "Philox counter: the low 64 bits must start below 2^63 (TensorFlow's seed "
+                "derivations start them at 0)");
   if (rng->antithetic) {
     TQF_REQUIRE(rng->type == TQF_RNG_PHILOX, "antithetic sampling needs the Philox generator");
     TQF_REQUIRE(num_paths_total % 2 == 0,
@@ -649,7 +653,12 @@ int tqf_plan_destroy(tqf_plan* plan) {
   if (!plan) return TQF_OK;
   void* blocks[7] = {plan->coef_dev,     plan->sobol_dev,  plan->lsplit_dev,   plan->colsum_dev,
                      plan->partials_dev, plan->record_dev, plan->swaptions_dev};
+  // (the blocks belong to the plan's device, whichever device is current in this thread)
+  int current = -1;
+  cudaGetDevice(&current);
+  if (current != plan->device) cudaSetDevice(plan->device);
   dev_release(blocks, 7);
+  if (current >= 0 && current != plan->device) cudaSetDevice(current);
   delete plan->record_cache;
   delete plan;
   return TQF_OK;

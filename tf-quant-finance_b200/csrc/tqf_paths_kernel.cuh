@@ -529,7 +529,7 @@ __device__ __forceinline__ void philox_box_muller_v(const PhiloxKey& key, const 
   double u1[PPT], v1[PPT], w[PPT], sn[PPT], cs[PPT];
 #pragma unroll
   for (int a = 0; a < PPT; ++a) {
-    const uint4 q = philox_group(ctr, key, group[a]);
+    const uint4 q = philox_group_nowrap(ctr, key, group[a]);   // group[] = counter low half
     ++group[a];
     u1[a] = uint64_to_double(q.x, q.y);
     v1[a] = 6.283185307179586476925286766559 * uint64_to_double(q.z, q.w);
@@ -568,7 +568,7 @@ struct PhiloxStreamV<double, PPT> {
                                        const Tab& tab,
                                        const uint64_t (&first_element)[PPT]) {
 #pragma unroll
-    for (int a = 0; a < PPT; ++a) group[a] = first_element[a] >> 1;
+    for (int a = 0; a < PPT; ++a) group[a] = philox_base_lo(ctr) + (first_element[a] >> 1);
     refill(key, ctr, tab);
     pos = static_cast<int>(first_element[0] & 1);
   }
@@ -593,7 +593,7 @@ struct PhiloxStreamV<float, PPT> {
   __device__ __forceinline__ void refill(const PhiloxKey& key, const PhiloxCtr& ctr) {
 #pragma unroll
     for (int a = 0; a < PPT; ++a) {
-      const uint4 w = philox_group(ctr, key, group[a]);
+      const uint4 w = philox_group_nowrap(ctr, key, group[a]);
       ++group[a];
       box_muller(w.x, w.y, &b[a][0], &b[a][1]);
       box_muller(w.z, w.w, &b[a][2], &b[a][3]);
@@ -604,7 +604,7 @@ struct PhiloxStreamV<float, PPT> {
                                        const Tab&,
                                        const uint64_t (&first_element)[PPT]) {
 #pragma unroll
-    for (int a = 0; a < PPT; ++a) group[a] = first_element[a] >> 2;
+    for (int a = 0; a < PPT; ++a) group[a] = philox_base_lo(ctr) + (first_element[a] >> 2);
     refill(key, ctr);
     pos = static_cast<int>(first_element[0] & 3);
   }
@@ -1139,7 +1139,7 @@ path_kernel(const KParams<typename Model::Real> P) {
     if (kPhiloxPairs) {
       uint64_t group[PPT];
 #pragma unroll
-      for (int a = 0; a < PPT; ++a) group[a] = first_element[a] >> 1;
+      for (int a = 0; a < PPT; ++a) group[a] = philox_base_lo(P.ctr) + (first_element[a] >> 1);
       double g0[PPT], g1[PPT];
       Real z[PPT][NF];
       int s = 0;

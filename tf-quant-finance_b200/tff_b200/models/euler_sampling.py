@@ -30,13 +30,12 @@ def _prepare(dim, drift_fn, volatility_fn, times, time_step, num_time_steps,
              num_samples, initial_state, random_type, seed, skip, times_grid,
              normal_draws, watch_params, validate_args, tolerance, dtype, use_cache=False):
   """Argument normalisation of `sample` (`euler_sampling.py:232-310`)."""
-  if watch_params is not None:
-    raise NotImplementedError(
-        '`watch_params` relies on TensorFlow differentiating Python closures. The '
-        'B200 engine carries the pathwise tangents in-kernel for the 1-d affine '
-        'family instead: build the closures with '
-        'closures.affine_tangent_closures(..., da0=, da1=, db=, db1=) and read '
-        'dX/dX0, dX/dtheta from the extra state components (SURVEY 8f-3).')
+  # `watch_params` (euler_sampling.py:393-402, 467-510) only chooses how TensorFlow
+  # DIFFERENTIATES the loop (custom_loops.for_loop instead of tf.while_loop); the sampled
+  # paths do not depend on it, and they are what this engine returns.  Sensitivities are
+  # carried in-kernel by the tangent closures instead (closures.affine_tangent_closures,
+  # closures.heston_tangent_closures: dX/dX0, dX/dtheta as extra state components).
+  del watch_params
   dtype = _tensor.infer_dtype(times, dtype)
   times = _tensor.to_numpy(times, dtype).reshape(-1)
   if tolerance is None:

@@ -45,8 +45,7 @@ def sample(*, dim, drift_fn, volatility_fn, times, time_step=None, num_time_step
   """
   del swap_memory, precompute_normal_draws, name, grad_volatility_fn
   dim = int(dim)
-  if watch_params is not None:
-    raise NotImplementedError('`watch_params` is not implemented by the B200 Milstein sampler')
+  del watch_params   # steers TensorFlow's differentiation of the loop only: same forward paths
   dtype = _tensor.infer_dtype(times, dtype)
   times = _tensor.to_numpy(times, dtype).reshape(-1)
   if num_time_steps is not None and time_step is not None:
