@@ -93,3 +93,41 @@ def test_tc5_counts_non_finite_paths_like_the_mma_kernel():
   assert out[True][2][0] >= 1
   np.testing.assert_array_equal(out[True][2], out[False][2])
   np.testing.assert_allclose(out[True][0], out[False][0], rtol=2e-5)
+
+
+@pytest.mark.parametrize('dim', [9, 17, 40, 63])
+def test_tc5_narrower_models(dim):
+  # 8 < dim < 64: padded factors / assets (zero rows of B, discarded draws)
+  from tff_b200 import engine
+  dtype = np.float32
+  tff, model, (odrift, ovol), x0 = _setup(dim, dtype)
+  n, steps = 1500, 7
+  kw = dict(num_samples=n, initial_state=x0, num_time_steps=steps)
+  payoffs = [engine.european_call(100.0, component=-1), engine.identity(component=dim - 1),
+             engine.identity(component=0)]
+  with _Tc5(True):
+    got = model.price_euler([1.0], payoffs, random_type=tff.math.random.RandomType.SOBOL, **kw)
+  with _Tc5(False):
+    legacy = model.price_euler([1.0], payoffs, random_type=tff.math.random.RandomType.SOBOL, **kw)
+  paths = oeuler.sample(dim, odrift, ovol, [1.0], random_type=odraws.RandomType.SOBOL, dtype=dtype,
+                        **kw)[:, 0, :].astype(np.float64)
+  want = [np.maximum(paths.mean(axis=1) - 100, 0).mean(), paths[:, dim - 1].mean(), paths[:, 0].mean()]
+  np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-4)
+  np.testing.assert_allclose(got, legacy, rtol=2e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize('dim', [17, 64])
+def test_tc5_materialised_paths_match_oracle(dim):
+  dtype = np.float32
+  tff, model, (odrift, ovol), x0 = _setup(dim, dtype)
+  kw = dict(num_samples=700, initial_state=x0, skip=300, num_time_steps=10)
+  rt = tff.math.random.RandomType.SOBOL
+  with _Tc5(True):
+    got = model.sample_paths_euler([0.5, 1.0], random_type=rt, **kw).cpu().numpy()
+  with _Tc5(False):
+    legacy = model.sample_paths_euler([0.5, 1.0], random_type=rt, **kw).cpu().numpy()
+  want = oeuler.sample(dim, odrift, ovol, [0.5, 1.0], random_type=odraws.RandomType.SOBOL,
+                       dtype=dtype, **kw)
+  assert got.shape == want.shape == (700, 2, dim) and got.dtype == dtype
+  np.testing.assert_allclose(got, want, rtol=1e-5)
+  np.testing.assert_allclose(got, legacy, rtol=1e-5)

@@ -1217,13 +1217,18 @@ constexpr int kT5StageIters = kMvDim * 8 / kT5Threads;
 struct T5Words {
   uint4 w[kT5StageIters];
 };
-__device__ __forceinline__ T5Words t5_stage_load(const uint32_t* __restrict__ sobol_v, int s, int tid) {
+// (dimensions beyond `dim` of a narrower model are staged as zero words: their draws are
+// discarded by the kernel)
+__device__ __forceinline__ T5Words t5_stage_load(const uint32_t* __restrict__ sobol_v, int s, int dim,
+                                                 int tid) {
   T5Words r;
 #pragma unroll
   for (int it = 0; it < kT5StageIters; ++it) {
     const int dd = it * (kT5Threads / 8) + (tid >> 3);
-    r.w[it] = __ldg(reinterpret_cast<const uint4*>(sobol_v + (static_cast<size_t>(s) * kMvDim + dd) * 32) +
-                    (tid & 7));
+    r.w[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (dd < dim)
+      r.w[it] = __ldg(reinterpret_cast<const uint4*>(sobol_v + (static_cast<size_t>(s) * dim + dd) * 32) +
+                      (tid & 7));
   }
   return r;
 }
@@ -1258,11 +1263,13 @@ __device__ __forceinline__ void t5_stage_write(const T5Words& r, uint32_t high_b
     if (q < 4) sH[q * kT5HStride + dd] = h ^ (v5 & (0u - (q & 1u))) ^ (v6 & (0u - ((q >> 1) & 1u)));
   }
 }
-__device__ __forceinline__ void t5_stage(const uint32_t* __restrict__ sobol_v, int s,
+__device__ __forceinline__ void t5_stage(const uint32_t* __restrict__ sobol_v, int s, int dim,
                                          uint32_t high_bits, uint32_t* sT, uint32_t* sH, int tid) {
-  t5_stage_write(t5_stage_load(sobol_v, s, tid), high_bits, sT, sH, tid);
+  t5_stage_write(t5_stage_load(sobol_v, s, dim, tid), high_bits, sT, sH, tid);
 }
 
+// FULL: dim == 64 (no padding checks in the draw loop).
+template <bool FULL>
 __global__ void __launch_bounds__(kT5Threads, 2)
 mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
   extern __shared__ __align__(1024) unsigned char t5_smem[];
@@ -1331,8 +1338,21 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
     for (int i = 0; i < kT5Half; ++i) x[i] = P.x0[half * kT5Half + i];
 
     // (called by all threads together: d.step and the payoff list are uniform)
-    auto record = [&](int step_index) {
+    auto record = [&](int step_index, int slot) {
       const int dim = P.dim;
+      if (P.mode != MODE_PRICE) {
+        // path materialisation: every thread stores its 32 assets of path p
+        if (valid) {
+          float* o = P.out + static_cast<int64_t>(index - P.first_index) * P.stride_path +
+                     static_cast<int64_t>(slot) * P.stride_time;
+#pragma unroll
+          for (int i = 0; i < kT5Half; ++i) {
+            const int a = half * kT5Half + i;
+            if (FULL || a < dim) o[a * P.stride_dim] = P.store_exp ? expf(x[i]) : x[i];
+          }
+        }
+        return;
+      }
       for (int pq = 0; pq < P.num_payoffs; ++pq) {
         const PayoffK& d = P.pay[pq];
         if (d.step != step_index) continue;
@@ -1371,10 +1391,10 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
         }
       }
     };
-    if (P.record_slot[0] >= 0) record(0);
+    if (P.record_slot[0] >= 0) record(0, P.record_slot[0]);
 
     __syncthreads();                       // every reader of the staging buffers is done
-    t5_stage(P.sobol_v, 0, high_bits, sT, sH, tid);
+    t5_stage(P.sobol_v, 0, P.dim, high_bits, sT, sH, tid);
     __syncthreads();
 
 #pragma unroll 1
@@ -1384,7 +1404,7 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
       const uint32_t* sHb = sH + buf * (4 * kT5HStride) + pw * kT5HStride + half * kT5Half;
       const float dt = P.coef[2 * s], sqdt = P.coef[2 * s + 1];
       T5Words next;
-      if (s + 1 < P.num_steps) next = t5_stage_load(P.sobol_v, s + 1, tid);
+      if (s + 1 < P.num_steps) next = t5_stage_load(P.sobol_v, s + 1, P.dim, tid);
       // ---- the 32 scaled normals of this half of the path -> A (hi / lo) in tensor memory
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -1402,7 +1422,8 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float zs = z[i] * sqdt;
+          // (a narrower model: the padded factors multiply zero rows of B, but inf * 0 is NaN)
+          const float zs = (FULL || half * kT5Half + c * 16 + i < P.dim) ? z[i] * sqdt : 0.0f;
           hi[i] = tf32_rna(zs);
           lo[i] = __float_as_uint(zs - __uint_as_float(hi[i]));
         }
@@ -1443,7 +1464,7 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
         for (int i = 0; i < 16; ++i)
           x[c * 16 + i] = P.exact_log ? x[c * 16 + i] + f[i] : fmaf(x[c * 16 + i], f[i], x[c * 16 + i]);
       }
-      if (P.record_slot[s + 1] >= 0) record(s + 1);
+      if (P.record_slot[s + 1] >= 0) record(s + 1, P.record_slot[s + 1]);
     }
   }
 
@@ -1453,17 +1474,19 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kT5TmemCols)
                  : "memory");
   }
-  for (int i = tid; i < TQF_MAX_PAYOFFS * 3; i += kT5Threads) {
-    const int q = i / 3, k = i - q * 3;
-    double v = 0.0;
+  if (P.mode == MODE_PRICE) {
+    for (int i = tid; i < TQF_MAX_PAYOFFS * 3; i += kT5Threads) {
+      const int q = i / 3, k = i - q * 3;
+      double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) v += s_acc[w * TQF_MAX_PAYOFFS * 3 + i];
-    P.partials[(static_cast<size_t>(blockIdx.x) * TQF_MAX_PAYOFFS + q) * 4 + k] = v;
+      for (int w = 0; w < 4; ++w) v += s_acc[w * TQF_MAX_PAYOFFS * 3 + i];
+      P.partials[(static_cast<size_t>(blockIdx.x) * TQF_MAX_PAYOFFS + q) * 4 + k] = v;
+    }
   }
 }
 
-// TQF_MVGBM_TC5=0 falls back to the mma.sync kernel (kept for the A/B and for dim < 64,
-// path materialisation and non-Sobol draws, which the tcgen05 kernel does not cover).
+// TQF_MVGBM_TC5=0 falls back to the mma.sync kernel (kept for the A/B; float64 and
+// non-Sobol draws take the split kernel).
 static bool tc5_enabled() {
   const char* e = std::getenv("TQF_MVGBM_TC5");   // read per launch: tests toggle it
   return !(e && e[0] == '0');
@@ -1541,8 +1564,7 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
     if (grid < 1) grid = 1;
     *grid_out = grid;
     if constexpr (sizeof(Real) == 4 && DMAX == kMvDim) {
-      if (a.rngk == RNGK_SOBOL && a.dim == kMvDim && a.mode == MODE_PRICE && a.ndtab != nullptr &&
-          tc5_enabled()) {
+      if (a.rngk == RNGK_SOBOL && a.ndtab != nullptr && tc5_enabled()) {
         P.ndtab = a.ndtab;
         const uint64_t base128 = a.first_index & ~static_cast<uint64_t>(kT5Paths - 1);
         const uint64_t chunks128 = (a.first_index + a.path_count - base128 + kT5Paths - 1) / kT5Paths;
@@ -1550,9 +1572,9 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
         if (g5 < 1) g5 = 1;
         if (g5 > a.max_grid) g5 = a.max_grid;      // partials hold max_grid rows
         *grid_out = g5;
-        TQF_CUDA_OK(cudaFuncSetAttribute(mvgbm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kT5SmemBytes));
-        mvgbm_tc5_kernel<<<g5, kT5Threads, kT5SmemBytes, stream>>>(P);
+        auto k5 = a.dim == kMvDim ? mvgbm_tc5_kernel<true> : mvgbm_tc5_kernel<false>;
+        TQF_CUDA_OK(cudaFuncSetAttribute(k5, cudaFuncAttributeMaxDynamicSharedMemorySize, kT5SmemBytes));
+        k5<<<g5, kT5Threads, kT5SmemBytes, stream>>>(P);
         TQF_CUDA_OK(cudaGetLastError());
         return TQF_OK;
       }
