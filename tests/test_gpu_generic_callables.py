@@ -213,3 +213,31 @@ def test_repeated_price_calls_are_bound_by_content():
   p2.price([1.0], [engine.european_call(650.0, log_state=True)], num_samples=1000, initial_state=x0,
            random_type=rt, seed=1, time_step=0.1)
   assert len(es._CALLS) == before
+
+
+def test_normal_draws_from_a_foreign_dlpack_exporter():
+  # every tensor argument accepts any object that speaks the DLPack protocol (a tf.Tensor through
+  # tf.experimental.dlpack, a cupy array, ...): an exporter that is not a torch.Tensor goes through
+  # `__dlpack__` / `__dlpack_device__` and is consumed in place (no copy through the host)
+  tff = _tff()
+  from tff_b200.models import closures
+
+  class Foreign:
+    def __init__(self, t):
+      self._t = t
+      self.shape = tuple(t.shape)
+
+    def __dlpack__(self, stream=None):
+      return self._t.__dlpack__(stream=stream) if stream is not None else self._t.__dlpack__()
+
+    def __dlpack_device__(self):
+      return self._t.__dlpack_device__()
+
+  d, v = closures.affine_closures(0.02, -0.3, 0.15, 0.25)
+  draws = torch.randn((512, 10, 1), dtype=torch.float64, device='cuda',
+                      generator=torch.Generator(device='cuda').manual_seed(5))
+  kw = dict(times=[0.5, 1.0], times_grid=np.linspace(0.0, 1.0, 11), initial_state=np.array([1.3]),
+            dtype=np.float64)
+  a = tff.models.euler_sampling.sample(1, d, v, normal_draws=draws, **kw)
+  b = tff.models.euler_sampling.sample(1, d, v, normal_draws=Foreign(draws), **kw)
+  assert torch.equal(a, b) and a.shape == (512, 2, 1)
