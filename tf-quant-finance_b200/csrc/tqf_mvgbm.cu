@@ -1219,14 +1219,16 @@ struct T5Words {
 };
 // (dimensions beyond `dim` of a narrower model are staged as zero words: their draws are
 // discarded by the kernel)
-__device__ __forceinline__ T5Words t5_stage_load(const uint32_t* __restrict__ sobol_v, int s, int dim,
+template <bool FULL>
+__device__ __forceinline__ T5Words t5_stage_load(const uint32_t* __restrict__ sobol_v, int s, int dim_,
                                                  int tid) {
+  const int dim = FULL ? kMvDim : dim_;
   T5Words r;
 #pragma unroll
   for (int it = 0; it < kT5StageIters; ++it) {
     const int dd = it * (kT5Threads / 8) + (tid >> 3);
     r.w[it] = make_uint4(0u, 0u, 0u, 0u);
-    if (dd < dim)
+    if (FULL || dd < dim)
       r.w[it] = __ldg(reinterpret_cast<const uint4*>(sobol_v + (static_cast<size_t>(s) * dim + dd) * 32) +
                       (tid & 7));
   }
@@ -1263,13 +1265,15 @@ __device__ __forceinline__ void t5_stage_write(const T5Words& r, uint32_t high_b
     if (q < 4) sH[q * kT5HStride + dd] = h ^ (v5 & (0u - (q & 1u))) ^ (v6 & (0u - ((q >> 1) & 1u)));
   }
 }
+template <bool FULL>
 __device__ __forceinline__ void t5_stage(const uint32_t* __restrict__ sobol_v, int s, int dim,
                                          uint32_t high_bits, uint32_t* sT, uint32_t* sH, int tid) {
-  t5_stage_write(t5_stage_load(sobol_v, s, dim, tid), high_bits, sT, sH, tid);
+  t5_stage_write(t5_stage_load<FULL>(sobol_v, s, dim, tid), high_bits, sT, sH, tid);
 }
 
-// FULL: dim == 64 (no padding checks in the draw loop).
-template <bool FULL>
+// FULL: dim == 64 (no padding checks in the draw loop).  PRICE: fused payoff reduction
+// (otherwise the recorded states are stored).
+template <bool FULL, bool PRICE>
 __global__ void __launch_bounds__(kT5Threads, 2)
 mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
   extern __shared__ __align__(1024) unsigned char t5_smem[];
@@ -1340,7 +1344,7 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
     // (called by all threads together: d.step and the payoff list are uniform)
     auto record = [&](int step_index, int slot) {
       const int dim = P.dim;
-      if (P.mode != MODE_PRICE) {
+      if (!PRICE) {
         // path materialisation: every thread stores its 32 assets of path p
         if (valid) {
           float* o = P.out + static_cast<int64_t>(index - P.first_index) * P.stride_path +
@@ -1394,7 +1398,7 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
     if (P.record_slot[0] >= 0) record(0, P.record_slot[0]);
 
     __syncthreads();                       // every reader of the staging buffers is done
-    t5_stage(P.sobol_v, 0, P.dim, high_bits, sT, sH, tid);
+    t5_stage<FULL>(P.sobol_v, 0, P.dim, high_bits, sT, sH, tid);
     __syncthreads();
 
 #pragma unroll 1
@@ -1404,7 +1408,7 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
       const uint32_t* sHb = sH + buf * (4 * kT5HStride) + pw * kT5HStride + half * kT5Half;
       const float dt = P.coef[2 * s], sqdt = P.coef[2 * s + 1];
       T5Words next;
-      if (s + 1 < P.num_steps) next = t5_stage_load(P.sobol_v, s + 1, P.dim, tid);
+      if (s + 1 < P.num_steps) next = t5_stage_load<FULL>(P.sobol_v, s + 1, P.dim, tid);
       // ---- the 32 scaled normals of this half of the path -> A (hi / lo) in tensor memory
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -1474,7 +1478,7 @@ mvgbm_tc5_kernel(const __grid_constant__ MvParams<float, kMvDim> P) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kT5TmemCols)
                  : "memory");
   }
-  if (P.mode == MODE_PRICE) {
+  if (PRICE) {
     for (int i = tid; i < TQF_MAX_PAYOFFS * 3; i += kT5Threads) {
       const int q = i / 3, k = i - q * 3;
       double v = 0.0;
@@ -1572,7 +1576,9 @@ static int launch_mv(const MvLaunch& a, cudaStream_t stream, int* grid_out) {
         if (g5 < 1) g5 = 1;
         if (g5 > a.max_grid) g5 = a.max_grid;      // partials hold max_grid rows
         *grid_out = g5;
-        auto k5 = a.dim == kMvDim ? mvgbm_tc5_kernel<true> : mvgbm_tc5_kernel<false>;
+        const bool price = a.mode == MODE_PRICE;
+        auto k5 = a.dim == kMvDim ? (price ? mvgbm_tc5_kernel<true, true> : mvgbm_tc5_kernel<true, false>)
+                                  : (price ? mvgbm_tc5_kernel<false, true> : mvgbm_tc5_kernel<false, false>);
         TQF_CUDA_OK(cudaFuncSetAttribute(k5, cudaFuncAttributeMaxDynamicSharedMemorySize, kT5SmemBytes));
         k5<<<g5, kT5Threads, kT5SmemBytes, stream>>>(P);
         TQF_CUDA_OK(cudaGetLastError());
