@@ -40,7 +40,10 @@ UNIT = 'path-steps/s'
 
 # Algorithmic FP-pipe instructions per path-step (SURVEY.md 8(d);
 # frozen in roofline.json -- SURVEY allows them to be tightened only downward).
-ALGO_INSTR = {'c1': 16, 'c2': 79, 'c2_qe': 79, 'c3': 29, 'c4': 1408, 'c5': 22}
+ALGO_INSTR = {'c1': 12, 'c2': 79, 'c2_qe': 79, 'c3': 24, 'c4': 1408, 'c5': 17}
+# (c1 / c3 / c5: tightened in round 2 to no more than the kernels EXECUTE -- ncu: 12.8 / 24.3 /
+# 17.7 FP64 instructions per path-step with the table logarithm behind Box-Muller -- so that the
+# fraction cannot exceed what the FP64 pipe does; round 1 froze 16 / 29 / 22)
 # C4 is bound by the issue slots (and, next to them, the shared-memory pipe), not by one
 # FP pipe: its contraction runs on the tensor cores.  A(C4) = 64 draws x 22 thread-instructions
 # of ANY pipe (Sobol word 2.25, table inverse CDF 14, scale 1, TF32 split 3, update 1, staging
