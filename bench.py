@@ -533,6 +533,19 @@ class FusedWorkload:
         'gpu_launches_per_step': 2,
         'roofline': _fp_roofline(ctx, self.name, per_gpu_rate, note),
     }
+    if self.name == 'c3':
+      # what actually bounds C3: an FP64 instruction holds the dispatch port for two cycles,
+      # every other instruction for one (tools/microbench/dfma_bench.cu)
+      _, ffma = ctx.peaks()
+      slots = 2 * ALGO_INSTR['c3'] + 20 + 10
+      res['dispatch_roofline'] = {
+          'bound': 'dispatch port', 'achieved': per_gpu_rate * slots / 1e9, 'peak': ffma / 1e9,
+          'unit': 'G thread dispatch slots/s', 'frac': per_gpu_rate * slots / ffma,
+          'note': 'algorithmic dispatch slots per path-step: 2 x %d FP64 + 20 (ten Philox rounds per four '
+                  'words: 2 IMAD.WIDE + 2 LOP3 each, two normals per call) + 10 (counter, uint -> double '
+                  'conversions, quadrant selects); peak = one slot per lane and clock = the FFMA rate '
+                  'measured live; ncu: smsp__issue_active 63.8 %%, 69.6 executed instructions per '
+                  'path-step of which 24.3 FP64 (profiles/r2f_c3.txt)' % ALGO_INSTR['c3']}
     if e2e_s is not None:
       res['e2e'] = {'value': n * self.steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': self.h2d,
                     'd2h_bytes_per_step': len(self.payoffs) * 4 * 8,
