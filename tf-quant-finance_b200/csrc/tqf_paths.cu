@@ -606,9 +606,7 @@ int tqf_plan_create(const tqf_model_desc* model, const tqf_rng_desc* rng,
   int sms = kSMs;
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device);
   if (e != cudaSuccess) rc = cuda_fail(e, "cudaGetDevice");
-  plan->max_grid = sms * 32;
-  if (const char* e = std::getenv("TQF_GRID_PER_SM"))
-    if (std::atoi(e) > 0) plan->max_grid = sms * std::atoi(e);
+  plan->max_grid = sms * grid_per_sm();
   if (rc == TQF_OK) {
     rc = model->dtype == TQF_F64 ? upload_coef<double>(model, info.ncoef, &plan->coef_dev)
                                  : upload_coef<float>(model, info.ncoef, &plan->coef_dev);

@@ -1294,10 +1294,21 @@ size_t path_kernel_smem(int ncoef, int num_steps, int rngk, int mode, bool table
 }
 
 // A run whose chunks, grouped `ppt` per CTA, leave most of the machine empty (fewer
-// CTAs than three per SM; max_grid = 32 per SM): such runs take the one-path-per-
+// CTAs than three per SM; max_grid = grid_per_sm() per SM): such runs take the one-path-per-
 // thread Philox kernels.
+// CTAs of the grid per SM (max_grid = that many per SM): 48 measured 0.3-1 % faster than 32 on
+// C2 / C2-QE / C3 at full size and neutral at an eighth of it (more, shorter CTAs in the last
+// wave); TQF_GRID_PER_SM overrides it for A/B runs.
+inline int grid_per_sm() {
+  static const int v = [] {
+    const char* e = std::getenv("TQF_GRID_PER_SM");
+    const int n = e ? std::atoi(e) : 0;
+    return n > 0 ? n : 48;
+  }();
+  return v;
+}
 inline bool small_run(uint64_t num_chunks, int ppt, int max_grid) {
-  return (num_chunks + ppt - 1) / ppt < static_cast<uint64_t>(max_grid / 32 * 3);
+  return (num_chunks + ppt - 1) / ppt < static_cast<uint64_t>(max_grid / grid_per_sm() * 3);
 }
 // A Sobol run with fewer than eight waves of CTAs (three resident per SM): the last,
 // partly filled wave would cost up to a sixth of the run (C2 sharded over 8 GPUs:
@@ -1309,7 +1320,7 @@ inline bool few_waves(uint64_t num_chunks, int ppt, int max_grid) {
     const char* e = std::getenv("TQF_FEW_WAVES");      // "0": always the default kernels (A/B)
     return e && e[0] == '0';
   }();
-  return !off && (num_chunks + ppt - 1) / ppt < static_cast<uint64_t>(max_grid / 32 * 3) * 8;
+  return !off && (num_chunks + ppt - 1) / ppt < static_cast<uint64_t>(max_grid / grid_per_sm() * 3) * 8;
 }
 
 // Models whose step is written for a full batch of paths per thread (the QE step compacts
@@ -1338,7 +1349,7 @@ int launch_path_kernel(int rngk, bool anti, int mode, int max_grid, size_t smem_
     if (smem > 48 * 1024)                                                              \
       TQF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        static_cast<int>(smem)));                       \
-    /* Many more CTAs than are resident (max_grid = 32 per SM, ~11 waves): the    */   \
+    /* Many more CTAs than are resident (max_grid = 48 per SM, ~16 waves): the    */   \
     /* CTAs of an SM drift out of phase, so the table staging of one overlaps the */   \
     /* arithmetic of the others (a grid of exactly the resident CTAs, which run   */   \
     /* in lock step, measured 8% slower on C2), and the last partial wave is      */   \
