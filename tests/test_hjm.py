@@ -195,6 +195,28 @@ def test_oracle_bond_option_and_cap_reference_values():
   assert abs(got - 0.2394242699989869) < 2.5e-3
 
 
+def test_oracle_bond_option_batches_and_call_put_reference_values():
+  # zero_coupon_bond_option_test.py:125-153 (2-d batch), 262-290 (mixed batch, two factors),
+  # 292-320 (calls and puts); tolerance 1e-2 there
+  rt = odraws.RandomType.STATELESS_ANTITHETIC
+  kw = dict(discount_rate_fn=RATE, num_samples=50_000, time_step=0.1, random_type=rt, seed=[1, 2])
+  exp = np.array([[1.0, 1.0], [2.0, 2.0]])
+  mat = np.array([[5.0, 5.0], [4.0, 4.0]])
+  got = ohjm.bond_option_price_mc(strikes=np.exp(-0.01 * mat) / np.exp(-0.01 * exp), expiries=exp,
+                                  maturities=mat, dim=1, mean_reversion=[0.03], volatility=[0.02], **kw)
+  assert got.shape == (2, 2)
+  np.testing.assert_allclose(got, [[0.02817777, 0.02817777], [0.02042677, 0.02042677]], rtol=1e-2,
+                             atol=1e-2)
+  exp, mat = np.array([1.0, 1.0, 2.0]), np.array([5.0, 6.0, 4.0])
+  two = dict(dim=2, mean_reversion=[0.03, 0.06], volatility=[0.02, 0.01])
+  got = ohjm.bond_option_price_mc(strikes=np.exp(-0.01 * mat) / np.exp(-0.01 * exp), expiries=exp,
+                                  maturities=mat, **two, **kw)
+  np.testing.assert_allclose(got, [0.03115176, 0.03789011, 0.02266191], rtol=1e-2, atol=1e-2)
+  got = ohjm.bond_option_price_mc(strikes=np.exp(-0.01 * mat) / np.exp(-0.01 * exp) - 0.01, expiries=exp,
+                                  maturities=mat, is_call_options=[True, False, False], **two, **kw)
+  np.testing.assert_allclose(got, [0.03620415, 0.03279728, 0.01784987], rtol=1e-2, atol=1e-2)
+
+
 @pytest.mark.parametrize('factors', [1, 2])
 def test_bond_option_descriptor_replay_matches_oracle_price(factors):
   """The bond-option route on the host: simulation grid, the reference's discounting weights
