@@ -657,8 +657,25 @@ def run_c5(ctx, steps, warmup, sample_clocks=False):
     split['lsm'].append(e1.elapsed_time(e2))
     return price
 
+  calls = {'n': 0}
+
+  def fresh_call():
+    # end to end with a parameter set no earlier call had: a new plan (tables rebuilt on the
+    # host and uploaded), paths, backward induction, price read back
+    calls['n'] += 1
+    fresh = engine.Plan(spec, all_times, nsteps, np.array([1e-12 * calls['n']]), rng, n, np.float64)
+    try:
+      paths, csums = fresh.paths(record_slot, 50, lo, count, exp_transform=True, column_sums=True)
+      price = lsm.least_square_mc(paths, np.arange(50), put, basis, discount_factors=df,
+                                  dtype=np.float64, global_path_offset=2 * lo, all_reduce=reduce_fn,
+                                  column_sums=csums, peer_exchange=ctx.px)
+      return float(price[0])
+    finally:
+      fresh.close()
+
   try:
     ms, wall, clocks, price = ctx.timed(one_step, steps, warmup, flush=False, sample_clocks=sample_clocks)
+    e2e_s = ctx.timed_wall(fresh_call, max(1, min(steps, 3)))
     gen = float(np.mean(split['gen'][-steps:]))
     lsm_ms = float(np.mean(split['lsm'][-steps:]))
     gen, lsm_ms = ctx.max_over_ranks([gen, lsm_ms])
@@ -676,10 +693,13 @@ def run_c5(ctx, steps, warmup, sample_clocks=False):
         'euler_steps': nsteps, 'exercise_dates': 50, 'dtype': 'f64', 'prices': [float(price[0])],
         'generation_ms': gen, 'lsm_ms': lsm_ms,
         'l2': 'inputs (3.2 GB of paths) exceed L2',
-        'e2e': {'value': n * nsteps / (wall / steps), 'unit': UNIT,
+        'e2e': {'value': n * nsteps / e2e_s, 'unit': UNIT,
                 'h2d_bytes_per_step': 50 * 8 * 2 + nsteps * 6 * 8, 'd2h_bytes_per_step': 16,
-                'api': 'engine.Plan.paths + longstaff_schwartz.least_square_mc (host tables in, price out; '
-                       'wall clock of the timed region)'},
+                'api': 'engine.Plan + Plan.paths + longstaff_schwartz.least_square_mc',
+                'inputs': 'a parameter set no earlier call had, every call: a new plan (tables rebuilt on '
+                          'the host and uploaded), paths, backward induction, price read back',
+                'repeated_call_value': n * nsteps / (wall / steps),
+                'repeated_call_note': 'the timed region itself: the same plan re-used'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': ctx.hbm_peak, 'unit': 'GB/s',
                      'frac': achieved / ctx.hbm_peak, 'traffic': traffic,
                      'traffic_unit': 'bytes per date of the backward induction (ncu capture named in roofline.json)',

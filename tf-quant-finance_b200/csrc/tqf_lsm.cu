@@ -814,10 +814,16 @@ static int ensure_partials(tqf_lsm* h, size_t doubles) {
     set_error("caller-provided LSM partials workspace is too small");
     return TQF_ERR_INVALID_ARGUMENT;
   }
-  cudaFree(h->partials_dev);
+  {
+    void* old = h->partials_dev;
+    dev_release(&old, 1);
+  }
   h->partials_dev = nullptr;
   h->partials_doubles = 0;
-  TQF_CUDA_OK(cudaMalloc(&h->partials_dev, doubles * sizeof(double)));
+  void* fresh = nullptr;
+  const int rc = dev_alloc(&fresh, doubles * sizeof(double));   // block cache (tqf_rng.cu)
+  if (rc != TQF_OK) return rc;
+  h->partials_dev = static_cast<double*>(fresh);
   h->partials_doubles = doubles;
   return TQF_OK;
 }
@@ -960,7 +966,8 @@ int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
     h->w_dev = desc->w_dev;
     h->external_w = true;
   } else {
-    e = cudaMalloc(&h->w_dev, esize * desc->batch * (desc->num_paths ? desc->num_paths : 1));
+    if (dev_alloc(&h->w_dev, esize * desc->batch * (desc->num_paths ? desc->num_paths : 1)) != TQF_OK)
+      e = cudaErrorMemoryAllocation;
   }
   if (desc->partials_dev) {
     h->partials_dev = desc->partials_dev;
@@ -968,9 +975,15 @@ int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
     h->external_partials = true;
   }
   h->strike0 = desc->strikes[0];
-  if (e == cudaSuccess) e = cudaMalloc(&h->ctrl_dev, 4 * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMalloc(&h->exponents_dev, sizeof(int) * h->K * desc->dim);
-  if (e == cudaSuccess) e = cudaMalloc(&h->strikes_dev, sizeof(double) * desc->batch);
+  // (small per-object buffers: from the block cache, no cudaMalloc / cudaFree per pricing call)
+  auto cached = [&e](auto** ptr, size_t bytes) {
+    void* p = nullptr;
+    if (e == cudaSuccess && dev_alloc(&p, bytes) != TQF_OK) e = cudaErrorMemoryAllocation;
+    *ptr = static_cast<std::remove_reference_t<decltype(**ptr)>*>(p);
+  };
+  cached(&h->ctrl_dev, 4 * sizeof(unsigned long long));
+  cached(&h->exponents_dev, sizeof(int) * h->K * desc->dim);
+  cached(&h->strikes_dev, sizeof(double) * desc->batch);
   if (e == cudaSuccess)
     e = cudaMemcpy(h->exponents_dev, desc->exponents, sizeof(int) * h->K * desc->dim,
                    cudaMemcpyHostToDevice);
@@ -1001,12 +1014,10 @@ int tqf_lsm_create(const tqf_lsm_desc* desc, tqf_lsm** out) {
 
 int tqf_lsm_destroy(tqf_lsm* h) {
   if (!h) return TQF_OK;
-  if (!h->external_w) cudaFree(h->w_dev);
-  cudaFree(h->exponents_dev);
-  cudaFree(h->strikes_dev);
-  if (!h->external_partials) cudaFree(h->partials_dev);
-  cudaFree(h->times_dev);
-  cudaFree(h->ctrl_dev);
+  void* blocks[6] = {h->external_w ? nullptr : h->w_dev, h->exponents_dev, h->strikes_dev,
+                     h->external_partials ? nullptr : static_cast<void*>(h->partials_dev),
+                     h->times_dev, h->ctrl_dev};
+  dev_release(blocks, 6);
   delete h->exercise_times;
   delete h;
   return TQF_OK;
@@ -1019,9 +1030,13 @@ int tqf_lsm_column_sums(tqf_lsm* h, const int32_t* time_indices, int num_times, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const tqf_lsm_desc& d = h->desc;
   if (num_times > h->times_cap) {
-    cudaFree(h->times_dev);
+    void* old = h->times_dev;
+    dev_release(&old, 1);
     h->times_dev = nullptr;
-    TQF_CUDA_OK(cudaMalloc(&h->times_dev, sizeof(int) * num_times));
+    void* fresh = nullptr;
+    const int rc = dev_alloc(&fresh, sizeof(int) * num_times);
+    if (rc != TQF_OK) return rc;
+    h->times_dev = static_cast<int*>(fresh);
     h->times_cap = num_times;
   }
   TQF_CUDA_OK(cudaMemcpyAsync(h->times_dev, time_indices, sizeof(int) * num_times,

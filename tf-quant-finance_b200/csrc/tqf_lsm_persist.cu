@@ -661,10 +661,14 @@ int lsm_run_persistent(tqf_lsm* h, const int32_t* exercise_times, int num_times,
     return TQF_ERR_UNSUPPORTED;
   }
   if (num_times > h->times_cap) {
-    cudaFree(h->times_dev);
+    void* old = h->times_dev;
+    dev_release(&old, 1);
     h->times_dev = nullptr;
     h->times_cap = 0;
-    TQF_CUDA_OK(cudaMalloc(&h->times_dev, sizeof(int) * num_times));
+    void* fresh = nullptr;
+    const int rc = dev_alloc(&fresh, sizeof(int) * num_times);
+    if (rc != TQF_OK) return rc;
+    h->times_dev = static_cast<int*>(fresh);
     h->times_cap = num_times;
   }
   TQF_CUDA_OK(cudaMemcpyAsync(h->times_dev, exercise_times, sizeof(int) * num_times,
@@ -676,10 +680,14 @@ int lsm_run_persistent(tqf_lsm* h, const int32_t* exercise_times, int num_times,
       set_error("caller-provided LSM partials workspace is too small");
       return TQF_ERR_INVALID_ARGUMENT;
     }
-    cudaFree(h->partials_dev);
+    void* old = h->partials_dev;
+    dev_release(&old, 1);
     h->partials_dev = nullptr;
     h->partials_doubles = 0;
-    TQF_CUDA_OK(cudaMalloc(&h->partials_dev, need * sizeof(double)));
+    void* fresh = nullptr;
+    const int rc = dev_alloc(&fresh, need * sizeof(double));
+    if (rc != TQF_OK) return rc;
+    h->partials_dev = static_cast<double*>(fresh);
     h->partials_doubles = need;
   }
   const int rc = h->desc.dtype == TQF_F64

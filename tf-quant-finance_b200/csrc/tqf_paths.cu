@@ -454,10 +454,14 @@ static int run_paths(tqf_plan* plan, uint64_t path_offset, uint64_t path_count,
     TQF_REQUIRE(num_slots >= 1 && cols <= 2048, "column sums: 1 <= num_slots * dim <= 2048");
     const size_t need = static_cast<size_t>(plan->max_grid) * cols;
     if (need > plan->colsum_doubles) {
-      cudaFree(plan->colsum_dev);
+      void* old = plan->colsum_dev;
+      dev_release(&old, 1);
       plan->colsum_dev = nullptr;
       plan->colsum_doubles = 0;
-      TQF_CUDA_OK(cudaMalloc(&plan->colsum_dev, need * sizeof(double)));
+      void* fresh = nullptr;
+      const int rc = dev_alloc(&fresh, need * sizeof(double));   // block cache: no cudaMalloc per plan
+      if (rc != TQF_OK) return rc;
+      plan->colsum_dev = static_cast<double*>(fresh);
       plan->colsum_doubles = need;
     }
     P.colsum_partials = plan->colsum_dev;

@@ -50,7 +50,8 @@ constexpr size_t kDevCacheLimit = 256ull << 20;
 
 int dev_alloc(void** out, size_t bytes) {
   size_t size = 512;
-  while (size < bytes) size <<= 1;
+  while (size < bytes && size < (64ull << 20)) size <<= 1;
+  if (size < bytes) size = (bytes + (16ull << 20) - 1) & ~((16ull << 20) - 1);   // large: 16 MB steps
   int dev = 0;
   TQF_CUDA_OK(cudaGetDevice(&dev));
   DevBlockCache& c = dev_cache();
