@@ -343,3 +343,24 @@ def test_analytic_bond_option_reference_kat():
       volatility=0.02, discount_rate_fn=_flat_rate, dtype=np.float64)
   assert price.shape == ()
   np.testing.assert_allclose(price, 0.02817777, rtol=1e-8, atol=1e-8)
+
+
+def test_heston_model_closures_reference_kat():
+  """heston_model_test.py:175-219 on the mirror's own `drift_fn()` / `volatility_fn()`
+  (they evaluate on the host; the device kernel gets the same numbers as a coefficient table)."""
+  import tff_b200 as tff
+  pw = piecewise.PiecewiseConstantFunc
+  process = tff.models.HestonModel(
+      mean_reversion=pw([0.5], [1, 1.1], dtype=np.float64), theta=pw([0.5], [1, 0.9], dtype=np.float64),
+      volvol=pw([0.3], [0.1, 0.2], dtype=np.float64), rho=pw([0.5], [0.4, 0.6], dtype=np.float64),
+      dtype=np.float64)
+  x0 = np.array([np.log(100), 0.045])
+  np.testing.assert_allclose(np.asarray(process.drift_fn()(0.1, x0)), [-0.0225, 0.955],
+                             rtol=1e-6, atol=1e-6)
+  np.testing.assert_allclose(np.asarray(process.volatility_fn()(0.1, x0)),
+                             [[0.21213203, 0.], [0.00848528, 0.01944222]], rtol=1e-6, atol=1e-6)
+  # the coefficient table the kernel reads holds the same parameters, taken at t_{i+1}
+  # (`euler_sampling.py:519`): columns sqrt(dt), -dt/2, dt kappa, theta, ...
+  tab = process.drift_fn().tqf_spec.coef_table(np.array([0.0, 0.1, 0.6, 0.7]), np.float64)
+  np.testing.assert_allclose(tab[:, 2], [0.1 * 1.0, 0.5 * 1.1, 0.1 * 1.1])
+  np.testing.assert_allclose(tab[:, 3], [1.0, 0.9, 0.9])

@@ -427,3 +427,34 @@ def test_philox_uniform_conversions():
                                              1 - 2.0**-20]))
   u = ophilox.stateless_uniform([4096, 3], [2, 2], np.float64)
   assert u.min() >= 0 and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+
+
+def test_heston_closures_reference_kat():
+  """heston_model_test.py:175-219: drift and volatility of the piecewise-constant
+  Heston process at `times[0] = 0.1`, state `[log 100, 0.045]`."""
+  from oracle import models as omodels
+  pw = omodels.PiecewiseConstantFunc
+  drift_fn, vol_fn = omodels.heston_closures(
+      pw([0.5], [1, 1.1], np.float64), pw([0.5], [1, 0.9], np.float64),
+      pw([0.3], [0.1, 0.2], np.float64), pw([0.5], [0.4, 0.6], np.float64), np.float64)
+  x0 = np.array([np.log(100), 0.045])
+  np.testing.assert_allclose(drift_fn(0.1, x0), [-0.0225, 0.955], rtol=1e-6, atol=1e-6)
+  np.testing.assert_allclose(vol_fn(0.1, x0), [[0.21213203, 0.], [0.00848528, 0.01944222]],
+                             rtol=1e-6, atol=1e-6)
+  # after the jumps (t = 0.6): kappa 1.1, theta 0.9, volvol 0.2, rho 0.6
+  np.testing.assert_allclose(drift_fn(0.6, x0), [-0.0225, 1.1 * (0.9 - 0.045)], rtol=1e-12)
+  v = np.sqrt(0.045)
+  np.testing.assert_allclose(vol_fn(0.6, x0), [[v, 0.], [0.2 * 0.6 * v, 0.2 * 0.8 * v]], rtol=1e-12)
+
+
+def test_black_scholes_reference_kat_for_the_c1_sanity_check():
+  """vanilla_prices_test.py:32-46: the closed form the C1 price is checked against
+  (tests/test_gpu_parity.py) reproduces the reference's own known values."""
+  from scipy.stats import norm
+  forwards = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+  strikes = np.full(5, 3.0)
+  vols = np.array([0.0001, 102.0, 2.0, 0.1, 0.4])
+  d1 = (np.log(forwards / strikes) + 0.5 * vols**2) / vols
+  prices = forwards * norm.cdf(d1) - strikes * norm.cdf(d1 - vols)
+  np.testing.assert_allclose(
+      prices, [0.0, 2.0, 2.0480684764112578, 1.0002029716043364, 2.0730313058959933], atol=1e-10)
