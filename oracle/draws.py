@@ -2,8 +2,8 @@
 
 Restates
   * `math/random_ops/multivariate_normal.py:47-451` (`multivariate_normal`
-    a.k.a. `mv_normal_sample`) for mean-only inputs (no scale matrix), the
-    form every caller on the hot path uses;
+    a.k.a. `mv_normal_sample`): mean-only inputs (the form every caller on the
+    hot path uses) and the `covariance_matrix` / `scale_matrix` forms;
   * `models/utils.py:20-128` (`generate_mc_normal_draws`).
 """
 import enum
@@ -40,9 +40,30 @@ def _erfinv_times_sqrt2(u, dtype):
   return z.astype(dtype)
 
 
-def _mvnormal_pseudo(sample_shape, mean, random_type, seed, dtype):
-  """`multivariate_normal.py:248-273` with scale_matrix=None."""
-  out_shape = tuple(sample_shape) + tuple(mean.shape)
+def _process_mean_scale(mean, scale_matrix, covariance_matrix, dtype):
+  """`multivariate_normal.py:427-451` -> (mean, scale, batch_shape, dtype)."""
+  if scale_matrix is not None:
+    scale_matrix = np.asarray(scale_matrix, dtype=dtype)
+  elif covariance_matrix is not None:
+    scale_matrix = np.linalg.cholesky(np.asarray(covariance_matrix, dtype=dtype))
+  if mean is None:
+    dtype = scale_matrix.dtype
+    return dtype.type(0.0), scale_matrix, tuple(scale_matrix.shape[:-1]), dtype
+  mean = np.asarray(mean, dtype=dtype)
+  return mean, scale_matrix, tuple(mean.shape), mean.dtype
+
+
+def _shift_scale(mean, scale_matrix, samples):
+  """`mean + tf.linalg.matvec(scale_matrix, samples)` (`multivariate_normal.py:270-273`)."""
+  if scale_matrix is None:
+    return mean + samples
+  return (mean + np.einsum('...ij,...j->...i', scale_matrix, samples)).astype(samples.dtype)
+
+
+def _mvnormal_pseudo(sample_shape, mean, random_type, seed, dtype, scale_matrix=None,
+                     batch_shape=None):
+  """`multivariate_normal.py:248-273`."""
+  out_shape = tuple(sample_shape) + tuple(mean.shape if batch_shape is None else batch_shape)
   if random_type == RandomType.PSEUDO:
     samples = philox.stateful_normal(out_shape, seed, dtype)
   else:
@@ -50,10 +71,11 @@ def _mvnormal_pseudo(sample_shape, mean, random_type, seed, dtype):
       raise ValueError('`seed` should be specified if the `random_type` is '
                        '`STATELESS` or `STATELESS_ANTITHETIC`')
     samples = philox.stateless_normal(out_shape, seed, dtype)
-  return mean + samples
+  return _shift_scale(mean, scale_matrix, samples)
 
 
-def _mvnormal_pseudo_antithetic(sample_shape, mean, random_type, seed, dtype):
+def _mvnormal_pseudo_antithetic(sample_shape, mean, random_type, seed, dtype, scale_matrix=None,
+                                batch_shape=None, mean_is_none=False):
   """`multivariate_normal.py:276-311`."""
   n0 = int(sample_shape[0])
   if n0 % 2 != 0:
@@ -62,13 +84,15 @@ def _mvnormal_pseudo_antithetic(sample_shape, mean, random_type, seed, dtype):
   half_shape = (n0 // 2,) + tuple(sample_shape[1:])
   base = (RandomType.PSEUDO if random_type == RandomType.PSEUDO_ANTITHETIC
           else RandomType.STATELESS)
-  r = _mvnormal_pseudo(half_shape, mean, base, seed, dtype)
+  r = _mvnormal_pseudo(half_shape, mean, base, seed, dtype, scale_matrix, batch_shape)
+  if mean_is_none:
+    return np.concatenate([r, -r], axis=0)
   return np.concatenate([r, 2 * mean - r], axis=0)
 
 
-def _mvnormal_sobol(sample_shape, mean, skip, dtype):
+def _mvnormal_sobol(sample_shape, mean, skip, dtype, scale_matrix=None, batch_shape=None):
   """`multivariate_normal.py:356-424` for SOBOL."""
-  batch_shape = tuple(mean.shape)
+  batch_shape = tuple(mean.shape if batch_shape is None else batch_shape)
   dim = batch_shape[-1]
   sample_shape = tuple(int(s) for s in sample_shape)
   output_shape_t = tuple(reversed(batch_shape)) + sample_shape
@@ -80,15 +104,16 @@ def _mvnormal_sobol(sample_shape, mean, skip, dtype):
   perm = (list(range(size_batch, size_batch + size_sample)) +
           list(range(size_batch - 1, -1, -1)))
   seq = np.transpose(seq.reshape(output_shape_t), perm)
-  return mean + _erfinv_times_sqrt2(seq, dtype)
+  return _shift_scale(mean, scale_matrix, _erfinv_times_sqrt2(seq, dtype))
 
 
-def _mvnormal_halton(sample_shape, mean, skip, dtype, randomized=False, seed=None):
+def _mvnormal_halton(sample_shape, mean, skip, dtype, randomized=False, seed=None,
+                     scale_matrix=None, batch_shape=None):
   """`multivariate_normal.py:356-424` for HALTON / HALTON_RANDOMIZED:
   `halton.sample(dim, sequence_indices=range(skip, skip + n))`, then the same
   transpose / reshape / erfinv as the Sobol branch."""
   from oracle import halton  # pylint: disable=g-import-not-at-top
-  batch_shape = tuple(mean.shape)
+  batch_shape = tuple(mean.shape if batch_shape is None else batch_shape)
   dim = batch_shape[-1]
   sample_shape = tuple(int(s) for s in sample_shape)
   output_shape_t = tuple(reversed(batch_shape)) + sample_shape
@@ -101,28 +126,33 @@ def _mvnormal_halton(sample_shape, mean, skip, dtype, randomized=False, seed=Non
   perm = (list(range(size_batch, size_batch + size_sample)) +
           list(range(size_batch - 1, -1, -1)))
   seq = np.transpose(seq.reshape(output_shape_t), perm)
-  return mean + _erfinv_times_sqrt2(seq, dtype)
+  return _shift_scale(mean, scale_matrix, _erfinv_times_sqrt2(seq, dtype))
 
 
-def mv_normal_sample(sample_shape, mean, random_type=None, seed=None,
-                     dtype=None, skip=0):
-  """`multivariate_normal` restricted to `mean` only (identity scale)."""
+def mv_normal_sample(sample_shape, mean=None, random_type=None, seed=None,
+                     dtype=None, skip=0, covariance_matrix=None, scale_matrix=None):
+  """`multivariate_normal` (`multivariate_normal.py:47-245`)."""
   random_type = RandomType.PSEUDO if random_type is None else random_type
   random_type = RandomType(random_type.value)
-  mean = np.asarray(mean, dtype=dtype)
-  dtype = mean.dtype
+  if mean is None and covariance_matrix is None and scale_matrix is None:
+    raise ValueError('At least one of mean, covariance_matrix or scale_matrix must be specified.')
+  if covariance_matrix is not None and scale_matrix is not None:
+    raise ValueError('Only one of covariance matrix or scale matrix must be specified')
+  mean_is_none = mean is None
+  mean, scale, batch_shape, dtype = _process_mean_scale(mean, scale_matrix, covariance_matrix, dtype)
   if random_type in (RandomType.PSEUDO, RandomType.STATELESS):
-    return _mvnormal_pseudo(sample_shape, mean, random_type, seed, dtype)
+    return _mvnormal_pseudo(sample_shape, mean, random_type, seed, dtype, scale, batch_shape)
   if random_type in (RandomType.PSEUDO_ANTITHETIC,
                      RandomType.STATELESS_ANTITHETIC):
     return _mvnormal_pseudo_antithetic(sample_shape, mean, random_type, seed,
-                                       dtype)
+                                       dtype, scale, batch_shape, mean_is_none)
   if random_type == RandomType.SOBOL:
-    return _mvnormal_sobol(sample_shape, mean, skip, dtype)
+    return _mvnormal_sobol(sample_shape, mean, skip, dtype, scale, batch_shape)
   if random_type == RandomType.HALTON:
-    return _mvnormal_halton(sample_shape, mean, skip, dtype)
+    return _mvnormal_halton(sample_shape, mean, skip, dtype, scale_matrix=scale, batch_shape=batch_shape)
   if random_type == RandomType.HALTON_RANDOMIZED:
-    return _mvnormal_halton(sample_shape, mean, skip, dtype, randomized=True, seed=seed)
+    return _mvnormal_halton(sample_shape, mean, skip, dtype, randomized=True, seed=seed,
+                            scale_matrix=scale, batch_shape=batch_shape)
   raise NotImplementedError(
       'Only STATELESS, PSEUDO, PSEUDO_ANTITHETIC, STATELESS_ANTITHETIC and '
       'SOBOL are restated by the oracle. Supplied: {}'.format(random_type))
