@@ -158,6 +158,31 @@ def mv_normal_sample(sample_shape, mean=None, random_type=None, seed=None,
       'SOBOL are restated by the oracle. Supplied: {}'.format(random_type))
 
 
+def uniform(dim, sample_shape, random_type=None, dtype=None, seed=None, skip=0):
+  """`tff.math.random.uniform` (`math/random_ops/uniform.py:25-153`)."""
+  random_type = RandomType.PSEUDO if random_type is None else RandomType(random_type.value)
+  dtype = np.dtype(dtype or np.float32)
+  sample_shape = [int(s) for s in sample_shape]
+  shape = sample_shape + [int(dim)]
+  if random_type == RandomType.PSEUDO:
+    return philox.stateful_uniform(shape, seed, dtype)
+  if random_type == RandomType.STATELESS:
+    if seed is None:
+      raise ValueError('`seed` must be supplied if the `random_type` is STATELESS.')
+    return philox.stateless_uniform(shape, seed, dtype)
+  if random_type == RandomType.PSEUDO_ANTITHETIC:
+    raise NotImplementedError('At the moment antithetic sampling is not supported for the uniform '
+                              'distribution.')
+  num = int(np.prod(sample_shape))
+  if random_type == RandomType.SOBOL:
+    seq = sobol.sample(int(dim), num, skip=skip, dtype=dtype)
+  else:   # uniform.py:135-150: everything else is a Halton sequence
+    from oracle import halton  # pylint: disable=g-import-not-at-top
+    seq = halton.sample(int(dim), sequence_indices=np.arange(skip, skip + num), dtype=dtype,
+                        randomized=random_type == RandomType.HALTON_RANDOMIZED, seed=seed)
+  return seq.reshape(shape)
+
+
 def _draws_of_path_range(num_normal_draws, num_time_steps, num_sample_paths,
                          random_type, skip, seed, dtype, path_range):
   """Rows [lo, hi) of the `[num_sample_paths, steps * draws]` matrix that

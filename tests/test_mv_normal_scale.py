@@ -1,4 +1,4 @@
-"""`mv_normal_sample` with `covariance_matrix` / `scale_matrix` (CPU).
+"""`mv_normal_sample` with `covariance_matrix` / `scale_matrix`, and `uniform` (CPU).
 
 1. The reference's own tests (`math/random_ops/multivariate_normal_test.py:31-281`)
    run on the oracle (`oracle/draws.py`), same sample counts / seeds / tolerances.
@@ -165,3 +165,52 @@ def test_host_wiring_of_multivariate_normal_equals_the_oracle(host_generators, c
   want = odraws.mv_normal_sample(sample_shape, random_type=getattr(RT, random_type), seed=seed, **kw, **extra)
   assert tuple(got.shape) == want.shape and got.dtype == torch.float64
   np.testing.assert_allclose(got.numpy(), want, rtol=1e-13, atol=1e-13)
+
+
+@pytest.fixture
+def host_uniform_generators(monkeypatch):
+  from tff_b200.math.random import halton, philox, sobol
+  monkeypatch.setattr(philox, 'uniform', lambda shape, dtype=None, seed=None: torch.from_numpy(
+      ophilox.stateful_uniform(list(shape), seed, np.dtype(dtype))))
+  monkeypatch.setattr(philox, 'stateless_uniform', lambda shape, seed, dtype=None: torch.from_numpy(
+      ophilox.stateless_uniform(list(shape), seed, np.dtype(dtype))))
+  monkeypatch.setattr(sobol, 'sample', lambda dim, num_results, skip=0, dtype=None: torch.from_numpy(
+      osobol.sample(dim, num_results, skip=skip, dtype=dtype)))
+
+  def halton_sample(dim, num_results=None, sequence_indices=None, randomized=True, randomization_params=None,
+                    seed=None, validate_args=False, dtype=None, name=None):
+    assert randomization_params is None and num_results is None
+    return torch.from_numpy(ohalton.sample(dim, sequence_indices=np.asarray(sequence_indices), dtype=dtype,
+                                           randomized=randomized, seed=seed)), None
+  monkeypatch.setattr(halton, 'sample', halton_sample)
+
+
+@pytest.mark.parametrize('random_type,seed', [
+    ('PSEUDO', 101), ('STATELESS', [2, 2]), ('SOBOL', None), ('HALTON', None), ('HALTON_RANDOMIZED', 7),
+    ('STATELESS_ANTITHETIC', [1, 2])])
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_host_wiring_of_uniform_equals_the_oracle(host_uniform_generators, random_type, seed, dtype):
+  # math/random_ops/uniform.py:92-153; STATELESS_ANTITHETIC falls into the reference's
+  # quasi-random `else` branch and yields the plain Halton sequence
+  import tff_b200 as tff
+  extra = {} if random_type in ('PSEUDO', 'STATELESS') else {'skip': 1000}
+  got = tff.math.random.uniform(5, [2, 3, 10], random_type=getattr(tff.math.random.RandomType, random_type),
+                                seed=seed, dtype=dtype, **extra)
+  want = odraws.uniform(5, [2, 3, 10], random_type=getattr(RT, random_type), seed=seed, dtype=dtype, **extra)
+  assert tuple(got.shape) == (2, 3, 10, 5) == want.shape and got.numpy().dtype == dtype
+  np.testing.assert_array_equal(got.numpy(), want)
+  if random_type == 'STATELESS_ANTITHETIC':
+    np.testing.assert_array_equal(want, odraws.uniform(5, [2, 3, 10], random_type=RT.HALTON, dtype=dtype, skip=1000))
+
+
+def test_uniform_errors():
+  import tff_b200 as tff
+  rt = tff.math.random.RandomType
+  with pytest.raises(ValueError):
+    tff.math.random.uniform(2, [4], random_type=rt.STATELESS)
+  with pytest.raises(NotImplementedError):
+    tff.math.random.uniform(2, [4], random_type=rt.PSEUDO_ANTITHETIC, seed=1)
+  with pytest.raises(ValueError):
+    odraws.uniform(2, [4], random_type=RT.STATELESS)
+  with pytest.raises(NotImplementedError):
+    odraws.uniform(2, [4], random_type=RT.PSEUDO_ANTITHETIC, seed=1)

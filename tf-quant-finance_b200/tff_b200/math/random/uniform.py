@@ -13,8 +13,10 @@ def uniform(dim, sample_shape, random_type=None, dtype=None, seed=None, name=Non
   Same contract as the reference: PSEUDO -> `tf.random.uniform(seed=)` (first
   invocation of a fresh op), STATELESS -> `tf.random.stateless_uniform(seed=[a, b],
   alg='philox')`, SOBOL -> `sobol.sample(dim, prod(sample_shape), skip)`;
-  PSEUDO_ANTITHETIC raises as in the reference (`uniform.py:102-105`); HALTON is
-  the non-randomized sequence, HALTON_RANDOMIZED is not implemented.
+  PSEUDO_ANTITHETIC raises as in the reference (`uniform.py:102-105`); every other
+  type takes the reference's quasi-random branch (`uniform.py:116-153`): HALTON,
+  HALTON_RANDOMIZED (`seed` / `randomization_params`) and -- as in the reference,
+  whose `else` catches it -- STATELESS_ANTITHETIC, which yields the plain Halton sequence.
   """
   del name
   random_type = RandomType.PSEUDO if random_type is None else random_type
@@ -35,8 +37,9 @@ def uniform(dim, sample_shape, random_type=None, dtype=None, seed=None, name=Non
     num = int(np.prod(sample_shape)) if sample_shape else 1
     seq = sobol.sample(dim=int(dim), num_results=num, skip=int(kwargs.get('skip', 0)), dtype=dtype)
     return seq.reshape(shape)
-  if random_type.value in (RandomType.HALTON.value, RandomType.HALTON_RANDOMIZED.value):
-    # uniform.py:135-150
+  if random_type.value in (RandomType.HALTON.value, RandomType.HALTON_RANDOMIZED.value,
+                           RandomType.STATELESS_ANTITHETIC.value):
+    # uniform.py:135-150 (the reference's `else` branch)
     from tff_b200.math.random import halton  # pylint: disable=g-import-not-at-top
     num = int(np.prod(sample_shape)) if sample_shape else 1
     skip = int(kwargs.get('skip', 0))
