@@ -1,0 +1,194 @@
+"""TEST INFRASTRUCTURE: a numpy stand-in for `tff_b200.engine.Plan`.
+
+The product has no CPU path (`_lib.require_cuda()` fails loudly without a GPU).  To run the
+mirror's HOST logic -- argument handling, grids, batch layout, record plan, coefficient tables,
+draw-unit bookkeeping, output layout -- in the `-m "not gpu"` suite, tests replace `engine.Plan`
+by `CpuPlan` with pytest's `monkeypatch` (inside the test only).  `CpuPlan` keeps what the real
+plan uploads and restates what the kernels do with it:
+
+  * the model `step()` functions of `csrc/tqf_paths_kernel.cuh` / `csrc/tqf_mvgbm.cu`, line for
+    line in numpy (`STEP`);
+  * the draw addressing of `tqf.h`: path p of a plan uses draw unit `p * unit_stride +
+    unit_offset`; unit u owns elements `[u D, (u + 1) D)` of the Philox stream, `D = steps *
+    factors` (TensorFlow's `[units, D]` normal matrix, `models/utils.py:98-128`), or Sobol point
+    `skip + 1 + u`; antithetic plans append the negated partners;
+  * the record plan (`record_slot[s + 1]` = output slot of the state after step s).
+
+The streams themselves come from the oracle.  Nothing here is shipped or imported by the package.
+"""
+import numpy as np
+import torch
+
+from oracle import draws as odraws
+from tff_b200 import _lib
+
+RT = odraws.RandomType
+
+
+# ---- the kernels' step() functions -------------------------------------------------------------
+def affine_1f(x, z, c, spec=None):            # AffineModel1F::step
+  dw = z[:, 0] * c[1]
+  dt_inc = c[0] * (c[2] + c[3] * x[:, 0])
+  dw_inc = (c[4] + c[5] * x[:, 0]) * dw
+  return ((x[:, 0] + dt_inc) + dw_inc)[:, None]
+
+
+def linear_1f(x, z, c, spec=None):            # LinearModel1F::step
+  return ((c[2] * x[:, 0] + c[3]) + c[4] * z[:, 0])[:, None]
+
+
+def gbm_1f(x, z, c, spec=None):               # GbmModel1F::step
+  dw = z[:, 0] * c[1]
+  return ((x[:, 0] + c[0] * (c[2] * x[:, 0])) + (c[3] * x[:, 0]) * dw)[:, None]
+
+
+def milstein_1f(x, z, c, spec=None):          # MilsteinAffine1FModel::step
+  dw = z[:, 0] * c[1]
+  vol = c[4] + c[5] * x[:, 0]
+  hot = ((vol * c[5]) * (dw * dw - c[0])) / 2
+  return (((x[:, 0] + c[0] * (c[2] + c[3] * x[:, 0])) + vol * dw) + hot)[:, None]
+
+
+def heston_euler(x, z, c, spec=None):         # HestonEulerModel::step
+  var = x[:, 1]
+  vol = np.sqrt(np.abs(var))
+  return np.stack([vol * (z[:, 0] * c[0]) + (c[1] * var + x[:, 0]),
+                   vol * (c[5] * z[:, 1] + c[4] * z[:, 0]) + (c[2] * (c[3] - var) + var)], -1)
+
+
+def affine_nd(x, z, c, spec=None):            # AffineModelND<D>::step
+  d = x.shape[1]
+  dw = z * c[1]
+  a0, a1, b = c[2:2 + d], c[2 + d:2 + d + d * d].reshape(d, d), c[2 + d + d * d:].reshape(d, d)
+  return (x + c[0] * (a0 + x @ a1.T)) + dw @ b.T
+
+
+def tangent_affine(x, z, c, spec=None):       # TangentAffine1FModel::step
+  dw = z[:, 0] * c[1]
+  xs = x[:, 0]
+  g = c[5] * dw + c[0] * c[3]
+  return np.stack([(xs + c[0] * (c[2] + c[3] * xs)) + (c[4] + c[5] * xs) * dw,
+                   x[:, 1] * g + x[:, 1],
+                   (x[:, 2] * g + x[:, 2]) + (c[0] * (c[6] + c[7] * xs) + (c[8] + c[9] * xs) * dw)], -1)
+
+
+def tangent_heston(x, z, c, spec=None):       # TangentHestonModel::step
+  dw0, dw1 = z[:, 0] * c[1], z[:, 1] * c[1]
+  v, vt = x[:, 1], x[:, 3]
+  s = np.sqrt(np.abs(v))
+  with np.errstate(divide='ignore', invalid='ignore'):
+    ds = np.where(s > 0, np.where(v < 0, -vt, vt) / (2 * s), 0.0)
+  w = c[5] * dw0 + c[6] * dw1
+  wp = c[10] * dw0 + c[11] * dw1
+  return np.stack([(x[:, 0] + c[0] * (-0.5 * v)) + s * dw0,
+                   (v + c[0] * (c[2] * (c[3] - v))) + (c[4] * s) * w,
+                   (x[:, 2] + c[0] * (-0.5 * vt)) + ds * dw0,
+                   (vt + c[0] * (c[7] * (c[3] - v) + c[2] * (c[8] - vt)))
+                   + ((c[9] * s + c[4] * ds) * w + (c[4] * s) * wp)], -1)
+
+
+def heston_qe(x, z, c, spec=None):            # HestonQeModel::step / step_reference
+  from scipy import special
+  if c[0] == 0:                               # zero-length step: consumes its draws only
+    return x
+  v = x[:, 1]
+  m = c[2] + (v - c[2]) * c[1]
+  s2 = v * c[3] + c[4]
+  psi = s2 / (m * m)
+  with np.errstate(all='ignore'):
+    psi_inv = 2 / psi
+    b2 = psi_inv - 1 + np.sqrt(psi_inv * (psi_inv - 1))
+    quad = (m / (1 + b2)) * (np.sqrt(b2) + z[:, 0])**2
+    p = (psi - 1) / (psi + 1)
+    beta = (1 - p) / m
+    u = 0.5 * (1 + special.erf(z[:, 0] * 0.70710678118654752440))
+    expo = np.where(u > p, (np.log(1 - p) - np.log(1 - u)) / beta, 0.0)
+  vn = np.where(psi < 1.5, quad, expo)
+  xn = (((x[:, 0] + c[5]) + c[6] * v) + c[7] * vn) + np.sqrt(c[8] * v + c[9] * vn) * z[:, 1]
+  return np.stack([xn, vn], -1).astype(x.dtype)
+
+
+def hull_white_1f(x, z, c, spec=None):        # HullWhite1FModel::step, state [x, integral]
+  xn = c[2] * z[:, 0] + (c[0] * x[:, 0] + c[1])
+  return np.stack([xn, c[3] * xn + (x[:, 1] + c[4])], -1)
+
+
+def mvgbm(x, z, c, spec):                     # csrc/tqf_mvgbm.cu
+  chol, (mu, sg) = spec.device_arrays(x.dtype)
+  chol, mu, sg = chol.astype(x.dtype), mu.astype(x.dtype), sg.astype(x.dtype)
+  if getattr(spec, 'exact_log', False):       # state log x: exact log-normal increment
+    return x + (mu * c[0] + c[1] * sg * (z @ chol.T))
+  return (x + c[0] * (mu * x)) + (sg * x) * ((z * c[1]) @ chol.T)
+
+
+STEP = {
+    _lib.MODEL_AFFINE_1F: affine_1f, _lib.MODEL_LINEAR_1F: linear_1f, _lib.MODEL_GBM_1F: gbm_1f,
+    _lib.MODEL_MILSTEIN_1F: milstein_1f, _lib.MODEL_HESTON_EULER: heston_euler, _lib.MODEL_AFFINE_ND: affine_nd,
+    _lib.MODEL_AFFINE_1F_TANGENT: tangent_affine, _lib.MODEL_HESTON_TANGENT: tangent_heston,
+    _lib.MODEL_HESTON_QE: heston_qe, _lib.MODEL_HW1F: hull_white_1f, _lib.MODEL_MVGBM: mvgbm,
+}
+
+
+def unit_draws(rng, num_factors, steps_total, units, dtype):
+  """Normals `[steps_total, units, num_factors]` of the plan's units (first halves for the
+  antithetic types), addressed as `tqf.h` documents."""
+  if rng.normal_draws is not None:
+    z = rng.normal_draws.detach().cpu().numpy() if isinstance(rng.normal_draws, torch.Tensor) else np.asarray(
+        rng.normal_draws)
+    return np.transpose(z.astype(dtype), [1, 0, 2])
+  base = {RT.PSEUDO_ANTITHETIC.value: RT.PSEUDO, RT.STATELESS_ANTITHETIC.value: RT.STATELESS}.get(
+      rng.random_type.value, RT(rng.random_type.value))
+  lo = rng.unit_offset
+  hi = lo + (units - 1) * rng.unit_stride + 1
+  rows = odraws._draws_of_path_range(num_factors, steps_total, 1 << 40, base, rng.skip, rng.seed, np.dtype(dtype),
+                                     (lo, hi))
+  return rows[:, ::rng.unit_stride]
+
+
+class CpuPlan:
+  """`engine.Plan` for the CPU suite: same constructor, `paths()`, `close()`, `release()`."""
+
+  def __init__(self, spec, all_times, num_steps, x0, rng, num_samples, dtype, x0_paths=None, table=None):
+    self.spec, self.rng, self.cached = spec, rng, False
+    self.dtype = np.dtype(dtype)
+    self.num_samples, self.num_steps = int(num_samples), int(num_steps)
+    self.all_times = np.asarray(all_times, dtype=self.dtype)
+    self.num_steps_total = self.all_times.shape[0] - 1
+    if rng.antithetic and self.num_samples % 2 != 0:
+      raise ValueError('First dimension of `sample_shape` should be even for PSEUDO_ANTITHETIC random type')
+    self.units = self.num_samples // 2 if rng.antithetic else self.num_samples
+    self.table = np.asarray(spec.coef_table(self.all_times, self.dtype) if table is None else table)[:self.num_steps]
+    self.x0 = np.asarray(x0, dtype=self.dtype).reshape(-1)
+    if self.x0.shape[0] != spec.dim:
+      raise ValueError('initial state must have {} components'.format(spec.dim))
+    self.x0_paths = None if x0_paths is None else np.asarray(x0_paths, dtype=self.dtype)
+
+  def close(self):
+    pass
+
+  release = close
+
+  def paths(self, record_slot, num_times, unit_offset=0, unit_count=None, exp_transform=False, out=None,
+            column_sums=False):
+    assert unit_offset == 0 and unit_count in (None, self.units) and not column_sums
+    dt = self.dtype
+    z = unit_draws(self.rng, self.spec.num_factors, self.num_steps_total, self.units, dt)
+    if self.rng.antithetic:
+      z = np.concatenate([z, -z], axis=1)
+    rows = z.shape[1]
+    x = (np.broadcast_to(self.x0, (rows, self.spec.dim)) if self.x0_paths is None else self.x0_paths).astype(dt)
+    buf = np.zeros((num_times, self.spec.dim, rows), dtype=dt)
+    step = STEP[self.spec.kind]
+    table = self.table.astype(dt)
+    record_slot = np.asarray(record_slot)
+    for s in range(-1, self.num_steps):
+      if s >= 0:
+        x = np.asarray(step(x, z[s], table[s], self.spec), dtype=dt)
+      slot = record_slot[s + 1]
+      if slot >= 0:
+        buf[slot] = (np.exp(x) if exp_transform else x).T
+    t = torch.from_numpy(buf)
+    if out is not None:
+      out.copy_(t)
+      t = out
+    return t.permute(2, 0, 1)
