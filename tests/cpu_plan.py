@@ -12,7 +12,11 @@ plan uploads and restates what the kernels do with it:
     unit_offset`; unit u owns elements `[u D, (u + 1) D)` of the Philox stream, `D = steps *
     factors` (TensorFlow's `[units, D]` normal matrix, `models/utils.py:98-128`), or Sobol point
     `skip + 1 + u`; antithetic plans append the negated partners;
-  * the record plan (`record_slot[s + 1]` = output slot of the state after step s).
+  * the record plan (`record_slot[s + 1]` = output slot of the state after step s);
+  * the payoff evaluation of the fused mode (`eval_payoff` and the swaption payoff of
+    `csrc/tqf_paths_kernel.cuh`: running extrema of state component 0 over the initial state and
+    every executed step, the claim evaluated at its `expiry_step`, sums / sums of squares /
+    non-finite counts).
 
 The streams themselves come from the oracle.  Nothing here is shipped or imported by the package.
 """
@@ -129,6 +133,35 @@ STEP = {
 }
 
 
+def eval_payoff(d, x, xmax, xmin):
+  """`eval_payoff` / the swaption branch of the price kernel for all paths (float64)."""
+  if d.kind == _lib.PAYOFF_HW_SWAPTION:
+    acc = sum(d.pay_coef[j] * np.exp(-d.pay_g[j] * x[:, 0] + d.pay_k[j]) for j in range(d.num_payments))
+    swap = np.exp(-x[:, -1]) * (1.0 - acc)
+    return np.maximum(swap if d.is_payer else -swap, 0.0) * d.scale
+  assert not d.brownian_bridge
+  f, fmax, fmin = x[:, d.component], xmax, xmin
+  tangent = x[:, d.tangent_component]
+  fprime = 1.0
+  with np.errstate(over='ignore', invalid='ignore'):
+    if d.transform == _lib.TRANSFORM_EXP:
+      f, fmax, fmin = np.exp(f), np.exp(fmax), np.exp(fmin)
+      fprime = f
+    call, put = f - d.strike, d.strike - f
+    v = {
+        _lib.PAYOFF_CALL: np.where(call > 0, call, 0.0),
+        _lib.PAYOFF_PUT: np.where(put > 0, put, 0.0),
+        _lib.PAYOFF_UP_OUT_CALL: np.where((call > 0) & ~(fmax > d.barrier), call, 0.0),
+        _lib.PAYOFF_UP_OUT_PUT: np.where((put > 0) & ~(fmax > d.barrier), put, 0.0),
+        _lib.PAYOFF_DOWN_OUT_PUT: np.where((put > 0) & ~(fmin < d.barrier), put, 0.0),
+        _lib.PAYOFF_DOWN_OUT_CALL: np.where((call > 0) & ~(fmin < d.barrier), call, 0.0),
+        _lib.PAYOFF_CALL_TANGENT: np.where(call > 0, fprime * tangent, 0.0),
+        _lib.PAYOFF_PUT_TANGENT: np.where(put > 0, -(fprime * tangent), 0.0),
+        _lib.PAYOFF_IDENTITY: f,
+    }[d.kind]
+    return np.where(np.isfinite(f), v, np.nan) * d.scale
+
+
 def unit_draws(rng, num_factors, steps_total, units, dtype):
   """Normals `[steps_total, units, num_factors]` of the plan's units (first halves for the
   antithetic types), addressed as `tqf.h` documents."""
@@ -168,15 +201,42 @@ class CpuPlan:
 
   release = close
 
-  def paths(self, record_slot, num_times, unit_offset=0, unit_count=None, exp_transform=False, out=None,
-            column_sums=False):
-    assert unit_offset == 0 and unit_count in (None, self.units) and not column_sums
+  def clear_peer_exchange(self):
+    pass
+
+  def _start(self):
     dt = self.dtype
     z = unit_draws(self.rng, self.spec.num_factors, self.num_steps_total, self.units, dt)
     if self.rng.antithetic:
       z = np.concatenate([z, -z], axis=1)
     rows = z.shape[1]
     x = (np.broadcast_to(self.x0, (rows, self.spec.dim)) if self.x0_paths is None else self.x0_paths).astype(dt)
+    return z, x, rows
+
+  def price_sums(self, payoffs, unit_offset=0, unit_count=None):
+    """`[num_payoffs, 4]`: sum, sum of squares, number of non-finite payoffs, 0 (`tqf_plan_price`)."""
+    assert unit_offset == 0 and unit_count in (None, self.units)
+    z, x, rows = self._start()
+    descs = [p.desc() for p in payoffs]
+    xmax, xmin = x[:, 0].astype(np.float64), x[:, 0].astype(np.float64)
+    step = STEP[self.spec.kind]
+    table = self.table.astype(self.dtype)
+    out = np.zeros((len(descs), 4))
+    for s in range(self.num_steps):
+      x = np.asarray(step(x, z[s], table[s], self.spec), dtype=self.dtype)
+      xmax, xmin = np.maximum(xmax, x[:, 0]), np.minimum(xmin, x[:, 0])
+      for q, d in enumerate(descs):
+        if (d.expiry_step if d.expiry_step > 0 else self.num_steps) == s + 1:
+          v = eval_payoff(d, x.astype(np.float64), xmax, xmin)
+          ok = np.isfinite(v)
+          out[q] = [v[ok].sum(), (v[ok]**2).sum(), float((~ok).sum()), 0.0]
+    return torch.from_numpy(out)
+
+  def paths(self, record_slot, num_times, unit_offset=0, unit_count=None, exp_transform=False, out=None,
+            column_sums=False):
+    assert unit_offset == 0 and unit_count in (None, self.units) and not column_sums
+    dt = self.dtype
+    z, x, rows = self._start()
     buf = np.zeros((num_times, self.spec.dim, rows), dtype=dt)
     step = STEP[self.spec.kind]
     table = self.table.astype(dt)

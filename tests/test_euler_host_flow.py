@@ -205,3 +205,96 @@ def test_model_classes_sample_paths(cpu_engine):
   want = oeuler.sample(3, drift, vol, [0.5, 1.0], num_samples=64, initial_state=x0, num_time_steps=8,
                        random_type=rt_o, seed=[4, 2], dtype=np.float64)
   np.testing.assert_allclose(got.numpy(), want, rtol=1e-12)
+
+
+# ---- the fused mode: `price` (nothing stored) ------------------------------------------------------
+@pytest.fixture
+def cpu_pricing(cpu_engine, monkeypatch):
+  from tff_b200.models import euler_sampling
+  monkeypatch.setattr(torch.cuda, 'current_device', lambda: 0)
+  monkeypatch.setattr(euler_sampling, '_CALLS', type(euler_sampling._CALLS)())
+
+
+def test_heston_price_host_flow(cpu_pricing):
+  # the public call `bench.py` times for C2: European + up-and-out call on the Euler scheme, Sobol,
+  # barrier monitored on every grid point -- against payoffs evaluated on the oracle's paths
+  heston = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=0.5, rho=-0.7, dtype=np.float64)
+  x0 = np.array([np.log(100.0), 0.04])
+  n, steps = 2048, 32
+  payoffs = [engine.european_call(100.0, log_state=True), engine.up_and_out_call(100.0, 130.0, log_state=True),
+             engine.european_put(95.0, log_state=True), engine.down_and_out_put(100.0, 85.0, log_state=True)]
+  mean, stderr, bad = heston.price([1.0], payoffs, num_samples=n, initial_state=x0, num_time_steps=steps,
+                                   random_type=tff.math.random.RandomType.SOBOL, return_stats=True)
+  drift, vol = omodels.heston_closures(2.0, 0.04, 0.5, -0.7, np.float64)
+  paths, xmax, xmin = oeuler.sample(2, drift, vol, [1.0], num_samples=n, initial_state=x0, num_time_steps=steps,
+                                    random_type=RT.SOBOL, dtype=np.float64, return_extrema=True)
+  s, smax, smin = np.exp(paths[:, -1, 0]), np.exp(xmax), np.exp(xmin)
+  want = np.stack([np.maximum(s - 100, 0), np.where(smax > 130, 0, np.maximum(s - 100, 0)), np.maximum(95 - s, 0),
+                   np.where(smin < 85, 0, np.maximum(100 - s, 0))], -1)
+  np.testing.assert_allclose(mean, want.mean(axis=0), rtol=1e-11)
+  np.testing.assert_allclose(stderr, np.sqrt(np.maximum((want**2).mean(0) - want.mean(0)**2, 0) / n), rtol=1e-9)
+  assert (bad == 0).all() and 0 < mean[1] < mean[0] and 0 < mean[3] < want[:, 2].mean() + 5
+
+
+def test_c1_call_price_host_flow(cpu_pricing):
+  # config C1: log-space GBM (additive noise -> TQF_MODEL_LINEAR_1F), PSEUDO_ANTITHETIC seed 42
+  from tff_b200.models import closures
+  r, sigma, spot, strike = 0.03, 0.2, 100.0, 100.0
+  drift_fn, vol_fn = closures.affine_closures(r - 0.5 * sigma**2, 0.0, sigma)
+  price = tff.models.euler_sampling.price(
+      1, drift_fn, vol_fn, [1.0], [engine.european_call(strike, log_state=True, scale=np.exp(-r))],
+      num_time_steps=100, num_samples=4096, initial_state=[np.log(spot)],
+      random_type=tff.math.random.RandomType.PSEUDO_ANTITHETIC, seed=42, dtype=np.float64)
+  paths = oeuler.sample(1, lambda t, x: (r - 0.5 * sigma**2) + 0 * x, lambda t, x: (sigma + 0 * x)[..., None], [1.0],
+                        num_time_steps=100, num_samples=4096, initial_state=np.array([np.log(spot)]),
+                        random_type=RT.PSEUDO_ANTITHETIC, seed=42, dtype=np.float64)
+  want = np.exp(-r) * np.maximum(np.exp(paths[:, -1, 0]) - strike, 0).mean()
+  np.testing.assert_allclose(price, [want], rtol=1e-11)
+  from scipy.stats import norm
+  d1 = (np.log(spot / strike) + r + 0.5 * sigma**2) / sigma
+  assert abs(want - (spot * norm.cdf(d1) - strike * np.exp(-r) * norm.cdf(d1 - sigma))) < 0.5
+
+
+def test_c3_swaption_price_host_flow(cpu_pricing):
+  # config C3 through its public call: `hull_white.swaption_price(use_analytic_pricing=False)`; the reference's
+  # case (swaption_test.py:85-125, 0.71632434 +- 1e-3) against the oracle's restatement of the same pricer
+  from oracle import hull_white as ohw
+  flat = lambda t: 0.01 * np.ones_like(np.asarray(t))
+  kw = dict(expiries=np.array([1.0]), fixed_leg_payment_times=np.array([[1.25, 1.5, 1.75, 2.0]]),
+            fixed_leg_daycount_fractions=0.25 * np.ones((1, 4)), fixed_leg_coupon=0.011 * np.ones((1, 4)),
+            reference_rate_fn=flat, notional=100., mean_reversion=0.03, volatility=0.02, num_samples=1 << 15,
+            time_step=0.1, seed=[4, 2], dtype=np.float64)
+  got, stderr, bad = tff.models.hull_white.swaption_price(
+      floating_leg_start_times=None, floating_leg_end_times=None, floating_leg_daycount_fractions=None,
+      use_analytic_pricing=False, random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, return_stats=True, **kw)
+  want = ohw.swaption_price_mc(random_type=RT.STATELESS_ANTITHETIC, **kw)
+  assert got.shape == want.shape == (1,) and bad[0] == 0
+  np.testing.assert_allclose(got, want, rtol=1e-11)
+  assert abs(got[0] - 0.71632434) < 4 * stderr[0] + 2e-3
+
+
+def test_pathwise_delta_and_vega_host_flow(cpu_pricing):
+  # the notebook's second half: delta / vega of a call on log-space GBM carried as tangents and reduced in the
+  # fused kernel (`TangentAffine1FModel`, `*_TANGENT` payoffs) -- against the oracle's tangent recursion
+  from oracle import tangent as otangent
+  from tff_b200.models import closures
+  r, sigma, spot, strike, n, steps = 0.03, 0.2, 100.0, 100.0, 4096, 16
+  # X = log S: a0 = r - sigma^2 / 2, b0 = sigma; d/dsigma: da0 = -sigma, db0 = 1
+  drift_fn, vol_fn = closures.affine_tangent_closures(r - 0.5 * sigma**2, 0.0, sigma, 0.0, da0=-sigma, db=1.0)
+  spec = drift_fn.tqf_spec
+  payoffs = [engine.european_call(strike, log_state=True, scale=np.exp(-r)),
+             engine.european_call_tangent(strike, spec.D_INITIAL, log_state=True, scale=np.exp(-r) / spot),
+             engine.european_call_tangent(strike, spec.D_THETA, log_state=True, scale=np.exp(-r))]
+  got = tff.models.euler_sampling.price(1, drift_fn, vol_fn, [1.0], payoffs, num_time_steps=steps, num_samples=n,
+                                        initial_state=[np.log(spot)], random_type=tff.math.random.RandomType.SOBOL,
+                                        dtype=np.float64)
+  st = otangent.sample_with_tangents(r - 0.5 * sigma**2, 0.0, sigma, 0.0, -sigma, 0.0, 1.0, 0.0, [1.0],
+                                     [np.log(spot)], n, random_type=RT.SOBOL, num_time_steps=steps)[:, -1]
+  s = np.exp(st[:, 0])
+  itm = s > strike
+  want = [np.exp(-r) * np.maximum(s - strike, 0).mean(), np.exp(-r) / spot * np.where(itm, s * st[:, 1], 0).mean(),
+          np.exp(-r) * np.where(itm, s * st[:, 2], 0).mean()]
+  np.testing.assert_allclose(got, want, rtol=1e-10)
+  from scipy.stats import norm
+  d1 = (np.log(spot / strike) + r + 0.5 * sigma**2) / sigma
+  assert abs(got[1] - norm.cdf(d1)) < 2e-2 and abs(got[2] - spot * norm.pdf(d1)) < 1.0     # Black-Scholes delta, vega
