@@ -252,3 +252,31 @@ class CpuPlan:
       out.copy_(t)
       t = out
     return t.permute(2, 0, 1)
+
+
+def install(monkeypatch):
+  """Replace, for one test, everything of the mirror that touches the device: the plan and the
+  stand-alone generator fills (`tff_b200.math.random.{philox, sobol, halton}`), whose outputs become
+  CPU tensors holding the oracle's streams."""
+  from oracle import halton as ohalton
+  from oracle import philox as ophilox
+  from oracle import sobol as osobol
+  from tff_b200 import _tensor
+  from tff_b200 import engine
+  from tff_b200.math.random import halton, philox, sobol
+  monkeypatch.setattr(engine, 'Plan', CpuPlan)
+  monkeypatch.setattr(engine, 'cached_plan', lambda *a, **k: CpuPlan(*a, **k))
+  monkeypatch.setattr(_tensor, 'device', lambda: torch.device('cpu'))
+  monkeypatch.setattr(torch.cuda, 'current_device', lambda: 0)
+  monkeypatch.setattr(philox, 'normal', lambda shape, dtype=None, seed=None: torch.from_numpy(
+      ophilox.stateful_normal(tuple(shape), seed, np.dtype(dtype))))
+  monkeypatch.setattr(philox, 'stateless_normal', lambda shape, seed, dtype=None: torch.from_numpy(
+      ophilox.stateless_normal(tuple(shape), seed, np.dtype(dtype))))
+  monkeypatch.setattr(sobol, 'sample_normal', lambda dim, n, skip=0, dtype=None: torch.from_numpy(
+      odraws._erfinv_times_sqrt2(osobol.sample(dim, n, skip=skip, dtype=dtype), dtype)))
+
+  def halton_normal(dim, n, skip=0, dtype=None, randomized=False, seed=None, randomization_params=None):
+    assert randomization_params is None
+    u = ohalton.sample(dim, sequence_indices=np.arange(skip, skip + n), dtype=dtype, randomized=randomized, seed=seed)
+    return torch.from_numpy(odraws._erfinv_times_sqrt2(u, dtype))
+  monkeypatch.setattr(halton, 'sample_normal', halton_normal)

@@ -21,7 +21,6 @@ import cpu_plan  # pylint: disable=g-import-not-at-top
 
 from oracle import draws as odraws
 from oracle import euler as oeuler
-from oracle import halton as ohalton
 from oracle import heston_qe as oqe
 from oracle import models as omodels
 from oracle import philox as ophilox
@@ -34,15 +33,7 @@ RT = odraws.RandomType
 
 @pytest.fixture
 def cpu_engine(monkeypatch):
-  monkeypatch.setattr(engine, 'Plan', cpu_plan.CpuPlan)
-  monkeypatch.setattr(engine, 'cached_plan', lambda *a, **k: cpu_plan.CpuPlan(*a, **k))
-  monkeypatch.setattr(_tensor, 'device', lambda: torch.device('cpu'))
-  from tff_b200.math.random import halton
-
-  def halton_normal(dim, n, skip=0, dtype=None, randomized=False, seed=None, randomization_params=None):
-    u = ohalton.sample(dim, sequence_indices=np.arange(skip, skip + n), dtype=dtype, randomized=randomized, seed=seed)
-    return torch.from_numpy(odraws._erfinv_times_sqrt2(u, dtype))
-  monkeypatch.setattr(halton, 'sample_normal', halton_normal)
+  cpu_plan.install(monkeypatch)
 
 
 def _rt(name):
@@ -211,7 +202,6 @@ def test_model_classes_sample_paths(cpu_engine):
 @pytest.fixture
 def cpu_pricing(cpu_engine, monkeypatch):
   from tff_b200.models import euler_sampling
-  monkeypatch.setattr(torch.cuda, 'current_device', lambda: 0)
   monkeypatch.setattr(euler_sampling, '_CALLS', type(euler_sampling._CALLS)())
 
 
@@ -298,3 +288,47 @@ def test_pathwise_delta_and_vega_host_flow(cpu_pricing):
   from scipy.stats import norm
   d1 = (np.log(spot / strike) + r + 0.5 * sigma**2) / sigma
   assert abs(got[1] - norm.cdf(d1)) < 2e-2 and abs(got[2] - spot * norm.pdf(d1)) < 1.0     # Black-Scholes delta, vega
+
+
+# ---- the Milstein sampler --------------------------------------------------------------------------
+@pytest.mark.parametrize('random_type,dtype', [('STATELESS_ANTITHETIC', np.float64), ('SOBOL', np.float64),
+                                               ('STATELESS', np.float32)])
+def test_milstein_host_flow(cpu_engine, random_type, dtype):
+  # milstein_sampling_test.py:165-230: dX = r X dt + sigma X dW, the correction sigma^2 X (dW^2 - dt) / 2 active;
+  # the reference's `dim + 3 dim order` draw tensor is generated and its first column fed to the kernel
+  from oracle import milstein as omilstein
+  prt, ort = _rt(random_type)
+  r, sigma = 0.5, 0.5
+  times = np.array([0.0, 0.1, 0.21, 0.32, 0.43, 0.55], dtype=dtype)
+  x0 = np.array([0.1], dtype=dtype)
+  process = tff.models.GeometricBrownianMotion(r, sigma, dtype=dtype)
+  kw = dict(num_samples=128, initial_state=x0, time_step=0.01, seed=[1, 42], skip=3)
+  got = tff.models.milstein_sampling.sample(dim=1, drift_fn=process.drift_fn(), volatility_fn=process.volatility_fn(),
+                                            times=times, random_type=prt, dtype=dtype, **kw)
+  want = omilstein.sample(dim=1, drift_fn=lambda t, x: dtype(r) * x, volatility_fn=lambda t, x: (dtype(sigma) * x)[..., None],
+                          grad_volatility_fn=lambda t, x: dtype(sigma) * np.ones(x.shape + (1,), dtype=dtype),
+                          times=times, random_type=ort, dtype=dtype, **kw)
+  assert tuple(got.shape) == want.shape == (128, 6, 1) and got.numpy().dtype == dtype
+  if dtype == np.float64:
+    np.testing.assert_allclose(got.numpy(), want, rtol=1e-12)
+  else:
+    np.testing.assert_allclose(got.numpy(), want, rtol=1e-5, atol=2e-7)
+
+
+def test_milstein_nd_host_flow(cpu_engine):
+  # state-independent volatility matrix: the gradient is zero, the Stratonovich terms vanish and the step is the
+  # Euler kernel on the first `dim` columns of the `dim + 3 dim order` draw tensor (`milstein_sampling.py:481-595`)
+  from oracle import milstein as omilstein
+  prt, ort = _rt('STATELESS')
+  times = np.array([0.1, 0.21, 0.32])
+  x0 = np.array([0.1, -1.1])
+  kw = dict(num_samples=64, initial_state=x0, time_step=0.01, seed=[1, 42])
+  got = tff.models.milstein_sampling.sample(
+      dim=2, drift_fn=lambda t, x: torch.as_tensor(MU2) * torch.sqrt(t) * torch.ones_like(x),
+      volatility_fn=lambda t, x: (torch.as_tensor(A2) * t + torch.as_tensor(B2)) * torch.ones([2, 2], dtype=torch.float64),
+      times=times, random_type=prt, dtype=np.float64, **kw)
+  want = omilstein.sample(dim=2, drift_fn=lambda t, x: MU2 * np.sqrt(t) * np.ones_like(x),
+                          volatility_fn=lambda t, x: np.broadcast_to(A2 * t + B2, x.shape + (2,)),
+                          grad_volatility_fn=lambda t, x: [np.zeros(x.shape + (2,)) for _ in range(2)],
+                          times=times, random_type=ort, dtype=np.float64, **kw)
+  np.testing.assert_allclose(got.numpy(), want, rtol=1e-9, atol=1e-11)
