@@ -204,19 +204,25 @@ class CpuPlan:
   def clear_peer_exchange(self):
     pass
 
-  def _start(self):
+  def _start(self, unit_offset=0, unit_count=None):
+    """Draws and initial states of the units [unit_offset, unit_offset + unit_count) -- the range a
+    rank owns in a sharded run; rows are [units | their antithetic partners]."""
     dt = self.dtype
+    unit_count = self.units - unit_offset if unit_count is None else int(unit_count)
+    assert 0 <= unit_offset and unit_offset + unit_count <= self.units
     z = unit_draws(self.rng, self.spec.num_factors, self.num_steps_total, self.units, dt)
+    z = z[:, unit_offset:unit_offset + unit_count]
+    sel = np.arange(unit_offset, unit_offset + unit_count)
     if self.rng.antithetic:
       z = np.concatenate([z, -z], axis=1)
+      sel = np.concatenate([sel, sel + self.units])
     rows = z.shape[1]
-    x = (np.broadcast_to(self.x0, (rows, self.spec.dim)) if self.x0_paths is None else self.x0_paths).astype(dt)
+    x = (np.broadcast_to(self.x0, (rows, self.spec.dim)) if self.x0_paths is None else self.x0_paths[sel]).astype(dt)
     return z, x, rows
 
   def price_sums(self, payoffs, unit_offset=0, unit_count=None):
     """`[num_payoffs, 4]`: sum, sum of squares, number of non-finite payoffs, 0 (`tqf_plan_price`)."""
-    assert unit_offset == 0 and unit_count in (None, self.units)
-    z, x, rows = self._start()
+    z, x, rows = self._start(unit_offset, unit_count)
     descs = [p.desc() for p in payoffs]
     xmax, xmin = x[:, 0].astype(np.float64), x[:, 0].astype(np.float64)
     step = STEP[self.spec.kind]
@@ -234,9 +240,9 @@ class CpuPlan:
 
   def paths(self, record_slot, num_times, unit_offset=0, unit_count=None, exp_transform=False, out=None,
             column_sums=False):
-    assert unit_offset == 0 and unit_count in (None, self.units) and not column_sums
+    assert not column_sums
     dt = self.dtype
-    z, x, rows = self._start()
+    z, x, rows = self._start(unit_offset, unit_count)
     buf = np.zeros((num_times, self.spec.dim, rows), dtype=dt)
     step = STEP[self.spec.kind]
     table = self.table.astype(dt)

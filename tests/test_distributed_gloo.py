@@ -212,3 +212,95 @@ def test_two_rank_sharded_lsm_matches_single_process_oracle(tmp_path):
   single = _sharded_lsm(paths, np.arange(9), 1.1, 3, df, lambda t: t)
   np.testing.assert_allclose(single, want[0], rtol=1e-6)
   np.testing.assert_allclose(got[0], single, rtol=1e-6)
+
+
+# ---- the product's own sharded flow, the device plan replaced by the CPU stand-in -----------------
+def _sharded_flow_worker(rank, world_size, port, out):
+  """`distributed.sharded()` around the public pricing calls, `paths_sharded`: every line of host
+  code the multi-GPU run executes, with `tests/cpu_plan.CpuPlan` in place of the device plan."""
+  import sys
+  import pytest as _pytest
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  import cpu_plan
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world_size)
+  mp_ = _pytest.MonkeyPatch()
+  try:
+    cpu_plan.install(mp_)
+    import tff_b200 as tff
+    from tff_b200 import distributed, engine
+    from tff_b200.models import euler_sampling
+    mp_.setattr(euler_sampling, '_CALLS', type(euler_sampling._CALLS)())
+    rt = tff.math.random.RandomType
+    heston = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=0.5, rho=-0.7, dtype=np.float64)
+    x0 = np.array([np.log(100.0), 0.04])
+    payoffs = [engine.european_call(100.0, log_state=True), engine.up_and_out_call(100.0, 130.0, log_state=True)]
+    res = {}
+    for name, kw in (('sobol', dict(random_type=rt.SOBOL)),
+                     ('anti', dict(random_type=rt.STATELESS_ANTITHETIC, seed=[4, 2]))):
+      with distributed.sharded():
+        res[name] = heston.price([1.0], payoffs, num_samples=1002, initial_state=x0, num_time_steps=8,
+                                 return_stats=True, **kw)
+    flat = lambda t: 0.01 * np.ones_like(np.asarray(t))
+    with distributed.sharded():
+      res['swaption'] = tff.models.hull_white.swaption_price(
+          expiries=np.array([1.0]), floating_leg_start_times=None, floating_leg_end_times=None,
+          floating_leg_daycount_fractions=None, fixed_leg_payment_times=np.array([[1.25, 1.5, 1.75, 2.0]]),
+          fixed_leg_daycount_fractions=0.25 * np.ones((1, 4)), fixed_leg_coupon=0.011 * np.ones((1, 4)),
+          reference_rate_fn=flat, notional=100., mean_reversion=0.03, volatility=0.02, num_samples=1000,
+          time_step=0.1, seed=[4, 2], dtype=np.float64, use_analytic_pricing=False,
+          random_type=rt.STATELESS_ANTITHETIC)
+    # this rank's rows of a materialised antithetic run and the global index of its first unit
+    gbm = tff.models.GeometricBrownianMotion(0.05, 0.3, dtype=np.float64)
+    plans, record_slot, k, _ = euler_sampling._prepare(
+        1, gbm.drift_fn(), gbm.volatility_fn(), [0.5, 1.0], None, 4, 10, [100.0], rt.STATELESS_ANTITHETIC, [1, 2],
+        0, None, None, None, False, None, np.float64)
+    rows, lo = distributed.paths_sharded(plans[0], record_slot, k)
+    res['rows'], res['lo'] = rows.numpy().copy(), lo
+    assert getattr(rows, '_tqf_antithetic_shard', False)
+    np.save(os.path.join(out, 'flow_%d.npy' % rank), np.array([res], dtype=object), allow_pickle=True)
+  finally:
+    mp_.undo()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_product_flow_matches_one_rank(tmp_path, monkeypatch):
+  port = _free_port()
+  mp.spawn(_sharded_flow_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  r0, r1 = (np.load(os.path.join(str(tmp_path), 'flow_%d.npy' % r), allow_pickle=True)[0] for r in (0, 1))
+  # the same calls on one rank
+  import sys
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  import cpu_plan
+  cpu_plan.install(monkeypatch)
+  import tff_b200 as tff
+  from tff_b200 import engine
+  from tff_b200.models import euler_sampling
+  monkeypatch.setattr(euler_sampling, '_CALLS', type(euler_sampling._CALLS)())
+  rt = tff.math.random.RandomType
+  heston = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=0.5, rho=-0.7, dtype=np.float64)
+  x0 = np.array([np.log(100.0), 0.04])
+  payoffs = [engine.european_call(100.0, log_state=True), engine.up_and_out_call(100.0, 130.0, log_state=True)]
+  for name, kw in (('sobol', dict(random_type=rt.SOBOL)), ('anti', dict(random_type=rt.STATELESS_ANTITHETIC, seed=[4, 2]))):
+    one = heston.price([1.0], payoffs, num_samples=1002, initial_state=x0, num_time_steps=8, return_stats=True, **kw)
+    for got in (r0[name], r1[name]):                   # GLOBAL prices on every rank
+      for a, b in zip(got, one):
+        np.testing.assert_allclose(a, b, rtol=1e-12)
+  np.testing.assert_allclose(r0['swaption'], r1['swaption'], rtol=0, atol=0)
+  from oracle import hull_white as ohw
+  flat = lambda t: 0.01 * np.ones_like(np.asarray(t))
+  want = ohw.swaption_price_mc(
+      expiries=np.array([1.0]), fixed_leg_payment_times=np.array([[1.25, 1.5, 1.75, 2.0]]),
+      fixed_leg_daycount_fractions=0.25 * np.ones((1, 4)), fixed_leg_coupon=0.011 * np.ones((1, 4)),
+      reference_rate_fn=flat, notional=100., mean_reversion=0.03, volatility=0.02, num_samples=1000, time_step=0.1,
+      seed=[4, 2], dtype=np.float64, random_type=odraws.RandomType.STATELESS_ANTITHETIC)
+  np.testing.assert_allclose(r0['swaption'], want, rtol=1e-11)
+  # materialised antithetic run of 10 paths = 5 units: rank 0 owns units 0..2, rank 1 units 3..4; rows are
+  # [units | partners] and together they are the one-rank tensor
+  gbm = tff.models.GeometricBrownianMotion(0.05, 0.3, dtype=np.float64)
+  full = tff.models.euler_sampling.sample(1, gbm.drift_fn(), gbm.volatility_fn(), [0.5, 1.0], num_time_steps=4,
+                                          num_samples=10, initial_state=[100.0], random_type=rt.STATELESS_ANTITHETIC,
+                                          seed=[1, 2], dtype=np.float64).numpy()
+  assert (r0['lo'], r1['lo']) == (0, 3) and r0['rows'].shape[0] == 6 and r1['rows'].shape[0] == 4
+  np.testing.assert_array_equal(np.concatenate([r0['rows'][:3], r1['rows'][:2], r0['rows'][3:], r1['rows'][2:]]), full)
