@@ -332,3 +332,34 @@ def test_milstein_nd_host_flow(cpu_engine):
                           grad_volatility_fn=lambda t, x: [np.zeros(x.shape + (2,)) for _ in range(2)],
                           times=times, random_type=ort, dtype=np.float64, **kw)
   np.testing.assert_allclose(got.numpy(), want, rtol=1e-9, atol=1e-11)
+
+
+# ---- batches of processes: one plan per batch element, draw units strided / offset -----------------
+@pytest.mark.parametrize('random_type,seed,skip', [('SOBOL', None, 3), ('STATELESS', [4, 2], 0),
+                                                   ('STATELESS_ANTITHETIC', [4, 2], 0), ('PSEUDO_ANTITHETIC', 9, 0)])
+def test_batch_of_initial_states(cpu_engine, random_type, seed, skip):
+  # batch_shape = initial_state.shape[:-2] (euler_sampling.py:251); draws laid out [steps] + batch + [N, dim], or
+  # [N / 2] + batch for the antithetic types (models/utils.py:98-128)
+  prt, ort = _rt(random_type)
+  heston = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=0.5, rho=-0.7, dtype=np.float64)
+  odrift, ovol = omodels.heston_closures(2.0, 0.04, 0.5, -0.7, np.float64)
+  x0 = np.array([[[np.log(100.0), 0.04]], [[np.log(90.0), 0.09]], [[np.log(120.0), 0.01]]])
+  kw = dict(num_samples=64, initial_state=x0, seed=seed, skip=skip, num_time_steps=6, dtype=np.float64)
+  got = tff.models.euler_sampling.sample(2, heston.drift_fn(), heston.volatility_fn(), [0.5, 1.0], random_type=prt, **kw)
+  want = oeuler.sample(2, odrift, ovol, [0.5, 1.0], random_type=ort, **kw)
+  assert tuple(got.shape) == want.shape == (3, 64, 2, 2)
+  np.testing.assert_allclose(got.numpy(), want, rtol=1e-11, atol=1e-13)
+
+
+def test_batch_of_gbm_parameters(cpu_engine):
+  # batched GBM parameters of shape batch_shape + [1] (univariate_geometric_brownian_motion.py:66-80)
+  from tff_b200.models import closures
+  mean, vol = np.array([[0.01], [0.05]]), np.array([[0.1], [0.3]])
+  drift, volf = closures.gbm_closures(mean, vol)
+  x0 = np.array([[[1.0]], [[2.0]]])
+  kw = dict(num_samples=70, initial_state=x0, seed=[1, 5], time_step=0.1, dtype=np.float64)
+  got = tff.models.euler_sampling.sample(1, drift, volf, [1.0], random_type=tff.math.random.RandomType.STATELESS, **kw)
+  want = oeuler.sample(1, lambda t, x: mean[:, None, :] * x, lambda t, x: (vol[:, None, :] * x)[..., None], [1.0],
+                       random_type=RT.STATELESS, **kw)
+  assert tuple(got.shape) == want.shape == (2, 70, 1, 1)
+  np.testing.assert_allclose(got.numpy(), want, rtol=1e-12)
