@@ -363,3 +363,43 @@ def test_batch_of_gbm_parameters(cpu_engine):
                        random_type=RT.STATELESS, **kw)
   assert tuple(got.shape) == want.shape == (2, 70, 1, 1)
   np.testing.assert_allclose(got.numpy(), want, rtol=1e-12)
+
+
+# ---- Hull-White samplers (exact OU step) -----------------------------------------------------------
+def _flat_rate(t):
+  return 0.01 * np.ones_like(np.asarray(t))
+
+
+def test_hull_white_1f_sample_paths(cpu_engine):
+  # vector_hull_white.py:641-781 for dim 1: piecewise-constant volatility (jumps enter the grid), a times_grid
+  from oracle import hull_white as ohw
+  prt, ort = _rt('STATELESS_ANTITHETIC')
+  pw = tff.math.piecewise.PiecewiseConstantFunc([0.1, 0.5], [0.01, 0.02, 0.015], dtype=np.float64)
+  opw = omodels.PiecewiseConstantFunc([0.1, 0.5], [0.01, 0.02, 0.015], dtype=np.float64)
+  model = tff.models.hull_white.HullWhiteModel1F(0.03, pw, _flat_rate, dtype=np.float64)
+  omodel = ohw.HullWhiteModel1F(0.03, opw, _flat_rate, np.float64)
+  for kw in (dict(), dict(times_grid=np.linspace(0.0, 1.0, 11))):
+    got = model.sample_paths([0.1, 0.5, 1.0], num_samples=64, random_type=prt, seed=[1, 2], **kw)
+    want = omodel.sample_paths([0.1, 0.5, 1.0], 64, ort, seed=[1, 2], **kw)
+    assert tuple(got.shape) == want.shape == (64, 3, 1)
+    np.testing.assert_allclose(got.numpy(), want, rtol=1e-11, atol=1e-14)
+
+
+def test_vector_hull_white_sample_paths(cpu_engine):
+  # hull_white_test.py:223-270: two correlated factors, one piecewise-constant volatility each
+  from oracle import hull_white as ohw
+  prt, ort = _rt('STATELESS_ANTITHETIC')
+  a, sigma = np.array([0.1, 0.05]), np.array([0.01, 0.02])
+  vol = tff.math.piecewise.PiecewiseConstantFunc([[0.1, 0.2, 0.5], [0.1, 2.0, 3.0]],
+                                                 [[0.01, 0.012, 0.009, 0.01], [0.02, 0.02, 0.02, 0.02]], dtype=np.float64)
+  ovols = [omodels.PiecewiseConstantFunc([0.1, 0.2, 0.5], [0.01, 0.012, 0.009, 0.01], dtype=np.float64),
+           omodels.PiecewiseConstantFunc([0.1, 2.0, 3.0], 4 * [0.02], dtype=np.float64)]
+  flat2 = lambda t: 0.01 * np.ones(np.shape(t) + (2,)) if not isinstance(t, torch.Tensor) else 0.01 * torch.ones(
+      tuple(t.shape) + (2,), dtype=t.dtype)
+  model = tff.models.hull_white.VectorHullWhiteModel(2, a, vol, flat2, corr_matrix=[[1., 0.5], [0.5, 1.]],
+                                                     dtype=np.float64)
+  omodel = ohw.VectorHullWhiteModel(2, a, ovols, _flat_rate, [[1., 0.5], [0.5, 1.]])
+  got = model.sample_paths([0.1, 0.5, 1.0], num_samples=64, random_type=prt, seed=[1, 2])
+  want = omodel.sample_paths([0.1, 0.5, 1.0], 64, ort, seed=[1, 2])
+  assert tuple(got.shape) == want.shape == (64, 3, 2)
+  np.testing.assert_allclose(got.numpy(), want, rtol=1e-10, atol=1e-13)
