@@ -403,3 +403,31 @@ def test_vector_hull_white_sample_paths(cpu_engine):
   want = omodel.sample_paths([0.1, 0.5, 1.0], 64, ort, seed=[1, 2])
   assert tuple(got.shape) == want.shape == (64, 3, 2)
   np.testing.assert_allclose(got.numpy(), want, rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize('mode', ['num_time_steps', 'time_step', 'times_grid', 'times_grid_and_draws'])
+def test_heston_qe_grid_modes(cpu_engine, mode):
+  # heston_model_test.py:270-378: the four ways `HestonModel.sample_paths` is told its grid, piecewise mean reversion
+  prt, ort = _rt('STATELESS_ANTITHETIC')
+  jumps, vals = [0.1, 0.2], [0.3, 0.3, 0.3]
+  heston = tff.models.HestonModel(mean_reversion=tff.math.piecewise.PiecewiseConstantFunc(jumps, vals, dtype=np.float64),
+                                  theta=0.05, volvol=0.02, rho=0.1, dtype=np.float64)
+  okappa = omodels.PiecewiseConstantFunc(jumps, vals, dtype=np.float64)
+  x0 = np.array([3.0, 0.05])
+  kw, okw = dict(num_samples=200, random_type=prt, seed=[1, 42]), dict(num_samples=200, random_type=ort, seed=[1, 42])
+  extra = {}
+  if mode == 'num_time_steps':
+    extra['num_time_steps'] = 100
+  else:
+    extra['time_step'] = 0.01
+  if mode.startswith('times_grid'):
+    extra['times_grid'] = np.linspace(0.0, 1.0, 101)
+  if mode == 'times_grid_and_draws':
+    z = ophilox.stateless_normal([100, 100, 2], [1, 42], np.float64)
+    draws = np.concatenate([z, -z], axis=0)
+    kw.update(num_samples=1, normal_draws=torch.from_numpy(draws))
+    okw.update(num_samples=1, normal_draws=draws)
+  got = heston.sample_paths(times=[0.5, 1.0], initial_state=x0, **kw, **extra)
+  want = oqe.sample_paths(okappa, 0.05, 0.02, 0.1, [0.5, 1.0], x0, **okw, **extra)
+  assert tuple(got.shape) == want.shape == (200, 2, 2)
+  np.testing.assert_allclose(got.numpy(), want, rtol=1e-10, atol=1e-12)
