@@ -224,13 +224,17 @@ class CpuPlan:
     """`[num_payoffs, 4]`: sum, sum of squares, number of non-finite payoffs, 0 (`tqf_plan_price`)."""
     z, x, rows = self._start(unit_offset, unit_count)
     descs = [p.desc() for p in payoffs]
-    xmax, xmin = x[:, 0].astype(np.float64), x[:, 0].astype(np.float64)
+    barrier_kinds = (_lib.PAYOFF_UP_OUT_CALL, _lib.PAYOFF_UP_OUT_PUT, _lib.PAYOFF_DOWN_OUT_PUT, _lib.PAYOFF_DOWN_OUT_CALL)
+    monitored = {d.component for d in descs if d.kind in barrier_kinds}
+    assert len(monitored) <= 1                  # the kernel monitors ONE state component (tqf_paths.cu)
+    mon = monitored.pop() if monitored else 0
+    xmax, xmin = x[:, mon].astype(np.float64), x[:, mon].astype(np.float64)
     step = STEP[self.spec.kind]
     table = self.table.astype(self.dtype)
     out = np.zeros((len(descs), 4))
     for s in range(self.num_steps):
       x = np.asarray(step(x, z[s], table[s], self.spec), dtype=self.dtype)
-      xmax, xmin = np.maximum(xmax, x[:, 0]), np.minimum(xmin, x[:, 0])
+      xmax, xmin = np.maximum(xmax, x[:, mon]), np.minimum(xmin, x[:, mon])
       for q, d in enumerate(descs):
         if (d.expiry_step if d.expiry_step > 0 else self.num_steps) == s + 1:
           v = eval_payoff(d, x.astype(np.float64), xmax, xmin)
