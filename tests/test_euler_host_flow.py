@@ -431,3 +431,65 @@ def test_heston_qe_grid_modes(cpu_engine, mode):
   want = oqe.sample_paths(okappa, 0.05, 0.02, 0.1, [0.5, 1.0], x0, **okw, **extra)
   assert tuple(got.shape) == want.shape == (200, 2, 2)
   np.testing.assert_allclose(got.numpy(), want, rtol=1e-10, atol=1e-12)
+
+
+# ---- a seeded sweep over grids: requested times on / off / near grid points, every grid mode -------
+@pytest.mark.parametrize('case', range(40))
+def test_grid_sweep(cpu_engine, case):
+  rs = np.random.RandomState(1000 + case)
+  dtype = np.float64 if case % 4 else np.float32
+  k = rs.randint(1, 6)
+  mode = ('time_step', 'num_time_steps', 'times_grid')[case % 3]
+  if mode == 'time_step':
+    step = dtype([0.05, 0.1, 0.125, 0.3][rs.randint(4)])
+    # some requested times are exact multiples of the step, some within the de-duplication tolerance of one
+    times = np.sort(np.concatenate([step * rs.randint(1, 12, size=k), rs.uniform(0.01, 1.2, size=rs.randint(0, 3))]))
+    if case % 5 == 0:
+      times[0] = times[0] * (1 + 1e-12)
+    grid = dict(time_step=step)
+  elif mode == 'num_time_steps':
+    times = np.sort(rs.uniform(0.01, 2.0, size=k))
+    grid = dict(num_time_steps=int(rs.randint(1, 20)))
+  else:
+    g = np.unique(np.concatenate([[0.0], np.round(rs.uniform(0.0, 2.0, size=rs.randint(3, 25)), 3)]))
+    times = np.sort(rs.choice(g[1:], size=min(k, g.shape[0] - 1), replace=False)) if case % 2 else np.sort(
+        rs.uniform(0.01, g[-1], size=k))
+    grid = dict(times_grid=g.astype(dtype))
+  if case % 7 == 0:
+    times = np.concatenate([[0.0], times])          # the initial time among the requested ones
+  times = times.astype(dtype)
+  gbm = tff.models.GeometricBrownianMotion(0.05, 0.3, dtype=dtype)
+  drift, vol = omodels.gbm_closures(0.05, 0.3, dtype)
+  kw = dict(num_samples=8, initial_state=np.array([1.5], dtype=dtype), seed=[case, 7], dtype=dtype, **grid)
+  want = oeuler.sample(1, drift, vol, times, random_type=RT.STATELESS, **kw)
+  got = tff.models.euler_sampling.sample(1, gbm.drift_fn(), gbm.volatility_fn(), times,
+                                         random_type=tff.math.random.RandomType.STATELESS, **kw)
+  assert tuple(got.shape) == want.shape
+  np.testing.assert_allclose(got.numpy(), want, rtol=1e-12 if dtype == np.float64 else 1e-5)
+
+
+@pytest.mark.parametrize('case', range(8))
+def test_swaption_batch_sweep(cpu_pricing, case):
+  # batches of swaptions with expiries off the time_step grid (on the grid the reference's own bookkeeping
+  # breaks, see tests/test_hw_replay.py), payer / receiver, piecewise volatility in half of the cases
+  from oracle import hull_white as ohw
+  rs = np.random.RandomState(50 + case)
+  b = rs.randint(1, 4)
+  expiries = np.sort(np.round(rs.uniform(0.3, 3.0, size=b), 2)) + 0.003
+  pay = expiries[:, None] + 0.25 * np.arange(1, 5)[None, :]
+  is_payer = rs.rand(b) < 0.5
+  if case % 2:
+    vol = tff.math.piecewise.PiecewiseConstantFunc([0.5, 1.7], [0.01, 0.02, 0.015], dtype=np.float64)
+    ovol = omodels.PiecewiseConstantFunc([0.5, 1.7], [0.01, 0.02, 0.015], dtype=np.float64)
+  else:
+    vol = ovol = 0.015
+  kw = dict(expiries=expiries, fixed_leg_payment_times=pay, fixed_leg_daycount_fractions=0.25 * np.ones((b, 4)),
+            fixed_leg_coupon=rs.uniform(0.005, 0.02) * np.ones((b, 4)), reference_rate_fn=_flat_rate, notional=100.,
+            mean_reversion=0.03, is_payer_swaption=is_payer, num_samples=512, time_step=[0.1, 0.25][case % 2],
+            seed=[case, 2], dtype=np.float64)
+  got = tff.models.hull_white.swaption_price(
+      floating_leg_start_times=None, floating_leg_end_times=None, floating_leg_daycount_fractions=None,
+      use_analytic_pricing=False, random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, volatility=vol, **kw)
+  want = ohw.swaption_price_mc(random_type=RT.STATELESS_ANTITHETIC, volatility=ovol, **kw)
+  assert got.shape == want.shape == (b,)
+  np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
