@@ -493,3 +493,34 @@ def test_swaption_batch_sweep(cpu_pricing, case):
   want = ohw.swaption_price_mc(random_type=RT.STATELESS_ANTITHETIC, volatility=ovol, **kw)
   assert got.shape == want.shape == (b,)
   np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize('case', range(24))
+def test_generator_and_initial_state_sweep(cpu_engine, case):
+  # random type x (single | batch | per-path) initial state x skip x dtype on the Heston closures
+  rs = np.random.RandomState(300 + case)
+  name = ['PSEUDO', 'STATELESS', 'SOBOL', 'PSEUDO_ANTITHETIC', 'STATELESS_ANTITHETIC', 'HALTON'][case % 6]
+  prt, ort = _rt(name)
+  seed = {'PSEUDO': 11 + case, 'PSEUDO_ANTITHETIC': 11 + case, 'SOBOL': None, 'HALTON': None}.get(name, [case, 3])
+  skip = int(rs.randint(0, 50)) if name in ('SOBOL', 'HALTON') else 0
+  dtype = np.float32 if case % 8 == 7 else np.float64
+  n = 32
+  shape_kind = ('single', 'batch', 'per_path')[(case // 6) % 3]
+  if name == 'HALTON' and shape_kind == 'batch':
+    shape_kind = 'single'                   # (batched processes with HALTON draws are refused by the mirror)
+  if shape_kind == 'single':
+    x0 = np.array([np.log(100.0), 0.04])
+  elif shape_kind == 'batch':
+    x0 = np.stack([np.log(rs.uniform(80, 120, size=3)), rs.uniform(0.01, 0.09, size=3)], -1)[:, None, :]
+  else:
+    x0 = np.stack([np.log(rs.uniform(80, 120, size=n)), rs.uniform(0.01, 0.09, size=n)], -1)
+  heston = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=0.5, rho=-0.7, dtype=dtype)
+  odrift, ovol = omodels.heston_closures(2.0, 0.04, 0.5, -0.7, dtype)
+  kw = dict(num_samples=n, initial_state=x0.astype(dtype), seed=seed, skip=skip, num_time_steps=5, dtype=dtype)
+  got = tff.models.euler_sampling.sample(2, heston.drift_fn(), heston.volatility_fn(), [0.4, 1.0], random_type=prt, **kw)
+  want = oeuler.sample(2, odrift, ovol, [0.4, 1.0], random_type=ort, **kw)
+  assert tuple(got.shape) == want.shape
+  if dtype == np.float64:
+    np.testing.assert_allclose(got.numpy(), want, rtol=1e-11, atol=1e-13)
+  else:
+    np.testing.assert_allclose(got.numpy(), want, rtol=2e-5, atol=2e-6)
