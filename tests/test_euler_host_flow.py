@@ -524,3 +524,22 @@ def test_generator_and_initial_state_sweep(cpu_engine, case):
     np.testing.assert_allclose(got.numpy(), want, rtol=1e-11, atol=1e-13)
   else:
     np.testing.assert_allclose(got.numpy(), want, rtol=2e-5, atol=2e-6)
+
+
+def test_heston_qe_price_host_flow(cpu_pricing):
+  # the C2-QE bench line's public call: `HestonModel.price(scheme='qe')`, barrier monitored on every grid point
+  heston = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=0.5, rho=-0.7, dtype=np.float64)
+  x0 = np.array([np.log(100.0), 0.04])
+  n, steps = 1024, 16
+  payoffs = [engine.european_call(100.0, log_state=True), engine.up_and_out_call(100.0, 130.0, log_state=True)]
+  mean, stderr, bad = heston.price([1.0], payoffs, num_samples=n, initial_state=x0, num_time_steps=steps,
+                                   random_type=tff.math.random.RandomType.SOBOL, scheme='qe', return_stats=True)
+  paths, xmax, _ = oqe.sample_paths(2.0, 0.04, 0.5, -0.7, [1.0], x0, num_samples=n, num_time_steps=steps,
+                                    random_type=RT.SOBOL, return_extrema=True)
+  s = np.exp(paths[:, -1, 0])
+  want = np.stack([np.maximum(s - 100, 0), np.where(np.exp(xmax) > 130, 0, np.maximum(s - 100, 0))], -1)
+  np.testing.assert_allclose(mean, want.mean(axis=0), rtol=1e-10)
+  assert (bad == 0).all() and (stderr > 0).all()
+  with pytest.raises(ValueError):
+    heston.price([1.0], payoffs, num_samples=n, initial_state=x0, num_time_steps=steps, scheme='milstein')
+  assert abs(heston.expected_total_variance(1.2, 0.3) - ((0.3 - 0.04) * (1 - np.exp(-2.0 * 1.2)) / 2.0 + 0.04 * 1.2)) < 1e-15
