@@ -140,7 +140,8 @@ def eval_payoff(d, x, xmax, xmin):
     swap = np.exp(-x[:, -1]) * (1.0 - acc)
     return np.maximum(swap if d.is_payer else -swap, 0.0) * d.scale
   assert not d.brownian_bridge
-  f, fmax, fmin = x[:, d.component], xmax, xmin
+  # component < 0: the basket mean over the assets (multi-asset kernels, csrc/tqf_mvgbm.cu)
+  f, fmax, fmin = (x[:, d.component] if d.component >= 0 else x.mean(axis=1)), xmax, xmin
   tangent = x[:, d.tangent_component]
   fprime = 1.0
   with np.errstate(over='ignore', invalid='ignore'):

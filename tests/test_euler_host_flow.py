@@ -543,3 +543,22 @@ def test_heston_qe_price_host_flow(cpu_pricing):
   with pytest.raises(ValueError):
     heston.price([1.0], payoffs, num_samples=n, initial_state=x0, num_time_steps=steps, scheme='milstein')
   assert abs(heston.expected_total_variance(1.2, 0.3) - ((0.3 - 0.04) * (1 - np.exp(-2.0 * 1.2)) / 2.0 + 0.04 * 1.2)) < 1e-15
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_c4_basket_price_host_flow(cpu_pricing, dtype):
+  # config C4 at a small size: correlated multi-asset GBM, Sobol, basket call (`component=-1`: mean over the assets)
+  dim, n, steps = 8, 512, 12
+  means, vols = np.full(dim, 0.03, dtype), np.linspace(0.1, 0.4, dim).astype(dtype)
+  corr = (0.3 + 0.7 * np.eye(dim)).astype(dtype)
+  mv = tff.models.MultivariateGeometricBrownianMotion(dim, means=means, volatilities=vols, corr_matrix=corr, dtype=dtype)
+  x0 = 100.0 * np.ones(dim, dtype)
+  got = tff.models.euler_sampling.price(dim, mv.drift_fn(), mv.volatility_fn(), np.array([1.0], dtype),
+                                        [engine.european_call(100.0, component=-1)], num_time_steps=steps,
+                                        num_samples=n, initial_state=x0, random_type=tff.math.random.RandomType.SOBOL,
+                                        skip=5, dtype=dtype)
+  d, v = omodels.mvgbm_closures(means, vols, corr, dtype)
+  paths = oeuler.sample(dim, d, v, np.array([1.0], dtype), num_time_steps=steps, num_samples=n, initial_state=x0,
+                        random_type=RT.SOBOL, skip=5, dtype=dtype)
+  want = np.maximum(paths[:, 0, :].astype(np.float64).mean(axis=1) - 100.0, 0).mean()
+  np.testing.assert_allclose(got, [want], rtol=1e-11 if dtype == np.float64 else 2e-5)
