@@ -117,6 +117,18 @@ def hull_white_1f(x, z, c, spec=None):        # HullWhite1FModel::step, state [x
   return np.stack([xn, c[3] * xn + (x[:, 1] + c[4])], -1)
 
 
+def hjm(x, z, c, spec):                       # HjmModel<F, NFS>::step, state [x_1..x_F, integral]
+  f = x.shape[1] - 1
+  dw = z[:, :f] * c[1]
+  a0, kap = c[2:2 + f], c[2 + f:2 + 2 * f]
+  b = c[2 + 2 * f:2 + 2 * f + f * f].reshape(f, f)
+  w_pre, w_post, w_const = c[2 + 2 * f + f * f], c[3 + 2 * f + f * f], c[4 + 2 * f + f * f]
+  xs = x[:, :f]
+  xn = (xs + c[0] * (a0 - kap * xs)) + dw @ b.T
+  integral = x[:, f] + (w_pre * xs.sum(axis=1) + w_post * xn.sum(axis=1) + w_const)
+  return np.concatenate([xn, integral[:, None]], axis=1)
+
+
 def mvgbm(x, z, c, spec):                     # csrc/tqf_mvgbm.cu
   chol, (mu, sg) = spec.device_arrays(x.dtype)
   chol, mu, sg = chol.astype(x.dtype), mu.astype(x.dtype), sg.astype(x.dtype)
@@ -130,13 +142,16 @@ STEP = {
     _lib.MODEL_MILSTEIN_1F: milstein_1f, _lib.MODEL_HESTON_EULER: heston_euler, _lib.MODEL_AFFINE_ND: affine_nd,
     _lib.MODEL_AFFINE_1F_TANGENT: tangent_affine, _lib.MODEL_HESTON_TANGENT: tangent_heston,
     _lib.MODEL_HESTON_QE: heston_qe, _lib.MODEL_HW1F: hull_white_1f, _lib.MODEL_MVGBM: mvgbm,
+    _lib.MODEL_HJM: hjm,
 }
 
 
 def eval_payoff(d, x, xmax, xmin):
   """`eval_payoff` / the swaption branch of the price kernel for all paths (float64)."""
   if d.kind == _lib.PAYOFF_HW_SWAPTION:
-    acc = sum(d.pay_coef[j] * np.exp(-d.pay_g[j] * x[:, 0] + d.pay_k[j]) for j in range(d.num_payments))
+    nf = max(int(d.num_factors), 1)           # several factors (TQF_MODEL_HJM): log P_j = k_j - sum_i g_ji x_i
+    acc = sum(d.pay_coef[j] * np.exp(d.pay_k[j] - sum(d.pay_g[j * nf + i] * x[:, i] for i in range(nf)))
+              for j in range(d.num_payments))
     swap = np.exp(-x[:, -1]) * (1.0 - acc)
     return np.maximum(swap if d.is_payer else -swap, 0.0) * d.scale
   assert not d.brownian_bridge
