@@ -260,7 +260,6 @@ class CpuPlan:
 
   def paths(self, record_slot, num_times, unit_offset=0, unit_count=None, exp_transform=False, out=None,
             column_sums=False):
-    assert not column_sums
     dt = self.dtype
     z, x, rows = self._start(unit_offset, unit_count)
     buf = np.zeros((num_times, self.spec.dim, rows), dtype=dt)
@@ -277,6 +276,8 @@ class CpuPlan:
     if out is not None:
       out.copy_(t)
       t = out
+    if column_sums:        # float64 sums over the rows of every stored value (`tqf_plan_paths_sums`)
+      return t.permute(2, 0, 1), torch.from_numpy(buf.astype(np.float64).sum(axis=2))
     return t.permute(2, 0, 1)
 
 

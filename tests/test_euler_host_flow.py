@@ -562,3 +562,33 @@ def test_c4_basket_price_host_flow(cpu_pricing, dtype):
                         random_type=RT.SOBOL, skip=5, dtype=dtype)
   want = np.maximum(paths[:, 0, :].astype(np.float64).mean(axis=1) - 100.0, 0).mean()
   np.testing.assert_allclose(got, [want], rtol=1e-11 if dtype == np.float64 else 2e-5)
+
+
+def test_c5_path_generation_host_flow(cpu_engine):
+  # config C5's first half: log-space GBM Euler paths at the 50 exercise dates, stored exponentiated with their
+  # column sums (what `least_square_mc(..., column_sums=)` consumes), STATELESS_ANTITHETIC -- the plan-level calls
+  # `bench.py` and the README's multi-GPU example make
+  from tff_b200 import distributed
+  from tff_b200.models import closures, euler_sampling
+  r, sigma, n = 0.06, 0.2, 256
+  drift_fn, vol_fn = closures.affine_closures(r - 0.5 * sigma**2, 0.0, sigma)
+  times = np.linspace(0.02, 1.0, 50)
+  plans, record_slot, k, _ = euler_sampling._prepare(
+      1, drift_fn, vol_fn, times, 0.01, None, n, [0.0], tff.math.random.RandomType.STATELESS_ANTITHETIC, [4, 2], 0,
+      None, None, None, False, None, np.float64)
+  plan = plans[0]
+  lo, count = distributed.shard_units(plan.units)
+  assert (lo, count) == (0, n // 2)
+  paths, sums = plan.paths(record_slot, k, lo, count, exp_transform=True, column_sums=True)
+  want = np.exp(oeuler.sample(1, lambda t, x: (r - 0.5 * sigma**2) + 0 * x, lambda t, x: (sigma + 0 * x)[..., None],
+                              times, time_step=0.01, num_samples=n, initial_state=np.array([0.0]),
+                              random_type=RT.STATELESS_ANTITHETIC, seed=[4, 2], dtype=np.float64))
+  assert tuple(paths.shape) == want.shape == (n, 50, 1) and plan.num_steps == 100
+  np.testing.assert_allclose(paths.numpy(), want, rtol=1e-12)
+  np.testing.assert_allclose(sums.numpy(), want.sum(axis=0), rtol=1e-12)
+  # the oracle's Longstaff-Schwartz price on those paths is the C5 number the GPU passes must reproduce
+  from oracle import lsm as olsm
+  df = np.exp(-r * times)
+  price = olsm.least_square_mc(want, np.arange(50), olsm.make_basket_put_payoff([1.1]), olsm.make_polynomial_basis(3),
+                               df, dtype=np.float64)
+  assert price.shape == (1,) and 0.09 < price[0] < 0.2
