@@ -146,7 +146,23 @@ STEP = {
 }
 
 
-def eval_payoff(d, x, xmax, xmin):
+BRIDGE_VAR = {       # Model::bridge_var(pre-step state, coefficients): variance of the monitored increment
+    _lib.MODEL_AFFINE_1F: lambda x, c: (c[4] + c[5] * x[:, 0])**2 * c[0],
+    _lib.MODEL_LINEAR_1F: lambda x, c: np.full(x.shape[0], c[4] * c[4]),
+    _lib.MODEL_HESTON_EULER: lambda x, c: np.abs(x[:, 1]) * (c[0] * c[0]),
+}
+
+
+def bridge_factor(level, xs, xe, var, upper):
+  """`brownian_bridge_single`: P(no touch) = 1 - exp(-2 (x_s - b)(x_e - b) / var) when both ends are on the
+  inner side of the barrier, 0 otherwise (`black_scholes/brownian_bridge.py:118-196`)."""
+  ds, de = (level - xs, level - xe) if upper else (xs - level, xe - level)
+  with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+    p = np.where(var > 0, 1.0 - np.exp(-2.0 * (ds * de) / np.where(var > 0, var, 1.0)), 1.0)
+  return np.where((ds > 0) & (de > 0), p, 0.0)
+
+
+def eval_payoff(d, x, xmax, xmin, surv_up=1.0, surv_dn=1.0):
   """`eval_payoff` / the swaption branch of the price kernel for all paths (float64)."""
   if d.kind == _lib.PAYOFF_HW_SWAPTION:
     nf = max(int(d.num_factors), 1)           # several factors (TQF_MODEL_HJM): log P_j = k_j - sum_i g_ji x_i
@@ -154,7 +170,6 @@ def eval_payoff(d, x, xmax, xmin):
               for j in range(d.num_payments))
     swap = np.exp(-x[:, -1]) * (1.0 - acc)
     return np.maximum(swap if d.is_payer else -swap, 0.0) * d.scale
-  assert not d.brownian_bridge
   # component < 0: the basket mean over the assets (multi-asset kernels, csrc/tqf_mvgbm.cu)
   f, fmax, fmin = (x[:, d.component] if d.component >= 0 else x.mean(axis=1)), xmax, xmin
   tangent = x[:, d.tangent_component]
@@ -175,6 +190,10 @@ def eval_payoff(d, x, xmax, xmin):
         _lib.PAYOFF_PUT_TANGENT: np.where(put > 0, -(fprime * tangent), 0.0),
         _lib.PAYOFF_IDENTITY: f,
     }[d.kind]
+    if d.brownian_bridge and d.kind in (_lib.PAYOFF_UP_OUT_CALL, _lib.PAYOFF_UP_OUT_PUT):
+      v = v * surv_up
+    if d.brownian_bridge and d.kind in (_lib.PAYOFF_DOWN_OUT_PUT, _lib.PAYOFF_DOWN_OUT_CALL):
+      v = v * surv_dn
     return np.where(np.isfinite(f), v, np.nan) * d.scale
 
 
@@ -245,15 +264,31 @@ class CpuPlan:
     assert len(monitored) <= 1                  # the kernel monitors ONE state component (tqf_paths.cu)
     mon = monitored.pop() if monitored else 0
     xmax, xmin = x[:, mon].astype(np.float64), x[:, mon].astype(np.float64)
+    # continuous monitoring (tqf_paths.cu): one level per direction, in state space
+    level = {}
+    for d in descs:
+      if d.kind in barrier_kinds and d.brownian_bridge:
+        assert d.component == 0 and self.spec.kind in BRIDGE_VAR
+        up = d.kind in (_lib.PAYOFF_UP_OUT_CALL, _lib.PAYOFF_UP_OUT_PUT)
+        lv = np.log(d.barrier) if d.transform == _lib.TRANSFORM_EXP else d.barrier
+        assert level.setdefault(up, lv) == lv
+    surv_up, surv_dn = np.ones(rows), np.ones(rows)
     step = STEP[self.spec.kind]
     table = self.table.astype(self.dtype)
     out = np.zeros((len(descs), 4))
     for s in range(self.num_steps):
+      if level:
+        var = BRIDGE_VAR[self.spec.kind](x.astype(np.float64), table[s].astype(np.float64))
+        pre = x[:, 0].astype(np.float64)
       x = np.asarray(step(x, z[s], table[s], self.spec), dtype=self.dtype)
+      if True in level:
+        surv_up = surv_up * bridge_factor(level[True], pre, x[:, 0].astype(np.float64), var, True)
+      if False in level:
+        surv_dn = surv_dn * bridge_factor(level[False], pre, x[:, 0].astype(np.float64), var, False)
       xmax, xmin = np.maximum(xmax, x[:, mon]), np.minimum(xmin, x[:, mon])
       for q, d in enumerate(descs):
         if (d.expiry_step if d.expiry_step > 0 else self.num_steps) == s + 1:
-          v = eval_payoff(d, x.astype(np.float64), xmax, xmin)
+          v = eval_payoff(d, x.astype(np.float64), xmax, xmin, surv_up, surv_dn)
           ok = np.isfinite(v)
           out[q] = [v[ok].sum(), (v[ok]**2).sum(), float((~ok).sum()), 0.0]
     return torch.from_numpy(out)

@@ -592,3 +592,56 @@ def test_c5_path_generation_host_flow(cpu_engine):
   price = olsm.least_square_mc(want, np.arange(50), olsm.make_basket_put_payoff([1.1]), olsm.make_polynomial_basis(3),
                                df, dtype=np.float64)
   assert price.shape == (1,) and 0.09 < price[0] < 0.2
+
+
+@pytest.mark.parametrize('model', ['heston', 'log_gbm'])
+def test_continuous_barrier_host_flow(cpu_pricing, model):
+  # `brownian_bridge=True`: the knock-out payoffs weighted by the bridge's no-touch probability between grid points
+  # (`black_scholes/brownian_bridge.py:118-196`); the same case as tests/test_brownian_bridge.py runs on the GPU
+  from oracle import brownian_bridge as obb
+  from oracle import grid as ogrid
+  from tff_b200.models import closures
+  n, steps = 1024, 20
+  rt = tff.math.random.RandomType
+  all_times, _, _ = ogrid.euler_grid([1.0], dtype=np.float64, num_time_steps=steps)
+  dt = np.diff(all_times)
+  if model == 'heston':
+    m = tff.models.HestonModel(mean_reversion=2.0, theta=0.04, volvol=0.5, rho=-0.7, dtype=np.float64)
+    x0 = np.array([np.log(100.0), 0.04])
+    od, ov = omodels.heston_closures(2.0, 0.04, 0.5, -0.7, np.float64)
+    okw = dict(random_type=RT.SOBOL)
+    dim, price = 2, lambda pay: m.price([1.0], pay, num_samples=n, initial_state=x0, random_type=rt.SOBOL,
+                                        num_time_steps=steps)
+  else:
+    r, sigma = 0.03, 0.25
+    d, v = closures.affine_closures(r - sigma**2 / 2, 0.0, sigma)
+    proc = tff.models.GenericItoProcess(1, d, v, dtype=np.float64)
+    x0 = np.array([np.log(100.0)])
+    od = lambda t, x: (r - sigma**2 / 2) + 0 * x
+    ov = lambda t, x: sigma * np.ones(x.shape + (1,))
+    okw = dict(random_type=RT.STATELESS_ANTITHETIC, seed=[3, 9])
+    dim, price = 1, lambda pay: proc.price([1.0], pay, num_samples=n, initial_state=x0,
+                                           random_type=rt.STATELESS_ANTITHETIC, seed=[3, 9], num_time_steps=steps)
+  up, dn = 125.0, 80.0
+  pay = [engine.up_and_out_call(100.0, up, log_state=True, brownian_bridge=True),
+         engine.up_and_out_call(100.0, up, log_state=True),
+         engine.down_and_out_put(105.0, dn, log_state=True, brownian_bridge=True),
+         engine.down_and_out_call(95.0, dn, log_state=True, brownian_bridge=True)]
+  got = price(pay)
+  paths = oeuler.sample(dim, od, ov, all_times[1:], times_grid=all_times, num_samples=n, initial_state=x0,
+                        dtype=np.float64, **okw)
+  full = np.concatenate([np.broadcast_to(x0, (n, 1, dim)), paths], axis=1)
+  xs, xe = full[:, :-1, 0], full[:, 1:, 0]
+  var = (np.abs(full[:, :-1, 1]) if model == 'heston' else 0.25**2 * np.ones_like(xs)) * dt[None, :]
+
+  def survive(level, upper):
+    inner = (xs < level) & (xe < level) if upper else (xs > level) & (xe > level)
+    p = obb.brownian_bridge_single(xs, xe, np.where(var > 0, var, 1.0), level)
+    return np.prod(np.where(inner, np.where(var > 0, p, 1.0), 0.0), axis=1)
+  st = np.exp(full[:, -1, 0])
+  smax, smin = np.exp(full[:, :, 0]).max(axis=1), np.exp(full[:, :, 0]).min(axis=1)
+  s_up, s_dn = survive(np.log(up), True), survive(np.log(dn), False)
+  want = [np.where(smax > up, 0, np.maximum(st - 100, 0)) * s_up, np.where(smax > up, 0, np.maximum(st - 100, 0)),
+          np.where(smin < dn, 0, np.maximum(105 - st, 0)) * s_dn, np.where(smin < dn, 0, np.maximum(st - 95, 0)) * s_dn]
+  np.testing.assert_allclose(got, [w.mean() for w in want], rtol=1e-10)
+  assert got[0] < got[1]
