@@ -15,8 +15,8 @@ plan uploads and restates what the kernels do with it:
   * the record plan (`record_slot[s + 1]` = output slot of the state after step s);
   * the payoff evaluation of the fused mode (`eval_payoff` and the swaption payoff of
     `csrc/tqf_paths_kernel.cuh`: running extrema of state component 0 over the initial state and
-    every executed step, the claim evaluated at its `expiry_step`, sums / sums of squares /
-    non-finite counts).
+    every executed step, the Brownian-bridge no-touch probabilities of `brownian_bridge=True`
+    barriers, the claim evaluated at its `expiry_step`, sums / sums of squares / non-finite counts).
 
 The streams themselves come from the oracle.  Nothing here is shipped or imported by the package.
 """
