@@ -14,7 +14,8 @@ class PiecewiseConstantFunc:
   """Left-continuous piecewise constant function (`math/piecewise.py:144-176`).
 
   f(x) = values[i] for jump_locations[i-1] < x <= jump_locations[i].
-  Batch-free (1-D `jump_locations`); `values` may carry an event shape.
+  `__call__` is batch-free (1-D `jump_locations`, `values` may carry an event shape); `integrate`
+  also takes batched functions.
   """
   is_piecewise_constant = True
 
@@ -39,9 +40,20 @@ class PiecewiseConstantFunc:
     return self._values[idx]
 
   def integrate(self, x1, x2):
-    """`math/piecewise.py:178-208` for x1 <= x2 (batch-free, scalar-valued)."""
+    """`math/piecewise.py:178-208` for x1 <= x2 (scalar-valued).  A batched function
+    (`jump_locations` of shape `batch_shape + [n]`) takes `x1`, `x2` broadcastable to
+    `batch_shape + [num_points]` and integrates element by element of the batch."""
     x1 = np.asarray(x1, dtype=self._dtype)
     x2 = np.asarray(x2, dtype=self._dtype)
+    if self._jumps.ndim > 1:
+      batch_shape = self._jumps.shape[:-1]
+      x1, x2 = np.broadcast_arrays(x1, x2)
+      x1 = np.broadcast_to(x1, batch_shape + x1.shape[-1:])
+      x2 = np.broadcast_to(x2, batch_shape + x2.shape[-1:])
+      out = np.empty(x1.shape, dtype=self._dtype)
+      for b in np.ndindex(*batch_shape):
+        out[b] = PiecewiseConstantFunc(self._jumps[b], self._values[b], dtype=self._dtype).integrate(x1[b], x2[b])
+      return out
     knots = self._jumps
     out = np.zeros(np.broadcast(x1, x2).shape, dtype=self._dtype)
     lo = np.concatenate([[-np.inf], knots])
@@ -159,31 +171,41 @@ def hull_white_1f_closures(mean_reversion, volatility, forward_rate_fn,
 
 def gbm_exact_sample_paths(mean, volatility, times, initial_state=None,
                            num_samples=1, random_type=None, seed=None, skip=0,
-                           dtype=np.float64):
+                           dtype=np.float64, normal_draws=None):
   """`GeometricBrownianMotion.sample_paths` (exact log-normal sampler,
-  `univariate_geometric_brownian_motion.py:155-317`) -> [N, k, 1]."""
+  `univariate_geometric_brownian_motion.py:155-317`) -> batch_shape + [N, k, 1].
+
+  Batches as in the reference: `mean` / `volatility` of shape `batch_shape + [1]` (or batched
+  `PiecewiseConstantFunc`s), `times` of shape `[k]` or `batch_shape + [k]`, `initial_state`
+  broadcastable to `batch_shape + [1]`.  The normal draws carry NO batch shape (`:277-282`): every
+  element of the batch is driven by the same `[k, N]` normals."""
   from oracle import draws as draws_lib
   dtype = np.dtype(dtype)
   times = np.asarray(times, dtype=dtype)
-  k = times.shape[0]
+  k = times.shape[-1]
   x0 = np.ones(1, dtype) if initial_state is None else np.asarray(initial_state, dtype)
-  z = draws_lib.generate_mc_normal_draws(
-      1, k, num_samples, draws_lib.RandomType.PSEUDO if random_type is None else random_type,
-      seed=seed, dtype=dtype, skip=skip)                      # [k, N, 1]
-  t = np.concatenate([np.zeros(1, dtype), times])
+  if normal_draws is None:
+    z = draws_lib.generate_mc_normal_draws(
+        1, k, num_samples, draws_lib.RandomType.PSEUDO if random_type is None else random_type,
+        seed=seed, dtype=dtype, skip=skip)                    # [k, N, 1]
+  else:
+    z = np.transpose(np.asarray(normal_draws, dtype), [1, 0, 2])
+  t = np.concatenate([np.zeros(times.shape[:-1] + (1,), dtype), times], -1)
 
   def integ(p, square=False):
     if callable(p):
       q = p if not square else PiecewiseConstantFunc(p.jump_locations(), p.values()**2, dtype=dtype)
-      return q.integrate(t[:-1], t[1:])
+      return q.integrate(t[..., :-1], t[..., 1:])
     v = np.asarray(p, dtype)
-    return (v * v if square else v) * (t[1:] - t[:-1])
-  mean_int = integ(mean)
-  vol2_int = integ(volatility, square=True)
-  log_inc = (mean_int - vol2_int / 2)[None, :] + np.sqrt(vol2_int)[None, :] * z[:, :, 0].T
+    return (v * v if square else v) * (t[..., 1:] - t[..., :-1])
+  mean_int = np.expand_dims(integ(mean), -2)                  # batch_shape + [1, k]
+  vol2_int = np.expand_dims(integ(volatility, square=True), -2)
+  with np.errstate(invalid='ignore'):
+    root = np.where(vol2_int > 0, np.sqrt(np.maximum(vol2_int, 0)), 0)      # _sqrt_no_nan
+  log_inc = (mean_int - vol2_int / 2) + root * z[:, :, 0].T   # batch_shape + [N, k]
   lower = np.tril(np.ones((k, k), dtype))
-  cumsum = log_inc @ lower.T
-  return (x0[..., None] * np.exp(cumsum))[..., None].astype(dtype)
+  cumsum = np.einsum('ij,...j->...i', lower, log_inc)
+  return (np.expand_dims(x0, -1) * np.exp(cumsum))[..., None].astype(dtype)
 
 
 def mvgbm_exact_sample_paths(means, volatilities, corr_matrix, times,

@@ -645,3 +645,68 @@ def test_continuous_barrier_host_flow(cpu_pricing, model):
           np.where(smin < dn, 0, np.maximum(105 - st, 0)) * s_dn, np.where(smin < dn, 0, np.maximum(st - 95, 0)) * s_dn]
   np.testing.assert_allclose(got, [w.mean() for w in want], rtol=1e-10)
   assert got[0] < got[1]
+
+
+# ---- batches of GBMs through the model class (`univariate_geometric_brownian_motion.py:66-80, 261-317`) --------
+def _gbm_batch_case(name, dtype):
+  pw, opw = tff.math.piecewise.PiecewiseConstantFunc, omodels.PiecewiseConstantFunc
+  if name == 'constant':                       # geometric_brownian_motion_test.py:284-302
+    mu = np.array([[0.05], [0.06], [0.04], [0.02]], dtype=dtype)
+    sigma = np.array([[0.05], [0.1], [0.15], [0.2]], dtype=dtype)
+    return mu, sigma, mu, sigma, np.array([0.1, 0.5, 1.0], dtype=dtype), np.array([[2.0], [10.0], [5.0], [25.0]], dtype)
+  if name == 'batched_times':                  # :318-340
+    mu = np.array([[0.05], [0.06], [0.04], [0.03]], dtype=dtype)
+    sigma = np.array([[0.05], [0.1], [0.15], [0.2]], dtype=dtype)
+    times = np.array([[0.1, 0.5, 1.0], [0.2, 0.4, 2.0], [0.3, 0.6, 5.0], [0.4, 0.9, 7.0]], dtype=dtype)
+    return mu, sigma, mu, sigma, times, np.array([[2.0], [10.0], [5.0], [25.0]], dtype)
+  if name == 'rank4':                          # :355-405
+    rs = np.random.RandomState(3)
+    mu = (0.3 * rs.uniform(size=(2, 3, 4, 1))).astype(dtype)
+    sigma = (0.2 * rs.uniform(size=(2, 3, 4, 1))).astype(dtype)
+    times = np.reshape(np.arange(1., 1. + (2 * 3 * 4 * 7), 1., dtype=dtype), (2, 3, 4, 7)) / 20
+    return mu, sigma, mu, sigma, times, np.ones_like(mu) * 100.0
+  # 'piecewise': batched piecewise drift and volatility, batched times, scalar initial state (:517-560, 637-700)
+  jm, vm = np.array([[0.0, 5.0, 10.0], [0.0, 7.0, 10.0]], dtype), np.array([[0.0, 0.0, 0.05, 0.05], [0.01, 0.01, 0.07, 0.07]], dtype)
+  js, vs = np.array([[0.0, 5.0, 10.0], [0.0, 7.0, 10.0]], dtype), np.array([[0.0, 0.2, 0.4, 0.6], [0.1, 0.1, 0.3, 0.3]], dtype)
+  times = np.array([[0.0, 1.0, 5.0, 7.0, 10.0], [0.0, 1.5, 3.2, 4.8, 25.3]], dtype=dtype)
+  return (pw(jm, vm, dtype=dtype), pw(js, vs, dtype=dtype), opw(jm, vm, dtype=dtype), opw(js, vs, dtype=dtype), times,
+          np.asarray(2.0, dtype))
+
+
+@pytest.mark.parametrize('name', ['constant', 'batched_times', 'rank4', 'piecewise'])
+@pytest.mark.parametrize('supply_draws', [False, True])
+def test_batched_gbm_sample_paths(cpu_engine, name, supply_draws):
+  dtype = np.float64
+  mu, sigma, omu, osigma, times, x0 = _gbm_batch_case(name, dtype)
+  k = times.shape[-1]
+  draws = ophilox.stateless_normal([64, k, 1], [4, 2], dtype) if supply_draws else None
+  process = tff.models.GeometricBrownianMotion(mu, sigma, dtype=dtype)
+  got = process.sample_paths(times=times, initial_state=x0, random_type=tff.math.random.RandomType.STATELESS,
+                             num_samples=64, seed=[1234, 5],
+                             normal_draws=None if draws is None else torch.from_numpy(draws))
+  want = omodels.gbm_exact_sample_paths(omu, osigma, times, initial_state=x0, num_samples=64,
+                                        random_type=RT.STATELESS, seed=[1234, 5], dtype=dtype, normal_draws=draws)
+  batch = {'constant': (4,), 'batched_times': (4,), 'rank4': (2, 3, 4), 'piecewise': (2,)}[name]
+  assert tuple(got.shape) == want.shape == batch + (64, k, 1)
+  np.testing.assert_allclose(got.numpy(), want, rtol=1e-12)
+  # every element of the batch runs on the SAME normals (the reference draws them without a batch shape)
+  if name == 'constant':
+    one = tff.models.GeometricBrownianMotion(float(mu[2, 0]), float(sigma[2, 0]), dtype=dtype).sample_paths(
+        times=times, initial_state=x0[2], random_type=tff.math.random.RandomType.STATELESS, num_samples=64,
+        seed=[1234, 5], normal_draws=None if draws is None else torch.from_numpy(draws))
+    np.testing.assert_allclose(got.numpy()[2], one.numpy(), rtol=1e-13)
+
+
+def test_batched_gbm_euler_closures(cpu_engine):
+  # the class's closures carry the batched parameters into `euler_sampling.sample` (one plan per batch element,
+  # draws laid out [steps] + batch + [N, dim])
+  mu = np.array([[0.01], [0.05]])
+  sigma = np.array([[0.1], [0.3]])
+  process = tff.models.GeometricBrownianMotion(mu, sigma, dtype=np.float64)
+  x0 = np.array([[[1.0]], [[2.0]]])
+  kw = dict(num_samples=70, initial_state=x0, seed=[1, 5], time_step=0.1, dtype=np.float64)
+  got = tff.models.euler_sampling.sample(1, process.drift_fn(), process.volatility_fn(), [1.0],
+                                         random_type=tff.math.random.RandomType.STATELESS, **kw)
+  want = oeuler.sample(1, lambda t, x: mu[:, None, :] * x, lambda t, x: (sigma[:, None, :] * x)[..., None], [1.0],
+                       random_type=RT.STATELESS, **kw)
+  np.testing.assert_allclose(got.numpy(), want, rtol=1e-12)

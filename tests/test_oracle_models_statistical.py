@@ -173,3 +173,36 @@ def test_heston_compare_monte_carlo_to_european_option(mode):
   want = _heston_call(np.exp(log_spot), strike, discounting, maturity, kappa, theta, volvol, rho, v0)
   assert abs(want - (np.exp(log_spot) - strike * np.exp(-discounting))) < 0.05      # deep in the money
   np.testing.assert_allclose(mc, want, atol=0.1, rtol=0.1)
+
+
+# ---- batches of GBMs (`geometric_brownian_motion_test.py:284-420, 517-560`) ------------------------------
+@pytest.mark.parametrize('batched_times', [False, True])
+def test_univariate_sample_mean_constant_parameters_batched(batched_times):
+  dtype = np.float64
+  mu = np.array([[0.05], [0.06], [0.04], [0.03]], dtype=dtype)
+  sigma = np.array([[0.05], [0.1], [0.15], [0.2]], dtype=dtype)
+  times = (np.array([[0.1, 0.5, 1.0], [0.2, 0.4, 2.0], [0.3, 0.6, 5.0], [0.4, 0.9, 7.0]], dtype=dtype) if batched_times
+           else np.array([0.1, 0.5, 1.0], dtype=dtype))
+  x0 = np.array([[2.0], [10.0], [5.0], [25.0]], dtype=dtype)
+  samples = omodels.gbm_exact_sample_paths(mu, sigma, times, initial_state=x0, num_samples=NUM_SAMPLES,
+                                           random_type=odraws.RandomType.STATELESS, seed=[1234, 5], dtype=dtype)
+  assert samples.shape == (4, NUM_SAMPLES, 3, 1)
+  mean, var, se_mean, se_var = _log_moments(samples, NUM_SAMPLES)
+  _within(mean, (mu - sigma**2 / 2) * times + np.log(x0), se_mean * NUM_STDERRS)
+  _within(var, sigma**2 * times * np.ones((4, 1)), se_var * NUM_STDERRS)
+
+
+def test_univariate_time_varying_drift_batched():
+  # geometric_brownian_motion_test.py:517-560: batched piecewise drift, batched times, sigma = 0
+  dtype = np.float64
+  mu = omodels.PiecewiseConstantFunc(np.array([[0.0, 5.0, 10.0], [0.0, 7.0, 10.0]], dtype),
+                                     np.array([[0.0, 0.0, 0.05, 0.05], [0.01, 0.01, 0.07, 0.07]], dtype), dtype=dtype)
+  times = np.array([[0.0, 1.0, 5.0, 7.0, 10.0], [0.0, 1.5, 3.2, 4.8, 25.3]], dtype=dtype)
+  samples = omodels.gbm_exact_sample_paths(mu, 0.0, times, initial_state=2.0, num_samples=1000,
+                                           random_type=odraws.RandomType.STATELESS, seed=[1234, 5], dtype=dtype)
+  assert samples.shape == (2, 1000, 5, 1)
+  mean, var, _, _ = _log_moments(samples, 1000)
+  expected = np.array([[0.0, 0.0, 0.0, 2.0 * 0.05, 5.0 * 0.05],
+                       [0.0, 1.5 * 0.01, 3.2 * 0.01, 4.8 * 0.01, 7.0 * 0.01 + 18.3 * 0.07]]) + np.log(2.0)
+  np.testing.assert_allclose(mean, expected, atol=1e-8)
+  np.testing.assert_allclose(var, np.zeros((2, 5)), atol=1e-8)

@@ -32,10 +32,9 @@ class GeometricBrownianMotion(ito_process.ItoProcess):
          volatility, dtype=self._dtype)
     if self._mean_is_constant:
       self._mean = np.asarray(self._mean, dtype=self._dtype)
-    if np.ndim(self._mean) > 1 or (not callable(self._volatility) and
-                                   np.ndim(self._volatility) > 1):
-      raise NotImplementedError('batched GBM parameters are not implemented '
-                                'by the B200 engine yet')
+    # parameters of shape `batch_shape + [1]` (or batched PiecewiseConstantFuncs) describe a batch of
+    # processes (`univariate_...py:66-80`): `sample_paths` loops over the batch, the Euler closures
+    # carry the arrays (`GbmSpec1F.for_batch`)
     self._dim = 1
     self._drift_fn, self._vol_fn = closures.gbm_closures(
         self._mean, self._volatility)
