@@ -204,7 +204,7 @@ def gbm_exact_sample_paths(mean, volatility, times, initial_state=None,
     root = np.where(vol2_int > 0, np.sqrt(np.maximum(vol2_int, 0)), 0)      # _sqrt_no_nan
   log_inc = (mean_int - vol2_int / 2) + root * z[:, :, 0].T   # batch_shape + [N, k]
   lower = np.tril(np.ones((k, k), dtype))
-  cumsum = np.einsum('ij,...j->...i', lower, log_inc)
+  cumsum = log_inc @ lower.T
   return (np.expand_dims(x0, -1) * np.exp(cumsum))[..., None].astype(dtype)
 
 
