@@ -710,3 +710,23 @@ def test_batched_gbm_euler_closures(cpu_engine):
   want = oeuler.sample(1, lambda t, x: mu[:, None, :] * x, lambda t, x: (sigma[:, None, :] * x)[..., None], [1.0],
                        random_type=RT.STATELESS, **kw)
   np.testing.assert_allclose(got.numpy(), want, rtol=1e-12)
+
+
+@pytest.mark.parametrize('batch_rank', [1, 2])
+def test_generic_ito_process_batch_sample_paths_2d(cpu_engine, batch_rank):
+  # generic_ito_process_test.py:147-211: a batch (rank 1 and 2) of initial states of a 2-d process given by plain
+  # callables, PSEUDO draws with an integer seed, through `GenericItoProcess.sample_paths`
+  process = tff.models.GenericItoProcess(
+      dim=2, drift_fn=lambda t, x: torch.as_tensor(MU2) * torch.sqrt(t) * torch.ones_like(x),
+      volatility_fn=lambda t, x: (torch.as_tensor(A2) * t + torch.as_tensor(B2)) * torch.ones(list(x.shape) + [2],
+                                                                                             dtype=torch.float64),
+      dtype=np.float64)
+  times = np.array([0.1, 0.21, 0.32, 0.43, 0.55])
+  x0 = np.array([0.1, -1.1]) * np.ones([2] * batch_rank + [1, 2]) + 0.01 * np.arange(2**batch_rank).reshape(
+      [2] * batch_rank + [1, 1])
+  got = process.sample_paths(times, num_samples=40, initial_state=x0, time_step=0.01, seed=12134)
+  want = oeuler.sample(2, lambda t, x: MU2 * np.sqrt(t) * np.ones_like(x),
+                       lambda t, x: (A2 * t + B2) * np.ones(x.shape + (2,)), times, num_samples=40, initial_state=x0,
+                       time_step=0.01, seed=12134, random_type=RT.PSEUDO, dtype=np.float64)
+  assert tuple(got.shape) == want.shape == tuple([2] * batch_rank + [40, 5, 2])
+  np.testing.assert_allclose(got.numpy(), want, rtol=1e-9, atol=1e-11)
