@@ -89,9 +89,10 @@ def _integrate(jump_locations, values, x1, x2):
   hi = np.concatenate([jump_locations, [np.inf]])
   out = np.zeros(np.broadcast(x1, x2).shape + values.shape[1:], dtype=values.dtype)
   for i in range(values.shape[0]):
-    w = np.maximum(np.minimum(x2, hi[i]) - np.maximum(x1, lo[i]), 0).astype(values.dtype)
+    w = np.maximum(np.minimum(x2, hi[i]) - np.maximum(x1, lo[i]), 0)
     out = out + w.reshape(w.shape + (1,) * (values.ndim - 1)) * values[i]
-  return out
+  # (the piece boundaries are float64: a float32 function accumulates in float64 and is rounded once)
+  return out.astype(values.dtype)
 
 
 def find_interval_index(query_xs, interval_lower_xs, last_interval_is_closed=False, dtype=None,
