@@ -730,3 +730,56 @@ def test_generic_ito_process_batch_sample_paths_2d(cpu_engine, batch_rank):
                        time_step=0.01, seed=12134, random_type=RT.PSEUDO, dtype=np.float64)
   assert tuple(got.shape) == want.shape == tuple([2] * batch_rank + [40, 5, 2])
   np.testing.assert_allclose(got.numpy(), want, rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize('case', range(16))
+def test_heston_qe_sweep(cpu_engine, case):
+  # `HestonModel.sample_paths`: its own grid (jumps and requested times merged into the uniform grid, duplicates kept,
+  # zero-length steps skipped by `tolerance`, parameters taken at `t + min(dt) / 2`; heston_model.py:322-460, 575-639)
+  rs = np.random.RandomState(700 + case)
+  prt, ort = _rt(['STATELESS', 'SOBOL', 'STATELESS_ANTITHETIC', 'PSEUDO'][case % 4])
+  seed = {0: [case, 1], 1: None, 2: [case, 1], 3: 40 + case}[case % 4]
+  step = [0.05, 0.1, 0.125, 0.25][rs.randint(4)]
+
+  def param(lo, hi):
+    if rs.rand() < 0.5:
+      return (float(rs.uniform(lo, hi)),) * 2
+    n = rs.randint(1, 3)
+    jumps = np.sort(np.where(rs.rand(n) < 0.5, step * rs.randint(1, 6, size=n), rs.uniform(0.05, 1.0, size=n)))
+    vals = rs.uniform(lo, hi, size=n + 1)
+    return (tff.math.piecewise.PiecewiseConstantFunc(jumps, vals, dtype=np.float64),
+            omodels.PiecewiseConstantFunc(jumps, vals, dtype=np.float64))
+  params = [param(0.5, 3.0), param(0.02, 0.09), param(0.2, 1.0), param(-0.8, 0.8)]
+  times = np.sort(np.concatenate([step * rs.randint(1, 9, size=2), rs.uniform(0.05, 1.5, size=rs.randint(0, 3))]))
+  x0 = np.array([np.log(100.0), 0.04])
+  heston = tff.models.HestonModel(*[p[0] for p in params], dtype=np.float64)
+  kw = dict(num_samples=32, seed=seed, time_step=step)
+  got = heston.sample_paths(times, x0, random_type=prt, **kw)
+  want = oqe.sample_paths(*[p[1] for p in params], times, x0, random_type=ort, **kw)
+  assert tuple(got.shape) == want.shape == (32, times.shape[0], 2)
+  np.testing.assert_allclose(got.numpy(), want, rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize('case', range(10))
+def test_hull_white_bond_option_sweep(cpu_pricing, case):
+  # batches of calls / puts with random expiries (some on the uniform grid, some at 0), piecewise volatility
+  from oracle import hull_white as ohw
+  rs = np.random.RandomState(900 + case)
+  step = [0.1, 0.25][case % 2]
+  b = rs.randint(1, 5)
+  expiries = np.where(rs.rand(b) < 0.4, step * rs.randint(0, 8, size=b), np.round(rs.uniform(0.1, 2.0, size=b), 3))
+  maturities = expiries + rs.uniform(0.25, 5.0, size=b)
+  strikes = np.exp(-0.01 * (maturities - expiries)) * rs.uniform(0.97, 1.03, size=b)
+  is_call = rs.rand(b) < 0.5
+  if case % 3:
+    vol = tff.math.piecewise.PiecewiseConstantFunc([0.5, 1.7], [0.01, 0.02, 0.015], dtype=np.float64)
+    ovol = omodels.PiecewiseConstantFunc([0.5, 1.7], [0.01, 0.02, 0.015], dtype=np.float64)
+  else:
+    vol = ovol = 0.015
+  kw = dict(strikes=strikes, expiries=expiries, maturities=maturities, discount_rate_fn=_flat_rate, mean_reversion=0.03,
+            is_call_options=is_call, num_samples=256, time_step=step, seed=[case, 9])
+  got = tff.models.hull_white.bond_option_price(use_analytic_pricing=False, volatility=vol, dtype=np.float64,
+                                                random_type=tff.math.random.RandomType.STATELESS_ANTITHETIC, **kw)
+  want = ohw.bond_option_price_mc(volatility=ovol, random_type=RT.STATELESS_ANTITHETIC, **kw)
+  assert got.shape == want.shape == (b,)
+  np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-13)
